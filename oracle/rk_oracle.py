@@ -1,0 +1,646 @@
+"""TEST INFRASTRUCTURE — CPU oracle (NumPy restatement) of extensisq's explicit
+adaptive Runge-Kutta path.  NOT part of the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` legs may import this module.
+
+It restates, as one tableau-driven function instead of the reference's
+``OdeSolver`` class hierarchy, the algorithm of
+
+* ``extensisq/common.py:30-66``    validate_tol / calculate_scale / norm
+* ``extensisq/common.py:123-220``  RungeKutta.__init__ (min-step rule,
+                                   controller presets, first step)
+* ``extensisq/common.py:222-356``  _step_impl / _reassess_stepsize /
+                                   _comp_sol_err / _rk_stage
+* ``extensisq/bogacki.py:238-393`` BS5 step with pre-error, its interpolants
+* ``extensisq/calvo.py:152-261``   CFMR7osc step with early rejection
+* ``extensisq/common.py:519-763``  h_start (Watts / SLATEC dhstrt)
+* ``extensisq/common.py:766-821``  Horner / cubic dense output
+* ``scipy/integrate/_ivp/ivp.py:659-731`` solve_ivp's loop and t_eval slicing
+* ``scipy/integrate/_ivp/base.py:179-210`` OdeSolver.step status handling
+
+The NumPy expressions deliberately use the same operations (``K[:i].T @ a``,
+``np.maximum``, ``x @ x``) as the reference so that, under the same
+NumPy/OpenBLAS, the oracle is *bit-identical* to the live reference.  That
+is how it is pinned: ``tools/gen_golden.py`` runs the unmodified reference in
+the build container and stores its outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` requires exact equality of step counts and
+states (to 1e-13 relative, to tolerate a different BLAS on the GPU host).
+
+Stiffness diagnosis (``common.py:370-516``) only emits warnings and extra RHS
+evaluations; it never changes t, y or h.  The oracle corresponds to
+``nfev_stiff_detect=0``.
+"""
+import json
+import os
+from math import copysign, sqrt
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_TABLEAUX_JSON = os.path.join(os.path.dirname(_HERE), "extensisq_b200",
+                              "data", "tableaux.json")
+
+TOO_SMALL_STEP = "Required step size is less than spacing between numbers."
+OVERFLOW = "Overflow or underflow encountered."
+
+MIN_FACTOR = 0.2        # common.py:18
+MAX_FACTOR = 4.0        # common.py:19
+MAX_FACTOR0 = 10        # common.py:20
+
+SC_PRESETS = {"G": (0.7, -0.4, 0, 0.9),      # common.py:167-169
+              "S": (0.6, -0.2, 0, 0.9),
+              "standard": (1, 0, 0, 0.9)}
+
+
+def _unhex(a):
+    if isinstance(a[0], list):
+        return np.array([[float.fromhex(x) for x in r] for r in a])
+    return np.array([float.fromhex(x) for x in a])
+
+
+class Tableau:
+    """Plain data holder (A, B, C, E, P, ...) for one method."""
+
+    def __init__(self, d):
+        self.name = d["name"]
+        self.n_stages = d["n_stages"]
+        self.order = d["order"]
+        self.order_secondary = d["order_secondary"]
+        self.sc_params = d["sc_params"]
+        for k in ("A", "B", "C", "E", "P", "E_pre", "B_scale_pre", "C_extra",
+                  "A_extra", "Plow", "Pbest"):
+            if k in d:
+                setattr(self, k, _unhex(d[k]))
+        if hasattr(self, "A_extra"):
+            # the reference builds A_extra as ``np.array(rows).T`` (strided
+            # rows, bogacki.py:148-160); keep that memory order so BLAS takes
+            # the same dgemv path and the oracle stays bit-identical
+            self.A_extra = np.asfortranarray(self.A_extra)
+        self.variant = {"BS5": "bs5", "CFMR7osc": "cfmr"}.get(self.name,
+                                                              "generic")
+
+
+def load_tableaux(path=_TABLEAUX_JSON):
+    with open(path) as fh:
+        raw = json.load(fh)["tableaux"]
+    return {k: Tableau(v) for k, v in raw.items()}
+
+
+# --------------------------------------------------------------------------
+# helpers  (common.py:30-66)
+# --------------------------------------------------------------------------
+def validate_tol(rtol, atol, y):
+    atol = np.asarray(atol)
+    if atol.ndim > 0 and atol.shape != (y.size,):
+        raise ValueError("`atol` has wrong shape.")
+    if np.any(atol < 0):
+        raise ValueError("`atol` must be positive.")
+    if not isinstance(rtol, float):
+        raise ValueError("`rtol` must be a float.")
+    if rtol < 0:
+        raise ValueError("`rtol` must be positive.")
+    tiny = np.finfo(y.dtype).tiny
+    atol = np.maximum(atol, sqrt(tiny))
+    epsneg = np.finfo(y.dtype).epsneg
+    rtol = np.minimum(np.maximum(rtol, 10 * epsneg), 0.1)
+    return rtol, atol
+
+
+def calculate_scale(atol, rtol, y, y_new, _mean=False):
+    if _mean:
+        return atol + rtol * 0.5 * (np.abs(y) + np.abs(y_new))
+    return atol + rtol * np.maximum(np.abs(y), np.abs(y_new))
+
+
+def norm(x):
+    return (np.real(x @ x.conjugate()) / x.size) ** 0.5
+
+
+# --------------------------------------------------------------------------
+# starting step  (common.py:519-763; J/T options are not on the RK path)
+# --------------------------------------------------------------------------
+def h_start(df, a, b, y, yprime, morder, rtol, atol):
+    if y.size == 0:
+        return np.inf
+    neq = y.size
+    spy = np.empty_like(y)
+    pv = np.empty_like(y)
+    etol = atol + rtol * np.abs(y)
+    big = sqrt(np.finfo(y.dtype).max)
+    small = np.nextafter(np.finfo(y.dtype).epsneg, 1.0)
+
+    dx = b - a
+    absdx = abs(dx)
+    relper = small ** 0.375
+    da = copysign(max(min(relper * abs(a), absdx), 100. * small * abs(a)), dx)
+    da = da or relper * dx
+    sf = df(a + da, y)
+    yp = sf - yprime
+    delf = norm(yp)
+    dfdxb = big
+    if delf < big * abs(da):
+        dfdxb = delf / abs(da)
+    fbnd = norm(sf)
+
+    dely = relper * norm(y)
+    dely = dely or relper
+    dely = copysign(dely, dx)
+    delf = norm(yprime)
+    fbnd = max(fbnd, delf)
+    if delf:
+        spy[:] = yprime
+        yp[:] = yprime
+    else:
+        spy[:] = 0.0
+        yp[:] = 1.0
+        delf = norm(yp)
+
+    dfdub = 0.0
+    lk = min(neq + 1, 3)
+    for k in range(1, lk + 1):
+        pv[:] = y + dely / delf * yp
+        if k == 2:
+            yp[:] = df(a + da, pv)
+            pv[:] = yp - sf
+        else:
+            yp[:] = df(a, pv)
+            pv[:] = yp - yprime
+        fbnd = max(fbnd, norm(yp))
+        delf = norm(pv)
+        if delf >= big * abs(dely):
+            dfdub = big
+            break
+        dfdub = max(dfdub, delf / abs(dely))
+        if k == lk:
+            break
+        delf = delf or 1.0
+        if k == 2:
+            dy = y.copy()
+            dy[:] = np.where(dy, dy, dely / relper)
+        else:
+            dy = pv.copy()
+            dy[:] = np.where(dy, dy, delf)
+        spy[:] = np.where(spy, spy, yp)
+        yp[:] = np.where(spy, np.copysign(dy, spy), dy)
+        delf = norm(yp)
+
+    ydpb = dfdxb + dfdub * fbnd
+    tolexp = np.log10(etol)
+    tolsum = tolexp.sum()
+    tolmin = min(tolexp.min(), big)
+    tolp = 10.0 ** (0.5 * (tolsum / neq + tolmin) / (morder + 1))
+    h = absdx
+    if ydpb == 0.0 and fbnd == 0.0:
+        if tolp < 1.0:
+            h = absdx * tolp
+    elif ydpb == 0.0:
+        if tolp < fbnd * absdx:
+            h = tolp / fbnd
+    else:
+        srydpb = sqrt(0.5 * ydpb)
+        if tolp < srydpb * absdx:
+            h = tolp / srydpb
+    if dfdub:
+        h = min(h, 1.0 / dfdub)
+    h = max(h, 100.0 * small * abs(a))
+    h = h or small * abs(b)
+    return copysign(h, dx)
+
+
+# --------------------------------------------------------------------------
+# dense output  (common.py:766-821)
+# --------------------------------------------------------------------------
+def horner(t_old, t, y_old, Q, ts):
+    """Q is K.T @ P (n x p), not yet scaled by h."""
+    h = t - t_old
+    Qh = Q * h
+    ts = np.asarray(ts, dtype=float)
+    x = (ts - t_old) / h
+    y = Qh.T[-1, :, np.newaxis] * x
+    for q in reversed(Qh.T[:-1]):
+        y += q[:, np.newaxis]
+        y *= x
+    y += y_old[:, np.newaxis]
+    return y
+
+
+def cubic(t_old, t, y_old, y, f_old, f, ts):
+    h = t - t_old
+    x = (np.asarray(ts, dtype=float) - t_old) / h
+    h00 = (1.0 + 2.0 * x) * (1.0 - x) ** 2
+    h10 = x * (1.0 - x) ** 2 * h
+    h01 = x ** 2 * (3.0 - 2.0 * x)
+    h11 = x ** 2 * (x - 1.0) * h
+    return (h00 * y_old[:, np.newaxis] + h10 * f_old[:, np.newaxis]
+            + h01 * y[:, np.newaxis] + h11 * f[:, np.newaxis])
+
+
+# --------------------------------------------------------------------------
+# the solver state + one step
+# --------------------------------------------------------------------------
+class RKState:
+    """Everything RungeKutta.__init__ sets up (common.py:187-220)."""
+
+    def __init__(self, tab, fun, t0, y0, t_bound, max_step=np.inf, rtol=1e-3,
+                 atol=1e-6, first_step=None, sc_params=None,
+                 interpolant=None):
+        self.tab = tab
+        self.nfev = 0
+        self._fun = fun
+        self.t = t0
+        self.t_old = None
+        self.y = np.array(y0, dtype=float)
+        self.n = self.y.size
+        self.t_bound = t_bound
+        self.direction = np.sign(t_bound - t0) if t_bound != t0 else 1
+        if max_step <= 0:
+            raise ValueError("`max_step` must be positive.")
+        self.max_step = max_step
+        self.rtol, self.atol = validate_tol(rtol, atol, self.y)
+        self.f = self.fun(self.t, self.y)
+        s = tab.n_stages
+        self.error_exponent = -1 / (min(tab.order_secondary, tab.order) + 1)
+        # min-step rule, common.py:123-148
+        cdiff = 1.
+        for c1 in tab.C:
+            for c2 in tab.C:
+                diff = abs(c1 - c2)
+                if diff:
+                    cdiff = min(cdiff, diff)
+        cdiff = max(cdiff, 1e-3)
+        self.h_min_a = 10 * np.finfo(float).epsneg / cdiff
+        self.h_min_b = sqrt(np.finfo(float).tiny)
+        self.tiny_err = self.h_min_b
+        # controller, common.py:166-185
+        scp = sc_params or tab.sc_params
+        if isinstance(scp, str) and scp in SC_PRESETS:
+            kb1, kb2, a, g = SC_PRESETS[scp]
+        elif isinstance(scp, tuple) and len(scp) == 4:
+            kb1, kb2, a, g = scp
+        else:
+            raise ValueError('sc_params should be a tuple of length 4 or one '
+                             'of the strings "G", "S", "W" or "standard"')
+        self.minbeta1 = kb1 * self.error_exponent
+        self.minbeta2 = kb2 * self.error_exponent
+        self.minalpha = -a
+        self.safety = g
+        self.safety_sc = g ** (kb1 + kb2)
+        self.standard_sc = True
+        self.max_factor = MAX_FACTOR0
+        self.min_factor = MIN_FACTOR
+        # first step, common.py:207-214 (+ scipy validate_first_step)
+        if first_step is None:
+            b = self.t + self.direction * min(abs(t_bound - self.t),
+                                              self.max_step)
+            self.h_abs = abs(h_start(self.fun, self.t, b, self.y, self.f,
+                                     tab.order_secondary, self.rtol,
+                                     self.atol))
+        else:
+            if first_step <= 0:
+                raise ValueError("`first_step` must be positive.")
+            if first_step > np.abs(t_bound - t0):
+                raise ValueError("`first_step` exceeds bounds.")
+            self.h_abs = first_step
+        self.FSAL = 1 if tab.E[s] else 0
+        # BS5 keeps extended storage for its interpolants, bogacki.py:217-236
+        self.interpolant = interpolant
+        nrow = s + 1
+        if tab.variant == "bs5":
+            self.interpolant = interpolant or "low"
+            if self.interpolant not in ("best", "low", "free"):
+                raise ValueError(
+                    "interpolant should be one of: 'best', 'low', 'free'")
+            nrow = {"best": s + 4, "low": s + 2, "free": s + 1}[
+                self.interpolant]
+        self.K_ext = np.zeros((nrow, self.n))
+        self.K = self.K_ext[:s + 1]
+        self.h_previous = None
+        self.y_old = None
+        self.f_old = None
+        self.error_norm_old = None
+        self.n_rejected = 0            # the reference's global NFS
+        self.n_accepted = 0
+        self.status = "running"
+
+    def fun(self, t, y):
+        self.nfev += 1
+        return np.asarray(self._fun(t, y), dtype=float)
+
+
+def _reassess_stepsize(st):                       # common.py:310-331
+    h_abs = st.h_abs
+    min_step = max(st.h_min_a * (abs(st.t) + h_abs), st.h_min_b)
+    if h_abs < min_step or h_abs > st.max_step:
+        h_abs = min(st.max_step, max(min_step, h_abs))
+        st.standard_sc = True
+    d = abs(st.t_bound - st.t)
+    if d < 2 * h_abs:
+        if d > h_abs:
+            h_abs = max(0.5 * d, min_step)
+            st.standard_sc = True
+        else:
+            h_abs = d
+    return h_abs, min_step
+
+
+def _rk_stage(st, h, i):                          # common.py:353-356
+    dy = h * (st.K[:i, :].T @ st.tab.A[i, :i])
+    st.K[i] = st.fun(st.t + st.tab.C[i] * h, st.y + dy)
+
+
+def _comp_sol_err(st, y, h):                      # common.py:333-351
+    s = st.tab.n_stages
+    y_new = y + h * (st.K[:s].T @ st.tab.B)
+    scale = calculate_scale(st.atol, st.rtol, y, y_new)
+    if st.FSAL:
+        st.K[s, :] = st.fun(st.t + h, y_new)
+    err = h * (st.K[:s + st.FSAL].T @ st.tab.E[:s + st.FSAL])
+    return y_new, norm(err / scale)
+
+
+def _pre_error(st, y, h):
+    tab = st.tab
+    if tab.variant == "bs5":                      # bogacki.py:340-346
+        y_pre = y + h * (st.K[:6].T @ tab.B_scale_pre)
+        scale = calculate_scale(st.atol, st.rtol, y, y_pre)
+        err = h * (st.K[:6, :].T @ tab.E_pre)
+    else:                                         # calvo.py:255-261
+        y_pre = y + h * (st.K[:8].T @ tab.A[8, :8])
+        scale = calculate_scale(st.atol, st.rtol, y, y_pre)
+        err = h * (st.K[:8, :].T @ tab.E[:8])
+    return norm(err / scale)
+
+
+def rk_step(st, forced_h=None):
+    """One call of _step_impl.  Returns (success, message).
+
+    ``forced_h``: take exactly this |h| and accept whatever the error is
+    (the "forced fixed step sequence" mode of BASELINE.json's north_star)."""
+    tab = st.tab
+    s = tab.n_stages
+    t, y = st.t, st.y
+    if forced_h is not None:
+        h = forced_h * st.direction
+        st.K[0] = st.f
+        for i in range(1, s):
+            _rk_stage(st, h, i)
+        y_new, error_norm = _comp_sol_err(st, y, h)
+        h_abs = forced_h
+    else:
+        h_abs, min_step = _reassess_stepsize(st)
+        step_accepted = False
+        step_rejected = False
+        early = tab.variant in ("bs5", "cfmr")
+        while not step_accepted:
+            if h_abs < min_step:
+                return False, TOO_SMALL_STEP
+            h = h_abs * st.direction
+            st.K[0] = st.f
+            n_first = s - 1 if early else s
+            for i in range(1, n_first):
+                _rk_stage(st, h, i)
+            if early:
+                # bogacki.py:262-275, calvo.py:174-187
+                error_norm_pre = _pre_error(st, y, h)
+                if error_norm_pre > 1:
+                    step_rejected = True
+                    h_abs *= max(st.min_factor, st.safety *
+                                 error_norm_pre ** st.error_exponent)
+                    st.n_rejected += 1
+                    continue
+                _rk_stage(st, h, s - 1)
+            y_new, error_norm = _comp_sol_err(st, y, h)
+
+            if error_norm < 1:                    # common.py:249-276
+                step_accepted = True
+                if error_norm < st.tiny_err:
+                    factor = st.max_factor
+                    st.standard_sc = True
+                elif st.standard_sc:
+                    factor = st.safety * error_norm ** st.error_exponent
+                    st.standard_sc = False
+                else:
+                    h_ratio = h / st.h_previous
+                    factor = st.safety_sc * (
+                        error_norm ** st.minbeta1 *
+                        st.error_norm_old ** st.minbeta2 *
+                        h_ratio ** st.minalpha)
+                    factor = min(st.max_factor, max(st.min_factor, factor))
+                if step_rejected:
+                    factor = min(1, factor)
+                h_abs *= factor
+                if factor < MAX_FACTOR:
+                    st.max_factor = MAX_FACTOR
+            else:
+                bad = np.isnan(error_norm) or np.isinf(error_norm)
+                if tab.variant == "bs5" and bad:  # bogacki.py:314-315
+                    return False, OVERFLOW
+                step_rejected = True
+                h_abs *= max(st.min_factor,
+                             st.safety * error_norm ** st.error_exponent)
+                st.n_rejected += 1
+                if bad:                           # common.py:286-287
+                    return False, OVERFLOW
+
+    if not st.FSAL:                               # common.py:289-291
+        st.K[s] = st.fun(t + h, y_new)
+    st.h_previous = h
+    st.y_old = y
+    st.h_abs = h_abs
+    st.f_old = st.f
+    st.f = st.K[s].copy()
+    st.error_norm_old = error_norm
+    st.t_old = t
+    st.t = t + h
+    st.y = y_new
+    st.n_accepted += 1
+    return True, None
+
+
+def dense_eval(st, ts):
+    """dense_output()(ts) over the last accepted step.
+    common.py:358-368; bogacki.py:348-393."""
+    tab = st.tab
+    if st.t == st.t_old:           # scipy base.py:224-226 ConstantDenseOutput
+        return np.repeat(st.y[:, None], np.size(ts), axis=1)
+    if tab.variant != "bs5":
+        Q = st.K.T @ tab.P
+        return horner(st.t_old, st.t, st.y_old, Q, ts)
+    h = st.h_previous
+    K = st.K_ext
+    s = tab.n_stages
+    if st.interpolant == "free":
+        return horner(st.t_old, st.t, st.y_old, K.T @ tab.P, ts)
+    if st.interpolant == "low":
+        r = s + 1
+        dy = K[:r, :].T @ tab.A_extra[0, :r] * h
+        K[r] = st.fun(st.t_old + tab.C_extra[0] * h, st.y_old + dy)
+        return horner(st.t_old, st.t, st.y_old, K.T @ tab.Plow, ts)
+    for r, (a, c) in enumerate(zip(tab.A_extra, tab.C_extra), start=s + 1):
+        dy = K[:r, :].T @ a[:r] * h
+        K[r] = st.fun(st.t_old + c * h, st.y_old + dy)
+    Pb = tab.Pbest
+    Q = np.empty((K.shape[1], Pb.shape[1]))
+    Q[:, 0] = st.K[7]
+    KP = K * Pb[:, 1, np.newaxis]
+    Q[:, 1] = (KP[4] + ((KP[5] + KP[7]) + KP[0]) + ((KP[2] + KP[8]) +
+               KP[9]) + ((KP[3] + KP[10]) + KP[6]))
+    KP = K * Pb[:, 2, np.newaxis]
+    Q[:, 2] = (KP[4] + KP[5] + ((KP[2] + KP[8]) + (KP[9] + KP[7]) +
+               KP[0]) + ((KP[3] + KP[10]) + KP[6]))
+    KP = K * Pb[:, 3, np.newaxis]
+    Q[:, 3] = (((KP[3] + KP[7]) + (KP[6] + KP[5]) + KP[4]) + ((KP[9] +
+               KP[8]) + (KP[2] + KP[10]) + KP[0]))
+    KP = K * Pb[:, 4, np.newaxis]
+    Q[:, 4] = ((KP[9] + KP[8]) + ((KP[6] + KP[5]) + KP[4]) + ((KP[3] +
+               KP[7]) + (KP[2] + KP[10]) + KP[0]))
+    KP = K * Pb[:, 5, np.newaxis]
+    Q[:, 5] = (KP[4] + ((KP[9] + KP[7]) + (KP[6] + KP[5])) + ((KP[3] +
+               KP[8]) + (KP[2] + KP[10]) + KP[0]))
+    # anchored at the END of the step (bogacki.py:389-393)
+    return horner(st.t, st.t + h, st.y, Q, ts)
+
+
+def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
+             first_step=None, t_eval=None, sc_params=None, interpolant=None,
+             forced_h=None, record=False, max_steps=None):
+    """solve_ivp(fun, t_span, y0, method=<tab>, ...) restated.
+
+    Returns a dict with t, y (n x n_t), n_accepted, n_rejected, nfev, status,
+    message, t_final, y_final and (``record=True``) the accepted |h| sequence.
+    With ``forced_h`` (sequence of |h|) exactly len(forced_h) steps are taken
+    and t_span[1] only gives the direction."""
+    t0, tf = map(float, t_span)
+    if forced_h is not None:
+        st = RKState(tab, fun, t0, y0, copysign(np.inf, tf - t0),
+                     rtol=rtol, atol=atol, first_step=forced_h[0],
+                     sc_params=sc_params, interpolant=interpolant)
+    else:
+        st = RKState(tab, fun, t0, y0, tf, max_step=max_step, rtol=rtol,
+                     atol=atol, first_step=first_step, sc_params=sc_params,
+                     interpolant=interpolant)
+    if t_eval is not None:
+        t_eval = np.asarray(t_eval, dtype=float)
+        if st.direction > 0:
+            t_eval_i = 0
+        else:
+            t_eval = t_eval[::-1]
+            t_eval_i = t_eval.shape[0]
+        ts, ys = [], []
+    else:
+        ts, ys = [t0], [st.y]
+    hs = []
+    status = None
+    message = None
+    k = 0
+    while status is None:
+        # OdeSolver.step, scipy base.py:179-210
+        if st.n == 0 or st.t == st.t_bound:
+            st.t_old = st.t
+            st.t = st.t_bound
+            st.status = "finished"
+        else:
+            if forced_h is not None:
+                ok, message = rk_step(st, forced_h=forced_h[k])
+            else:
+                ok, message = rk_step(st)
+            if not ok:
+                st.status = "failed"
+            elif st.direction * (st.t - st.t_bound) >= 0:
+                st.status = "finished"
+        k += 1
+        if st.status == "finished":
+            status = 0
+        elif st.status == "failed":
+            status = -1
+            break
+        if record:
+            hs.append(abs(st.h_previous))
+        t = st.t
+        if t_eval is None:
+            ts.append(t)
+            ys.append(st.y)
+        else:                                     # ivp.py:711-728
+            if st.direction > 0:
+                i_new = np.searchsorted(t_eval, t, side="right")
+                step_pts = t_eval[t_eval_i:i_new]
+            else:
+                i_new = np.searchsorted(t_eval, t, side="left")
+                step_pts = t_eval[i_new:t_eval_i][::-1]
+            if step_pts.size > 0:
+                ts.append(step_pts)
+                ys.append(dense_eval(st, step_pts))
+                t_eval_i = i_new
+        if forced_h is not None and k >= len(forced_h):
+            status = 0
+        if max_steps is not None and k >= max_steps and status is None:
+            status = 0
+    if t_eval is None:
+        ts = np.array(ts)
+        ys = np.vstack(ys).T
+    elif ts:
+        ts = np.hstack(ts)
+        ys = np.hstack(ys)
+    else:
+        ts = np.zeros(0)
+        ys = np.zeros((st.n, 0))
+    out = dict(t=ts, y=ys, n_accepted=st.n_accepted, n_rejected=st.n_rejected,
+               nfev=st.nfev, status=status, message=message, t_final=st.t,
+               y_final=st.y.copy(), h_next=st.h_abs)
+    if record:
+        out["h"] = np.array(hs)
+    return out
+
+
+# --------------------------------------------------------------------------
+# built-in right-hand sides (SURVEY.md §8d synthetic inputs)
+# --------------------------------------------------------------------------
+def lorenz63(sigma, rho, beta):
+    def f(t, y):
+        return np.array([sigma * (y[1] - y[0]),
+                         y[0] * (rho - y[2]) - y[1],
+                         y[0] * y[1] - beta * y[2]])
+    return f
+
+
+def vanderpol(mu):
+    def f(t, y):
+        return np.array([y[1], mu * (1.0 - y[0] * y[0]) * y[1] - y[0]])
+    return f
+
+
+def arenstorf(mu):
+    def f(t, y):
+        x, yy, vx, vy = y
+        mup = 1.0 - mu
+        d1 = ((x + mu) * (x + mu) + yy * yy)
+        d1 = d1 * sqrt(d1)
+        d2 = ((x - mup) * (x - mup) + yy * yy)
+        d2 = d2 * sqrt(d2)
+        return np.array([
+            vx, vy,
+            x + 2.0 * vy - mup * (x + mu) / d1 - mu * (x - mup) / d2,
+            yy - 2.0 * vx - mup * yy / d1 - mu * yy / d2])
+    return f
+
+
+def nbody(masses, eps2):
+    """3-D softened gravity, G=1; y = [pos(3*nb), vel(3*nb)] body-major."""
+    m = np.asarray(masses, dtype=float)
+    nb = m.size
+
+    def f(t, y):
+        pos = y[:3 * nb].reshape(nb, 3)
+        acc = np.zeros((nb, 3))
+        for i in range(nb):
+            a = np.zeros(3)
+            for j in range(nb):
+                if j == i:
+                    continue
+                d = pos[j] - pos[i]
+                r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + eps2
+                inv = 1.0 / (r2 * sqrt(r2))
+                a += m[j] * inv * d
+            acc[i] = a
+        return np.concatenate([y[3 * nb:], acc.ravel()])
+    return f
