@@ -1,0 +1,17 @@
+"""extensisq_b200 -- B200 (sm_100a) implementation of extensisq's explicit
+Runge-Kutta / SWAG / SSV2stab stepping path for ensembles and large PDEs.
+
+Same export names as the reference for the hot-path classes
+(``extensisq/__init__.py:4-12``); everything else of the reference (ESDIRK,
+Nystrom, sensitivity) is out of scope.
+"""
+from .tableaux import (RungeKutta, Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
+                       CFMR7osc, BUILTIN, REFERENCE_VERSION)
+from .batched import (DeviceRHS, BatchedOdeResult, solve_ivp_batched, NFS,
+                      update_nfs)
+from .sharding import shard_bounds, gather_result
+
+__version__ = "0.1.0"
+__all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "Me4", "Pr7", "Pr8", "Pr9",
+           "CFMR7osc", "DeviceRHS", "BatchedOdeResult", "solve_ivp_batched",
+           "NFS", "update_nfs", "shard_bounds", "gather_result"]

@@ -1,0 +1,325 @@
+"""``solve_ivp_batched`` -- the batched, device-resident counterpart of
+``scipy.integrate.solve_ivp(fun, t_span, y0, method=Cls, t_eval=..., **opts)``
+for the reference's explicit Runge-Kutta classes.
+
+Host logic only: argument validation with the reference's semantics and
+exception types (``extensisq/common.py:30-54, 166-185, 187-214``; scipy
+``_ivp/common.py:10-23``; ``_ivp/ivp.py:600-620`` for ``t_eval``), layout
+conversion to the SoA buffers the kernel wants, and the ctypes call into
+``libxsq.so``.  PyTorch is the memory / stream provider.  No arithmetic of the
+method happens here and there is no CPU path.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tableaux import RungeKutta
+
+__all__ = ["DeviceRHS", "BatchedOdeResult", "solve_ivp_batched", "NFS"]
+
+# The reference keeps a module-global failed-step counter reset by every
+# constructor (common.py:14, 220).  For ensembles it holds the SUM over lanes of
+# the last solve; per-lane values are in BatchedOdeResult.n_rejected.
+NFS = np.array(0)
+
+
+class DeviceRHS:
+    """A right-hand side that exists as device code.
+
+    ``DeviceRHS.builtin("lorenz63")`` or ``DeviceRHS.from_source(src, "rhs",
+    n_state, n_param)`` where ``src`` defines
+    ``__device__ void rhs(double t, const double* y, const double* p,
+    double* dy)``.  Replaces the Python callable ``fun`` of common.py:187."""
+
+    def __init__(self, handle, n_state, n_param, name):
+        self.handle, self.n_state, self.n_param, self.name = (
+            handle, n_state, n_param, name)
+
+    _builtin_cache = {}
+
+    @classmethod
+    def builtin(cls, name):
+        if name in cls._builtin_cache:
+            return cls._builtin_cache[name]
+        lib = _lib.load()
+        h, ns, npar = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(lib.xsq_rhs_builtin(name.encode(), C.byref(h), C.byref(ns),
+                                       C.byref(npar)))
+        r = cls(h.value, ns.value, npar.value, name)
+        cls._builtin_cache[name] = r
+        return r
+
+    @classmethod
+    def from_source(cls, cuda_src, entry, n_state, n_param=0):
+        lib = _lib.load()
+        h = C.c_int32()
+        _lib.check(lib.xsq_rhs_register_source(
+            cuda_src.encode(), entry.encode(), int(n_state), int(n_param),
+            C.byref(h)))
+        return cls(h.value, int(n_state), int(n_param), f"user:{entry}")
+
+
+@dataclass
+class BatchedOdeResult:
+    """Per-lane results; mirrors scipy's OdeResult field names where they
+    exist (ivp.py:758-760)."""
+    t: object                   # t_eval tensor [n_eval] or None
+    y: object                   # [N, n, n_eval] or None
+    t_final: torch.Tensor       # [N]
+    y_final: torch.Tensor       # [N, n]
+    h_next: torch.Tensor        # [N]
+    n_accepted: torch.Tensor    # int32 [N]
+    n_rejected: torch.Tensor    # int32 [N]   (the reference's NFS)
+    nfev: torch.Tensor          # int32 [N]
+    status: torch.Tensor        # int32 [N]   xsq_lane_status
+    n_eval_done: object = None  # int32 [N] or None
+    njev: int = 0
+    nlu: int = 0
+
+    @property
+    def success(self):
+        return self.status >= 0
+
+    def message(self, lane):
+        return _lib.LANE_MESSAGES[int(self.status[lane])]
+
+
+def _as_device(x, device, dtype=torch.float64):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(device,
+                                                         non_blocking=True)
+
+
+def _upload_user_tableau(cls):
+    cls.validate()
+    lib = _lib.load()
+    t = _lib.XsqTableau()
+    s = cls.n_stages
+    if s > _lib.XSQ_MAX_STAGES - 1:
+        raise ValueError(f"n_stages > {_lib.XSQ_MAX_STAGES - 1} not supported")
+    t.n_stages, t.order, t.order_secondary = s, cls.order, cls.order_secondary
+    for i in range(s):
+        for j in range(s):
+            t.A[i][j] = float(cls.A[i, j])
+        t.B[i] = float(cls.B[i])
+        t.C[i] = float(cls.C[i])
+    for i in range(s + 1):
+        t.E[i] = float(cls.E[i])
+    if isinstance(cls.P, np.ndarray):
+        if cls.P.shape[1] > _lib.XSQ_MAX_POLY:
+            raise ValueError("P has too many columns")
+        t.n_poly = cls.P.shape[1]
+        for i in range(s + 1):
+            for k in range(t.n_poly):
+                t.P[i][k] = float(cls.P[i, k])
+    else:
+        t.n_poly = 0
+    kb = _sc_tuple(cls.sc_params)
+    for i in range(4):
+        t.sc_params[i] = kb[i]
+    _lib.check(lib.xsq_tableau_load(C.byref(t)))
+
+
+_SC = {"G": (0.7, -0.4, 0, 0.9), "S": (0.6, -0.2, 0, 0.9),
+       "standard": (1, 0, 0, 0.9)}          # common.py:167-169
+
+
+def _sc_tuple(sc_params):
+    if isinstance(sc_params, str) and sc_params in _SC:
+        return tuple(float(v) for v in _SC[sc_params])
+    if isinstance(sc_params, tuple) and len(sc_params) == 4:
+        return tuple(float(v) for v in sc_params)
+    raise ValueError('sc_params should be a tuple of length 4 or one '
+                     'of the strings "G", "S", "W" or "standard"')
+
+
+def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
+                      rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf,
+                      sc_params=None, interpolant=None, max_steps=None,
+                      forced_steps=None, device=None, stream=None,
+                      **extraneous):
+    """Integrate N independent systems ``y' = fun(t, y; params_i)``.
+
+    Parameters follow ``solve_ivp`` / ``RungeKutta.__init__`` (common.py:187):
+
+    fun : DeviceRHS or str (built-in name)
+    t_span : (t0, tf), shared by all lanes
+    y0 : [N, n] float64 tensor/array (a 1-D [n] input is one lane)
+    method : a tableau class from this package or a RungeKutta subclass
+    t_eval : [n_eval] times inside t_span, sorted along the direction
+    params : [N, p] per-lane parameters of the RHS
+    rtol : float;  atol : float or [n];  first_step, max_step : float
+    sc_params : "G" | "S" | "standard" | (kb1, kb2, a, g)
+    interpolant : BS5 only, 'best' | 'low' | 'free' (bogacki.py:217)
+    max_steps : attempted-step budget per lane (GPU safety net, no reference
+        analogue)
+    forced_steps : [k] sequence of |h|; takes exactly these steps, accepting
+        each (parity mode of BASELINE.json's north_star)
+
+    Returns a :class:`BatchedOdeResult` with device tensors.
+    """
+    global NFS
+    if extraneous:
+        import warnings
+        warnings.warn("The following arguments have no effect for a chosen "
+                      f"solver: {', '.join(f'`{k}`' for k in extraneous)}.",
+                      stacklevel=2)
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("extensisq_b200 needs a CUDA device; there is no "
+                           "CPU fallback")
+    if isinstance(fun, str):
+        fun = DeviceRHS.builtin(fun)
+    if not isinstance(fun, DeviceRHS):
+        raise TypeError("`fun` must be a DeviceRHS or the name of a built-in "
+                        "right-hand side; Python callables cannot run on the "
+                        "device")
+    if not (isinstance(method, type) and issubclass(method, RungeKutta)):
+        raise ValueError("`method` must be one of the tableau classes or a "
+                         "RungeKutta subclass")
+    if device is None:
+        device = (y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda
+                  else torch.device("cuda", torch.cuda.current_device()))
+    device = torch.device(device)
+    t0, tf = map(float, t_span)
+    n, p = fun.n_state, fun.n_param
+
+    # --- validation, same order/messages as the reference -----------------
+    if not isinstance(rtol, float):
+        raise ValueError("`rtol` must be a float.")
+    if rtol < 0:
+        raise ValueError("`rtol` must be positive.")
+    atol_np = np.atleast_1d(np.asarray(atol, dtype=float))
+    if atol_np.ndim > 1 or atol_np.size not in (1, n):
+        raise ValueError("`atol` has wrong shape.")
+    if np.any(atol_np < 0):
+        raise ValueError("`atol` must be positive.")
+    if max_step <= 0:
+        raise ValueError("`max_step` must be positive.")
+    if first_step is not None and forced_steps is None:
+        if first_step <= 0:
+            raise ValueError("`first_step` must be positive.")
+        if first_step > abs(tf - t0):
+            raise ValueError("`first_step` exceeds bounds.")
+    sc = _sc_tuple(sc_params) if sc_params is not None else None
+    if interpolant not in (None, "best", "low", "free"):
+        raise ValueError("interpolant should be one of: 'best', 'low', 'free'")
+
+    with torch.cuda.device(device):
+        y0_t = _as_device(y0, device)
+        if y0_t.ndim == 1:
+            y0_t = y0_t[None, :]
+        if y0_t.ndim != 2 or y0_t.shape[1] != n:
+            raise ValueError(f"`y0` must have shape [N, {n}]")
+        N = y0_t.shape[0]
+        y0_soa = y0_t.t().contiguous()                     # [n, N]
+        if p > 0:
+            if params is None:
+                raise ValueError(f"`params` [N, {p}] required by {fun.name}")
+            prm = _as_device(params, device)
+            if prm.ndim == 1:
+                prm = prm[:, None] if p == 1 else prm[None, :]
+            if prm.shape[0] == 1 and N > 1:
+                prm = prm.expand(N, p)
+            if prm.shape != (N, p):
+                raise ValueError(f"`params` must have shape [N, {p}]")
+            prm_soa = prm.t().contiguous()
+        else:
+            prm_soa = None
+
+        n_eval = 0
+        te = None
+        if t_eval is not None:                              # ivp.py:600-612
+            te = _as_device(t_eval, device)
+            if te.ndim != 1:
+                raise ValueError("`t_eval` must be 1-dimensional.")
+            if te.numel() > 0:
+                lo, hi = min(t0, tf), max(t0, tf)
+                if bool((te < lo).any()) or bool((te > hi).any()):
+                    raise ValueError("Values in `t_eval` are not within "
+                                     "`t_span`.")
+                d = te[1:] - te[:-1]
+                if (tf > t0 and bool((d <= 0).any())) or \
+                        (tf < t0 and bool((d >= 0).any())):
+                    raise ValueError("Values in `t_eval` are not properly "
+                                     "sorted.")
+            n_eval = te.numel()
+            te = te.contiguous()
+        hf = None
+        if forced_steps is not None:
+            hf = _as_device(forced_steps, device).contiguous()
+            if hf.ndim != 1 or hf.numel() < 1:
+                raise ValueError("`forced_steps` must be a non-empty 1-D "
+                                 "sequence")
+
+        if method._xsq_method is None:
+            _upload_user_tableau(method)
+            mid = _lib.XSQ_METHOD_USER
+        else:
+            mid = method._xsq_method
+
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        y_eval = torch.empty((N, n, n_eval), **f64) if n_eval else None
+        t_final = torch.empty(N, **f64)
+        y_final = torch.empty((n, N), **f64)
+        h_next = torch.empty(N, **f64)
+        n_acc = torch.empty(N, **i32)
+        n_rej = torch.empty(N, **i32)
+        nfev = torch.empty(N, **i32)
+        status = torch.empty(N, **i32)
+        n_done = torch.empty(N, **i32) if n_eval else None
+
+        a = _lib.XsqRkArgs()
+        a.struct_size = C.sizeof(_lib.XsqRkArgs)
+        a.method, a.rhs = mid, fun.handle
+        a.n_state, a.n_param = n, p
+        a.interpolant = _lib.INTERPOLANTS[interpolant]
+        a.n_lanes = N
+        a.y0 = y0_soa.data_ptr()
+        a.params = prm_soa.data_ptr() if prm_soa is not None else None
+        a.t0, a.t_bound = t0, tf
+        a.rtol = rtol
+        atol_c = (C.c_double * atol_np.size)(*atol_np.tolist())
+        a.atol = C.cast(atol_c, C.POINTER(C.c_double))
+        a.n_atol = atol_np.size
+        a.use_sc_params = 1 if sc is not None else 0
+        if sc is not None:
+            for i in range(4):
+                a.sc_params[i] = sc[i]
+        a.first_step = float(first_step) if first_step is not None else 0.0
+        a.max_step = float(max_step)
+        a.t_eval = te.data_ptr() if n_eval else None
+        a.n_eval = n_eval
+        a.max_steps = int(max_steps) if max_steps else 0
+        a.y_eval = y_eval.data_ptr() if n_eval else None
+        a.h_forced = hf.data_ptr() if hf is not None else None
+        a.n_forced = hf.numel() if hf is not None else 0
+        a.t_final = t_final.data_ptr()
+        a.y_final = y_final.data_ptr()
+        a.h_next = h_next.data_ptr()
+        a.n_accepted = n_acc.data_ptr()
+        a.n_rejected = n_rej.data_ptr()
+        a.nfev = nfev.data_ptr()
+        a.status = status.data_ptr()
+        a.n_eval_done = n_done.data_ptr() if n_eval else None
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        _lib.check(lib.xsq_rk_solve(C.byref(a), C.c_void_p(st.cuda_stream)))
+        # the kernel runs on `st`; tensors above stay referenced by the result
+
+    res = BatchedOdeResult(
+        t=te, y=y_eval, t_final=t_final, y_final=y_final.t(), h_next=h_next,
+        n_accepted=n_acc, n_rejected=n_rej, nfev=nfev, status=status,
+        n_eval_done=n_done)
+    res._keepalive = (y0_soa, prm_soa, hf, atol_c)
+    return res
+
+
+def update_nfs(result):
+    """Mirror the reference's global NFS (sum over lanes; forces a sync)."""
+    NFS[()] = int(result.n_rejected.sum().item())
+    return int(NFS)

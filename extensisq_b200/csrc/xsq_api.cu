@@ -1,0 +1,442 @@
+// xsq_api.cu -- the C ABI of libxsq.so (see include/xsq.h).  Host-side
+// argument validation mirrors the reference's constructors:
+//   validate_tol            extensisq/common.py:30-54
+//   _init_sc_control        extensisq/common.py:166-185
+//   validate_first_step /   scipy/integrate/_ivp/common.py:10-23 (third party)
+//   validate_max_step
+// There is NO CPU fallback: every entry point either runs on the CUDA device
+// or returns XSQ_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "xsq.h"
+#include "xsq_launch.h"
+#include "xsq_user.h"
+
+namespace xsq {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+thread_local std::string g_detail;
+void set_detail(const std::string& s) { g_detail = s; }
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_detail = std::string(what) + ": " + cudaGetErrorString(e);
+    return XSQ_ERR_CUDA;
+}
+#define XSQ_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+    } while (0)
+
+template <class T>
+static MethodInfo info_of() {
+    return MethodInfo{T::S, T::ORDER, T::ORDER2, T::FSAL, T::NPOL,
+                      {T::SC_KB1, T::SC_KB2, T::SC_A, T::SC_G}};
+}
+
+static bool method_info(int method, MethodInfo* mi) {
+    switch (method) {
+        case XSQ_TS5: *mi = info_of<tab::Ts5>(); return true;
+        case XSQ_BS5: *mi = info_of<tab::BS5>(); return true;
+        case XSQ_CK5: *mi = info_of<tab::CK5>(); return true;
+        case XSQ_ME4: *mi = info_of<tab::Me4>(); return true;
+        case XSQ_PR7: *mi = info_of<tab::Pr7>(); return true;
+        case XSQ_PR8: *mi = info_of<tab::Pr8>(); return true;
+        case XSQ_PR9: *mi = info_of<tab::Pr9>(); return true;
+        case XSQ_CFMR7OSC: *mi = info_of<tab::CFMR7osc>(); return true;
+        default: return false;
+    }
+}
+
+// ---- device read-back of a built-in tableau ---------------------------------
+template <class T>
+__global__ void tableau_dump(xsq_tableau_t* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out->n_stages = T::S;
+    out->order = T::ORDER;
+    out->order_secondary = T::ORDER2;
+    out->n_poly = T::NPOL;
+    for (int i = 0; i < T::S; ++i) {
+        for (int j = 0; j < T::S; ++j) out->A[i][j] = T::a(i, j);
+        out->B[i] = T::b(i);
+        out->C[i] = T::c(i);
+    }
+    for (int i = 0; i <= T::S; ++i) {
+        out->E[i] = T::e(i);
+        for (int k = 0; k < T::NPOL; ++k) out->P[i][k] = T::p(i, k);
+    }
+    out->sc_params[0] = T::SC_KB1;
+    out->sc_params[1] = T::SC_KB2;
+    out->sc_params[2] = T::SC_A;
+    out->sc_params[3] = T::SC_G;
+}
+
+// ---- fp64 FMA peak microbenchmark -------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters,
+                                                        double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] =
+        ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+static int dispatch(int method, int rhs, const RkDev& P, cudaStream_t st,
+                    LaunchInfo* info) {
+    if (rhs >= XSQ_RHS_USER_BASE) return user_rk_launch(method, rhs, P, st);
+    switch (method) {
+        case XSQ_TS5: return launch_Ts5(rhs, P, st, info);
+        case XSQ_BS5: return launch_BS5(rhs, P, st, info);
+        case XSQ_CK5: return launch_CK5(rhs, P, st, info);
+        case XSQ_ME4: return launch_Me4(rhs, P, st, info);
+        case XSQ_PR7: return launch_Pr7(rhs, P, st, info);
+        case XSQ_PR8: return launch_Pr8(rhs, P, st, info);
+        case XSQ_PR9: return launch_Pr9(rhs, P, st, info);
+        case XSQ_CFMR7OSC: return launch_CFMR7osc(rhs, P, st, info);
+        default: return XSQ_ERR_UNSUPPORTED;
+    }
+}
+
+struct RhsInfo { const char* name; int id, n_state, n_param; };
+static const RhsInfo kBuiltinRhs[] = {
+    {"lorenz63", XSQ_RHS_LORENZ63, 3, 3},
+    {"vanderpol", XSQ_RHS_VANDERPOL, 2, 1},
+    {"arenstorf", XSQ_RHS_ARENSTORF, 4, 1},
+    {"nbody32", XSQ_RHS_NBODY32, 192, 33},
+};
+
+static bool rhs_shape(int rhs, int* n_state, int* n_param) {
+    for (const RhsInfo& r : kBuiltinRhs)
+        if (r.id == rhs) { *n_state = r.n_state; *n_param = r.n_param; return true; }
+    return user_rhs_shape(rhs, n_state, n_param);
+}
+
+// Build the device parameter block from the ABI struct; validation follows
+// the reference constructors.
+static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
+                        std::vector<double>* atol_full) {
+    if (!a || a->struct_size != (int32_t)sizeof(xsq_rk_args_t)) {
+        g_detail = "xsq_rk_args_t.struct_size mismatch";
+        return XSQ_ERR_ARG;
+    }
+    if (a->method == XSQ_METHOD_USER) {
+        if (!user_tableau_info(mi)) {
+            g_detail = "no user tableau loaded";
+            return XSQ_ERR_ARG;
+        }
+    } else if (!method_info(a->method, mi)) {
+        g_detail = "unknown method";
+        return XSQ_ERR_ARG;
+    }
+    int ns = 0, np = 0;
+    if (!rhs_shape(a->rhs, &ns, &np)) { g_detail = "unknown rhs"; return XSQ_ERR_ARG; }
+    if (a->n_state != ns || a->n_param != np) {
+        g_detail = "n_state/n_param do not match the rhs";
+        return XSQ_ERR_ARG;
+    }
+    if (a->n_lanes < 0) { g_detail = "n_lanes < 0"; return XSQ_ERR_ARG; }
+    if (!a->y0 || !a->t_final || !a->y_final || !a->n_accepted ||
+        !a->n_rejected || !a->nfev || !a->status ||
+        (np > 0 && !a->params)) {
+        g_detail = "required pointer is NULL";
+        return XSQ_ERR_ARG;
+    }
+    // validate_tol, common.py:30-54
+    if (!(a->n_atol == 1 || a->n_atol == ns) || !a->atol) {
+        g_detail = "`atol` has wrong shape.";
+        return XSQ_ERR_ARG;
+    }
+    if (!(a->rtol >= 0)) { g_detail = "`rtol` must be positive."; return XSQ_ERR_ARG; }
+    atol_full->resize(ns);
+    for (int i = 0; i < ns; ++i) {
+        double v = a->atol[a->n_atol == 1 ? 0 : i];
+        if (!(v >= 0)) { g_detail = "`atol` must be positive."; return XSQ_ERR_ARG; }
+        (*atol_full)[i] = std::fmax(v, 0x1.0p-511);          // sqrt(tiny)
+    }
+    std::memset(P, 0, sizeof(*P));
+    P->rtol = std::fmin(std::fmax(a->rtol, 0x1.4p-50), 0.1);  // 10*epsneg
+    if (ns <= XSQ_MAX_LANE_STATE)
+        for (int i = 0; i < ns; ++i) P->atol[i] = (*atol_full)[i];
+    // validate_max_step / validate_first_step (scipy _ivp/common.py:10-23)
+    if (!(a->max_step > 0)) { g_detail = "`max_step` must be positive."; return XSQ_ERR_ARG; }
+    if (a->n_forced == 0 && a->first_step > 0 &&
+        a->first_step > std::fabs(a->t_bound - a->t0)) {
+        g_detail = "`first_step` exceeds bounds.";
+        return XSQ_ERR_ARG;
+    }
+    if (a->n_eval < 0 || (a->n_eval > 0 && (!a->t_eval || !a->y_eval))) {
+        g_detail = "t_eval / y_eval inconsistent";
+        return XSQ_ERR_ARG;
+    }
+    if (a->n_forced < 0 || (a->n_forced > 0 && !a->h_forced)) {
+        g_detail = "h_forced inconsistent";
+        return XSQ_ERR_ARG;
+    }
+    // _init_sc_control, common.py:166-185
+    const double* sc = a->use_sc_params ? a->sc_params : mi->sc;
+    const int order_error = mi->order2 < mi->order ? mi->order2 : mi->order;
+    P->err_exp = -1.0 / (order_error + 1);
+    P->minbeta1 = sc[0] * P->err_exp;
+    P->minbeta2 = sc[1] * P->err_exp;
+    P->minalpha = -sc[2];
+    P->safety = sc[3];
+    P->safety_sc = std::pow(sc[3], sc[0] + sc[1]);
+    P->n_lanes = a->n_lanes;
+    P->y0 = a->y0;
+    P->params = a->params;
+    P->t0 = a->t0;
+    P->t_bound = a->t_bound;
+    // OdeSolver.__init__, base.py:165
+    P->direction = (a->t_bound != a->t0) ? (a->t_bound > a->t0 ? 1.0 : -1.0) : 1.0;
+    P->first_step = a->first_step;
+    P->max_step = a->max_step;
+    P->t_eval = a->t_eval;
+    P->y_eval = a->y_eval;
+    P->n_eval = a->n_eval;
+    P->h_forced = a->h_forced;
+    P->n_forced = a->n_forced;
+    P->max_steps = a->max_steps > 0 ? a->max_steps
+                                    : std::numeric_limits<int>::max();
+    int ip = a->interpolant;
+    if (ip == XSQ_INTERP_DEFAULT) ip = XSQ_INTERP_LOW;      // bogacki.py:218
+    if (ip < XSQ_INTERP_FREE || ip > XSQ_INTERP_BEST) {
+        g_detail = "interpolant should be one of: 'best', 'low', 'free'";
+        return XSQ_ERR_ARG;
+    }
+    P->interpolant = ip;
+    P->t_final = a->t_final;
+    P->y_final = a->y_final;
+    P->h_next = a->h_next;
+    P->n_acc = a->n_accepted;
+    P->n_rej = a->n_rejected;
+    P->nfev = a->nfev;
+    P->status = a->status;
+    P->n_eval_done = a->n_eval_done;
+    return XSQ_OK;
+}
+
+static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
+                        LaunchInfo* info) {
+    RkDev P;
+    MethodInfo mi;
+    std::vector<double> atol;
+    int rc = build_params(a, &P, &mi, &atol);
+    if (rc != XSQ_OK) return rc;
+    if (a->n_lanes == 0) return XSQ_OK;
+    // scratch: [queue counter (8 B, padded to 16)] [atol vector]
+    const size_t bytes = 16 + atol.size() * sizeof(double);
+    char* scratch = nullptr;
+    XSQ_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
+    XSQ_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
+    XSQ_CUDA(cudaMemcpyAsync(scratch + 16, atol.data(),
+                             atol.size() * sizeof(double),
+                             cudaMemcpyHostToDevice, st));
+    // the pageable atol copy is staged by the runtime before returning
+    P.queue = (unsigned long long*)scratch;
+    P.atol_dev = (const double*)(scratch + 16);
+    rc = dispatch(a->method, a->rhs, P, st, info);
+    cudaError_t e = cudaFreeAsync(scratch, st);
+    if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+    return rc;
+}
+
+}  // namespace xsq
+
+using namespace xsq;
+
+extern "C" {
+
+int xsq_abi_version(void) { return XSQ_ABI_VERSION; }
+
+const char* xsq_strerror(int err) {
+    switch (err) {
+        case XSQ_OK: return "ok";
+        case XSQ_ERR_ARG: return "invalid argument";
+        case XSQ_ERR_CUDA: return "CUDA error (no usable device or launch failure)";
+        case XSQ_ERR_NVRTC: return "runtime compilation of the user RHS failed";
+        case XSQ_ERR_UNSUPPORTED: return "method/rhs combination not available";
+        case XSQ_ERR_NOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+const char* xsq_last_error_detail(void) { return g_detail.c_str(); }
+
+int xsq_device_info(int device, int32_t* n_sm, int32_t* cc_major,
+                    int32_t* cc_minor) {
+    int n = 0;
+    XSQ_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { g_detail = "no such device"; return XSQ_ERR_CUDA; }
+    int v = 0;
+    XSQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    if (n_sm) *n_sm = v;
+    XSQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+    if (cc_major) *cc_major = v;
+    XSQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+    if (cc_minor) *cc_minor = v;
+    return XSQ_OK;
+}
+
+int xsq_tableau_get(int32_t method, xsq_tableau_t* out) {
+    if (!out) return XSQ_ERR_ARG;
+    xsq_tableau_t* d = nullptr;
+    XSQ_CUDA(cudaMalloc((void**)&d, sizeof(xsq_tableau_t)));
+    cudaMemset(d, 0, sizeof(xsq_tableau_t));
+    switch (method) {
+        case XSQ_TS5: tableau_dump<tab::Ts5><<<1, 32>>>(d); break;
+        case XSQ_BS5: tableau_dump<tab::BS5><<<1, 32>>>(d); break;
+        case XSQ_CK5: tableau_dump<tab::CK5><<<1, 32>>>(d); break;
+        case XSQ_ME4: tableau_dump<tab::Me4><<<1, 32>>>(d); break;
+        case XSQ_PR7: tableau_dump<tab::Pr7><<<1, 32>>>(d); break;
+        case XSQ_PR8: tableau_dump<tab::Pr8><<<1, 32>>>(d); break;
+        case XSQ_PR9: tableau_dump<tab::Pr9><<<1, 32>>>(d); break;
+        case XSQ_CFMR7OSC: tableau_dump<tab::CFMR7osc><<<1, 32>>>(d); break;
+        default: cudaFree(d); return XSQ_ERR_ARG;
+    }
+    count_launch();
+    cudaError_t e = cudaMemcpy(out, d, sizeof(xsq_tableau_t),
+                               cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "tableau_dump");
+    return XSQ_OK;
+}
+
+int xsq_rhs_builtin(const char* name, int32_t* rhs_out, int32_t* n_state,
+                    int32_t* n_param) {
+    if (!name) return XSQ_ERR_ARG;
+    for (const RhsInfo& r : kBuiltinRhs) {
+        if (std::strcmp(r.name, name) == 0) {
+            if (rhs_out) *rhs_out = r.id;
+            if (n_state) *n_state = r.n_state;
+            if (n_param) *n_param = r.n_param;
+            return XSQ_OK;
+        }
+    }
+    g_detail = std::string("unknown built-in rhs: ") + name;
+    return XSQ_ERR_ARG;
+}
+
+int xsq_rk_solve(const xsq_rk_args_t* args, void* stream) {
+    return solve_device(args, (cudaStream_t)stream, nullptr);
+}
+
+int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
+    if (!h || h->struct_size != (int32_t)sizeof(xsq_rk_args_t)) return XSQ_ERR_ARG;
+    XSQ_CUDA(cudaSetDevice(device));
+    int ns = h->n_state, np = h->n_param;
+    const long long N = h->n_lanes;
+    if (N < 0 || ns <= 0 || np < 0) return XSQ_ERR_ARG;
+    cudaStream_t st;
+    XSQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    xsq_rk_args_t d = *h;
+    std::vector<void*> owned;
+    int rc = XSQ_OK;
+    auto dalloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (bytes == 0) bytes = 8;
+        if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { rc = XSQ_ERR_NOMEM; return nullptr; }
+        owned.push_back(p);
+        return p;
+    };
+    auto h2d = [&](const void* src, size_t bytes) -> void* {
+        void* p = dalloc(bytes);
+        if (p && src && bytes)
+            if (cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                rc = XSQ_ERR_CUDA;
+        return p;
+    };
+    const size_t nd = sizeof(double), ni = sizeof(int32_t);
+    d.y0 = (const double*)h2d(h->y0, (size_t)N * ns * nd);
+    d.params = np ? (const double*)h2d(h->params, (size_t)N * np * nd) : nullptr;
+    d.t_eval = h->n_eval ? (const double*)h2d(h->t_eval, (size_t)h->n_eval * nd) : nullptr;
+    d.h_forced = h->n_forced ? (const double*)h2d(h->h_forced, (size_t)h->n_forced * nd) : nullptr;
+    d.y_eval = h->n_eval ? (double*)dalloc((size_t)N * ns * h->n_eval * nd) : nullptr;
+    d.t_final = (double*)dalloc((size_t)N * nd);
+    d.y_final = (double*)dalloc((size_t)N * ns * nd);
+    d.h_next = h->h_next ? (double*)dalloc((size_t)N * nd) : nullptr;
+    d.n_accepted = (int32_t*)dalloc((size_t)N * ni);
+    d.n_rejected = (int32_t*)dalloc((size_t)N * ni);
+    d.nfev = (int32_t*)dalloc((size_t)N * ni);
+    d.status = (int32_t*)dalloc((size_t)N * ni);
+    d.n_eval_done = h->n_eval_done ? (int32_t*)dalloc((size_t)N * ni) : nullptr;
+    if (rc == XSQ_OK) rc = solve_device(&d, st, nullptr);
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+        if (rc == XSQ_OK && dst && bytes)
+            if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                rc = XSQ_ERR_CUDA;
+    };
+    if (h->n_eval) d2h(h->y_eval, d.y_eval, (size_t)N * ns * h->n_eval * nd);
+    d2h(h->t_final, d.t_final, (size_t)N * nd);
+    d2h(h->y_final, d.y_final, (size_t)N * ns * nd);
+    if (h->h_next) d2h(h->h_next, d.h_next, (size_t)N * nd);
+    d2h(h->n_accepted, d.n_accepted, (size_t)N * ni);
+    d2h(h->n_rejected, d.n_rejected, (size_t)N * ni);
+    d2h(h->nfev, d.nfev, (size_t)N * ni);
+    d2h(h->status, d.status, (size_t)N * ni);
+    if (h->n_eval_done) d2h(h->n_eval_done, d.n_eval_done, (size_t)N * ni);
+    for (void* p : owned) cudaFreeAsync(p, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "xsq_rk_solve_host");
+    return rc;
+}
+
+int64_t xsq_launch_count(int reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int xsq_fp64_peak(int device, int32_t iters, double* tflops) {
+    if (!tflops || iters <= 0) return XSQ_ERR_ARG;
+    XSQ_CUDA(cudaSetDevice(device));
+    int n_sm = 0;
+    XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const int block = 256, grid = n_sm * 8;
+    double* out = nullptr;
+    XSQ_CUDA(cudaMalloc((void**)&out, sizeof(double) * grid * block));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_peak_kernel<<<grid, block>>>(out, iters / 4 + 1, 0.999999, 1e-9);  // warm-up
+    count_launch();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        count_launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(out);
+    if (e != cudaSuccess) return cuda_fail(e, "fp64_peak_kernel");
+    const double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * block;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return XSQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,760 @@
+// xsq_rk_core.cuh -- the tableau-driven adaptive explicit Runge-Kutta step as
+// a persistent fp64 kernel: one lane (thread) or one warp per ODE system,
+// state + all stage vectors in registers, per-lane step control, finished
+// lanes retired by warp ballot and refilled from a global work queue.
+//
+// What it computes is what these reference functions compute (file:line in
+// /root/reference/extensisq):
+//   RungeKutta.__init__            common.py:187-220
+//   _init_min_step_parameters      common.py:123-148   (H_MIN_A, h_min_b)
+//   _init_sc_control               common.py:166-185   (host side, xsq_api.cu)
+//   h_start                        common.py:519-763   -> h_start_dev()
+//   _reassess_stepsize             common.py:310-331   -> reassess()
+//   _rk_stage                      common.py:353-356   -> stage sums below
+//   _comp_sol_err/_estimate_error  common.py:333-351
+//   calculate_scale, norm          common.py:57-66
+//   controller in _step_impl       common.py:249-287
+//   BS5._step_impl + pre-error     bogacki.py:238-346
+//   CFMR7osc._step_impl + pre-err  calvo.py:152-261
+//   _dense_output_impl / Horner    common.py:358-368, 766-790
+//   BS5 interpolants               bogacki.py:348-393
+//   solve_ivp t_eval slicing       scipy/integrate/_ivp/ivp.py:711-728
+//   OdeSolver.step finish test     scipy/integrate/_ivp/base.py:195-210
+//
+// This header is also the translation unit NVRTC compiles for user-supplied
+// right-hand sides, so it includes nothing from the host toolchain.
+#pragma once
+#include "xsq_tableaux_gen.cuh"
+
+namespace xsq {
+
+// ---- machine constants (numpy.finfo(float64)) ------------------------------
+#define XSQ_SQRT_TINY 0x1.0p-511               /* sqrt(2.2250738585072014e-308) */
+#define XSQ_BIG 0x1.fffffffffffffp+511         /* sqrt(DBL_MAX)                 */
+#define XSQ_SMALL 0x1.0000000000001p-53        /* nextafter(epsneg, 1)          */
+#define XSQ_RELPER 0x1.172b83c7d517bp-20       /* XSQ_SMALL ** 0.375  (libm)    */
+#define XSQ_NAN __longlong_as_double(0x7ff8000000000000LL)
+#define XSQ_INF __longlong_as_double(0x7ff0000000000000LL)
+
+static constexpr double kMinFactor = 0.2;       // common.py:18
+static constexpr double kMaxFactor = 4.0;       // common.py:19
+static constexpr double kMaxFactor0 = 10.0;     // common.py:20
+
+enum LaneStatus : int {
+    LANE_FINISHED = 0, LANE_TOO_SMALL = -1, LANE_OVERFLOW = -2,
+    LANE_STEP_BUDGET = -5, LANE_RUNNING = 1
+};
+enum Interp : int { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
+
+// Device-side parameter block; passed by value as the kernel argument so every
+// field is a constant-bank operand.
+struct RkDev {
+    long long n_lanes;
+    const double* y0;
+    const double* params;
+    double t0, t_bound, direction;
+    double rtol;
+    double atol[16];
+    const double* atol_dev;       // [n_state], used by warp-per-system kernels
+    double first_step, max_step;
+    double err_exp, minbeta1, minbeta2, minalpha, safety, safety_sc;
+    double h_min_a;               // user tableaux; built-ins use Tab::H_MIN_A
+    const double* t_eval;
+    double* y_eval;
+    const double* h_forced;
+    double* t_final;
+    double* y_final;
+    double* h_next;
+    int* n_acc;
+    int* n_rej;
+    int* nfev;
+    int* status;
+    int* n_eval_done;
+    unsigned long long* queue;
+    int n_eval, n_forced, max_steps, interpolant;
+};
+
+// ---- reductions over one system -------------------------------------------
+template <bool WARP>
+__device__ __forceinline__ double sys_sum(double x) {
+    if (WARP) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    return x;
+}
+template <bool WARP>
+__device__ __forceinline__ double sys_min(double x) {
+    if (WARP) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+    }
+    return x;
+}
+
+// RMS norm, common.py:64-66
+template <class R>
+__device__ __forceinline__ double rms(const double (&x)[R::NL]) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < R::NL; ++c) s = fma(x[c], x[c], s);
+    s = sys_sum<R::WARP>(s);
+    return sqrt(s / (double)R::N);
+}
+
+template <class R>
+__device__ __forceinline__ double atol_of(const RkDev& P, int k, int lane) {
+    if (R::WARP) return P.atol_dev[R::comp(k, lane)];
+    return P.atol[k];
+}
+
+// ---- Watts' starting step, common.py:519-763 --------------------------------
+template <class R>
+__device__ double h_start_dev(const RkDev& P, double a, double b,
+                              const double (&y)[R::NL],
+                              const double (&yprime)[R::NL],
+                              const double (&prm)[R::NPL], int morder,
+                              int lane, int& nfev) {
+    constexpr int NL = R::NL;
+    const double big = XSQ_BIG, small = XSQ_SMALL, relper = XSQ_RELPER;
+    double spy[NL], pv[NL], yp[NL], sf[NL];
+    const double dx = b - a;
+    const double absdx = fabs(dx);
+    double da = copysign(fmax(fmin(relper * fabs(a), absdx),
+                              100.0 * small * fabs(a)), dx);
+    if (da == 0.0) da = relper * dx;
+    R::f(a + da, y, prm, sf);
+    ++nfev;
+#pragma unroll
+    for (int c = 0; c < NL; ++c) yp[c] = sf[c] - yprime[c];
+    double delf = rms<R>(yp);
+    double dfdxb = big;
+    if (delf < big * fabs(da)) dfdxb = delf / fabs(da);
+    double fbnd = rms<R>(sf);
+
+    double dely = relper * rms<R>(y);
+    if (dely == 0.0) dely = relper;
+    dely = copysign(dely, dx);
+    delf = rms<R>(yprime);
+    fbnd = fmax(fbnd, delf);
+    if (delf != 0.0) {
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { spy[c] = yprime[c]; yp[c] = yprime[c]; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { spy[c] = 0.0; yp[c] = 1.0; }
+        delf = rms<R>(yp);
+    }
+    double dfdub = 0.0;
+    const int lk = R::N + 1 < 3 ? R::N + 1 : 3;
+    for (int k = 1; k <= lk; ++k) {
+        const double q = dely / delf;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) pv[c] = fma(q, yp[c], y[c]);
+        if (k == 2) {
+            R::f(a + da, pv, prm, yp);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) pv[c] = yp[c] - sf[c];
+        } else {
+            R::f(a, pv, prm, yp);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) pv[c] = yp[c] - yprime[c];
+        }
+        ++nfev;
+        fbnd = fmax(fbnd, rms<R>(yp));
+        delf = rms<R>(pv);
+        if (delf >= big * fabs(dely)) { dfdub = big; break; }
+        dfdub = fmax(dfdub, delf / fabs(dely));
+        if (k == lk) break;
+        if (delf == 0.0) delf = 1.0;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double dy;
+            if (k == 2) dy = (y[c] != 0.0) ? y[c] : dely / relper;
+            else dy = (pv[c] != 0.0) ? pv[c] : delf;
+            if (spy[c] == 0.0) spy[c] = yp[c];
+            yp[c] = (spy[c] != 0.0) ? copysign(dy, spy[c]) : dy;
+        }
+        delf = rms<R>(yp);
+    }
+    const double ydpb = fma(dfdub, fbnd, dfdxb);
+    double tolsum = 0.0, tolmin = XSQ_INF;
+#pragma unroll
+    for (int c = 0; c < NL; ++c) {
+        const double etol = fma(P.rtol, fabs(y[c]), atol_of<R>(P, c, lane));
+        const double te = log10(etol);
+        tolsum += te;
+        tolmin = fmin(tolmin, te);
+    }
+    tolsum = sys_sum<R::WARP>(tolsum);
+    tolmin = fmin(sys_min<R::WARP>(tolmin), big);
+    const double tolp =
+        pow(10.0, 0.5 * (tolsum / (double)R::N + tolmin) / (double)(morder + 1));
+    double h = absdx;
+    if (ydpb == 0.0 && fbnd == 0.0) {
+        if (tolp < 1.0) h = absdx * tolp;
+    } else if (ydpb == 0.0) {
+        if (tolp < fbnd * absdx) h = tolp / fbnd;
+    } else {
+        const double srydpb = sqrt(0.5 * ydpb);
+        if (tolp < srydpb * absdx) h = tolp / srydpb;
+    }
+    if (dfdub != 0.0) h = fmin(h, 1.0 / dfdub);
+    h = fmax(h, 100.0 * small * fabs(a));
+    if (h == 0.0) h = small * fabs(b);
+    return fabs(h);
+}
+
+// ---- one trajectory ---------------------------------------------------------
+template <class Tab, class R>
+struct Lane {
+    static constexpr int S = Tab::S;
+    static constexpr int NL = R::NL;
+    // rows of K: S+1, plus BS5's extra stages for the low/best interpolants
+    static constexpr int KROWS = (Tab::VARIANT == tab::BS5V) ? S + 4 : S + 1;
+
+    long long sys;          // trajectory index
+    double t, h_abs, h_prev, err_old, max_factor, min_step;
+    double y[NL], f[NL], prm[R::NPL];
+    int n_acc, n_rej, nfev, ieval, attempts;
+    bool standard_sc, fresh, step_rejected;
+
+    // RungeKutta.__init__, common.py:187-220
+    __device__ __forceinline__ void init(const RkDev& P, long long idx,
+                                         int lane) {
+        sys = idx;
+        t = P.t0;
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+        R::load_params(P.params, idx, P.n_lanes, lane, prm);
+        n_acc = n_rej = ieval = attempts = 0;
+        nfev = 1;
+        R::f(t, y, prm, f);
+        standard_sc = true;
+        fresh = true;
+        step_rejected = false;
+        max_factor = kMaxFactor0;
+        h_prev = 0.0;
+        err_old = 0.0;
+        min_step = 0.0;
+        if (P.n_forced > 0) {
+            h_abs = P.h_forced[0];
+        } else if (P.first_step > 0.0) {
+            h_abs = P.first_step;
+        } else {
+            const double b = P.t0 + P.direction *
+                fmin(fabs(P.t_bound - P.t0), P.max_step);
+            h_abs = h_start_dev<R>(P, P.t0, b, y, f, prm, Tab::ORDER2, lane,
+                                   nfev);
+        }
+    }
+
+    // _reassess_stepsize, common.py:310-331
+    __device__ __forceinline__ void reassess(const RkDev& P) {
+        min_step = fmax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+        if (h_abs < min_step || h_abs > P.max_step) {
+            h_abs = fmin(P.max_step, fmax(min_step, h_abs));
+            standard_sc = true;
+        }
+        const double d = fabs(P.t_bound - t);
+        if (d < 2.0 * h_abs) {
+            if (d > h_abs) {
+                h_abs = fmax(0.5 * d, min_step);
+                standard_sc = true;
+            } else {
+                h_abs = d;
+            }
+        }
+    }
+
+    // K_i = f(t + c_i h, y + h * sum_j a_ij K_j), common.py:353-356
+    template <int I>
+    __device__ __forceinline__ void stage(double (&K)[KROWS][NL], double h) {
+        double ys[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < I; ++j) {
+                const double a = Tab::a(I, j);
+                if (a != 0.0) {
+                    acc = first ? a * K[j][c] : fma(a, K[j][c], acc);
+                    first = false;
+                }
+            }
+            ys[c] = fma(h, acc, y[c]);
+        }
+        R::f(__dadd_rn(t, __dmul_rn(Tab::c(I), h)), ys, prm, K[I]);
+    }
+    template <int I, int END>
+    __device__ __forceinline__ void stages(double (&K)[KROWS][NL], double h) {
+        if constexpr (I < END) {
+            stage<I>(K, h);
+            stages<I + 1, END>(K, h);
+        }
+    }
+
+    // err_norm of  h * sum_i w_i K_i  against scale(y, y_ref)
+    __device__ __forceinline__ double scaled_norm(
+        const RkDev& P, const double (&errv)[NL], const double (&yref)[NL],
+        int lane) {
+        double q[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            const double scale = fma(P.rtol, fmax(fabs(y[c]), fabs(yref[c])),
+                                     atol_of<R>(P, c, lane));
+            q[c] = errv[c] / scale;
+        }
+        return rms<R>(q);
+    }
+
+    // rejection update shared by all branches, common.py:278-284
+    __device__ __forceinline__ void shrink(const RkDev& P, double err) {
+        step_rejected = true;
+        h_abs *= fmax(kMinFactor, P.safety * pow(err, P.err_exp));
+        ++n_rej;
+    }
+
+    // Dense output over the step just accepted: emit every t_eval point in
+    // (t_old, t_new] (ivp.py:711-728).  K holds all stages of the step.
+    __device__ void emit(const RkDev& P, double (&K)[KROWS][NL], double h,
+                         double t_new, const double (&y_new)[NL], int lane) {
+        if (ieval >= P.n_eval) return;
+        if (P.direction * (P.t_eval[ieval] - t_new) > 0.0) return;
+        if constexpr (Tab::NPOL == 0) emit_cubic(P, K, t_new, y_new, lane);
+        else emit_poly(P, K, h, t_new, y_new, lane);
+    }
+
+    // CubicDenseOutput, common.py:793-821 (tableaux without P)
+    __device__ void emit_cubic(const RkDev& P, double (&K)[KROWS][NL],
+                               double t_new, const double (&y_new)[NL],
+                               int lane) {
+        const double hh = t_new - t;
+        double te = P.t_eval[ieval];
+        do {
+            const double x = (te - t) / hh;
+            const double omx = 1.0 - x;
+            const double h00 = (1.0 + 2.0 * x) * (omx * omx);
+            const double h10 = x * (omx * omx) * hh;
+            const double h01 = (x * x) * (3.0 - 2.0 * x);
+            const double h11 = (x * x) * (x - 1.0) * hh;
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                const long long row = sys * (long long)R::N + R::comp(c, lane);
+                P.y_eval[row * P.n_eval + ieval] =
+                    ((h00 * y[c] + h10 * K[0][c]) + h01 * y_new[c]) +
+                    h11 * K[S][c];
+            }
+            ++ieval;
+            if (ieval >= P.n_eval) break;
+            te = P.t_eval[ieval];
+        } while (P.direction * (te - t_new) <= 0.0);
+    }
+
+    __device__ void emit_poly(const RkDev& P, double (&K)[KROWS][NL], double h,
+                              double t_new, const double (&y_new)[NL],
+                              int lane) {
+        double te = P.t_eval[ieval];
+        constexpr int NQ = (Tab::VARIANT == tab::BS5V) ? 6
+                         : (Tab::NPOL > 0 ? Tab::NPOL : 1);
+        double Q[NQ][NL];
+        int npol = Tab::NPOL;
+        double t_anchor = t, h_anchor = t_new - t;
+        bool anchor_end = false;
+        if constexpr (Tab::VARIANT == tab::BS5V) {
+            if (P.interpolant == IP_FREE) {
+                form_q_free(K, Q);
+            } else if (P.interpolant == IP_LOW) {
+                bs5_low(K, Q, h);
+                npol = Tab::NPOL_LOW;
+            } else {
+                bs5_best(K, Q, h, y_new);
+                npol = Tab::NPOL_BEST;
+                anchor_end = true;
+                t_anchor = t_new;
+                h_anchor = (t_new + h) - t_new;
+            }
+        } else {
+            form_q_free(K, Q);
+        }
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) Q[k][c] *= h_anchor;
+        do {
+            const double x = (te - t_anchor) / h_anchor;
+            double out[NL];
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double v = 0.0;
+                // Horner, common.py:781-785: y = Q[-1]*x; (y += q; y *= x)...
+#pragma unroll
+                for (int k = NQ - 1; k >= 0; --k) {
+                    if (k < npol) {
+                        v = (k == npol - 1) ? Q[k][c] * x : (v + Q[k][c]) * x;
+                    }
+                }
+                out[c] = v + (anchor_end ? y_new[c] : y[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                const long long row = sys * (long long)R::N + R::comp(c, lane);
+                P.y_eval[row * P.n_eval + ieval] = out[c];
+            }
+            ++ieval;
+            if (ieval >= P.n_eval) break;
+            te = P.t_eval[ieval];
+        } while (P.direction * (te - t_new) <= 0.0);
+    }
+
+    // Q = K.T @ P, common.py:363
+    template <int NQ>
+    __device__ __forceinline__ void form_q_free(double (&K)[KROWS][NL],
+                                                double (&Q)[NQ][NL]) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double acc = 0.0;
+                if (k < Tab::NPOL) {
+#pragma unroll
+                    for (int i = 0; i <= S; ++i) {
+                        const double p = Tab::p(i, k);
+                        if (p != 0.0) acc = fma(p, K[i][c], acc);
+                    }
+                }
+                Q[k][c] = acc;
+            }
+        }
+    }
+
+    // BS5 extra stage r (row S+1+R_), bogacki.py:356-361, 366-369
+    template <int R_>
+    __device__ __forceinline__ void bs5_extra_stage(double (&K)[KROWS][NL],
+                                                    double h) {
+        if constexpr (Tab::VARIANT == tab::BS5V) {
+            constexpr int ROW = S + 1 + R_;
+            double ys[NL];
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < ROW; ++j) {
+                    const double a = Tab::a_extra(R_, j);
+                    if (a != 0.0) acc = fma(a, K[j][c], acc);
+                }
+                ys[c] = fma(acc, h, y[c]);
+            }
+            R::f(__dadd_rn(t, __dmul_rn(Tab::c_extra(R_), h)), ys, prm,
+                 K[ROW]);
+            ++nfev;
+        }
+    }
+    template <int NQ>
+    __device__ void bs5_low(double (&K)[KROWS][NL], double (&Q)[NQ][NL],
+                            double h) {
+        if constexpr (Tab::VARIANT == tab::BS5V) {
+            bs5_extra_stage<0>(K, h);
+#pragma unroll
+            for (int k = 0; k < NQ; ++k)
+#pragma unroll
+                for (int c = 0; c < NL; ++c) {
+                    double acc = 0.0;
+                    if (k < Tab::NPOL_LOW) {
+#pragma unroll
+                        for (int i = 0; i <= S + 1; ++i) {
+                            const double p = Tab::plow(i, k);
+                            if (p != 0.0) acc = fma(p, K[i][c], acc);
+                        }
+                    }
+                    Q[k][c] = acc;
+                }
+        }
+    }
+    // RKSuite's grouped summation, bogacki.py:372-388
+    template <int NQ>
+    __device__ void bs5_best(double (&K)[KROWS][NL], double (&Q)[NQ][NL],
+                             double h, const double (&y_new)[NL]) {
+        if constexpr (Tab::VARIANT == tab::BS5V) {
+            bs5_extra_stage<0>(K, h);
+            bs5_extra_stage<1>(K, h);
+            bs5_extra_stage<2>(K, h);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double kp[11];
+                Q[0][c] = K[7][c];
+#define XSQ_KP(col)                                                      \
+    _Pragma("unroll") for (int i = 0; i < 11; ++i)                       \
+        kp[i] = __dmul_rn(K[i][c], Tab::pbest(i, col));
+#define A2(a, b) __dadd_rn(a, b)
+                XSQ_KP(1)
+                Q[1][c] = A2(A2(A2(kp[4], A2(A2(kp[5], kp[7]), kp[0])),
+                                A2(A2(kp[2], kp[8]), kp[9])),
+                             A2(A2(kp[3], kp[10]), kp[6]));
+                XSQ_KP(2)
+                Q[2][c] = A2(A2(A2(kp[4], kp[5]),
+                                A2(A2(A2(kp[2], kp[8]), A2(kp[9], kp[7])),
+                                   kp[0])),
+                             A2(A2(kp[3], kp[10]), kp[6]));
+                XSQ_KP(3)
+                Q[3][c] = A2(A2(A2(A2(kp[3], kp[7]), A2(kp[6], kp[5])), kp[4]),
+                             A2(A2(A2(kp[9], kp[8]), A2(kp[2], kp[10])),
+                                kp[0]));
+                XSQ_KP(4)
+                Q[4][c] = A2(A2(A2(kp[9], kp[8]), A2(A2(kp[6], kp[5]), kp[4])),
+                             A2(A2(A2(kp[3], kp[7]), A2(kp[2], kp[10])),
+                                kp[0]));
+                XSQ_KP(5)
+                Q[5][c] = A2(A2(kp[4], A2(A2(kp[9], kp[7]), A2(kp[6], kp[5]))),
+                             A2(A2(A2(kp[3], kp[8]), A2(kp[2], kp[10])),
+                                kp[0]));
+#undef A2
+#undef XSQ_KP
+            }
+        }
+    }
+
+    // One ATTEMPT of a step (the body of `while not step_accepted`,
+    // common.py:232-287).  Returns the lane status: LANE_RUNNING, or a final
+    // code when the trajectory ends here.
+    __device__ __forceinline__ int attempt(const RkDev& P, int lane) {
+        const bool forced = P.n_forced > 0;
+        if (forced) {
+            h_abs = P.h_forced[n_acc];
+        } else {
+            if (fresh) {
+                reassess(P);
+                step_rejected = false;
+                fresh = false;
+            }
+            if (h_abs < min_step) return LANE_TOO_SMALL;
+            if (attempts >= P.max_steps) return LANE_STEP_BUDGET;
+        }
+        ++attempts;
+        const double h = h_abs * P.direction;
+        const double t_new = t + h;
+        double K[KROWS][NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) K[0][c] = f[c];
+
+        constexpr bool EARLY = Tab::VARIANT != tab::GENERIC;
+        constexpr int NFIRST = EARLY ? S - 1 : S;
+        stages<1, NFIRST>(K, h);
+        nfev += NFIRST - 1;
+
+        if constexpr (EARLY) {
+            // pre-error from the first S-1 stages: bogacki.py:340-346 uses
+            // (B_scale_pre, E_pre), calvo.py:255-261 uses (A[8,:8], E[:8])
+            double ypre[NL], errv[NL];
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double sb = 0.0, se = 0.0;
+#pragma unroll
+                for (int i = 0; i < S - 1; ++i) {
+                    double wb, we;
+                    if constexpr (Tab::VARIANT == tab::BS5V) {
+                        wb = Tab::b_scale_pre(i);
+                        we = Tab::e_pre(i);
+                    } else {
+                        wb = Tab::a(S - 1, i);
+                        we = Tab::e(i);
+                    }
+                    if (wb != 0.0) sb = fma(wb, K[i][c], sb);
+                    if (we != 0.0) se = fma(we, K[i][c], se);
+                }
+                ypre[c] = fma(h, sb, y[c]);
+                errv[c] = h * se;
+            }
+            const double err_pre = scaled_norm(P, errv, ypre, lane);
+            if (!forced && err_pre > 1.0) {
+                shrink(P, err_pre);
+                return LANE_RUNNING;
+            }
+            stage<S - 1>(K, h);
+            ++nfev;
+        }
+
+        // _comp_sol_err, common.py:341-351
+        double y_new[NL], errv[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double sb = 0.0;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const double b = Tab::b(i);
+                if (b != 0.0) sb = fma(b, K[i][c], sb);
+            }
+            y_new[c] = fma(h, sb, y[c]);
+        }
+        if constexpr (Tab::FSAL) {
+            R::f(t_new, y_new, prm, K[S]);
+            ++nfev;
+        }
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double se = 0.0;
+#pragma unroll
+            for (int i = 0; i < S + Tab::FSAL; ++i) {
+                const double e = Tab::e(i);
+                if (e != 0.0) se = fma(e, K[i][c], se);
+            }
+            errv[c] = h * se;
+        }
+        const double err = scaled_norm(P, errv, y_new, lane);
+
+        if (!forced) {
+            if (err < 1.0) {                    // common.py:249-276
+                double factor;
+                if (err < XSQ_SQRT_TINY) {
+                    factor = max_factor;
+                    standard_sc = true;
+                } else if (standard_sc) {
+                    factor = P.safety * pow(err, P.err_exp);
+                    standard_sc = false;
+                } else {
+                    const double h_ratio = h / h_prev;
+                    double fac = pow(err, P.minbeta1);
+                    if (P.minbeta2 != 0.0) fac *= pow(err_old, P.minbeta2);
+                    if (P.minalpha != 0.0) fac *= pow(h_ratio, P.minalpha);
+                    factor = P.safety_sc * fac;
+                    factor = fmin(max_factor, fmax(kMinFactor, factor));
+                }
+                if (step_rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                if (factor < kMaxFactor) max_factor = kMaxFactor;
+            } else {
+                const bool bad = isnan(err) || isinf(err);
+                if (Tab::VARIANT == tab::BS5V && bad)    // bogacki.py:314-315
+                    return LANE_OVERFLOW;
+                shrink(P, err);
+                return bad ? LANE_OVERFLOW : LANE_RUNNING;   // common.py:286
+            }
+        }
+        if constexpr (!Tab::FSAL) {             // common.py:289-291
+            R::f(t_new, y_new, prm, K[S]);
+            ++nfev;
+        }
+        if (P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
+        // common.py:294-303
+        h_prev = h;
+        err_old = err;
+        t = t_new;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
+        ++n_acc;
+        fresh = true;
+        if (forced) return n_acc >= P.n_forced ? LANE_FINISHED : LANE_RUNNING;
+        // OdeSolver.step, base.py:207-208
+        return (P.direction * (t - P.t_bound) >= 0.0) ? LANE_FINISHED
+                                                      : LANE_RUNNING;
+    }
+
+    // `constant`: zero-length span, every t_eval point equals t0 and scipy
+    // returns y0 there (ConstantDenseOutput, base.py:224-226).
+    __device__ __forceinline__ void store(const RkDev& P, int st, int lane,
+                                          bool constant = false) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            P.y_final[(long long)R::comp(k, lane) * P.n_lanes + sys] = y[k];
+        if (P.n_eval > 0 && ieval < P.n_eval) {
+            // failed lane: the reference returns only the points reached;
+            // the rest of the lane's y_eval row is NaN
+            for (int i = ieval; i < P.n_eval; ++i)
+#pragma unroll
+                for (int c = 0; c < NL; ++c) {
+                    const long long row =
+                        sys * (long long)R::N + R::comp(c, lane);
+                    P.y_eval[row * P.n_eval + i] = constant ? y[c] : XSQ_NAN;
+                }
+            if (constant) ieval = P.n_eval;
+        }
+        if (!R::WARP || lane == 0) {
+            P.t_final[sys] = t;
+            if (P.h_next) P.h_next[sys] = h_abs;
+            P.n_acc[sys] = n_acc;
+            P.n_rej[sys] = n_rej;
+            P.nfev[sys] = nfev;
+            P.status[sys] = st;
+            if (P.n_eval_done) P.n_eval_done[sys] = ieval;
+        }
+    }
+};
+
+// ---- the persistent kernel ---------------------------------------------------
+// Lane-per-system: every thread owns one trajectory; when it ends the thread
+// stores it and claims the next index from the global queue (warp-aggregated
+// atomicAdd), so divergence in step counts does not idle the warp.
+// Warp-per-system: the claim is made once per warp and broadcast.
+template <class Tab, class R>
+__device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    Lane<Tab, R> L;
+    bool live = false;
+    bool exhausted = false;
+    for (;;) {
+        // ---- refill ----
+        if (R::WARP) {
+            if (!live && !exhausted) {
+                unsigned long long idx = 0;
+                if (lane == 0) idx = atomicAdd(P.queue, 1ULL);
+                idx = __shfl_sync(full, idx, 0);
+                if ((long long)idx < P.n_lanes) {
+                    L.init(P, (long long)idx, lane);
+                    live = true;
+                    if (P.n_forced == 0 && P.t0 == P.t_bound) {
+                        L.store(P, LANE_FINISHED, lane, true);
+                        live = false;
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        } else {
+            const unsigned need = __ballot_sync(full, !live && !exhausted);
+            if (need) {
+                unsigned long long base = 0;
+                const int leader = __ffs(need) - 1;
+                if (lane == leader)
+                    base = atomicAdd(P.queue, (unsigned long long)__popc(need));
+                base = __shfl_sync(full, base, leader);
+                if (!live && !exhausted) {
+                    const long long idx =
+                        (long long)base + __popc(need & ((1u << lane) - 1u));
+                    if (idx < P.n_lanes) {
+                        L.init(P, idx, lane);
+                        live = true;
+                        // t0 == t_bound / zero-length span: scipy base.py:197
+                        if (P.n_forced == 0 && P.t0 == P.t_bound) {
+                            L.store(P, LANE_FINISHED, lane, true);
+                            live = false;
+                        }
+                    } else {
+                        exhausted = true;
+                    }
+                }
+            }
+            __syncwarp(full);
+        }
+        if (__all_sync(full, !live)) break;
+        // ---- one attempt ----
+        if (live) {
+            const int st = L.attempt(P, lane);
+            if (st != LANE_RUNNING) {
+                L.store(P, st, lane);
+                live = false;
+            }
+        }
+        __syncwarp(full);
+    }
+}
+
+template <class Tab, class R, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) rk_persistent(const RkDev P) {
+    rk_persistent_body<Tab, R>(P);
+}
+
+}  // namespace xsq

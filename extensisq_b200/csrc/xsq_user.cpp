@@ -1,0 +1,439 @@
+// xsq_user.cpp -- user right-hand sides and user tableaux.
+//
+// The reference takes any Python callable as `fun` (extensisq/common.py:187)
+// and any subclass of RungeKutta with its own A/B/C/E/P as `method`
+// (common.py:88-121, docs/Demo_own_RK.ipynb).  On the device both must be
+// compile-time constants of the persistent kernel (a function-pointer call per
+// stage would serialise the fp64 pipe), so they are compiled at run time:
+// the solver headers are embedded in the library (tools/embed.py), the user's
+// CUDA source / tableau image is appended, and NVRTC produces a cubin for
+// sm_100a that is loaded through the driver API.
+//
+// libnvrtc and libcuda are dlopen'ed lazily so that libxsq.so itself loads on
+// a machine without a driver (the CPU-side ABI tests).
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "xsq.h"
+#include "xsq_user.h"
+
+namespace xsq {
+
+extern const int kNumEmbedded;
+extern const char* const kEmbeddedNames[];
+extern const char* const kEmbeddedSources[];
+
+namespace {
+
+std::mutex g_mu;
+
+struct UserRhs {
+    std::string src, entry;
+    int n_state, n_param;
+};
+std::vector<UserRhs> g_rhs;               // handle = XSQ_RHS_USER_BASE + index
+
+struct UserTab {
+    bool loaded = false;
+    int generation = 0;
+    xsq_tableau_t t;
+    std::string src;
+} g_tab;
+
+struct Compiled {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    int occ = 0;
+};
+std::map<std::string, Compiled> g_cache;
+
+// ---- lazily bound driver / NVRTC entry points ------------------------------
+struct Api {
+    void* nvrtc = nullptr;
+    void* cuda = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int,
+                                 const char* const*, const char* const*);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+    const char* (*GetErrorString)(nvrtcResult);
+    CUresult (*ModuleLoadData)(CUmodule*, const void*);
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, unsigned, unsigned, CUstream, void**,
+                             void**);
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t);
+    CUresult (*CuGetErrorString)(CUresult, const char**);
+} g_api;
+
+template <class F>
+bool bind(void* lib, const char* name, F* out) {
+    *out = reinterpret_cast<F>(dlsym(lib, name));
+    return *out != nullptr;
+}
+
+bool load_nvrtc() {
+    if (g_api.nvrtc) return true;
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "libnvrtc.so"};
+    for (const char* n : names) {
+        g_api.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_api.nvrtc) break;
+    }
+    if (!g_api.nvrtc) { set_detail("cannot dlopen libnvrtc.so.12"); return false; }
+    void* l = g_api.nvrtc;
+    bool ok = bind(l, "nvrtcCreateProgram", &g_api.CreateProgram) &&
+              bind(l, "nvrtcCompileProgram", &g_api.CompileProgram) &&
+              bind(l, "nvrtcGetCUBINSize", &g_api.GetCUBINSize) &&
+              bind(l, "nvrtcGetCUBIN", &g_api.GetCUBIN) &&
+              bind(l, "nvrtcGetProgramLogSize", &g_api.GetProgramLogSize) &&
+              bind(l, "nvrtcGetProgramLog", &g_api.GetProgramLog) &&
+              bind(l, "nvrtcDestroyProgram", &g_api.DestroyProgram) &&
+              bind(l, "nvrtcGetErrorString", &g_api.GetErrorString);
+    if (!ok) set_detail("libnvrtc is missing a required symbol");
+    return ok;
+}
+
+bool load_cuda() {
+    if (g_api.cuda) return true;
+    g_api.cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!g_api.cuda) { set_detail("cannot dlopen libcuda.so.1 (no driver)"); return false; }
+    void* l = g_api.cuda;
+    bool ok = bind(l, "cuModuleLoadData", &g_api.ModuleLoadData) &&
+              bind(l, "cuModuleGetFunction", &g_api.ModuleGetFunction) &&
+              bind(l, "cuLaunchKernel", &g_api.LaunchKernel) &&
+              bind(l, "cuOccupancyMaxActiveBlocksPerMultiprocessor",
+                   &g_api.OccupancyMaxActiveBlocks) &&
+              bind(l, "cuGetErrorString", &g_api.CuGetErrorString);
+    if (!ok) set_detail("libcuda is missing a required symbol");
+    return ok;
+}
+
+const char* builtin_tab_name(int method) {
+    switch (method) {
+        case XSQ_TS5: return "Ts5";
+        case XSQ_BS5: return "BS5";
+        case XSQ_CK5: return "CK5";
+        case XSQ_ME4: return "Me4";
+        case XSQ_PR7: return "Pr7";
+        case XSQ_PR8: return "Pr8";
+        case XSQ_PR9: return "Pr9";
+        case XSQ_CFMR7OSC: return "CFMR7osc";
+        default: return nullptr;
+    }
+}
+const char* builtin_rhs_name(int rhs) {
+    switch (rhs) {
+        case XSQ_RHS_LORENZ63: return "Lorenz63";
+        case XSQ_RHS_VANDERPOL: return "VanDerPol";
+        case XSQ_RHS_ARENSTORF: return "Arenstorf";
+        case XSQ_RHS_NBODY32: return "NBody32";
+        default: return nullptr;
+    }
+}
+
+void append_table(std::string* s, const char* fn, const char* args,
+                  const std::string& idx, const std::vector<double>& v) {
+    char buf[64];
+    *s += "    XSQ_HD static constexpr double ";
+    *s += fn;
+    *s += "(";
+    *s += args;
+    *s += ") {\n        constexpr double T[" + std::to_string(v.size() ? v.size() : 1) + "] = {";
+    for (size_t i = 0; i < v.size(); ++i) {
+        std::snprintf(buf, sizeof buf, "%a, ", v[i]);
+        *s += buf;
+    }
+    if (v.empty()) *s += "0.0";
+    *s += "};\n        return T[" + idx + "];\n    }\n";
+}
+
+// the same struct layout tools/gen_header.py emits for the built-ins
+std::string tableau_source(const xsq_tableau_t& t) {
+    const int s = t.n_stages;
+    std::string o = "namespace xsq { namespace tab {\nstruct UserTab {\n";
+    double cdiff = 1.0;                               // common.py:129-137
+    for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) {
+            double d = t.C[i] - t.C[j];
+            if (d < 0) d = -d;
+            if (d != 0.0 && d < cdiff) cdiff = d;
+        }
+    if (cdiff < 1e-3) cdiff = 1e-3;
+    char buf[256];
+    std::snprintf(buf, sizeof buf,
+                  "    static constexpr int ID = 100, S = %d, ORDER = %d, "
+                  "ORDER2 = %d, FSAL = %d, NPOL = %d, VARIANT = GENERIC;\n"
+                  "    static constexpr double H_MIN_A = %a;\n",
+                  s, t.order, t.order_secondary, t.E[s] != 0.0 ? 1 : 0,
+                  t.n_poly, 10 * 0x1.0p-53 / cdiff);
+    o += buf;
+    std::snprintf(buf, sizeof buf,
+                  "    static constexpr double SC_KB1 = %a, SC_KB2 = %a, "
+                  "SC_A = %a, SC_G = %a;\n",
+                  t.sc_params[0], t.sc_params[1], t.sc_params[2],
+                  t.sc_params[3]);
+    o += buf;
+    std::vector<double> v;
+    for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) v.push_back(t.A[i][j]);
+    append_table(&o, "a", "int i, int j", "i * " + std::to_string(s) + " + j", v);
+    v.assign(t.B, t.B + s);
+    append_table(&o, "b", "int i", "i", v);
+    v.assign(t.C, t.C + s);
+    append_table(&o, "c", "int i", "i", v);
+    v.assign(t.E, t.E + s + 1);
+    append_table(&o, "e", "int i", "i", v);
+    v.clear();
+    for (int i = 0; i <= s; ++i)
+        for (int k = 0; k < t.n_poly; ++k) v.push_back(t.P[i][k]);
+    append_table(&o, "p", "int i, int k",
+                 "i * " + std::to_string(t.n_poly > 0 ? t.n_poly : 1) + " + k", v);
+    o += "};\n} }\n";
+    return o;
+}
+
+std::string rhs_wrapper(const UserRhs& r) {
+    char buf[1024];
+    std::snprintf(
+        buf, sizeof buf,
+        "namespace xsq { namespace rhs {\nstruct User {\n"
+        "    static constexpr int N = %d, NL = %d, NPAR = %d, NPL = %d;\n"
+        "    static constexpr bool WARP = false;\n"
+        "    static constexpr int FLOPS = 0;\n"
+        "    __device__ __forceinline__ static int comp(int k, int) { return k; }\n"
+        "    __device__ __forceinline__ static void load_params(\n"
+        "        const double* __restrict__ params, long long sys, long long n_lanes,\n"
+        "        int, double (&p)[NPL]) {\n"
+        "#pragma unroll\n"
+        "        for (int k = 0; k < NPAR; ++k) p[k] = params[k * n_lanes + sys];\n"
+        "    }\n"
+        "    __device__ __forceinline__ static void f(double t, const double (&y)[NL],\n"
+        "        const double (&p)[NPL], double (&dy)[NL]) { ::%s(t, y, p, dy); }\n"
+        "};\n} }\n",
+        r.n_state, r.n_state, r.n_param, r.n_param > 0 ? r.n_param : 1,
+        r.entry.c_str());
+    return buf;
+}
+
+int minb_for(int s, int nl) {
+    const int kd = (s + 1) * nl;
+    return kd <= 21 ? 4 : (kd <= 36 ? 3 : 2);
+}
+
+int compile(const std::string& key, const std::string& src, Compiled* out) {
+    if (!load_nvrtc()) return XSQ_ERR_NVRTC;
+    nvrtcProgram prog;
+    nvrtcResult r = g_api.CreateProgram(&prog, src.c_str(), "xsq_user.cu",
+                                        kNumEmbedded, kEmbeddedSources,
+                                        kEmbeddedNames);
+    if (r != NVRTC_SUCCESS) { set_detail(g_api.GetErrorString(r)); return XSQ_ERR_NVRTC; }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
+                          "-lineinfo", "-default-device"};
+    r = g_api.CompileProgram(prog, 3, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_api.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_api.GetProgramLog(prog, &log[0]);
+        set_detail(std::string("NVRTC: ") + g_api.GetErrorString(r) + "\n" + log);
+        g_api.DestroyProgram(&prog);
+        return XSQ_ERR_NVRTC;
+    }
+    size_t n = 0;
+    g_api.GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    g_api.GetCUBIN(prog, cubin.data());
+    g_api.DestroyProgram(&prog);
+    if (!load_cuda()) return XSQ_ERR_CUDA;
+    cudaFree(0);                           // make the primary context current
+    CUresult cr = g_api.ModuleLoadData(&out->mod, cubin.data());
+    if (cr == CUDA_SUCCESS)
+        cr = g_api.ModuleGetFunction(&out->fn, out->mod, "xsq_user_kernel");
+    if (cr == CUDA_SUCCESS)
+        cr = g_api.OccupancyMaxActiveBlocks(&out->occ, out->fn, 128, 0);
+    if (cr != CUDA_SUCCESS) {
+        const char* es = nullptr;
+        g_api.CuGetErrorString(cr, &es);
+        set_detail(std::string("driver: ") + (es ? es : "?"));
+        return XSQ_ERR_CUDA;
+    }
+    (void)key;
+    return XSQ_OK;
+}
+
+}  // namespace
+
+// Build the translation unit for (method, rhs); exposed for the CPU-side test
+// that NVRTC accepts it (no device needed to compile).
+int user_build_source(int method, int rhs, std::string* src, std::string* key) {
+    std::string tabname, rhsname, body = "#include \"xsq_rk_core.cuh\"\n";
+    int s = 0, nl = 0;
+    if (method == XSQ_METHOD_USER) {
+        if (!g_tab.loaded) { set_detail("no user tableau loaded"); return XSQ_ERR_ARG; }
+        body += g_tab.src;
+        tabname = "UserTab";
+        s = g_tab.t.n_stages;
+        *key = "T" + std::to_string(g_tab.generation);
+    } else {
+        const char* n = builtin_tab_name(method);
+        if (!n) return XSQ_ERR_ARG;
+        tabname = n;
+        MethodInfo mi;
+        (void)mi;
+        *key = n;
+        s = 17;  // conservative default; refined below for built-ins
+        static const int ks[] = {6, 7, 6, 5, 10, 13, 17, 9};
+        s = ks[method];
+    }
+    if (rhs >= XSQ_RHS_USER_BASE) {
+        const size_t i = (size_t)(rhs - XSQ_RHS_USER_BASE);
+        if (i >= g_rhs.size()) { set_detail("unknown rhs handle"); return XSQ_ERR_ARG; }
+        body += g_rhs[i].src + "\n" + rhs_wrapper(g_rhs[i]);
+        rhsname = "User";
+        nl = g_rhs[i].n_state;
+        *key += "/U" + std::to_string(i);
+    } else {
+        const char* n = builtin_rhs_name(rhs);
+        if (!n) return XSQ_ERR_ARG;
+        body += "#include \"xsq_rhs.cuh\"\n";
+        rhsname = n;
+        nl = 6;
+        *key += std::string("/") + n;
+    }
+    char buf[512];
+    std::snprintf(buf, sizeof buf,
+                  "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
+                  "xsq_user_kernel(const xsq::RkDev P) {\n"
+                  "    xsq::rk_persistent_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
+                  minb_for(s, nl), tabname.c_str(), rhsname.c_str());
+    *src = body + buf;
+    return XSQ_OK;
+}
+
+bool user_tableau_info(MethodInfo* mi) {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_tab.loaded) return false;
+    const xsq_tableau_t& t = g_tab.t;
+    *mi = MethodInfo{t.n_stages, t.order, t.order_secondary,
+                     t.E[t.n_stages] != 0.0 ? 1 : 0, t.n_poly,
+                     {t.sc_params[0], t.sc_params[1], t.sc_params[2],
+                      t.sc_params[3]}};
+    return true;
+}
+
+bool user_rhs_shape(int rhs, int* n_state, int* n_param) {
+    std::lock_guard<std::mutex> g(g_mu);
+    const size_t i = (size_t)(rhs - XSQ_RHS_USER_BASE);
+    if (rhs < XSQ_RHS_USER_BASE || i >= g_rhs.size()) return false;
+    *n_state = g_rhs[i].n_state;
+    *n_param = g_rhs[i].n_param;
+    return true;
+}
+
+int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
+    std::lock_guard<std::mutex> g(g_mu);
+    std::string src, key;
+    int rc = user_build_source(method, rhs, &src, &key);
+    if (rc != XSQ_OK) return rc;
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+        Compiled c;
+        rc = compile(key, src, &c);
+        if (rc != XSQ_OK) return rc;
+        it = g_cache.emplace(key, c).first;
+    }
+    const Compiled& c = it->second;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)n_sm * (c.occ > 0 ? c.occ : 1);
+    const long long want = (P.n_lanes + 127) / 128;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    RkDev Pc = P;
+    void* args[] = {&Pc};
+    CUresult cr = g_api.LaunchKernel(c.fn, (unsigned)grid, 1, 1, 128, 1, 1, 0,
+                                     (CUstream)st, args, nullptr);
+    count_launch();
+    if (cr != CUDA_SUCCESS) {
+        const char* es = nullptr;
+        g_api.CuGetErrorString(cr, &es);
+        set_detail(std::string("cuLaunchKernel: ") + (es ? es : "?"));
+        return XSQ_ERR_CUDA;
+    }
+    return XSQ_OK;
+}
+
+}  // namespace xsq
+
+using namespace xsq;
+
+extern "C" {
+
+int xsq_rhs_register_source(const char* cuda_src, const char* entry,
+                            int32_t n_state, int32_t n_param,
+                            int32_t* rhs_out) {
+    if (!cuda_src || !entry || !rhs_out || n_state < 1 ||
+        n_state > XSQ_MAX_LANE_STATE || n_param < 0) {
+        set_detail("xsq_rhs_register_source: bad argument (1 <= n_state <= 16)");
+        return XSQ_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    g_rhs.push_back(UserRhs{cuda_src, entry, n_state, n_param});
+    *rhs_out = XSQ_RHS_USER_BASE + (int)g_rhs.size() - 1;
+    return XSQ_OK;
+}
+
+int xsq_tableau_load(const xsq_tableau_t* tab) {
+    if (!tab || tab->n_stages < 1 || tab->n_stages > XSQ_MAX_STAGES - 1 ||
+        tab->n_poly < 0 || tab->n_poly > XSQ_MAX_POLY || tab->order < 1 ||
+        tab->order_secondary < 1) {
+        set_detail("xsq_tableau_load: bad tableau");
+        return XSQ_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    g_tab.t = *tab;
+    g_tab.src = tableau_source(*tab);
+    g_tab.loaded = true;
+    ++g_tab.generation;
+    return XSQ_OK;
+}
+
+/* Compile-only probe (no device needed): does NVRTC accept the translation
+ * unit for (method, rhs)?  Used by the CPU-side tests. */
+int xsq_user_compile_check(int32_t method, int32_t rhs) {
+    std::lock_guard<std::mutex> g(g_mu);
+    std::string src, key;
+    int rc = user_build_source(method, rhs, &src, &key);
+    if (rc != XSQ_OK) return rc;
+    if (!load_nvrtc()) return XSQ_ERR_NVRTC;
+    nvrtcProgram prog;
+    if (g_api.CreateProgram(&prog, src.c_str(), "xsq_user.cu", kNumEmbedded,
+                            kEmbeddedSources, kEmbeddedNames) != NVRTC_SUCCESS)
+        return XSQ_ERR_NVRTC;
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
+    nvrtcResult r = g_api.CompileProgram(prog, 2, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_api.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_api.GetProgramLog(prog, &log[0]);
+        set_detail(std::string("NVRTC: ") + g_api.GetErrorString(r) + "\n" + log);
+    }
+    g_api.DestroyProgram(&prog);
+    return r == NVRTC_SUCCESS ? XSQ_OK : XSQ_ERR_NVRTC;
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// Internal: runtime-specialised kernels (NVRTC) for user right-hand sides and
+// user tableaux.  See xsq_user.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "xsq_rk_core.cuh"
+
+namespace xsq {
+
+struct MethodInfo {
+    int s, order, order2, fsal, npol;
+    double sc[4];
+};
+
+void set_detail(const std::string& s);
+void count_launch();
+
+bool user_tableau_info(MethodInfo* mi);
+bool user_rhs_shape(int rhs, int* n_state, int* n_param);
+int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st);
+
+}  // namespace xsq

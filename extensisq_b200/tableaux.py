@@ -1,0 +1,116 @@
+"""Tableau classes with the reference's names and class attributes.
+
+Each class carries ``n_stages, order, order_secondary, A, B, C, E, P, stbrad,
+tanang, sc_params`` exactly as the reference's classes do
+(``extensisq/common.py:88-121``; data read from the reference at dev time by
+``tools/gen_tableaux.py`` and stored lossless in ``data/tableaux.json``).  They
+are passed as ``method=`` to :func:`extensisq_b200.solve_ivp_batched`, the way
+the reference's classes are passed to ``scipy.integrate.solve_ivp``
+(``README.md:26-35``).
+
+User-defined methods subclass :class:`RungeKutta` and define the same
+attributes (``docs/Demo_own_RK.ipynb``); they are uploaded to the device with
+``xsq_tableau_load`` and compiled into a specialised kernel on first use.
+"""
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_JSON = os.path.join(_HERE, "data", "tableaux.json")
+
+MIN_FACTOR = 0.2        # common.py:18
+MAX_FACTOR = 4.0        # common.py:19
+MAX_FACTOR0 = 10        # common.py:20
+
+
+def _unhex(a):
+    if isinstance(a[0], list):
+        return np.array([[float.fromhex(x) for x in r] for r in a])
+    return np.array([float.fromhex(x) for x in a])
+
+
+class RungeKutta:
+    """Base of all explicit tableau methods (reference: common.py:69-121).
+
+    Unlike the reference's class this is not a scipy ``OdeSolver``: the
+    stepping loop lives in the persistent CUDA kernel, so the class is the
+    method *description*; see :class:`extensisq_b200.batched.BatchedSolver`
+    for the object that holds device state."""
+    n_stages: int = NotImplemented
+    order: int = NotImplemented
+    order_secondary: int = NotImplemented
+    A: np.ndarray = NotImplemented
+    B: np.ndarray = NotImplemented
+    C: np.ndarray = NotImplemented
+    E: np.ndarray = NotImplemented
+    P: np.ndarray = NotImplemented
+    stbrad: float = NotImplemented
+    tanang: float = NotImplemented
+    sc_params = "standard"
+    max_factor = MAX_FACTOR0
+    min_factor = MIN_FACTOR
+    _xsq_method = None          # built-in id, None for user tableaux
+
+    @classmethod
+    def validate(cls):
+        """Shape checks a user tableau must satisfy (common.py:98-111)."""
+        s = cls.n_stages
+        if not isinstance(s, int) or s < 1:
+            raise ValueError("n_stages must be a positive int")
+        for name, shape in (("A", (s, s)), ("B", (s,)), ("C", (s,)),
+                            ("E", (s + 1,))):
+            a = getattr(cls, name)
+            if not isinstance(a, np.ndarray) or a.shape != shape:
+                raise ValueError(f"{cls.__name__}.{name} must have shape "
+                                 f"{shape}")
+        if isinstance(cls.P, np.ndarray) and cls.P.shape[0] != s + 1:
+            raise ValueError(f"{cls.__name__}.P must have {s + 1} rows")
+        if np.any(np.triu(cls.A) != 0):
+            raise ValueError("explicit methods need a strictly lower "
+                             "triangular A")
+
+
+def _make(name, d):
+    attrs = dict(
+        __doc__=f"{name} tableau; reference {d['source']}.",
+        n_stages=d["n_stages"], order=d["order"],
+        order_secondary=d["order_secondary"], sc_params=d["sc_params"],
+        stbrad=d["stbrad"], tanang=d["tanang"],
+        A=_unhex(d["A"]), B=_unhex(d["B"]), C=_unhex(d["C"]),
+        E=_unhex(d["E"]), P=_unhex(d["P"]),
+    )
+    for k in ("E_pre", "B_scale_pre", "C_extra", "A_extra", "Plow", "Pbest"):
+        if k in d:
+            attrs[k] = _unhex(d[k])
+    if "n_extra_stages" in d:
+        attrs["n_extra_stages"] = d["n_extra_stages"]
+    for v in attrs.values():
+        if isinstance(v, np.ndarray):
+            v.setflags(write=False)
+    return type(name, (RungeKutta,), attrs)
+
+
+with open(_JSON) as _fh:
+    _raw = json.load(_fh)
+REFERENCE_VERSION = _raw["reference_version"]
+_METHOD_IDS = {"Ts5": 0, "BS5": 1, "CK5": 2, "Me4": 3, "Pr7": 4, "Pr8": 5,
+               "Pr9": 6, "CFMR7osc": 7}
+
+Ts5 = _make("Ts5", _raw["tableaux"]["Ts5"])
+BS5 = _make("BS5", _raw["tableaux"]["BS5"])
+CK5 = _make("CK5", _raw["tableaux"]["CK5"])
+Me4 = _make("Me4", _raw["tableaux"]["Me4"])
+Pr7 = _make("Pr7", _raw["tableaux"]["Pr7"])
+Pr8 = _make("Pr8", _raw["tableaux"]["Pr8"])
+Pr9 = _make("Pr9", _raw["tableaux"]["Pr9"])
+CFMR7osc = _make("CFMR7osc", _raw["tableaux"]["CFMR7osc"])
+for _n, _c in (("Ts5", Ts5), ("BS5", BS5), ("CK5", CK5), ("Me4", Me4),
+               ("Pr7", Pr7), ("Pr8", Pr8), ("Pr9", Pr9),
+               ("CFMR7osc", CFMR7osc)):
+    _c._xsq_method = _METHOD_IDS[_n]
+del _raw, _fh, _n, _c
+
+BUILTIN = {c.__name__: c for c in (Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
+                                   CFMR7osc)}

@@ -1,0 +1,191 @@
+/*
+ * xsq.h -- C ABI of libxsq.so: the B200 (sm_100a) implementation of
+ * extensisq's explicit adaptive Runge-Kutta / SWAG / SSV2stab stepping path
+ * for ensembles of small ODE systems and for one large parabolic PDE.
+ *
+ * The reference (WRKampi/extensisq v0.6.0) is pure Python and has NO FFI; each
+ * entry point below names the reference interface it replaces (file:line in
+ * the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no C++ exceptions cross the boundary;
+ *   - every function returns XSQ_OK (0) or a negative xsq_err;
+ *   - the CALLER owns every buffer; the library borrows device pointers for
+ *     the duration of the call and allocates only its own scratch on the
+ *     given stream (freed before returning);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     unless the name ends in _host;
+ *   - per-lane outcome is reported in status[] with the xsq_lane_status codes,
+ *     mirroring the reference's in-band (False, message) -> status=-1.
+ */
+#ifndef XSQ_H
+#define XSQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XSQ_ABI_VERSION 1
+#define XSQ_MAX_STAGES 18      /* Pr9: n_stages=17, +1 row for f(t+h, y_new) */
+#define XSQ_MAX_POLY 8         /* Pr9 interpolant has 8 columns             */
+#define XSQ_MAX_LANE_STATE 16  /* lane-per-system kernels: n_state <= 16    */
+
+typedef enum xsq_err {
+    XSQ_OK = 0,
+    XSQ_ERR_ARG = -1,         /* bad argument (Python layer raises ValueError) */
+    XSQ_ERR_CUDA = -2,        /* CUDA runtime/driver error                   */
+    XSQ_ERR_NVRTC = -3,       /* user RHS failed to compile/link             */
+    XSQ_ERR_UNSUPPORTED = -4, /* combination not compiled into the library   */
+    XSQ_ERR_NOMEM = -5
+} xsq_err;
+
+/* per-lane status[] codes */
+typedef enum xsq_lane_status {
+    XSQ_LANE_FINISHED = 0,
+    XSQ_LANE_STEP_TOO_SMALL = -1, /* OdeSolver.TOO_SMALL_STEP, common.py:234   */
+    XSQ_LANE_OVERFLOW = -2,       /* "Overflow or underflow", common.py:286    */
+    XSQ_LANE_TOL_TOO_TIGHT = -3,  /* SWAG, shampine.py:235-238                 */
+    XSQ_LANE_SPRAD_FAILED = -4,   /* SSV2stab, sommeijer.py:179-182            */
+    XSQ_LANE_STEP_BUDGET = -5     /* max_steps exhausted (no reference analogue;
+                                     guards the GPU against runaway lanes)     */
+} xsq_lane_status;
+
+/* Built-in tableau methods: the reference's classes
+ * Ts5 (tsitouras.py:83), BS5 (bogacki.py:103), CK5 (cash.py:82),
+ * Me4 (merson.py:82), Pr7/Pr8/Pr9 (prince.py:79,205,449),
+ * CFMR7osc (calvo.py:89).  XSQ_METHOD_USER selects the tableau uploaded with
+ * xsq_tableau_load (user subclasses of common.RungeKutta, common.py:88-121). */
+typedef enum xsq_method {
+    XSQ_TS5 = 0, XSQ_BS5 = 1, XSQ_CK5 = 2, XSQ_ME4 = 3,
+    XSQ_PR7 = 4, XSQ_PR8 = 5, XSQ_PR9 = 6, XSQ_CFMR7OSC = 7,
+    XSQ_METHOD_USER = 100
+} xsq_method;
+
+/* Built-in right-hand sides (the reference takes a Python callable `fun`,
+ * common.py:187; on the device the RHS must be device code). Handles returned
+ * by xsq_rhs_register_source are >= XSQ_RHS_USER_BASE. */
+typedef enum xsq_rhs_id {
+    XSQ_RHS_LORENZ63 = 0,   /* n=3, p=(sigma, rho, beta)                     */
+    XSQ_RHS_VANDERPOL = 1,  /* n=2, p=(mu)                                   */
+    XSQ_RHS_ARENSTORF = 2,  /* n=4, p=(mu)                                   */
+    XSQ_RHS_NBODY32 = 3,    /* n=192 (32 bodies, 3-D), p=(eps2, m[32]); warp per system */
+    XSQ_RHS_USER_BASE = 1000
+} xsq_rhs_id;
+
+typedef enum xsq_interpolant {      /* BS5 only, bogacki.py:217-236 */
+    XSQ_INTERP_DEFAULT = 0, XSQ_INTERP_FREE = 1, XSQ_INTERP_LOW = 2,
+    XSQ_INTERP_BEST = 3
+} xsq_interpolant;
+
+/* POD image of a user tableau: the class attributes of a common.RungeKutta
+ * subclass (common.py:88-121).  P may be absent (n_poly = 0): the cubic
+ * Hermite fallback of common.py:793-821 is used. */
+typedef struct xsq_tableau {
+    int32_t n_stages, order, order_secondary, n_poly;
+    double A[XSQ_MAX_STAGES][XSQ_MAX_STAGES];
+    double B[XSQ_MAX_STAGES];
+    double C[XSQ_MAX_STAGES];
+    double E[XSQ_MAX_STAGES + 1];
+    double P[XSQ_MAX_STAGES + 1][XSQ_MAX_POLY];
+    double sc_params[4];            /* (kb1, kb2, a, g), common.py:166-185   */
+} xsq_tableau_t;
+
+/* Arguments of one batched explicit-RK solve: replaces
+ *   solve_ivp(fun, t_span, y0, method=Cls, t_eval=..., **options)
+ * (scipy ivp.py:161-760 driving RungeKutta.__init__/_step_impl/
+ * _dense_output_impl, common.py:187-368; BS5 bogacki.py:238-393; CFMR7osc
+ * calvo.py:152-261) for n_lanes independent trajectories.
+ * All array pointers are DEVICE pointers unless stated otherwise. */
+typedef struct xsq_rk_args {
+    int32_t struct_size;      /* sizeof(xsq_rk_args_t), ABI guard            */
+    int32_t method;           /* xsq_method                                  */
+    int32_t rhs;              /* xsq_rhs_id or registered handle             */
+    int32_t n_state;          /* n                                           */
+    int32_t n_param;          /* parameters per lane                         */
+    int32_t interpolant;      /* xsq_interpolant (BS5)                       */
+    int64_t n_lanes;          /* N trajectories                              */
+    const double* y0;         /* SoA [n_state][n_lanes]                      */
+    const double* params;     /* SoA [n_param][n_lanes], NULL if n_param==0  */
+    double t0, t_bound;       /* t_span                                      */
+    double rtol;              /* clipped like validate_tol, common.py:30-54  */
+    const double* atol;       /* HOST pointer, n_atol in {1, n_state}        */
+    int32_t n_atol;
+    int32_t use_sc_params;    /* 0: the method's default controller          */
+    double sc_params[4];      /* (kb1, kb2, a, g) if use_sc_params           */
+    double first_step;        /* <= 0: Watts' h_start, common.py:519-763     */
+    double max_step;          /* +inf for none                               */
+    const double* t_eval;     /* [n_eval] sorted along the direction, or NULL */
+    int32_t n_eval;
+    int32_t max_steps;        /* attempted-step budget per lane, <=0: 2^31-1 */
+    double* y_eval;           /* [n_lanes][n_state][n_eval]                  */
+    const double* h_forced;   /* forced |h| sequence [n_forced] or NULL      */
+    int32_t n_forced;
+    int32_t reserved0;
+    double* t_final;          /* [n_lanes]                                   */
+    double* y_final;          /* SoA [n_state][n_lanes]                      */
+    double* h_next;           /* [n_lanes] next |h| proposal, may be NULL    */
+    int32_t* n_accepted;      /* [n_lanes]                                   */
+    int32_t* n_rejected;      /* [n_lanes]  (the reference's NFS counter)    */
+    int32_t* nfev;            /* [n_lanes]                                   */
+    int32_t* status;          /* [n_lanes]  xsq_lane_status                  */
+    int32_t* n_eval_done;     /* [n_lanes] t_eval points written, may be NULL */
+} xsq_rk_args_t;
+
+int xsq_abi_version(void);
+const char* xsq_strerror(int err);
+/* text of the last NVRTC / CUDA failure on this thread ("" if none) */
+const char* xsq_last_error_detail(void);
+
+/* Number of SMs / device name probe; returns XSQ_ERR_CUDA if there is no
+ * usable device (the product has no CPU fallback). */
+int xsq_device_info(int device, int32_t* n_sm, int32_t* cc_major,
+                    int32_t* cc_minor);
+
+/* Upload a user tableau into the device's constant-memory slot.
+ * Replaces: subclassing common.RungeKutta with own A/B/C/E/P
+ * (common.py:88-121, docs/Demo_own_RK.ipynb). */
+int xsq_tableau_load(const xsq_tableau_t* tab);
+/* Read back the constant-memory image of a built-in method (for the
+ * order-condition checks of the reference's tests/test_rk.py:14-72). */
+int xsq_tableau_get(int32_t method, xsq_tableau_t* out);
+
+/* Look up a built-in RHS by name: "lorenz63", "vanderpol", "arenstorf",
+ * "nbody32".  Replaces the `fun` argument of common.py:187. */
+int xsq_rhs_builtin(const char* name, int32_t* rhs_out, int32_t* n_state,
+                    int32_t* n_param);
+/* Register CUDA source defining
+ *   __device__ void <entry>(double t, const double* y, const double* p,
+ *                           double* dy);
+ * It is compiled with NVRTC together with the solver template so the RHS
+ * inlines into the persistent kernel. */
+int xsq_rhs_register_source(const char* cuda_src, const char* entry,
+                            int32_t n_state, int32_t n_param,
+                            int32_t* rhs_out);
+
+/* Compile-only probe: does NVRTC accept the specialised kernel for
+ * (method, rhs)?  Needs libnvrtc but no device. */
+int xsq_user_compile_check(int32_t method, int32_t rhs);
+
+/* Batched adaptive explicit RK solve, device buffers, asynchronous. */
+int xsq_rk_solve(const xsq_rk_args_t* args, void* stream);
+/* Same, but EVERY array pointer in args is a HOST pointer; H2D/D2H copies and
+ * the solve happen inside the call, which returns when the results are in the
+ * host buffers. */
+int xsq_rk_solve_host(const xsq_rk_args_t* args, int device);
+
+/* Kernel-launch bookkeeping for benchmarks: number of kernels this library
+ * launched since the last reset. */
+int64_t xsq_launch_count(int reset);
+
+/* fp64 FMA peak microbenchmark (roofline denominator for the ensemble
+ * kernels): runs `iters` dependent-chain DFMA blocks on all SMs and returns
+ * the achieved TFLOP/s in *tflops. */
+int xsq_fp64_peak(int device, int32_t iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSQ_H */

@@ -1,0 +1,166 @@
+"""TEST INFRASTRUCTURE -- ctypes wrapper of ``oracle/libxsq_oracle.so`` (the
+plain-C restatement in ``oracle/xsq_oracle.c``).  Not part of the product."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import rk_oracle as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxsq_oracle.so")
+MAXS, MAXPOL = 18, 8
+
+RHS_IDS = {"lorenz63": 0, "vanderpol": 1, "arenstorf": 2, "nbody32": 3}
+RHS_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double),
+                     C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+class OTab(C.Structure):
+    _fields_ = [
+        ("s", C.c_int32), ("order", C.c_int32), ("order2", C.c_int32),
+        ("npol", C.c_int32), ("variant", C.c_int32), ("pad", C.c_int32),
+        ("A", (C.c_double * MAXS) * MAXS), ("B", C.c_double * MAXS),
+        ("C", C.c_double * MAXS), ("E", C.c_double * (MAXS + 1)),
+        ("P", (C.c_double * MAXPOL) * (MAXS + 1)),
+        ("E_pre", C.c_double * MAXS), ("B_scale_pre", C.c_double * MAXS),
+        ("C_extra", C.c_double * 3), ("A_extra", (C.c_double * MAXS) * 3),
+        ("Plow", (C.c_double * MAXPOL) * (MAXS + 2)),
+        ("Pbest", (C.c_double * MAXPOL) * (MAXS + 4)),
+        ("npol_low", C.c_int32), ("npol_best", C.c_int32),
+        ("sc", C.c_double * 4),
+    ]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} missing: run `make -C oracle`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.xsq_oracle_tab_size.restype = C.c_size_t
+        assert _lib.xsq_oracle_tab_size() == C.sizeof(OTab)
+    return _lib
+
+
+def max_threads():
+    return load().xsq_oracle_max_threads()
+
+
+def _fill2(dst, src):
+    src = np.asarray(src)
+    for i in range(src.shape[0]):
+        for j in range(src.shape[1]):
+            dst[i][j] = float(src[i, j])
+
+
+def make_tab(tab, sc_params=None):
+    """tab: oracle.rk_oracle.Tableau or any object with the reference's class
+    attributes (n_stages, order, order_secondary, A, B, C, E[, P])."""
+    t = OTab()
+    s = tab.n_stages
+    t.s, t.order, t.order2 = s, tab.order, tab.order_secondary
+    name = getattr(tab, "name", getattr(tab, "__name__", ""))
+    t.variant = {"BS5": 1, "CFMR7osc": 2}.get(name, 0)
+    _fill2(t.A, tab.A)
+    for i in range(s):
+        t.B[i] = float(tab.B[i])
+        t.C[i] = float(tab.C[i])
+    for i in range(s + 1):
+        t.E[i] = float(tab.E[i])
+    P = getattr(tab, "P", None)
+    if isinstance(P, np.ndarray):
+        t.npol = P.shape[1]
+        _fill2(t.P, P)
+    else:
+        t.npol = 0
+    if t.variant == 1:
+        for i in range(6):
+            t.E_pre[i] = float(tab.E_pre[i])
+            t.B_scale_pre[i] = float(tab.B_scale_pre[i])
+        for i in range(3):
+            t.C_extra[i] = float(tab.C_extra[i])
+        _fill2(t.A_extra, np.asarray(tab.A_extra))
+        _fill2(t.Plow, tab.Plow)
+        _fill2(t.Pbest, tab.Pbest)
+        t.npol_low, t.npol_best = tab.Plow.shape[1], tab.Pbest.shape[1]
+    scp = sc_params if sc_params is not None else tab.sc_params
+    if isinstance(scp, str):
+        scp = O.SC_PRESETS[scp]
+    for i in range(4):
+        t.sc[i] = float(scp[i])
+    return t
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
+             first_step=None, max_step=np.inf, sc_params=None,
+             interpolant=None, t_eval=None, forced_h=None, max_steps=0,
+             n_threads=1, user_fn=None, n_param=None):
+    """Integrate N lanes with the C oracle.  y0 [N, n], params [N, p].
+    `rhs`: built-in name, or None with `user_fn` = python callable
+    f(t, y) -> dy (slow; single thread).  Returns a dict of numpy arrays."""
+    lib = load()
+    y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, dtype=float)))
+    N, n = y0.shape
+    rtol_v, atol_v = O.validate_tol(float(rtol), atol, y0[0])
+    atol_v = np.ascontiguousarray(np.broadcast_to(atol_v, (n,)), dtype=float)
+    if params is not None:
+        params = np.ascontiguousarray(np.asarray(params, dtype=float))
+        if params.ndim == 1:
+            params = params.reshape(N, -1)
+        p = params.shape[1]
+    else:
+        p = 0
+    t = make_tab(tab, sc_params)
+    te = (np.ascontiguousarray(np.asarray(t_eval, dtype=float))
+          if t_eval is not None else None)
+    n_eval = te.size if te is not None else 0
+    hf = (np.ascontiguousarray(np.asarray(forced_h, dtype=float))
+          if forced_h is not None else None)
+    y_eval = np.empty((N, n, n_eval)) if n_eval else None
+    t_final = np.empty(N)
+    y_final = np.empty((N, n))
+    h_next = np.empty(N)
+    n_acc = np.empty(N, np.int32)
+    n_rej = np.empty(N, np.int32)
+    nfev = np.empty(N, np.int32)
+    status = np.empty(N, np.int32)
+    n_done = np.empty(N, np.int32)
+    if rhs is not None:
+        rid, cb = RHS_IDS[rhs], RHS_FN()
+    else:
+        rid = -1
+
+        def _cb(tt, yp, pp, dyp):
+            yv = np.ctypeslib.as_array(yp, (n,))
+            out = np.asarray(user_fn(tt, yv), dtype=float)
+            for i in range(n):
+                dyp[i] = out[i]
+        cb = RHS_FN(_cb)
+    ip = {None: 0, "free": 1, "low": 2, "best": 3}[interpolant]
+    rc = lib.xsq_oracle_rk_batch(
+        C.byref(t), C.c_int(rid), cb, C.c_int(n), C.c_int(p), C.c_int64(N),
+        _dp(y0), _dp(params), C.c_double(t_span[0]), C.c_double(t_span[1]),
+        C.c_double(float(rtol_v)), _dp(atol_v),
+        C.c_double(first_step if first_step is not None else 0.0),
+        C.c_double(max_step), t.sc, C.c_int(ip), _dp(te), C.c_int(n_eval),
+        _dp(y_eval), _dp(hf), C.c_int(hf.size if hf is not None else 0),
+        C.c_int(max_steps), _dp(t_final), _dp(y_final), _dp(h_next),
+        _ip(n_acc), _ip(n_rej), _ip(nfev), _ip(status), _ip(n_done),
+        C.c_int(n_threads))
+    if rc != 0:
+        raise RuntimeError("xsq_oracle_rk_batch failed")
+    return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
+                h_next=h_next, n_accepted=n_acc, n_rejected=n_rej, nfev=nfev,
+                status=status, n_eval_done=n_done)

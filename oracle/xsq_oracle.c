@@ -1,0 +1,563 @@
+/*
+ * TEST INFRASTRUCTURE -- plain-C restatement of extensisq's explicit adaptive
+ * Runge-Kutta path (scalar loops, one trajectory at a time, OpenMP over
+ * trajectories).  NOT part of the product: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.
+ *
+ * It follows, function by function (file:line in /root/reference/extensisq):
+ *   validate_tol                 common.py:30-54     (done by the caller, oracle/c_oracle.py)
+ *   calculate_scale, norm        common.py:57-66     -> scaled_norm(), rms()
+ *   _init_min_step_parameters    common.py:123-148   -> h_min_a()
+ *   _init_sc_control             common.py:166-185   -> in rk_solve_one()
+ *   RungeKutta.__init__          common.py:187-220
+ *   _step_impl                   common.py:222-308
+ *   _reassess_stepsize           common.py:310-331
+ *   _comp_sol_err, _rk_stage     common.py:333-356
+ *   _dense_output_impl, Horner   common.py:358-368, 766-790 (+ cubic 793-821)
+ *   h_start                      common.py:519-763
+ *   BS5._step_impl, pre-error    bogacki.py:238-346, interpolants 348-393
+ *   CFMR7osc._step_impl          calvo.py:152-261
+ *   solve_ivp loop / t_eval      scipy/integrate/_ivp/ivp.py:659-731
+ *
+ * Pinning: tests/test_oracle_golden.py checks this library against the golden
+ * vectors produced by the unmodified reference (tools/gen_golden.py): equal
+ * accepted/rejected/nfev counts and states to 1e-11 relative.
+ *
+ * Arithmetic: IEEE double, sums accumulated in index order with fma(), i.e.
+ * the summation order differs from the OpenBLAS dgemv the reference uses
+ *  -- hence a tolerance, not bit equality, against the
+ * reference; but it is the SAME order the CUDA kernels use, so forced-step
+ * runs of the CUDA path are compared bit-for-bit against this file.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXS 18
+#define MAXN 192
+#define MAXPOL 8
+#define KROWS (MAXS + 4)
+
+#define SQRT_TINY 0x1.0p-511
+#define BIG 0x1.fffffffffffffp+511
+#define SMALL 0x1.0000000000001p-53
+#define RELPER 0x1.172b83c7d517bp-20
+
+enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2 };
+enum { ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_OVERFLOW = -2, ST_BUDGET = -5 };
+enum { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
+enum { RHS_LORENZ = 0, RHS_VDP = 1, RHS_ARENSTORF = 2, RHS_NBODY32 = 3 };
+
+typedef struct {
+    int32_t s, order, order2, npol, variant, pad;
+    double A[MAXS][MAXS], B[MAXS], C[MAXS], E[MAXS + 1];
+    double P[MAXS + 1][MAXPOL];
+    /* BS5 only */
+    double E_pre[MAXS], B_scale_pre[MAXS], C_extra[3], A_extra[3][MAXS];
+    double Plow[MAXS + 2][MAXPOL], Pbest[MAXS + 4][MAXPOL];
+    int32_t npol_low, npol_best;
+    double sc[4];
+} otab_t;
+
+typedef void (*rhs_fn)(double t, const double* y, const double* p, double* dy);
+
+/* ---- built-in right-hand sides (same expression trees as xsq_rhs.cuh) ---- */
+static void f_lorenz(double t, const double* y, const double* p, double* dy) {
+    (void)t;
+    dy[0] = p[0] * (y[1] - y[0]);
+    dy[1] = fma(y[0], p[1] - y[2], -y[1]);
+    dy[2] = fma(y[0], y[1], -(p[2] * y[2]));
+}
+static void f_vdp(double t, const double* y, const double* p, double* dy) {
+    (void)t;
+    dy[0] = y[1];
+    dy[1] = fma(p[0] * fma(-y[0], y[0], 1.0), y[1], -y[0]);
+}
+static void f_arenstorf(double t, const double* y, const double* p, double* dy) {
+    (void)t;
+    const double mu = p[0], mup = 1.0 - mu;
+    const double xa = y[0] + mu, xb = y[0] - mup;
+    double d1 = fma(xa, xa, y[1] * y[1]);
+    d1 = d1 * sqrt(d1);
+    double d2 = fma(xb, xb, y[1] * y[1]);
+    d2 = d2 * sqrt(d2);
+    dy[0] = y[2];
+    dy[1] = y[3];
+    dy[2] = fma(2.0, y[3], y[0]) - mup * xa / d1 - mu * xb / d2;
+    dy[3] = fma(-2.0, y[2], y[1]) - mup * y[1] / d1 - mu * y[1] / d2;
+}
+/* y = [pos(3*32), vel(3*32)], p = (eps2, m[32]) */
+static void f_nbody32(double t, const double* y, const double* p, double* dy) {
+    (void)t;
+    const int nb = 32;
+    for (int i = 0; i < nb; ++i) {
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int j = 0; j < nb; ++j) {
+            const double dx = y[3 * j] - y[3 * i];
+            const double dyy = y[3 * j + 1] - y[3 * i + 1];
+            const double dz = y[3 * j + 2] - y[3 * i + 2];
+            const double r2 = fma(dz, dz, fma(dyy, dyy, fma(dx, dx, p[0])));
+            const double inv = 1.0 / (r2 * sqrt(r2));
+            const double w = (j == i) ? 0.0 : p[1 + j] * inv;
+            ax = fma(w, dx, ax);
+            ay = fma(w, dyy, ay);
+            az = fma(w, dz, az);
+        }
+        dy[3 * i] = y[3 * nb + 3 * i];
+        dy[3 * i + 1] = y[3 * nb + 3 * i + 1];
+        dy[3 * i + 2] = y[3 * nb + 3 * i + 2];
+        dy[3 * nb + 3 * i] = ax;
+        dy[3 * nb + 3 * i + 1] = ay;
+        dy[3 * nb + 3 * i + 2] = az;
+    }
+}
+static rhs_fn builtin_rhs(int id) {
+    switch (id) {
+        case RHS_LORENZ: return f_lorenz;
+        case RHS_VDP: return f_vdp;
+        case RHS_ARENSTORF: return f_arenstorf;
+        case RHS_NBODY32: return f_nbody32;
+        default: return 0;
+    }
+}
+
+typedef struct {
+    const otab_t* T;
+    rhs_fn f;
+    const double* prm;
+    int n;
+    double rtol;
+    const double* atol; /* [n] */
+    double t_bound, direction, max_step;
+    double err_exp, minbeta1, minbeta2, minalpha, safety, safety_sc, h_min_a;
+    int interpolant;
+    /* state */
+    double t, h_abs, h_prev, err_old, max_factor, min_step;
+    double y[MAXN], fcur[MAXN];
+    double K[KROWS][MAXN];
+    int n_acc, n_rej, nfev, standard_sc;
+} lane_t;
+
+/* common.py:64-66, sequential accumulation */
+static double rms(const double* x, int n) {
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) s = fma(x[c], x[c], s);
+    return sqrt(s / (double)n);
+}
+
+/* common.py:519-763 */
+static double h_start(lane_t* L, double a, double b, int morder) {
+    const int n = L->n;
+    double spy[MAXN], pv[MAXN], yp[MAXN], sf[MAXN];
+    const double* y = L->y;
+    const double* yprime = L->fcur;
+    const double dx = b - a, absdx = fabs(dx);
+    double da = copysign(fmax(fmin(RELPER * fabs(a), absdx), 100.0 * SMALL * fabs(a)), dx);
+    if (da == 0.0) da = RELPER * dx;
+    L->f(a + da, y, L->prm, sf);
+    L->nfev++;
+    for (int c = 0; c < n; ++c) yp[c] = sf[c] - yprime[c];
+    double delf = rms(yp, n);
+    double dfdxb = BIG;
+    if (delf < BIG * fabs(da)) dfdxb = delf / fabs(da);
+    double fbnd = rms(sf, n);
+    double dely = RELPER * rms(y, n);
+    if (dely == 0.0) dely = RELPER;
+    dely = copysign(dely, dx);
+    delf = rms(yprime, n);
+    fbnd = fmax(fbnd, delf);
+    if (delf != 0.0) {
+        for (int c = 0; c < n; ++c) { spy[c] = yprime[c]; yp[c] = yprime[c]; }
+    } else {
+        for (int c = 0; c < n; ++c) { spy[c] = 0.0; yp[c] = 1.0; }
+        delf = rms(yp, n);
+    }
+    double dfdub = 0.0;
+    const int lk = n + 1 < 3 ? n + 1 : 3;
+    for (int k = 1; k <= lk; ++k) {
+        const double q = dely / delf;
+        for (int c = 0; c < n; ++c) pv[c] = fma(q, yp[c], y[c]);
+        if (k == 2) {
+            L->f(a + da, pv, L->prm, yp);
+            for (int c = 0; c < n; ++c) pv[c] = yp[c] - sf[c];
+        } else {
+            L->f(a, pv, L->prm, yp);
+            for (int c = 0; c < n; ++c) pv[c] = yp[c] - yprime[c];
+        }
+        L->nfev++;
+        fbnd = fmax(fbnd, rms(yp, n));
+        delf = rms(pv, n);
+        if (delf >= BIG * fabs(dely)) { dfdub = BIG; break; }
+        dfdub = fmax(dfdub, delf / fabs(dely));
+        if (k == lk) break;
+        if (delf == 0.0) delf = 1.0;
+        for (int c = 0; c < n; ++c) {
+            double dy;
+            if (k == 2) dy = (y[c] != 0.0) ? y[c] : dely / RELPER;
+            else dy = (pv[c] != 0.0) ? pv[c] : delf;
+            if (spy[c] == 0.0) spy[c] = yp[c];
+            yp[c] = (spy[c] != 0.0) ? copysign(dy, spy[c]) : dy;
+        }
+        delf = rms(yp, n);
+    }
+    const double ydpb = fma(dfdub, fbnd, dfdxb);
+    double tolsum = 0.0, tolmin = INFINITY;
+    for (int c = 0; c < n; ++c) {
+        const double etol = fma(L->rtol, fabs(y[c]), L->atol[c]);
+        const double te = log10(etol);
+        tolsum += te;
+        tolmin = fmin(tolmin, te);
+    }
+    tolmin = fmin(tolmin, BIG);
+    const double tolp = pow(10.0, 0.5 * (tolsum / (double)n + tolmin) / (double)(morder + 1));
+    double h = absdx;
+    if (ydpb == 0.0 && fbnd == 0.0) {
+        if (tolp < 1.0) h = absdx * tolp;
+    } else if (ydpb == 0.0) {
+        if (tolp < fbnd * absdx) h = tolp / fbnd;
+    } else {
+        const double srydpb = sqrt(0.5 * ydpb);
+        if (tolp < srydpb * absdx) h = tolp / srydpb;
+    }
+    if (dfdub != 0.0) h = fmin(h, 1.0 / dfdub);
+    h = fmax(h, 100.0 * SMALL * fabs(a));
+    if (h == 0.0) h = SMALL * fabs(b);
+    return fabs(h);
+}
+
+/* sum_j w[j] K[j][c] over nonzero weights, first term a plain product */
+static double wsum_first(lane_t* L, const double* w, int m, int c) {
+    double acc = 0.0;
+    int first = 1;
+    for (int j = 0; j < m; ++j) {
+        if (w[j] != 0.0) {
+            acc = first ? w[j] * L->K[j][c] : fma(w[j], L->K[j][c], acc);
+            first = 0;
+        }
+    }
+    return acc;
+}
+/* same but accumulated with fma from 0.0 */
+static double wsum(lane_t* L, const double* w, int m, int c) {
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j)
+        if (w[j] != 0.0) acc = fma(w[j], L->K[j][c], acc);
+    return acc;
+}
+
+/* common.py:353-356 */
+static void rk_stage(lane_t* L, double h, int i) {
+    double ys[MAXN];
+    for (int c = 0; c < L->n; ++c) ys[c] = fma(h, wsum_first(L, L->T->A[i], i, c), L->y[c]);
+    L->f(L->t + L->T->C[i] * h, ys, L->prm, L->K[i]);
+    L->nfev++;
+}
+
+/* norm(err / scale(y, yref)), common.py:57-66, 338-339 */
+static double scaled_norm(lane_t* L, const double* errv, const double* yref) {
+    double q[MAXN];
+    for (int c = 0; c < L->n; ++c) {
+        const double scale = fma(L->rtol, fmax(fabs(L->y[c]), fabs(yref[c])), L->atol[c]);
+        q[c] = errv[c] / scale;
+    }
+    return rms(q, L->n);
+}
+
+static void reassess(lane_t* L) { /* common.py:310-331 */
+    L->min_step = fmax(L->h_min_a * (fabs(L->t) + L->h_abs), SQRT_TINY);
+    if (L->h_abs < L->min_step || L->h_abs > L->max_step) {
+        L->h_abs = fmin(L->max_step, fmax(L->min_step, L->h_abs));
+        L->standard_sc = 1;
+    }
+    const double d = fabs(L->t_bound - L->t);
+    if (d < 2.0 * L->h_abs) {
+        if (d > L->h_abs) {
+            L->h_abs = fmax(0.5 * d, L->min_step);
+            L->standard_sc = 1;
+        } else {
+            L->h_abs = d;
+        }
+    }
+}
+
+/* Dense output over [t, t_new] (K complete); writes points into out[c*n_eval+i] */
+static void bs5_extra(lane_t* L, double h, int r) {
+    const int row = L->T->s + 1 + r;
+    double ys[MAXN];
+    for (int c = 0; c < L->n; ++c) ys[c] = fma(wsum(L, L->T->A_extra[r], row, c), h, L->y[c]);
+    L->f(L->t + L->T->C_extra[r] * h, ys, L->prm, L->K[row]);
+    L->nfev++;
+}
+
+static int emit(lane_t* L, double h, double t_new, const double* y_new,
+                const double* t_eval, int n_eval, int ieval, double* out) {
+    const otab_t* T = L->T;
+    const int n = L->n, s = T->s;
+    if (ieval >= n_eval) return ieval;
+    if (L->direction * (t_eval[ieval] - t_new) > 0.0) return ieval;
+    if (T->npol == 0) { /* CubicDenseOutput, common.py:793-821 */
+        const double hh = t_new - L->t;
+        while (ieval < n_eval && L->direction * (t_eval[ieval] - t_new) <= 0.0) {
+            const double x = (t_eval[ieval] - L->t) / hh, omx = 1.0 - x;
+            const double h00 = (1.0 + 2.0 * x) * (omx * omx);
+            const double h10 = x * (omx * omx) * hh;
+            const double h01 = (x * x) * (3.0 - 2.0 * x);
+            const double h11 = (x * x) * (x - 1.0) * hh;
+            for (int c = 0; c < n; ++c)
+                out[(size_t)c * n_eval + ieval] =
+                    ((h00 * L->y[c] + h10 * L->K[0][c]) + h01 * y_new[c]) + h11 * L->K[s][c];
+            ++ieval;
+        }
+        return ieval;
+    }
+    double Q[MAXPOL][MAXN];
+    int npol = T->npol, anchor_end = 0;
+    double t_anchor = L->t, h_anchor = t_new - L->t;
+    if (T->variant == V_BS5 && L->interpolant == IP_LOW) {
+        bs5_extra(L, h, 0);
+        npol = T->npol_low;
+        for (int k = 0; k < npol; ++k)
+            for (int c = 0; c < n; ++c) {
+                double acc = 0.0;
+                for (int i = 0; i <= s + 1; ++i)
+                    if (T->Plow[i][k] != 0.0) acc = fma(T->Plow[i][k], L->K[i][c], acc);
+                Q[k][c] = acc;
+            }
+    } else if (T->variant == V_BS5 && L->interpolant == IP_BEST) {
+        bs5_extra(L, h, 0);
+        bs5_extra(L, h, 1);
+        bs5_extra(L, h, 2);
+        npol = T->npol_best;
+        for (int c = 0; c < n; ++c) { /* bogacki.py:372-388 */
+            double kp[11];
+            Q[0][c] = L->K[7][c];
+#define KP(col) for (int i = 0; i < 11; ++i) kp[i] = L->K[i][c] * T->Pbest[i][col];
+            KP(1) Q[1][c] = (kp[4] + ((kp[5] + kp[7]) + kp[0]) + ((kp[2] + kp[8]) + kp[9]) +
+                             ((kp[3] + kp[10]) + kp[6]));
+            KP(2) Q[2][c] = (kp[4] + kp[5] + ((kp[2] + kp[8]) + (kp[9] + kp[7]) + kp[0]) +
+                             ((kp[3] + kp[10]) + kp[6]));
+            KP(3) Q[3][c] = (((kp[3] + kp[7]) + (kp[6] + kp[5]) + kp[4]) +
+                             ((kp[9] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
+            KP(4) Q[4][c] = ((kp[9] + kp[8]) + ((kp[6] + kp[5]) + kp[4]) +
+                             ((kp[3] + kp[7]) + (kp[2] + kp[10]) + kp[0]));
+            KP(5) Q[5][c] = (kp[4] + ((kp[9] + kp[7]) + (kp[6] + kp[5])) +
+                             ((kp[3] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
+#undef KP
+        }
+        anchor_end = 1;
+        t_anchor = t_new;
+        h_anchor = (t_new + h) - t_new;
+    } else { /* Q = K.T @ P, common.py:363 */
+        for (int k = 0; k < npol; ++k)
+            for (int c = 0; c < n; ++c) {
+                double acc = 0.0;
+                for (int i = 0; i <= s; ++i)
+                    if (T->P[i][k] != 0.0) acc = fma(T->P[i][k], L->K[i][c], acc);
+                Q[k][c] = acc;
+            }
+    }
+    for (int k = 0; k < npol; ++k)
+        for (int c = 0; c < n; ++c) Q[k][c] *= h_anchor;
+    while (ieval < n_eval && L->direction * (t_eval[ieval] - t_new) <= 0.0) {
+        const double x = (t_eval[ieval] - t_anchor) / h_anchor;
+        for (int c = 0; c < n; ++c) { /* Horner, common.py:781-785 */
+            double v = Q[npol - 1][c] * x;
+            for (int k = npol - 2; k >= 0; --k) v = (v + Q[k][c]) * x;
+            out[(size_t)c * n_eval + ieval] = v + (anchor_end ? y_new[c] : L->y[c]);
+        }
+        ++ieval;
+    }
+    return ieval;
+}
+
+/* One trajectory: solve_ivp(fun, (t0, tf), y0, method=T, ...). */
+static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
+                         const double* prm, double t0, double tf, double rtol,
+                         const double* atol, double first_step, double max_step,
+                         const double* sc, int interpolant, const double* t_eval,
+                         int n_eval, double* y_eval, const double* h_forced,
+                         int n_forced, int max_steps, double* t_final,
+                         double* y_final, double* h_next, int32_t* n_acc,
+                         int32_t* n_rej, int32_t* nfev, int32_t* status,
+                         int32_t* n_eval_done) {
+    lane_t* L = (lane_t*)malloc(sizeof(lane_t));
+    const int s = T->s;
+    L->T = T; L->f = f; L->prm = prm; L->n = n;
+    L->rtol = rtol; L->atol = atol;
+    L->t_bound = tf;
+    L->direction = (tf != t0) ? (tf > t0 ? 1.0 : -1.0) : 1.0;
+    L->max_step = max_step;
+    const int oe = T->order2 < T->order ? T->order2 : T->order;
+    L->err_exp = -1.0 / (oe + 1);
+    L->minbeta1 = sc[0] * L->err_exp;
+    L->minbeta2 = sc[1] * L->err_exp;
+    L->minalpha = -sc[2];
+    L->safety = sc[3];
+    L->safety_sc = pow(sc[3], sc[0] + sc[1]);
+    double cdiff = 1.0; /* common.py:129-137 */
+    for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) {
+            const double d = fabs(T->C[i] - T->C[j]);
+            if (d != 0.0 && d < cdiff) cdiff = d;
+        }
+    if (cdiff < 1e-3) cdiff = 1e-3;
+    L->h_min_a = 10 * 0x1.0p-53 / cdiff;
+    L->interpolant = interpolant ? interpolant : IP_LOW;
+    L->t = t0;
+    memcpy(L->y, y0, sizeof(double) * n);
+    L->n_acc = L->n_rej = 0;
+    L->nfev = 1;
+    f(t0, L->y, prm, L->fcur);
+    L->standard_sc = 1;
+    L->max_factor = 10.0;
+    L->h_prev = 0.0; L->err_old = 0.0; L->min_step = 0.0;
+    const int forced = n_forced > 0;
+    if (forced) L->h_abs = h_forced[0];
+    else if (first_step > 0.0) L->h_abs = first_step;
+    else {
+        const double b = t0 + L->direction * fmin(fabs(tf - t0), max_step);
+        L->h_abs = h_start(L, t0, b, T->order2);
+    }
+    int ieval = 0, st = 1, attempts = 0;
+    const int early = T->variant != V_GENERIC;
+    const int fsal = T->E[s] != 0.0;
+    if (!forced && t0 == tf) { /* scipy base.py:195-200 */
+        for (int i = 0; i < n_eval; ++i)
+            for (int c = 0; c < n; ++c) y_eval[(size_t)c * n_eval + i] = L->y[c];
+        ieval = n_eval;
+        st = ST_FINISHED;
+    }
+    while (st == 1) {
+        int step_rejected = 0;
+        if (!forced) reassess(L);
+        for (;;) { /* while not step_accepted */
+            if (forced) L->h_abs = h_forced[L->n_acc];
+            else {
+                if (L->h_abs < L->min_step) { st = ST_TOO_SMALL; break; }
+                if (attempts >= max_steps) { st = ST_BUDGET; break; }
+            }
+            ++attempts;
+            const double h = L->h_abs * L->direction;
+            const double t_new = L->t + h;
+            memcpy(L->K[0], L->fcur, sizeof(double) * n);
+            const int nfirst = early ? s - 1 : s;
+            for (int i = 1; i < nfirst; ++i) rk_stage(L, h, i);
+            double y_new[MAXN], errv[MAXN];
+            if (early) { /* bogacki.py:340-346, calvo.py:255-261 */
+                const double* wb = T->variant == V_BS5 ? T->B_scale_pre : T->A[s - 1];
+                const double* we = T->variant == V_BS5 ? T->E_pre : T->E;
+                for (int c = 0; c < n; ++c) {
+                    y_new[c] = fma(h, wsum(L, wb, s - 1, c), L->y[c]);
+                    errv[c] = h * wsum(L, we, s - 1, c);
+                }
+                const double err_pre = scaled_norm(L, errv, y_new);
+                if (!forced && err_pre > 1.0) {
+                    step_rejected = 1;
+                    L->h_abs *= fmax(0.2, L->safety * pow(err_pre, L->err_exp));
+                    L->n_rej++;
+                    continue;
+                }
+                rk_stage(L, h, s - 1);
+            }
+            for (int c = 0; c < n; ++c) y_new[c] = fma(h, wsum(L, T->B, s, c), L->y[c]);
+            if (fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
+            for (int c = 0; c < n; ++c) errv[c] = h * wsum(L, T->E, s + fsal, c);
+            const double err = scaled_norm(L, errv, y_new);
+            if (!forced) {
+                if (err < 1.0) { /* common.py:249-276 */
+                    double factor;
+                    if (err < SQRT_TINY) {
+                        factor = L->max_factor;
+                        L->standard_sc = 1;
+                    } else if (L->standard_sc) {
+                        factor = L->safety * pow(err, L->err_exp);
+                        L->standard_sc = 0;
+                    } else {
+                        const double h_ratio = h / L->h_prev;
+                        double fac = pow(err, L->minbeta1);
+                        if (L->minbeta2 != 0.0) fac *= pow(L->err_old, L->minbeta2);
+                        if (L->minalpha != 0.0) fac *= pow(h_ratio, L->minalpha);
+                        factor = L->safety_sc * fac;
+                        factor = fmin(L->max_factor, fmax(0.2, factor));
+                    }
+                    if (step_rejected) factor = fmin(1.0, factor);
+                    L->h_abs *= factor;
+                    if (factor < 4.0) L->max_factor = 4.0;
+                } else {
+                    const int bad = isnan(err) || isinf(err);
+                    if (T->variant == V_BS5 && bad) { st = ST_OVERFLOW; break; }
+                    step_rejected = 1;
+                    L->h_abs *= fmax(0.2, L->safety * pow(err, L->err_exp));
+                    L->n_rej++;
+                    if (bad) { st = ST_OVERFLOW; break; }
+                    continue;
+                }
+            }
+            if (!fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
+            if (n_eval > 0) ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
+            L->h_prev = h;
+            L->err_old = err;
+            L->t = t_new;
+            memcpy(L->y, y_new, sizeof(double) * n);
+            memcpy(L->fcur, L->K[s], sizeof(double) * n);
+            L->n_acc++;
+            if (forced) { if (L->n_acc >= n_forced) st = ST_FINISHED; }
+            else if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
+            break;
+        }
+    }
+    for (int i = ieval; i < n_eval; ++i)
+        for (int c = 0; c < n; ++c) y_eval[(size_t)c * n_eval + i] = NAN;
+    *t_final = L->t;
+    memcpy(y_final, L->y, sizeof(double) * n);
+    if (h_next) *h_next = L->h_abs;
+    *n_acc = L->n_acc; *n_rej = L->n_rej; *nfev = L->nfev; *status = st;
+    if (n_eval_done) *n_eval_done = ieval;
+    free(L);
+}
+
+/* Batch entry: AoS inputs y0[N][n], params[N][p]; outputs y_final[N][n],
+ * y_eval[N][n][n_eval].  rhs >= 0 selects a built-in; rhs < 0 uses `user_f`
+ * (a C function pointer, e.g. a ctypes callback, single thread only). */
+int xsq_oracle_rk_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
+                        int64_t n_lanes, const double* y0, const double* params,
+                        double t0, double tf, double rtol, const double* atol,
+                        double first_step, double max_step, const double* sc,
+                        int interpolant, const double* t_eval, int n_eval,
+                        double* y_eval, const double* h_forced, int n_forced,
+                        int max_steps, double* t_final, double* y_final,
+                        double* h_next, int32_t* n_acc, int32_t* n_rej,
+                        int32_t* nfev, int32_t* status, int32_t* n_eval_done,
+                        int n_threads) {
+    rhs_fn f = rhs >= 0 ? builtin_rhs(rhs) : user_f;
+    if (!f || n > MAXN || T->s >= MAXS) return -1;
+    if (max_steps <= 0) max_steps = 2147483647;
+    if (rhs < 0) n_threads = 1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n_lanes; ++i) {
+        rk_solve_one(T, f, n, y0 + i * n, params ? params + i * p : 0, t0, tf, rtol,
+                     atol, first_step, max_step, sc, interpolant, t_eval, n_eval,
+                     y_eval ? y_eval + (size_t)i * n * n_eval : 0, h_forced, n_forced,
+                     max_steps, t_final + i, y_final + i * n, h_next ? h_next + i : 0,
+                     n_acc + i, n_rej + i, nfev + i, status + i,
+                     n_eval_done ? n_eval_done + i : 0);
+    }
+    return 0;
+}
+
+int xsq_oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+size_t xsq_oracle_tab_size(void) { return sizeof(otab_t); }

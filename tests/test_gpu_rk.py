@@ -1,0 +1,468 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through
+the C ABI (ctypes -> libxsq.so), against
+
+* the C oracle (oracle/xsq_oracle.c) on the same seeded inputs:
+    - forced step sequence: BIT-EXACT states (same fma order on both sides),
+      which is stronger than the 1e-12 relative BASELINE.json asks for;
+    - adaptive: accepted / rejected / nfev counts equal per trajectory and
+      states within 10 x rtol (BASELINE.json north_star), on spans inside the
+      predictability horizon (hard part 1);
+* the golden vectors of the unmodified reference (tests/golden/);
+* size-independent properties at ensemble scale.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import extensisq_b200 as xb
+from extensisq_b200 import _lib
+from golden_util import (Golden, BUILTIN_PROBLEMS, case_options, case_span,
+                         case_t_eval, stability_limited)
+from oracle import c_oracle as CO
+from oracle import rk_oracle as O
+from oracle.problems import CUDA_SOURCES
+
+pytestmark = pytest.mark.gpu
+
+METHODS = [xb.Ts5, xb.BS5, xb.CK5, xb.Me4, xb.Pr7, xb.Pr8, xb.Pr9, xb.CFMR7osc]
+TABS = O.load_tableaux()
+G = Golden()
+_RHS = {}
+
+
+def rhs_for(problem):
+    if problem in BUILTIN_PROBLEMS:
+        return problem
+    if problem not in _RHS:
+        n, p, src = CUDA_SOURCES[problem]
+        _RHS[problem] = xb.DeviceRHS.from_source(src, "rhs", n, p)
+    return _RHS[problem]
+
+
+def lorenz_lanes(N, seed=12345):
+    rng = np.random.default_rng(seed)
+    y0 = np.stack([rng.uniform(-15, 15, N), rng.uniform(-20, 20, N),
+                   rng.uniform(5, 40, N)], axis=1)
+    prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N),
+                    rng.uniform(2.4, 2.9, N)], axis=1)
+    return y0, prm
+
+
+def vdp_lanes(N):
+    mu = 10.0 ** (-1 + 3 * np.arange(N) / max(N - 1, 1))    # C3
+    return np.tile([2.0, 0.0], (N, 1)), mu[:, None]
+
+
+def arenstorf_lanes(N, seed=2024):
+    rng = np.random.default_rng(seed)
+    y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252240537862224])
+    y0 = y0 + rng.uniform(-1e-3, 1e-3, (N, 4))
+    return y0, np.full((N, 1), 0.012277471)
+
+
+def to_np(res):
+    torch.cuda.synchronize()
+    return {k: (getattr(res, k).cpu().numpy()
+                if getattr(res, k) is not None else None)
+            for k in ("y", "t_final", "y_final", "h_next", "n_accepted",
+                      "n_rejected", "nfev", "status", "n_eval_done")}
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# --------------------------------------------------------------------------
+def test_extension_is_loaded_and_device_is_blackwell():
+    lib = _lib.load()
+    n_sm, major, minor = C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.xsq_device_info(0, C.byref(n_sm), C.byref(major),
+                               C.byref(minor)) == 0
+    assert major.value == 10 and n_sm.value >= 100
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_tableau_image_on_device_equals_reference_data(m):
+    """Read the coefficients back from the device (xsq_tableau_get) and compare
+    bit-for-bit with the reference's class attributes."""
+    lib = _lib.load()
+    t = _lib.XsqTableau()
+    assert lib.xsq_tableau_get(m._xsq_method, C.byref(t)) == 0
+    s = m.n_stages
+    assert (t.n_stages, t.order, t.order_secondary) == (s, m.order,
+                                                        m.order_secondary)
+    A = np.array([[t.A[i][j] for j in range(s)] for i in range(s)])
+    assert np.array_equal(A, m.A)
+    assert np.array_equal(np.array(t.B[:s]), m.B)
+    assert np.array_equal(np.array(t.C[:s]), m.C)
+    assert np.array_equal(np.array(t.E[:s + 1]), m.E)
+    P = np.array([[t.P[i][k] for k in range(t.n_poly)] for i in range(s + 1)])
+    assert np.array_equal(P, m.P)
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_forced_steps_bit_exact_vs_c_oracle(m, prob):
+    N = 96
+    y0, prm = {"lorenz63": lorenz_lanes, "vanderpol": vdp_lanes,
+               "arenstorf": arenstorf_lanes}[prob](N)
+    k = np.arange(120)
+    hs = {"lorenz63": 0.01, "vanderpol": 0.004, "arenstorf": 0.002}[prob] * \
+        (1.0 + 0.6 * np.sin(0.37 * k)) + 1e-4
+    res = to_np(xb.solve_ivp_batched(prob, (0.0, 1.0), y0, m, params=prm,
+                                     forced_steps=hs))
+    ref = CO.rk_batch(TABS[m.__name__], prob, (0.0, 1.0), y0, params=prm,
+                      forced_h=hs, n_threads=4)
+    assert np.array_equal(res["n_accepted"], ref["n_accepted"])
+    assert np.array_equal(res["nfev"], ref["nfev"])
+    assert np.array_equal(res["t_final"], ref["t_final"])
+    assert np.array_equal(res["y_final"], ref["y_final"])      # bit-exact
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_forced_steps_vs_reference_golden(m):
+    """North star: forced fixed step sequence -> states agree with the
+    reference to 1e-12 relative."""
+    for cid, prob in ((f"forced_lorenz_{m.__name__}", "lorenz63"),
+                      (f"forced_vdp_back_{m.__name__}", "vanderpol")):
+        c = G.by_id[cid]
+        h = G.arr(cid, "h")
+        span = (0.0, 1.0) if prob == "lorenz63" else (0.0, -1.0)
+        res = to_np(xb.solve_ivp_batched(prob, span, [c["y0"]], m,
+                                         params=[c["params"]], forced_steps=h))
+        assert res["nfev"][0] == c["nfev"]
+        assert rel(res["y_final"][0], G.arr(cid, "y")[:, -1]) <= 1e-12
+        assert rel(res["t_final"], G.arr(cid, "t")[-1:]) <= 1e-15
+
+
+ADAPTIVE = [("lorenz63", lorenz_lanes, (0.0, 5.0), 1e-8, 1e-10),
+            ("vanderpol", lambda n: vdp_lanes(n), (0.0, 20.0), 1e-8, 1e-10),
+            ("arenstorf", arenstorf_lanes, (0.0, 3.0), 1e-8, 1e-10)]
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+@pytest.mark.parametrize("prob,lanes,span,rtol,atol", ADAPTIVE,
+                         ids=[a[0] for a in ADAPTIVE])
+def test_adaptive_parity_vs_c_oracle(m, prob, lanes, span, rtol, atol):
+    """Accepted/rejected/nfev equal per trajectory, states within 10 x rtol.
+    Lanes whose accept/reject decisions sit on the stability boundary
+    (Van der Pol, mu >~ 10) may flip under the 1-2 ulp difference between
+    CUDA's and glibc's pow(); they are counted and bounded, not hidden."""
+    N = 256
+    y0, prm = lanes(N)
+    res = to_np(xb.solve_ivp_batched(prob, span, y0, m, params=prm, rtol=rtol,
+                                     atol=atol))
+    ref = CO.rk_batch(TABS[m.__name__], prob, span, y0, params=prm, rtol=rtol,
+                      atol=atol, n_threads=8)
+    assert (res["status"] == 0).all() and (ref["status"] == 0).all()
+    same = ((res["n_accepted"] == ref["n_accepted"]) &
+            (res["n_rejected"] == ref["n_rejected"]) &
+            (res["nfev"] == ref["nfev"]))
+    frac_same = same.mean()
+    scale = np.abs(ref["y_final"]).max(axis=1, keepdims=True) + 1e-300
+    err = (np.abs(res["y_final"] - ref["y_final"]) / scale).max(axis=1)
+    if prob == "vanderpol":
+        easy = prm[:, 0] < 5.0
+        assert same[easy].mean() >= 0.99
+        assert frac_same >= 0.80
+        # total work agrees closely even where individual decisions flip
+        assert abs(res["nfev"].sum() - ref["nfev"].sum()) <= \
+            0.01 * ref["nfev"].sum()
+        assert err[same].max() <= 10 * rtol
+        assert np.median(err) <= 10 * rtol
+    else:
+        assert frac_same >= 0.99
+        assert err[same].max() <= 10 * rtol
+    assert np.array_equal(res["t_final"], np.full(N, span[1]))
+
+
+def _golden_cases():
+    out = []
+    for c in G.cases:
+        if c.get("forced") or c.get("keep") == "counts":
+            continue
+        out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("c", _golden_cases(), ids=lambda c: c["id"])
+def test_adaptive_vs_reference_golden(c):
+    """Every adaptive golden case of the unmodified reference, through the
+    CUDA path: step counts equal (approximately for stability-limited cases),
+    solutions at t_eval / final state within 10 x rtol."""
+    m = getattr(xb, c["method"])
+    opts = case_options(c)
+    rtol = opts.get("rtol", 1e-3)
+    te = case_t_eval(c)
+    prm = [c["params"]] if c["params"] else None
+    res = to_np(xb.solve_ivp_batched(rhs_for(c["problem"]), case_span(c),
+                                     [c["y0"]], m, params=prm, t_eval=te,
+                                     **opts))
+    if c["status"] == -1:
+        assert res["status"][0] == -1
+        assert _lib.LANE_MESSAGES[-1] == c["message"]
+        return
+    assert res["status"][0] == 0
+    if stability_limited(c):
+        assert abs(res["n_rejected"][0] - c["nfs"]) <= max(3, 0.15 * c["nfs"])
+        assert abs(res["nfev"][0] - c["nfev"]) <= 0.05 * c["nfev"]
+    else:
+        assert res["n_rejected"][0] == c["nfs"]
+        assert res["nfev"][0] == c["nfev"]
+        if te is None:
+            assert res["n_accepted"][0] == c["n_t"] - 1
+    tol = 10 * rtol
+    if te is None:
+        assert rel(res["y_final"][0], G.arr(c["id"], "y")[:, -1]) <= tol
+    else:
+        yg = G.arr(c["id"], "y")
+        assert res["n_eval_done"][0] == yg.shape[1]
+        assert rel(res["y"][0], yg) <= tol
+        if not stability_limited(c):
+            # interpolants agree far better than the tolerance
+            assert rel(res["y"][0], yg) <= 1e-8
+
+
+def test_known_answers_from_the_reference_notebooks():
+    """docs/Demo_BS5.ipynb: BS5 212 evals on Duffing, free/low/best
+    interpolants 212/238/290; docs/Demo_CFMR7osc.ipynb: 275 (DETEST B3);
+    docs/Demo_own_RK.ipynb: 24 points / 212 evals."""
+    duff = rhs_for("duffing")
+    r = to_np(xb.solve_ivp_batched(duff, (0.0, 20.0), [[0.0, 0.0]], xb.BS5))
+    assert r["nfev"][0] == 212
+    r = to_np(xb.solve_ivp_batched(duff, (0.0, 20.0), [[0.0, 0.0]], xb.Ts5))
+    assert r["nfev"][0] == 341
+    # with dense output the reference builds the interpolant on EVERY step;
+    # t_eval only on steps that bracket a point, so compare to the golden runs
+    for ip in ("free", "low", "best"):
+        c = G.by_id[f"duffing_BS5_{ip}"]
+        r = to_np(xb.solve_ivp_batched(duff, (0.0, 20.0), [[0.0, 0.0]], xb.BS5,
+                                       t_eval=np.linspace(0, 20, 201),
+                                       interpolant=ip))
+        assert r["nfev"][0] == c["nfev"]
+    r = to_np(xb.solve_ivp_batched(rhs_for("detest_b3"), (0.0, 20.0),
+                                   [[1.0, 0.0, 0.0]], xb.CFMR7osc, rtol=1e-6,
+                                   atol=1e-9))
+    assert r["nfev"][0] == 275
+    r = to_np(xb.solve_ivp_batched(rhs_for("mass_spring_damper"), (0.0, 16.0),
+                                   [[0.0, -1.0]], xb.CFMR7osc, rtol=1e-6))
+    assert (r["n_accepted"][0] + 1, r["nfev"][0]) == (24, 212)
+
+
+def test_known_answer_forced_oscillator_long_run():
+    """docs/Demo_CFMR7osc.ipynb:74 -- 109 091 evaluations over t in [0, 1000]
+    (11 622 accepted, 633 rejected steps in the golden run)."""
+    c = G.by_id["known_forcedosc_CFMR7osc"]
+    r = to_np(xb.solve_ivp_batched(rhs_for("forced_osc"), (0.0, 1000.0),
+                                   [[1.0, 11.0]], xb.CFMR7osc, rtol=1e-5,
+                                   atol=1e-8))
+    assert abs(r["nfev"][0] - 109091) <= 0.002 * 109091
+    assert abs(r["n_rejected"][0] - c["nfs"]) <= 0.05 * c["nfs"]
+    assert rel(r["y_final"][0], G.arr(c["id"], "y_final")) <= 1e-3
+
+
+# ---- edge cases the reference tests (tests/test_ivp.py) ---------------------
+def test_first_step_is_taken_exactly_and_max_step_is_respected():
+    # tests/test_ivp.py:627-665 / 582-624
+    y0, prm = lorenz_lanes(8)
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5,
+                                   params=prm, rtol=1e-3, atol=1e-6,
+                                   first_step=0.01, max_steps=1))
+    # budget of one attempt: the lane stops after exactly one step
+    assert (r["status"] == -5).all()
+    assert np.array_equal(r["t_final"], np.full(8, 0.01))
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5,
+                                   params=prm, rtol=1e-3, atol=1e-6,
+                                   max_step=0.004))
+    assert (r["n_accepted"] >= 250).all() and (r["status"] == 0).all()
+    with pytest.raises(ValueError, match="first_step"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             first_step=-1.0)
+    with pytest.raises(ValueError, match="exceeds bounds"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             first_step=5.0)
+    with pytest.raises(ValueError, match="max_step"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             max_step=-1.0)
+    with pytest.raises(ValueError, match="rtol"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             rtol=1)
+    with pytest.raises(ValueError, match="atol"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             atol=[1e-6, 1e-6])
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_too_small_step_fails_in_band(m):
+    # tests/test_ivp.py:600-616: max_step=1e-20 -> status 'failed'
+    y0, prm = lorenz_lanes(4)
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, m, params=prm,
+                                   max_step=1e-20))
+    assert (r["status"] == -1).all()
+    assert (r["n_accepted"] == 0).all() and (r["t_final"] == 0.0).all()
+    assert "step size is less" in xb.batched._lib.LANE_MESSAGES[-1]
+
+
+def test_overflow_lane_does_not_poison_its_warp():
+    """One lane with parameters that blow up (rho = 1e200) fails with the
+    reference's "Overflow or underflow" status; its neighbours finish and
+    match the oracle."""
+    y0, prm = lorenz_lanes(64)
+    prm[5, 1] = 1e200
+    y0[5] = [1e150, 1e150, 1e150]
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 2.0), y0, xb.CK5,
+                                   params=prm, rtol=1e-8, atol=1e-10))
+    ref = CO.rk_batch(TABS["CK5"], "lorenz63", (0.0, 2.0), y0, params=prm,
+                      rtol=1e-8, atol=1e-10, n_threads=4)
+    assert r["status"][5] == ref["status"][5] == -2
+    ok = np.arange(64) != 5
+    assert (r["status"][ok] == 0).all()
+    assert np.array_equal(r["n_accepted"][ok], ref["n_accepted"][ok])
+
+
+def test_empty_ensemble_and_zero_length_span():
+    # tests/test_ivp.py:785-825 (no integration / empty)
+    r = xb.solve_ivp_batched("lorenz63", (0.0, 1.0), np.zeros((0, 3)), xb.Ts5,
+                             params=np.zeros((0, 3)))
+    assert r.y_final.shape == (0, 3) and r.status.numel() == 0
+    y0, prm = lorenz_lanes(5)
+    r = to_np(xb.solve_ivp_batched("lorenz63", (3.0, 3.0), y0, xb.Pr8,
+                                   params=prm, t_eval=[3.0]))
+    assert (r["status"] == 0).all() and (r["n_accepted"] == 0).all()
+    assert np.array_equal(r["y_final"], y0)
+    assert np.array_equal(r["y"][:, :, 0], y0)
+
+
+def test_t_eval_validation():
+    y0, prm = lorenz_lanes(2)
+    with pytest.raises(ValueError, match="not within"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             t_eval=[0.5, 1.5])
+    with pytest.raises(ValueError, match="not properly sorted"):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, params=prm,
+                             t_eval=[0.5, 0.2])
+
+
+@pytest.mark.parametrize("m", [xb.Pr8, xb.Pr9, xb.BS5, xb.Ts5],
+                         ids=lambda m: m.__name__)
+def test_dense_output_at_t_eval_vs_c_oracle(m):
+    """C3: free dense output at t_eval for a mu sweep (Horner of K.T @ P)."""
+    N = 128
+    y0, prm = vdp_lanes(N)
+    prm = np.minimum(prm, 8.0)
+    te = np.linspace(0.0, 20.0, 200)
+    res = to_np(xb.solve_ivp_batched("vanderpol", (0.0, 20.0), y0, m,
+                                     params=prm, t_eval=te, rtol=1e-8,
+                                     atol=1e-10))
+    ref = CO.rk_batch(TABS[m.__name__], "vanderpol", (0.0, 20.0), y0,
+                      params=prm, t_eval=te, rtol=1e-8, atol=1e-10,
+                      n_threads=8)
+    assert (res["n_eval_done"] == te.size).all()
+    same = (res["n_accepted"] == ref["n_accepted"]) & \
+        (res["n_rejected"] == ref["n_rejected"])
+    assert same.mean() >= 0.95
+    assert rel(res["y"][same], ref["y"][same]) <= 1e-7
+    assert np.array_equal(res["y"][:, :, 0], y0)         # t_eval[0] == t0
+
+
+def test_user_tableau_heun_matches_oracle():
+    """docs/Demo_own_RK.ipynb: a user subclass with its own A/B/C/E (no P ->
+    cubic Hermite dense output)."""
+    class Heun(xb.RungeKutta):
+        n_stages = 2
+        order = 2
+        order_secondary = 1
+        C = np.array([0, 1.])
+        A = np.array([[0, 0], [1., 0]])
+        B = np.array([1 / 2, 1 / 2])
+        E = np.array([1., 0, 0])
+        E[:-1] -= B
+
+    class HeunTab:
+        name = "Heun"
+        n_stages, order, order_secondary = 2, 2, 1
+        A, B, C, E = Heun.A, Heun.B, Heun.C, Heun.E
+        P = None
+        sc_params = "standard"
+    msd = rhs_for("mass_spring_damper")
+    te = np.linspace(0, 16, 33)
+    r = to_np(xb.solve_ivp_batched(msd, (0.0, 16.0), [[0.0, -1.0]], Heun,
+                                   atol=0.05, t_eval=te))
+    from oracle.problems import mass_spring_damper
+    ref = CO.rk_batch(HeunTab, None, (0.0, 16.0), [[0.0, -1.0]], atol=0.05,
+                      t_eval=te, user_fn=mass_spring_damper)
+    # docs/Demo_own_RK.ipynb:103-104: 29 points, 61 evaluations
+    assert (ref["n_accepted"][0] + 1, ref["nfev"][0]) == (29, 61)
+    assert (r["n_accepted"][0], r["n_rejected"][0], r["nfev"][0]) == \
+        (ref["n_accepted"][0], ref["n_rejected"][0], ref["nfev"][0])
+    assert rel(r["y"][0], ref["y"][0]) <= 1e-12
+    assert rel(r["y_final"][0], ref["y_final"][0]) <= 1e-12
+
+
+def test_nbody32_warp_per_system_vs_c_oracle():
+    """C4 (ii): 32-body softened gravity, n = 192, one warp per system."""
+    rng = np.random.default_rng(2025)
+    N, nb = 6, 32
+    m = rng.uniform(0.5, 1.5, (N, nb))
+    pos = rng.normal(0, 1, (N, nb, 3))
+    vel = rng.normal(0, 0.3, (N, nb, 3))
+    vel -= (m[:, :, None] * vel).sum(1, keepdims=True) / m.sum(1)[:, None, None]
+    y0 = np.concatenate([pos.reshape(N, -1), vel.reshape(N, -1)], axis=1)
+    prm = np.concatenate([np.full((N, 1), 0.05 ** 2), m], axis=1)
+    hs = np.full(20, 0.002)
+    r = to_np(xb.solve_ivp_batched("nbody32", (0.0, 1.0), y0, xb.Ts5,
+                                   params=prm, forced_steps=hs))
+    ref = CO.rk_batch(TABS["Ts5"], "nbody32", (0.0, 1.0), y0, params=prm,
+                      forced_h=hs, n_threads=6)
+    assert rel(r["y_final"], ref["y_final"]) <= 1e-12
+    r = to_np(xb.solve_ivp_batched("nbody32", (0.0, 0.25), y0, xb.Pr8,
+                                   params=prm, rtol=1e-8, atol=1e-10))
+    ref = CO.rk_batch(TABS["Pr8"], "nbody32", (0.0, 0.25), y0, params=prm,
+                      rtol=1e-8, atol=1e-10, n_threads=6)
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["n_accepted"], ref["n_accepted"])
+    assert np.array_equal(r["n_rejected"], ref["n_rejected"])
+    assert rel(r["y_final"], ref["y_final"]) <= 1e-7
+
+
+# ---- ensemble-scale, size-independent properties ----------------------------
+def test_large_ensemble_properties_and_queue_refill():
+    """200k lanes (more than the resident lane slots, so the work queue
+    refills): every lane finishes exactly at t_bound, results are independent
+    of the lane's position in the batch (permutation invariance, bit-exact),
+    and a sample agrees with the C oracle."""
+    N = 200_000
+    y0, prm = lorenz_lanes(N, seed=7)
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5,
+                                   params=prm, rtol=1e-8, atol=1e-10))
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["t_final"], np.full(N, 1.0))
+    perm = np.random.default_rng(1).permutation(N)
+    r2 = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0[perm], xb.Ts5,
+                                    params=prm[perm], rtol=1e-8, atol=1e-10))
+    assert np.array_equal(r2["y_final"], r["y_final"][perm])
+    assert np.array_equal(r2["n_accepted"], r["n_accepted"][perm])
+    assert np.array_equal(r2["nfev"], r["nfev"][perm])
+    # nfev bookkeeping identity for an FSAL method: 1 + 4 (h_start) + 6/attempt
+    assert np.array_equal(r["nfev"],
+                          5 + 6 * (r["n_accepted"] + r["n_rejected"]))
+    idx = np.arange(0, N, 997)
+    ref = CO.rk_batch(TABS["Ts5"], "lorenz63", (0.0, 1.0), y0[idx],
+                      params=prm[idx], rtol=1e-8, atol=1e-10, n_threads=8)
+    assert (r["n_accepted"][idx] == ref["n_accepted"]).mean() >= 0.99
+    assert rel(r["y_final"][idx], ref["y_final"]) <= 1e-7
+
+
+def test_forward_then_backward_round_trip():
+    """Integrate forward, then backward from the end state: returns to y0
+    within the tolerance (exercises direction = -1 at ensemble scale)."""
+    N = 4096
+    y0, prm = lorenz_lanes(N, seed=3)
+    f = xb.solve_ivp_batched("lorenz63", (0.0, 0.5), y0, xb.Pr8, params=prm,
+                             rtol=1e-10, atol=1e-12)
+    b = to_np(xb.solve_ivp_batched("lorenz63", (0.5, 0.0), f.y_final.contiguous(),
+                                   xb.Pr8, params=prm, rtol=1e-10, atol=1e-12))
+    assert (b["status"] == 0).all()
+    assert np.abs(b["y_final"] - y0).max() <= 1e-6

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: tableau classes (same attribute protocol and
+algebraic properties the reference checks in tests/test_rk.py:14-72), argument
+validation with the reference's exception types/messages, and ensemble
+sharding over ranks (gloo, world_size 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import extensisq_b200 as xb
+from extensisq_b200 import batched
+
+METHODS = [xb.Ts5, xb.BS5, xb.CK5, xb.Me4, xb.Pr7, xb.Pr8, xb.Pr9, xb.CFMR7osc]
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_coefficient_properties(m):
+    # reference tests/test_rk.py:45-72
+    s = m.n_stages
+    assert m.A.shape == (s, s) and m.B.shape == (s,) and m.C.shape == (s,)
+    assert m.E.shape == (s + 1,) and m.P.shape[0] == s + 1
+    assert abs(m.B.sum() - 1) < 1e-15
+    assert abs(m.E.sum()) < 1e-15
+    assert np.all(np.abs(m.A.sum(axis=1) - m.C) < 1e-13)
+    assert np.all(np.triu(m.A) == 0)
+    # interpolant continuity, same formulation/tolerances as the reference
+    Ps = m.P.sum(axis=1)                       # C0 end
+    Ps[:s] -= m.B
+    assert np.all(np.abs(Ps) < 1e-12)
+    Ps = m.P.sum(axis=0)                       # C1 start
+    Ps[0] -= 1
+    assert np.all(np.abs(Ps) < 1e-12)
+    dPs = (m.P * (np.arange(m.P.shape[1]) + 1)).sum(axis=1)   # C1 end
+    dPs[-1] -= 1
+    assert np.all(np.abs(dPs) < 2e-12)
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_low_order_conditions(m):
+    """Order conditions up to order 4 for (B, C, A) and for the embedded
+    weights B + E[:-1] up to its own order (cf. tests/test_rk.py:14-42)."""
+    A, C = m.A, m.C
+    for b, order in ((m.B, m.order), (m.B + m.E[:-1], m.order_secondary)):
+        if m.E[-1] != 0 and b is not m.B:
+            continue            # FSAL pairs use the extra stage; checked on GPU
+        tol = m.n_stages * 1e-14
+        conds = [(b.sum(), 1.0)]
+        if order >= 2:
+            conds.append((b @ C, 1 / 2))
+        if order >= 3:
+            conds += [(b @ C**2, 1 / 3), (b @ (A @ C), 1 / 6)]
+        if order >= 4:
+            conds += [(b @ C**3, 1 / 4), (b @ (C * (A @ C)), 1 / 8),
+                      (b @ (A @ C**2), 1 / 12), (b @ (A @ (A @ C)), 1 / 24)]
+        for got, want in conds:
+            assert abs(got - want) < tol
+
+
+def test_class_attributes_are_read_only_and_named_like_the_reference():
+    assert [m.__name__ for m in METHODS] == ["Ts5", "BS5", "CK5", "Me4",
+                                             "Pr7", "Pr8", "Pr9", "CFMR7osc"]
+    assert xb.Ts5.sc_params == "G" and xb.Pr7.sc_params == "S"
+    assert xb.BS5.sc_params == "standard" and xb.BS5.n_extra_stages == 3
+    assert (xb.Pr9.n_stages, xb.Pr9.order, xb.Pr9.order_secondary) == (17, 9, 7)
+    with pytest.raises(ValueError):
+        xb.Ts5.A[1, 0] = 0.0
+
+
+def test_user_tableau_validation():
+    class Bad(xb.RungeKutta):
+        n_stages = 2
+        order, order_secondary = 2, 1
+        A = np.array([[0, 1.0], [1.0, 0]])
+        B = np.array([0.5, 0.5])
+        C = np.array([0, 1.0])
+        E = np.array([0.5, -0.5, 0])
+    with pytest.raises(ValueError, match="lower triangular"):
+        Bad.validate()
+
+
+def test_sc_params_parsing():
+    assert batched._sc_tuple("G") == (0.7, -0.4, 0.0, 0.9)
+    assert batched._sc_tuple((0.6, -0.25, 0.1, 0.85)) == (0.6, -0.25, 0.1, 0.85)
+    with pytest.raises(ValueError, match="sc_params should be a tuple"):
+        batched._sc_tuple("W")
+
+
+def test_shard_bounds_cover_all_lanes():
+    for n, w in ((10, 3), (7, 8), (10_000_000, 8), (0, 2), (5, 1)):
+        spans = [xb.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and b >= a
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        xb.shard_bounds(4, 2, 2)
+
+
+def _gather_worker(rank, world, port, n_lanes, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = xb.shard_bounds(n_lanes, rank, world)
+    mine = dict(y_final=torch.arange(lo, hi, dtype=torch.float64)[:, None]
+                * torch.ones(1, 3, dtype=torch.float64),
+                n_accepted=torch.arange(lo, hi, dtype=torch.int32))
+    full = xb.gather_result(mine, n_lanes)
+    ok = (torch.equal(full["n_accepted"],
+                      torch.arange(n_lanes, dtype=torch.int32))
+          and full["y_final"].shape == (n_lanes, 3)
+          and torch.equal(full["y_final"][:, 1],
+                          torch.arange(n_lanes, dtype=torch.float64)))
+    root = xb.gather_result(mine, n_lanes, dst=0)
+    ok = ok and ((root["n_accepted"] is not None) == (rank == 0))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gather_result_world_size_2_gloo():
+    """The N>1 path: lanes are sharded, no data-path collective, one final
+    gather."""
+    world, n_lanes = 2, 11
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        port = 29500 + (os.getpid() % 2000)
+        mp.spawn(_gather_worker, args=(world, port, n_lanes, out),
+                 nprocs=world, join=True)
+        assert out[0] and out[1]
