@@ -153,9 +153,10 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         return XSQ_ERR_ARG;
     }
     if (a->n_lanes < 0) { g_detail = "n_lanes < 0"; return XSQ_ERR_ARG; }
-    if (!a->y0 || !a->t_final || !a->y_final || !a->n_accepted ||
-        !a->n_rejected || !a->nfev || !a->status ||
-        (np > 0 && !a->params)) {
+    if (a->n_lanes > 0 &&
+        (!a->y0 || !a->t_final || !a->y_final || !a->n_accepted ||
+         !a->n_rejected || !a->nfev || !a->status ||
+         (np > 0 && !a->params))) {
         g_detail = "required pointer is NULL";
         return XSQ_ERR_ARG;
     }
@@ -182,7 +183,8 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         g_detail = "`first_step` exceeds bounds.";
         return XSQ_ERR_ARG;
     }
-    if (a->n_eval < 0 || (a->n_eval > 0 && (!a->t_eval || !a->y_eval))) {
+    if (a->n_eval < 0 ||
+        (a->n_eval > 0 && a->n_lanes > 0 && (!a->t_eval || !a->y_eval))) {
         g_detail = "t_eval / y_eval inconsistent";
         return XSQ_ERR_ARG;
     }
@@ -199,6 +201,7 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     P->minalpha = -sc[2];
     P->safety = sc[3];
     P->safety_sc = std::pow(sc[3], sc[0] + sc[1]);
+    P->log2n = std::log2((double)ns);
     P->n_lanes = a->n_lanes;
     P->y0 = a->y0;
     P->params = a->params;

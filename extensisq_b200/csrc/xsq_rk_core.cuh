@@ -58,7 +58,7 @@ struct RkDev {
     const double* atol_dev;       // [n_state], used by warp-per-system kernels
     double first_step, max_step;
     double err_exp, minbeta1, minbeta2, minalpha, safety, safety_sc;
-    double h_min_a;               // user tableaux; built-ins use Tab::H_MIN_A
+    double log2n;                 // log2(n_state), for log2(error_norm)
     const double* t_eval;
     double* y_eval;
     const double* h_forced;
@@ -91,6 +91,76 @@ __device__ __forceinline__ double sys_min(double x) {
             x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
     }
     return x;
+}
+
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (5 fp64-pipe slots
+// instead of ~11 for the IEEE-exact division; x is a scale >= atol > 0).
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// Python's built-in max(a, b) / min(a, b): "b if b > a else a".  A plain
+// compare-and-select (3 instructions); fmax()/fmin() cost ~8 on sm_100 because
+// of their NaN rules, and these are the reference's semantics anyway.
+__device__ __forceinline__ double pymax(double a, double b) { return b > a ? b : a; }
+__device__ __forceinline__ double pymin(double a, double b) { return b < a ? b : a; }
+
+// ---- log2 / exp2 for the step-size controller -------------------------------
+// error_norm ** x  (common.py:257, 264-266, 281) is evaluated as
+// exp2(x * log2(error_norm)).  |x| <= 0.25, so plain double-precision log2 and
+// exp2 (each ~1 ulp) give the factor to ~2 ulp, the accuracy class of pow().
+// Coefficients sit in __constant__ memory so each one is a c[bank][offset]
+// operand of its DFMA.  Rare inputs (0, subnormal, Inf, NaN, |z| >= 1000) take
+// the libdevice routines.
+static __constant__ double c_xsq_lg[7] = {   // fdlibm e_log.c Lg1..Lg7
+    6.666666666666735130e-01, 3.999999999940941908e-01,
+    2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01,
+    1.479819860511658591e-01};
+static __constant__ double c_xsq_e2[14] = {  // ln(2)^k / k!
+    0x1.0000000000000p+0, 0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3,
+    0x1.c6b08d704a0c0p-5, 0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10,
+    0x1.430912f86c787p-13, 0x1.ffcbfc588b0c7p-17, 0x1.62c0223a5c824p-20,
+    0x1.b5253d395e7c4p-24, 0x1.e4cf5158b8ecap-28, 0x1.e8cac7351bb25p-32,
+    0x1.c3bd650fc2986p-36, 0x1.816193166d0f9p-40};
+static __constant__ double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
+                                            0x1.8p52};              // rint magic
+
+__device__ __forceinline__ double log2_fast(double x) {
+    const int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log2(x);
+    int e = (hi >> 20) - 1023;
+    int mhi = (hi & 0x000fffff) | 0x3ff00000;
+    if (mhi >= 0x3ff6a09f) {            // m in [sqrt(1/2), sqrt(2))
+        mhi -= 0x00100000;
+        ++e;
+    }
+    const double f = __hiloint2double(mhi, __double2loint(x)) - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s;
+    double r = c_xsq_lg[6];
+#pragma unroll
+    for (int k = 5; k >= 0; --k) r = fma(r, z, c_xsq_lg[k]);
+    r *= z;
+    const double hfsq = 0.5 * f * f;
+    const double lg = f - (hfsq - s * (hfsq + r));      // ln(1 + f)
+    return fma(lg, c_xsq_misc[0], (double)e);
+}
+
+__device__ __forceinline__ double exp2_fast(double z) {
+    if (!(fabs(z) < 1000.0)) return exp2(z);
+    const double t = z + c_xsq_misc[1];
+    const int n = __double2loint(t);
+    const double r = z - (t - c_xsq_misc[1]);           // |r| <= 1/2, exact
+    double p = c_xsq_e2[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = fma(p, r, c_xsq_e2[k]);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
 // RMS norm, common.py:64-66
@@ -215,9 +285,12 @@ struct Lane {
     static constexpr int KROWS = (Tab::VARIANT == tab::BS5V) ? S + 4 : S + 1;
 
     long long sys;          // trajectory index
-    double t, h_abs, h_prev, err_old, max_factor, min_step;
+    double t, h_abs, h_prev, lerr_old, max_factor, min_step;  // lerr_old = log2(error_norm_old)
     double y[NL], f[NL], prm[R::NPL];
-    int n_acc, n_rej, nfev, ieval, attempts;
+    // nfev holds only the evaluations made outside the hot loop (f0, h_start,
+    // BS5 extra stages); the per-attempt evaluations are added in store() from
+    // the step counters, so the hot loop maintains no evaluation counter.
+    int n_acc, n_rej, n_pre, nfev, ieval;
     bool standard_sc, fresh, step_rejected;
 
     // RungeKutta.__init__, common.py:187-220
@@ -229,7 +302,7 @@ struct Lane {
         for (int k = 0; k < NL; ++k)
             y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
-        n_acc = n_rej = ieval = attempts = 0;
+        n_acc = n_rej = n_pre = ieval = 0;
         nfev = 1;
         R::f(t, y, prm, f);
         standard_sc = true;
@@ -237,7 +310,7 @@ struct Lane {
         step_rejected = false;
         max_factor = kMaxFactor0;
         h_prev = 0.0;
-        err_old = 0.0;
+        lerr_old = 0.0;
         min_step = 0.0;
         if (P.n_forced > 0) {
             h_abs = P.h_forced[0];
@@ -253,15 +326,15 @@ struct Lane {
 
     // _reassess_stepsize, common.py:310-331
     __device__ __forceinline__ void reassess(const RkDev& P) {
-        min_step = fmax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+        min_step = pymax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
         if (h_abs < min_step || h_abs > P.max_step) {
-            h_abs = fmin(P.max_step, fmax(min_step, h_abs));
+            h_abs = pymin(P.max_step, pymax(min_step, h_abs));
             standard_sc = true;
         }
         const double d = fabs(P.t_bound - t);
         if (d < 2.0 * h_abs) {
             if (d > h_abs) {
-                h_abs = fmax(0.5 * d, min_step);
+                h_abs = pymax(0.5 * d, min_step);
                 standard_sc = true;
             } else {
                 h_abs = d;
@@ -279,15 +352,15 @@ struct Lane {
             bool first = true;
 #pragma unroll
             for (int j = 0; j < I; ++j) {
-                const double a = Tab::a(I, j);
-                if (a != 0.0) {
+                if (Tab::a(I, j) != 0.0) {     // structure: compile time
+                    const double a = Tab::av(I, j);   // value: constant bank
                     acc = first ? a * K[j][c] : fma(a, K[j][c], acc);
                     first = false;
                 }
             }
             ys[c] = fma(h, acc, y[c]);
         }
-        R::f(__dadd_rn(t, __dmul_rn(Tab::c(I), h)), ys, prm, K[I]);
+        R::f(__dadd_rn(t, __dmul_rn(Tab::cv(I), h)), ys, prm, K[I]);
     }
     template <int I, int END>
     __device__ __forceinline__ void stages(double (&K)[KROWS][NL], double h) {
@@ -297,25 +370,24 @@ struct Lane {
         }
     }
 
-    // err_norm of  h * sum_i w_i K_i  against scale(y, y_ref)
-    __device__ __forceinline__ double scaled_norm(
+    // sum_c (err_c / scale_c)^2 with scale = atol + rtol*max(|y|,|y_ref|)
+    // (common.py:57-61, 338-339).  The RMS norm is sqrt(ss / n); the kernel
+    // works with ss directly:  error_norm < 1  <=>  ss < n  holds EXACTLY in
+    // IEEE arithmetic (sqrt and the division by n are monotone and correctly
+    // rounded, and every double below n is also below n*(1 - 2^-54)), and
+    // log2(error_norm) = (log2(ss) - log2(n)) / 2 feeds the controller.
+    __device__ __forceinline__ double scaled_ss(
         const RkDev& P, const double (&errv)[NL], const double (&yref)[NL],
         int lane) {
-        double q[NL];
+        double ss = 0.0;
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
-            const double scale = fma(P.rtol, fmax(fabs(y[c]), fabs(yref[c])),
+            const double scale = fma(P.rtol, pymax(fabs(y[c]), fabs(yref[c])),
                                      atol_of<R>(P, c, lane));
-            q[c] = errv[c] / scale;
+            const double q = errv[c] * rcp_fast(scale);
+            ss = fma(q, q, ss);
         }
-        return rms<R>(q);
-    }
-
-    // rejection update shared by all branches, common.py:278-284
-    __device__ __forceinline__ void shrink(const RkDev& P, double err) {
-        step_rejected = true;
-        h_abs *= fmax(kMinFactor, P.safety * pow(err, P.err_exp));
-        ++n_rej;
+        return sys_sum<R::WARP>(ss);
     }
 
     // Dense output over the step just accepted: emit every t_eval point in
@@ -422,8 +494,8 @@ struct Lane {
                 if (k < Tab::NPOL) {
 #pragma unroll
                     for (int i = 0; i <= S; ++i) {
-                        const double p = Tab::p(i, k);
-                        if (p != 0.0) acc = fma(p, K[i][c], acc);
+                        if (Tab::p(i, k) != 0.0)
+                            acc = fma(Tab::pv(i, k), K[i][c], acc);
                     }
                 }
                 Q[k][c] = acc;
@@ -443,12 +515,12 @@ struct Lane {
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < ROW; ++j) {
-                    const double a = Tab::a_extra(R_, j);
-                    if (a != 0.0) acc = fma(a, K[j][c], acc);
+                    if (Tab::a_extra(R_, j) != 0.0)
+                        acc = fma(Tab::a_extrav(R_, j), K[j][c], acc);
                 }
                 ys[c] = fma(acc, h, y[c]);
             }
-            R::f(__dadd_rn(t, __dmul_rn(Tab::c_extra(R_), h)), ys, prm,
+            R::f(__dadd_rn(t, __dmul_rn(Tab::c_extrav(R_), h)), ys, prm,
                  K[ROW]);
             ++nfev;
         }
@@ -466,8 +538,8 @@ struct Lane {
                     if (k < Tab::NPOL_LOW) {
 #pragma unroll
                         for (int i = 0; i <= S + 1; ++i) {
-                            const double p = Tab::plow(i, k);
-                            if (p != 0.0) acc = fma(p, K[i][c], acc);
+                            if (Tab::plow(i, k) != 0.0)
+                                acc = fma(Tab::plowv(i, k), K[i][c], acc);
                         }
                     }
                     Q[k][c] = acc;
@@ -488,7 +560,7 @@ struct Lane {
                 Q[0][c] = K[7][c];
 #define XSQ_KP(col)                                                      \
     _Pragma("unroll") for (int i = 0; i < 11; ++i)                       \
-        kp[i] = __dmul_rn(K[i][c], Tab::pbest(i, col));
+        kp[i] = __dmul_rn(K[i][c], Tab::pbestv(i, col));
 #define A2(a, b) __dadd_rn(a, b)
                 XSQ_KP(1)
                 Q[1][c] = A2(A2(A2(kp[4], A2(A2(kp[5], kp[7]), kp[0])),
@@ -521,19 +593,18 @@ struct Lane {
     // common.py:232-287).  Returns the lane status: LANE_RUNNING, or a final
     // code when the trajectory ends here.
     __device__ __forceinline__ int attempt(const RkDev& P, int lane) {
+        // Forced-step mode shares every instruction of the adaptive path: h
+        // comes from the table instead of reassess(), every step is accepted,
+        // and the controller's h update is overwritten at the next step.
         const bool forced = P.n_forced > 0;
-        if (forced) {
-            h_abs = P.h_forced[n_acc];
-        } else {
-            if (fresh) {
-                reassess(P);
-                step_rejected = false;
-                fresh = false;
-            }
-            if (h_abs < min_step) return LANE_TOO_SMALL;
-            if (attempts >= P.max_steps) return LANE_STEP_BUDGET;
+        if (fresh) {
+            if (forced) h_abs = P.h_forced[n_acc];
+            else reassess(P);
+            step_rejected = false;
+            fresh = false;
         }
-        ++attempts;
+        if (h_abs < min_step) return LANE_TOO_SMALL;      // min_step = 0 if forced
+        if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
         const double h = h_abs * P.direction;
         const double t_new = t + h;
         double K[KROWS][NL];
@@ -543,113 +614,130 @@ struct Lane {
         constexpr bool EARLY = Tab::VARIANT != tab::GENERIC;
         constexpr int NFIRST = EARLY ? S - 1 : S;
         stages<1, NFIRST>(K, h);
-        nfev += NFIRST - 1;
 
+        constexpr double NTOT = (double)R::N;
+        double y_new[NL], errv[NL];
+        double ss;                      // sum of squares of err/scale
+        bool pre_reject = false;
         if constexpr (EARLY) {
             // pre-error from the first S-1 stages: bogacki.py:340-346 uses
             // (B_scale_pre, E_pre), calvo.py:255-261 uses (A[8,:8], E[:8])
-            double ypre[NL], errv[NL];
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
                 double sb = 0.0, se = 0.0;
 #pragma unroll
                 for (int i = 0; i < S - 1; ++i) {
-                    double wb, we;
                     if constexpr (Tab::VARIANT == tab::BS5V) {
-                        wb = Tab::b_scale_pre(i);
-                        we = Tab::e_pre(i);
+                        if (Tab::b_scale_pre(i) != 0.0)
+                            sb = fma(Tab::b_scale_prev(i), K[i][c], sb);
+                        if (Tab::e_pre(i) != 0.0)
+                            se = fma(Tab::e_prev(i), K[i][c], se);
                     } else {
-                        wb = Tab::a(S - 1, i);
-                        we = Tab::e(i);
+                        if (Tab::a(S - 1, i) != 0.0)
+                            sb = fma(Tab::av(S - 1, i), K[i][c], sb);
+                        if (Tab::e(i) != 0.0)
+                            se = fma(Tab::ev(i), K[i][c], se);
                     }
-                    if (wb != 0.0) sb = fma(wb, K[i][c], sb);
-                    if (we != 0.0) se = fma(we, K[i][c], se);
                 }
-                ypre[c] = fma(h, sb, y[c]);
+                y_new[c] = fma(h, sb, y[c]);
                 errv[c] = h * se;
             }
-            const double err_pre = scaled_norm(P, errv, ypre, lane);
-            if (!forced && err_pre > 1.0) {
-                shrink(P, err_pre);
-                return LANE_RUNNING;
+            ss = scaled_ss(P, errv, y_new, lane);
+            // error_norm_pre > 1: certainly when ss exceeds n by a few ulp,
+            // decided with the reference's own expression inside that band
+            pre_reject = !forced && ss > NTOT &&
+                (ss >= NTOT * (1.0 + 0x1.0p-48) || sqrt(ss / NTOT) > 1.0);
+        }
+        if (!pre_reject) {
+            if constexpr (EARLY) stage<S - 1>(K, h);
+            // _comp_sol_err, common.py:341-351
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double sb = 0.0;
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    if (Tab::b(i) != 0.0) sb = fma(Tab::bv(i), K[i][c], sb);
+                }
+                y_new[c] = fma(h, sb, y[c]);
             }
-            stage<S - 1>(K, h);
-            ++nfev;
+            if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double se = 0.0;
+#pragma unroll
+                for (int i = 0; i < S + Tab::FSAL; ++i) {
+                    if (Tab::e(i) != 0.0) se = fma(Tab::ev(i), K[i][c], se);
+                }
+                errv[c] = h * se;
+            }
+            ss = scaled_ss(P, errv, y_new, lane);
         }
 
-        // _comp_sol_err, common.py:341-351
-        double y_new[NL], errv[NL];
-#pragma unroll
-        for (int c = 0; c < NL; ++c) {
-            double sb = 0.0;
-#pragma unroll
-            for (int i = 0; i < S; ++i) {
-                const double b = Tab::b(i);
-                if (b != 0.0) sb = fma(b, K[i][c], sb);
+        double lerr;
+        {
+            // ---- controller, common.py:249-287, evaluated branch-free ------
+            // error_norm**x is exp2(x * log2(error_norm)); accepted and
+            // rejected lanes share ONE exp2 so a warp holding both does not
+            // serialise two pow() calls.
+            const bool accept = forced || (!pre_reject && ss < NTOT);
+            const bool bad = !forced && !pre_reject && !(ss < XSQ_INF);  // NaN/Inf
+            if (Tab::VARIANT == tab::BS5V && bad) {      // bogacki.py:314-315
+                nfev += S - 1 + Tab::FSAL;    // this attempt is in no counter
+                return LANE_OVERFLOW;
             }
-            y_new[c] = fma(h, sb, y[c]);
-        }
-        if constexpr (Tab::FSAL) {
-            R::f(t_new, y_new, prm, K[S]);
-            ++nfev;
-        }
-#pragma unroll
-        for (int c = 0; c < NL; ++c) {
-            double se = 0.0;
-#pragma unroll
-            for (int i = 0; i < S + Tab::FSAL; ++i) {
-                const double e = Tab::e(i);
-                if (e != 0.0) se = fma(e, K[i][c], se);
-            }
-            errv[c] = h * se;
-        }
-        const double err = scaled_norm(P, errv, y_new, lane);
-
-        if (!forced) {
-            if (err < 1.0) {                    // common.py:249-276
-                double factor;
-                if (err < XSQ_SQRT_TINY) {
+            lerr = 0.5 * (log2_fast(ss) - P.log2n);
+            const bool tiny_err = ss < NTOT * 0x1.0p-1022;   // err < sqrt(tiny)
+            const bool second = accept && !standard_sc;
+            double z = second ? fma(P.minbeta2, lerr_old, P.minbeta1 * lerr)
+                              : P.err_exp * lerr;
+            if (P.minalpha != 0.0 && second)
+                z = fma(P.minalpha, log2_fast(h / h_prev), z);
+            double factor = (second ? P.safety_sc : P.safety) * exp2_fast(z);
+            if (accept) {
+                if (tiny_err) {
                     factor = max_factor;
                     standard_sc = true;
                 } else if (standard_sc) {
-                    factor = P.safety * pow(err, P.err_exp);
                     standard_sc = false;
                 } else {
-                    const double h_ratio = h / h_prev;
-                    double fac = pow(err, P.minbeta1);
-                    if (P.minbeta2 != 0.0) fac *= pow(err_old, P.minbeta2);
-                    if (P.minalpha != 0.0) fac *= pow(h_ratio, P.minalpha);
-                    factor = P.safety_sc * fac;
-                    factor = fmin(max_factor, fmax(kMinFactor, factor));
+                    factor = pymin(max_factor, pymax(kMinFactor, factor));
                 }
-                if (step_rejected) factor = fmin(1.0, factor);
+                if (step_rejected) factor = pymin(1.0, factor);
                 h_abs *= factor;
                 if (factor < kMaxFactor) max_factor = kMaxFactor;
             } else {
-                const bool bad = isnan(err) || isinf(err);
-                if (Tab::VARIANT == tab::BS5V && bad)    // bogacki.py:314-315
-                    return LANE_OVERFLOW;
-                shrink(P, err);
+                step_rejected = true;
+                h_abs *= pymax(kMinFactor, factor);
+                ++n_rej;
+                if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
                 return bad ? LANE_OVERFLOW : LANE_RUNNING;   // common.py:286
             }
         }
-        if constexpr (!Tab::FSAL) {             // common.py:289-291
+        if constexpr (!Tab::FSAL)               // common.py:289-291
             R::f(t_new, y_new, prm, K[S]);
-            ++nfev;
-        }
         if (P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
         // common.py:294-303
         h_prev = h;
-        err_old = err;
+        lerr_old = lerr;
         t = t_new;
 #pragma unroll
         for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
         ++n_acc;
         fresh = true;
-        if (forced) return n_acc >= P.n_forced ? LANE_FINISHED : LANE_RUNNING;
         // OdeSolver.step, base.py:207-208
-        return (P.direction * (t - P.t_bound) >= 0.0) ? LANE_FINISHED
-                                                      : LANE_RUNNING;
+        const bool done = forced ? (n_acc >= P.n_forced)
+                                 : (P.direction * (t - P.t_bound) >= 0.0);
+        return done ? LANE_FINISHED : LANE_RUNNING;
+    }
+
+    // RHS evaluations made by attempt(): S-1 stages (+1 if FSAL) per full
+    // attempt, one fewer stage and no FSAL evaluation for a pre-rejected
+    // attempt (bogacki.py:266-275, calvo.py:178-187), and f(t+h, y_new) per
+    // ACCEPTED step for non-FSAL pairs (common.py:289-291).
+    __device__ __forceinline__ int evals_in_loop() const {
+        const int attempts = n_acc + n_rej;
+        return (S - 1 + Tab::FSAL) * (attempts - n_pre) + (S - 2) * n_pre +
+               (Tab::FSAL ? 0 : n_acc);
     }
 
     // `constant`: zero-length span, every t_eval point equals t0 and scipy
@@ -676,7 +764,7 @@ struct Lane {
             if (P.h_next) P.h_next[sys] = h_abs;
             P.n_acc[sys] = n_acc;
             P.n_rej[sys] = n_rej;
-            P.nfev[sys] = nfev;
+            P.nfev[sys] = nfev + evals_in_loop();
             P.status[sys] = st;
             if (P.n_eval_done) P.n_eval_done[sys] = ieval;
         }
@@ -740,13 +828,14 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
             __syncwarp(full);
         }
         if (__all_sync(full, !live)) break;
-        // ---- one attempt ----
-        if (live) {
-            const int st = L.attempt(P, lane);
-            if (st != LANE_RUNNING) {
-                L.store(P, st, lane);
-                live = false;
-            }
+        // ---- attempts, until some lane of the warp ends its trajectory ----
+        int st = LANE_RUNNING;
+        do {
+            if (live) st = L.attempt(P, lane);
+        } while (!__any_sync(full, st != LANE_RUNNING));
+        if (st != LANE_RUNNING) {
+            L.store(P, st, lane);
+            live = false;
         }
         __syncwarp(full);
     }

@@ -4,6 +4,8 @@
 #include "xsq_launch.h"
 #include "xsq_rhs.cuh"
 #include "xsq.h"
+#include <cstdlib>
+#include <string>
 
 #ifndef XSQ_INST_TAB
 #error "compile with -DXSQ_INST_TAB=<tableau>"
@@ -25,31 +27,44 @@ struct Geometry {
         KDOUBLES <= 21 ? 4 : (KDOUBLES <= 36 ? 3 : 2);
 };
 
-template <class Tab, class R>
+template <class Tab, class R, int BLOCK = Geometry<Tab, R>::BLOCK,
+          int MINB = Geometry<Tab, R>::MINB>
 static int launch_one(const RkDev& P, cudaStream_t st, LaunchInfo* info) {
     using G = Geometry<Tab, R>;
-    auto kern = rk_persistent<Tab, R, G::BLOCK, G::MINB>;
+#ifdef XSQ_TUNE
+    // occupancy sweep for profiling builds: XSQ_GEOM=<block>x<CTAs per SM>
+    if (BLOCK == G::BLOCK && MINB == G::MINB) {
+        const char* e = getenv("XSQ_GEOM");
+        const std::string want = e ? e : "";
+#define XSQ_TRY(B, M) if (want == #B "x" #M) return launch_one<Tab, R, B, M>(P, st, info);
+        XSQ_TRY(128, 3) XSQ_TRY(128, 5) XSQ_TRY(32, 16) XSQ_TRY(32, 17)
+        XSQ_TRY(32, 18) XSQ_TRY(32, 19) XSQ_TRY(32, 20) XSQ_TRY(64, 9)
+        XSQ_TRY(64, 10) XSQ_TRY(256, 2)
+#undef XSQ_TRY
+    }
+#endif
+    auto kern = rk_persistent<Tab, R, BLOCK, MINB>;
     int dev = 0, n_sm = 0, occ = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) !=
         cudaSuccess)
         return XSQ_ERR_CUDA;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK,
                                                       0) != cudaSuccess ||
         occ < 1)
         return XSQ_ERR_CUDA;
-    const long long per_block = R::WARP ? G::BLOCK / 32 : G::BLOCK;
-    long long want = (P.n_lanes + per_block - 1) / per_block;
+    const long long per_block = R::WARP ? BLOCK / 32 : BLOCK;
+    long long want_blocks = (P.n_lanes + per_block - 1) / per_block;
     long long grid = (long long)n_sm * occ;          // persistent: fill the GPU
-    if (want < grid) grid = want;
+    if (want_blocks < grid) grid = want_blocks;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, G::BLOCK, 0, st>>>(P);
+    kern<<<(unsigned)grid, BLOCK, 0, st>>>(P);
     count_launch();
     if (info) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, kern);
         info->grid = (int)grid;
-        info->block = G::BLOCK;
+        info->block = BLOCK;
         info->blocks_per_sm = occ;
         info->regs = fa.numRegs;
     }

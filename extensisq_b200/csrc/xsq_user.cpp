@@ -143,26 +143,33 @@ const char* builtin_rhs_name(int rhs) {
     }
 }
 
-void append_table(std::string* s, const char* fn, const char* args,
-                  const std::string& idx, const std::vector<double>& v) {
+// constexpr accessor (structure) + __constant__ image accessor (values), the
+// same pair tools/gen_header.py emits for the built-ins
+void append_table(std::string* images, std::string* s, const char* fn,
+                  const char* args, const std::string& idx,
+                  const std::vector<double>& v) {
     char buf[64];
-    *s += "    XSQ_HD static constexpr double ";
-    *s += fn;
-    *s += "(";
-    *s += args;
-    *s += ") {\n        constexpr double T[" + std::to_string(v.size() ? v.size() : 1) + "] = {";
+    std::string vals;
     for (size_t i = 0; i < v.size(); ++i) {
         std::snprintf(buf, sizeof buf, "%a, ", v[i]);
-        *s += buf;
+        vals += buf;
     }
-    if (v.empty()) *s += "0.0";
-    *s += "};\n        return T[" + idx + "];\n    }\n";
+    if (v.empty()) vals = "0.0";
+    const std::string n = std::to_string(v.size() ? v.size() : 1);
+    *images += std::string("static __constant__ double c_UserTab_") + fn + "[" +
+               n + "] = {" + vals + "};\n";
+    *s += std::string("    XSQ_HD static constexpr double ") + fn + "(" + args +
+          ") {\n        constexpr double T[" + n + "] = {" + vals +
+          "};\n        return T[" + idx + "];\n    }\n";
+    *s += std::string("    __device__ __forceinline__ static double ") + fn +
+          "v(" + args + ") { return c_UserTab_" + fn + "[" + idx + "]; }\n";
 }
 
 // the same struct layout tools/gen_header.py emits for the built-ins
 std::string tableau_source(const xsq_tableau_t& t) {
     const int s = t.n_stages;
-    std::string o = "namespace xsq { namespace tab {\nstruct UserTab {\n";
+    std::string images = "namespace xsq { namespace tab {\n";
+    std::string o = "struct UserTab {\n";
     double cdiff = 1.0;                               // common.py:129-137
     for (int i = 0; i < s; ++i)
         for (int j = 0; j < s; ++j) {
@@ -188,20 +195,20 @@ std::string tableau_source(const xsq_tableau_t& t) {
     std::vector<double> v;
     for (int i = 0; i < s; ++i)
         for (int j = 0; j < s; ++j) v.push_back(t.A[i][j]);
-    append_table(&o, "a", "int i, int j", "i * " + std::to_string(s) + " + j", v);
+    append_table(&images, &o, "a", "int i, int j", "i * " + std::to_string(s) + " + j", v);
     v.assign(t.B, t.B + s);
-    append_table(&o, "b", "int i", "i", v);
+    append_table(&images, &o, "b", "int i", "i", v);
     v.assign(t.C, t.C + s);
-    append_table(&o, "c", "int i", "i", v);
+    append_table(&images, &o, "c", "int i", "i", v);
     v.assign(t.E, t.E + s + 1);
-    append_table(&o, "e", "int i", "i", v);
+    append_table(&images, &o, "e", "int i", "i", v);
     v.clear();
     for (int i = 0; i <= s; ++i)
         for (int k = 0; k < t.n_poly; ++k) v.push_back(t.P[i][k]);
-    append_table(&o, "p", "int i, int k",
+    append_table(&images, &o, "p", "int i, int k",
                  "i * " + std::to_string(t.n_poly > 0 ? t.n_poly : 1) + " + k", v);
     o += "};\n} }\n";
-    return o;
+    return images + o;
 }
 
 std::string rhs_wrapper(const UserRhs& r) {
