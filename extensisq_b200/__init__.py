@@ -6,12 +6,12 @@ Same export names as the reference for the hot-path classes
 Nystrom, sensitivity) is out of scope.
 """
 from .tableaux import (RungeKutta, Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
-                       CFMR7osc, BUILTIN, REFERENCE_VERSION)
+                       CFMR7osc, SWAG, BUILTIN, REFERENCE_VERSION)
 from .batched import (DeviceRHS, BatchedOdeResult, solve_ivp_batched, NFS,
                       update_nfs)
 from .sharding import shard_bounds, gather_result
 
 __version__ = "0.1.0"
 __all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "Me4", "Pr7", "Pr8", "Pr9",
-           "CFMR7osc", "DeviceRHS", "BatchedOdeResult", "solve_ivp_batched",
+           "CFMR7osc", "SWAG", "DeviceRHS", "BatchedOdeResult", "solve_ivp_batched",
            "NFS", "update_nfs", "shard_bounds", "gather_result"]

@@ -34,7 +34,7 @@ EXPORTS = [
     "xsq_abi_version", "xsq_strerror", "xsq_last_error_detail",
     "xsq_device_info", "xsq_tableau_load", "xsq_tableau_get",
     "xsq_rhs_builtin", "xsq_rhs_register_source", "xsq_user_compile_check",
-    "xsq_rk_solve", "xsq_rk_solve_host", "xsq_launch_count", "xsq_fp64_peak",
+    "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve", "xsq_launch_count", "xsq_fp64_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -112,6 +112,7 @@ def load():
     lib.xsq_user_compile_check.argtypes = [C.c_int32, C.c_int32]
     lib.xsq_rk_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_void_p]
     lib.xsq_rk_solve_host.argtypes = [C.POINTER(XsqRkArgs), C.c_int]
+    lib.xsq_swag_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_int32, C.c_void_p]
     lib.xsq_launch_count.restype = C.c_int64
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .tableaux import RungeKutta
+from .tableaux import RungeKutta, SWAG
 
 __all__ = ["DeviceRHS", "BatchedOdeResult", "solve_ivp_batched", "NFS"]
 
@@ -139,8 +139,9 @@ def _sc_tuple(sc_params):
 
 def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                       rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf,
-                      sc_params=None, interpolant=None, max_steps=None,
-                      forced_steps=None, device=None, stream=None,
+                      sc_params=None, interpolant=None, k_max=None,
+                      max_steps=None, forced_steps=None, device=None,
+                      stream=None,
                       **extraneous):
     """Integrate N independent systems ``y' = fun(t, y; params_i)``.
 
@@ -155,6 +156,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     rtol : float;  atol : float or [n];  first_step, max_step : float
     sc_params : "G" | "S" | "standard" | (kb1, kb2, a, g)
     interpolant : BS5 only, 'best' | 'low' | 'free' (bogacki.py:217)
+    k_max : SWAG only, maximum order 1..12 (shampine.py:99-103)
     max_steps : attempted-step budget per lane (GPU safety net, no reference
         analogue)
     forced_steps : [k] sequence of |h|; takes exactly these steps, accepting
@@ -178,9 +180,21 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         raise TypeError("`fun` must be a DeviceRHS or the name of a built-in "
                         "right-hand side; Python callables cannot run on the "
                         "device")
-    if not (isinstance(method, type) and issubclass(method, RungeKutta)):
-        raise ValueError("`method` must be one of the tableau classes or a "
-                         "RungeKutta subclass")
+    is_swag = isinstance(method, type) and issubclass(method, SWAG)
+    if not (isinstance(method, type) and
+            (issubclass(method, RungeKutta) or is_swag)):
+        raise ValueError("`method` must be one of the tableau classes, SWAG or "
+                         "a RungeKutta subclass")
+    if is_swag:
+        k_max = method.k_max if k_max is None else k_max
+        if not (isinstance(k_max, int) and 0 < k_max < 13):  # shampine.py:102
+            raise ValueError("`k_max` should be an integer between 1 and 12.")
+        if forced_steps is not None or sc_params is not None or \
+                interpolant is not None:
+            raise ValueError("forced_steps / sc_params / interpolant do not "
+                             "apply to SWAG")
+    elif k_max is not None:
+        raise ValueError("`k_max` only applies to SWAG")
     if device is None:
         device = (y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda
                   else torch.device("cuda", torch.cuda.current_device()))
@@ -256,7 +270,9 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                 raise ValueError("`forced_steps` must be a non-empty 1-D "
                                  "sequence")
 
-        if method._xsq_method is None:
+        if is_swag:
+            mid = 0
+        elif method._xsq_method is None:
             _upload_user_tableau(method)
             mid = _lib.XSQ_METHOD_USER
         else:
@@ -308,7 +324,12 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         a.status = status.data_ptr()
         a.n_eval_done = n_done.data_ptr() if n_eval else None
         st = stream if stream is not None else torch.cuda.current_stream(device)
-        _lib.check(lib.xsq_rk_solve(C.byref(a), C.c_void_p(st.cuda_stream)))
+        if is_swag:
+            _lib.check(lib.xsq_swag_solve(C.byref(a), k_max,
+                                          C.c_void_p(st.cuda_stream)))
+        else:
+            _lib.check(lib.xsq_rk_solve(C.byref(a),
+                                        C.c_void_p(st.cuda_stream)))
         # the kernel runs on `st`; tensors above stay referenced by the result
 
     res = BatchedOdeResult(

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters,
 static int dispatch(int method, int rhs, const RkDev& P, cudaStream_t st,
                     LaunchInfo* info) {
     if (rhs >= XSQ_RHS_USER_BASE) return user_rk_launch(method, rhs, P, st);
+    if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
     switch (method) {
         case XSQ_TS5: return launch_Ts5(rhs, P, st, info);
         case XSQ_BS5: return launch_BS5(rhs, P, st, info);
@@ -137,7 +138,9 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         g_detail = "xsq_rk_args_t.struct_size mismatch";
         return XSQ_ERR_ARG;
     }
-    if (a->method == XSQ_METHOD_USER) {
+    if (a->method == XSQ_METHOD_SWAG) {
+        *mi = MethodInfo{1, 1, 1, 0, 0, {1.0, 0.0, 0.0, 0.9}};
+    } else if (a->method == XSQ_METHOD_USER) {
         if (!user_tableau_info(mi)) {
             g_detail = "no user tableau loaded";
             return XSQ_ERR_ARG;
@@ -224,7 +227,7 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         g_detail = "interpolant should be one of: 'best', 'low', 'free'";
         return XSQ_ERR_ARG;
     }
-    P->interpolant = ip;
+    P->interpolant = (a->method == XSQ_METHOD_SWAG) ? a->reserved0 : ip;
     P->t_final = a->t_final;
     P->y_final = a->y_final;
     P->h_next = a->h_next;
@@ -339,6 +342,22 @@ int xsq_rhs_builtin(const char* name, int32_t* rhs_out, int32_t* n_state,
 
 int xsq_rk_solve(const xsq_rk_args_t* args, void* stream) {
     return solve_device(args, (cudaStream_t)stream, nullptr);
+}
+
+int xsq_swag_solve(const xsq_swag_args_t* args, int32_t k_max, void* stream) {
+    if (!args) return XSQ_ERR_ARG;
+    if (k_max < 1 || k_max > 12) {          // shampine.py:102-103
+        g_detail = "`k_max` should be an integer between 1 and 12.";
+        return XSQ_ERR_ARG;
+    }
+    xsq_rk_args_t a = *args;
+    a.method = XSQ_METHOD_SWAG;
+    a.interpolant = XSQ_INTERP_FREE;
+    a.use_sc_params = 0;
+    a.h_forced = nullptr;
+    a.n_forced = 0;
+    a.reserved0 = k_max;
+    return solve_device(&a, (cudaStream_t)stream, nullptr);
 }
 
 int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {

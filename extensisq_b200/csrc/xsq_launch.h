@@ -22,6 +22,8 @@ XSQ_DECL_LAUNCH(Pr9)
 XSQ_DECL_LAUNCH(CFMR7osc)
 #undef XSQ_DECL_LAUNCH
 
+int launch_swag(int rhs, const RkDev& P, cudaStream_t st);
+
 void count_launch();
 
 }  // namespace xsq

@@ -1,0 +1,42 @@
+// Instantiates swag_persistent<Rhs> for the built-in right-hand sides and
+// provides launch_swag(), called by xsq_swag_solve (xsq_api.cu).
+#include "xsq_launch.h"
+#include "xsq_swag_core.cuh"
+#include "xsq_rhs.cuh"
+#include "xsq.h"
+
+namespace xsq {
+
+template <class R>
+static int launch_swag_one(const RkDev& P, cudaStream_t st) {
+    constexpr int BLOCK = 128, MINB = 2;
+    auto kern = swag_persistent<R, BLOCK, MINB>;
+    int dev = 0, n_sm = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) !=
+        cudaSuccess)
+        return XSQ_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, 0) !=
+            cudaSuccess || occ < 1)
+        return XSQ_ERR_CUDA;
+    const long long per_block = R::WARP ? BLOCK / 32 : BLOCK;
+    long long want = (P.n_lanes + per_block - 1) / per_block;
+    long long grid = (long long)n_sm * occ;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, BLOCK, 0, st>>>(P);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+}
+
+int launch_swag(int rhs, const RkDev& P, cudaStream_t st) {
+    switch (rhs) {
+        case XSQ_RHS_LORENZ63: return launch_swag_one<rhs::Lorenz63>(P, st);
+        case XSQ_RHS_VANDERPOL: return launch_swag_one<rhs::VanDerPol>(P, st);
+        case XSQ_RHS_ARENSTORF: return launch_swag_one<rhs::Arenstorf>(P, st);
+        case XSQ_RHS_NBODY32: return launch_swag_one<rhs::NBody32>(P, st);
+        default: return XSQ_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace xsq

@@ -287,7 +287,12 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
 int user_build_source(int method, int rhs, std::string* src, std::string* key) {
     std::string tabname, rhsname, body = "#include \"xsq_rk_core.cuh\"\n";
     int s = 0, nl = 0;
-    if (method == XSQ_METHOD_USER) {
+    const bool swag = method == XSQ_METHOD_SWAG;
+    if (swag) {
+        body += "#include \"xsq_swag_core.cuh\"\n";
+        *key = "SWAG";
+        s = 17;
+    } else if (method == XSQ_METHOD_USER) {
         if (!g_tab.loaded) { set_detail("no user tableau loaded"); return XSQ_ERR_ARG; }
         body += g_tab.src;
         tabname = "UserTab";
@@ -320,11 +325,18 @@ int user_build_source(int method, int rhs, std::string* src, std::string* key) {
         *key += std::string("/") + n;
     }
     char buf[512];
-    std::snprintf(buf, sizeof buf,
-                  "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
-                  "xsq_user_kernel(const xsq::RkDev P) {\n"
-                  "    xsq::rk_persistent_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
-                  minb_for(s, nl), tabname.c_str(), rhsname.c_str());
+    if (swag)
+        std::snprintf(buf, sizeof buf,
+                      "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
+                      "xsq_user_kernel(const xsq::RkDev P) {\n"
+                      "    xsq::swag_persistent_body<xsq::rhs::%s>(P);\n}\n",
+                      rhsname.c_str());
+    else
+        std::snprintf(buf, sizeof buf,
+                      "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
+                      "xsq_user_kernel(const xsq::RkDev P) {\n"
+                      "    xsq::rk_persistent_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
+                      minb_for(s, nl), tabname.c_str(), rhsname.c_str());
     *src = body + buf;
     return XSQ_OK;
 }

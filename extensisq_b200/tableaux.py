@@ -114,3 +114,13 @@ del _raw, _fh, _n, _c
 
 BUILTIN = {c.__name__: c for c in (Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
                                    CFMR7osc)}
+
+
+class SWAG:
+    """Variable-order (1..12) Adams-Bashforth-Moulton PECE of Shampine, Gordon
+    and Watts; reference ``extensisq/shampine.py:10-495``.  Like the tableau
+    classes this is the method *description* handed to ``solve_ivp_batched``
+    (``method=SWAG``, option ``k_max``); the stepping runs in the
+    ``swag_persistent`` CUDA kernel."""
+    k_max = 12
+    _xsq_method = 200

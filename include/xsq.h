@@ -61,7 +61,8 @@ typedef enum xsq_lane_status {
 typedef enum xsq_method {
     XSQ_TS5 = 0, XSQ_BS5 = 1, XSQ_CK5 = 2, XSQ_ME4 = 3,
     XSQ_PR7 = 4, XSQ_PR8 = 5, XSQ_PR9 = 6, XSQ_CFMR7OSC = 7,
-    XSQ_METHOD_USER = 100
+    XSQ_METHOD_USER = 100,
+    XSQ_METHOD_SWAG = 200   /* internal tag used by xsq_swag_solve */
 } xsq_method;
 
 /* Built-in right-hand sides (the reference takes a Python callable `fun`,
@@ -175,6 +176,16 @@ int xsq_rk_solve(const xsq_rk_args_t* args, void* stream);
  * the solve happen inside the call, which returns when the results are in the
  * host buffers. */
 int xsq_rk_solve_host(const xsq_rk_args_t* args, int device);
+
+/* Batched SWAG solve (Shampine-Gordon-Watts variable-order Adams PECE):
+ * replaces solve_ivp(fun, t_span, y0, method=SWAG, t_eval=..., k_max=...)
+ * i.e. SWAG.__init__/_step_impl (shampine.py:99-480) and SwagDenseOutput
+ * (shampine.py:498-587).  Same argument block as the RK solve; the fields
+ * method, interpolant, use_sc_params, sc_params, h_forced and n_forced are
+ * ignored.  n_rejected receives the failed-step count (the reference's NFS).
+ * 1 <= k_max <= 12 (shampine.py:102-103). */
+typedef xsq_rk_args_t xsq_swag_args_t;
+int xsq_swag_solve(const xsq_swag_args_t* args, int32_t k_max, void* stream);
 
 /* Kernel-launch bookkeeping for benchmarks: number of kernels this library
  * launched since the last reset. */

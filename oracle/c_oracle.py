@@ -164,3 +164,55 @@ def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
     return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
                 h_next=h_next, n_accepted=n_acc, n_rejected=n_rej, nfev=nfev,
                 status=status, n_eval_done=n_done)
+
+
+def swag_batch(rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
+               first_step=None, max_step=np.inf, k_max=12, t_eval=None,
+               max_steps=0, n_threads=1, user_fn=None):
+    """Integrate N lanes with the C restatement of SWAG
+    (oracle/xsq_oracle_swag.c).  Same conventions as rk_batch."""
+    lib = load()
+    y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, dtype=float)))
+    N, n = y0.shape
+    rtol_v, atol_v = O.validate_tol(float(rtol), atol, y0[0])
+    atol_v = np.ascontiguousarray(np.broadcast_to(atol_v, (n,)), dtype=float)
+    if params is not None:
+        params = np.ascontiguousarray(np.asarray(params, dtype=float))
+        if params.ndim == 1:
+            params = params.reshape(N, -1)
+        p = params.shape[1]
+    else:
+        p = 0
+    te = (np.ascontiguousarray(np.asarray(t_eval, dtype=float))
+          if t_eval is not None else None)
+    n_eval = te.size if te is not None else 0
+    y_eval = np.empty((N, n, n_eval)) if n_eval else None
+    t_final = np.empty(N)
+    y_final = np.empty((N, n))
+    ints = [np.empty(N, np.int32) for _ in range(6)]
+    n_acc, n_fail, nfev, status, n_done, k_final = ints
+    if rhs is not None:
+        rid, cb = RHS_IDS[rhs], RHS_FN()
+    else:
+        rid = -1
+
+        def _cb(tt, yp, pp, dyp):
+            out = np.asarray(user_fn(tt, np.ctypeslib.as_array(yp, (n,))),
+                             dtype=float)
+            for i in range(n):
+                dyp[i] = out[i]
+        cb = RHS_FN(_cb)
+    rc = lib.xsq_oracle_swag_batch(
+        C.c_int(rid), cb, C.c_int(n), C.c_int(p), C.c_int64(N), _dp(y0),
+        _dp(params), C.c_double(t_span[0]), C.c_double(t_span[1]),
+        C.c_double(float(rtol_v)), _dp(atol_v),
+        C.c_double(first_step if first_step is not None else 0.0),
+        C.c_double(max_step), C.c_int(k_max), _dp(te), C.c_int(n_eval),
+        _dp(y_eval), C.c_int(max_steps), _dp(t_final), _dp(y_final),
+        _ip(n_acc), _ip(n_fail), _ip(nfev), _ip(status), _ip(n_done),
+        _ip(k_final), C.c_int(n_threads))
+    if rc != 0:
+        raise RuntimeError("xsq_oracle_swag_batch failed")
+    return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
+                n_accepted=n_acc, n_rejected=n_fail, nfev=nfev, status=status,
+                n_eval_done=n_done, k_final=k_final)

@@ -561,3 +561,19 @@ int xsq_oracle_max_threads(void) {
 }
 
 size_t xsq_oracle_tab_size(void) { return sizeof(otab_t); }
+
+/* ---- shared with the SWAG / RKC restatements (other translation units) ---- */
+rhs_fn xsq_oracle_builtin_rhs(int id) { return builtin_rhs(id); }
+
+double xsq_oracle_h_start(rhs_fn f, const double* prm, int n, double a, double b,
+                          const double* y, const double* yprime, int morder,
+                          double rtol, const double* atol, int* nfev) {
+    lane_t* L = (lane_t*)malloc(sizeof(lane_t));
+    L->f = f; L->prm = prm; L->n = n; L->rtol = rtol; L->atol = atol; L->nfev = 0;
+    memcpy(L->y, y, sizeof(double) * n);
+    memcpy(L->fcur, yprime, sizeof(double) * n);
+    const double h = h_start(L, a, b, morder);
+    *nfev += L->nfev;
+    free(L);
+    return h;
+}

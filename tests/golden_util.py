@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden", "rk_golden.npz")
 
-BUILTIN_PROBLEMS = {"lorenz63", "vanderpol"}
+BUILTIN_PROBLEMS = {"lorenz63", "vanderpol", "arenstorf"}
 
 
 class Golden:
