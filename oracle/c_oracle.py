@@ -216,3 +216,50 @@ def swag_batch(rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
     return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
                 n_accepted=n_acc, n_rejected=n_fail, nfev=nfev, status=status,
                 n_eval_done=n_done, k_final=k_final)
+
+
+VEC_RHS_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double),
+                         C.POINTER(C.c_double), C.c_int64, C.c_void_p)
+
+
+def rkc_solve(y0, t_span, rtol=1e-3, atol=1e-6, first_step=None,
+              max_step=np.inf, const_jac=False, rho=None, t_eval=None,
+              max_steps=0, fun=None):
+    """SSV2stab through the C restatement (oracle/xsq_oracle_rkc.c).
+    ``fun=None`` uses the built-in 2-D reaction-diffusion RHS (len(y0) must be
+    a square); otherwise ``fun(t, y) -> dy`` is called back from C.
+    ``rho``: constant playing the role of rho_jac, None -> power iteration."""
+    lib = load()
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=float))
+    n = y0.size
+    te = (np.ascontiguousarray(np.asarray(t_eval, dtype=float))
+          if t_eval is not None else None)
+    n_eval = te.size if te is not None else 0
+    y_eval = np.empty((n_eval, n)) if n_eval else None
+    t_final = C.c_double()
+    y_final = np.empty(n)
+    counters = np.zeros(6, np.int32)
+    if fun is None:
+        kind, cb = 1, VEC_RHS_FN()
+    else:
+        kind = 0
+
+        def _cb(t, yp, dyp, nn, ctx):
+            yv = np.ctypeslib.as_array(yp, (n,))
+            np.ctypeslib.as_array(dyp, (n,))[:] = fun(t, yv)
+        cb = VEC_RHS_FN(_cb)
+    rc = lib.xsq_oracle_rkc_solve(
+        C.c_int(kind), cb, C.c_int64(n), _dp(y0), C.c_double(t_span[0]),
+        C.c_double(t_span[1]), C.c_double(rtol), C.c_double(atol),
+        C.c_double(first_step if first_step is not None else 0.0),
+        C.c_double(max_step), C.c_int(1 if const_jac else 0),
+        C.c_double(rho if rho is not None else 0.0), _dp(te), C.c_int(n_eval),
+        _dp(y_eval), C.c_int(max_steps), C.byref(t_final), _dp(y_final),
+        _ip(counters))
+    if rc != 0:
+        raise RuntimeError("xsq_oracle_rkc_solve failed")
+    return dict(t=te, y=y_eval.T if y_eval is not None else None,
+                t_final=t_final.value, y_final=y_final,
+                n_accepted=int(counters[0]), n_rejected=int(counters[1]),
+                nfev=int(counters[2]), nfesig=int(counters[3]),
+                maxm=int(counters[4]), status=int(counters[5]))

@@ -84,3 +84,54 @@ __device__ void rhs(double t, const double* y, const double* p, double* dy) {
     dy[1] = p[0] * y[1];
 }"""),
 }
+
+
+# ---- PDE problems for SSV2stab ------------------------------------------------
+def heat2d_reaction(nx):
+    """u_t = Lap(u) + u - u^3 on (0,1)^2, Dirichlet 0, nx x nx interior points,
+    5-point stencil.  Returns (fun, y0, rho)."""
+    h = 1.0 / (nx + 1)
+    inv_h2 = (nx + 1.0) * (nx + 1.0)
+    x = np.arange(1, nx + 1) * h
+    y0 = np.outer(np.sin(np.pi * x), np.sin(np.pi * x)).reshape(-1)
+    work = np.zeros((nx + 2, nx + 2))
+
+    def fun(t, y):
+        work[1:-1, 1:-1] = y.reshape(nx, nx)
+        u = work[1:-1, 1:-1]
+        lap = (((work[:-2, 1:-1] + work[2:, 1:-1]) +
+                (work[1:-1, :-2] + work[1:-1, 2:])) - 4.0 * u) * inv_h2
+        return (lap + (u - u * u * u)).reshape(-1)
+    rho = 8.0 * inv_h2 + 2.0
+    return fun, y0, rho
+
+
+def heat3d_notebook(N=39):
+    """The linear 3-D heat problem of the reference's docs/Demo_SSV2stab.ipynb
+    (cells 7-9), restated; returns (fun, y0, rho)."""
+    def solution(x, y, z, t):
+        return np.tanh(5 * x + 10 * y + 7.5 * z - (2.5 + 5 * t))
+
+    def src(x, y, z, t):
+        s = solution(x, y, z, t)
+        return 362.5 * (s - s ** 3) + 5 * s ** 2 - 5
+    g = np.linspace(0., 1., N + 2)
+    X, Y, Z = np.meshgrid(g, g, g)
+    W = solution(X, Y, Z, 0)
+    y0 = W[1:-1, 1:-1, 1:-1].copy().reshape(-1)
+    h = 1. / (N + 1.)
+
+    def fun(t, y):
+        W[0, :, :] = solution(X[0, :, :], Y[0, :, :], Z[0, :, :], t)
+        W[-1, :, :] = solution(X[-1, :, :], Y[-1, :, :], Z[-1, :, :], t)
+        W[:, 0, :] = solution(X[:, 0, :], Y[:, 0, :], Z[:, 0, :], t)
+        W[:, -1, :] = solution(X[:, -1, :], Y[:, -1, :], Z[:, -1, :], t)
+        W[:, :, 0] = solution(X[:, :, 0], Y[:, :, 0], Z[:, :, 0], t)
+        W[:, :, -1] = solution(X[:, :, -1], Y[:, :, -1], Z[:, :, -1], t)
+        W[1:-1, 1:-1, 1:-1] = y.reshape(N, N, N)
+        lap = (1. / h ** 2) * (-6 * W[1:-1, 1:-1, 1:-1] +
+                               W[:-2, 1:-1, 1:-1] + W[2:, 1:-1, 1:-1] +
+                               W[1:-1, :-2, 1:-1] + W[1:-1, 2:, 1:-1] +
+                               W[1:-1, 1:-1, :-2] + W[1:-1, 1:-1, 2:])
+        return (lap + src(X, Y, Z, t)[1:-1, 1:-1, 1:-1]).reshape(-1)
+    return fun, y0, 12 / h ** 2
