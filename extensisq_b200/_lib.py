@@ -34,7 +34,10 @@ EXPORTS = [
     "xsq_abi_version", "xsq_strerror", "xsq_last_error_detail",
     "xsq_device_info", "xsq_tableau_load", "xsq_tableau_get",
     "xsq_rhs_builtin", "xsq_rhs_register_source", "xsq_user_compile_check",
-    "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve", "xsq_launch_count", "xsq_fp64_peak",
+    "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
+    "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
+    "xsq_rkc_solve", "xsq_rkc_stage_bench", "xsq_launch_count",
+    "xsq_fp64_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -79,6 +82,36 @@ class XsqRkArgs(C.Structure):
     ]
 
 
+RHO_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
+
+class XsqRkcResult(C.Structure):
+    _fields_ = [
+        ("t_final", C.c_double),
+        ("n_accepted", C.c_int32), ("n_rejected", C.c_int32),
+        ("nfev", C.c_int32), ("nfesig", C.c_int32), ("maxm", C.c_int32),
+        ("status", C.c_int32), ("n_eval_done", C.c_int32),
+        ("reserved", C.c_int32), ("kernel_launches", C.c_int64),
+    ]
+
+
+class XsqRkcArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("pde", C.c_int32), ("nx", C.c_int32),
+        ("rows_global", C.c_int32), ("rows_local", C.c_int32),
+        ("row0", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("u0", C.c_void_p),
+        ("t0", C.c_double), ("t_bound", C.c_double),
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("first_step", C.c_double), ("max_step", C.c_double),
+        ("const_jac", C.c_int32), ("max_steps", C.c_int32),
+        ("rho_const", C.c_double), ("rho_cb", RHO_FN), ("rho_user", C.c_void_p),
+        ("t_eval", _dp), ("n_eval", C.c_int32), ("reserved", C.c_int32),
+        ("u_eval", C.c_void_p), ("u_final", C.c_void_p),
+        ("result", C.POINTER(XsqRkcResult)),
+    ]
+
+
 class XsqError(RuntimeError):
     def __init__(self, code, what, detail):
         self.code = code
@@ -113,6 +146,14 @@ def load():
     lib.xsq_rk_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_void_p]
     lib.xsq_rk_solve_host.argtypes = [C.POINTER(XsqRkArgs), C.c_int]
     lib.xsq_swag_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_int32, C.c_void_p]
+    lib.xsq_comm_unique_id.argtypes = [C.c_char_p]
+    lib.xsq_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_char_p,
+                                    C.POINTER(C.c_void_p)]
+    lib.xsq_comm_destroy.argtypes = [C.c_void_p]
+    lib.xsq_rkc_solve.argtypes = [C.POINTER(XsqRkcArgs), C.c_void_p,
+                                  C.c_void_p]
+    lib.xsq_rkc_stage_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp,
+                                        C.c_void_p]
     lib.xsq_launch_count.restype = C.c_int64
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]

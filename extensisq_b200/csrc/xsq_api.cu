@@ -19,8 +19,12 @@
 #include "xsq.h"
 #include "xsq_launch.h"
 #include "xsq_user.h"
+#include "xsq_comm.h"
 
 namespace xsq {
+
+int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st);
+int rkc_stage_bench(int nx, int rows, int reps, double* ms, cudaStream_t st);
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -419,6 +423,27 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     cudaStreamDestroy(st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "xsq_rk_solve_host");
     return rc;
+}
+
+int xsq_comm_unique_id(char id[128]) { return comm_unique_id(id); }
+int xsq_comm_create(int32_t rank, int32_t world, const char id[128], void** comm) {
+    if (!comm || world < 1 || rank < 0 || rank >= world) return XSQ_ERR_ARG;
+    Comm* c = nullptr;
+    int rc = comm_create(rank, world, id, &c);
+    *comm = c;
+    return rc;
+}
+int xsq_comm_destroy(void* comm) {
+    comm_destroy((Comm*)comm);
+    return XSQ_OK;
+}
+int xsq_rkc_solve(const xsq_rkc_args_t* args, void* comm, void* stream) {
+    return rkc_solve(args, (Comm*)comm, (cudaStream_t)stream);
+}
+int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
+                        void* stream) {
+    if (!ms_per_stage || nx < 4 || nx % 4 || rows < 1 || reps < 1) return XSQ_ERR_ARG;
+    return rkc_stage_bench(nx, rows, reps, ms_per_stage, (cudaStream_t)stream);
 }
 
 int64_t xsq_launch_count(int reset) {

@@ -1,0 +1,123 @@
+// xsq_comm.cpp -- NCCL plumbing for the domain-decomposed SSV2stab path
+// (per stage a nearest-neighbour halo over NVLink, per
+// step attempt a scalar all-gather).  The reference has no communication layer
+// at all (single Python thread); this file is new.
+#include "xsq_comm.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "xsq.h"
+#include "xsq_user.h"
+
+namespace xsq {
+
+struct Comm {
+    ncclComm_t nccl;
+    int rank, world;
+};
+
+namespace {
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+} g;
+std::mutex g_mu;
+
+template <class F>
+bool bind(const char* name, F* out) {
+    *out = reinterpret_cast<F>(dlsym(g.lib, name));
+    return *out != nullptr;
+}
+
+bool load() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.lib) return true;
+    // inside a torch process this resolves to the libnccl torch already loaded
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g.lib) break;
+    }
+    if (!g.lib) { set_detail("cannot dlopen libnccl.so.2"); return false; }
+    bool ok = bind("ncclGetUniqueId", &g.GetUniqueId) &&
+              bind("ncclCommInitRank", &g.CommInitRank) &&
+              bind("ncclCommDestroy", &g.CommDestroy) && bind("ncclSend", &g.Send) &&
+              bind("ncclRecv", &g.Recv) && bind("ncclGroupStart", &g.GroupStart) &&
+              bind("ncclGroupEnd", &g.GroupEnd) && bind("ncclAllGather", &g.AllGather) &&
+              bind("ncclGetErrorString", &g.GetErrorString);
+    if (!ok) set_detail("libnccl is missing a required symbol");
+    return ok;
+}
+
+int check(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return 0;
+    set_detail(std::string(what) + ": " + g.GetErrorString(r));
+    return -1;
+}
+}  // namespace
+
+int comm_unique_id(char id[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (!load()) return XSQ_ERR_CUDA;
+    ncclUniqueId u;
+    if (check(g.GetUniqueId(&u), "ncclGetUniqueId")) return XSQ_ERR_CUDA;
+    std::memcpy(id, &u, 128);
+    return XSQ_OK;
+}
+
+int comm_create(int rank, int world, const char id[128], Comm** out) {
+    if (!load()) return XSQ_ERR_CUDA;
+    ncclUniqueId u;
+    std::memcpy(&u, id, 128);
+    Comm* c = new Comm{nullptr, rank, world};
+    if (check(g.CommInitRank(&c->nccl, world, u, rank), "ncclCommInitRank")) {
+        delete c;
+        return XSQ_ERR_CUDA;
+    }
+    *out = c;
+    return XSQ_OK;
+}
+
+void comm_destroy(Comm* c) {
+    if (!c) return;
+    if (g.lib) g.CommDestroy(c->nccl);
+    delete c;
+}
+int comm_rank(const Comm* c) { return c->rank; }
+int comm_world(const Comm* c) { return c->world; }
+
+int comm_halo(Comm* c, int up, int down, const double* first_row, double* top_ghost,
+              const double* last_row, double* bottom_ghost, size_t n, cudaStream_t st) {
+    int rc = 0;
+    rc |= check(g.GroupStart(), "ncclGroupStart");
+    if (up >= 0) {
+        rc |= check(g.Send(first_row, n, ncclDouble, up, c->nccl, st), "ncclSend");
+        rc |= check(g.Recv(top_ghost, n, ncclDouble, up, c->nccl, st), "ncclRecv");
+    }
+    if (down >= 0) {
+        rc |= check(g.Send(last_row, n, ncclDouble, down, c->nccl, st), "ncclSend");
+        rc |= check(g.Recv(bottom_ghost, n, ncclDouble, down, c->nccl, st), "ncclRecv");
+    }
+    rc |= check(g.GroupEnd(), "ncclGroupEnd");
+    return rc;
+}
+
+int comm_allgather1(Comm* c, const double* send, double* recv, cudaStream_t st) {
+    return check(g.AllGather(send, recv, 1, ncclDouble, c->nccl, st), "ncclAllGather");
+}
+
+}  // namespace xsq

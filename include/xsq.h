@@ -187,6 +187,69 @@ int xsq_rk_solve_host(const xsq_rk_args_t* args, int device);
 typedef xsq_rk_args_t xsq_swag_args_t;
 int xsq_swag_solve(const xsq_swag_args_t* args, int32_t k_max, void* stream);
 
+/* ---- SSV2stab: one large parabolic PDE, row-slab decomposed -------------- */
+typedef enum xsq_pde_id {
+    /* u_t = Lap(u) + u - u^3 on (0,1)^2, Dirichlet 0, nx x rows_global interior
+     * points, 5-point stencil, h = 1/(nx+1)   */
+    XSQ_PDE_HEAT2D_REACTION = 0
+} xsq_pde_id;
+
+typedef double (*xsq_rho_fn)(double t, void* user);   /* rho_jac(t, .) */
+
+typedef struct xsq_rkc_result {     /* HOST struct filled by xsq_rkc_solve */
+    double t_final;
+    int32_t n_accepted, n_rejected; /* rejected = the reference's NFS/nrejct  */
+    int32_t nfev, nfesig, maxm;     /* sommeijer.py:12-14 counters            */
+    int32_t status;                 /* xsq_lane_status                        */
+    int32_t n_eval_done, reserved;
+    int64_t kernel_launches;
+} xsq_rkc_result_t;
+
+/* Replaces solve_ivp(fun, t_span, y0, method=SSV2stab, rtol, atol, first_step,
+ * max_step, const_jac, rho_jac, t_eval) -- SSV2stab.__init__/_step_impl/
+ * _stages/_rho/_dense_output_impl, sommeijer.py:93-406 -- for the built-in
+ * PDE right-hand sides.  Each rank owns rows [row0, row0 + rows_local) of the
+ * rows_global x nx grid. */
+typedef struct xsq_rkc_args {
+    int32_t struct_size;
+    int32_t pde;                  /* xsq_pde_id                               */
+    int32_t nx;                   /* points per row (multiple of 4)           */
+    int32_t rows_global, rows_local, row0;
+    int32_t rank, world;          /* position in the row-slab decomposition   */
+    const double* u0;             /* DEVICE [rows_local][nx]                  */
+    double t0, t_bound;
+    double rtol, atol;            /* scalars; clipped like validate_tol       */
+    double first_step;            /* <= 0: _init_step_size                    */
+    double max_step;
+    int32_t const_jac;            /* sommeijer.py:95                          */
+    int32_t max_steps;            /* attempted-step budget, <= 0: unlimited   */
+    double rho_const;             /* > 0: rho_jac(t, y) = rho_const           */
+    xsq_rho_fn rho_cb;            /* else if non-NULL: host callback          */
+    void* rho_user;               /* else: nonlinear power iteration (_rho)   */
+    const double* t_eval;         /* HOST [n_eval], sorted along direction    */
+    int32_t n_eval, reserved;
+    double* u_eval;               /* DEVICE [n_eval][rows_local][nx]          */
+    double* u_final;              /* DEVICE [rows_local][nx]                  */
+    xsq_rkc_result_t* result;     /* HOST                                     */
+} xsq_rkc_args_t;
+
+/* NCCL communicator for the slab decomposition (new; the reference has no
+ * communication layer).  Rank 0 calls xsq_comm_unique_id and distributes the
+ * 128 bytes out of band (e.g. torch.distributed.broadcast); every rank then
+ * calls xsq_comm_create with its CUDA device current. */
+int xsq_comm_unique_id(char id[128]);
+int xsq_comm_create(int32_t rank, int32_t world, const char id[128], void** comm);
+int xsq_comm_destroy(void* comm);
+
+/* comm may be NULL when world == 1.  Synchronous with respect to the host
+ * (the step-size decisions need the error norm); work runs on `stream`. */
+int xsq_rkc_solve(const xsq_rkc_args_t* args, void* comm, void* stream);
+
+/* Stage-kernel microbenchmark (roofline of the HBM-streaming stage):
+ * average device milliseconds per fused stage on a rows x nx slab. */
+int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
+                        void* stream);
+
 /* Kernel-launch bookkeeping for benchmarks: number of kernels this library
  * launched since the last reset. */
 int64_t xsq_launch_count(int reset);

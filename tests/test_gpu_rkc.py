@@ -1,0 +1,125 @@
+"""GPU parity tests of the SSV2stab path (xsq_rkc_solve through ctypes):
+against the reference's golden vectors, the C oracle at larger grids, and --
+when two devices are visible -- the 2-rank slab decomposition against the
+1-rank run."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import extensisq_b200 as xb
+from oracle import c_oracle as CO
+from oracle.problems import heat2d_reaction
+from test_rkc_oracle_golden import CASES, Z
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def solve(c_or_nx, t_span, use_rho=True, t_eval=None, **opts):
+    nx = c_or_nx
+    _, y0, rho = heat2d_reaction(nx)
+    r = xb.solve_pde_rkc("heat2d_reaction", t_span, y0.reshape(nx, nx),
+                         rho_jac=float(rho) if use_rho else None,
+                         t_eval=t_eval, max_steps=100000, **opts)
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if not c.get("notebook")],
+                         ids=lambda c: c["id"])
+def test_rkc_vs_reference_golden(c):
+    te = np.linspace(*c["t_eval"]) if c.get("t_eval") else None
+    r = solve(c["nx"], c["t_span"], c["use_rho"], te, **c["options"])
+    assert r.status == 0
+    assert (r.nfev, r.n_rejected, r.nfesig, r.maxm) == \
+        (c["nfev"], c["nfs"], c["nfesig"], c["maxm"])
+    yg = Z[c["id"] + "/y"]
+    if te is None:
+        assert r.n_accepted == c["n_t"] - 1
+        got = r.y_final.cpu().numpy().reshape(-1)
+    else:
+        got = r.y.cpu().numpy().reshape(te.size, -1).T
+    assert np.abs(got - yg).max() <= 1e-11
+    assert xb.maxm == c["maxm"] and xb.nfesig == c["nfesig"]
+
+
+@pytest.mark.parametrize("nx,tol", [(256, 1e-4), (512, 1e-4), (256, 1e-6)])
+def test_rkc_vs_c_oracle_larger_grids(nx, tol):
+    """BASELINE.md section 2, C5 proxy: N = 256 / 512 -> 10 accepted steps,
+    nfev 607 / 1205, s-max 76 / 151 at tol 1e-4."""
+    _, y0, rho = heat2d_reaction(nx)
+    r = solve(nx, (0.0, 0.05), rtol=tol, atol=tol)
+    ref = CO.rkc_solve(y0, (0.0, 0.05), rtol=tol, atol=tol, rho=rho)
+    assert (r.n_accepted, r.n_rejected, r.nfev, r.maxm) == \
+        (ref["n_accepted"], ref["n_rejected"], ref["nfev"], ref["maxm"])
+    if tol == 1e-4:
+        assert (r.n_accepted, r.nfev, r.maxm) == \
+            {256: (10, 607, 76), 512: (10, 1205, 151)}[nx]
+    got = r.y_final.cpu().numpy().reshape(-1)
+    assert np.abs(got - ref["y_final"]).max() <= 1e-11
+
+
+def test_rkc_power_iteration_and_rho_callback():
+    nx = 64
+    _, y0, rho = heat2d_reaction(nx)
+    r = solve(nx, (0.0, 0.05), use_rho=False, rtol=1e-4, atol=1e-4)
+    ref = CO.rkc_solve(y0, (0.0, 0.05), rtol=1e-4, atol=1e-4, rho=None)
+    assert (r.nfev, r.nfesig, r.maxm, r.n_accepted) == \
+        (ref["nfev"], ref["nfesig"], ref["maxm"], ref["n_accepted"])
+    assert r.nfesig > 0
+    got = r.y_final.cpu().numpy().reshape(-1)
+    assert np.abs(got - ref["y_final"]).max() <= 1e-10
+    calls = []
+    r2 = xb.solve_pde_rkc("heat2d_reaction", (0.0, 0.05), y0.reshape(nx, nx),
+                          rho_jac=lambda t: calls.append(t) or float(rho),
+                          rtol=1e-4, atol=1e-4)
+    r3 = solve(nx, (0.0, 0.05), rtol=1e-4, atol=1e-4)
+    assert len(calls) >= r2.n_accepted
+    assert torch.equal(r2.y_final, r3.y_final)
+
+
+def test_rkc_argument_errors_and_edge_cases():
+    nx = 32
+    _, y0, rho = heat2d_reaction(nx)
+    u0 = y0.reshape(nx, nx)
+    with pytest.raises(TypeError, match="const_jac"):
+        xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), u0, const_jac=1)
+    with pytest.raises(TypeError, match="rho_jac"):
+        xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), u0, rho_jac=3)
+    with pytest.raises(ValueError, match="positive float"):
+        xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), u0, rho_jac=-1.0)
+    with pytest.raises(ValueError, match="first_step"):
+        xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), u0, first_step=1.0)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), np.zeros((5, 5)))
+    r = xb.solve_pde_rkc("heat2d_reaction", (0.3, 0.3), u0, rho_jac=float(rho),
+                         t_eval=[0.3])
+    assert r.status == 0 and r.n_accepted == 0
+    assert np.array_equal(r.y_final.cpu().numpy(), u0)
+    assert np.array_equal(r.y[0].cpu().numpy(), u0)
+    # step budget: the safety net reports -5 instead of running on
+    r = xb.solve_pde_rkc("heat2d_reaction", (0, 0.05), u0, rho_jac=float(rho),
+                         rtol=1e-6, atol=1e-6, max_steps=3)
+    assert r.status == -5 and r.n_accepted == 3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rkc_two_rank_slab_decomposition_matches_one_rank(tmp_path):
+    """Domain decomposition: 2 ranks, NCCL halo rows
+    per stage + scalar all-gather per step; same step counts as 1 rank and the
+    same state to 1e-12 (the error-norm partial sums are added in a different
+    order)."""
+    out = tmp_path / "mp.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "tests",
+                                                   "mp_rkc_worker.py"),
+           str(out)]
+    subprocess.check_call(cmd, cwd=ROOT, timeout=600)
+    import json
+    res = json.loads(out.read_text())
+    assert res["ok"], res
