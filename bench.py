@@ -369,6 +369,21 @@ def main():
                 "hbm_peak_gbs_measured": hbm},
             "wall_s_timed_region": t_wall,
         }
+        # second hot path of the north star: SSV2stab's fused stage kernel
+        # (HBM-bound, 40 B algorithmic per grid point and stage) on this GPU's
+        # slab of the 16384^2 grid (configs[4]: 2048 rows x 16384 at 8 GPUs)
+        ms_stage = C.c_double()
+        if lib.xsq_rkc_stage_bench(16384, 2048, 40, C.byref(ms_stage), None) == 0:
+            gbs = 16384 * 2048 * 40 / 1e9 / (ms_stage.value * 1e-3)
+            line["ssv2stab"] = {
+                "kernel": "k_stage (stencil RHS + three-term recurrence)",
+                "slab": "2048 x 16384 (1/8 of the 16384^2 grid)",
+                "ms_per_stage": ms_stage.value,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm,
+                             "unit": "GB/s",
+                             "frac": gbs / hbm if hbm else None,
+                             "traffic": None,
+                             "bytes_per_point_stage": 40}}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             lanes_np = args.cpu_lanes or max(cores, int(cores * 1.2e4 * 8 /

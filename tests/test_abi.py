@@ -37,14 +37,17 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_sizes_match_the_c_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "xsq.h"\nint main(void){'
-                   'printf("%zu %zu\\n", sizeof(xsq_rk_args_t), '
-                   'sizeof(xsq_tableau_t)); return 0;}\n')
+                   'printf("%zu %zu %zu %zu\\n", sizeof(xsq_rk_args_t), '
+                   'sizeof(xsq_tableau_t), sizeof(xsq_rkc_args_t), '
+                   'sizeof(xsq_rkc_result_t)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe)])
-    a, t = map(int, subprocess.check_output([str(exe)]).split())
+    a, t, ra, rr = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(_lib.XsqRkArgs)
     assert t == C.sizeof(_lib.XsqTableau)
+    assert ra == C.sizeof(_lib.XsqRkcArgs)
+    assert rr == C.sizeof(_lib.XsqRkcResult)
 
 
 def test_strerror_and_builtin_rhs_lookup():
