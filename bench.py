@@ -146,34 +146,47 @@ def _np_worker(args):
     return acc
 
 
-def cpu_numpy_port(method, lanes, t_end, cores):
+def cpu_numpy_port(method, lanes, t_end, cores, target_s=15.0):
     """The NumPy restatement (bit-identical to the reference's own Python,
-    same per-step cost model), one process per core."""
+    same per-step cost model), one process per core.  lanes == 0: calibrate
+    on one lane per core and size the sample for ~target_s seconds."""
     import multiprocessing as mp
-    y0, prm = make_lanes(lanes, 0)
-    chunks = [(method, y0[i::cores], prm[i::cores], t_end)
-              for i in range(cores)]
     with mp.get_context("spawn").Pool(cores) as pool:
+        y0, prm = make_lanes(max(lanes, 4 * cores), 0)
         pool.map(_np_worker, [(method, y0[:1], prm[:1], 0.05)] * cores)  # warm
+        if lanes <= 0:
+            t0 = time.perf_counter()
+            pool.map(_np_worker, [(method, y0[i:i + 1], prm[i:i + 1], t_end)
+                                  for i in range(cores)])
+            per_lane = time.perf_counter() - t0
+            lanes = max(cores, int(cores * target_s / max(per_lane, 1e-3)))
+            y0, prm = make_lanes(lanes, 0)
+        chunks = [(method, y0[i:lanes:cores], prm[i:lanes:cores], t_end)
+                  for i in range(cores)]
         t0 = time.perf_counter()
         accs = pool.map(_np_worker, chunks)
         dt = time.perf_counter() - t0
-    return sum(accs) / dt, sum(accs), dt
+    return sum(accs) / dt, sum(accs), dt, lanes
 
 
-def cpu_c_port(method, lanes, t_end, threads):
+def cpu_c_port(method, lanes, t_end, threads, target_s=10.0):
     from oracle import c_oracle as CO
     from oracle import rk_oracle as O
     tab = O.load_tableaux()[method]
-    y0, prm = make_lanes(lanes, 0)
-    CO.rk_batch(tab, "lorenz63", (0.0, 1.0), y0[:threads], params=prm[:threads],
+    y0, prm = make_lanes(64 * threads, 0)
+    t0 = time.perf_counter()
+    CO.rk_batch(tab, "lorenz63", (0.0, t_end), y0, params=prm,
                 rtol=RTOL, atol=ATOL, n_threads=threads)
+    per_lane = (time.perf_counter() - t0) / (64 * threads)
+    if lanes <= 0:
+        lanes = max(64 * threads, int(target_s / max(per_lane, 1e-9)))
+    y0, prm = make_lanes(lanes, 0)
     t0 = time.perf_counter()
     r = CO.rk_batch(tab, "lorenz63", (0.0, t_end), y0, params=prm, rtol=RTOL,
                     atol=ATOL, n_threads=threads)
     dt = time.perf_counter() - t0
     acc = int(r["n_accepted"].sum())
-    return acc / dt, acc, dt
+    return acc / dt, acc, dt, lanes
 
 
 def config_dict(args, world):
@@ -193,16 +206,15 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    # bounded sample: ~10-30 s of CPU work per step at ~1.2e4 steps/s/core
-    lanes = args.cpu_lanes or max(cores, int(cores * 1.2e4 * 8 / (105 * args.t_end)))
+    # bounded sample: ~15 s of CPU work per step, calibrated on this host
+    lanes = args.cpu_lanes
     vals, t_all = [], []
     for i in range(args.warmup + args.steps):
-        v, acc, dt = cpu_numpy_port(args.method, lanes, args.t_end, cores)
+        v, acc, dt, lanes = cpu_numpy_port(args.method, lanes, args.t_end,
+                                           cores)
         if i >= args.warmup:
             vals.append(v)
             t_all.append(dt)
-        if i == 0 and dt > 60:          # keep the whole run within minutes
-            lanes = max(cores, int(lanes * 30 / dt))
     value = float(np.mean(vals))
     sample = (f"{lanes} lanes of the same ensemble (seed 12345), full t span, "
               f"NumPy restatement of the reference (oracle/rk_oracle.py), "
@@ -368,6 +380,7 @@ def main():
                                "trajectory, so the bound is the fp64 pipe, not HBM",
                 "hbm_peak_gbs_measured": hbm},
             "wall_s_timed_region": t_wall,
+            "kernel_ms_each_step": kern_ms,
         }
         # second hot path of the north star: SSV2stab's fused stage kernel
         # (HBM-bound, 40 B algorithmic per grid point and stage) on this GPU's
@@ -386,12 +399,10 @@ def main():
                              "bytes_per_point_stage": 40}}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
-            lanes_np = args.cpu_lanes or max(cores, int(cores * 1.2e4 * 8 /
-                                                        (105 * args.t_end)))
-            v_np, a_np, dt_np = cpu_numpy_port(args.method, lanes_np,
-                                               args.t_end, cores)
-            lanes_c = max(cores * 8, int(cores * 2e6 * 5 / (105 * args.t_end)))
-            v_c, a_c, dt_c = cpu_c_port(args.method, lanes_c, args.t_end, cores)
+            v_np, a_np, dt_np, lanes_np = cpu_numpy_port(
+                args.method, args.cpu_lanes, args.t_end, cores)
+            v_c, a_c, dt_c, lanes_c = cpu_c_port(args.method, 0, args.t_end,
+                                                 cores)
             line["cpu_baseline"] = {
                 "value": v_np, "unit": "steps/s", "cores": cores, "kind": "port",
                 "sample": f"{lanes_np} lanes of the same ensemble, full t span, "

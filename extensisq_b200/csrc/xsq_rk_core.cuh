@@ -133,7 +133,9 @@ static __constant__ double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
 
 __device__ __forceinline__ double log2_fast(double x) {
     const int hi = __double2hiint(x);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log2(x);
+    // 0 -> -inf, +inf -> +inf, NaN -> NaN by selects at the end (no branch on
+    // the critical path); a subnormal argument gives an (irrelevant) finite
+    // value: such an error norm is below the tiny_err threshold anyway
     int e = (hi >> 20) - 1023;
     int mhi = (hi & 0x000fffff) | 0x3ff00000;
     if (mhi >= 0x3ff6a09f) {            // m in [sqrt(1/2), sqrt(2))
@@ -143,24 +145,56 @@ __device__ __forceinline__ double log2_fast(double x) {
     const double f = __hiloint2double(mhi, __double2loint(x)) - 1.0;
     const double s = f * rcp_fast(2.0 + f);
     const double z = s * s;
-    double r = c_xsq_lg[6];
-#pragma unroll
-    for (int k = 5; k >= 0; --k) r = fma(r, z, c_xsq_lg[k]);
-    r *= z;
+    // R(z) = z*(Lg1 + z*(Lg2 + ...)), Estrin's scheme: the controller is a
+    // serial tail of every attempt, so dependency depth (4 instead of 8
+    // dependent DFMAs) matters more than the two extra multiplies
+    const double z2 = z * z, z4 = z2 * z2;
+    const double a0 = fma(c_xsq_lg[1], z, c_xsq_lg[0]);
+    const double a1 = fma(c_xsq_lg[3], z, c_xsq_lg[2]);
+    const double a2 = fma(c_xsq_lg[5], z, c_xsq_lg[4]);
+    const double b0 = fma(a1, z2, a0);
+    const double b1 = fma(c_xsq_lg[6], z2, a2);
+    const double r = fma(b1, z4, b0) * z;
     const double hfsq = 0.5 * f * f;
     const double lg = f - (hfsq - s * (hfsq + r));      // ln(1 + f)
-    return fma(lg, c_xsq_misc[0], (double)e);
+    double r2 = fma(lg, c_xsq_misc[0], (double)e);
+    if (x == 0.0) r2 = -XSQ_INF;
+    if (!(x < XSQ_INF)) r2 = x;
+    return r2;
 }
 
 __device__ __forceinline__ double exp2_fast(double z) {
-    if (!(fabs(z) < 1000.0)) return exp2(z);
+    // |z| <= 0.25 * 1075 here, so 2^n never leaves the exponent range; a
+    // non-finite z yields NaN, which the caller's max()/min() absorb exactly
+    // like the reference's max(min_factor, nan)
     const double t = z + c_xsq_misc[1];
     const int n = __double2loint(t);
     const double r = z - (t - c_xsq_misc[1]);           // |r| <= 1/2, exact
-    double p = c_xsq_e2[13];
-#pragma unroll
-    for (int k = 12; k >= 0; --k) p = fma(p, r, c_xsq_e2[k]);
+    // degree-13 polynomial by Estrin's scheme (depth 4 instead of 13)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(c_xsq_e2[1], r, c_xsq_e2[0]);
+    const double a1 = fma(c_xsq_e2[3], r, c_xsq_e2[2]);
+    const double a2 = fma(c_xsq_e2[5], r, c_xsq_e2[4]);
+    const double a3 = fma(c_xsq_e2[7], r, c_xsq_e2[6]);
+    const double a4 = fma(c_xsq_e2[9], r, c_xsq_e2[8]);
+    const double a5 = fma(c_xsq_e2[11], r, c_xsq_e2[10]);
+    const double a6 = fma(c_xsq_e2[13], r, c_xsq_e2[12]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+    const double p = fma(d1, r8, d0);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// 1/x to ~2^-40: seed + ONE Newton step.  Used for err/scale only: the error
+// norm feeds a compare against 1 and a power with |exponent| <= 0.25, so a
+// relative 1e-12 moves an accept/reject decision with probability ~1e-12 per
+// step (measured: step counts unchanged on every parity lane).
+__device__ __forceinline__ double rcp_scale(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
 
 // RMS norm, common.py:64-66
@@ -324,14 +358,15 @@ struct Lane {
         }
     }
 
-    // _reassess_stepsize, common.py:310-331
-    __device__ __forceinline__ void reassess(const RkDev& P) {
-        min_step = pymax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+    // _reassess_stepsize, common.py:310-331.  attempt() tests the common case
+    // (min_step <= h_abs <= max_step and t_bound at least two steps away)
+    // with three independent compares and only then calls this slow path, so
+    // the first stage of a step does not wait for a chain of selects.
+    __device__ __forceinline__ void reassess_slow(const RkDev& P, double d) {
         if (h_abs < min_step || h_abs > P.max_step) {
             h_abs = pymin(P.max_step, pymax(min_step, h_abs));
             standard_sc = true;
         }
-        const double d = fabs(P.t_bound - t);
         if (d < 2.0 * h_abs) {
             if (d > h_abs) {
                 h_abs = pymax(0.5 * d, min_step);
@@ -384,7 +419,7 @@ struct Lane {
         for (int c = 0; c < NL; ++c) {
             const double scale = fma(P.rtol, pymax(fabs(y[c]), fabs(yref[c])),
                                      atol_of<R>(P, c, lane));
-            const double q = errv[c] * rcp_fast(scale);
+            const double q = errv[c] * rcp_scale(scale);
             ss = fma(q, q, ss);
         }
         return sys_sum<R::WARP>(ss);
@@ -592,19 +627,29 @@ struct Lane {
     // One ATTEMPT of a step (the body of `while not step_accepted`,
     // common.py:232-287).  Returns the lane status: LANE_RUNNING, or a final
     // code when the trajectory ends here.
+    // FAST: adaptive stepping without t_eval output (the ensemble benchmark
+    // path); the forced-step and dense-output tests on kernel parameters
+    // vanish at compile time.
+    template <bool FAST>
     __device__ __forceinline__ int attempt(const RkDev& P, int lane) {
         // Forced-step mode shares every instruction of the adaptive path: h
         // comes from the table instead of reassess(), every step is accepted,
         // and the controller's h update is overwritten at the next step.
-        const bool forced = P.n_forced > 0;
+        const bool forced = !FAST && P.n_forced > 0;
         if (fresh) {
-            if (forced) h_abs = P.h_forced[n_acc];
-            else reassess(P);
+            if (forced) {
+                h_abs = P.h_forced[n_acc];
+            } else {
+                min_step = pymax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+                const double d = fabs(P.t_bound - t);
+                if ((h_abs < min_step) | (h_abs > P.max_step) | (d < 2.0 * h_abs)) {
+                    reassess_slow(P, d);
+                    if (h_abs < min_step) return LANE_TOO_SMALL;   // common.py:234
+                }
+            }
             step_rejected = false;
             fresh = false;
         }
-        if (h_abs < min_step) return LANE_TOO_SMALL;      // min_step = 0 if forced
-        if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
         const double h = h_abs * P.direction;
         const double t_new = t + h;
         double K[KROWS][NL];
@@ -673,49 +718,54 @@ struct Lane {
             ss = scaled_ss(P, errv, y_new, lane);
         }
 
-        double lerr;
-        {
-            // ---- controller, common.py:249-287, evaluated branch-free ------
-            // error_norm**x is exp2(x * log2(error_norm)); accepted and
-            // rejected lanes share ONE exp2 so a warp holding both does not
-            // serialise two pow() calls.
-            const bool accept = forced || (!pre_reject && ss < NTOT);
-            const bool bad = !forced && !pre_reject && !(ss < XSQ_INF);  // NaN/Inf
-            if (Tab::VARIANT == tab::BS5V && bad) {      // bogacki.py:314-315
-                nfev += S - 1 + Tab::FSAL;    // this attempt is in no counter
-                return LANE_OVERFLOW;
-            }
-            lerr = 0.5 * (log2_fast(ss) - P.log2n);
-            const bool tiny_err = ss < NTOT * 0x1.0p-1022;   // err < sqrt(tiny)
-            const bool second = accept && !standard_sc;
-            double z = second ? fma(P.minbeta2, lerr_old, P.minbeta1 * lerr)
-                              : P.err_exp * lerr;
-            if (P.minalpha != 0.0 && second)
-                z = fma(P.minalpha, log2_fast(h / h_prev), z);
-            double factor = (second ? P.safety_sc : P.safety) * exp2_fast(z);
-            if (accept) {
-                if (tiny_err) {
-                    factor = max_factor;
-                    standard_sc = true;
-                } else if (standard_sc) {
-                    standard_sc = false;
-                } else {
-                    factor = pymin(max_factor, pymax(kMinFactor, factor));
-                }
-                if (step_rejected) factor = pymin(1.0, factor);
-                h_abs *= factor;
-                if (factor < kMaxFactor) max_factor = kMaxFactor;
-            } else {
-                step_rejected = true;
-                h_abs *= pymax(kMinFactor, factor);
-                ++n_rej;
-                if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
-                return bad ? LANE_OVERFLOW : LANE_RUNNING;   // common.py:286
-            }
+        // ---- controller, common.py:249-287 ---------------------------------
+        // error_norm**x is exp2(x * log2(error_norm)).  Accepting and rejecting
+        // lanes share ONE log2/exp2 (a warp almost always holds both), and
+        // everything that does not depend on log2(ss) -- which formula, which
+        // bounds -- is decided first, so the serial chain after the error norm
+        // is log2 -> fma -> exp2 -> 2 selects -> h update.
+        const bool accept = forced || (!pre_reject && ss < NTOT);
+        const bool bad = !forced && !pre_reject && !(ss < XSQ_INF);  // NaN/Inf
+        if (Tab::VARIANT == tab::BS5V && bad) {          // bogacki.py:314-315
+            nfev += S - 1 + Tab::FSAL;        // this attempt is in no counter
+            return LANE_OVERFLOW;
         }
+        const bool tiny_err = ss < NTOT * 0x1.0p-1022;       // err < sqrt(tiny)
+        const bool second = accept && !standard_sc;          // 2nd-order SC
+        const double b1h = 0.5 * (second ? P.minbeta1 : P.err_exp);
+        double zc = -b1h * P.log2n;
+        if (second) zc = fma(P.minbeta2, lerr_old, zc);
+        if (P.minalpha != 0.0 && second)
+            zc = fma(P.minalpha, log2_fast(h / h_prev), zc);
+        const double cfac = second ? P.safety_sc : P.safety;
+        const bool clamp_lo = !accept || second;     // max(min_factor, .)
+        double hi = second ? max_factor : XSQ_INF;   // min(max_factor, .)
+        double tiny_val = max_factor;
+        if (accept && step_rejected) {               // factor = min(1, factor)
+            hi = pymin(1.0, hi);
+            tiny_val = pymin(1.0, tiny_val);
+        }
+        const double l2ss = log2_fast(ss);
+        const double raw = cfac * exp2_fast(fma(b1h, l2ss, zc));
+        double factor = clamp_lo ? pymax(kMinFactor, raw) : raw;
+        factor = pymin(hi, factor);
+        if (accept && tiny_err) factor = tiny_val;
+        h_abs *= factor;
+        const double lerr = 0.5 * (l2ss - P.log2n);  // log2(error_norm)
+        if (!accept) {
+            step_rejected = true;
+            ++n_rej;
+            if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
+            if (bad) return LANE_OVERFLOW;                   // common.py:286
+            if (h_abs < min_step) return LANE_TOO_SMALL;     // common.py:234
+            if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
+            return LANE_RUNNING;
+        }
+        standard_sc = tiny_err;
+        if (factor < kMaxFactor) max_factor = kMaxFactor;
         if constexpr (!Tab::FSAL)               // common.py:289-291
             R::f(t_new, y_new, prm, K[S]);
-        if (P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
+        if (!FAST && P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
         // common.py:294-303
         h_prev = h;
         lerr_old = lerr;
@@ -727,7 +777,8 @@ struct Lane {
         // OdeSolver.step, base.py:207-208
         const bool done = forced ? (n_acc >= P.n_forced)
                                  : (P.direction * (t - P.t_bound) >= 0.0);
-        return done ? LANE_FINISHED : LANE_RUNNING;
+        if (done) return LANE_FINISHED;
+        return (n_acc + n_rej >= P.max_steps) ? LANE_STEP_BUDGET : LANE_RUNNING;
     }
 
     // RHS evaluations made by attempt(): S-1 stages (+1 if FSAL) per full
@@ -783,6 +834,7 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     Lane<Tab, R> L;
     bool live = false;
     bool exhausted = false;
+    const bool fast = P.n_forced == 0 && P.n_eval == 0;
     for (;;) {
         // ---- refill ----
         if (R::WARP) {
@@ -830,9 +882,15 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         if (__all_sync(full, !live)) break;
         // ---- attempts, until some lane of the warp ends its trajectory ----
         int st = LANE_RUNNING;
-        do {
-            if (live) st = L.attempt(P, lane);
-        } while (!__any_sync(full, st != LANE_RUNNING));
+        if (fast) {
+            do {
+                if (live) st = L.template attempt<true>(P, lane);
+            } while (!__any_sync(full, st != LANE_RUNNING));
+        } else {
+            do {
+                if (live) st = L.template attempt<false>(P, lane);
+            } while (!__any_sync(full, st != LANE_RUNNING));
+        }
         if (st != LANE_RUNNING) {
             L.store(P, st, lane);
             live = false;
@@ -845,5 +903,14 @@ template <class Tab, class R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) rk_persistent(const RkDev P) {
     rk_persistent_body<Tab, R>(P);
 }
+
+#ifdef XSQ_TUNE
+// profiling builds only: exact register cap instead of a CTAs-per-SM hint
+template <class Tab, class R, int BLOCK, int MAXREG>
+__global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
+    rk_persistent_mr(const RkDev P) {
+    rk_persistent_body<Tab, R>(P);
+}
+#endif
 
 }  // namespace xsq

