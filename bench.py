@@ -371,7 +371,12 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at
+                # this size from the committed capture profiles/r01_ncu_full_
+                # rk_persistent_Ts5_lorenz_1250k_T100.txt (69.9 MB + 32.4 MB)
+                "traffic": 102.2e6 if (args.method == "Ts5" and N == LANES_PER_GPU
+                                       and args.t_end == T_END) else None,
+                "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
                 "kernel": f"rk_persistent<{args.method}, Lorenz63>",
                 "flops_per_attempted_step": att_f,
                 "peak_source": "xsq_fp64_peak: dependent-chain DFMA microbenchmark "
@@ -395,7 +400,10 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm,
                              "unit": "GB/s",
                              "frac": gbs / hbm if hbm else None,
-                             "traffic": None,
+                             # ncu, profiles/r01_ncu_full_rkc_k_stage_
+                             # 2048x16384.txt: 1.074 GB read + 0.2525 GB
+                             # written per launch (algorithmic 1.342 GB)
+                             "traffic": 1.3266e9,
                              "bytes_per_point_stage": 40}}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
