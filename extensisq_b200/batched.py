@@ -280,7 +280,11 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
 
         f64 = dict(dtype=torch.float64, device=device)
         i32 = dict(dtype=torch.int32, device=device)
-        y_eval = torch.empty((N, n, n_eval), **f64) if n_eval else None
+        # rows padded to a multiple of 4 doubles: the kernel writes aligned
+        # 32-byte groups (include/xsq.h); the result exposes [:, :, :n_eval]
+        pitch = (n_eval + 3) // 4 * 4
+        y_eval_buf = torch.empty((N, n, pitch), **f64) if n_eval else None
+        y_eval = y_eval_buf[:, :, :n_eval] if n_eval else None
         t_final = torch.empty(N, **f64)
         y_final = torch.empty((n, N), **f64)
         h_next = torch.empty(N, **f64)
@@ -312,7 +316,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         a.t_eval = te.data_ptr() if n_eval else None
         a.n_eval = n_eval
         a.max_steps = int(max_steps) if max_steps else 0
-        a.y_eval = y_eval.data_ptr() if n_eval else None
+        a.y_eval = y_eval_buf.data_ptr() if n_eval else None
         a.h_forced = hf.data_ptr() if hf is not None else None
         a.n_forced = hf.numel() if hf is not None else 0
         a.t_final = t_final.data_ptr()

@@ -221,6 +221,7 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     P->t_eval = a->t_eval;
     P->y_eval = a->y_eval;
     P->n_eval = a->n_eval;
+    P->eval_pitch = (a->n_eval + 3) & ~3;     // rows padded to 32 bytes
     P->h_forced = a->h_forced;
     P->n_forced = a->n_forced;
     P->max_steps = a->max_steps > 0 ? a->max_steps
@@ -394,7 +395,8 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d.params = np ? (const double*)h2d(h->params, (size_t)N * np * nd) : nullptr;
     d.t_eval = h->n_eval ? (const double*)h2d(h->t_eval, (size_t)h->n_eval * nd) : nullptr;
     d.h_forced = h->n_forced ? (const double*)h2d(h->h_forced, (size_t)h->n_forced * nd) : nullptr;
-    d.y_eval = h->n_eval ? (double*)dalloc((size_t)N * ns * h->n_eval * nd) : nullptr;
+    const size_t pitch = ((size_t)h->n_eval + 3) & ~(size_t)3;
+    d.y_eval = h->n_eval ? (double*)dalloc((size_t)N * ns * pitch * nd) : nullptr;
     d.t_final = (double*)dalloc((size_t)N * nd);
     d.y_final = (double*)dalloc((size_t)N * ns * nd);
     d.h_next = h->h_next ? (double*)dalloc((size_t)N * nd) : nullptr;
@@ -409,7 +411,11 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
             if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 rc = XSQ_ERR_CUDA;
     };
-    if (h->n_eval) d2h(h->y_eval, d.y_eval, (size_t)N * ns * h->n_eval * nd);
+    if (h->n_eval && rc == XSQ_OK)            // strip the row padding
+        if (cudaMemcpy2DAsync(h->y_eval, (size_t)h->n_eval * nd, d.y_eval, pitch * nd,
+                              (size_t)h->n_eval * nd, (size_t)N * ns,
+                              cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = XSQ_ERR_CUDA;
     d2h(h->t_final, d.t_final, (size_t)N * nd);
     d2h(h->y_final, d.y_final, (size_t)N * ns * nd);
     if (h->h_next) d2h(h->h_next, d.h_next, (size_t)N * nd);

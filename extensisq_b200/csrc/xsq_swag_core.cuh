@@ -153,11 +153,7 @@ struct SwagLane {
                P.direction * (P.t_eval[ieval] - t) <= 0.0) {
             double yout[NL];
             interp(P.t_eval[ieval], yout);
-#pragma unroll
-            for (int c = 0; c < NL; ++c) {
-                const long long row = sys * (long long)R::N + R::comp(c, lane);
-                P.y_eval[row * P.n_eval + ieval] = yout[c];
-            }
+            eval_put<R>(P, sys, lane, ieval, yout);
             ++ieval;
         }
     }
@@ -396,13 +392,7 @@ struct SwagLane {
         for (int c = 0; c < NL; ++c)
             P.y_final[(long long)R::comp(c, lane) * P.n_lanes + sys] = y[c];
         if (P.n_eval > 0 && ieval < P.n_eval) {
-            for (int i = ieval; i < P.n_eval; ++i)
-#pragma unroll
-                for (int c = 0; c < NL; ++c) {
-                    const long long row =
-                        sys * (long long)R::N + R::comp(c, lane);
-                    P.y_eval[row * P.n_eval + i] = constant ? y[c] : XSQ_NAN;
-                }
+            eval_finish<R>(P, sys, lane, ieval, constant, y);
             if (constant) ieval = P.n_eval;
         }
         if (!R::WARP || lane == 0) {

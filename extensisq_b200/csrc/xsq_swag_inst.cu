@@ -16,7 +16,8 @@ static int launch_swag_one(const RkDev& P, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) !=
         cudaSuccess)
         return XSQ_ERR_CUDA;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, 0) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, kern, BLOCK, P.n_eval > 0 ? sizeof(double) * 4 * R::NL * BLOCK : 0) !=
             cudaSuccess || occ < 1)
         return XSQ_ERR_CUDA;
     const long long per_block = R::WARP ? BLOCK / 32 : BLOCK;
@@ -24,7 +25,9 @@ static int launch_swag_one(const RkDev& P, cudaStream_t st) {
     long long grid = (long long)n_sm * occ;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, BLOCK, 0, st>>>(P);
+    // dense-output staging: 4 points x NL components per thread
+    const size_t smem = P.n_eval > 0 ? sizeof(double) * 4 * R::NL * BLOCK : 0;
+    kern<<<(unsigned)grid, BLOCK, smem, st>>>(P);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
 }

@@ -383,7 +383,12 @@ int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
     if (grid < 1) grid = 1;
     RkDev Pc = P;
     void* args[] = {&Pc};
-    CUresult cr = g_api.LaunchKernel(c.fn, (unsigned)grid, 1, 1, 128, 1, 1, 0,
+    // dense-output staging buffer (xsq_rk_core.cuh::eval_put): 4 x NL x 128
+    int ns = 0, npar = 0;
+    if (rhs >= XSQ_RHS_USER_BASE) { ns = g_rhs[rhs - XSQ_RHS_USER_BASE].n_state; (void)npar; }
+    else ns = 6;   // built-in rhs with a user tableau: NL <= 6
+    const unsigned smem = P.n_eval > 0 ? (unsigned)(sizeof(double) * 4 * ns * 128) : 0;
+    CUresult cr = g_api.LaunchKernel(c.fn, (unsigned)grid, 1, 1, 128, 1, 1, smem,
                                      (CUstream)st, args, nullptr);
     count_launch();
     if (cr != CUDA_SUCCESS) {

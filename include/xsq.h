@@ -121,7 +121,8 @@ typedef struct xsq_rk_args {
     const double* t_eval;     /* [n_eval] sorted along the direction, or NULL */
     int32_t n_eval;
     int32_t max_steps;        /* attempted-step budget per lane, <=0: 2^31-1 */
-    double* y_eval;           /* [n_lanes][n_state][n_eval]                  */
+    double* y_eval;           /* [n_lanes][n_state][pitch], pitch = n_eval
+                                 rounded up to a multiple of 4 (32-byte rows) */
     const double* h_forced;   /* forced |h| sequence [n_forced] or NULL      */
     int32_t n_forced;
     int32_t reserved0;
