@@ -405,6 +405,30 @@ def main():
                              # written per launch (algorithmic 1.342 GB)
                              "traffic": 1.3266e9,
                              "bytes_per_point_stage": 40}}
+            try:    # end-to-end SSV2stab solve on the same slab (host loop,
+                    # error-norm reductions, first/final stages included)
+                import time as _t
+                nxs, rws = 16384, 2048
+                xg = torch.arange(1, nxs + 1, dtype=torch.float64, device=dev) / (nxs + 1)
+                yg = torch.arange(1, rws + 1, dtype=torch.float64, device=dev) / (rws + 1)
+                u0 = torch.outer(torch.sin(math.pi * yg), torch.sin(math.pi * xg))
+                rho = 8.0 * (nxs + 1.0) ** 2 + 2.0
+                for _ in range(2):
+                    torch.cuda.synchronize()
+                    t0 = _t.perf_counter()
+                    rr = xb.solve_pde_rkc("heat2d_reaction", (0.0, 3e-4), u0,
+                                          rho_jac=rho, rtol=1e-4, atol=1e-4,
+                                          max_steps=100)
+                    torch.cuda.synchronize()
+                    dt = _t.perf_counter() - t0
+                line["ssv2stab"]["solve"] = {
+                    "t_span": [0.0, 3e-4], "accepted": rr.n_accepted,
+                    "rejected": rr.n_rejected, "nfev": rr.nfev, "s_max": rr.maxm,
+                    "seconds": dt, "kernel_launches": rr.kernel_launches,
+                    "algorithmic_GBps": nxs * rws * 40 * rr.nfev / dt / 1e9}
+                del u0, rr
+            except Exception as exc:     # never lose the headline line
+                line["ssv2stab"]["solve"] = {"error": repr(exc)}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             v_np, a_np, dt_np, lanes_np = cpu_numpy_port(

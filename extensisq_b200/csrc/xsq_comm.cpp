@@ -1,6 +1,8 @@
-// xsq_comm.cpp -- NCCL plumbing for the domain-decomposed SSV2stab path
-// (per stage a nearest-neighbour halo over NVLink, per
-// step attempt a scalar all-gather).  The reference has no communication layer
+// xsq_comm.cpp -- NCCL plumbing for the domain-decomposed SSV2stab path: the
+// set-up exchange of CUDA-IPC handles and, per step attempt, the all-gather of
+// one scalar per rank (error norm).  The per-stage halo does NOT go through
+// NCCL: the stage kernel loads the neighbour's boundary row in place over
+// NVLink (xsq_rkc.cu).  The reference has no communication layer
 // at all (single Python thread); this file is new.
 #include "xsq_comm.h"
 
@@ -27,10 +29,6 @@ struct Nccl {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*);
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
     ncclResult_t (*CommDestroy)(ncclComm_t);
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*GroupStart)();
-    ncclResult_t (*GroupEnd)();
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
                               cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
@@ -55,9 +53,8 @@ bool load() {
     if (!g.lib) { set_detail("cannot dlopen libnccl.so.2"); return false; }
     bool ok = bind("ncclGetUniqueId", &g.GetUniqueId) &&
               bind("ncclCommInitRank", &g.CommInitRank) &&
-              bind("ncclCommDestroy", &g.CommDestroy) && bind("ncclSend", &g.Send) &&
-              bind("ncclRecv", &g.Recv) && bind("ncclGroupStart", &g.GroupStart) &&
-              bind("ncclGroupEnd", &g.GroupEnd) && bind("ncclAllGather", &g.AllGather) &&
+              bind("ncclCommDestroy", &g.CommDestroy) &&
+              bind("ncclAllGather", &g.AllGather) &&
               bind("ncclGetErrorString", &g.GetErrorString);
     if (!ok) set_detail("libnccl is missing a required symbol");
     return ok;
@@ -100,20 +97,8 @@ void comm_destroy(Comm* c) {
 int comm_rank(const Comm* c) { return c->rank; }
 int comm_world(const Comm* c) { return c->world; }
 
-int comm_halo(Comm* c, int up, int down, const double* first_row, double* top_ghost,
-              const double* last_row, double* bottom_ghost, size_t n, cudaStream_t st) {
-    int rc = 0;
-    rc |= check(g.GroupStart(), "ncclGroupStart");
-    if (up >= 0) {
-        rc |= check(g.Send(first_row, n, ncclDouble, up, c->nccl, st), "ncclSend");
-        rc |= check(g.Recv(top_ghost, n, ncclDouble, up, c->nccl, st), "ncclRecv");
-    }
-    if (down >= 0) {
-        rc |= check(g.Send(last_row, n, ncclDouble, down, c->nccl, st), "ncclSend");
-        rc |= check(g.Recv(bottom_ghost, n, ncclDouble, down, c->nccl, st), "ncclRecv");
-    }
-    rc |= check(g.GroupEnd(), "ncclGroupEnd");
-    return rc;
+int comm_allgather_bytes(Comm* c, const void* send, void* recv, size_t nbytes, cudaStream_t st) {
+    return check(g.AllGather(send, recv, nbytes, ncclChar, c->nccl, st), "ncclAllGather");
 }
 
 int comm_allgather1(Comm* c, const double* send, double* recv, cudaStream_t st) {

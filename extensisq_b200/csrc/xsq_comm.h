@@ -14,12 +14,8 @@ void comm_destroy(Comm* c);
 int comm_rank(const Comm* c);
 int comm_world(const Comm* c);
 
-// Nearest-neighbour halo exchange of one row each way (grouped send/recv):
-// send `first_row` to `up` and receive its last row into `top_ghost`; send
-// `last_row` to `down` and receive its first row into `bottom_ghost`.
-// up/down < 0: no neighbour on that side.
-int comm_halo(Comm* c, int up, int down, const double* first_row, double* top_ghost,
-              const double* last_row, double* bottom_ghost, size_t n, cudaStream_t st);
+// all-gather of `nbytes` bytes per rank (device buffers)
+int comm_allgather_bytes(Comm* c, const void* send, void* recv, size_t nbytes, cudaStream_t st);
 // all-gather of one double per rank: recv[r] = *send of rank r
 int comm_allgather1(Comm* c, const double* send, double* recv, cudaStream_t st);
 

@@ -28,6 +28,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -64,13 +66,27 @@ __device__ __forceinline__ void store4(double* __restrict__ p, const double (&v)
     reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
 }
 
-__device__ __forceinline__ void rhs_heat2d(const double* __restrict__ u, int nx,
-                                           size_t idx, int col, double inv_h2,
-                                           double (&f)[PX]) {
+// Rows above the slab's first row and below its last row are read through
+// `up_row` / `dn_row`: the slab's own (zero) ghost row at the domain edge, or --
+// multi-GPU -- the neighbour rank's boundary row in ITS memory, mapped with
+// CUDA IPC and loaded over NVLink by the threads that need it.  The halo is
+// therefore part of the stage kernel; there is no separate exchange step.
+__device__ __forceinline__ void load4_peer(const double* p, double (&v)[PX]) {
+    const double2 a = __ldcv(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldcv(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+__device__ __forceinline__ void rhs_heat2d(const double* __restrict__ u,
+                                           const double* up_row, const double* dn_row,
+                                           int nx, int rows, int row, size_t idx, int col,
+                                           double inv_h2, double (&f)[PX]) {
     double c[PX], up[PX], dn[PX];
     load4(u + idx, c);
-    load4(u + idx - nx, up);
-    load4(u + idx + nx, dn);
+    if (row == 0) load4_peer(up_row + col, up);
+    else load4(u + idx - nx, up);
+    if (row == rows - 1) load4_peer(dn_row + col, dn);
+    else load4(u + idx + nx, dn);
     const double left = col > 0 ? __ldg(u + idx - 1) : 0.0;
     const double right = col + PX < nx ? __ldg(u + idx + PX) : 0.0;
 #pragma unroll
@@ -82,6 +98,30 @@ __device__ __forceinline__ void rhs_heat2d(const double* __restrict__ u, int nx,
     }
 }
 
+// Neighbour handshake (one thread): tell both neighbours that every kernel
+// enqueued before this one has finished (so the buffer about to be read is
+// complete and the buffer about to be overwritten is no longer being read),
+// then wait for the same message from them.  Flags live in the RECEIVER's
+// memory (remote store, local spin).  The spin is bounded: on timeout an
+// error word is set and the host aborts the solve instead of hanging the GPU.
+__global__ void k_peer_sync(long long seq, volatile long long* up_flag_remote,
+                            volatile long long* dn_flag_remote,
+                            volatile long long* my_flags, long long* err) {
+    __threadfence_system();
+    if (up_flag_remote) *up_flag_remote = seq;     // my "from_down" slot at the upper rank
+    if (dn_flag_remote) *dn_flag_remote = seq;     // my "from_up" slot at the lower rank
+    __threadfence_system();
+    const long long t0 = clock64();
+    const long long budget = 4000000000LL;         // ~2 s
+    bool ok = true;
+    if (up_flag_remote)
+        while (my_flags[0] < seq) if (clock64() - t0 > budget) { ok = false; break; }
+    if (dn_flag_remote && ok)
+        while (my_flags[1] < seq) if (clock64() - t0 > budget) { ok = false; break; }
+    if (!ok) *err = seq;
+    __threadfence_system();
+}
+
 #define XSQ_RKC_INDEX                                                     \
     const int col = (blockIdx.x * TX + threadIdx.x) * PX;                 \
     const int row = blockIdx.y * TY + threadIdx.y;                        \
@@ -90,11 +130,12 @@ __device__ __forceinline__ void rhs_heat2d(const double* __restrict__ u, int nx,
 
 // dy = f(u)
 __global__ void __launch_bounds__(TX* TY) k_eval(Slab S, const double* __restrict__ u,
+                                                 const double* up_row, const double* dn_row,
                                                  double* __restrict__ dy) {
     XSQ_RKC_INDEX
     if (!active) return;
     double f[PX];
-    rhs_heat2d(u, S.nx, idx, col, S.inv_h2, f);
+    rhs_heat2d(u, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
     store4(dy + idx, f);
 }
 
@@ -115,14 +156,15 @@ __global__ void __launch_bounds__(TX* TY) k_axpy(Slab S, const double* __restric
 // Stage j >= 2 (sommeijer.py:311-313), fused with the RHS evaluation:
 //   Y_j = mu*Y_{j-1} + nu*Y_{j-2} + (1-mu-nu)*y_n + h*mus*(f(Y_{j-1}) - a_{j-1}*f_n)
 __global__ void __launch_bounds__(TX* TY)
-    k_stage(Slab S, const double* __restrict__ yjm1, const double* __restrict__ yjm2,
+    k_stage(Slab S, const double* __restrict__ yjm1, const double* up_row,
+            const double* dn_row, const double* __restrict__ yjm2,
             const double* __restrict__ yn, const double* __restrict__ fn,
             double* __restrict__ yj, double mu, double nu, double c3, double hmus,
             double ajm1) {
     XSQ_RKC_INDEX
     if (!active) return;
     double f[PX], a[PX], b[PX], c[PX], d[PX], o[PX];
-    rhs_heat2d(yjm1, S.nx, idx, col, S.inv_h2, f);
+    rhs_heat2d(yjm1, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
     load4(yjm1 + idx, a);
     load4(yjm2 + idx, b);
     load4(yn + idx, c);
@@ -152,14 +194,15 @@ __device__ __forceinline__ void block_sum_to(double s, double* __restrict__ part
 //   f1 = f(y);  est = 0.8*(yn - y) + 0.4*h*(fn + f1);  wt = atol + rtol*max(|y|,|yn|)
 //   partial[block] = sum (est/wt)^2
 __global__ void __launch_bounds__(TX* TY)
-    k_final(Slab S, const double* __restrict__ y, const double* __restrict__ yn,
+    k_final(Slab S, const double* __restrict__ y, const double* up_row, const double* dn_row,
+            const double* __restrict__ yn,
             const double* __restrict__ fn, double* __restrict__ f1, double h, double rtol,
             double atol, double* __restrict__ partial) {
     XSQ_RKC_INDEX
     double s = 0.0;
     if (active) {
         double f[PX], a[PX], b[PX], c[PX];
-        rhs_heat2d(y, S.nx, idx, col, S.inv_h2, f);
+        rhs_heat2d(y, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
         load4(y + idx, a);
         load4(yn + idx, b);
         load4(fn + idx, c);
@@ -296,21 +339,34 @@ struct Ctx {
     }
     void launched() { count_launch(); ++launches; }
 
-    // Fill the ghost rows of a padded vector: neighbour boundary rows over
-    // NCCL, or nothing to do at the domain edge (ghost rows stay zero).
-    void halo(double* u) {
-        if (world == 1 || !comm) return;
+    // ---- peer (NVLink) halo -------------------------------------------------
+    double* base = nullptr;            // start of this rank's vector storage
+    const double* peer_up = nullptr;   // IPC mapping of the upper rank's storage
+    const double* peer_dn = nullptr;
+    int rows_up = 0;                   // interior rows of the upper rank's slab
+    long long* flags = nullptr;        // [0] from upper rank, [1] from lower, [2] error
+    long long* up_flag_remote = nullptr;   // upper rank's flags[1]
+    long long* dn_flag_remote = nullptr;   // lower rank's flags[0]
+    long long seq = 0;
+    const double* up_row = nullptr;    // set by halo() for the vector about to be read
+    const double* dn_row = nullptr;
+
+    // Prepare the stencil read of the padded vector u: at a domain edge the
+    // neighbour row is u's own zero ghost row; between ranks it is the
+    // neighbour's boundary row of the SAME vector (identical layout and
+    // rotation state on every rank), read in place over NVLink after a
+    // neighbour handshake.  No data is copied.
+    void halo(const double* u) {
         const size_t nx = S.nx;
-        double* top_ghost = u;
-        double* first_row = u + nx;
-        double* last_row = u + nx * S.rows;
-        double* bottom_ghost = u + nx * (S.rows + 1);
-        if (comm_halo(comm, rank > 0 ? rank - 1 : -1, rank + 1 < world ? rank + 1 : -1,
-                      first_row, top_ghost, last_row, bottom_ghost, nx, st) != 0 &&
-            rc == XSQ_OK) {
-            rc = XSQ_ERR_CUDA;
-            set_detail("NCCL halo exchange failed");
-        }
+        up_row = u;                                   // top ghost row
+        dn_row = u + nx * (S.rows + 1);               // bottom ghost row
+        if (world == 1) return;
+        const size_t off = (size_t)(u - base);
+        if (peer_up) up_row = peer_up + off + nx * rows_up;   // its last interior row
+        if (peer_dn) dn_row = peer_dn + off + nx;             // its first interior row
+        ++seq;
+        k_peer_sync<<<1, 1, 0, st>>>(seq, up_flag_remote, dn_flag_remote, flags, flags + 2);
+        launched();
     }
 
     // global sum of this rank's block partials: deterministic on every rank
@@ -329,6 +385,14 @@ struct Ctx {
             fail("global_sum");
             return NAN;
         }
+        if (world > 1 && flags) {
+            long long e = 0;
+            cudaMemcpy(&e, flags + 2, sizeof e, cudaMemcpyDeviceToHost);
+            if (e != 0 && rc == XSQ_OK) {
+                rc = XSQ_ERR_CUDA;
+                set_detail("rkc: neighbour handshake timed out (peer rank stalled or failed)");
+            }
+        }
         double s = 0.0;
         for (int r = 0; r < world; ++r) s += scalar_host[r];
         return s;
@@ -336,7 +400,7 @@ struct Ctx {
 
     void eval(double* u, double* dy) {           // dy = f(u), with halo
         halo(u);
-        k_eval<<<grid, block, 0, st>>>(S, u, dy);
+        k_eval<<<grid, block, 0, st>>>(S, u, up_row, dn_row, dy);
         launched();
     }
     double norm2(const double* a) {
@@ -386,19 +450,86 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     C.n_total = (long long)A->nx * A->rows_global;
     const size_t na = C.S.n_alloc();
     // device scratch: yn, fn, w0, w1, w2, V + partials + scalars
+    {   // keep freed scratch cached in the stream-ordered pool: by default the
+        // pool returns memory to the OS at every synchronisation, and mapping
+        // gigabytes again on the next call costs hundreds of milliseconds
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    const bool dbg0 = getenv("XSQ_RKC_DEBUG") != nullptr;
+    auto wall0 = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_enter = wall0();
     double* buf = nullptr;
-    const size_t total = na * 6 + C.nblocks + C.world + 8;
-    if (cudaMallocAsync((void**)&buf, total * sizeof(double), st) != cudaSuccess) {
+    const size_t total = na * 6 + C.nblocks + C.world + 8 + 64;
+    const bool multi = C.world > 1;
+    // multi-GPU: plain cudaMalloc so the storage can be exported with CUDA IPC
+    cudaError_t me = multi ? cudaMalloc((void**)&buf, total * sizeof(double))
+                           : cudaMallocAsync((void**)&buf, total * sizeof(double), st);
+    if (me != cudaSuccess) {
         set_detail("rkc: out of device memory");
         return XSQ_ERR_NOMEM;
     }
+    auto release = [&]() {
+        if (C.peer_up) cudaIpcCloseMemHandle((void*)C.peer_up);
+        if (C.peer_dn) cudaIpcCloseMemHandle((void*)C.peer_dn);
+        if (multi) { cudaStreamSynchronize(st); cudaFree(buf); }
+        else cudaFreeAsync(buf, st);
+    };
     cudaMemsetAsync(buf, 0, total * sizeof(double), st);      // ghost rows = Dirichlet 0
+    C.base = buf;
+    C.flags = reinterpret_cast<long long*>(buf + na * 6 + C.nblocks + C.world + 8);
+    if (multi) {
+        // exchange (IPC handle, rows_local) with an all-gather, open the two
+        // neighbours' storage
+        struct Card { cudaIpcMemHandle_t h; long long rows; long long pad; };
+        static_assert(sizeof(Card) == 80, "card");
+        Card mine;
+        std::memset(&mine, 0, sizeof mine);
+        if (cudaIpcGetMemHandle(&mine.h, buf) != cudaSuccess) {
+            set_detail("rkc: cudaIpcGetMemHandle failed");
+            release();
+            return XSQ_ERR_CUDA;
+        }
+        mine.rows = A->rows_local;
+        char* xchg = nullptr;
+        std::vector<Card> cards(C.world);
+        bool ok = cudaMalloc((void**)&xchg, sizeof(Card) * (C.world + 1)) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(xchg, &mine, sizeof(Card), cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && comm_allgather_bytes(comm, xchg, xchg + sizeof(Card), sizeof(Card), st) == 0;
+        ok = ok && cudaMemcpyAsync(cards.data(), xchg + sizeof(Card), sizeof(Card) * C.world,
+                                   cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+        if (xchg) cudaFree(xchg);
+        void* p = nullptr;
+        if (ok && C.rank > 0) {
+            ok = cudaIpcOpenMemHandle(&p, cards[C.rank - 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            C.peer_up = (const double*)p;
+            C.rows_up = (int)cards[C.rank - 1].rows;
+        }
+        if (ok && C.rank + 1 < C.world) {
+            ok = cudaIpcOpenMemHandle(&p, cards[C.rank + 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            C.peer_dn = (const double*)p;
+        }
+        if (!ok) {
+            set_detail(std::string("rkc: peer mapping failed: ") + cudaGetErrorString(cudaGetLastError()));
+            release();
+            return XSQ_ERR_CUDA;
+        }
+        const size_t flag_off = na * 6 + C.nblocks + C.world + 8;
+        if (C.peer_up) C.up_flag_remote = (long long*)(C.peer_up + flag_off) + 1;
+        if (C.peer_dn) C.dn_flag_remote = (long long*)(C.peer_dn + flag_off) + 0;
+    }
     double *yn = buf, *fn = buf + na, *w0 = buf + 2 * na, *w1 = buf + 3 * na,
            *w2 = buf + 4 * na, *V = buf + 5 * na;
     C.partial = buf + 6 * na;
     C.scalar_dev = C.partial + C.nblocks;
     if (cudaMallocHost((void**)&C.scalar_host, sizeof(double) * C.world) != cudaSuccess) {
-        cudaFreeAsync(buf, st);
+        release();
         return XSQ_ERR_NOMEM;
     }
     xsq_rkc_result_t* R = A->result;
@@ -443,6 +574,14 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
         status = 0;
     }
     double* W[3] = {w0, w1, w2};                     // rotating work vectors
+    const bool dbg = getenv("XSQ_RKC_DEBUG") != nullptr;
+    auto wall_ms = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    double t_dbg = wall_ms();
+    if (dbg) { cudaStreamSynchronize(st); std::fprintf(stderr, "[rkc r%d] setup %.3f ms\n", C.rank, wall_ms() - t_enter); t_dbg = wall_ms(); }
 
     while (status == 1 && C.rc == XSQ_OK) {
         // ---------------- one step (sommeijer.py:162-271) -------------------
@@ -567,7 +706,8 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
                 const double nu = -bj / bjm2;
                 mus = mu * w1c / w0c;
                 C.halo(W[i1]);
-                k_stage<<<C.grid, C.block, 0, st>>>(C.S, W[i1], i2 < 0 ? yn : W[i2], yn, fn,
+                k_stage<<<C.grid, C.block, 0, st>>>(C.S, W[i1], C.up_row, C.dn_row,
+                                                    i2 < 0 ? yn : W[i2], yn, fn,
                                                     W[i0], mu, nu, 1.0 - mu - nu, h * mus, ajm1);
                 C.launched();
                 ++nfev;
@@ -586,11 +726,18 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
             double* third = W[3 - i0 - i1];
             // ---- final evaluation + error estimate (:214-220) ---------------
             C.halo(y);
-            k_final<<<C.grid, C.block, 0, st>>>(C.S, y, yn, fn, f1, h, rtol, atol, C.partial);
+            k_final<<<C.grid, C.block, 0, st>>>(C.S, y, C.up_row, C.dn_row, yn, fn, f1, h, rtol,
+                                                atol, C.partial);
             C.launched();
             ++nfev;
             err = std::sqrt(C.global_sum() / (double)C.n_total);
             if (C.rc != XSQ_OK) break;
+            if (dbg) {
+                const double now = wall_ms();
+                std::fprintf(stderr, "[rkc r%d] t=%.3e h=%.3e m=%d err=%.3e  %.3f ms (%.4f ms/stage)\n",
+                             C.rank, t, h, m, err, now - t_dbg, (now - t_dbg) / m);
+                t_dbg = now;
+            }
             if (err < 1.0) {
                 // accepted: (yn, fn) <- (y, f1); the old (yn, fn) are the
                 // interpolation data (:246-251), then become work vectors
@@ -648,8 +795,13 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     R->status = status == 1 ? XSQ_LANE_STEP_BUDGET : status;
     R->n_eval_done = ieval;
     R->kernel_launches = C.launches;
-    cudaFreeAsync(buf, st);
+    if (multi) {              // nobody frees storage a neighbour may still read
+        C.halo(yn);
+        cudaStreamSynchronize(st);
+    }
+    release();
     cudaFreeHost(C.scalar_host);
+    if (dbg0) std::fprintf(stderr, "[rkc r%d] total %.3f ms\n", C.rank, wall0() - t_enter);
     if (C.rc != XSQ_OK) return C.rc;
     if (e != cudaSuccess) { set_detail(std::string("rkc: ") + cudaGetErrorString(e)); return XSQ_ERR_CUDA; }
     return XSQ_OK;
@@ -670,13 +822,15 @@ int rkc_stage_bench(int nx, int rows, int reps, double* ms_per_stage, cudaStream
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int w = 0; w < 3; ++w) {
-        k_stage<<<grid, block, 0, st>>>(S, v[1], v[2], yn, fn, v[0], 1.9, -0.95, 0.05, 1e-9, 0.3);
+        k_stage<<<grid, block, 0, st>>>(S, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2], yn, fn,
+                                        v[0], 1.9, -0.95, 0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e0, st);
     for (int r = 0; r < reps; ++r) {
-        k_stage<<<grid, block, 0, st>>>(S, v[(r + 1) % 3], v[(r + 2) % 3], yn, fn, v[r % 3], 1.9,
-                                        -0.95, 0.05, 1e-9, 0.3);
+        const double* in = v[(r + 1) % 3];
+        k_stage<<<grid, block, 0, st>>>(S, in, in, in + (size_t)nx * (rows + 1), v[(r + 2) % 3], yn,
+                                        fn, v[r % 3], 1.9, -0.95, 0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e1, st);
