@@ -480,3 +480,50 @@ def test_forward_then_backward_round_trip():
                                    xb.Pr8, params=prm, rtol=1e-10, atol=1e-12))
     assert (b["status"] == 0).all()
     assert np.abs(b["y_final"] - y0).max() <= 1e-6
+
+
+def test_c_abi_host_buffer_entry_point():
+    """xsq_rk_solve_host: every array pointer is a HOST pointer (NumPy), the
+    H2D/D2H copies happen inside the call -- the binding INTEGRATION.md shows.
+    Must agree bit-for-bit with the device-buffer entry point."""
+    import ctypes as C
+    lib = _lib.load()
+    N, n_eval = 777, 10
+    y0, prm = lorenz_lanes(N, seed=11)
+    te = np.linspace(0.0, 2.0, n_eval)
+    y0_soa = np.ascontiguousarray(y0.T)
+    prm_soa = np.ascontiguousarray(prm.T)
+    atol = np.array([1e-10])
+    out = dict(t_final=np.empty(N), y_final=np.empty((3, N)), h_next=np.empty(N),
+               y_eval=np.empty((N, 3, n_eval)))
+    ints = {k: np.empty(N, np.int32) for k in
+            ("n_accepted", "n_rejected", "nfev", "status", "n_eval_done")}
+    a = _lib.XsqRkArgs()
+    a.struct_size = C.sizeof(_lib.XsqRkArgs)
+    a.method, a.rhs, a.n_state, a.n_param = 2, 0, 3, 3      # CK5, lorenz63
+    a.n_lanes = N
+    a.y0, a.params = y0_soa.ctypes.data, prm_soa.ctypes.data
+    a.t0, a.t_bound, a.rtol = 0.0, 2.0, 1e-8
+    a.atol = atol.ctypes.data_as(C.POINTER(C.c_double))
+    a.n_atol = 1
+    a.first_step, a.max_step = 0.0, float("inf")
+    a.t_eval, a.n_eval, a.y_eval = te.ctypes.data, n_eval, out["y_eval"].ctypes.data
+    a.t_final, a.y_final = out["t_final"].ctypes.data, out["y_final"].ctypes.data
+    a.h_next = out["h_next"].ctypes.data
+    for k, v in ints.items():
+        setattr(a, k, v.ctypes.data)
+    assert lib.xsq_rk_solve_host(C.byref(a), 0) == 0, \
+        lib.xsq_last_error_detail().decode()
+    r = to_np(xb.solve_ivp_batched("lorenz63", (0.0, 2.0), y0, xb.CK5,
+                                   params=prm, rtol=1e-8, atol=1e-10,
+                                   t_eval=te))
+    assert (ints["status"] == 0).all()
+    assert np.array_equal(ints["n_accepted"], r["n_accepted"])
+    assert np.array_equal(ints["nfev"], r["nfev"])
+    assert np.array_equal(out["y_final"].T, r["y_final"])
+    assert np.array_equal(out["y_eval"], r["y"])
+    assert np.array_equal(out["y_eval"][:, :, 0], y0)
+    # argument errors come back as XSQ_ERR_ARG with the reference's message
+    a.rtol = -1.0
+    assert lib.xsq_rk_solve_host(C.byref(a), 0) == -1
+    assert b"rtol" in lib.xsq_last_error_detail()
