@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters,
 static int dispatch(int method, int rhs, const RkDev& P, cudaStream_t st,
                     LaunchInfo* info) {
     if (rhs >= XSQ_RHS_USER_BASE) return user_rk_launch(method, rhs, P, st);
+    int rc = launch_ens_init(rhs, P, st);       // f0 + h_start for all lanes
+    if (rc != XSQ_OK) return rc;
     if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
     switch (method) {
         case XSQ_TS5: return launch_Ts5(rhs, P, st, info);
@@ -244,8 +246,24 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     return XSQ_OK;
 }
 
+// Keep freed scratch cached in the stream-ordered pool: by default the pool
+// returns memory to the OS at every synchronisation, and mapping tens of
+// megabytes again on each call costs milliseconds.
+void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
                         LaunchInfo* info) {
+    keep_pool_memory();
     RkDev P;
     MethodInfo mi;
     std::vector<double> atol;
@@ -253,7 +271,12 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     if (rc != XSQ_OK) return rc;
     if (a->n_lanes == 0) return XSQ_OK;
     // scratch: [queue counter (8 B, padded to 16)] [atol vector]
-    const size_t bytes = 16 + atol.size() * sizeof(double);
+    //          [init_h N] [init_f0 n_state x N] [init_nfev N]
+    const size_t N = (size_t)a->n_lanes, ns = atol.size();
+    const size_t off_h = (16 + ns * sizeof(double) + 15) & ~(size_t)15;
+    const size_t off_f = off_h + N * sizeof(double);
+    const size_t off_n = off_f + N * ns * sizeof(double);
+    const size_t bytes = off_n + N * sizeof(int);
     char* scratch = nullptr;
     XSQ_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
     XSQ_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
@@ -263,6 +286,10 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     // the pageable atol copy is staged by the runtime before returning
     P.queue = (unsigned long long*)scratch;
     P.atol_dev = (const double*)(scratch + 16);
+    P.init_h = (double*)(scratch + off_h);
+    P.init_f0 = (double*)(scratch + off_f);
+    P.init_nfev = (int*)(scratch + off_n);
+    P.morder = (a->method == XSQ_METHOD_SWAG) ? 1 : mi.order2;
     rc = dispatch(a->method, a->rhs, P, st, info);
     cudaError_t e = cudaFreeAsync(scratch, st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");

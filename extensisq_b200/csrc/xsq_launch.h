@@ -23,6 +23,7 @@ XSQ_DECL_LAUNCH(CFMR7osc)
 #undef XSQ_DECL_LAUNCH
 
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st);
+int launch_ens_init(int rhs, const RkDev& P, cudaStream_t st);
 
 void count_launch();
 

@@ -73,6 +73,11 @@ struct RkDev {
     unsigned long long* queue;
     int n_eval, n_forced, max_steps, interpolant;
     int eval_pitch;               // row pitch of y_eval in doubles, multiple of 4
+    // written by ens_init (one convergent pass over all lanes), read at refill
+    double* init_f0;              // SoA [n_state][n_lanes]: f(t0, y0)
+    double* init_h;               // [n_lanes]: |h| from h_start (if needed)
+    int* init_nfev;               // [n_lanes]: evaluations spent so far
+    int morder;                   // h_start's order argument (common.py:210-212)
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -362,6 +367,45 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
     return fabs(h);
 }
 
+// ---- initialisation pass ---------------------------------------------------
+// f(t0, y0) and Watts' starting step for EVERY lane, one thread (or warp) per
+// lane, fully convergent.  The persistent kernel then refills a finished lane
+// with a handful of loads; doing the 4-5 RHS evaluations + log10/pow of
+// h_start inside the refill would stall the other 31 lanes of the warp each
+// time (~15 % of the run for trajectories of a few hundred steps).
+template <class R>
+__device__ __forceinline__ void ens_init_body(const RkDev& P) {
+    const int lane = threadIdx.x & 31;
+    const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = R::WARP ? gthread / 32 : gthread;
+    if (idx >= P.n_lanes) return;
+    double y[R::NL], f[R::NL], prm[R::NPL];
+#pragma unroll
+    for (int k = 0; k < R::NL; ++k)
+        y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+    R::load_params(P.params, idx, P.n_lanes, lane, prm);
+    int nfev = 1;
+    R::f(P.t0, y, prm, f);
+    double h = 0.0;
+    if (P.n_forced == 0 && !(P.first_step > 0.0)) {
+        const double b = P.t0 + P.direction *
+            fmin(fabs(P.t_bound - P.t0), P.max_step);
+        h = h_start_dev<R>(P, P.t0, b, y, f, prm, P.morder, lane, nfev);
+    }
+#pragma unroll
+    for (int k = 0; k < R::NL; ++k)
+        P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx] = f[k];
+    if (!R::WARP || lane == 0) {
+        P.init_h[idx] = h;
+        P.init_nfev[idx] = nfev;
+    }
+}
+
+template <class R, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) ens_init(const RkDev P) {
+    ens_init_body<R>(P);
+}
+
 // ---- one trajectory ---------------------------------------------------------
 template <class Tab, class R>
 struct Lane {
@@ -389,8 +433,10 @@ struct Lane {
             y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
         n_acc = n_rej = n_pre = ieval = 0;
-        nfev = 1;
-        R::f(t, y, prm, f);
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            f[k] = P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+        nfev = P.init_nfev[idx];
         standard_sc = true;
         fresh = true;
         step_rejected = false;
@@ -398,16 +444,10 @@ struct Lane {
         h_prev = 0.0;
         lerr_old = 0.0;
         min_step = 0.0;
-        if (P.n_forced > 0) {
-            h_abs = P.h_forced[0];
-        } else if (P.first_step > 0.0) {
-            h_abs = P.first_step;
-        } else {
-            const double b = P.t0 + P.direction *
-                fmin(fabs(P.t_bound - P.t0), P.max_step);
-            h_abs = h_start_dev<R>(P, P.t0, b, y, f, prm, Tab::ORDER2, lane,
-                                   nfev);
-        }
+        // first step: forced table, first_step, or Watts' h_start (ens_init)
+        if (P.n_forced > 0) h_abs = P.h_forced[0];
+        else if (P.first_step > 0.0) h_abs = P.first_step;
+        else h_abs = P.init_h[idx];
     }
 
     // _reassess_stepsize, common.py:310-331.  attempt() tests the common case

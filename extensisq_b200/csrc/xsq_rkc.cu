@@ -39,6 +39,8 @@
 
 namespace xsq {
 
+void keep_pool_memory();   // xsq_api.cu
+
 namespace {
 
 constexpr double kURound = 0x1.0000000000001p-53;
@@ -450,17 +452,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     C.n_total = (long long)A->nx * A->rows_global;
     const size_t na = C.S.n_alloc();
     // device scratch: yn, fn, w0, w1, w2, V + partials + scalars
-    {   // keep freed scratch cached in the stream-ordered pool: by default the
-        // pool returns memory to the OS at every synchronisation, and mapping
-        // gigabytes again on the next call costs hundreds of milliseconds
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
+    keep_pool_memory();
     const bool dbg0 = getenv("XSQ_RKC_DEBUG") != nullptr;
     auto wall0 = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_enter = wall0();

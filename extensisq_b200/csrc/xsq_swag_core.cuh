@@ -64,16 +64,14 @@ struct SwagLane {
         for (int c = 0; c < NL; ++c)
             y[c] = P.y0[(long long)R::comp(c, lane) * P.n_lanes + idx];
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
-        R::f(t, y, prm, yp);
-        nfev = 1;
-        if (P.first_step > 0.0) {
-            h = copysign(P.first_step, P.direction);
-        } else {
-            const double b = P.t0 + copysign(
-                fmin(fabs(P.t_bound - P.t0), P.max_step), P.direction);
-            h = copysign(h_start_dev<R>(P, P.t0, b, y, yp, prm, 1, lane, nfev),
-                         b - P.t0);
-        }
+#pragma unroll
+        for (int c = 0; c < NL; ++c)
+            yp[c] = P.init_f0[(long long)R::comp(c, lane) * P.n_lanes + idx];
+        nfev = P.init_nfev[idx];
+        const double b = P.t0 + copysign(
+            fmin(fabs(P.t_bound - P.t0), P.max_step), P.direction);
+        if (P.first_step > 0.0) h = copysign(P.first_step, P.direction);
+        else h = copysign(P.init_h[idx], b - P.t0);      // ens_init, morder = 1
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
             const double yb = y[c] - h * yp[c];

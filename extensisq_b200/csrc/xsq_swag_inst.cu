@@ -32,6 +32,27 @@ static int launch_swag_one(const RkDev& P, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
 }
 
+template <class R>
+static int launch_init_one(const RkDev& P, cudaStream_t st) {
+    constexpr int BLOCK = 128;
+    const long long threads = R::WARP ? P.n_lanes * 32 : P.n_lanes;
+    const long long grid = (threads + BLOCK - 1) / BLOCK;
+    if (grid < 1) return XSQ_OK;
+    ens_init<R, BLOCK><<<(unsigned)grid, BLOCK, 0, st>>>(P);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+}
+
+int launch_ens_init(int rhs, const RkDev& P, cudaStream_t st) {
+    switch (rhs) {
+        case XSQ_RHS_LORENZ63: return launch_init_one<rhs::Lorenz63>(P, st);
+        case XSQ_RHS_VANDERPOL: return launch_init_one<rhs::VanDerPol>(P, st);
+        case XSQ_RHS_ARENSTORF: return launch_init_one<rhs::Arenstorf>(P, st);
+        case XSQ_RHS_NBODY32: return launch_init_one<rhs::NBody32>(P, st);
+        default: return XSQ_ERR_UNSUPPORTED;
+    }
+}
+
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st) {
     switch (rhs) {
         case XSQ_RHS_LORENZ63: return launch_swag_one<rhs::Lorenz63>(P, st);

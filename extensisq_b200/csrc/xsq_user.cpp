@@ -51,6 +51,7 @@ struct UserTab {
 struct Compiled {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
+    CUfunction init_fn = nullptr;
     int occ = 0;
 };
 std::map<std::string, Compiled> g_cache;
@@ -269,6 +270,8 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
     if (cr == CUDA_SUCCESS)
         cr = g_api.ModuleGetFunction(&out->fn, out->mod, "xsq_user_kernel");
     if (cr == CUDA_SUCCESS)
+        cr = g_api.ModuleGetFunction(&out->init_fn, out->mod, "xsq_user_init");
+    if (cr == CUDA_SUCCESS)
         cr = g_api.OccupancyMaxActiveBlocks(&out->occ, out->fn, 128, 0);
     if (cr != CUDA_SUCCESS) {
         const char* es = nullptr;
@@ -337,7 +340,12 @@ int user_build_source(int method, int rhs, std::string* src, std::string* key) {
                       "xsq_user_kernel(const xsq::RkDev P) {\n"
                       "    xsq::rk_persistent_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
                       minb_for(s, nl), tabname.c_str(), rhsname.c_str());
-    *src = body + buf;
+    char buf2[256];
+    std::snprintf(buf2, sizeof buf2,
+                  "extern \"C\" __global__ void __launch_bounds__(128)\n"
+                  "xsq_user_init(const xsq::RkDev P) { xsq::ens_init_body<xsq::rhs::%s>(P); }\n",
+                  rhsname.c_str());
+    *src = body + buf + buf2;
     return XSQ_OK;
 }
 
@@ -383,6 +391,15 @@ int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
     if (grid < 1) grid = 1;
     RkDev Pc = P;
     void* args[] = {&Pc};
+    {   // initialisation pass (f0 + h_start), thread per lane
+        const bool warp = rhs == XSQ_RHS_NBODY32;
+        const long long threads = warp ? P.n_lanes * 32 : P.n_lanes;
+        const unsigned igrid = (unsigned)((threads + 127) / 128);
+        CUresult ci = g_api.LaunchKernel(c.init_fn, igrid ? igrid : 1, 1, 1, 128, 1, 1, 0,
+                                         (CUstream)st, args, nullptr);
+        count_launch();
+        if (ci != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_init) failed"); return XSQ_ERR_CUDA; }
+    }
     // dense-output staging buffer (xsq_rk_core.cuh::eval_put): 4 x NL x 128
     int ns = 0, npar = 0;
     if (rhs >= XSQ_RHS_USER_BASE) { ns = g_rhs[rhs - XSQ_RHS_USER_BASE].n_state; (void)npar; }
