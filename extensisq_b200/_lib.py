@@ -36,7 +36,8 @@ EXPORTS = [
     "xsq_rhs_builtin", "xsq_rhs_register_source", "xsq_user_compile_check",
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
-    "xsq_rkc_solve", "xsq_rkc_stage_bench", "xsq_launch_count",
+    "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
+    "xsq_launch_count",
     "xsq_fp64_peak",
 ]
 
@@ -109,6 +110,8 @@ class XsqRkcArgs(C.Structure):
         ("t_eval", _dp), ("n_eval", C.c_int32), ("reserved", C.c_int32),
         ("u_eval", C.c_void_p), ("u_final", C.c_void_p),
         ("result", C.POINTER(XsqRkcResult)),
+        ("pde_params", _dp), ("n_pde_params", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -150,6 +153,8 @@ def load():
     lib.xsq_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_char_p,
                                     C.POINTER(C.c_void_p)]
     lib.xsq_comm_destroy.argtypes = [C.c_void_p]
+    lib.xsq_pde_register_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int32,
+                                            _ip]
     lib.xsq_rkc_solve.argtypes = [C.POINTER(XsqRkcArgs), C.c_void_p,
                                   C.c_void_p]
     lib.xsq_rkc_stage_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp,

@@ -36,6 +36,7 @@
 #include "xsq.h"
 #include "xsq_comm.h"
 #include "xsq_user.h"   // set_detail, count_launch
+#include "xsq_rkc_kernels.cuh"
 
 namespace xsq {
 
@@ -45,60 +46,7 @@ namespace {
 
 constexpr double kURound = 0x1.0000000000001p-53;
 constexpr double kSqrtTiny = 0x1.0p-511;
-constexpr int TX = 32, TY = 8, PX = 4;        // CTA = 32 x 8 threads, 4 points/thread
-
-struct Slab {
-    int nx, rows;        // local interior rows
-    double inv_h2;
-    size_t pitch() const { return (size_t)nx; }
-    size_t n() const { return (size_t)nx * rows; }
-    size_t n_alloc() const { return (size_t)nx * (rows + 2); }
-};
-
-// f(u) at 4 consecutive points of one row for the built-in PDE
-//   u_t = Lap(u) + u - u^3,  5-point stencil, Dirichlet 0 left/right,
-// ghost rows above/below.  `u` points at the start of the padded slab.
-__device__ __forceinline__ void load4(const double* __restrict__ p, double (&v)[PX]) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-__device__ __forceinline__ void store4(double* __restrict__ p, const double (&v)[PX]) {
-    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
-    reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
-}
-
-// Rows above the slab's first row and below its last row are read through
-// `up_row` / `dn_row`: the slab's own (zero) ghost row at the domain edge, or --
-// multi-GPU -- the neighbour rank's boundary row in ITS memory, mapped with
-// CUDA IPC and loaded over NVLink by the threads that need it.  The halo is
-// therefore part of the stage kernel; there is no separate exchange step.
-__device__ __forceinline__ void load4_peer(const double* p, double (&v)[PX]) {
-    const double2 a = __ldcv(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldcv(reinterpret_cast<const double2*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
-__device__ __forceinline__ void rhs_heat2d(const double* __restrict__ u,
-                                           const double* up_row, const double* dn_row,
-                                           int nx, int rows, int row, size_t idx, int col,
-                                           double inv_h2, double (&f)[PX]) {
-    double c[PX], up[PX], dn[PX];
-    load4(u + idx, c);
-    if (row == 0) load4_peer(up_row + col, up);
-    else load4(u + idx - nx, up);
-    if (row == rows - 1) load4_peer(dn_row + col, dn);
-    else load4(u + idx + nx, dn);
-    const double left = col > 0 ? __ldg(u + idx - 1) : 0.0;
-    const double right = col + PX < nx ? __ldg(u + idx + PX) : 0.0;
-#pragma unroll
-    for (int k = 0; k < PX; ++k) {
-        const double w = k == 0 ? left : c[k - 1];
-        const double e = k == PX - 1 ? right : c[k + 1];
-        const double lap = (((up[k] + dn[k]) + (w + e)) - 4.0 * c[k]) * inv_h2;
-        f[k] = lap + (c[k] - c[k] * c[k] * c[k]);
-    }
-}
+using namespace rkc;
 
 // Neighbour handshake (one thread): tell both neighbours that every kernel
 // enqueued before this one has finished (so the buffer about to be read is
@@ -124,23 +72,6 @@ __global__ void k_peer_sync(long long seq, volatile long long* up_flag_remote,
     __threadfence_system();
 }
 
-#define XSQ_RKC_INDEX                                                     \
-    const int col = (blockIdx.x * TX + threadIdx.x) * PX;                 \
-    const int row = blockIdx.y * TY + threadIdx.y;                        \
-    const bool active = col < S.nx && row < S.rows;                       \
-    const size_t idx = (size_t)(row + 1) * S.nx + col;
-
-// dy = f(u)
-__global__ void __launch_bounds__(TX* TY) k_eval(Slab S, const double* __restrict__ u,
-                                                 const double* up_row, const double* dn_row,
-                                                 double* __restrict__ dy) {
-    XSQ_RKC_INDEX
-    if (!active) return;
-    double f[PX];
-    rhs_heat2d(u, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
-    store4(dy + idx, f);
-}
-
 // out = a + s * b      (first stage, sommeijer.py:289; step-size probe :152)
 __global__ void __launch_bounds__(TX* TY) k_axpy(Slab S, const double* __restrict__ a,
                                                  const double* __restrict__ b, double s,
@@ -153,72 +84,6 @@ __global__ void __launch_bounds__(TX* TY) k_axpy(Slab S, const double* __restric
 #pragma unroll
     for (int k = 0; k < PX; ++k) o[k] = va[k] + s * vb[k];
     store4(out + idx, o);
-}
-
-// Stage j >= 2 (sommeijer.py:311-313), fused with the RHS evaluation:
-//   Y_j = mu*Y_{j-1} + nu*Y_{j-2} + (1-mu-nu)*y_n + h*mus*(f(Y_{j-1}) - a_{j-1}*f_n)
-__global__ void __launch_bounds__(TX* TY)
-    k_stage(Slab S, const double* __restrict__ yjm1, const double* up_row,
-            const double* dn_row, const double* __restrict__ yjm2,
-            const double* __restrict__ yn, const double* __restrict__ fn,
-            double* __restrict__ yj, double mu, double nu, double c3, double hmus,
-            double ajm1) {
-    XSQ_RKC_INDEX
-    if (!active) return;
-    double f[PX], a[PX], b[PX], c[PX], d[PX], o[PX];
-    rhs_heat2d(yjm1, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
-    load4(yjm1 + idx, a);
-    load4(yjm2 + idx, b);
-    load4(yn + idx, c);
-    load4(fn + idx, d);
-#pragma unroll
-    for (int k = 0; k < PX; ++k)
-        o[k] = ((mu * a[k] + nu * b[k]) + c3 * c[k]) + hmus * (f[k] - ajm1 * d[k]);
-    store4(yj + idx, o);
-}
-
-__device__ __forceinline__ void block_sum_to(double s, double* __restrict__ partial) {
-    __shared__ double sm[TX * TY / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const int tid = threadIdx.y * TX + threadIdx.x;
-    if ((tid & 31) == 0) sm[tid >> 5] = s;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < TX * TY / 32; ++w) t += sm[w];
-        partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
-    }
-}
-
-// Final evaluation fused with the error estimate (sommeijer.py:214-220):
-//   f1 = f(y);  est = 0.8*(yn - y) + 0.4*h*(fn + f1);  wt = atol + rtol*max(|y|,|yn|)
-//   partial[block] = sum (est/wt)^2
-__global__ void __launch_bounds__(TX* TY)
-    k_final(Slab S, const double* __restrict__ y, const double* up_row, const double* dn_row,
-            const double* __restrict__ yn,
-            const double* __restrict__ fn, double* __restrict__ f1, double h, double rtol,
-            double atol, double* __restrict__ partial) {
-    XSQ_RKC_INDEX
-    double s = 0.0;
-    if (active) {
-        double f[PX], a[PX], b[PX], c[PX];
-        rhs_heat2d(y, up_row, dn_row, S.nx, S.rows, row, idx, col, S.inv_h2, f);
-        load4(y + idx, a);
-        load4(yn + idx, b);
-        load4(fn + idx, c);
-        store4(f1 + idx, f);
-        const double h04 = 0.4 * h;
-#pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            const double est = 0.8 * (b[k] - a[k]) + h04 * (c[k] + f[k]);
-            const double wt = atol + rtol * fmax(fabs(a[k]), fabs(b[k]));
-            const double q = est / wt;
-            s = fma(q, q, s);
-        }
-    }
-    block_sum_to(s, partial);
 }
 
 // partial[block] = sum over the block of g(a, b)^2 with
@@ -318,8 +183,16 @@ __global__ void __launch_bounds__(TX* TY)
     store4(dst + (to_padded ? idx : cidx), v);
 }
 
+// The three kernels that contain the PDE right-hand side: the built-in PDE is
+// launched through the runtime API, a user PDE (NVRTC module) through the
+// driver API (xsq_user.cpp).
+struct PdeLaunch {
+    void* user_fn[3] = {nullptr, nullptr, nullptr};   // CUfunction eval/stage/final
+};
+
 struct Ctx {
     Slab S;
+    PdeLaunch pl;
     dim3 grid, block;
     int nblocks;
     cudaStream_t st;
@@ -400,10 +273,43 @@ struct Ctx {
         return s;
     }
 
-    void eval(double* u, double* dy) {           // dy = f(u), with halo
-        halo(u);
-        k_eval<<<grid, block, 0, st>>>(S, u, up_row, dn_row, dy);
+    double t_eval_arg = 0.0;                     // time argument of the next eval()
+    void launch_eval(const double* u, double t, double* dy) {
+        if (pl.user_fn[0]) {
+            void* args[] = {&S, &u, &up_row, &dn_row, &t, &dy};
+            if (user_launch(pl.user_fn[0], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde eval");
+        } else {
+            k_eval<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, u, up_row, dn_row, t, dy);
+        }
         launched();
+    }
+    void launch_stage(const double* yjm1, const double* yjm2, const double* yn, const double* fn,
+                      double* yj, double t, double mu, double nu, double c3, double hmus,
+                      double ajm1) {
+        if (pl.user_fn[1]) {
+            void* args[] = {&S, &yjm1, &up_row, &dn_row, &yjm2, &yn, &fn, &yj, &t, &mu, &nu, &c3, &hmus, &ajm1};
+            if (user_launch(pl.user_fn[1], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde stage");
+        } else {
+            k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, yjm1, up_row, dn_row, yjm2, yn, fn,
+                                                                yj, t, mu, nu, c3, hmus, ajm1);
+        }
+        launched();
+    }
+    void launch_final(const double* y, const double* yn, const double* fn, double* f1, double t,
+                      double h, double rtol, double atol) {
+        double* part = partial;
+        if (pl.user_fn[2]) {
+            void* args[] = {&S, &y, &up_row, &dn_row, &yn, &fn, &f1, &t, &h, &rtol, &atol, &part};
+            if (user_launch(pl.user_fn[2], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde final");
+        } else {
+            k_final<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, y, up_row, dn_row, yn, fn, f1, t, h,
+                                                                rtol, atol, part);
+        }
+        launched();
+    }
+    void eval(double* u, double* dy) {           // dy = f(t_eval_arg, u), with halo
+        halo(u);
+        launch_eval(u, t_eval_arg, dy);
     }
     double norm2(const double* a) {
         k_sumsq<0><<<grid, block, 0, st>>>(S, a, nullptr, nullptr, 0, 0, partial);
@@ -424,7 +330,19 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
         set_detail("xsq_rkc_args_t.struct_size mismatch");
         return XSQ_ERR_ARG;
     }
-    if (A->pde != XSQ_PDE_HEAT2D_REACTION) { set_detail("unknown pde"); return XSQ_ERR_UNSUPPORTED; }
+    PdeLaunch pl;
+    int n_pde_param_expected = 0;
+    if (A->pde >= XSQ_PDE_USER_BASE) {
+        int rc = user_pde_kernels(A->pde, pl.user_fn, &n_pde_param_expected);
+        if (rc != XSQ_OK) return rc;
+    } else if (A->pde != XSQ_PDE_HEAT2D_REACTION) {
+        set_detail("unknown pde");
+        return XSQ_ERR_UNSUPPORTED;
+    }
+    if (A->n_pde_params != n_pde_param_expected || (A->n_pde_params > 0 && !A->pde_params)) {
+        set_detail("rkc: pde_params does not match the registered PDE");
+        return XSQ_ERR_ARG;
+    }
     if (A->nx < 4 || A->nx % 4 != 0 || A->rows_local < 1 || A->rows_global < A->rows_local ||
         !A->u0 || !A->u_final || !A->result) {
         set_detail("rkc: bad grid (nx must be a positive multiple of 4) or NULL pointer");
@@ -439,9 +357,14 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
         return XSQ_ERR_ARG;
     }
     Ctx C;
+    C.pl = pl;
     C.S.nx = A->nx;
     C.S.rows = A->rows_local;
+    C.S.row0 = A->row0;
+    C.S.pad = 0;
     C.S.inv_h2 = ((double)A->nx + 1.0) * ((double)A->nx + 1.0);
+    C.S.hgrid = 1.0 / ((double)A->nx + 1.0);
+    C.S.prm = nullptr;
     C.block = dim3(TX, TY);
     C.grid = dim3((A->nx / PX + TX - 1) / TX, (A->rows_local + TY - 1) / TY);
     C.nblocks = C.grid.x * C.grid.y;
@@ -457,7 +380,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     auto wall0 = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_enter = wall0();
     double* buf = nullptr;
-    const size_t total = na * 6 + C.nblocks + C.world + 8 + 64;
+    const size_t total = na * 6 + C.nblocks + C.world + 8 + 64 + (size_t)A->n_pde_params;
     const bool multi = C.world > 1;
     // multi-GPU: plain cudaMalloc so the storage can be exported with CUDA IPC
     cudaError_t me = multi ? cudaMalloc((void**)&buf, total * sizeof(double))
@@ -547,6 +470,13 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
 
     k_copy<<<C.grid, C.block, 0, st>>>(C.S, A->u0, yn, 1);
     C.launched();
+    if (A->n_pde_params > 0) {       // PDE parameters live behind the flag words
+        double* dprm = buf + na * 6 + C.nblocks + C.world + 8 + 64;
+        cudaMemcpyAsync(dprm, A->pde_params, sizeof(double) * A->n_pde_params,
+                        cudaMemcpyHostToDevice, st);
+        C.S.prm = dprm;
+    }
+    C.t_eval_arg = t0;
     C.eval(yn, fn);
     nfev = 1;
     int ieval = 0;
@@ -614,6 +544,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
                     double sigma = 0.0;
                     bool converged = false;
                     for (int iter = 0; iter < 50; ++iter) {
+                        C.t_eval_arg = t;
                         C.eval(v, fv);
                         ++nfesig;
                         const double dfnrm = C.norm2_diff(fv, fn);
@@ -651,6 +582,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
                 absh = std::fmax(absh, hmin0);
                 k_axpy<<<C.grid, C.block, 0, st>>>(C.S, yn, fn, absh, W[0]);
                 C.launched();
+                C.t_eval_arg = t + absh;
                 C.eval(W[0], W[1]);
                 ++nfev;
                 k_sumsq<2><<<C.grid, C.block, 0, st>>>(C.S, W[1], fn, yn, rtol, atol, C.partial);
@@ -698,10 +630,8 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
                 const double nu = -bj / bjm2;
                 mus = mu * w1c / w0c;
                 C.halo(W[i1]);
-                k_stage<<<C.grid, C.block, 0, st>>>(C.S, W[i1], C.up_row, C.dn_row,
-                                                    i2 < 0 ? yn : W[i2], yn, fn,
-                                                    W[i0], mu, nu, 1.0 - mu - nu, h * mus, ajm1);
-                C.launched();
+                C.launch_stage(W[i1], i2 < 0 ? yn : W[i2], yn, fn, W[i0], t + h * thjm1, mu, nu,
+                               1.0 - mu - nu, h * mus, ajm1);
                 ++nfev;
                 const double thj = mu * thjm1 + nu * thjm2 + mus * (1.0 - ajm1);
                 if (j < m) {       // rotate slots instead of the copies of :318-319
@@ -718,9 +648,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
             double* third = W[3 - i0 - i1];
             // ---- final evaluation + error estimate (:214-220) ---------------
             C.halo(y);
-            k_final<<<C.grid, C.block, 0, st>>>(C.S, y, C.up_row, C.dn_row, yn, fn, f1, h, rtol,
-                                                atol, C.partial);
-            C.launched();
+            C.launch_final(y, yn, fn, f1, t + h, h, rtol, atol);
             ++nfev;
             err = std::sqrt(C.global_sum() / (double)C.n_total);
             if (C.rc != XSQ_OK) break;
@@ -802,7 +730,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
 // Stage-kernel micro-benchmark for the roofline: runs `reps` stage launches on
 // a rows x nx slab and returns the average device time per launch.
 int rkc_stage_bench(int nx, int rows, int reps, double* ms_per_stage, cudaStream_t st) {
-    Slab S{nx, rows, ((double)nx + 1.0) * ((double)nx + 1.0)};
+    Slab S{nx, rows, 0, 0, ((double)nx + 1.0) * ((double)nx + 1.0), 1.0 / ((double)nx + 1.0), nullptr};
     const size_t na = S.n_alloc();
     double* buf = nullptr;
     if (cudaMalloc((void**)&buf, na * 5 * sizeof(double)) != cudaSuccess) return XSQ_ERR_NOMEM;
@@ -814,15 +742,17 @@ int rkc_stage_bench(int nx, int rows, int reps, double* ms_per_stage, cudaStream
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int w = 0; w < 3; ++w) {
-        k_stage<<<grid, block, 0, st>>>(S, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2], yn, fn,
-                                        v[0], 1.9, -0.95, 0.05, 1e-9, 0.3);
+        k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(
+            S, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2], yn, fn, v[0], 0.0, 1.9, -0.95,
+            0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e0, st);
     for (int r = 0; r < reps; ++r) {
         const double* in = v[(r + 1) % 3];
-        k_stage<<<grid, block, 0, st>>>(S, in, in, in + (size_t)nx * (rows + 1), v[(r + 2) % 3], yn,
-                                        fn, v[r % 3], 1.9, -0.95, 0.05, 1e-9, 0.3);
+        k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(
+            S, in, in, in + (size_t)nx * (rows + 1), v[(r + 2) % 3], yn, fn, v[r % 3], 0.0, 1.9,
+            -0.95, 0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e1, st);

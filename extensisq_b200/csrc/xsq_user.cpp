@@ -48,6 +48,15 @@ struct UserTab {
     std::string src;
 } g_tab;
 
+struct UserPde {
+    std::string src, entry;
+    int n_param;
+    bool ready = false;
+    CUmodule mod = nullptr;
+    CUfunction fn[3] = {nullptr, nullptr, nullptr};
+};
+std::vector<UserPde> g_pde;               // handle = XSQ_PDE_USER_BASE + index
+
 struct Compiled {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
@@ -240,6 +249,62 @@ int minb_for(int s, int nl) {
     return kd <= 21 ? 4 : (kd <= 36 ? 3 : 2);
 }
 
+// NVRTC source -> loaded CUmodule
+int compile_module(const std::string& src, CUmodule* mod) {
+    if (!load_nvrtc()) return XSQ_ERR_NVRTC;
+    nvrtcProgram prog;
+    nvrtcResult r = g_api.CreateProgram(&prog, src.c_str(), "xsq_user.cu", kNumEmbedded,
+                                        kEmbeddedSources, kEmbeddedNames);
+    if (r != NVRTC_SUCCESS) { set_detail(g_api.GetErrorString(r)); return XSQ_ERR_NVRTC; }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=false"};
+    r = g_api.CompileProgram(prog, 4, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_api.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_api.GetProgramLog(prog, &log[0]);
+        set_detail(std::string("NVRTC: ") + g_api.GetErrorString(r) + "\n" + log);
+        g_api.DestroyProgram(&prog);
+        return XSQ_ERR_NVRTC;
+    }
+    size_t n = 0;
+    g_api.GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    g_api.GetCUBIN(prog, cubin.data());
+    g_api.DestroyProgram(&prog);
+    if (!load_cuda()) return XSQ_ERR_CUDA;
+    cudaFree(0);
+    CUresult cr = g_api.ModuleLoadData(mod, cubin.data());
+    if (cr != CUDA_SUCCESS) {
+        const char* es = nullptr;
+        g_api.CuGetErrorString(cr, &es);
+        set_detail(std::string("driver: ") + (es ? es : "?"));
+        return XSQ_ERR_CUDA;
+    }
+    return XSQ_OK;
+}
+
+std::string pde_source(const UserPde& u) {
+    std::string s = "#include \"xsq_rkc_kernels.cuh\"\n" + u.src + "\n";
+    s += "namespace xsq { namespace rkc { namespace pde { struct User {\n"
+         "  __device__ __forceinline__ static double rhs(double t, double x, double y, double inv_h2,\n"
+         "      double c, double n, double s, double w, double e, const double* p) {\n"
+         "    return ::" + u.entry + "(t, x, y, inv_h2, c, n, s, w, e, p); }\n};\n} } }\n";
+    s += "using namespace xsq::rkc;\n"
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_eval(Slab S, const double* u,\n"
+         "    const double* up, const double* dn, double t, double* dy) {\n"
+         "  eval_body<pde::User>(S, u, up, dn, t, dy); }\n"
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_stage(Slab S, const double* a,\n"
+         "    const double* up, const double* dn, const double* b, const double* yn, const double* fn,\n"
+         "    double* yj, double t, double mu, double nu, double c3, double hmus, double ajm1) {\n"
+         "  stage_body<pde::User>(S, a, up, dn, b, yn, fn, yj, t, mu, nu, c3, hmus, ajm1); }\n"
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_final(Slab S, const double* y,\n"
+         "    const double* up, const double* dn, const double* yn, const double* fn, double* f1,\n"
+         "    double t, double h, double rtol, double atol, double* partial) {\n"
+         "  final_body<pde::User>(S, y, up, dn, yn, fn, f1, t, h, rtol, atol, partial); }\n";
+    return s;
+}
+
 int compile(const std::string& key, const std::string& src, Compiled* out) {
     if (!load_nvrtc()) return XSQ_ERR_NVRTC;
     nvrtcProgram prog;
@@ -417,6 +482,33 @@ int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
     return XSQ_OK;
 }
 
+int user_pde_kernels(int pde, void* fn[3], int* n_param) {
+    std::lock_guard<std::mutex> g(g_mu);
+    const size_t i = (size_t)(pde - XSQ_PDE_USER_BASE);
+    if (pde < XSQ_PDE_USER_BASE || i >= g_pde.size()) { set_detail("unknown pde handle"); return XSQ_ERR_ARG; }
+    UserPde& u = g_pde[i];
+    if (!u.ready) {
+        int rc = compile_module(pde_source(u), &u.mod);
+        if (rc != XSQ_OK) return rc;
+        const char* names[3] = {"xsq_pde_eval", "xsq_pde_stage", "xsq_pde_final"};
+        for (int k = 0; k < 3; ++k)
+            if (g_api.ModuleGetFunction(&u.fn[k], u.mod, names[k]) != CUDA_SUCCESS) {
+                set_detail("user pde module lacks a kernel");
+                return XSQ_ERR_CUDA;
+            }
+        u.ready = true;
+    }
+    for (int k = 0; k < 3; ++k) fn[k] = (void*)u.fn[k];
+    *n_param = u.n_param;
+    return XSQ_OK;
+}
+
+int user_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** args,
+                cudaStream_t st) {
+    return g_api.LaunchKernel((CUfunction)fn, gx, gy, 1, bx, by, 1, 0, (CUstream)st, args,
+                              nullptr) == CUDA_SUCCESS ? 0 : -1;
+}
+
 }  // namespace xsq
 
 using namespace xsq;
@@ -449,6 +541,19 @@ int xsq_tableau_load(const xsq_tableau_t* tab) {
     g_tab.src = tableau_source(*tab);
     g_tab.loaded = true;
     ++g_tab.generation;
+    return XSQ_OK;
+}
+
+int xsq_pde_register_source(const char* cuda_src, const char* entry, int32_t n_param,
+                            int32_t* pde_out) {
+    if (!cuda_src || !entry || !pde_out || n_param < 0) return XSQ_ERR_ARG;
+    std::lock_guard<std::mutex> g(g_mu);
+    UserPde u;
+    u.src = cuda_src;
+    u.entry = entry;
+    u.n_param = n_param;
+    g_pde.push_back(u);
+    *pde_out = XSQ_PDE_USER_BASE + (int)g_pde.size() - 1;
     return XSQ_OK;
 }
 

@@ -17,14 +17,38 @@ import torch.distributed as dist
 from . import _lib
 from .sharding import shard_bounds
 
-__all__ = ["SSV2stab", "SlabComm", "PdeResult", "solve_pde_rkc", "nfesig",
-           "maxm"]
+__all__ = ["SSV2stab", "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc",
+           "nfesig", "maxm"]
 
 # module-level counters of the reference (sommeijer.py:12-14), last solve
 nfesig = np.array(0)
 maxm = np.array(0)
 
 PDES = {"heat2d_reaction": 0}
+
+
+class PdeRHS:
+    """Right-hand side of a 2-D parabolic PDE on the unit square (homogeneous
+    Dirichlet boundaries, 5-point neighbourhood) as CUDA source defining
+
+        __device__ double <entry>(double t, double x, double y, double inv_h2,
+                                  double uc, double un, double us, double uw,
+                                  double ue, const double* p);
+
+    compiled with NVRTC into the fused SSV2stab stage kernels.  Replaces the
+    Python callable `fun` of the reference (sommeijer.py:93)."""
+
+    def __init__(self, handle, n_param, name):
+        self.handle, self.n_param, self.name = handle, n_param, name
+
+    @classmethod
+    def from_source(cls, cuda_src, entry, n_param=0):
+        lib = _lib.load()
+        h = C.c_int32()
+        _lib.check(lib.xsq_pde_register_source(cuda_src.encode(),
+                                               entry.encode(), int(n_param),
+                                               C.byref(h)))
+        return cls(h.value, int(n_param), f"user:{entry}")
 
 
 class SSV2stab:
@@ -138,7 +162,7 @@ def validate_rkc_options(rtol, atol, first_step, max_step, const_jac, rho_jac,
 def solve_pde_rkc(pde, t_span, u0, rows_global=None, row0=0, t_eval=None,
                   rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf,
                   const_jac=False, rho_jac=None, max_steps=None, comm=None,
-                  stream=None, method=SSV2stab):
+                  stream=None, method=SSV2stab, pde_params=None):
     """Integrate the PDE `pde` ("heat2d_reaction") with SSV2stab.
 
     u0 : [rows_local, nx] float64 tensor -- this rank's row slab of the grid
@@ -155,8 +179,17 @@ def solve_pde_rkc(pde, t_span, u0, rows_global=None, row0=0, t_eval=None,
                            "CPU fallback")
     if method is not SSV2stab:
         raise ValueError("solve_pde_rkc only implements SSV2stab")
-    if pde not in PDES:
-        raise ValueError(f"unknown pde {pde!r}; available: {sorted(PDES)}")
+    if isinstance(pde, PdeRHS):
+        pde_id, n_prm = pde.handle, pde.n_param
+    elif pde in PDES:
+        pde_id, n_prm = PDES[pde], 0
+    else:
+        raise ValueError(f"unknown pde {pde!r}; available: {sorted(PDES)} or "
+                         "a PdeRHS")
+    prm_np = np.ascontiguousarray(np.asarray(
+        pde_params if pde_params is not None else [], dtype=float))
+    if prm_np.size != n_prm:
+        raise ValueError(f"`pde_params` must have {n_prm} entries")
     t0, tf = map(float, t_span)
     rho_const, rho_fn = validate_rkc_options(rtol, atol, first_step, max_step,
                                              const_jac, rho_jac, t0, tf)
@@ -194,7 +227,10 @@ def solve_pde_rkc(pde, t_span, u0, rows_global=None, row0=0, t_eval=None,
         res = _lib.XsqRkcResult()
         a = _lib.XsqRkcArgs()
         a.struct_size = C.sizeof(_lib.XsqRkcArgs)
-        a.pde = PDES[pde]
+        a.pde = pde_id
+        a.pde_params = (prm_np.ctypes.data_as(C.POINTER(C.c_double))
+                        if n_prm else None)
+        a.n_pde_params = n_prm
         a.nx, a.rows_global, a.rows_local, a.row0 = nx, rows_global, \
             rows_local, int(row0)
         a.rank, a.world = rank, world

@@ -192,7 +192,8 @@ int xsq_swag_solve(const xsq_swag_args_t* args, int32_t k_max, void* stream);
 typedef enum xsq_pde_id {
     /* u_t = Lap(u) + u - u^3 on (0,1)^2, Dirichlet 0, nx x rows_global interior
      * points, 5-point stencil, h = 1/(nx+1)   */
-    XSQ_PDE_HEAT2D_REACTION = 0
+    XSQ_PDE_HEAT2D_REACTION = 0,
+    XSQ_PDE_USER_BASE = 1000      /* handles from xsq_pde_register_source */
 } xsq_pde_id;
 
 typedef double (*xsq_rho_fn)(double t, void* user);   /* rho_jac(t, .) */
@@ -232,7 +233,21 @@ typedef struct xsq_rkc_args {
     double* u_eval;               /* DEVICE [n_eval][rows_local][nx]          */
     double* u_final;              /* DEVICE [rows_local][nx]                  */
     xsq_rkc_result_t* result;     /* HOST                                     */
+    const double* pde_params;     /* HOST [n_pde_params], user PDE parameters */
+    int32_t n_pde_params, reserved2;
 } xsq_rkc_args_t;
+
+/* Register the right-hand side of a 2-D parabolic PDE on the unit square with
+ * homogeneous Dirichlet boundaries and a 5-point neighbourhood, as CUDA source
+ * defining
+ *   __device__ double <entry>(double t, double x, double y, double inv_h2,
+ *                             double uc, double un, double us, double uw,
+ *                             double ue, const double* p);
+ * (n = row above = smaller y).  It is compiled with NVRTC into the fused stage
+ * kernels.  Replaces the Python callable `fun` handed to SSV2stab
+ * (sommeijer.py:93). */
+int xsq_pde_register_source(const char* cuda_src, const char* entry, int32_t n_param,
+                            int32_t* pde_out);
 
 /* NCCL communicator for the slab decomposition (new; the reference has no
  * communication layer).  Rank 0 calls xsq_comm_unique_id and distributes the
