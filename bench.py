@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--t-end", type=float, default=T_END)
     ap.add_argument("--cpu-lanes", type=int, default=0,
                     help="lanes of the CPU sample (0 = auto)")
+    ap.add_argument("--stiff", type=int, default=5000,
+                    help="nfev_stiff_detect (reference default 5000; 0 = off)")
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
@@ -264,7 +266,8 @@ def main():
 
     def solve_resident():
         return xb.solve_ivp_batched("lorenz63", (0.0, args.t_end), y0_d, method,
-                                    params=prm_d, rtol=RTOL, atol=ATOL)
+                                    params=prm_d, rtol=RTOL, atol=ATOL,
+                                    nfev_stiff_detect=args.stiff)
 
     out_pin = {"y": torch.empty((N, 3), dtype=torch.float64).pin_memory(),
                "acc": torch.empty(N, dtype=torch.int32).pin_memory(),
@@ -275,7 +278,8 @@ def main():
         a = y0_pin.to(dev, non_blocking=True)
         b = prm_pin.to(dev, non_blocking=True)
         r = xb.solve_ivp_batched("lorenz63", (0.0, args.t_end), a, method,
-                                 params=b, rtol=RTOL, atol=ATOL)
+                                 params=b, rtol=RTOL, atol=ATOL,
+                                 nfev_stiff_detect=args.stiff)
         out_pin["y"].copy_(r.y_final, non_blocking=True)
         out_pin["acc"].copy_(r.n_accepted, non_blocking=True)
         out_pin["rej"].copy_(r.n_rejected, non_blocking=True)

@@ -55,6 +55,7 @@ class XsqTableau(C.Structure):
         ("E", C.c_double * (XSQ_MAX_STAGES + 1)),
         ("P", (C.c_double * XSQ_MAX_POLY) * (XSQ_MAX_STAGES + 1)),
         ("sc_params", C.c_double * 4),
+        ("stbrad", C.c_double), ("tanang", C.c_double),
     ]
 
 
@@ -80,6 +81,8 @@ class XsqRkArgs(C.Structure):
         ("n_accepted", C.c_void_p), ("n_rejected", C.c_void_p),
         ("nfev", C.c_void_p), ("status", C.c_void_p),
         ("n_eval_done", C.c_void_p),
+        ("nfev_stiff_detect", C.c_int32), ("reserved1", C.c_int32),
+        ("stiff_flags", C.c_void_p),
     ]
 
 

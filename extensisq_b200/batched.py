@@ -76,6 +76,8 @@ class BatchedOdeResult:
     nfev: torch.Tensor          # int32 [N]
     status: torch.Tensor        # int32 [N]   xsq_lane_status
     n_eval_done: object = None  # int32 [N] or None
+    stiff_flags: object = None  # int32 [N]: 1 stiff (real root), 2 stiff
+    #                             (complex pair), 4 oscillatory + many failures
     njev: int = 0
     nlu: int = 0
 
@@ -121,6 +123,10 @@ def _upload_user_tableau(cls):
     kb = _sc_tuple(cls.sc_params)
     for i in range(4):
         t.sc_params[i] = kb[i]
+    # stiffness detection needs both; NotImplemented disables it (common.py:155)
+    ok = all(isinstance(getattr(cls, k), (int, float)) for k in ("stbrad", "tanang"))
+    t.stbrad = float(cls.stbrad) if ok else 0.0
+    t.tanang = float(cls.tanang) if ok else 0.0
     _lib.check(lib.xsq_tableau_load(C.byref(t)))
 
 
@@ -140,8 +146,8 @@ def _sc_tuple(sc_params):
 def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                       rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf,
                       sc_params=None, interpolant=None, k_max=None,
-                      max_steps=None, forced_steps=None, device=None,
-                      stream=None,
+                      nfev_stiff_detect=5000, max_steps=None,
+                      forced_steps=None, device=None, stream=None,
                       **extraneous):
     """Integrate N independent systems ``y' = fun(t, y; params_i)``.
 
@@ -157,6 +163,9 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     sc_params : "G" | "S" | "standard" | (kb1, kb2, a, g)
     interpolant : BS5 only, 'best' | 'low' | 'free' (bogacki.py:217)
     k_max : SWAG only, maximum order 1..12 (shampine.py:99-103)
+    nfev_stiff_detect : stiffness diagnosis every this many evaluations or on
+        >= 10 failed steps in 40 (common.py:150-164, 370-516); 0 turns it off.
+        Instead of warnings the result carries per-lane ``stiff_flags``
     max_steps : attempted-step budget per lane (GPU safety net, no reference
         analogue)
     forced_steps : [k] sequence of |h|; takes exactly these steps, accepting
@@ -219,6 +228,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
             raise ValueError("`first_step` must be positive.")
         if first_step > abs(tf - t0):
             raise ValueError("`first_step` exceeds bounds.")
+    if not (isinstance(nfev_stiff_detect, int) and nfev_stiff_detect >= 0):
+        raise ValueError("`nfev_stiff_detect` must be a non-negative integer.")
     sc = _sc_tuple(sc_params) if sc_params is not None else None
     if interpolant not in (None, "best", "low", "free"):
         raise ValueError("interpolant should be one of: 'best', 'low', 'free'")
@@ -293,6 +304,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         nfev = torch.empty(N, **i32)
         status = torch.empty(N, **i32)
         n_done = torch.empty(N, **i32) if n_eval else None
+        stiff = torch.zeros(N, **i32)
 
         a = _lib.XsqRkArgs()
         a.struct_size = C.sizeof(_lib.XsqRkArgs)
@@ -327,6 +339,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         a.nfev = nfev.data_ptr()
         a.status = status.data_ptr()
         a.n_eval_done = n_done.data_ptr() if n_eval else None
+        a.nfev_stiff_detect = 0 if is_swag else nfev_stiff_detect
+        a.stiff_flags = stiff.data_ptr()
         st = stream if stream is not None else torch.cuda.current_stream(device)
         if is_swag:
             _lib.check(lib.xsq_swag_solve(C.byref(a), k_max,
@@ -339,7 +353,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     res = BatchedOdeResult(
         t=te, y=y_eval, t_final=t_final, y_final=y_final.t(), h_next=h_next,
         n_accepted=n_acc, n_rejected=n_rej, nfev=nfev, status=status,
-        n_eval_done=n_done)
+        n_eval_done=n_done, stiff_flags=stiff)
     res._keepalive = (y0_soa, prm_soa, hf, atol_c)
     return res
 

@@ -45,7 +45,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 template <class T>
 static MethodInfo info_of() {
     return MethodInfo{T::S, T::ORDER, T::ORDER2, T::FSAL, T::NPOL,
-                      {T::SC_KB1, T::SC_KB2, T::SC_A, T::SC_G}};
+                      {T::SC_KB1, T::SC_KB2, T::SC_A, T::SC_G}, T::STBRAD, T::TANANG};
 }
 
 static bool method_info(int method, MethodInfo* mi) {
@@ -83,6 +83,8 @@ __global__ void tableau_dump(xsq_tableau_t* out) {
     out->sc_params[1] = T::SC_KB2;
     out->sc_params[2] = T::SC_A;
     out->sc_params[3] = T::SC_G;
+    out->stbrad = T::STBRAD;
+    out->tanang = T::TANANG;
 }
 
 // ---- fp64 FMA peak microbenchmark -------------------------------------------
@@ -145,7 +147,7 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         return XSQ_ERR_ARG;
     }
     if (a->method == XSQ_METHOD_SWAG) {
-        *mi = MethodInfo{1, 1, 1, 0, 0, {1.0, 0.0, 0.0, 0.9}};
+        *mi = MethodInfo{1, 1, 1, 0, 0, {1.0, 0.0, 0.0, 0.9}, 0.0, 0.0};
     } else if (a->method == XSQ_METHOD_USER) {
         if (!user_tableau_info(mi)) {
             g_detail = "no user tableau loaded";
@@ -243,6 +245,16 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     P->nfev = a->nfev;
     P->status = a->status;
     P->n_eval_done = a->n_eval_done;
+    // _init_stiffness_detection, common.py:150-164
+    if (a->nfev_stiff_detect < 0) {
+        g_detail = "`nfev_stiff_detect` must be a non-negative integer.";
+        return XSQ_ERR_ARG;
+    }
+    P->nfev_stiff_detect = (mi->stbrad > 0.0 && mi->tanang > 0.0 && a->n_forced == 0)
+                               ? a->nfev_stiff_detect : 0;
+    if (P->nfev_stiff_detect > 0 && P->nfev_stiff_detect / mi->s < 1) P->nfev_stiff_detect = mi->s;
+    P->stiff_many_steps = P->nfev_stiff_detect > 0 ? P->nfev_stiff_detect / mi->s : 1;
+    P->stiff_flags = a->stiff_flags;
     return XSQ_OK;
 }
 
@@ -290,7 +302,32 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     P.init_f0 = (double*)(scratch + off_f);
     P.init_nfev = (int*)(scratch + off_n);
     P.morder = (a->method == XSQ_METHOD_SWAG) ? 1 : mi.order2;
+    // stiffness probes wait in two slots per resident thread (xsq_rk_core.cuh,
+    // Lane::diagnose); 2048 threads per SM is the most any geometry launches
+    double* slots = nullptr;
+    P.stiff_slot = nullptr;
+    P.stiff_threads = 0;
+    if (P.nfev_stiff_detect > 0 && a->method != XSQ_METHOD_SWAG) {
+        int dev = 0, n_sm = 0;
+        XSQ_CUDA(cudaGetDevice(&dev));
+        XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        const bool warp_rhs = a->rhs == XSQ_RHS_NBODY32;
+        const size_t nl = warp_rhs ? 6 : (size_t)a->n_state;
+        const size_t npl = warp_rhs ? 2 : (size_t)(a->n_param > 0 ? a->n_param : 1);
+        size_t threads = (size_t)n_sm * 2048;
+        const size_t want = ((warp_rhs ? N * 32 : N) + 255) & ~(size_t)255;
+        if (want < threads) threads = want;
+        P.stiff_threads = (long long)threads;
+        cudaError_t es = cudaMallocAsync((void**)&slots,
+                                         2 * (5 + 4 * nl + npl) * threads * sizeof(double), st);
+        if (es != cudaSuccess) {
+            cudaFreeAsync(scratch, st);
+            return cuda_fail(es, "cudaMallocAsync");
+        }
+        P.stiff_slot = slots;
+    }
     rc = dispatch(a->method, a->rhs, P, st, info);
+    if (slots) cudaFreeAsync(slots, st);
     cudaError_t e = cudaFreeAsync(scratch, st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
     return rc;
@@ -432,6 +469,7 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d.nfev = (int32_t*)dalloc((size_t)N * ni);
     d.status = (int32_t*)dalloc((size_t)N * ni);
     d.n_eval_done = h->n_eval_done ? (int32_t*)dalloc((size_t)N * ni) : nullptr;
+    d.stiff_flags = h->stiff_flags ? (int32_t*)dalloc((size_t)N * ni) : nullptr;
     if (rc == XSQ_OK) rc = solve_device(&d, st, nullptr);
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
         if (rc == XSQ_OK && dst && bytes)
@@ -451,6 +489,7 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d2h(h->nfev, d.nfev, (size_t)N * ni);
     d2h(h->status, d.status, (size_t)N * ni);
     if (h->n_eval_done) d2h(h->n_eval_done, d.n_eval_done, (size_t)N * ni);
+    if (h->stiff_flags) d2h(h->stiff_flags, d.stiff_flags, (size_t)N * ni);
     for (void* p : owned) cudaFreeAsync(p, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaStreamDestroy(st);

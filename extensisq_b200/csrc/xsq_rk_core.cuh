@@ -42,8 +42,12 @@ static constexpr double kMaxFactor0 = 10.0;     // common.py:20
 
 enum LaneStatus : int {
     LANE_FINISHED = 0, LANE_TOO_SMALL = -1, LANE_OVERFLOW = -2,
-    LANE_STEP_BUDGET = -5, LANE_RUNNING = 1
+    LANE_STEP_BUDGET = -5, LANE_RUNNING = 1,
+    LANE_FLUSH = 2      // internal: still running, stiffness probe slots are full
 };
+#ifndef XSQ_MAX_BLOCK
+#define XSQ_MAX_BLOCK 256   // largest CTA any rk_persistent geometry launches
+#endif
 enum Interp : int { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
 
 // Device-side parameter block; passed by value as the kernel argument so every
@@ -78,6 +82,13 @@ struct RkDev {
     double* init_h;               // [n_lanes]: |h| from h_start (if needed)
     int* init_nfev;               // [n_lanes]: evaluations spent so far
     int morder;                   // h_start's order argument (common.py:210-212)
+    // stiffness diagnosis (common.py:150-164, 370-516); 0 = off
+    int nfev_stiff_detect;
+    int stiff_many_steps;         // nfev_stiff_detect // n_stages
+    int* stiff_flags;             // [n_lanes] OR of STIFF_* codes, may be null
+    // deferred probes: 2 slots per resident thread, SoA [slot][field][thread]
+    double* stiff_slot;
+    long long stiff_threads;      // thread stride of stiff_slot (>= grid size)
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -406,6 +417,189 @@ __global__ void __launch_bounds__(BLOCK) ens_init(const RkDev P) {
     ens_init_body<R>(P);
 }
 
+// ---- stiffness diagnosis ----------------------------------------------------
+// Port of the reference's _diagnose_stiffness / stiff_a..d (common.py:370-516,
+// 824-1204, themselves a port of RKSuite): a nonlinear power iteration for the
+// two dominant eigenvalues of havg*J, compared with the method's stability
+// radius.  It never changes t, y or h; it spends a few RHS evaluations (counted
+// in nfev, as in the reference) and, instead of warnings, sets per-lane flags.
+// Runs every nfev_stiff_detect/n_stages accepted steps or after >= 10 failures
+// in 40 steps, so it is kept out of line: only copies of the lane's vectors
+// are handed to it, the hot loop's register allocation is untouched.
+enum : int { STIFF_REAL = 1, STIFF_COMPLEX = 2, STIFF_OSCILLATORY = 4 };
+
+template <class R>
+__device__ __forceinline__ double wdot(const double (&a)[R::NL], const double (&b)[R::NL],
+                                       const double (&wt)[R::NL]) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < R::NL; ++c) s = fma(a[c] / wt[c], b[c] / wt[c], s);
+    return sys_sum<R::WARP>(s);
+}
+
+// stiff_d: z ~ havg * J * v by a difference of f; returns <z, z>
+template <class R>
+__device__ double stiff_jac_times(const double (&v)[R::NL], double havg, double x,
+                                  const double (&y)[R::NL], const double (&fxy)[R::NL],
+                                  const double (&wt)[R::NL], const double (&prm)[R::NPL],
+                                  double scale, double vdotv, double (&z)[R::NL], int& nfev) {
+    const double temp1 = scale / sqrt(vdotv);
+    double yp[R::NL];
+#pragma unroll
+    for (int c = 0; c < R::NL; ++c) yp[c] = fma(temp1, v[c], y[c]);
+    R::f(x, yp, prm, z);
+    ++nfev;
+    const double q = havg / temp1;
+#pragma unroll
+    for (int c = 0; c < R::NL; ++c) z[c] = q * (z[c] - fxy[c]);
+    return wdot<R>(z, z, wt);
+}
+
+// stiff_b
+__device__ __forceinline__ bool stiff_dominant_real(double v1v1, double v0v1, double v0v0,
+                                                    double& rold, double& rho,
+                                                    double (&root1)[2], double (&root2)[2]) {
+    const double r = v0v1 / v0v0;
+    rho = fabs(r);
+    const double det = v0v0 * v1v1 - v0v1 * v0v1;
+    const double res = fabs(det / v0v0);
+    const bool rootre = det == 0.0 || (res <= 1e-6 * v1v1 && fabs(r - rold) <= 0.001 * rho);
+    root1[0] = rootre ? r : 0.0;
+    root1[1] = root2[0] = root2[1] = 0.0;
+    rold = r;
+    return rootre;
+}
+
+// stiff_c
+__device__ __forceinline__ void stiff_quadratic_roots(double alpha, double beta,
+                                                      double (&r1)[2], double (&r2)[2]) {
+    r1[0] = r1[1] = r2[0] = r2[1] = 0.0;
+    const double temp = alpha / 2;
+    const double disc = temp * temp - beta;
+    if (disc == 0.0) { r1[0] = r2[0] = -temp; return; }
+    const double sqdisc = sqrt(fabs(disc));
+    if (disc < 0.0) { r1[0] = r2[0] = -temp; r1[1] = sqdisc; r2[1] = -sqdisc; }
+    else { r1[0] = temp > 0.0 ? -temp - sqdisc : -temp + sqdisc; r2[0] = beta / r1[0]; }
+}
+
+// stiff_a + the classification of common.py:424-455.  All inputs come from a
+// probe slot (see Lane::diagnose); returns flags | evaluations << 8.
+template <class R>
+struct StiffSlot {
+    // x, hnow, havg, lotsfl, trajectory index, then y_new, y_old, f_new, h*K.E
+    // and the parameters
+    static constexpr int HEAD = 5;
+    static constexpr int DOUBLES = HEAD + 4 * R::NL + R::NPL;
+};
+
+template <class R>
+__device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride, double xend,
+                                            int maxfcn, int cost, double stbrad,
+                                            double tanang) {
+    constexpr int NL = R::NL;
+    const double x = slot[0], hnow = slot[stride], havg = slot[2 * stride];
+    const bool lotsfl = slot[3 * stride] != 0.0;
+    const double* q = slot + StiffSlot<R>::HEAD * stride;
+    double y[NL], fxy[NL], wt[NL], v0[NL], v1[NL], v2[NL], v3[NL], prm[R::NPL];
+#pragma unroll
+    for (int c = 0; c < NL; ++c) {
+        y[c] = q[c * stride];
+        fxy[c] = q[(2 * NL + c) * stride];
+        v0[c] = q[(3 * NL + c) * stride];
+        wt[c] = fmax(0.5 * (fabs(y[c]) + fabs(q[(NL + c) * stride])), XSQ_SQRT_TINY);
+    }
+#pragma unroll
+    for (int c = 0; c < R::NPL; ++c) prm[c] = q[(4 * NL + c) * stride];
+    int nfev = 0;
+    const double epsneg = 0x1.0p-53;
+    int stif = 0, rootre = -1;          // stif: 1 / 0 / -1 (unsure)
+    bool have_root = false;
+    double root1[2] = {0, 0}, root2[2] = {0, 0}, rho = 0.0;
+    do {
+        if (fabs(hnow / havg) > 5 || fabs(hnow / havg) < 0.2) break;
+        if (cost * fabs((xend - x) / havg) <= maxfcn) break;
+        double ynrm = sqrt(wdot<R>(y, y, wt));
+        const double sqrrmc = sqrt(epsneg);
+        double scale = ynrm * sqrrmc;
+        if (scale == 0.0) {
+            ynrm = sqrt(wdot<R>(v0, v0, wt));
+            scale = ynrm * sqrrmc;
+            if (scale == 0.0) { stif = -1; break; }
+        }
+        double v0v0 = wdot<R>(v0, v0, wt);
+        if (v0v0 == 0.0) {
+#pragma unroll
+            for (int c = 0; c < NL; ++c) v0[c] = 1.0;
+            v0v0 = wdot<R>(v0, v0, wt);
+        }
+        const double v0nrm = sqrt(v0v0);
+#pragma unroll
+        for (int c = 0; c < NL; ++c) v0[c] /= v0nrm;
+        v0v0 = 1.0;
+        double rold = 0.0;
+        bool converged = false, early = false;
+        for (int ntry = 0; ntry < 8; ++ntry) {
+            const double v1v1 = stiff_jac_times<R>(v0, havg, x, y, fxy, wt, prm, scale, v0v0, v1, nfev);
+            if (sqrt(v1v1) > 1.0e10 * sqrt(v0v0)) { stif = -1; rootre = -1; early = true; break; }
+            const double v0v1 = wdot<R>(v0, v1, wt);
+            if (ntry == 0) {
+                rold = v0v1 / v0v0;
+                if (fabs(rold) < cbrt(epsneg)) { stif = 0; rootre = -1; early = true; break; }
+            } else {
+                if (stiff_dominant_real(v1v1, v0v1, v0v0, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
+                rootre = 0;
+            }
+            const double v2v2 = stiff_jac_times<R>(v1, havg, x, y, fxy, wt, prm, scale, v1v1, v2, nfev);
+            const double v0v2 = wdot<R>(v0, v2, wt), v1v2 = wdot<R>(v1, v2, wt);
+            if (stiff_dominant_real(v2v2, v1v2, v1v1, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
+            rootre = 0;
+            const double det1 = v0v0 * v1v1 - v0v1 * v0v1;
+            const double alpha1 = (-v0v0 * v1v2 + v0v1 * v0v2) / det1;
+            const double beta1 = (v0v1 * v1v2 - v1v1 * v0v2) / det1;
+            const double v3v3 = stiff_jac_times<R>(v2, havg, x, y, fxy, wt, prm, scale, v2v2, v3, nfev);
+            const double v1v3 = wdot<R>(v1, v3, wt), v2v3 = wdot<R>(v2, v3, wt);
+            if (stiff_dominant_real(v3v3, v2v3, v2v2, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
+            const double det2 = v1v1 * v2v2 - v1v2 * v1v2;
+            const double alpha2 = (-v1v1 * v2v3 + v1v2 * v1v3) / det2;
+            const double beta2 = (v1v2 * v2v3 - v2v2 * v1v3) / det2;
+            const double res2 = fabs(v3v3 + v2v2 * (alpha2 * alpha2) + v1v1 * (beta2 * beta2) +
+                                     2 * v2v3 * alpha2 + 2 * v1v3 * beta2 + 2 * v1v2 * alpha2 * beta2);
+            if (res2 <= 1e-6 * v3v3) {
+                double r1[2], r2[2];
+                stiff_quadratic_roots(alpha1, beta1, r1, r2);
+                stiff_quadratic_roots(alpha2, beta2, root1, root2);
+                rho = sqrt(root1[0] * root1[0] + root1[1] * root1[1]);
+                const double D1 = (root1[0] - r1[0]) * (root1[0] - r1[0]) + (root1[1] - r1[1]) * (root1[1] - r1[1]);
+                const double D2 = (root1[0] - r2[0]) * (root1[0] - r2[0]) + (root1[1] - r2[1]) * (root1[1] - r2[1]);
+                if (sqrt(fmin(D1, D2)) <= 0.001 * rho) { converged = true; break; }
+            }
+            const double v3nrm = sqrt(v3v3);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) v0[c] = v3[c] / v3nrm;
+            v0v0 = 1.0;
+        }
+        if (early) break;
+        if (!converged) { stif = -1; rootre = -1; break; }
+        have_root = true;
+        stif = -1;
+    } while (false);
+    int flags = 0;
+    if (have_root) {                                   // common.py:424-455
+        rootre = root1[1] == 0.0 ? 1 : 0;
+        if (root1[0] > 0.0) {
+            stif = 0;
+        } else {
+            const double rho2 = sqrt(root2[0] * root2[0] + root2[1] * root2[1]);
+            if (rho2 >= 0.9 * rho && root2[0] > 0.0) stif = 0;
+            else if (fabs(root1[1]) > fabs(root1[0]) * tanang) stif = -1;
+            else stif = rho >= 0.9 * stbrad ? 1 : 0;
+        }
+    }
+    if (stif < 0) flags = (rootre == 0 && lotsfl) ? STIFF_OSCILLATORY : 0;
+    else if (stif == 1 && rootre >= 0) flags = rootre ? STIFF_REAL : STIFF_COMPLEX;
+    return flags | (nfev << 8);
+}
+
 // ---- one trajectory ---------------------------------------------------------
 template <class Tab, class R>
 struct Lane {
@@ -421,6 +615,23 @@ struct Lane {
     // BS5 extra stages); the per-attempt evaluations are added in store() from
     // the step counters, so the hot loop maintains no evaluation counter.
     int n_acc, n_rej, n_pre, nfev, ieval;
+    // Stiffness diagnosis state lives in shared memory, not in registers: it is
+    // touched once per accepted step, while every register of the lane is
+    // needed for the stage vectors (the kernel sits at its register cap).
+    // Countdowns replace the reference's okstp % 40 and okstp % many_steps.
+    // bits: [0:5] steps to the next 40-step check, [6] okstp > 20,
+    // [7:8] probes waiting in the slots, [9:11] STIFF_* flags, [16:31] jflstp.
+    static constexpr unsigned SB_PAST20 = 1u << 6, SB_PEND1 = 1u << 7, SB_PEND2 = 1u << 8,
+                              SB_FLAG_SHIFT = 9, SB_JFL_SHIFT = 16;
+    struct StiffState {
+        double havg[XSQ_MAX_BLOCK];
+        unsigned bits[XSQ_MAX_BLOCK];
+        int many[XSQ_MAX_BLOCK];
+    };
+    static __device__ __forceinline__ StiffState& stiff_state() {
+        __shared__ StiffState s;
+        return s;
+    }
     bool standard_sc, fresh, step_rejected;
 
     // RungeKutta.__init__, common.py:187-220
@@ -433,6 +644,12 @@ struct Lane {
             y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
         n_acc = n_rej = n_pre = ieval = 0;
+        StiffState& ss = stiff_state();
+        // okstp % 40 == 39 first at step 39; probes of the thread's previous
+        // trajectory may still wait in the slots
+        ss.bits[threadIdx.x] = 38u | (ss.bits[threadIdx.x] & (SB_PEND1 | SB_PEND2));
+        ss.many[threadIdx.x] = P.stiff_many_steps - 2;  // okstp % many == many - 1
+        ss.havg[threadIdx.x] = 0.0;
 #pragma unroll
         for (int k = 0; k < NL; ++k)
             f[k] = P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx];
@@ -817,6 +1034,16 @@ struct Lane {
             nfev += S - 1 + Tab::FSAL;        // this attempt is in no counter
             return LANE_OVERFLOW;
         }
+        // Accepted lanes: f(t+h, y_new) of non-FSAL pairs (common.py:289-291)
+        // and the stiffness bookkeeping (common.py:306) come BEFORE the
+        // controller arithmetic, while the error vector is still live.
+        bool flush = false;
+        if (accept) {
+            if constexpr (!Tab::FSAL)
+                R::f(t_new, y_new, prm, K[S]);
+            if (P.nfev_stiff_detect > 0 && !forced)
+                flush = diagnose(P, K, errv, y_new, t_new, h);
+        }
         const bool tiny_err = ss < NTOT * 0x1.0p-1022;       // err < sqrt(tiny)
         const bool second = accept && !standard_sc;          // 2nd-order SC
         const double b1h = 0.5 * (second ? P.minbeta1 : P.err_exp);
@@ -843,6 +1070,10 @@ struct Lane {
             step_rejected = true;
             ++n_rej;
             if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
+            if (P.nfev_stiff_detect > 0) {                   // ++jflstp, common.py:284
+                unsigned& sb = stiff_state().bits[threadIdx.x];
+                if (sb < 0xFFFF0000u) sb += 1u << SB_JFL_SHIFT;
+            }
             if (bad) return LANE_OVERFLOW;                   // common.py:286
             if (h_abs < min_step) return LANE_TOO_SMALL;     // common.py:234
             if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
@@ -850,8 +1081,6 @@ struct Lane {
         }
         standard_sc = tiny_err;
         if (factor < kMaxFactor) max_factor = kMaxFactor;
-        if constexpr (!Tab::FSAL)               // common.py:289-291
-            R::f(t_new, y_new, prm, K[S]);
         if (!FAST && P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
         // common.py:294-303
         h_prev = h;
@@ -865,7 +1094,104 @@ struct Lane {
         const bool done = forced ? (n_acc >= P.n_forced)
                                  : (P.direction * (t - P.t_bound) >= 0.0);
         if (done) return LANE_FINISHED;
-        return (n_acc + n_rej >= P.max_steps) ? LANE_STEP_BUDGET : LANE_RUNNING;
+        if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
+        return flush ? LANE_FLUSH : LANE_RUNNING;
+    }
+
+    // _diagnose_stiffness, common.py:370-516, bookkeeping part.  Called after an
+    // accepted step, before the state moves on: y is still the old state,
+    // y_new / K[S] / errv belong to the new one.  The probe itself changes
+    // nothing but nfev and the flags, so it is DEFERRED: its inputs go to a
+    // slot in global memory and the persistent loop runs the probes of all
+    // lanes of the warp together (flush_probes) instead of one lane at a time
+    // with 31 lanes idle.
+    // Returns true when both slots are taken: the warp must flush before this
+    // lane's next accepted step.
+    __device__ __forceinline__ bool diagnose(const RkDev& P, double (&K)[KROWS][NL],
+                                             const double (&errv)[NL],
+                                             const double (&y_new)[NL],
+                                             double t_new, double h) {
+        StiffState& ss = stiff_state();
+        unsigned sbits = ss.bits[threadIdx.x];
+        double havg = ss.havg[threadIdx.x];
+        const int cmany = ss.many[threadIdx.x];
+        const unsigned c40 = sbits & 63u;
+        havg = 0.9 * havg + 0.1 * h;
+        if (c40 == 19u && !(sbits & SB_PAST20)) {            // okstp == 20
+            havg = h;
+            sbits = (sbits & 0xFFFFu) | SB_PAST20;           // jflstp = 0
+        }
+        bool lotsfl = false;
+        if (c40 == 0u) {                                     // okstp % 40 == 39
+            lotsfl = (sbits >> SB_JFL_SHIFT) >= 10u;
+            sbits = (sbits & 0xFFC0u) | 39u;                 // jflstp = 0
+        } else {
+            --sbits;
+        }
+        const bool toomch = cmany <= 0;
+        ss.many[threadIdx.x] = toomch ? P.stiff_many_steps - 1 : cmany - 1;
+        ss.havg[threadIdx.x] = havg;
+        bool urgent = false;
+        if (toomch || lotsfl) {
+            using SL = StiffSlot<R>;
+            const long long stride = P.stiff_threads;
+            const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const int islot = (sbits & SB_PEND1) ? 1 : 0;
+            double* s = P.stiff_slot + (long long)islot * SL::DOUBLES * stride + gtid;
+            s[0] = t_new;
+            s[stride] = h;
+            s[2 * stride] = havg;
+            s[3 * stride] = lotsfl ? 1.0 : 0.0;
+            s[4 * stride] = __longlong_as_double(sys);
+            s += SL::HEAD * stride;
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                s[c * stride] = y_new[c];
+                s[(NL + c) * stride] = y[c];
+                s[(2 * NL + c) * stride] = K[S][c];
+                s[(3 * NL + c) * stride] = errv[c];
+            }
+#pragma unroll
+            for (int c = 0; c < R::NPL; ++c) s[(4 * NL + c) * stride] = prm[c];
+            sbits += SB_PEND1;                               // 0 -> 1 -> 2
+            urgent = (sbits & SB_PEND2) != 0u;
+        }
+        ss.bits[threadIdx.x] = sbits;
+        return urgent;
+    }
+
+    static __device__ __forceinline__ bool probes_pending() {
+        return (stiff_state().bits[threadIdx.x] & (SB_PEND1 | SB_PEND2)) != 0u;
+    }
+
+    // Runs the waiting probes of this thread.  A probe only adds to nfev and to
+    // the flags of its trajectory: for the trajectory the thread is on now
+    // (`cur`) they are returned / kept in shared memory, for one that has
+    // already been stored they are applied to its results in global memory.
+    // Touches no Lane member (see rk_persistent_body).
+    static __device__ __forceinline__ int flush_probes(const RkDev& P, long long cur, int lane) {
+        using SL = StiffSlot<R>;
+        const long long stride = P.stiff_threads;
+        const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned sbits = stiff_state().bits[threadIdx.x];
+        int evals = 0;
+        while (sbits & (SB_PEND1 | SB_PEND2)) {
+            sbits -= SB_PEND1;
+            const int islot = (sbits & SB_PEND1) ? 1 : 0;
+            const double* slot = P.stiff_slot + (long long)islot * SL::DOUBLES * stride + gtid;
+            const int r = stiff_probe_dev<R>(slot, stride, P.t_bound, P.nfev_stiff_detect, S,
+                                             Tab::STBRAD, Tab::TANANG);
+            const long long owner = __double_as_longlong(slot[4 * stride]);
+            if (owner == cur) {
+                evals += r >> 8;
+                sbits |= (unsigned)(r & 7) << SB_FLAG_SHIFT;
+            } else if (!R::WARP || lane == 0) {
+                P.nfev[owner] += r >> 8;
+                if (P.stiff_flags) P.stiff_flags[owner] |= r & 7;
+            }
+        }
+        stiff_state().bits[threadIdx.x] = sbits;
+        return evals;
     }
 
     // RHS evaluations made by attempt(): S-1 stages (+1 if FSAL) per full
@@ -897,6 +1223,8 @@ struct Lane {
             P.nfev[sys] = nfev + evals_in_loop();
             P.status[sys] = st;
             if (P.n_eval_done) P.n_eval_done[sys] = ieval;
+            if (P.stiff_flags) P.stiff_flags[sys] =
+                    (int)((stiff_state().bits[threadIdx.x] >> SB_FLAG_SHIFT) & 7u);
         }
     }
 };
@@ -914,6 +1242,28 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     bool live = false;
     bool exhausted = false;
     const bool fast = P.n_forced == 0 && P.n_eval == 0;
+    Lane<Tab, R>::stiff_state().bits[threadIdx.x] = 0u;
+    // Stiffness probes wait in their slots until kProbeWindow attempts have
+    // passed, so that one pass serves many lanes of the warp (a trajectory may
+    // end, and the thread start the next one, while its probes wait).  The
+    // probe is an out-of-line call in a kernel that sits at its register cap:
+    // anything live across it would be spilled for the whole kernel, hot loop
+    // included.  So the lane is parked in local memory by hand for the
+    // duration of the (rare) pass and nothing but `live` crosses it.
+    constexpr int kProbeWindow = 1024;
+    int it = 0;
+    auto flush = [&](long long cur) {
+        if (!__any_sync(full, Lane<Tab, R>::probes_pending())) return;
+        if (Lane<Tab, R>::probes_pending()) {
+            Lane<Tab, R> parked = L;
+            asm volatile("" ::"l"(&parked) : "memory");
+            const int evals = Lane<Tab, R>::flush_probes(P, cur, lane);
+            asm volatile("" ::"l"(&parked) : "memory");
+            L = parked;
+            L.nfev += evals;
+        }
+        __syncwarp(full);
+    };
     for (;;) {
         // ---- refill ----
         if (R::WARP) {
@@ -960,22 +1310,30 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         }
         if (__all_sync(full, !live)) break;
         // ---- attempts, until some lane of the warp ends its trajectory ----
+        // Leaves the loop when a lane ends or has both probe slots taken
+        // (LANE_FLUSH), and after kProbeWindow attempts (see below).
         int st = LANE_RUNNING;
         if (fast) {
             do {
                 if (live) st = L.template attempt<true>(P, lane);
-            } while (!__any_sync(full, st != LANE_RUNNING));
+            } while (!__any_sync(full, st != LANE_RUNNING) && ++it < kProbeWindow);
         } else {
             do {
                 if (live) st = L.template attempt<false>(P, lane);
-            } while (!__any_sync(full, st != LANE_RUNNING));
+            } while (!__any_sync(full, st != LANE_RUNNING) && ++it < kProbeWindow);
         }
+        const bool expired = it >= kProbeWindow;
+        if (expired) it = 0;
+        if (P.nfev_stiff_detect > 0 && (expired || __any_sync(full, st == LANE_FLUSH)))
+            flush(live ? L.sys : -1);
+        if (st == LANE_FLUSH) st = LANE_RUNNING;
         if (st != LANE_RUNNING) {
             L.store(P, st, lane);
             live = false;
         }
         __syncwarp(full);
     }
+    if (P.nfev_stiff_detect > 0) flush(-1);      // probes of stored trajectories
 }
 
 template <class Tab, class R, int BLOCK, int MINB>

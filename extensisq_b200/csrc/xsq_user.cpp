@@ -188,13 +188,14 @@ std::string tableau_source(const xsq_tableau_t& t) {
             if (d != 0.0 && d < cdiff) cdiff = d;
         }
     if (cdiff < 1e-3) cdiff = 1e-3;
-    char buf[256];
+    char buf[512];
     std::snprintf(buf, sizeof buf,
                   "    static constexpr int ID = 100, S = %d, ORDER = %d, "
                   "ORDER2 = %d, FSAL = %d, NPOL = %d, VARIANT = GENERIC;\n"
-                  "    static constexpr double H_MIN_A = %a;\n",
+                  "    static constexpr double H_MIN_A = %a;\n"
+                  "    static constexpr double STBRAD = %a, TANANG = %a;\n",
                   s, t.order, t.order_secondary, t.E[s] != 0.0 ? 1 : 0,
-                  t.n_poly, 10 * 0x1.0p-53 / cdiff);
+                  t.n_poly, 10 * 0x1.0p-53 / cdiff, t.stbrad, t.tanang);
     o += buf;
     std::snprintf(buf, sizeof buf,
                   "    static constexpr double SC_KB1 = %a, SC_KB2 = %a, "
@@ -421,7 +422,7 @@ bool user_tableau_info(MethodInfo* mi) {
     *mi = MethodInfo{t.n_stages, t.order, t.order_secondary,
                      t.E[t.n_stages] != 0.0 ? 1 : 0, t.n_poly,
                      {t.sc_params[0], t.sc_params[1], t.sc_params[2],
-                      t.sc_params[3]}};
+                      t.sc_params[3]}, t.stbrad, t.tanang};
     return true;
 }
 

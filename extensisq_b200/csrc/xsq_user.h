@@ -10,6 +10,7 @@ namespace xsq {
 struct MethodInfo {
     int s, order, order2, fsal, npol;
     double sc[4];
+    double stbrad, tanang;
 };
 
 void set_detail(const std::string& s);

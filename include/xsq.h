@@ -76,6 +76,14 @@ typedef enum xsq_rhs_id {
     XSQ_RHS_USER_BASE = 1000
 } xsq_rhs_id;
 
+/* what the reference reports as warnings (common.py:459-516) */
+typedef enum xsq_stiff_flag {
+    XSQ_STIFF_REAL = 1,        /* real dominant root, diagnosed as stiff        */
+    XSQ_STIFF_COMPLEX = 2,     /* complex dominant pair, diagnosed as stiff     */
+    XSQ_STIFF_OSCILLATORY = 4  /* complex pair near the imaginary axis and many
+                                  recently failed steps                         */
+} xsq_stiff_flag;
+
 typedef enum xsq_interpolant {      /* BS5 only, bogacki.py:217-236 */
     XSQ_INTERP_DEFAULT = 0, XSQ_INTERP_FREE = 1, XSQ_INTERP_LOW = 2,
     XSQ_INTERP_BEST = 3
@@ -92,6 +100,8 @@ typedef struct xsq_tableau {
     double E[XSQ_MAX_STAGES + 1];
     double P[XSQ_MAX_STAGES + 1][XSQ_MAX_POLY];
     double sc_params[4];            /* (kb1, kb2, a, g), common.py:166-185   */
+    double stbrad, tanang;          /* stiffness detection (common.py:113-115);
+                                       <= 0: not implemented for this method */
 } xsq_tableau_t;
 
 /* Arguments of one batched explicit-RK solve: replaces
@@ -134,6 +144,11 @@ typedef struct xsq_rk_args {
     int32_t* nfev;            /* [n_lanes]                                   */
     int32_t* status;          /* [n_lanes]  xsq_lane_status                  */
     int32_t* n_eval_done;     /* [n_lanes] t_eval points written, may be NULL */
+    int32_t nfev_stiff_detect;/* stiffness diagnosis every this many RHS
+                                 evaluations (common.py:150-164, 370-516);
+                                 0 = off; the reference's default is 5000   */
+    int32_t reserved1;
+    int32_t* stiff_flags;     /* [n_lanes] OR of xsq_stiff_flag, may be NULL  */
 } xsq_rk_args_t;
 
 int xsq_abi_version(void);

@@ -29,6 +29,7 @@ class OTab(C.Structure):
         ("Pbest", (C.c_double * MAXPOL) * (MAXS + 4)),
         ("npol_low", C.c_int32), ("npol_best", C.c_int32),
         ("sc", C.c_double * 4),
+        ("stbrad", C.c_double), ("tanang", C.c_double),
     ]
 
 
@@ -92,6 +93,9 @@ def make_tab(tab, sc_params=None):
         scp = O.SC_PRESETS[scp]
     for i in range(4):
         t.sc[i] = float(scp[i])
+    sb, ta = getattr(tab, "stbrad", None), getattr(tab, "tanang", None)
+    t.stbrad = float(sb) if isinstance(sb, (int, float)) else 0.0
+    t.tanang = float(ta) if isinstance(ta, (int, float)) else 0.0
     return t
 
 
@@ -106,7 +110,7 @@ def _ip(a):
 def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
              first_step=None, max_step=np.inf, sc_params=None,
              interpolant=None, t_eval=None, forced_h=None, max_steps=0,
-             n_threads=1, user_fn=None, n_param=None):
+             n_threads=1, user_fn=None, n_param=None, nfev_stiff_detect=5000):
     """Integrate N lanes with the C oracle.  y0 [N, n], params [N, p].
     `rhs`: built-in name, or None with `user_fn` = python callable
     f(t, y) -> dy (slow; single thread).  Returns a dict of numpy arrays."""
@@ -137,6 +141,7 @@ def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
     nfev = np.empty(N, np.int32)
     status = np.empty(N, np.int32)
     n_done = np.empty(N, np.int32)
+    stiff = np.zeros(N, np.int32)
     if rhs is not None:
         rid, cb = RHS_IDS[rhs], RHS_FN()
     else:
@@ -158,12 +163,12 @@ def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
         _dp(y_eval), _dp(hf), C.c_int(hf.size if hf is not None else 0),
         C.c_int(max_steps), _dp(t_final), _dp(y_final), _dp(h_next),
         _ip(n_acc), _ip(n_rej), _ip(nfev), _ip(status), _ip(n_done),
-        C.c_int(n_threads))
+        C.c_int(n_threads), C.c_int(nfev_stiff_detect), _ip(stiff))
     if rc != 0:
         raise RuntimeError("xsq_oracle_rk_batch failed")
     return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
                 h_next=h_next, n_accepted=n_acc, n_rejected=n_rej, nfev=nfev,
-                status=status, n_eval_done=n_done)
+                status=status, n_eval_done=n_done, stiff_flags=stiff)
 
 
 def swag_batch(rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,

@@ -26,9 +26,10 @@ the build container and stores its outputs under ``tests/golden/``;
 ``tests/test_oracle_golden.py`` requires exact equality of step counts and
 states (to 1e-13 relative, to tolerate a different BLAS on the GPU host).
 
-Stiffness diagnosis (``common.py:370-516``) only emits warnings and extra RHS
-evaluations; it never changes t, y or h.  The oracle corresponds to
-``nfev_stiff_detect=0``.
+Stiffness diagnosis (``common.py:370-516``, ``stiff_a..d`` ``:824-1204``, a
+port of RKSuite) only emits warnings and spends extra RHS evaluations; it
+never changes t, y or h.  It is restated in ``_diagnose_stiffness`` /
+``stiff_probe``; default ``nfev_stiff_detect=5000`` as in the reference.
 """
 import json
 import os
@@ -67,6 +68,8 @@ class Tableau:
         self.order = d["order"]
         self.order_secondary = d["order_secondary"]
         self.sc_params = d["sc_params"]
+        self.stbrad = d.get("stbrad")
+        self.tanang = d.get("tanang")
         for k in ("A", "B", "C", "E", "P", "E_pre", "B_scale_pre", "C_extra",
                   "A_extra", "Plow", "Pbest"):
             if k in d:
@@ -236,6 +239,179 @@ def cubic(t_old, t, y_old, y, f_old, f, ts):
 
 
 # --------------------------------------------------------------------------
+# stiffness diagnosis  (common.py:824-1204: stiff_a, stiff_b, stiff_c, stiff_d)
+# --------------------------------------------------------------------------
+def _wdot(a, b, wt):
+    return (a / wt) @ (b / wt)
+
+
+def _jac_times(v, havg, x, y, f, fxy, wt, scale, vdotv):      # stiff_d
+    temp1 = scale / sqrt(vdotv)
+    z = f(x, y + temp1 * v)
+    z = havg / temp1 * (z - fxy)
+    return z, (z / wt) @ (z / wt)
+
+
+def _dominant_real(v1v1, v0v1, v0v0, rold):                   # stiff_b
+    r = v0v1 / v0v0
+    rho = abs(r)
+    det = v0v0 * v1v1 - v0v1 ** 2
+    res = abs(det / v0v0)
+    rootre = det == 0.0 or (res <= 1e-6 * v1v1 and
+                            abs(r - rold) <= 0.001 * rho)
+    root1 = [r if rootre else 0.0, 0.0]
+    return r, rho, root1, [0.0, 0.0], rootre
+
+
+def _quadratic_roots(alpha, beta):                            # stiff_c
+    r1, r2 = [0.0, 0.0], [0.0, 0.0]
+    temp = alpha / 2
+    disc = temp ** 2 - beta
+    if disc == 0.0:
+        r1[0] = r2[0] = -temp
+        return r1, r2
+    sqdisc = sqrt(abs(disc))
+    if disc < 0.0:
+        r1[0] = r2[0] = -temp
+        r1[1] = sqdisc
+        r2[1] = -sqdisc
+    else:
+        r1[0] = -temp - sqdisc if temp > 0.0 else -temp + sqdisc
+        r2[0] = beta / r1[0]
+    return r1, r2
+
+
+def stiff_probe(f, x, y, hnow, havg, xend, maxfcn, wt, fxy, v0, cost):
+    """stiff_a: returns (stif, rootre, roots) with stif in {True, False,
+    None}; roots = (root1, root2, rho) or None."""
+    epsneg = np.finfo(float).epsneg
+    rootre = None
+    if abs(hnow / havg) > 5 or abs(hnow / havg) < 0.2:
+        return False, rootre, None
+    xtrfcn = cost * abs((xend - x) / havg)
+    if xtrfcn <= maxfcn:
+        return False, rootre, None
+    ynrm = sqrt((y / wt) @ (y / wt))
+    sqrrmc = sqrt(epsneg)
+    scale = ynrm * sqrrmc
+    if scale == 0.0:
+        ynrm = sqrt((v0 / wt) @ (v0 / wt))
+        scale = ynrm * sqrrmc
+        if scale == 0.0:
+            return None, rootre, None
+    v0v0 = (v0 / wt) @ (v0 / wt)
+    if v0v0 == 0.0:
+        v0[:] = 1.0
+        v0v0 = (v0 / wt) @ (v0 / wt)
+    v0nrm = sqrt(v0v0)
+    v0 /= v0nrm
+    v0v0 = 1.0
+    for ntry in range(8):
+        v1, v1v1 = _jac_times(v0, havg, x, y, f, fxy, wt, scale, v0v0)
+        if sqrt(v1v1) > 1.0e10 * sqrt(v0v0):
+            return None, None, None
+        v0v1 = (v0 / wt) @ (v1 / wt)
+        if ntry == 0:
+            rold = v0v1 / v0v0
+            if abs(rold) < epsneg ** (1 / 3):
+                return False, None, None
+        else:
+            rold, rho, root1, root2, rootre = _dominant_real(v1v1, v0v1,
+                                                             v0v0, rold)
+            if rootre:
+                break
+        v2, v2v2 = _jac_times(v1, havg, x, y, f, fxy, wt, scale, v1v1)
+        v0v2 = (v0 / wt) @ (v2 / wt)
+        v1v2 = (v1 / wt) @ (v2 / wt)
+        rold, rho, root1, root2, rootre = _dominant_real(v2v2, v1v2, v1v1,
+                                                         rold)
+        if rootre:
+            break
+        det1 = v0v0 * v1v1 - v0v1 ** 2
+        alpha1 = (-v0v0 * v1v2 + v0v1 * v0v2) / det1
+        beta1 = (v0v1 * v1v2 - v1v1 * v0v2) / det1
+        v3, v3v3 = _jac_times(v2, havg, x, y, f, fxy, wt, scale, v2v2)
+        v1v3 = (v1 / wt) @ (v3 / wt)
+        v2v3 = (v2 / wt) @ (v3 / wt)
+        rold, rho, root1, root2, rootre = _dominant_real(v3v3, v2v3, v2v2,
+                                                         rold)
+        if rootre:
+            break
+        det2 = v1v1 * v2v2 - v1v2 ** 2
+        alpha2 = (-v1v1 * v2v3 + v1v2 * v1v3) / det2
+        beta2 = (v1v2 * v2v3 - v2v2 * v1v3) / det2
+        res2 = abs(v3v3 + v2v2 * alpha2 ** 2 + v1v1 * beta2 ** 2 +
+                   2 * v2v3 * alpha2 + 2 * v1v3 * beta2 +
+                   2 * v1v2 * alpha2 * beta2)
+        if res2 <= 1e-6 * v3v3:
+            r1, r2 = _quadratic_roots(alpha1, beta1)
+            root1, root2 = _quadratic_roots(alpha2, beta2)
+            rho = sqrt(root1[0] ** 2 + root1[1] ** 2)
+            D1 = (root1[0] - r1[0]) ** 2 + (root1[1] - r1[1]) ** 2
+            D2 = (root1[0] - r2[0]) ** 2 + (root1[1] - r2[1]) ** 2
+            if sqrt(min(D1, D2)) <= 0.001 * rho:
+                break
+        v3nrm = sqrt(v3v3)
+        v0 = v3 / v3nrm
+        v0v0 = 1.0
+    else:
+        return None, None, None
+    return None, rootre, (root1, root2, rho)
+
+
+# diagnosis codes recorded per trajectory (the reference only warns/logs)
+STIFF_REAL, STIFF_COMPLEX, OSCILLATORY = 1, 2, 4
+
+
+def _diagnose_stiffness(st):                      # common.py:370-516
+    if st.nfev_stiff_detect == 0:
+        return
+    tab = st.tab
+    st.okstp += 1
+    h = st.h_previous
+    st.havg = 0.9 * st.havg + 0.1 * h
+    if st.okstp == 20:
+        st.havg = h
+        st.jflstp = 0
+    if st.okstp % 40 == 39:
+        lotsfl = st.jflstp >= 10
+        st.jflstp = 0
+    else:
+        lotsfl = False
+    many_steps = st.nfev_stiff_detect // tab.n_stages
+    toomch = st.okstp % many_steps == many_steps - 1
+    if not (toomch or lotsfl):
+        return
+    s = tab.n_stages
+    avgy = 0.5 * (np.abs(st.y) + np.abs(st.y_old))
+    wt = np.maximum(avgy, sqrt(np.finfo(float).tiny))
+    v0 = np.atleast_1d(st.h_previous * (st.K[:s + st.FSAL].T @
+                                        tab.E[:s + st.FSAL]))
+    stif, rootre, root = stiff_probe(
+        st.fun, st.t, st.y, st.h_previous, st.havg, st.t_bound,
+        st.nfev_stiff_detect, wt, st.f, v0, s)
+    st.n_stiff_tests += 1
+    if root is not None:
+        root1, root2, rho = root
+        rootre = root1[1] == 0.0
+        if root1[0] > 0.0:
+            stif = False
+        else:
+            rho2 = sqrt(root2[0] ** 2 + root2[1] ** 2)
+            if rho2 >= 0.9 * rho and root2[0] > 0.0:
+                stif = False
+            elif abs(root1[1]) > abs(root1[0]) * tab.tanang:
+                stif = None
+            else:
+                stif = rho >= 0.9 * tab.stbrad
+    if stif is None:
+        if rootre is not None and not rootre and lotsfl:
+            st.stiff_flags |= OSCILLATORY
+    elif stif and rootre is not None:
+        st.stiff_flags |= STIFF_REAL if rootre else STIFF_COMPLEX
+
+
+# --------------------------------------------------------------------------
 # the solver state + one step
 # --------------------------------------------------------------------------
 class RKState:
@@ -243,7 +419,7 @@ class RKState:
 
     def __init__(self, tab, fun, t0, y0, t_bound, max_step=np.inf, rtol=1e-3,
                  atol=1e-6, first_step=None, sc_params=None,
-                 interpolant=None):
+                 interpolant=None, nfev_stiff_detect=5000):
         self.tab = tab
         self.nfev = 0
         self._fun = fun
@@ -318,6 +494,18 @@ class RKState:
         self.y_old = None
         self.f_old = None
         self.error_norm_old = None
+        # stiffness diagnosis state, common.py:150-164
+        if not (isinstance(nfev_stiff_detect, int) and nfev_stiff_detect >= 0):
+            raise ValueError(
+                "`nfev_stiff_detect` must be a non-negative integer.")
+        self.nfev_stiff_detect = nfev_stiff_detect
+        if tab.stbrad is None or tab.tanang is None:   # common.py:155-160
+            self.nfev_stiff_detect = 0
+        self.jflstp = 0
+        self.okstp = 0
+        self.havg = 0.0
+        self.n_stiff_tests = 0
+        self.stiff_flags = 0
         self.n_rejected = 0            # the reference's global NFS
         self.n_accepted = 0
         self.status = "running"
@@ -407,6 +595,8 @@ def rk_step(st, forced_h=None):
                     h_abs *= max(st.min_factor, st.safety *
                                  error_norm_pre ** st.error_exponent)
                     st.n_rejected += 1
+                    if st.nfev_stiff_detect:          # bogacki.py:272-273
+                        st.jflstp += 1
                     continue
                 _rk_stage(st, h, s - 1)
             y_new, error_norm = _comp_sol_err(st, y, h)
@@ -439,6 +629,7 @@ def rk_step(st, forced_h=None):
                 h_abs *= max(st.min_factor,
                              st.safety * error_norm ** st.error_exponent)
                 st.n_rejected += 1
+                st.jflstp += 1                    # common.py:284
                 if bad:                           # common.py:286-287
                     return False, OVERFLOW
 
@@ -454,6 +645,8 @@ def rk_step(st, forced_h=None):
     st.t = t + h
     st.y = y_new
     st.n_accepted += 1
+    if forced_h is None:
+        _diagnose_stiffness(st)                   # common.py:306
     return True, None
 
 
@@ -503,7 +696,8 @@ def dense_eval(st, ts):
 
 def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
              first_step=None, t_eval=None, sc_params=None, interpolant=None,
-             forced_h=None, record=False, max_steps=None):
+             forced_h=None, record=False, max_steps=None,
+             nfev_stiff_detect=5000):
     """solve_ivp(fun, t_span, y0, method=<tab>, ...) restated.
 
     Returns a dict with t, y (n x n_t), n_accepted, n_rejected, nfev, status,
@@ -514,11 +708,13 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
     if forced_h is not None:
         st = RKState(tab, fun, t0, y0, copysign(np.inf, tf - t0),
                      rtol=rtol, atol=atol, first_step=forced_h[0],
-                     sc_params=sc_params, interpolant=interpolant)
+                     sc_params=sc_params, interpolant=interpolant,
+                     nfev_stiff_detect=0)
     else:
         st = RKState(tab, fun, t0, y0, tf, max_step=max_step, rtol=rtol,
                      atol=atol, first_step=first_step, sc_params=sc_params,
-                     interpolant=interpolant)
+                     interpolant=interpolant,
+                     nfev_stiff_detect=nfev_stiff_detect)
     if t_eval is not None:
         t_eval = np.asarray(t_eval, dtype=float)
         if st.direction > 0:
@@ -586,7 +782,8 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
         ys = np.zeros((st.n, 0))
     out = dict(t=ts, y=ys, n_accepted=st.n_accepted, n_rejected=st.n_rejected,
                nfev=st.nfev, status=status, message=message, t_final=st.t,
-               y_final=st.y.copy(), h_next=st.h_abs)
+               y_final=st.y.copy(), h_next=st.h_abs,
+               n_stiff_tests=st.n_stiff_tests, stiff_flags=st.stiff_flags)
     if record:
         out["h"] = np.array(hs)
     return out

@@ -61,6 +61,7 @@ typedef struct {
     double Plow[MAXS + 2][MAXPOL], Pbest[MAXS + 4][MAXPOL];
     int32_t npol_low, npol_best;
     double sc[4];
+    double stbrad, tanang;      /* <= 0: stiffness diagnosis not implemented */
 } otab_t;
 
 typedef void (*rhs_fn)(double t, const double* y, const double* p, double* dy);
@@ -140,6 +141,9 @@ typedef struct {
     double y[MAXN], fcur[MAXN];
     double K[KROWS][MAXN];
     int n_acc, n_rej, nfev, standard_sc;
+    /* stiffness diagnosis, common.py:150-164 */
+    int nfev_stiff_detect, jflstp, okstp, stiff_flags, n_stiff_tests;
+    double havg;
 } lane_t;
 
 /* common.py:64-66, sequential accumulation */
@@ -374,6 +378,159 @@ static int emit(lane_t* L, double h, double t_new, const double* y_new,
     return ieval;
 }
 
+/* ---- stiffness diagnosis: common.py:370-516 and stiff_a..d (:824-1204) ---- */
+static double wdot(const double* a, const double* b, const double* wt, int n) {
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) s = fma(a[c] / wt[c], b[c] / wt[c], s);
+    return s;
+}
+/* stiff_d: z ~ havg * J * v by a difference of f; returns <z, z> */
+static double jac_times(lane_t* L, const double* v, double havg, double x, const double* y,
+                        const double* fxy, const double* wt, double scale, double vdotv,
+                        double* z) {
+    const int n = L->n;
+    const double temp1 = scale / sqrt(vdotv);
+    double yp[MAXN];
+    for (int c = 0; c < n; ++c) yp[c] = fma(temp1, v[c], y[c]);
+    L->f(x, yp, L->prm, z);
+    L->nfev++;
+    const double q = havg / temp1;
+    for (int c = 0; c < n; ++c) z[c] = q * (z[c] - fxy[c]);
+    return wdot(z, z, wt, n);
+}
+/* stiff_b */
+static int dominant_real(double v1v1, double v0v1, double v0v0, double* rold, double* rho,
+                         double* root1, double* root2) {
+    const double r = v0v1 / v0v0;
+    *rho = fabs(r);
+    const double det = v0v0 * v1v1 - v0v1 * v0v1;
+    const double res = fabs(det / v0v0);
+    const int rootre = det == 0.0 || (res <= 1e-6 * v1v1 && fabs(r - *rold) <= 0.001 * *rho);
+    root1[0] = rootre ? r : 0.0; root1[1] = 0.0; root2[0] = root2[1] = 0.0;
+    *rold = r;
+    return rootre;
+}
+/* stiff_c: roots of x^2 + alpha x + beta */
+static void quadratic_roots(double alpha, double beta, double* r1, double* r2) {
+    r1[0] = r1[1] = r2[0] = r2[1] = 0.0;
+    const double temp = alpha / 2;
+    const double disc = temp * temp - beta;
+    if (disc == 0.0) { r1[0] = r2[0] = -temp; return; }
+    const double sqdisc = sqrt(fabs(disc));
+    if (disc < 0.0) { r1[0] = r2[0] = -temp; r1[1] = sqdisc; r2[1] = -sqdisc; }
+    else { r1[0] = temp > 0.0 ? -temp - sqdisc : -temp + sqdisc; r2[0] = beta / r1[0]; }
+}
+/* stiff_a.  returns stif: 1 true, 0 false, -1 unsure; *rootre: 1/0/-1;
+ * *have_root: roots/rho valid */
+static int stiff_probe(lane_t* L, double x, const double* y, double hnow, double havg,
+                       double xend, int maxfcn, const double* wt, const double* fxy,
+                       double* v0, int cost, int* rootre, int* have_root, double* root1,
+                       double* root2, double* rho) {
+    const int n = L->n;
+    const double epsneg = 0x1.0p-53;
+    *rootre = -1; *have_root = 0;
+    if (fabs(hnow / havg) > 5 || fabs(hnow / havg) < 0.2) return 0;
+    const double xtrfcn = cost * fabs((xend - x) / havg);
+    if (xtrfcn <= maxfcn) return 0;
+    double ynrm = sqrt(wdot(y, y, wt, n));
+    const double sqrrmc = sqrt(epsneg);
+    double scale = ynrm * sqrrmc;
+    if (scale == 0.0) {
+        ynrm = sqrt(wdot(v0, v0, wt, n));
+        scale = ynrm * sqrrmc;
+        if (scale == 0.0) return -1;
+    }
+    double v0v0 = wdot(v0, v0, wt, n);
+    if (v0v0 == 0.0) {
+        for (int c = 0; c < n; ++c) v0[c] = 1.0;
+        v0v0 = wdot(v0, v0, wt, n);
+    }
+    const double v0nrm = sqrt(v0v0);
+    for (int c = 0; c < n; ++c) v0[c] /= v0nrm;
+    v0v0 = 1.0;
+    double v1[MAXN], v2[MAXN], v3[MAXN], rold = 0.0;
+    int converged = 0;
+    for (int ntry = 0; ntry < 8; ++ntry) {
+        const double v1v1 = jac_times(L, v0, havg, x, y, fxy, wt, scale, v0v0, v1);
+        if (sqrt(v1v1) > 1.0e10 * sqrt(v0v0)) { *rootre = -1; return -1; }
+        const double v0v1 = wdot(v0, v1, wt, n);
+        if (ntry == 0) {
+            rold = v0v1 / v0v0;
+            if (fabs(rold) < cbrt(epsneg)) { *rootre = -1; return 0; }
+        } else {
+            if (dominant_real(v1v1, v0v1, v0v0, &rold, rho, root1, root2)) { *rootre = 1; converged = 1; break; }
+            *rootre = 0;
+        }
+        const double v2v2 = jac_times(L, v1, havg, x, y, fxy, wt, scale, v1v1, v2);
+        const double v0v2 = wdot(v0, v2, wt, n), v1v2 = wdot(v1, v2, wt, n);
+        if (dominant_real(v2v2, v1v2, v1v1, &rold, rho, root1, root2)) { *rootre = 1; converged = 1; break; }
+        *rootre = 0;
+        const double det1 = v0v0 * v1v1 - v0v1 * v0v1;
+        const double alpha1 = (-v0v0 * v1v2 + v0v1 * v0v2) / det1;
+        const double beta1 = (v0v1 * v1v2 - v1v1 * v0v2) / det1;
+        const double v3v3 = jac_times(L, v2, havg, x, y, fxy, wt, scale, v2v2, v3);
+        const double v1v3 = wdot(v1, v3, wt, n), v2v3 = wdot(v2, v3, wt, n);
+        if (dominant_real(v3v3, v2v3, v2v2, &rold, rho, root1, root2)) { *rootre = 1; converged = 1; break; }
+        const double det2 = v1v1 * v2v2 - v1v2 * v1v2;
+        const double alpha2 = (-v1v1 * v2v3 + v1v2 * v1v3) / det2;
+        const double beta2 = (v1v2 * v2v3 - v2v2 * v1v3) / det2;
+        const double res2 = fabs(v3v3 + v2v2 * (alpha2 * alpha2) + v1v1 * (beta2 * beta2) +
+                                 2 * v2v3 * alpha2 + 2 * v1v3 * beta2 + 2 * v1v2 * alpha2 * beta2);
+        if (res2 <= 1e-6 * v3v3) {
+            double r1[2], r2[2];
+            quadratic_roots(alpha1, beta1, r1, r2);
+            quadratic_roots(alpha2, beta2, root1, root2);
+            *rho = sqrt(root1[0] * root1[0] + root1[1] * root1[1]);
+            const double D1 = (root1[0] - r1[0]) * (root1[0] - r1[0]) + (root1[1] - r1[1]) * (root1[1] - r1[1]);
+            const double D2 = (root1[0] - r2[0]) * (root1[0] - r2[0]) + (root1[1] - r2[1]) * (root1[1] - r2[1]);
+            if (sqrt(fmin(D1, D2)) <= 0.001 * *rho) { converged = 1; break; }
+        }
+        const double v3nrm = sqrt(v3v3);
+        for (int c = 0; c < n; ++c) v0[c] = v3[c] / v3nrm;
+        v0v0 = 1.0;
+    }
+    if (!converged) { *rootre = -1; return -1; }
+    *have_root = 1;
+    return -1;
+}
+
+/* called after every accepted step (state already advanced); errv = h * K^T E */
+static void diagnose_stiffness(lane_t* L, const double* y_old, const double* errv, double h) {
+    if (L->nfev_stiff_detect == 0) return;
+    const otab_t* T = L->T;
+    const int n = L->n;
+    L->okstp += 1;
+    L->havg = 0.9 * L->havg + 0.1 * h;
+    if (L->okstp == 20) { L->havg = h; L->jflstp = 0; }
+    int lotsfl = 0;
+    if (L->okstp % 40 == 39) { lotsfl = L->jflstp >= 10; L->jflstp = 0; }
+    const int many_steps = L->nfev_stiff_detect / T->s;
+    const int toomch = L->okstp % many_steps == many_steps - 1;
+    if (!(toomch || lotsfl)) return;
+    double wt[MAXN], v0[MAXN];
+    for (int c = 0; c < n; ++c) {
+        wt[c] = fmax(0.5 * (fabs(L->y[c]) + fabs(y_old[c])), SQRT_TINY);
+        v0[c] = errv[c];
+    }
+    int rootre, have_root;
+    double root1[2], root2[2], rho = 0.0;
+    int stif = stiff_probe(L, L->t, L->y, h, L->havg, L->t_bound, L->nfev_stiff_detect, wt,
+                           L->fcur, v0, T->s, &rootre, &have_root, root1, root2, &rho);
+    L->n_stiff_tests++;
+    if (have_root) {
+        rootre = root1[1] == 0.0;
+        if (root1[0] > 0.0) stif = 0;
+        else {
+            const double rho2 = sqrt(root2[0] * root2[0] + root2[1] * root2[1]);
+            if (rho2 >= 0.9 * rho && root2[0] > 0.0) stif = 0;
+            else if (fabs(root1[1]) > fabs(root1[0]) * T->tanang) stif = -1;
+            else stif = rho >= 0.9 * T->stbrad;
+        }
+    }
+    if (stif < 0) { if (rootre == 0 && lotsfl) L->stiff_flags |= 4; }
+    else if (stif == 1 && rootre >= 0) L->stiff_flags |= rootre ? 1 : 2;
+}
+
 /* One trajectory: solve_ivp(fun, (t0, tf), y0, method=T, ...). */
 static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                          const double* prm, double t0, double tf, double rtol,
@@ -383,8 +540,12 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                          int n_forced, int max_steps, double* t_final,
                          double* y_final, double* h_next, int32_t* n_acc,
                          int32_t* n_rej, int32_t* nfev, int32_t* status,
-                         int32_t* n_eval_done) {
+                         int32_t* n_eval_done, int nfev_stiff_detect,
+                         int32_t* stiff_flags) {
     lane_t* L = (lane_t*)malloc(sizeof(lane_t));
+    L->nfev_stiff_detect = (T->stbrad > 0.0 && T->tanang > 0.0) ? nfev_stiff_detect : 0;
+    L->jflstp = L->okstp = L->stiff_flags = L->n_stiff_tests = 0;
+    L->havg = 0.0;
     const int s = T->s;
     L->T = T; L->f = f; L->prm = prm; L->n = n;
     L->rtol = rtol; L->atol = atol;
@@ -459,6 +620,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                     step_rejected = 1;
                     L->h_abs *= fmax(0.2, L->safety * pow(err_pre, L->err_exp));
                     L->n_rej++;
+                    if (L->nfev_stiff_detect) L->jflstp++;
                     continue;
                 }
                 rk_stage(L, h, s - 1);
@@ -493,6 +655,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                     step_rejected = 1;
                     L->h_abs *= fmax(0.2, L->safety * pow(err, L->err_exp));
                     L->n_rej++;
+                    L->jflstp++;
                     if (bad) { st = ST_OVERFLOW; break; }
                     continue;
                 }
@@ -502,9 +665,12 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
             L->h_prev = h;
             L->err_old = err;
             L->t = t_new;
+            double y_old[MAXN];
+            memcpy(y_old, L->y, sizeof(double) * n);
             memcpy(L->y, y_new, sizeof(double) * n);
             memcpy(L->fcur, L->K[s], sizeof(double) * n);
             L->n_acc++;
+            if (!forced) diagnose_stiffness(L, y_old, errv, h);
             if (forced) { if (L->n_acc >= n_forced) st = ST_FINISHED; }
             else if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
             break;
@@ -517,6 +683,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     if (h_next) *h_next = L->h_abs;
     *n_acc = L->n_acc; *n_rej = L->n_rej; *nfev = L->nfev; *status = st;
     if (n_eval_done) *n_eval_done = ieval;
+    if (stiff_flags) *stiff_flags = L->stiff_flags;
     free(L);
 }
 
@@ -532,7 +699,7 @@ int xsq_oracle_rk_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
                         int max_steps, double* t_final, double* y_final,
                         double* h_next, int32_t* n_acc, int32_t* n_rej,
                         int32_t* nfev, int32_t* status, int32_t* n_eval_done,
-                        int n_threads) {
+                        int n_threads, int nfev_stiff_detect, int32_t* stiff_flags) {
     rhs_fn f = rhs >= 0 ? builtin_rhs(rhs) : user_f;
     if (!f || n > MAXN || T->s >= MAXS) return -1;
     if (max_steps <= 0) max_steps = 2147483647;
@@ -547,7 +714,8 @@ int xsq_oracle_rk_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
                      y_eval ? y_eval + (size_t)i * n * n_eval : 0, h_forced, n_forced,
                      max_steps, t_final + i, y_final + i * n, h_next ? h_next + i : 0,
                      n_acc + i, n_rej + i, nfev + i, status + i,
-                     n_eval_done ? n_eval_done + i : 0);
+                     n_eval_done ? n_eval_done + i : 0, nfev_stiff_detect,
+                     stiff_flags ? stiff_flags + i : 0);
     }
     return 0;
 }

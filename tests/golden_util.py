@@ -23,9 +23,10 @@ class Golden:
 
 
 def case_options(c):
-    """solver options of a golden case (without nfev_stiff_detect)."""
+    """solver options of a golden case; like the reference, stiffness
+    diagnosis defaults to every 5000 evaluations when not given."""
     opts = dict(c.get("options", {}))
-    opts.pop("nfev_stiff_detect", None)
+    opts.setdefault("nfev_stiff_detect", 5000)
     if "atol_vec" in c:
         opts["atol"] = np.array(c["atol_vec"])
     if "sc_params" in opts:

@@ -527,3 +527,54 @@ def test_c_abi_host_buffer_entry_point():
     a.rtol = -1.0
     assert lib.xsq_rk_solve_host(C.byref(a), 0) == -1
     assert b"rtol" in lib.xsq_last_error_detail()
+
+
+# ---- stiffness diagnosis ---------------------
+from test_stiffness_golden import CASES as STIFF_CASES, check_fma_path  # noqa: E402
+
+
+@pytest.mark.parametrize("c", STIFF_CASES, ids=lambda c: c["id"])
+def test_stiffness_diagnosis_vs_reference_golden(c):
+    prm = [c["params"]] if c["params"] else None
+    r = xb.solve_ivp_batched(rhs_for(c["problem"]), c["t_span"], [c["y0"]],
+                             getattr(xb, c["method"]), params=prm,
+                             max_steps=500000, **c["options"])
+    flags = int(r.stiff_flags.cpu()[0])
+    r = to_np(r)
+    assert r["status"][0] == 0
+    check_fma_path(c, r["nfev"][0], r["n_rejected"][0], flags)
+    yg = np.array([float.fromhex(v) for v in c["y_final"]])
+    # same accept/reject sequence: rounding only; a flipped decision moves the
+    # end point by a fraction of the tolerance
+    same = r["n_rejected"][0] == c["nfs"]
+    tol = 1e-4 if same else max(1e-4, 10 * c["options"].get("rtol", 1e-3))
+    atol = np.max(np.atleast_1d(c["options"].get("atol", 1e-6)))
+    err = np.abs(r["y_final"][0] - yg)
+    assert (err <= tol * np.abs(yg) + 10 * atol).all(), (err, tol)
+
+
+def test_stiff_lanes_are_flagged_in_a_mu_sweep():
+    """Per-lane 'this lane is stiff' flags for the Van der Pol mu sweep; the
+    diagnosis never changes the trajectory (same steps with it off)."""
+    N = 64
+    y0, prm = vdp_lanes(N)
+    kw = dict(params=prm, rtol=1e-6, atol=1e-8, max_steps=500000)
+    on = xb.solve_ivp_batched("vanderpol", (0.0, 60.0), y0, xb.Ts5,
+                              nfev_stiff_detect=1000, **kw)
+    off = xb.solve_ivp_batched("vanderpol", (0.0, 60.0), y0, xb.Ts5,
+                               nfev_stiff_detect=0, **kw)
+    flags = on.stiff_flags.cpu().numpy()
+    a, b = to_np(on), to_np(off)
+    assert np.array_equal(a["y_final"], b["y_final"])
+    assert np.array_equal(a["n_accepted"], b["n_accepted"])
+    assert (a["nfev"] >= b["nfev"]).all() and (a["nfev"] > b["nfev"]).any()
+    assert (off.stiff_flags.cpu().numpy() == 0).all()
+    mu = prm[:, 0]
+    assert (flags[mu > 50] & 1).all()          # stiff, real dominant root
+    assert (flags[mu < 1] == 0).all()
+    ref = CO.rk_batch(TABS["Ts5"], "vanderpol", (0.0, 60.0), y0, params=prm,
+                      rtol=1e-6, atol=1e-8, nfev_stiff_detect=1000, n_threads=8)
+    same = a["n_rejected"] == ref["n_rejected"]
+    assert same.mean() >= 0.8
+    assert np.array_equal(a["nfev"][same], ref["nfev"][same])
+    assert np.array_equal(flags[same], ref["stiff_flags"][same])
