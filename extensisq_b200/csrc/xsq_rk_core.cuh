@@ -145,6 +145,7 @@ static __constant__ double c_xsq_e2[14] = {  // ln(2)^k / k!
     0x1.430912f86c787p-13, 0x1.ffcbfc588b0c7p-17, 0x1.62c0223a5c824p-20,
     0x1.b5253d395e7c4p-24, 0x1.e4cf5158b8ecap-28, 0x1.e8cac7351bb25p-32,
     0x1.c3bd650fc2986p-36, 0x1.816193166d0f9p-40};
+static __constant__ double c_xsq_havg[2] = {0.9, 0.1};       // common.py:372
 static __constant__ double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
                                             0x1.8p52};              // rint magic
 
@@ -618,15 +619,22 @@ struct Lane {
     // Stiffness diagnosis state lives in shared memory, not in registers: it is
     // touched once per accepted step, while every register of the lane is
     // needed for the stage vectors (the kernel sits at its register cap).
-    // Countdowns replace the reference's okstp % 40 and okstp % many_steps.
-    // bits: [0:5] steps to the next 40-step check, [6] okstp > 20,
-    // [7:8] probes waiting in the slots, [9:11] STIFF_* flags, [16:31] jflstp.
-    static constexpr unsigned SB_PAST20 = 1u << 6, SB_PEND1 = 1u << 7, SB_PEND2 = 1u << 8,
-                              SB_FLAG_SHIFT = 9, SB_JFL_SHIFT = 16;
+    // The reference's okstp equals n_acc + 1 at the time of the check (the
+    // diagnosis is off for forced step sequences) and jflstp is n_rej minus
+    // its value at the last reset, so rejected attempts touch nothing here:
+    //   hot.cnt        accepted steps until okstp == 20 or okstp % 40 == 39
+    //   hot.next_many  the next okstp with okstp % many_steps == many_steps - 1
+    //   rej_base       n_rej when jflstp was last set to 0
+    //   bits           [7:8] probes waiting in the slots, [9:11] STIFF_* flags
+    static constexpr unsigned SB_PEND1 = 1u << 7, SB_PEND2 = 1u << 8, SB_FLAG_SHIFT = 9;
+    struct alignas(16) StiffHot {
+        double havg;
+        int next_many, cnt;
+    };
     struct StiffState {
-        double havg[XSQ_MAX_BLOCK];
+        StiffHot hot[XSQ_MAX_BLOCK];
+        int rej_base[XSQ_MAX_BLOCK];
         unsigned bits[XSQ_MAX_BLOCK];
-        int many[XSQ_MAX_BLOCK];
     };
     static __device__ __forceinline__ StiffState& stiff_state() {
         __shared__ StiffState s;
@@ -645,11 +653,12 @@ struct Lane {
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
         n_acc = n_rej = n_pre = ieval = 0;
         StiffState& ss = stiff_state();
-        // okstp % 40 == 39 first at step 39; probes of the thread's previous
-        // trajectory may still wait in the slots
-        ss.bits[threadIdx.x] = 38u | (ss.bits[threadIdx.x] & (SB_PEND1 | SB_PEND2));
-        ss.many[threadIdx.x] = P.stiff_many_steps - 2;  // okstp % many == many - 1
-        ss.havg[threadIdx.x] = 0.0;
+        // probes of the thread's previous trajectory may still wait in the slots
+        ss.bits[threadIdx.x] &= SB_PEND1 | SB_PEND2;
+        ss.hot[threadIdx.x].havg = 0.0;
+        ss.hot[threadIdx.x].next_many = P.stiff_many_steps > 1 ? P.stiff_many_steps - 1 : 1;
+        ss.hot[threadIdx.x].cnt = 20;
+        ss.rej_base[threadIdx.x] = 0;
 #pragma unroll
         for (int k = 0; k < NL; ++k)
             f[k] = P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx];
@@ -1070,10 +1079,7 @@ struct Lane {
             step_rejected = true;
             ++n_rej;
             if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
-            if (P.nfev_stiff_detect > 0) {                   // ++jflstp, common.py:284
-                unsigned& sb = stiff_state().bits[threadIdx.x];
-                if (sb < 0xFFFF0000u) sb += 1u << SB_JFL_SHIFT;
-            }
+            // ++jflstp (common.py:284) is ++n_rej, see StiffState
             if (bad) return LANE_OVERFLOW;                   // common.py:286
             if (h_abs < min_step) return LANE_TOO_SMALL;     // common.py:234
             if (n_acc + n_rej >= P.max_steps) return LANE_STEP_BUDGET;
@@ -1112,25 +1118,27 @@ struct Lane {
                                              const double (&y_new)[NL],
                                              double t_new, double h) {
         StiffState& ss = stiff_state();
-        unsigned sbits = ss.bits[threadIdx.x];
-        double havg = ss.havg[threadIdx.x];
-        const int cmany = ss.many[threadIdx.x];
-        const unsigned c40 = sbits & 63u;
-        havg = 0.9 * havg + 0.1 * h;
-        if (c40 == 19u && !(sbits & SB_PAST20)) {            // okstp == 20
-            havg = h;
-            sbits = (sbits & 0xFFFFu) | SB_PAST20;           // jflstp = 0
-        }
+        const double2 hot = *reinterpret_cast<const double2*>(&ss.hot[threadIdx.x]);
+        double havg = c_xsq_havg[0] * hot.x + c_xsq_havg[1] * h;
+        int next_many = __double2loint(hot.y), cnt = __double2hiint(hot.y) - 1;
+        const bool toomch = n_acc + 1 == next_many;
         bool lotsfl = false;
-        if (c40 == 0u) {                                     // okstp % 40 == 39
-            lotsfl = (sbits >> SB_JFL_SHIFT) >= 10u;
-            sbits = (sbits & 0xFFC0u) | 39u;                 // jflstp = 0
-        } else {
-            --sbits;
+        if (cnt == 0) {                       // okstp == 20 or okstp % 40 == 39
+            if (n_acc == 19) {
+                havg = h;
+                cnt = 19;
+            } else {
+                lotsfl = n_rej - ss.rej_base[threadIdx.x] >= 10;
+                cnt = 40;
+            }
+            ss.rej_base[threadIdx.x] = n_rej;                // jflstp = 0
         }
-        const bool toomch = cmany <= 0;
-        ss.many[threadIdx.x] = toomch ? P.stiff_many_steps - 1 : cmany - 1;
-        ss.havg[threadIdx.x] = havg;
+        if (toomch) next_many += P.stiff_many_steps;
+        *reinterpret_cast<double2*>(&ss.hot[threadIdx.x]) =
+            make_double2(havg, __hiloint2double(cnt, next_many));
+        if (!(toomch || lotsfl)) return false;
+        // ---- rare from here ----
+        unsigned sbits = ss.bits[threadIdx.x];
         bool urgent = false;
         if (toomch || lotsfl) {
             using SL = StiffSlot<R>;
@@ -1250,7 +1258,7 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     // anything live across it would be spilled for the whole kernel, hot loop
     // included.  So the lane is parked in local memory by hand for the
     // duration of the (rare) pass and nothing but `live` crosses it.
-    constexpr int kProbeWindow = 1024;
+    constexpr int kProbeWindow = 640;
     int it = 0;
     auto flush = [&](long long cur) {
         if (!__any_sync(full, Lane<Tab, R>::probes_pending())) return;
