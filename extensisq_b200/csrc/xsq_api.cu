@@ -105,12 +105,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters,
         ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-static int dispatch(int method, int rhs, const RkDev& P, cudaStream_t st,
-                    LaunchInfo* info) {
-    if (rhs >= XSQ_RHS_USER_BASE) return user_rk_launch(method, rhs, P, st);
-    int rc = launch_ens_init(rhs, P, st);       // f0 + h_start for all lanes
-    if (rc != XSQ_OK) return rc;
-    if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
+static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
+                         LaunchInfo* info) {
     switch (method) {
         case XSQ_TS5: return launch_Ts5(rhs, P, st, info);
         case XSQ_BS5: return launch_BS5(rhs, P, st, info);
@@ -122,6 +118,20 @@ static int dispatch(int method, int rhs, const RkDev& P, cudaStream_t st,
         case XSQ_CFMR7OSC: return launch_CFMR7osc(rhs, P, st, info);
         default: return XSQ_ERR_UNSUPPORTED;
     }
+}
+
+// init kernel -> persistent kernel -> (stiffness diagnosis on) probe queue kernel
+static int dispatch(int method, int rhs, const RkDev& P, const MethodInfo& mi,
+                    cudaStream_t st, LaunchInfo* info) {
+    if (rhs >= XSQ_RHS_USER_BASE)
+        return user_rk_launch(method, rhs, P, mi.s, mi.stbrad, mi.tanang, st);
+    int rc = launch_ens_init(rhs, P, st);       // f0 + h_start for all lanes
+    if (rc != XSQ_OK) return rc;
+    if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
+    rc = launch_method(method, rhs, P, st, info);
+    if (rc == XSQ_OK && P.stiff_q_cap > 0)
+        rc = launch_stiff_queue(rhs, P, mi.s, mi.stbrad, mi.tanang, st);
+    return rc;
 }
 
 struct RhsInfo { const char* name; int id, n_state, n_param; };
@@ -307,6 +317,9 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     double* slots = nullptr;
     P.stiff_slot = nullptr;
     P.stiff_threads = 0;
+    P.stiff_q = nullptr;
+    P.stiff_q_cap = 0;
+    P.stiff_q_count = (unsigned long long*)(scratch + 8);
     if (P.nfev_stiff_detect > 0 && a->method != XSQ_METHOD_SWAG) {
         int dev = 0, n_sm = 0;
         XSQ_CUDA(cudaGetDevice(&dev));
@@ -318,15 +331,30 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         const size_t want = ((warp_rhs ? N * 32 : N) + 255) & ~(size_t)255;
         if (want < threads) threads = want;
         P.stiff_threads = (long long)threads;
-        cudaError_t es = cudaMallocAsync((void**)&slots,
-                                         2 * (5 + 4 * nl + npl) * threads * sizeof(double), st);
+        // ... and, for thread-per-system kernels, in a queue that a separate
+        // kernel works off afterwards: up to 48 records per trajectory, at most
+        // a quarter of the free memory.  When it is full the slots take over.
+        const size_t rec = 5 + 4 * nl + npl;
+        size_t qcap = 0;
+        if (!warp_rhs) {
+            size_t free_b = 0, total_b = 0;
+            XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            qcap = N * 48;
+            const size_t fit = free_b / 4 / (rec * sizeof(double));
+            if (fit < qcap) qcap = fit;
+            if (const char* e = getenv("XSQ_STIFF_QUEUE_RECORDS")) qcap = (size_t)atoll(e);
+        }
+        cudaError_t es = cudaMallocAsync(
+            (void**)&slots, (2 * threads + qcap) * rec * sizeof(double), st);
         if (es != cudaSuccess) {
             cudaFreeAsync(scratch, st);
             return cuda_fail(es, "cudaMallocAsync");
         }
         P.stiff_slot = slots;
+        P.stiff_q = slots + 2 * threads * rec;
+        P.stiff_q_cap = (long long)qcap;
     }
-    rc = dispatch(a->method, a->rhs, P, st, info);
+    rc = dispatch(a->method, a->rhs, P, mi, st, info);
     if (slots) cudaFreeAsync(slots, st);
     cudaError_t e = cudaFreeAsync(scratch, st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");

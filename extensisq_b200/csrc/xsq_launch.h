@@ -24,6 +24,8 @@ XSQ_DECL_LAUNCH(CFMR7osc)
 
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st);
 int launch_ens_init(int rhs, const RkDev& P, cudaStream_t st);
+int launch_stiff_queue(int rhs, const RkDev& P, int cost, double stbrad, double tanang,
+                       cudaStream_t st);
 
 void count_launch();
 

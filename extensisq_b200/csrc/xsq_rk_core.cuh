@@ -89,6 +89,11 @@ struct RkDev {
     // deferred probes: 2 slots per resident thread, SoA [slot][field][thread]
     double* stiff_slot;
     long long stiff_threads;      // thread stride of stiff_slot (>= grid size)
+    // probe queue: records of StiffSlot<R>::DOUBLES doubles, appended by the
+    // persistent kernel, worked off by stiff_queue after it
+    double* stiff_q;
+    long long stiff_q_cap;                  // records; 0 = no queue
+    unsigned long long* stiff_q_count;      // may run past stiff_q_cap
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -429,31 +434,61 @@ __global__ void __launch_bounds__(BLOCK) ens_init(const RkDev P) {
 // are handed to it, the hot loop's register allocation is untouched.
 enum : int { STIFF_REAL = 1, STIFF_COMPLEX = 2, STIFF_OSCILLATORY = 4 };
 
+// <a, b> = sum (a/wt)(b/wt) over one system.  Every vector the probe makes is
+// divided by wt ONCE (the quotient is the same number wherever the reference
+// recomputes it), so the inner products are plain FMAs: 4x fewer divisions
+// and a much smaller probe -- its size matters, the hot loop of a 13-stage
+// pair already fills the instruction cache.
 template <class R>
-__device__ __forceinline__ double wdot(const double (&a)[R::NL], const double (&b)[R::NL],
-                                       const double (&wt)[R::NL]) {
+__device__ __forceinline__ double wdotq(const double (&aq)[R::NL], const double (&bq)[R::NL]) {
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < R::NL; ++c) s = fma(a[c] / wt[c], b[c] / wt[c], s);
+    for (int c = 0; c < R::NL; ++c) s = fma(aq[c], bq[c], s);
     return sys_sum<R::WARP>(s);
 }
 
-// stiff_d: z ~ havg * J * v by a difference of f; returns <z, z>
+// everything stiff_d needs that does not change during one probe
 template <class R>
-__device__ double stiff_jac_times(const double (&v)[R::NL], double havg, double x,
-                                  const double (&y)[R::NL], const double (&fxy)[R::NL],
-                                  const double (&wt)[R::NL], const double (&prm)[R::NPL],
-                                  double scale, double vdotv, double (&z)[R::NL], int& nfev) {
-    const double temp1 = scale / sqrt(vdotv);
+struct StiffCtx {
+    double havg, x, scale;
+    double y[R::NL], fxy[R::NL], wt[R::NL], prm[R::NPL];
+};
+
+// stiff_d: z ~ havg * J * v by a difference of f; zq = z / wt; returns <z, z>.
+// Out of line: called three times per iteration, and it holds the only copy
+// of the right-hand side in the probe.
+template <class R>
+__device__ __forceinline__ double stiff_jac_times_impl(const StiffCtx<R>& C,
+                                                       const double (&v)[R::NL], double vdotv,
+                                                       double (&z)[R::NL], double (&zq)[R::NL]) {
+    const double temp1 = C.scale / sqrt(vdotv);
     double yp[R::NL];
 #pragma unroll
-    for (int c = 0; c < R::NL; ++c) yp[c] = fma(temp1, v[c], y[c]);
-    R::f(x, yp, prm, z);
-    ++nfev;
-    const double q = havg / temp1;
+    for (int c = 0; c < R::NL; ++c) yp[c] = fma(temp1, v[c], C.y[c]);
+    R::f(C.x, yp, C.prm, z);
+    const double q = C.havg / temp1;
 #pragma unroll
-    for (int c = 0; c < R::NL; ++c) z[c] = q * (z[c] - fxy[c]);
-    return wdot<R>(z, z, wt);
+    for (int c = 0; c < R::NL; ++c) {
+        z[c] = q * (z[c] - C.fxy[c]);
+        zq[c] = z[c] / C.wt[c];
+    }
+    return wdotq<R>(zq, zq);
+}
+
+template <class R>
+__device__ __noinline__ double stiff_jac_times_ool(const StiffCtx<R>& C, const double (&v)[R::NL],
+                                                   double vdotv, double (&z)[R::NL],
+                                                   double (&zq)[R::NL]) {
+    return stiff_jac_times_impl<R>(C, v, vdotv, z, zq);
+}
+
+// SMALL: inside the persistent kernel, where code size is what matters
+template <class R, bool SMALL>
+__device__ __forceinline__ double stiff_jac_times(const StiffCtx<R>& C, const double (&v)[R::NL],
+                                                  double vdotv, double (&z)[R::NL],
+                                                  double (&zq)[R::NL]) {
+    if constexpr (SMALL) return stiff_jac_times_ool<R>(C, v, vdotv, z, zq);
+    else return stiff_jac_times_impl<R>(C, v, vdotv, z, zq);
 }
 
 // stiff_b
@@ -493,24 +528,28 @@ struct StiffSlot {
     static constexpr int DOUBLES = HEAD + 4 * R::NL + R::NPL;
 };
 
-template <class R>
-__device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride, double xend,
+template <class R, bool SMALL>
+__device__ __forceinline__ int stiff_probe_impl(const double* slot, long long stride, double xend,
                                             int maxfcn, int cost, double stbrad,
                                             double tanang) {
     constexpr int NL = R::NL;
-    const double x = slot[0], hnow = slot[stride], havg = slot[2 * stride];
+    StiffCtx<R> C;
+    C.x = slot[0];
+    C.havg = slot[2 * stride];
+    const double x = C.x, hnow = slot[stride], havg = C.havg;
     const bool lotsfl = slot[3 * stride] != 0.0;
     const double* q = slot + StiffSlot<R>::HEAD * stride;
-    double y[NL], fxy[NL], wt[NL], v0[NL], v1[NL], v2[NL], v3[NL], prm[R::NPL];
+    double v0[NL], v1[NL], v2[NL], v3[NL];        // the Krylov vectors ...
+    double v0q[NL], v1q[NL], v2q[NL], v3q[NL];    // ... and each divided by wt
 #pragma unroll
     for (int c = 0; c < NL; ++c) {
-        y[c] = q[c * stride];
-        fxy[c] = q[(2 * NL + c) * stride];
+        C.y[c] = q[c * stride];
+        C.fxy[c] = q[(2 * NL + c) * stride];
         v0[c] = q[(3 * NL + c) * stride];
-        wt[c] = fmax(0.5 * (fabs(y[c]) + fabs(q[(NL + c) * stride])), XSQ_SQRT_TINY);
+        C.wt[c] = fmax(0.5 * (fabs(C.y[c]) + fabs(q[(NL + c) * stride])), XSQ_SQRT_TINY);
     }
 #pragma unroll
-    for (int c = 0; c < R::NPL; ++c) prm[c] = q[(4 * NL + c) * stride];
+    for (int c = 0; c < R::NPL; ++c) C.prm[c] = q[(4 * NL + c) * stride];
     int nfev = 0;
     const double epsneg = 0x1.0p-53;
     int stif = 0, rootre = -1;          // stif: 1 / 0 / -1 (unsure)
@@ -519,30 +558,43 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
     do {
         if (fabs(hnow / havg) > 5 || fabs(hnow / havg) < 0.2) break;
         if (cost * fabs((xend - x) / havg) <= maxfcn) break;
-        double ynrm = sqrt(wdot<R>(y, y, wt));
-        const double sqrrmc = sqrt(epsneg);
-        double scale = ynrm * sqrrmc;
-        if (scale == 0.0) {
-            ynrm = sqrt(wdot<R>(v0, v0, wt));
-            scale = ynrm * sqrrmc;
-            if (scale == 0.0) { stif = -1; break; }
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            v1q[c] = C.y[c] / C.wt[c];              // scratch: y / wt
+            v0q[c] = v0[c] / C.wt[c];
         }
-        double v0v0 = wdot<R>(v0, v0, wt);
+        double ynrm = sqrt(wdotq<R>(v1q, v1q));
+        const double sqrrmc = sqrt(epsneg);
+        C.scale = ynrm * sqrrmc;
+        if (C.scale == 0.0) {
+            ynrm = sqrt(wdotq<R>(v0q, v0q));
+            C.scale = ynrm * sqrrmc;
+            if (C.scale == 0.0) { stif = -1; break; }
+        }
+        double v0v0 = wdotq<R>(v0q, v0q);
         if (v0v0 == 0.0) {
 #pragma unroll
-            for (int c = 0; c < NL; ++c) v0[c] = 1.0;
-            v0v0 = wdot<R>(v0, v0, wt);
+            for (int c = 0; c < NL; ++c) {
+                v0[c] = 1.0;
+                v0q[c] = 1.0 / C.wt[c];
+            }
+            v0v0 = wdotq<R>(v0q, v0q);
         }
         const double v0nrm = sqrt(v0v0);
 #pragma unroll
-        for (int c = 0; c < NL; ++c) v0[c] /= v0nrm;
+        for (int c = 0; c < NL; ++c) {
+            v0[c] /= v0nrm;
+            v0q[c] = v0[c] / C.wt[c];
+        }
         v0v0 = 1.0;
         double rold = 0.0;
         bool converged = false, early = false;
+#pragma unroll 1
         for (int ntry = 0; ntry < 8; ++ntry) {
-            const double v1v1 = stiff_jac_times<R>(v0, havg, x, y, fxy, wt, prm, scale, v0v0, v1, nfev);
+            const double v1v1 = stiff_jac_times<R, SMALL>(C, v0, v0v0, v1, v1q);
+            ++nfev;
             if (sqrt(v1v1) > 1.0e10 * sqrt(v0v0)) { stif = -1; rootre = -1; early = true; break; }
-            const double v0v1 = wdot<R>(v0, v1, wt);
+            const double v0v1 = wdotq<R>(v0q, v1q);
             if (ntry == 0) {
                 rold = v0v1 / v0v0;
                 if (fabs(rold) < cbrt(epsneg)) { stif = 0; rootre = -1; early = true; break; }
@@ -550,15 +602,17 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
                 if (stiff_dominant_real(v1v1, v0v1, v0v0, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
                 rootre = 0;
             }
-            const double v2v2 = stiff_jac_times<R>(v1, havg, x, y, fxy, wt, prm, scale, v1v1, v2, nfev);
-            const double v0v2 = wdot<R>(v0, v2, wt), v1v2 = wdot<R>(v1, v2, wt);
+            const double v2v2 = stiff_jac_times<R, SMALL>(C, v1, v1v1, v2, v2q);
+            ++nfev;
+            const double v0v2 = wdotq<R>(v0q, v2q), v1v2 = wdotq<R>(v1q, v2q);
             if (stiff_dominant_real(v2v2, v1v2, v1v1, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
             rootre = 0;
             const double det1 = v0v0 * v1v1 - v0v1 * v0v1;
             const double alpha1 = (-v0v0 * v1v2 + v0v1 * v0v2) / det1;
             const double beta1 = (v0v1 * v1v2 - v1v1 * v0v2) / det1;
-            const double v3v3 = stiff_jac_times<R>(v2, havg, x, y, fxy, wt, prm, scale, v2v2, v3, nfev);
-            const double v1v3 = wdot<R>(v1, v3, wt), v2v3 = wdot<R>(v2, v3, wt);
+            const double v3v3 = stiff_jac_times<R, SMALL>(C, v2, v2v2, v3, v3q);
+            ++nfev;
+            const double v1v3 = wdotq<R>(v1q, v3q), v2v3 = wdotq<R>(v2q, v3q);
             if (stiff_dominant_real(v3v3, v2v3, v2v2, rold, rho, root1, root2)) { rootre = 1; converged = true; break; }
             const double det2 = v1v1 * v2v2 - v1v2 * v1v2;
             const double alpha2 = (-v1v1 * v2v3 + v1v2 * v1v3) / det2;
@@ -576,7 +630,10 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
             }
             const double v3nrm = sqrt(v3v3);
 #pragma unroll
-            for (int c = 0; c < NL; ++c) v0[c] = v3[c] / v3nrm;
+            for (int c = 0; c < NL; ++c) {
+                v0[c] = v3[c] / v3nrm;
+                v0q[c] = v0[c] / C.wt[c];
+            }
             v0v0 = 1.0;
         }
         if (early) break;
@@ -599,6 +656,14 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
     if (stif < 0) flags = (rootre == 0 && lotsfl) ? STIFF_OSCILLATORY : 0;
     else if (stif == 1 && rootre >= 0) flags = rootre ? STIFF_REAL : STIFF_COMPLEX;
     return flags | (nfev << 8);
+}
+
+// the copy inside the persistent kernel: out of line (see rk_persistent_body)
+template <class R>
+__device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride, double xend,
+                                            int maxfcn, int cost, double stbrad,
+                                            double tanang) {
+    return stiff_probe_impl<R, true>(slot, stride, xend, maxfcn, cost, stbrad, tanang);
 }
 
 // ---- one trajectory ---------------------------------------------------------
@@ -1138,33 +1203,42 @@ struct Lane {
             make_double2(havg, __hiloint2double(cnt, next_many));
         if (!(toomch || lotsfl)) return false;
         // ---- rare from here ----
-        unsigned sbits = ss.bits[threadIdx.x];
+        // Where the probe's inputs go: a record of the probe queue, worked off
+        // by stiff_queue after this kernel (thread-per-system policies, while
+        // the queue has room), else one of the thread's two slots.
+        using SL = StiffSlot<R>;
+        double* s = nullptr;
+        long long stride = 1;
+        if (!R::WARP && P.stiff_q_cap > 0) {
+            const unsigned long long qi = atomicAdd(P.stiff_q_count, 1ULL);
+            if (qi < (unsigned long long)P.stiff_q_cap) s = P.stiff_q + qi * SL::DOUBLES;
+        }
         bool urgent = false;
-        if (toomch || lotsfl) {
-            using SL = StiffSlot<R>;
-            const long long stride = P.stiff_threads;
+        if (s == nullptr) {
+            unsigned sbits = ss.bits[threadIdx.x];
+            stride = P.stiff_threads;
             const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
             const int islot = (sbits & SB_PEND1) ? 1 : 0;
-            double* s = P.stiff_slot + (long long)islot * SL::DOUBLES * stride + gtid;
-            s[0] = t_new;
-            s[stride] = h;
-            s[2 * stride] = havg;
-            s[3 * stride] = lotsfl ? 1.0 : 0.0;
-            s[4 * stride] = __longlong_as_double(sys);
-            s += SL::HEAD * stride;
-#pragma unroll
-            for (int c = 0; c < NL; ++c) {
-                s[c * stride] = y_new[c];
-                s[(NL + c) * stride] = y[c];
-                s[(2 * NL + c) * stride] = K[S][c];
-                s[(3 * NL + c) * stride] = errv[c];
-            }
-#pragma unroll
-            for (int c = 0; c < R::NPL; ++c) s[(4 * NL + c) * stride] = prm[c];
+            s = P.stiff_slot + (long long)islot * SL::DOUBLES * stride + gtid;
             sbits += SB_PEND1;                               // 0 -> 1 -> 2
             urgent = (sbits & SB_PEND2) != 0u;
+            ss.bits[threadIdx.x] = sbits;
         }
-        ss.bits[threadIdx.x] = sbits;
+        s[0] = t_new;
+        s[stride] = h;
+        s[2 * stride] = havg;
+        s[3 * stride] = lotsfl ? 1.0 : 0.0;
+        s[4 * stride] = __longlong_as_double(sys);
+        s += SL::HEAD * stride;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            s[c * stride] = y_new[c];
+            s[(NL + c) * stride] = y[c];
+            s[(2 * NL + c) * stride] = K[S][c];
+            s[(3 * NL + c) * stride] = errv[c];
+        }
+#pragma unroll
+        for (int c = 0; c < R::NPL; ++c) s[(4 * NL + c) * stride] = prm[c];
         return urgent;
     }
 
@@ -1342,6 +1416,34 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         __syncwarp(full);
     }
     if (P.nfev_stiff_detect > 0) flush(-1);      // probes of stored trajectories
+}
+
+// Works off the probe queue: one thread per record, grid-stride (the record
+// count is only known on the device).  A probe adds to nfev and to the flags of
+// the trajectory that queued it; several records may belong to one trajectory.
+template <class R>
+__device__ __forceinline__ void stiff_queue_body(const RkDev& P, int cost, double stbrad,
+                                                 double tanang) {
+    if constexpr (!R::WARP) {
+        unsigned long long n = *P.stiff_q_count;
+        if (n > (unsigned long long)P.stiff_q_cap) n = (unsigned long long)P.stiff_q_cap;
+        const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += step) {
+            const double* rec = P.stiff_q + i * StiffSlot<R>::DOUBLES;
+            const int r = stiff_probe_impl<R, false>(rec, 1, P.t_bound, P.nfev_stiff_detect,
+                                                     cost, stbrad, tanang);
+            const long long owner = __double_as_longlong(rec[4]);
+            if (r >> 8) atomicAdd(&P.nfev[owner], r >> 8);
+            if ((r & 7) && P.stiff_flags) atomicOr(&P.stiff_flags[owner], r & 7);
+        }
+    }
+}
+
+template <class R>
+__global__ void __launch_bounds__(128, 6) stiff_queue(const RkDev P, int cost, double stbrad,
+                                                   double tanang) {
+    stiff_queue_body<R>(P, cost, stbrad, tanang);
 }
 
 template <class Tab, class R, int BLOCK, int MINB>

@@ -53,6 +53,29 @@ int launch_ens_init(int rhs, const RkDev& P, cudaStream_t st) {
     }
 }
 
+template <class R>
+static int launch_queue_one(const RkDev& P, int cost, double stbrad, double tanang,
+                            cudaStream_t st) {
+    int dev = 0, n_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return XSQ_ERR_CUDA;
+    stiff_queue<R><<<(unsigned)(n_sm * 12), 128, 0, st>>>(P, cost, stbrad, tanang);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+}
+
+// The stiffness probes the persistent kernel queued (xsq_rk_core.cuh, Lane::diagnose).
+int launch_stiff_queue(int rhs, const RkDev& P, int cost, double stbrad, double tanang,
+                       cudaStream_t st) {
+    switch (rhs) {
+        case XSQ_RHS_LORENZ63: return launch_queue_one<rhs::Lorenz63>(P, cost, stbrad, tanang, st);
+        case XSQ_RHS_VANDERPOL: return launch_queue_one<rhs::VanDerPol>(P, cost, stbrad, tanang, st);
+        case XSQ_RHS_ARENSTORF: return launch_queue_one<rhs::Arenstorf>(P, cost, stbrad, tanang, st);
+        default: return XSQ_OK;          // warp-per-system policies do not queue
+    }
+}
+
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st) {
     switch (rhs) {
         case XSQ_RHS_LORENZ63: return launch_swag_one<rhs::Lorenz63>(P, st);

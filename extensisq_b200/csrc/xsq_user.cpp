@@ -61,6 +61,7 @@ struct Compiled {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
     CUfunction init_fn = nullptr;
+    CUfunction probe_fn = nullptr;   // null for SWAG modules
     int occ = 0;
 };
 std::map<std::string, Compiled> g_cache;
@@ -337,6 +338,9 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
         cr = g_api.ModuleGetFunction(&out->fn, out->mod, "xsq_user_kernel");
     if (cr == CUDA_SUCCESS)
         cr = g_api.ModuleGetFunction(&out->init_fn, out->mod, "xsq_user_init");
+    if (cr == CUDA_SUCCESS &&
+        g_api.ModuleGetFunction(&out->probe_fn, out->mod, "xsq_user_probe") != CUDA_SUCCESS)
+        out->probe_fn = nullptr;
     if (cr == CUDA_SUCCESS)
         cr = g_api.OccupancyMaxActiveBlocks(&out->occ, out->fn, 128, 0);
     if (cr != CUDA_SUCCESS) {
@@ -411,7 +415,14 @@ int user_build_source(int method, int rhs, std::string* src, std::string* key) {
                   "extern \"C\" __global__ void __launch_bounds__(128)\n"
                   "xsq_user_init(const xsq::RkDev P) { xsq::ens_init_body<xsq::rhs::%s>(P); }\n",
                   rhsname.c_str());
-    *src = body + buf + buf2;
+    char buf3[320] = "";
+    if (!swag)
+        std::snprintf(buf3, sizeof buf3,
+                      "extern \"C\" __global__ void __launch_bounds__(128)\n"
+                      "xsq_user_probe(const xsq::RkDev P, int cost, double stbrad, double tanang) {\n"
+                      "    xsq::stiff_queue_body<xsq::rhs::%s>(P, cost, stbrad, tanang);\n}\n",
+                      rhsname.c_str());
+    *src = body + buf + buf2 + buf3;
     return XSQ_OK;
 }
 
@@ -435,7 +446,8 @@ bool user_rhs_shape(int rhs, int* n_state, int* n_param) {
     return true;
 }
 
-int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
+int user_rk_launch(int method, int rhs, const RkDev& P, int cost, double stbrad,
+                   double tanang, cudaStream_t st) {
     std::lock_guard<std::mutex> g(g_mu);
     std::string src, key;
     int rc = user_build_source(method, rhs, &src, &key);
@@ -479,6 +491,13 @@ int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st) {
         g_api.CuGetErrorString(cr, &es);
         set_detail(std::string("cuLaunchKernel: ") + (es ? es : "?"));
         return XSQ_ERR_CUDA;
+    }
+    if (P.stiff_q_cap > 0 && c.probe_fn) {   // the queued stiffness probes
+        void* pargs[] = {&Pc, &cost, &stbrad, &tanang};
+        CUresult cp = g_api.LaunchKernel(c.probe_fn, (unsigned)(n_sm * 8), 1, 1, 128, 1, 1, 0,
+                                         (CUstream)st, pargs, nullptr);
+        count_launch();
+        if (cp != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_probe) failed"); return XSQ_ERR_CUDA; }
     }
     return XSQ_OK;
 }

@@ -18,7 +18,8 @@ void count_launch();
 
 bool user_tableau_info(MethodInfo* mi);
 bool user_rhs_shape(int rhs, int* n_state, int* n_param);
-int user_rk_launch(int method, int rhs, const RkDev& P, cudaStream_t st);
+int user_rk_launch(int method, int rhs, const RkDev& P, int cost, double stbrad,
+                   double tanang, cudaStream_t st);
 // user PDE for SSV2stab: CUfunctions (as void*) of the eval / stage / final kernels
 int user_pde_kernels(int pde, void* fn[3], int* n_param);
 int user_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** args,

@@ -578,3 +578,30 @@ def test_stiff_lanes_are_flagged_in_a_mu_sweep():
     assert same.mean() >= 0.8
     assert np.array_equal(a["nfev"][same], ref["nfev"][same])
     assert np.array_equal(flags[same], ref["stiff_flags"][same])
+
+
+@pytest.mark.parametrize("method", ["Ts5", "Pr8"])
+def test_stiffness_probe_queue_and_slots_agree(method, monkeypatch):
+    """The probes run either from the queue (separate kernel) or, when it is
+    full, from the per-thread slots inside the persistent kernel: same nfev,
+    same flags, whatever the split."""
+    N = 4096
+    y0, prm = vdp_lanes(N)
+    kw = dict(params=prm, rtol=1e-6, atol=1e-8, max_steps=500000, nfev_stiff_detect=600)
+    out = []
+    for records in (None, "0", "1000"):
+        if records is None:
+            monkeypatch.delenv("XSQ_STIFF_QUEUE_RECORDS", raising=False)
+        else:
+            monkeypatch.setenv("XSQ_STIFF_QUEUE_RECORDS", records)
+        r = xb.solve_ivp_batched("vanderpol", (0.0, 30.0), y0, getattr(xb, method), **kw)
+        out.append((to_np(r), r.stiff_flags.cpu().numpy()))
+    off = to_np(xb.solve_ivp_batched("vanderpol", (0.0, 30.0), y0, getattr(xb, method),
+                                     **{**kw, "nfev_stiff_detect": 0}))
+    (a, fa), (b, fb), (c, fc) = out
+    assert (a["nfev"] > off["nfev"]).mean() > 0.5          # the probes did run
+    assert fa.any()
+    for o, f in ((b, fb), (c, fc)):
+        assert np.array_equal(a["nfev"], o["nfev"])
+        assert np.array_equal(fa, f)
+        assert np.array_equal(a["y_final"], o["y_final"])
