@@ -377,16 +377,20 @@ def main():
                 "unit": "TFLOP/s", "frac": achieved / peak.value,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at
                 # this size from the committed capture profiles/r01_ncu_full_
-                # rk_persistent_Ts5_lorenz_1250k_T100.txt (69.9 MB + 32.4 MB)
-                "traffic": 102.2e6 if (args.method == "Ts5" and N == LANES_PER_GPU
-                                       and args.t_end == T_END) else None,
+                # rk_persistent_Ts5_lorenz_1250k_T100.txt: 0.18 GB + 2.48 GB with
+                # the stiffness diagnosis on (the 2.4 GB are the probe-queue
+                # records, 17.5 M x 160 B); 69.9 MB + 32.4 MB with it off
+                "traffic": (None if not (args.method == "Ts5" and N == LANES_PER_GPU
+                                         and args.t_end == T_END)
+                            else 2.662e9 if args.stiff > 0 else 102.2e6),
                 "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
                 "kernel": f"rk_persistent<{args.method}, Lorenz63>",
                 "flops_per_attempted_step": att_f,
                 "peak_source": "xsq_fp64_peak: dependent-chain DFMA microbenchmark "
                                "measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry); "
                                "the kernel keeps state in registers, HBM traffic is ~100 B per "
-                               "trajectory, so the bound is the fp64 pipe, not HBM",
+                               "trajectory plus 160 B per queued stiffness probe (<1% of HBM "
+                               "bandwidth), so the bound is the fp64 pipe, not HBM",
                 "hbm_peak_gbs_measured": hbm},
             "wall_s_timed_region": t_wall,
             "kernel_ms_each_step": kern_ms,

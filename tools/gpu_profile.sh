@@ -10,3 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
 ncu --set full --clock-control none --import-source on -k regex:rk_persistent -s 3 -c 1 \
     -f -o gpurun_out/prof_${TAG} $BENCH > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out
+# the probe-queue kernel of the same command (stiffness diagnosis on by default)
+ncu --set full --clock-control none --import-source on -k regex:stiff_queue -s 3 -c 1 \
+    -f -o gpurun_out/prof_${TAG}_queue $BENCH > gpurun_out/ncu_full_${TAG}_queue.log 2>&1
