@@ -31,6 +31,15 @@ def mass_spring_damper(t, y):  # reference docs/Demo_own_RK.ipynb
     return np.array([y[1], 1. - (y[0] + y[1] / 2)])
 
 
+def detest_f2(t, y):          # reference docs/Cash_Karp.ipynb (DETEST F2)
+    return np.array([(55 - 1.5 * y[0]) if (t % 2 >= 1.) else
+                     (55 - 0.5 * y[0])])
+
+
+def square_forced(t, y):      # oscillator driven by a square wave (non-smooth)
+    return np.array([y[1], -y[0] + (1.0 if sin(3.0 * t) >= 0.0 else -1.0)])
+
+
 def linear(lam):
     return lambda t, y: np.array([lam * y[0], lam * y[1]])
 
@@ -46,7 +55,8 @@ def make_fun(problem, params):
         return linear(params[0])
     return {"rational": rational, "duffing": duffing,
             "forced_osc": forced_osc, "detest_b3": detest_b3,
-            "mass_spring_damper": mass_spring_damper}[problem]
+            "mass_spring_damper": mass_spring_damper,
+            "detest_f2": detest_f2, "square_forced": square_forced}[problem]
 
 
 # CUDA device-function sources for xsq_rhs_register_source (entry name "rhs";
@@ -77,6 +87,17 @@ __device__ void rhs(double t, const double* y, const double* p, double* dy) {
 __device__ void rhs(double t, const double* y, const double* p, double* dy) {
     dy[0] = y[1];
     dy[1] = 1. - (y[0] + y[1] / 2);
+}"""),
+    "detest_f2": (1, 0, r"""
+__device__ void rhs(double t, const double* y, const double* p, double* dy) {
+    double r = fmod(t, 2.0);               // Python's t % 2: sign of the divisor
+    if (r < 0) r += 2.0;
+    dy[0] = (r >= 1.) ? (55 - 1.5 * y[0]) : (55 - 0.5 * y[0]);
+}"""),
+    "square_forced": (2, 0, r"""
+__device__ void rhs(double t, const double* y, const double* p, double* dy) {
+    dy[0] = y[1];
+    dy[1] = -y[0] + (sin(3.0 * t) >= 0.0 ? 1.0 : -1.0);
 }"""),
     "linear": (2, 1, r"""
 __device__ void rhs(double t, const double* y, const double* p, double* dy) {

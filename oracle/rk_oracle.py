@@ -70,8 +70,12 @@ class Tableau:
         self.sc_params = d["sc_params"]
         self.stbrad = d.get("stbrad")
         self.tanang = d.get("tanang")
+        for k in ("max_factor", "min_factor", "safety"):      # CKdisc
+            if k in d:
+                setattr(self, k, float(d[k]))
         for k in ("A", "B", "C", "E", "P", "E_pre", "B_scale_pre", "C_extra",
-                  "A_extra", "Plow", "Pbest"):
+                  "A_extra", "Plow", "Pbest", "B_assess", "E_assess",
+                  "C_fallback", "B_fallback", "E_fallback"):
             if k in d:
                 setattr(self, k, _unhex(d[k]))
         if hasattr(self, "A_extra"):
@@ -79,14 +83,21 @@ class Tableau:
             # rows, bogacki.py:148-160); keep that memory order so BLAS takes
             # the same dgemv path and the oracle stays bit-identical
             self.A_extra = np.asfortranarray(self.A_extra)
-        self.variant = {"BS5": "bs5", "CFMR7osc": "cfmr"}.get(self.name,
-                                                              "generic")
+        self.variant = {"BS5": "bs5", "CFMR7osc": "cfmr",
+                        "CKdisc": "ckdisc"}.get(self.name, "generic")
 
 
 def load_tableaux(path=_TABLEAUX_JSON):
     with open(path) as fh:
         raw = json.load(fh)["tableaux"]
     return {k: Tableau(v) for k, v in raw.items()}
+
+
+def load_ckdisc(path=_TABLEAUX_JSON):
+    """CKdisc's coefficient set (cash.py:184-236); not a RungeKutta._step_impl
+    method, so it is kept apart from load_tableaux()."""
+    with open(path) as fh:
+        return Tableau(json.load(fh)["ckdisc"])
 
 
 # --------------------------------------------------------------------------
@@ -650,12 +661,121 @@ def rk_step(st, forced_h=None):
     return True, None
 
 
+def _ck_sol_err_tol(st, h, B, E, i=6):             # cash.py:394-404
+    sol = h * (st.K[:i, :].T @ B[:i]) + st.y
+    err = h * (st.K[:i, :].T @ E[:i])
+    tol = calculate_scale(st.atol, st.rtol, st.y, sol)
+    return sol, err, tol
+
+
+def ckdisc_step(st):
+    """CKdisc._step_impl, cash.py:245-388: the Cash-Karp variable order
+    (5, 3, 2) step.  Convergence is assessed after stages 1 and 3; when the
+    fifth order result is not accepted, embedded third / second order
+    solutions over a FRACTION of the step (c = 3/5, 1/5) are tried before the
+    step is repeated."""
+    tab = st.tab
+    t, y = st.t, st.y
+    if not hasattr(st, "twiddle"):                 # cash.py:241-243
+        st.twiddle = [1.5, 1.1]
+        st.quit = [100., 100.]
+    twiddle, quit = st.twiddle, st.quit
+    h_abs, min_step = _reassess_stepsize(st)
+    order_accepted = 0
+    step_rejected = False
+    while not order_accepted:
+        if h_abs < min_step:
+            return False, TOO_SMALL_STEP
+        h = h_abs * st.direction
+        st.K[0] = st.f
+        _rk_stage(st, h, 1)
+        _, err_a, tol = _ck_sol_err_tol(st, h, tab.B_assess[0],
+                                        tab.E_assess[0], 2)
+        E1 = norm(err_a / tol) ** (1 / 2)
+        esttol = E1 / quit[0]
+        if E1 < twiddle[0] * quit[0]:
+            _rk_stage(st, h, 2)
+            _rk_stage(st, h, 3)
+            _, err_a, tol = _ck_sol_err_tol(st, h, tab.B_assess[1],
+                                            tab.E_assess[1], 4)
+            E2 = norm(err_a / tol) ** (1 / 3)
+            esttol = E2 / quit[1]
+            if E2 < twiddle[1] * quit[1]:
+                _rk_stage(st, h, 4)
+                _rk_stage(st, h, 5)
+                y_new, err, tol = _ck_sol_err_tol(st, h, tab.B, tab.E)
+                E4 = norm(err / tol) ** (1 / 5)
+                E4 = E4 or 1e-160
+                esttol = E4
+                if E4 < 1:
+                    order_accepted = 4
+                    factor = min(tab.max_factor, tab.safety / E4)
+                    if step_rejected:
+                        factor = min(1.0, factor)
+                    h_abs *= factor
+                    q = [E1 / E4, E2 / E4]
+                    for j in (0, 1):
+                        if q[j] > quit[j]:
+                            q[j] = min(q[j], 10 * quit[j])
+                        else:
+                            q[j] = max(q[j], 2 / 3 * quit[j])
+                        quit[j] = max(1., min(10000., q[j]))
+                    break
+                if np.isnan(E4) or np.isinf(E4):
+                    return False, OVERFLOW
+                e = [E1, E2]
+                for i in (0, 1):
+                    EQ = e[i] / quit[i]
+                    if EQ < twiddle[i]:
+                        twiddle[i] = max(1.1, EQ)
+                if E2 < 1:
+                    y_new, err, tol = _ck_sol_err_tol(
+                        st, h, tab.B_fallback[1], tab.E_fallback[1], 4)
+                    if norm(err / tol) < 1:
+                        order_accepted = 2
+                        h_abs *= tab.C_fallback[1]
+                        h = h_abs * st.direction
+                        break
+            if E1 < 1:
+                y_new, err, tol = _ck_sol_err_tol(
+                    st, h, tab.B_fallback[0], tab.E_fallback[0], 2)
+                if norm(err / tol) < 1:
+                    order_accepted = 1
+                    h_abs *= tab.C_fallback[0]
+                    h = h_abs * st.direction
+                    break
+                else:
+                    step_rejected = True
+                    h_abs *= tab.C_fallback[0]
+                    st.n_rejected += 1
+                    continue
+        step_rejected = True
+        h_abs *= max(tab.min_factor, tab.safety / esttol)
+        st.n_rejected += 1
+        continue
+    t_new = t + h
+    f_new = st.fun(t_new, y_new)
+    st.K[-1, :] = f_new
+    st.order_accepted = order_accepted
+    st.h_previous = h
+    st.y_old = y
+    st.h_abs = h_abs
+    st.f = f_new
+    st.t_old = t
+    st.t = t_new
+    st.y = y_new
+    st.n_accepted += 1
+    return True, None
+
+
 def dense_eval(st, ts):
     """dense_output()(ts) over the last accepted step.
-    common.py:358-368; bogacki.py:348-393."""
+    common.py:358-368; bogacki.py:348-393; cash.py:406-416."""
     tab = st.tab
     if st.t == st.t_old:           # scipy base.py:224-226 ConstantDenseOutput
         return np.repeat(st.y[:, None], np.size(ts), axis=1)
+    if tab.variant == "ckdisc" and st.order_accepted != 4:
+        return cubic(st.t_old, st.t, st.y_old, st.y, st.K[0], st.K[-1], ts)
     if tab.variant != "bs5":
         Q = st.K.T @ tab.P
         return horner(st.t_old, st.t, st.y_old, Q, ts)
@@ -705,6 +825,11 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
     With ``forced_h`` (sequence of |h|) exactly len(forced_h) steps are taken
     and t_span[1] only gives the direction."""
     t0, tf = map(float, t_span)
+    step_fn = ckdisc_step if tab.variant == "ckdisc" else rk_step
+    if tab.variant == "ckdisc":
+        if forced_h is not None or sc_params is not None:
+            raise ValueError("CKdisc has no forced steps / sc_params")
+        nfev_stiff_detect = 0                      # cash.py:238-240
     if forced_h is not None:
         st = RKState(tab, fun, t0, y0, copysign(np.inf, tf - t0),
                      rtol=rtol, atol=atol, first_step=forced_h[0],
@@ -739,7 +864,7 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
             if forced_h is not None:
                 ok, message = rk_step(st, forced_h=forced_h[k])
             else:
-                ok, message = rk_step(st)
+                ok, message = step_fn(st)
             if not ok:
                 st.status = "failed"
             elif st.direction * (st.t - st.t_bound) >= 0:

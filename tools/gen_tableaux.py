@@ -66,10 +66,24 @@ def main():
         Plow=hexarr(ref.BS5.Plow), Pbest=hexarr(ref.BS5.Pbest),
         n_extra_stages=int(ref.BS5.n_extra_stages))
     tabs["BS5"] = bs5
+    # CKdisc (cash.py:184-236): CK5's A and C, its own E (B_all[5] - B_all[4]
+    # evaluated in floating point), assessment and fallback weights.  Kept out
+    # of "tableaux": it is not a RungeKutta._step_impl method.
+    ck = ref.CKdisc
+    ckdisc = dict(
+        name="CKdisc", source="extensisq/cash.py:184-236",
+        n_stages=int(ck.n_stages), order=int(ck.order),
+        order_secondary=int(ck.order_secondary), sc_params="standard",
+        max_factor=float(ck.max_factor), min_factor=float(ck.min_factor),
+        safety=0.9,                                   # cash.py:6
+        A=hexarr(ck.A), B=hexarr(ck.B), C=hexarr(ck.C), E=hexarr(ck.E),
+        P=hexarr(ck.P), B_assess=hexarr(ck.B_assess),
+        E_assess=hexarr(ck.E_assess), C_fallback=hexarr(ck.C_fallback),
+        B_fallback=hexarr(ck.B_fallback), E_fallback=hexarr(ck.E_fallback))
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as fh:
-        json.dump(dict(reference_version=ref.__version__, tableaux=tabs), fh,
-                  indent=0)
+        json.dump(dict(reference_version=ref.__version__, tableaux=tabs,
+                       ckdisc=ckdisc), fh, indent=0)
     print("wrote", OUT, {k: v["n_stages"] for k, v in tabs.items()})
 
 
