@@ -5,7 +5,7 @@ Same export names as the reference for the hot-path classes
 (``extensisq/__init__.py:4-12``); everything else of the reference (ESDIRK,
 Nystrom, sensitivity) is out of scope.
 """
-from .tableaux import (RungeKutta, Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
+from .tableaux import (RungeKutta, Ts5, BS5, CK5, CKdisc, Me4, Pr7, Pr8, Pr9,
                        CFMR7osc, SWAG, BUILTIN, REFERENCE_VERSION)
 from .batched import (DeviceRHS, BatchedOdeResult, solve_ivp_batched, NFS,
                       update_nfs)
@@ -14,7 +14,7 @@ from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
                   nfesig, maxm)
 
 __version__ = "0.1.0"
-__all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "Me4", "Pr7", "Pr8", "Pr9",
+__all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "CKdisc", "Me4", "Pr7", "Pr8", "Pr9",
            "CFMR7osc", "SWAG", "DeviceRHS", "BatchedOdeResult", "solve_ivp_batched",
            "NFS", "update_nfs", "shard_bounds", "gather_result", "SSV2stab",
            "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc", "slab_of", "nfesig",

@@ -16,7 +16,7 @@ XSQ_METHOD_USER = 100
 XSQ_RHS_USER_BASE = 1000
 
 METHOD_IDS = {"Ts5": 0, "BS5": 1, "CK5": 2, "Me4": 3, "Pr7": 4, "Pr8": 5,
-              "Pr9": 6, "CFMR7osc": 7}
+              "Pr9": 6, "CFMR7osc": 7, "CKdisc": 8}
 INTERPOLANTS = {None: 0, "free": 1, "low": 2, "best": 3}
 
 # xsq_lane_status -> the reference's messages

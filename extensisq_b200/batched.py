@@ -204,6 +204,13 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                              "apply to SWAG")
     elif k_max is not None:
         raise ValueError("`k_max` only applies to SWAG")
+    is_ckdisc = not is_swag and getattr(method, "_xsq_method", None) == _lib.METHOD_IDS["CKdisc"]
+    if is_ckdisc:
+        # CKdisc.__init__(fun, t0, y0, t_bound, **extraneous) passes
+        # nfev_stiff_detect=0 itself (cash.py:238-240) and has its own step rule
+        if forced_steps is not None or interpolant is not None:
+            raise ValueError("forced_steps / interpolant do not apply to CKdisc")
+        nfev_stiff_detect = 0
     if device is None:
         device = (y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda
                   else torch.device("cuda", torch.cuda.current_device()))

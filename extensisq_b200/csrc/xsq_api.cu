@@ -58,6 +58,7 @@ static bool method_info(int method, MethodInfo* mi) {
         case XSQ_PR8: *mi = info_of<tab::Pr8>(); return true;
         case XSQ_PR9: *mi = info_of<tab::Pr9>(); return true;
         case XSQ_CFMR7OSC: *mi = info_of<tab::CFMR7osc>(); return true;
+        case XSQ_CKDISC: *mi = info_of<tab::CKdisc>(); return true;
         default: return false;
     }
 }
@@ -116,6 +117,7 @@ static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
         case XSQ_PR8: return launch_Pr8(rhs, P, st, info);
         case XSQ_PR9: return launch_Pr9(rhs, P, st, info);
         case XSQ_CFMR7OSC: return launch_CFMR7osc(rhs, P, st, info);
+        case XSQ_CKDISC: return launch_CKdisc(rhs, P, st, info);
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }
@@ -207,6 +209,10 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     if (a->n_eval < 0 ||
         (a->n_eval > 0 && a->n_lanes > 0 && (!a->t_eval || !a->y_eval))) {
         g_detail = "t_eval / y_eval inconsistent";
+        return XSQ_ERR_ARG;
+    }
+    if (a->method == XSQ_CKDISC && a->n_forced > 0) {
+        g_detail = "CKdisc takes no forced step sequence (cash.py:245-388 has its own step rule)";
         return XSQ_ERR_ARG;
     }
     if (a->n_forced < 0 || (a->n_forced > 0 && !a->h_forced)) {
@@ -412,6 +418,7 @@ int xsq_tableau_get(int32_t method, xsq_tableau_t* out) {
         case XSQ_PR8: tableau_dump<tab::Pr8><<<1, 32>>>(d); break;
         case XSQ_PR9: tableau_dump<tab::Pr9><<<1, 32>>>(d); break;
         case XSQ_CFMR7OSC: tableau_dump<tab::CFMR7osc><<<1, 32>>>(d); break;
+        case XSQ_CKDISC: tableau_dump<tab::CKdisc><<<1, 32>>>(d); break;
         default: cudaFree(d); return XSQ_ERR_ARG;
     }
     count_launch();

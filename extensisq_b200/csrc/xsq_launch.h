@@ -20,6 +20,7 @@ XSQ_DECL_LAUNCH(Pr7)
 XSQ_DECL_LAUNCH(Pr8)
 XSQ_DECL_LAUNCH(Pr9)
 XSQ_DECL_LAUNCH(CFMR7osc)
+XSQ_DECL_LAUNCH(CKdisc)
 #undef XSQ_DECL_LAUNCH
 
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st);

@@ -706,6 +706,7 @@ struct Lane {
         return s;
     }
     bool standard_sc, fresh, step_rejected;
+    double ck_tw[2], ck_q[2];      // CKdisc's twiddle / quit factors (cash.py:241-243)
 
     // RungeKutta.__init__, common.py:187-220
     __device__ __forceinline__ void init(const RkDev& P, long long idx,
@@ -735,6 +736,9 @@ struct Lane {
         h_prev = 0.0;
         lerr_old = 0.0;
         min_step = 0.0;
+        ck_tw[0] = 1.5;
+        ck_tw[1] = 1.1;
+        ck_q[0] = ck_q[1] = 100.0;
         // first step: forced table, first_step, or Watts' h_start (ens_init)
         if (P.n_forced > 0) h_abs = P.h_forced[0];
         else if (P.first_step > 0.0) h_abs = P.first_step;
@@ -1010,6 +1014,162 @@ struct Lane {
     // vanish at compile time.
     template <bool FAST>
     __device__ __forceinline__ int attempt(const RkDev& P, int lane) {
+        if constexpr (Tab::VARIANT == tab::CKDISCV) return attempt_ckdisc<FAST>(P, lane);
+        else return attempt_rk<FAST>(P, lane);
+    }
+
+    // ---- CKdisc, cash.py:245-388 ------------------------------------------
+    // y + h * sum_{i<NS} w_i K_i and h * sum_{i<NS} e_i K_i for one of the
+    // embedded solutions (cash.py:390-404), then sum((err/tol)^2).
+    // SEL: 0/1 assessment pair, 2/3 fallback pair, 4 the fifth order pair.
+    template <int SEL>
+    __device__ __forceinline__ double ck_solution(const RkDev& P, double (&K)[KROWS][NL],
+                                                  double h, double (&sol)[NL], int lane) {
+        if constexpr (Tab::VARIANT == tab::CKDISCV) {
+            constexpr int NS = (SEL == 0 || SEL == 2) ? 2 : (SEL == 4 ? 6 : 4);
+            double errv[NL];
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double sb = 0.0, se = 0.0;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    if constexpr (SEL < 2) {
+                        if (Tab::b_assess(SEL, i) != 0.0) sb = fma(Tab::b_assessv(SEL, i), K[i][c], sb);
+                        if (Tab::e_assess(SEL, i) != 0.0) se = fma(Tab::e_assessv(SEL, i), K[i][c], se);
+                    } else if constexpr (SEL < 4) {
+                        if (Tab::b_fallback(SEL - 2, i) != 0.0) sb = fma(Tab::b_fallbackv(SEL - 2, i), K[i][c], sb);
+                        if (Tab::e_fallback(SEL - 2, i) != 0.0) se = fma(Tab::e_fallbackv(SEL - 2, i), K[i][c], se);
+                    } else {
+                        if (Tab::b(i) != 0.0) sb = fma(Tab::bv(i), K[i][c], sb);
+                        if (Tab::e(i) != 0.0) se = fma(Tab::ev(i), K[i][c], se);
+                    }
+                }
+                sol[c] = fma(h, sb, y[c]);
+                errv[c] = h * se;
+            }
+            return scaled_ss(P, errv, sol, lane);
+        } else {
+            return 0.0;
+        }
+    }
+    // norm(err/tol) ** (1/p) with norm = sqrt(ss/n): (ss/n) ** (1/(2p))
+    static __device__ __forceinline__ double ck_root(const RkDev& P, double ss, double inv2p) {
+        if (ss == 0.0) return 0.0;
+        if (!(ss < XSQ_INF)) return ss;                      // inf / nan pass through
+        return exp2_fast(inv2p * (log2_fast(ss) - P.log2n));
+    }
+
+    // One pass of `while not order_accepted` (cash.py:255-367).
+    template <bool FAST>
+    __device__ __forceinline__ int attempt_ckdisc(const RkDev& P, int lane) {
+        if (fresh) {
+            min_step = pymax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+            const double d = fabs(P.t_bound - t);
+            if ((h_abs < min_step) | (h_abs > P.max_step) | (d < 2.0 * h_abs)) reassess_slow(P, d);
+            step_rejected = false;
+            fresh = false;
+        }
+        if (h_abs < min_step) return LANE_TOO_SMALL;          // cash.py:257-258
+        constexpr double NTOT = (double)R::N;
+        double h = h_abs * P.direction;
+        double K[KROWS][NL];
+        double y_new[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) K[0][c] = f[c];
+        stage<1>(K, h);
+        ++nfev;
+        // first order error, second order solution (cash.py:266-270)
+        const double E1 = ck_root(P, ck_solution<0>(P, K, h, y_new, lane), 0.25);
+        double esttol = E1 / ck_q[0];
+        int accepted = 0;
+        bool retried = false;
+        if (E1 < ck_tw[0] * ck_q[0]) {
+            stage<2>(K, h);
+            stage<3>(K, h);
+            nfev += 2;
+            // second order error, third order solution (cash.py:278-282)
+            const double E2 = ck_root(P, ck_solution<1>(P, K, h, y_new, lane), 1.0 / 6.0);
+            esttol = E2 / ck_q[1];
+            if (E2 < ck_tw[1] * ck_q[1]) {
+                stage<4>(K, h);
+                stage<5>(K, h);
+                nfev += 2;
+                double E4 = ck_root(P, ck_solution<4>(P, K, h, y_new, lane), 0.1);
+                if (E4 == 0.0) E4 = 1e-160;                   // cash.py:293
+                esttol = E4;
+                if (E4 < 1.0) {
+                    accepted = 4;                             // cash.py:297-317
+                    double factor = pymin(Tab::MAX_FACTOR, Tab::SAFETY / E4);
+                    if (step_rejected) factor = pymin(1.0, factor);
+                    h_abs *= factor;
+                    const double e12[2] = {E1, E2};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        double q = e12[j] / E4;
+                        if (q > ck_q[j]) q = pymin(q, 10 * ck_q[j]);
+                        else q = pymax(q, 2.0 / 3.0 * ck_q[j]);
+                        ck_q[j] = pymax(1.0, pymin(10000.0, q));
+                    }
+                } else {
+                    if (!(E4 < XSQ_INF)) return LANE_OVERFLOW;    // cash.py:320-321
+                    const double e12[2] = {E1, E2};               // cash.py:324-328
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double EQ = e12[i] / ck_q[i];
+                        if (EQ < ck_tw[i]) ck_tw[i] = pymax(1.1, EQ);
+                    }
+                    // third order fallback over 3/5 of the step (cash.py:331-341)
+                    if (E2 < 1.0 && ck_solution<3>(P, K, h, y_new, lane) < NTOT) {
+                        accepted = 2;
+                        h_abs *= Tab::c_fallback(1);
+                        h = h_abs * P.direction;
+                    }
+                }
+            }
+            // second order fallback over 1/5 of the step (cash.py:344-361)
+            if (accepted == 0 && E1 < 1.0) {
+                if (ck_solution<2>(P, K, h, y_new, lane) < NTOT) {
+                    accepted = 1;
+                    h_abs *= Tab::c_fallback(0);
+                    h = h_abs * P.direction;
+                } else {                                      // non-smooth: retry with h/5
+                    step_rejected = true;
+                    h_abs *= Tab::c_fallback(0);
+                    ++n_rej;
+                    retried = true;
+                }
+            }
+        }
+        if (accepted == 0) {
+            if (!retried) {                                   // cash.py:363-367
+                step_rejected = true;
+                h_abs *= pymax(Tab::MIN_FACTOR, Tab::SAFETY / esttol);
+                ++n_rej;
+            }
+            return (n_acc + n_rej >= P.max_steps) ? LANE_STEP_BUDGET : LANE_RUNNING;
+        }
+        // the accepted solution's derivative: first stage of the next step and
+        // end slope of the interpolants (cash.py:371-375)
+        const double t_new = t + h;
+        R::f(t_new, y_new, prm, K[S]);
+        ++nfev;
+        if (!FAST && P.n_eval > 0 && ieval < P.n_eval &&
+            P.direction * (P.t_eval[ieval] - t_new) <= 0.0) {
+            // cash.py:406-416: Horner for the fifth order solution, else cubic
+            if (accepted == 4) emit_poly(P, K, h, t_new, y_new, lane);
+            else emit_cubic(P, K, t_new, y_new, lane);
+        }
+        t = t_new;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
+        ++n_acc;
+        fresh = true;
+        if (P.direction * (t - P.t_bound) >= 0.0) return LANE_FINISHED;
+        return (n_acc + n_rej >= P.max_steps) ? LANE_STEP_BUDGET : LANE_RUNNING;
+    }
+
+    template <bool FAST>
+    __device__ __forceinline__ int attempt_rk(const RkDev& P, int lane) {
         // Forced-step mode shares every instruction of the adaptive path: h
         // comes from the table instead of reassess(), every step is accepted,
         // and the controller's h update is overwritten at the next step.
@@ -1281,6 +1441,7 @@ struct Lane {
     // attempt (bogacki.py:266-275, calvo.py:178-187), and f(t+h, y_new) per
     // ACCEPTED step for non-FSAL pairs (common.py:289-291).
     __device__ __forceinline__ int evals_in_loop() const {
+        if (Tab::VARIANT == tab::CKDISCV) return 0;   // counted where they are made
         const int attempts = n_acc + n_rej;
         return (S - 1 + Tab::FSAL) * (attempts - n_pre) + (S - 2) * n_pre +
                (Tab::FSAL ? 0 : n_acc);

@@ -141,6 +141,7 @@ const char* builtin_tab_name(int method) {
         case XSQ_PR8: return "Pr8";
         case XSQ_PR9: return "Pr9";
         case XSQ_CFMR7OSC: return "CFMR7osc";
+        case XSQ_CKDISC: return "CKdisc";
         default: return nullptr;
     }
 }
@@ -379,7 +380,7 @@ int user_build_source(int method, int rhs, std::string* src, std::string* key) {
         (void)mi;
         *key = n;
         s = 17;  // conservative default; refined below for built-ins
-        static const int ks[] = {6, 7, 6, 5, 10, 13, 17, 9};
+        static const int ks[] = {6, 7, 6, 5, 10, 13, 17, 9, 6};
         s = ks[method];
     }
     if (rhs >= XSQ_RHS_USER_BASE) {

@@ -96,7 +96,7 @@ with open(_JSON) as _fh:
     _raw = json.load(_fh)
 REFERENCE_VERSION = _raw["reference_version"]
 _METHOD_IDS = {"Ts5": 0, "BS5": 1, "CK5": 2, "Me4": 3, "Pr7": 4, "Pr8": 5,
-               "Pr9": 6, "CFMR7osc": 7}
+               "Pr9": 6, "CFMR7osc": 7, "CKdisc": 8}
 
 Ts5 = _make("Ts5", _raw["tableaux"]["Ts5"])
 BS5 = _make("BS5", _raw["tableaux"]["BS5"])
@@ -110,6 +110,26 @@ for _n, _c in (("Ts5", Ts5), ("BS5", BS5), ("CK5", CK5), ("Me4", Me4),
                ("Pr7", Pr7), ("Pr8", Pr8), ("Pr9", Pr9),
                ("CFMR7osc", CFMR7osc)):
     _c._xsq_method = _METHOD_IDS[_n]
+
+
+def _make_ckdisc(d):
+    """CKdisc (cash.py:115-416): CK5's stages with assessment and fallback
+    weights; its own step rule (max_factor 5, min_factor 1/5), so `sc_params`
+    has no effect and the stiffness diagnosis is off (cash.py:238-240)."""
+    cls = _make("CKdisc", dict(d, stbrad=None, tanang=None))
+    for k in ("B_assess", "E_assess", "C_fallback", "B_fallback", "E_fallback"):
+        v = _unhex(d[k])
+        v.setflags(write=False)
+        setattr(cls, k, v)
+    cls.max_factor = d["max_factor"]
+    cls.min_factor = d["min_factor"]
+    cls.__doc__ = ("Cash-Karp variable order (5, 3, 2) method for non-smooth "
+                   "problems; reference extensisq/cash.py:115-416.")
+    return cls
+
+
+CKdisc = _make_ckdisc(_raw["ckdisc"])
+CKdisc._xsq_method = _METHOD_IDS["CKdisc"]
 del _raw, _fh, _n, _c
 
 BUILTIN = {c.__name__: c for c in (Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,

@@ -56,11 +56,14 @@ typedef enum xsq_lane_status {
 /* Built-in tableau methods: the reference's classes
  * Ts5 (tsitouras.py:83), BS5 (bogacki.py:103), CK5 (cash.py:82),
  * Me4 (merson.py:82), Pr7/Pr8/Pr9 (prince.py:79,205,449),
- * CFMR7osc (calvo.py:89).  XSQ_METHOD_USER selects the tableau uploaded with
+ * CFMR7osc (calvo.py:89), CKdisc (cash.py:115).  XSQ_METHOD_USER selects the tableau uploaded with
  * xsq_tableau_load (user subclasses of common.RungeKutta, common.py:88-121). */
 typedef enum xsq_method {
     XSQ_TS5 = 0, XSQ_BS5 = 1, XSQ_CK5 = 2, XSQ_ME4 = 3,
     XSQ_PR7 = 4, XSQ_PR8 = 5, XSQ_PR9 = 6, XSQ_CFMR7OSC = 7,
+    XSQ_CKDISC = 8,         /* cash.py:115-416: variable order (5,3,2); ignores
+                               sc_params, never runs the stiffness diagnosis,
+                               no forced step sequences */
     XSQ_METHOD_USER = 100,
     XSQ_METHOD_SWAG = 200   /* internal tag used by xsq_swag_solve */
 } xsq_method;

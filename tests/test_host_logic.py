@@ -131,3 +131,19 @@ def test_gather_result_world_size_2_gloo():
         mp.spawn(_gather_worker, args=(world, port, n_lanes, out),
                  nprocs=world, join=True)
         assert out[0] and out[1]
+
+
+def test_ckdisc_class_mirrors_the_reference_attributes():
+    # cash.py:184-236
+    import extensisq_b200 as xb
+    ck = xb.CKdisc
+    assert (ck.n_stages, ck.order, ck.order_secondary) == (6, 5, 4)
+    assert ck.max_factor == 5 and ck.min_factor == 1 / 5
+    assert np.array_equal(ck.A, xb.CK5.A) and np.array_equal(ck.C, xb.CK5.C)
+    assert np.array_equal(ck.B, xb.CK5.B) and np.array_equal(ck.P, xb.CK5.P)
+    assert ck.E.shape == (7,) and ck.E[-1] == 0.0
+    assert ck.B_assess.shape == (2, 6) and ck.E_assess.shape == (2, 6)
+    assert ck.B_fallback.shape == (2, 6) and ck.E_fallback.shape == (2, 6)
+    assert np.array_equal(ck.C_fallback, ck.C[[1, 3]])
+    assert ck._xsq_method == 8 and "CKdisc" not in xb.BUILTIN
+    assert ck.stbrad is None and ck.tanang is None      # no stiffness diagnosis
