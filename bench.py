@@ -104,7 +104,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Samples before this moment (nvidia-smi starting up during the last
+        warm-up step) are not part of the report."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -118,7 +123,9 @@ class ClockSampler:
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < getattr(self, "t_mark", 0.0):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -293,7 +300,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    # nvidia-smi is started BEFORE the last warm-up step: its start-up stalls
+    # the GPU for tens of ms, which must not land in the first timed step; only
+    # the samples taken inside the timed region are reported (sampler.mark()).
+    sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        if rank == 0 and i == args.warmup - 1:
+            sampler.start()
         r = solve_resident()
     barrier()
     acc_total = int(r.n_accepted.sum().item())
@@ -301,9 +314,9 @@ def main():
     assert bool((r.status == 0).all()), "lanes failed"
 
     # ---- timed region 1: inputs resident in HBM ---------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sampler.proc is None:
         sampler.start()
+    sampler.mark()
     lib.xsq_launch_count(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
