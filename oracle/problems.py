@@ -40,6 +40,10 @@ def square_forced(t, y):      # oscillator driven by a square wave (non-smooth)
     return np.array([y[1], -y[0] + (1.0 if sin(3.0 * t) >= 0.0 else -1.0)])
 
 
+def ballistic(t, y):          # falling body with linear drag (events: ground hit)
+    return np.array([y[1], -9.81 - 0.1 * y[1]])
+
+
 def linear(lam):
     return lambda t, y: np.array([lam * y[0], lam * y[1]])
 
@@ -56,7 +60,8 @@ def make_fun(problem, params):
     return {"rational": rational, "duffing": duffing,
             "forced_osc": forced_osc, "detest_b3": detest_b3,
             "mass_spring_damper": mass_spring_damper,
-            "detest_f2": detest_f2, "square_forced": square_forced}[problem]
+            "detest_f2": detest_f2, "square_forced": square_forced,
+            "ballistic": ballistic}[problem]
 
 
 # CUDA device-function sources for xsq_rhs_register_source (entry name "rhs";
@@ -98,6 +103,11 @@ __device__ void rhs(double t, const double* y, const double* p, double* dy) {
 __device__ void rhs(double t, const double* y, const double* p, double* dy) {
     dy[0] = y[1];
     dy[1] = -y[0] + (sin(3.0 * t) >= 0.0 ? 1.0 : -1.0);
+}"""),
+    "ballistic": (2, 0, r"""
+__device__ void rhs(double t, const double* y, const double* p, double* dy) {
+    dy[0] = y[1];
+    dy[1] = -9.81 - 0.1 * y[1];
 }"""),
     "linear": (2, 1, r"""
 __device__ void rhs(double t, const double* y, const double* p, double* dy) {
@@ -156,3 +166,28 @@ def heat3d_notebook(N=39):
                                W[1:-1, 1:-1, :-2] + W[1:-1, 1:-1, 2:])
         return (lap + src(X, Y, Z, t)[1:-1, 1:-1, 1:-1]).reshape(-1)
     return fun, y0, 12 / h ** 2
+
+
+# ---- event functions (scipy solve_ivp `events=`), Python and CUDA twins -------
+# name -> (python callables [g_k(t, y)], CUDA source of
+#          `double event(int k, double t, const double* y, const double* p)`)
+EVENT_SETS = {
+    "ground": ([lambda t, y: y[0], lambda t, y: y[1]], r"""
+__device__ double event(int k, double t, const double* y, const double* p) {
+    return k == 0 ? y[0] : y[1];
+}"""),
+    "lorenz_sections": ([lambda t, y: y[2] - 27.0, lambda t, y: y[0],
+                         lambda t, y: y[0] * y[1] - 30.0], r"""
+__device__ double event(int k, double t, const double* y, const double* p) {
+    if (k == 0) return y[2] - 27.0;
+    if (k == 1) return y[0];
+    return y[0] * y[1] - 30.0;
+}"""),
+    "vdp_cross": ([lambda t, y: y[0], lambda t, y: y[1] - 1.0,
+                   lambda t, y: t - 7.25], r"""
+__device__ double event(int k, double t, const double* y, const double* p) {
+    if (k == 0) return y[0];
+    if (k == 1) return y[1] - 1.0;
+    return t - 7.25;
+}"""),
+}

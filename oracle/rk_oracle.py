@@ -768,30 +768,43 @@ def ckdisc_step(st):
     return True, None
 
 
-def dense_eval(st, ts):
-    """dense_output()(ts) over the last accepted step.
-    common.py:358-368; bogacki.py:348-393; cash.py:406-416."""
+def make_dense(st):
+    """``solver.dense_output()`` for the last accepted step: a callable sol(ts)
+    (ts scalar or array).  common.py:358-368; bogacki.py:348-393 (the extra
+    stages of BS5's 'low'/'best' interpolants are evaluated HERE, once per
+    call, as in the reference); cash.py:406-416."""
     tab = st.tab
-    if st.t == st.t_old:           # scipy base.py:224-226 ConstantDenseOutput
-        return np.repeat(st.y[:, None], np.size(ts), axis=1)
+    t_old, t, y_old, y = st.t_old, st.t, st.y_old, st.y
+
+    def wrap(fn):
+        def sol(ts):
+            ts = np.asarray(ts, dtype=float)
+            out = fn(np.atleast_1d(ts))
+            return out if ts.shape else out[:, 0]
+        return sol
+    if t == t_old:                 # scipy base.py:224-226 ConstantDenseOutput
+        return wrap(lambda ts: np.repeat(y[:, None], np.size(ts), axis=1))
     if tab.variant == "ckdisc" and st.order_accepted != 4:
-        return cubic(st.t_old, st.t, st.y_old, st.y, st.K[0], st.K[-1], ts)
+        K0, K1 = st.K[0].copy(), st.K[-1].copy()
+        return wrap(lambda ts: cubic(t_old, t, y_old, y, K0, K1, ts))
     if tab.variant != "bs5":
         Q = st.K.T @ tab.P
-        return horner(st.t_old, st.t, st.y_old, Q, ts)
+        return wrap(lambda ts: horner(t_old, t, y_old, Q, ts))
     h = st.h_previous
     K = st.K_ext
     s = tab.n_stages
     if st.interpolant == "free":
-        return horner(st.t_old, st.t, st.y_old, K.T @ tab.P, ts)
+        Q = K.T @ tab.P
+        return wrap(lambda ts: horner(t_old, t, y_old, Q, ts))
     if st.interpolant == "low":
         r = s + 1
         dy = K[:r, :].T @ tab.A_extra[0, :r] * h
-        K[r] = st.fun(st.t_old + tab.C_extra[0] * h, st.y_old + dy)
-        return horner(st.t_old, st.t, st.y_old, K.T @ tab.Plow, ts)
+        K[r] = st.fun(t_old + tab.C_extra[0] * h, y_old + dy)
+        Q = K.T @ tab.Plow
+        return wrap(lambda ts: horner(t_old, t, y_old, Q, ts))
     for r, (a, c) in enumerate(zip(tab.A_extra, tab.C_extra), start=s + 1):
         dy = K[:r, :].T @ a[:r] * h
-        K[r] = st.fun(st.t_old + c * h, st.y_old + dy)
+        K[r] = st.fun(t_old + c * h, y_old + dy)
     Pb = tab.Pbest
     Q = np.empty((K.shape[1], Pb.shape[1]))
     Q[:, 0] = st.K[7]
@@ -811,13 +824,100 @@ def dense_eval(st, ts):
     Q[:, 5] = (KP[4] + ((KP[9] + KP[7]) + (KP[6] + KP[5])) + ((KP[3] +
                KP[8]) + (KP[2] + KP[10]) + KP[0]))
     # anchored at the END of the step (bogacki.py:389-393)
-    return horner(st.t, st.t + h, st.y, Q, ts)
+    return wrap(lambda ts: horner(t, t + h, y, Q, ts))
+
+
+def dense_eval(st, ts):
+    """dense_output()(ts) over the last accepted step."""
+    return make_dense(st)(ts)
+
+
+# --------------------------------------------------------------------------
+# events: scipy's solve_ivp machinery (third party, scipy/integrate/_ivp/ivp.py
+# find_active_events / handle_events / solve_event_equation, and
+# scipy/optimize/Zeros/brentq.c), restated; pinned in tests against
+# scipy.optimize.brentq and against solve_ivp runs of the reference.
+# --------------------------------------------------------------------------
+_EPS = float(np.finfo(float).eps)
+
+
+def brentq(f, xa, xb, xtol=4 * _EPS, rtol=4 * _EPS, maxiter=100):
+    """Brent's method as coded in scipy's brentq.c.  Returns (root, calls)."""
+    def neg(v):
+        return copysign(1.0, v) < 0
+    xpre, xcur = xa, xb
+    xblk = fblk = spre = scur = 0.0
+    fpre, fcur = f(xpre), f(xcur)
+    calls = 2
+    if fpre == 0:
+        return xpre, calls
+    if fcur == 0:
+        return xcur, calls
+    if neg(fpre) == neg(fcur):
+        raise ValueError("f(a) and f(b) must have different signs")
+    for _ in range(maxiter):
+        if fpre != 0 and fcur != 0 and neg(fpre) != neg(fcur):
+            xblk, fblk = xpre, fpre
+            spre = scur = xcur - xpre
+        if abs(fblk) < abs(fcur):
+            xpre, xcur, xblk = xcur, xblk, xcur
+            fpre, fcur, fblk = fcur, fblk, fcur
+        delta = (xtol + rtol * abs(xcur)) / 2
+        sbis = (xblk - xcur) / 2
+        if fcur == 0 or abs(sbis) < delta:
+            return xcur, calls
+        if abs(spre) > delta and abs(fcur) < abs(fpre):
+            if xpre == xblk:
+                stry = -fcur * (xcur - xpre) / (fcur - fpre)
+            else:
+                dpre = (fpre - fcur) / (xpre - xcur)
+                dblk = (fblk - fcur) / (xblk - xcur)
+                stry = (-fcur * (fblk * dblk - fpre * dpre) /
+                        (dblk * dpre * (fblk - fpre)))
+            if 2 * abs(stry) < min(abs(spre), 3 * abs(sbis) - delta):
+                spre, scur = scur, stry
+            else:
+                spre = scur = sbis
+        else:
+            spre = scur = sbis
+        xpre, fpre = xcur, fcur
+        if abs(scur) > delta:
+            xcur += scur
+        else:
+            xcur += delta if sbis > 0 else -delta
+        fcur = f(xcur)
+        calls += 1
+    return xcur, calls
+
+
+def find_active_events(g, g_new, direction):       # ivp.py
+    g, g_new = np.asarray(g), np.asarray(g_new)
+    up = (g <= 0) & (g_new >= 0)
+    down = (g >= 0) & (g_new <= 0)
+    either = up | down
+    mask = (up & (direction > 0) | down & (direction < 0) |
+            either & (direction == 0))
+    return np.nonzero(mask)[0]
+
+
+def handle_events(sol, events, active_events, event_count, max_events,
+                  t_old, t):                          # ivp.py
+    roots = np.asarray([brentq(lambda tt, ev=events[i]: ev(tt, sol(tt)),
+                               t_old, t)[0] for i in active_events])
+    if np.any(event_count[active_events] >= max_events[active_events]):
+        order = np.argsort(roots) if t > t_old else np.argsort(-roots)
+        active_events = active_events[order]
+        roots = roots[order]
+        k = np.nonzero(event_count[active_events] >=
+                       max_events[active_events])[0][0]
+        return active_events[:k + 1], roots[:k + 1], True
+    return active_events, roots, False
 
 
 def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
              first_step=None, t_eval=None, sc_params=None, interpolant=None,
              forced_h=None, record=False, max_steps=None,
-             nfev_stiff_detect=5000):
+             nfev_stiff_detect=5000, events=None):
     """solve_ivp(fun, t_span, y0, method=<tab>, ...) restated.
 
     Returns a dict with t, y (n x n_t), n_accepted, n_rejected, nfev, status,
@@ -854,6 +954,18 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
     status = None
     message = None
     k = 0
+    # events: list of (fn(t, y), terminal, direction); terminal False/0 = never,
+    # True/1 = first occurrence, n = n-th occurrence (ivp.py prepare_events)
+    t_events = y_events = None
+    if events is not None:
+        ev_fns = [e[0] for e in events]
+        max_events = np.array([np.inf if not e[1] else float(int(e[1]))
+                               for e in events])
+        ev_dir = np.array([float(e[2]) for e in events])
+        event_count = np.zeros(len(events))
+        g = [ev(t0, st.y) for ev in ev_fns]
+        t_events = [[] for _ in events]
+        y_events = [[] for _ in events]
     while status is None:
         # OdeSolver.step, scipy base.py:179-210
         if st.n == 0 or st.t == st.t_bound:
@@ -878,9 +990,27 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
         if record:
             hs.append(abs(st.h_previous))
         t = st.t
+        y_out = st.y
+        sol = None
+        if events is not None:                    # ivp.py, event block
+            g_new = [ev(t, st.y) for ev in ev_fns]
+            active = find_active_events(g, g_new, ev_dir)
+            if active.size > 0:
+                sol = make_dense(st)
+                event_count[active] += 1
+                idx, roots, terminate = handle_events(
+                    sol, ev_fns, active, event_count, max_events, st.t_old, t)
+                for e, te in zip(idx, roots):
+                    t_events[e].append(te)
+                    y_events[e].append(sol(te))
+                if terminate:
+                    status = 1
+                    t = roots[-1]
+                    y_out = sol(t)
+            g = g_new
         if t_eval is None:
             ts.append(t)
-            ys.append(st.y)
+            ys.append(y_out)
         else:                                     # ivp.py:711-728
             if st.direction > 0:
                 i_new = np.searchsorted(t_eval, t, side="right")
@@ -889,8 +1019,10 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
                 i_new = np.searchsorted(t_eval, t, side="left")
                 step_pts = t_eval[i_new:t_eval_i][::-1]
             if step_pts.size > 0:
+                if sol is None:
+                    sol = make_dense(st)
                 ts.append(step_pts)
-                ys.append(dense_eval(st, step_pts))
+                ys.append(sol(step_pts))
                 t_eval_i = i_new
         if forced_h is not None and k >= len(forced_h):
             status = 0
@@ -909,6 +1041,11 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
                nfev=st.nfev, status=status, message=message, t_final=st.t,
                y_final=st.y.copy(), h_next=st.h_abs,
                n_stiff_tests=st.n_stiff_tests, stiff_flags=st.stiff_flags)
+    if events is not None:
+        out["t_events"] = [np.asarray(te) for te in t_events]
+        out["y_events"] = [np.asarray(ye) for ye in y_events]
+        if status == 1:                  # the solver itself stands at st.t
+            out["t_final"], out["y_final"] = t, np.array(y_out)
     if record:
         out["h"] = np.array(hs)
     return out
