@@ -7,7 +7,7 @@ Nystrom, sensitivity) is out of scope.
 """
 from .tableaux import (RungeKutta, Ts5, BS5, CK5, CKdisc, Me4, Pr7, Pr8, Pr9,
                        CFMR7osc, SWAG, BUILTIN, REFERENCE_VERSION)
-from .batched import (DeviceRHS, BatchedOdeResult, solve_ivp_batched, NFS,
+from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, solve_ivp_batched, NFS,
                       update_nfs)
 from .sharding import shard_bounds, gather_result
 from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
@@ -15,7 +15,7 @@ from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
 
 __version__ = "0.1.0"
 __all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "CKdisc", "Me4", "Pr7", "Pr8", "Pr9",
-           "CFMR7osc", "SWAG", "DeviceRHS", "BatchedOdeResult", "solve_ivp_batched",
+           "CFMR7osc", "SWAG", "DeviceRHS", "DeviceEvents", "BatchedOdeResult", "solve_ivp_batched",
            "NFS", "update_nfs", "shard_bounds", "gather_result", "SSV2stab",
            "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc", "slab_of", "nfesig",
            "maxm"]

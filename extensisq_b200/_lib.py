@@ -22,6 +22,7 @@ INTERPOLANTS = {None: 0, "free": 1, "low": 2, "best": 3}
 # xsq_lane_status -> the reference's messages
 LANE_MESSAGES = {
     0: "The solver successfully reached the end of the integration interval.",
+    1: "A termination event occurred.",
     -1: "Required step size is less than spacing between numbers.",
     -2: "Overflow or underflow encountered.",
     -3: "tolerance too tight",
@@ -34,6 +35,7 @@ EXPORTS = [
     "xsq_abi_version", "xsq_strerror", "xsq_last_error_detail",
     "xsq_device_info", "xsq_tableau_load", "xsq_tableau_get",
     "xsq_rhs_builtin", "xsq_rhs_register_source", "xsq_user_compile_check",
+    "xsq_events_register_source", "xsq_events_compile_check",
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
     "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
@@ -83,6 +85,11 @@ class XsqRkArgs(C.Structure):
         ("n_eval_done", C.c_void_p),
         ("nfev_stiff_detect", C.c_int32), ("reserved1", C.c_int32),
         ("stiff_flags", C.c_void_p),
+        ("events", C.c_int32), ("n_event_fns", C.c_int32),
+        ("ev_terminal", _ip), ("ev_direction", _ip),
+        ("ev_capacity", C.c_int32), ("reserved2", C.c_int32),
+        ("t_events", C.c_void_p), ("y_events", C.c_void_p),
+        ("ev_count", C.c_void_p),
     ]
 
 
@@ -149,6 +156,8 @@ def load():
     lib.xsq_rhs_register_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int32,
                                             C.c_int32, _ip]
     lib.xsq_user_compile_check.argtypes = [C.c_int32, C.c_int32]
+    lib.xsq_events_register_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, _ip]
+    lib.xsq_events_compile_check.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.xsq_rk_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_void_p]
     lib.xsq_rk_solve_host.argtypes = [C.POINTER(XsqRkArgs), C.c_int]
     lib.xsq_swag_solve.argtypes = [C.POINTER(XsqRkArgs), C.c_int32, C.c_void_p]
@@ -165,7 +174,7 @@ def load():
     lib.xsq_launch_count.restype = C.c_int64
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]
-    if lib.xsq_abi_version() != 1:
+    if lib.xsq_abi_version() != 2:
         raise ImportError("libxsq.so ABI version mismatch")
     _lib = lib
     return lib

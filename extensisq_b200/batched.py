@@ -62,6 +62,43 @@ class DeviceRHS:
         return cls(h.value, int(n_state), int(n_param), f"user:{entry}")
 
 
+class DeviceEvents:
+    """The ``events=`` argument of scipy's ``solve_ivp`` as device code.
+
+    ``DeviceEvents.from_source(src, "event", n_events, terminal=[...],
+    direction=[...])`` where ``src`` defines
+    ``__device__ double event(int k, double t, const double* y, const double* p)``
+    returning the value of event function ``k``.  ``terminal[k]``: False / 0
+    (never), True / 1 (first occurrence) or n (n-th occurrence); ``direction[k]``
+    as in scipy (ivp.py prepare_events / find_active_events)."""
+
+    def __init__(self, handle, n_events, terminal, direction, name):
+        self.handle, self.n_events, self.name = handle, n_events, name
+        self.terminal = [int(v) for v in terminal]
+        self.direction = [int(np.sign(v)) for v in direction]
+        if len(self.terminal) != n_events or len(self.direction) != n_events:
+            raise ValueError("terminal / direction need one entry per event")
+        if any(v < 0 for v in self.terminal):
+            raise ValueError("The `terminal` attribute of each event must be a "
+                             "boolean or positive integer.")
+
+    @classmethod
+    def from_source(cls, cuda_src, entry, n_events, terminal=None, direction=None):
+        lib = _lib.load()
+        h = C.c_int32()
+        _lib.check(lib.xsq_events_register_source(
+            cuda_src.encode(), entry.encode(), int(n_events), C.byref(h)))
+        return cls(h.value, int(n_events), terminal or [0] * n_events,
+                   direction or [0] * n_events, f"events:{entry}")
+
+    def with_attributes(self, terminal=None, direction=None):
+        """Same compiled functions, other terminal / direction attributes."""
+        return DeviceEvents(self.handle, self.n_events,
+                            self.terminal if terminal is None else terminal,
+                            self.direction if direction is None else direction,
+                            self.name)
+
+
 @dataclass
 class BatchedOdeResult:
     """Per-lane results; mirrors scipy's OdeResult field names where they
@@ -78,6 +115,9 @@ class BatchedOdeResult:
     n_eval_done: object = None  # int32 [N] or None
     stiff_flags: object = None  # int32 [N]: 1 stiff (real root), 2 stiff
     #                             (complex pair), 4 oscillatory + many failures
+    t_events: object = None     # [N, n_events, capacity], NaN where unused
+    y_events: object = None     # [N, n_events, capacity, n]
+    event_counts: object = None  # int32 [N, n_events] occurrences found
     njev: int = 0
     nlu: int = 0
 
@@ -146,7 +186,8 @@ def _sc_tuple(sc_params):
 def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                       rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf,
                       sc_params=None, interpolant=None, k_max=None,
-                      nfev_stiff_detect=5000, max_steps=None,
+                      nfev_stiff_detect=5000, max_steps=None, events=None,
+                      max_event_records=16,
                       forced_steps=None, device=None, stream=None,
                       **extraneous):
     """Integrate N independent systems ``y' = fun(t, y; params_i)``.
@@ -163,6 +204,11 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     sc_params : "G" | "S" | "standard" | (kb1, kb2, a, g)
     interpolant : BS5 only, 'best' | 'low' | 'free' (bogacki.py:217)
     k_max : SWAG only, maximum order 1..12 (shampine.py:99-103)
+    events : DeviceEvents or None -- scipy's `events=` (terminal, direction,
+        root finding with brentq on the method's dense output, ivp.py); the
+        result carries t_events / y_events / event_counts per lane, lanes stopped
+        by a terminal event have status 1 and t_final / y_final at the event
+    max_event_records : occurrences kept per event function and lane
     nfev_stiff_detect : stiffness diagnosis every this many evaluations or on
         >= 10 failed steps in 40 (common.py:150-164, 370-516); 0 turns it off.
         Instead of warnings the result carries per-lane ``stiff_flags``
@@ -204,6 +250,14 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                              "apply to SWAG")
     elif k_max is not None:
         raise ValueError("`k_max` only applies to SWAG")
+    if events is not None:
+        if not isinstance(events, DeviceEvents):
+            raise ValueError("`events` must be a DeviceEvents (device code; a "
+                             "Python callable cannot run inside the kernel)")
+        if is_swag or forced_steps is not None:
+            raise ValueError("events do not apply to SWAG or forced_steps")
+        if not (isinstance(max_event_records, int) and max_event_records > 0):
+            raise ValueError("`max_event_records` must be a positive integer")
     is_ckdisc = not is_swag and getattr(method, "_xsq_method", None) == _lib.METHOD_IDS["CKdisc"]
     if is_ckdisc:
         # CKdisc.__init__(fun, t0, y0, t_bound, **extraneous) passes
@@ -312,6 +366,12 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         status = torch.empty(N, **i32)
         n_done = torch.empty(N, **i32) if n_eval else None
         stiff = torch.zeros(N, **i32)
+        t_ev = y_ev = ev_cnt = None
+        if events is not None:
+            cap = int(max_event_records)
+            t_ev = torch.full((N, events.n_events, cap), float("nan"), **f64)
+            y_ev = torch.full((N, events.n_events, cap, n), float("nan"), **f64)
+            ev_cnt = torch.zeros((N, events.n_events), **i32)
 
         a = _lib.XsqRkArgs()
         a.struct_size = C.sizeof(_lib.XsqRkArgs)
@@ -348,6 +408,17 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         a.n_eval_done = n_done.data_ptr() if n_eval else None
         a.nfev_stiff_detect = 0 if is_swag else nfev_stiff_detect
         a.stiff_flags = stiff.data_ptr()
+        if events is not None:
+            ne = events.n_events
+            term_c = (C.c_int32 * ne)(*events.terminal)
+            dir_c = (C.c_int32 * ne)(*events.direction)
+            a.events, a.n_event_fns = events.handle, ne
+            a.ev_terminal = C.cast(term_c, _lib._ip)
+            a.ev_direction = C.cast(dir_c, _lib._ip)
+            a.ev_capacity = int(max_event_records)
+            a.t_events = t_ev.data_ptr()
+            a.y_events = y_ev.data_ptr()
+            a.ev_count = ev_cnt.data_ptr()
         st = stream if stream is not None else torch.cuda.current_stream(device)
         if is_swag:
             _lib.check(lib.xsq_swag_solve(C.byref(a), k_max,
@@ -360,7 +431,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     res = BatchedOdeResult(
         t=te, y=y_eval, t_final=t_final, y_final=y_final.t(), h_next=h_next,
         n_accepted=n_acc, n_rejected=n_rej, nfev=nfev, status=status,
-        n_eval_done=n_done, stiff_flags=stiff)
+        n_eval_done=n_done, stiff_flags=stiff, t_events=t_ev, y_events=y_ev,
+        event_counts=ev_cnt)
     res._keepalive = (y0_soa, prm_soa, hf, atol_c)
     return res
 

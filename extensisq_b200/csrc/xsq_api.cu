@@ -123,10 +123,12 @@ static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
 }
 
 // init kernel -> persistent kernel -> (stiffness diagnosis on) probe queue kernel
-static int dispatch(int method, int rhs, const RkDev& P, const MethodInfo& mi,
+static int dispatch(int method, int rhs, int events, const RkDev& P, const MethodInfo& mi,
                     cudaStream_t st, LaunchInfo* info) {
-    if (rhs >= XSQ_RHS_USER_BASE)
-        return user_rk_launch(method, rhs, P, mi.s, mi.stbrad, mi.tanang, st);
+    // user right-hand sides and event functions are device code compiled at
+    // run time into their own kernel
+    if (rhs >= XSQ_RHS_USER_BASE || events != 0)
+        return user_rk_launch(method, rhs, events, P, mi.s, mi.stbrad, mi.tanang, st);
     int rc = launch_ens_init(rhs, P, st);       // f0 + h_start for all lanes
     if (rc != XSQ_OK) return rc;
     if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
@@ -211,6 +213,25 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
         g_detail = "t_eval / y_eval inconsistent";
         return XSQ_ERR_ARG;
     }
+    if (a->events != 0) {
+        const int ne = user_events_count(a->events);
+        if (ne < 0 || ne != a->n_event_fns || !a->ev_terminal || !a->ev_direction ||
+            a->ev_capacity < 1 ||
+            (a->n_lanes > 0 && (!a->t_events || !a->y_events || !a->ev_count))) {
+            g_detail = "events arguments inconsistent";
+            return XSQ_ERR_ARG;
+        }
+        if (a->n_forced > 0 || a->rhs == XSQ_RHS_NBODY32 || a->method == XSQ_METHOD_SWAG) {
+            g_detail = "events are not available with forced steps, SWAG or nbody32";
+            return XSQ_ERR_UNSUPPORTED;
+        }
+        for (int k = 0; k < ne; ++k)
+            if (a->ev_terminal[k] < 0) {
+                g_detail = "The `terminal` attribute of each event must be a boolean or "
+                           "positive integer.";           // ivp.py prepare_events
+                return XSQ_ERR_ARG;
+            }
+    }
     if (a->method == XSQ_CKDISC && a->n_forced > 0) {
         g_detail = "CKdisc takes no forced step sequence (cash.py:245-388 has its own step rule)";
         return XSQ_ERR_ARG;
@@ -271,6 +292,15 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     if (P->nfev_stiff_detect > 0 && P->nfev_stiff_detect / mi->s < 1) P->nfev_stiff_detect = mi->s;
     P->stiff_many_steps = P->nfev_stiff_detect > 0 ? P->nfev_stiff_detect / mi->s : 1;
     P->stiff_flags = a->stiff_flags;
+    P->n_events = a->events != 0 ? a->n_event_fns : 0;
+    P->ev_capacity = a->ev_capacity;
+    for (int k = 0; k < P->n_events; ++k) {
+        P->ev_terminal[k] = a->ev_terminal[k];
+        P->ev_direction[k] = a->ev_direction[k] > 0 ? 1 : (a->ev_direction[k] < 0 ? -1 : 0);
+    }
+    P->t_events = a->t_events;
+    P->y_events = a->y_events;
+    P->ev_count = a->ev_count;
     return XSQ_OK;
 }
 
@@ -360,7 +390,7 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         P.stiff_q = slots + 2 * threads * rec;
         P.stiff_q_cap = (long long)qcap;
     }
-    rc = dispatch(a->method, a->rhs, P, mi, st, info);
+    rc = dispatch(a->method, a->rhs, a->events, P, mi, st, info);
     if (slots) cudaFreeAsync(slots, st);
     cudaError_t e = cudaFreeAsync(scratch, st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
@@ -505,6 +535,13 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d.status = (int32_t*)dalloc((size_t)N * ni);
     d.n_eval_done = h->n_eval_done ? (int32_t*)dalloc((size_t)N * ni) : nullptr;
     d.stiff_flags = h->stiff_flags ? (int32_t*)dalloc((size_t)N * ni) : nullptr;
+    const size_t nev = h->events ? (size_t)N * (size_t)h->n_event_fns : 0;
+    const size_t nrec = nev * (size_t)(h->ev_capacity > 0 ? h->ev_capacity : 0);
+    if (h->events) {
+        d.t_events = (double*)dalloc(nrec * nd);
+        d.y_events = (double*)dalloc(nrec * ns * nd);
+        d.ev_count = (int32_t*)dalloc(nev * ni);
+    }
     if (rc == XSQ_OK) rc = solve_device(&d, st, nullptr);
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
         if (rc == XSQ_OK && dst && bytes)
@@ -525,6 +562,11 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d2h(h->status, d.status, (size_t)N * ni);
     if (h->n_eval_done) d2h(h->n_eval_done, d.n_eval_done, (size_t)N * ni);
     if (h->stiff_flags) d2h(h->stiff_flags, d.stiff_flags, (size_t)N * ni);
+    if (h->events) {
+        d2h(h->t_events, d.t_events, nrec * nd);
+        d2h(h->y_events, d.y_events, nrec * ns * nd);
+        d2h(h->ev_count, d.ev_count, nev * ni);
+    }
     for (void* p : owned) cudaFreeAsync(p, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaStreamDestroy(st);

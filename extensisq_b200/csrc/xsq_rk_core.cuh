@@ -43,7 +43,8 @@ static constexpr double kMaxFactor0 = 10.0;     // common.py:20
 enum LaneStatus : int {
     LANE_FINISHED = 0, LANE_TOO_SMALL = -1, LANE_OVERFLOW = -2,
     LANE_STEP_BUDGET = -5, LANE_RUNNING = 1,
-    LANE_FLUSH = 2      // internal: still running, stiffness probe slots are full
+    LANE_FLUSH = 2,     // internal: still running, stiffness probe slots are full
+    LANE_EVENT = 3      // internal: a terminal event ended the trajectory (status 1)
 };
 #ifndef XSQ_MAX_BLOCK
 #define XSQ_MAX_BLOCK 256   // largest CTA any rk_persistent geometry launches
@@ -94,6 +95,13 @@ struct RkDev {
     double* stiff_q;
     long long stiff_q_cap;                  // records; 0 = no queue
     unsigned long long* stiff_q_count;      // may run past stiff_q_cap
+    // events (scipy solve_ivp `events=`; only kernels built with XSQ_EVENTS_N)
+    int n_events, ev_capacity;
+    int ev_terminal[8];           // 0: never; k: stop at the k-th occurrence
+    int ev_direction[8];          // -1, 0, +1
+    double* t_events;             // [n_lanes][n_events][ev_capacity]
+    double* y_events;             // [n_lanes][n_events][ev_capacity][n_state]
+    int* ev_count;                // [n_lanes][n_events]
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -707,6 +715,10 @@ struct Lane {
     }
     bool standard_sc, fresh, step_rejected;
     double ck_tw[2], ck_q[2];      // CKdisc's twiddle / quit factors (cash.py:241-243)
+#ifdef XSQ_EVENTS_N
+    double ev_g[XSQ_EVENTS_N];     // event function values at (t, y)  (ivp.py `g`)
+    int ev_n[XSQ_EVENTS_N];        // occurrences so far               (`event_count`)
+#endif
 
     // RungeKutta.__init__, common.py:187-220
     __device__ __forceinline__ void init(const RkDev& P, long long idx,
@@ -739,6 +751,13 @@ struct Lane {
         ck_tw[0] = 1.5;
         ck_tw[1] = 1.1;
         ck_q[0] = ck_q[1] = 100.0;
+#ifdef XSQ_EVENTS_N
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            ev_g[k] = user_event(k, t, y, prm);        // g = [event(t0, y0)]
+            ev_n[k] = 0;
+        }
+#endif
         // first step: forced table, first_step, or Watts' h_start (ens_init)
         if (P.n_forced > 0) h_abs = P.h_forced[0];
         else if (P.first_step > 0.0) h_abs = P.first_step;
@@ -1006,6 +1025,218 @@ struct Lane {
         }
     }
 
+#ifdef XSQ_EVENTS_N
+    // ---- events: scipy's solve_ivp loop (ivp.py) on the device ---------------
+    // The dense output of the step just accepted ("sol = solver.dense_output()"),
+    // formed once per step and evaluated wherever the root finder asks.
+    struct Dense {
+        static constexpr int NQ = (Tab::VARIANT == tab::BS5V) ? 6
+                                : (Tab::NPOL > 0 ? Tab::NPOL : 1);
+        double Q[NQ][NL];
+        double t_anchor, h_anchor;
+        int npol;
+        bool anchor_end, cubic, built;
+    };
+    __device__ void dense_build(const RkDev& P, Dense& D, double (&K)[KROWS][NL], double h,
+                                double t_new, const double (&y_new)[NL], bool cubic) {
+        D.built = true;
+        D.cubic = cubic || Tab::NPOL == 0;
+        D.npol = Tab::NPOL;
+        D.t_anchor = t;
+        D.h_anchor = t_new - t;
+        D.anchor_end = false;
+        if (D.cubic) return;
+        if constexpr (Tab::VARIANT == tab::BS5V) {
+            if (P.interpolant == IP_FREE) {
+                form_q_free(K, D.Q);
+            } else if (P.interpolant == IP_LOW) {
+                bs5_low(K, D.Q, h);
+                D.npol = Tab::NPOL_LOW;
+            } else {
+                bs5_best(K, D.Q, h, y_new);
+                D.npol = Tab::NPOL_BEST;
+                D.anchor_end = true;
+                D.t_anchor = t_new;
+                D.h_anchor = (t_new + h) - t_new;
+            }
+        } else {
+            form_q_free(K, D.Q);
+        }
+#pragma unroll
+        for (int k = 0; k < Dense::NQ; ++k)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) D.Q[k][c] *= D.h_anchor;
+    }
+    // sol(te): HornerDenseOutput / CubicDenseOutput, common.py:766-821
+    __device__ void dense_eval(const Dense& D, double (&K)[KROWS][NL], double t_new,
+                               const double (&y_new)[NL], double te, double (&out)[NL]) {
+        if (D.cubic) {
+            const double hh = t_new - t;
+            const double x = (te - t) / hh;
+            const double omx = 1.0 - x;
+            const double h00 = (1.0 + 2.0 * x) * (omx * omx);
+            const double h10 = x * (omx * omx) * hh;
+            const double h01 = (x * x) * (3.0 - 2.0 * x);
+            const double h11 = (x * x) * (x - 1.0) * hh;
+#pragma unroll
+            for (int c = 0; c < NL; ++c)
+                out[c] = ((h00 * y[c] + h10 * K[0][c]) + h01 * y_new[c]) + h11 * K[S][c];
+            return;
+        }
+        const double x = (te - D.t_anchor) / D.h_anchor;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = Dense::NQ - 1; k >= 0; --k) {
+                if (k < D.npol) v = (k == D.npol - 1) ? D.Q[k][c] * x : (v + D.Q[k][c]) * x;
+            }
+            out[c] = v + (D.anchor_end ? y_new[c] : y[c]);
+        }
+    }
+    // scipy/optimize/Zeros/brentq.c with xtol = rtol = 4 eps, 100 iterations,
+    // on  tt -> event(k, tt, sol(tt))   (ivp.py solve_event_equation)
+    __device__ double event_root(const Dense& D, double (&K)[KROWS][NL], double t_new,
+                                 const double (&y_new)[NL], int k, double g_old, double g_new) {
+        const double tol = 4.0 * 0x1.0p-52;
+        double xpre = t, xcur = t_new;
+        double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+        double ytmp[NL];
+        // f(t_old) and f(t) through the interpolant, as brentq evaluates them
+        dense_eval(D, K, t_new, y_new, xpre, ytmp);
+        double fpre = user_event(k, xpre, ytmp, prm);
+        dense_eval(D, K, t_new, y_new, xcur, ytmp);
+        double fcur = user_event(k, xcur, ytmp, prm);
+        (void)g_old; (void)g_new;
+        if (fpre == 0.0) return xpre;
+        if (fcur == 0.0) return xcur;
+        auto neg = [](double v) { return __double2hiint(v) < 0; };
+        if (neg(fpre) == neg(fcur)) return xcur;     // scipy raises; cannot happen after
+                                                     // find_active_events up to rounding
+        for (int it = 0; it < 100; ++it) {
+            if (fpre != 0.0 && fcur != 0.0 && neg(fpre) != neg(fcur)) {
+                xblk = xpre;
+                fblk = fpre;
+                spre = scur = xcur - xpre;
+            }
+            if (fabs(fblk) < fabs(fcur)) {
+                xpre = xcur; xcur = xblk; xblk = xpre;
+                fpre = fcur; fcur = fblk; fblk = fpre;
+            }
+            const double delta = (tol + tol * fabs(xcur)) / 2;
+            const double sbis = (xblk - xcur) / 2;
+            if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+            if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+                double stry;
+                if (xpre == xblk) {
+                    stry = -fcur * (xcur - xpre) / (fcur - fpre);
+                } else {
+                    const double dpre = (fpre - fcur) / (xpre - xcur);
+                    const double dblk = (fblk - fcur) / (xblk - xcur);
+                    stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+                }
+                if (2 * fabs(stry) < pymin(fabs(spre), 3 * fabs(sbis) - delta)) {
+                    spre = scur;
+                    scur = stry;
+                } else {
+                    spre = sbis;
+                    scur = sbis;
+                }
+            } else {
+                spre = sbis;
+                scur = sbis;
+            }
+            xpre = xcur;
+            fpre = fcur;
+            if (fabs(scur) > delta) xcur += scur;
+            else xcur += (sbis > 0 ? delta : -delta);
+            dense_eval(D, K, t_new, y_new, xcur, ytmp);
+            fcur = user_event(k, xcur, ytmp, prm);
+        }
+        return xcur;
+    }
+    // Everything solve_ivp does after solver.step() returned (ivp.py): events,
+    // then the t_eval points of the step.  Returns true when a terminal event
+    // ends the trajectory; t_new / y_new are then the event point.
+    __device__ bool after_step(const RkDev& P, double (&K)[KROWS][NL], double h, double& t_new,
+                               double (&y_new)[NL], int lane, bool cubic) {
+        Dense D;
+        D.built = false;
+        double g_new[XSQ_EVENTS_N], root[XSQ_EVENTS_N];
+        unsigned active = 0;
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            g_new[k] = user_event(k, t_new, y_new, prm);
+            const bool up = ev_g[k] <= 0.0 && g_new[k] >= 0.0;      // find_active_events
+            const bool down = ev_g[k] >= 0.0 && g_new[k] <= 0.0;
+            const int d = P.ev_direction[k];
+            if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) active |= 1u << k;
+        }
+        bool terminate = false;
+        double t_stop = t_new;
+        if (active) {
+            dense_build(P, D, K, h, t_new, y_new, cubic);
+            bool any_term = false;
+            double r_star = 0.0;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                ++ev_n[k];
+                root[k] = event_root(D, K, t_new, y_new, k, ev_g[k], g_new[k]);
+                if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
+                    // handle_events: the first terminal root in time order
+                    if (!any_term || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
+                    any_term = true;
+                }
+            }
+            terminate = any_term;
+            if (terminate) t_stop = r_star;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                if (terminate && P.direction * (root[k] - r_star) > 0.0) continue;   // after the stop
+                const int slot = ev_n[k] - 1;
+                if (slot < P.ev_capacity) {
+                    const long long base = (sys * XSQ_EVENTS_N + k) * P.ev_capacity + slot;
+                    double ye[NL];
+                    dense_eval(D, K, t_new, y_new, root[k], ye);
+                    P.t_events[base] = root[k];
+#pragma unroll
+                    for (int c = 0; c < NL; ++c) P.y_events[base * NL + c] = ye[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_g[k] = g_new[k];
+        // the t_eval points of (t_old, t] -- up to the event when it is terminal
+        if (P.n_eval > 0 && ieval < P.n_eval &&
+            P.direction * (P.t_eval[ieval] - t_stop) <= 0.0) {
+            if (!D.built) dense_build(P, D, K, h, t_new, y_new, cubic);
+            double te = P.t_eval[ieval];
+            do {
+                double out[NL];
+                dense_eval(D, K, t_new, y_new, te, out);
+                eval_put<R>(P, sys, lane, ieval, out);
+                ++ieval;
+                if (ieval >= P.n_eval) break;
+                te = P.t_eval[ieval];
+            } while (P.direction * (te - t_stop) <= 0.0);
+        }
+        if (terminate) {
+            double ys[NL];
+            dense_eval(D, K, t_new, y_new, t_stop, ys);          // y = sol(t)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) y_new[c] = ys[c];
+            t_new = t_stop;
+        }
+        return terminate;
+    }
+    __device__ void store_event_counts(const RkDev& P) {
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) P.ev_count[sys * XSQ_EVENTS_N + k] = ev_n[k];
+    }
+#endif
+
     // One ATTEMPT of a step (the body of `while not step_accepted`,
     // common.py:232-287).  Returns the lane status: LANE_RUNNING, or a final
     // code when the trajectory ends here.
@@ -1153,17 +1384,25 @@ struct Lane {
         const double t_new = t + h;
         R::f(t_new, y_new, prm, K[S]);
         ++nfev;
+#ifdef XSQ_EVENTS_N
+        double t_end = t_new;
+        const bool ev_stop = after_step(P, K, h, t_end, y_new, lane, accepted != 4);
+#else
+        const double t_end = t_new;
+        const bool ev_stop = false;
         if (!FAST && P.n_eval > 0 && ieval < P.n_eval &&
             P.direction * (P.t_eval[ieval] - t_new) <= 0.0) {
             // cash.py:406-416: Horner for the fifth order solution, else cubic
             if (accepted == 4) emit_poly(P, K, h, t_new, y_new, lane);
             else emit_cubic(P, K, t_new, y_new, lane);
         }
-        t = t_new;
+#endif
+        t = t_end;
 #pragma unroll
         for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
         ++n_acc;
         fresh = true;
+        if (ev_stop) return LANE_EVENT;
         if (P.direction * (t - P.t_bound) >= 0.0) return LANE_FINISHED;
         return (n_acc + n_rej >= P.max_steps) ? LANE_STEP_BUDGET : LANE_RUNNING;
     }
@@ -1312,15 +1551,23 @@ struct Lane {
         }
         standard_sc = tiny_err;
         if (factor < kMaxFactor) max_factor = kMaxFactor;
+#ifdef XSQ_EVENTS_N
+        double t_end = t_new;
+        const bool ev_stop = after_step(P, K, h, t_end, y_new, lane, false);
+#else
+        const double t_end = t_new;
+        const bool ev_stop = false;
         if (!FAST && P.n_eval > 0) emit(P, K, h, t_new, y_new, lane);
+#endif
         // common.py:294-303
         h_prev = h;
         lerr_old = lerr;
-        t = t_new;
+        t = t_end;
 #pragma unroll
         for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
         ++n_acc;
         fresh = true;
+        if (ev_stop) return LANE_EVENT;
         // OdeSolver.step, base.py:207-208
         const bool done = forced ? (n_acc >= P.n_forced)
                                  : (P.direction * (t - P.t_bound) >= 0.0);
@@ -1464,7 +1711,10 @@ struct Lane {
             P.n_acc[sys] = n_acc;
             P.n_rej[sys] = n_rej;
             P.nfev[sys] = nfev + evals_in_loop();
-            P.status[sys] = st;
+            P.status[sys] = st == LANE_EVENT ? 1 : st;    // 1: a termination event occurred
+#ifdef XSQ_EVENTS_N
+            store_event_counts(P);
+#endif
             if (P.n_eval_done) P.n_eval_done[sys] = ieval;
             if (P.stiff_flags) P.stiff_flags[sys] =
                     (int)((stiff_state().bits[threadIdx.x] >> SB_FLAG_SHIFT) & 7u);

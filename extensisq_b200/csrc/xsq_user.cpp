@@ -40,6 +40,11 @@ struct UserRhs {
     int n_state, n_param;
 };
 std::vector<UserRhs> g_rhs;               // handle = XSQ_RHS_USER_BASE + index
+struct UserEvents {
+    std::string src, entry;
+    int n;
+};
+std::vector<UserEvents> g_events;         // handle = index + 1
 
 struct UserTab {
     bool loaded = false;
@@ -358,8 +363,23 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
 
 // Build the translation unit for (method, rhs); exposed for the CPU-side test
 // that NVRTC accepts it (no device needed to compile).
-int user_build_source(int method, int rhs, std::string* src, std::string* key) {
-    std::string tabname, rhsname, body = "#include \"xsq_rk_core.cuh\"\n";
+int user_build_source(int method, int rhs, int events, std::string* src, std::string* key) {
+    std::string tabname, rhsname, body;
+    if (events != 0) {
+        // scipy's `events=`: the functions are device code too; the core header
+        // compiles its event machinery in when XSQ_EVENTS_N is defined
+        if (events < 1 || (size_t)events > g_events.size()) {
+            set_detail("unknown events handle");
+            return XSQ_ERR_ARG;
+        }
+        const UserEvents& e = g_events[(size_t)events - 1];
+        body += "#define XSQ_EVENTS_N " + std::to_string(e.n) + "\n"
+                "__device__ double " + e.entry + "(int, double, const double*, const double*);\n"
+                "namespace xsq { __device__ __forceinline__ double user_event(int k, double t,\n"
+                "    const double* y, const double* p) { return ::" + e.entry + "(k, t, y, p); } }\n";
+    }
+    body += "#include \"xsq_rk_core.cuh\"\n";
+    if (events != 0) body += g_events[(size_t)events - 1].src + "\n";
     int s = 0, nl = 0;
     const bool swag = method == XSQ_METHOD_SWAG;
     if (swag) {
@@ -424,6 +444,7 @@ int user_build_source(int method, int rhs, std::string* src, std::string* key) {
                       "    xsq::stiff_queue_body<xsq::rhs::%s>(P, cost, stbrad, tanang);\n}\n",
                       rhsname.c_str());
     *src = body + buf + buf2 + buf3;
+    if (events != 0) *key += "/E" + std::to_string(events);
     return XSQ_OK;
 }
 
@@ -447,11 +468,17 @@ bool user_rhs_shape(int rhs, int* n_state, int* n_param) {
     return true;
 }
 
-int user_rk_launch(int method, int rhs, const RkDev& P, int cost, double stbrad,
+int user_events_count(int events) {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (events < 1 || (size_t)events > g_events.size()) return -1;
+    return g_events[(size_t)events - 1].n;
+}
+
+int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, double stbrad,
                    double tanang, cudaStream_t st) {
     std::lock_guard<std::mutex> g(g_mu);
     std::string src, key;
-    int rc = user_build_source(method, rhs, &src, &key);
+    int rc = user_build_source(method, rhs, events, &src, &key);
     if (rc != XSQ_OK) return rc;
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
@@ -580,10 +607,26 @@ int xsq_pde_register_source(const char* cuda_src, const char* entry, int32_t n_p
 
 /* Compile-only probe (no device needed): does NVRTC accept the translation
  * unit for (method, rhs)?  Used by the CPU-side tests. */
+int xsq_events_register_source(const char* cuda_src, const char* entry, int32_t n_events,
+                               int32_t* handle_out) {
+    if (!cuda_src || !entry || !handle_out || n_events < 1 || n_events > XSQ_MAX_EVENTS) {
+        set_detail("xsq_events_register_source: bad argument (1 <= n_events <= 8)");
+        return XSQ_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    g_events.push_back(UserEvents{cuda_src, entry, n_events});
+    *handle_out = (int32_t)g_events.size();
+    return XSQ_OK;
+}
+
 int xsq_user_compile_check(int32_t method, int32_t rhs) {
+    return xsq_events_compile_check(method, rhs, 0);
+}
+
+int xsq_events_compile_check(int32_t method, int32_t rhs, int32_t events) {
     std::lock_guard<std::mutex> g(g_mu);
     std::string src, key;
-    int rc = user_build_source(method, rhs, &src, &key);
+    int rc = user_build_source(method, rhs, events, &src, &key);
     if (rc != XSQ_OK) return rc;
     if (!load_nvrtc()) return XSQ_ERR_NVRTC;
     nvrtcProgram prog;

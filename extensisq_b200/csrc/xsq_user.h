@@ -18,8 +18,10 @@ void count_launch();
 
 bool user_tableau_info(MethodInfo* mi);
 bool user_rhs_shape(int rhs, int* n_state, int* n_param);
-int user_rk_launch(int method, int rhs, const RkDev& P, int cost, double stbrad,
+int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, double stbrad,
                    double tanang, cudaStream_t st);
+// number of event functions behind an events handle, -1 if unknown
+int user_events_count(int events);
 // user PDE for SSV2stab: CUfunctions (as void*) of the eval / stage / final kernels
 int user_pde_kernels(int pde, void* fn[3], int* n_param);
 int user_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** args,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XSQ_ABI_VERSION 1
+#define XSQ_ABI_VERSION 2
 #define XSQ_MAX_STAGES 18      /* Pr9: n_stages=17, +1 row for f(t+h, y_new) */
 #define XSQ_MAX_POLY 8         /* Pr9 interpolant has 8 columns             */
 #define XSQ_MAX_LANE_STATE 16  /* lane-per-system kernels: n_state <= 16    */
@@ -45,6 +45,8 @@ typedef enum xsq_err {
 /* per-lane status[] codes */
 typedef enum xsq_lane_status {
     XSQ_LANE_FINISHED = 0,
+    XSQ_LANE_EVENT = 1,           /* "A termination event occurred." (scipy
+                                     solve_ivp status 1)                       */
     XSQ_LANE_STEP_TOO_SMALL = -1, /* OdeSolver.TOO_SMALL_STEP, common.py:234   */
     XSQ_LANE_OVERFLOW = -2,       /* "Overflow or underflow", common.py:286    */
     XSQ_LANE_TOL_TOO_TIGHT = -3,  /* SWAG, shampine.py:235-238                 */
@@ -152,6 +154,21 @@ typedef struct xsq_rk_args {
                                  0 = off; the reference's default is 5000   */
     int32_t reserved1;
     int32_t* stiff_flags;     /* [n_lanes] OR of xsq_stiff_flag, may be NULL  */
+    /* events: scipy solve_ivp(events=...) on the device -- find_active_events,
+     * handle_events, solve_event_equation (scipy/integrate/_ivp/ivp.py) and
+     * brentq (scipy/optimize/Zeros/brentq.c), evaluated on the method's own
+     * dense output.  Not for SWAG, forced steps or XSQ_RHS_NBODY32. */
+    int32_t events;           /* handle of xsq_events_register_source, 0 = none */
+    int32_t n_event_fns;      /* must equal the handle's n_events               */
+    const int32_t* ev_terminal;  /* HOST [n_event_fns]: 0 never terminal, k > 0
+                                    stop at the k-th occurrence (event.terminal) */
+    const int32_t* ev_direction; /* HOST [n_event_fns]: -1, 0, +1 (event.direction) */
+    int32_t ev_capacity;      /* records kept per event function and lane       */
+    int32_t reserved2;
+    double* t_events;         /* [n_lanes][n_event_fns][ev_capacity]            */
+    double* y_events;         /* [n_lanes][n_event_fns][ev_capacity][n_state]   */
+    int32_t* ev_count;        /* [n_lanes][n_event_fns] occurrences found (can
+                                 exceed ev_capacity: later ones are not kept)   */
 } xsq_rk_args_t;
 
 int xsq_abi_version(void);
@@ -188,6 +205,17 @@ int xsq_rhs_register_source(const char* cuda_src, const char* entry,
 /* Compile-only probe: does NVRTC accept the specialised kernel for
  * (method, rhs)?  Needs libnvrtc but no device. */
 int xsq_user_compile_check(int32_t method, int32_t rhs);
+
+/* Event functions (the `events=` argument of scipy's solve_ivp, ivp.py) as
+ * CUDA source defining
+ *     __device__ double <entry>(int k, double t, const double* y, const double* p)
+ * for k = 0 .. n_events-1; terminal / direction attributes travel in
+ * xsq_rk_args_t.  The kernel for (method, rhs, events) is compiled with NVRTC
+ * on first use. */
+#define XSQ_MAX_EVENTS 8
+int xsq_events_register_source(const char* cuda_src, const char* entry, int32_t n_events,
+                               int32_t* handle_out);
+int xsq_events_compile_check(int32_t method, int32_t rhs, int32_t events);
 
 /* Batched adaptive explicit RK solve, device buffers, asynchronous. */
 int xsq_rk_solve(const xsq_rk_args_t* args, void* stream);

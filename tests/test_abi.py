@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libxsq.so does not export {s}"
     assert set(_lib.EXPORTS) == set(syms)
-    assert lib.xsq_abi_version() == 1
+    assert lib.xsq_abi_version() == 2
 
 
 def test_struct_sizes_match_the_c_header(tmp_path):
@@ -121,3 +121,21 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt
                 assert "libxsq_oracle" not in txt
+
+
+def test_event_kernels_compile_for_sm100a():
+    """NVRTC accepts the (method, rhs, events) translation units (no device
+    needed): the event machinery of xsq_rk_core.cuh behind XSQ_EVENTS_N."""
+    import ctypes as C
+    from extensisq_b200 import _lib
+    from oracle.problems import EVENT_SETS
+    lib = _lib.load()
+    py, src = EVENT_SETS["lorenz_sections"]
+    h = C.c_int32()
+    assert lib.xsq_events_register_source(src.encode(), b"event", len(py), C.byref(h)) == 0
+    for method in (_lib.METHOD_IDS["Ts5"], _lib.METHOD_IDS["BS5"], _lib.METHOD_IDS["CKdisc"]):
+        rc = lib.xsq_events_compile_check(method, 0, h.value)
+        if rc == -4 and b"libnvrtc" in lib.xsq_last_error_detail():
+            pytest.skip("libnvrtc not available")
+        assert rc == 0, lib.xsq_last_error_detail().decode()
+    assert lib.xsq_events_register_source(src.encode(), b"event", 9, C.byref(h)) == -1

@@ -1,0 +1,136 @@
+"""GPU parity of event detection (scipy's solve_ivp `events=` on the device;
+SURVEY.md section 8f rank 3), through the C ABI, against the golden vectors
+of the reference + scipy and the NumPy restatement on seeded ensembles."""
+import numpy as np
+import pytest
+import torch
+
+import extensisq_b200 as xb
+from oracle import rk_oracle as RO
+from oracle.problems import CUDA_SOURCES, EVENT_SETS, make_fun
+from test_events_golden import CASES, TABS, ev_list, ev_options, ev_t_eval, unhex
+
+pytestmark = pytest.mark.gpu
+BUILTIN_PROBLEMS = {"lorenz63", "vanderpol", "arenstorf"}
+_RHS, _EV = {}, {}
+
+
+def rhs_for(problem):
+    if problem in BUILTIN_PROBLEMS:
+        return problem
+    if problem not in _RHS:
+        n, p, src = CUDA_SOURCES[problem]
+        _RHS[problem] = xb.DeviceRHS.from_source(src, "rhs", n, p)
+    return _RHS[problem]
+
+
+def events_for(name, terminal, direction):
+    if name not in _EV:
+        py, src = EVENT_SETS[name]
+        _EV[name] = xb.DeviceEvents.from_source(src, "event", len(py))
+    return _EV[name].with_attributes(terminal=terminal, direction=direction)
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c["id"])
+def test_events_vs_reference_golden(c):
+    o = ev_options(c)
+    te = ev_t_eval(c)
+    ev = events_for(c["events"], c["terminal"], c["direction"])
+    r = xb.solve_ivp_batched(rhs_for(c["problem"]), c["t_span"], [c["y0"]],
+                             getattr(xb, c["method"]),
+                             params=[c["params"]] if c["params"] else None, t_eval=te,
+                             events=ev, max_event_records=32, max_steps=100000, **o)
+    torch.cuda.synchronize()
+    assert int(r.status[0]) == c["status"]
+    rtol = o.get("rtol", 1e-3)
+    # the step sequence is the reference's (same counts), so event times agree
+    # to rounding amplified by the root finder's conditioning, far below rtol
+    assert int(r.nfev[0]) == c["nfev"] and int(r.n_rejected[0]) == c["nfs"]
+    tol = 1e-9
+    cnt = r.event_counts.cpu().numpy()[0]
+    t_ev = r.t_events.cpu().numpy()[0]
+    y_ev = r.y_events.cpu().numpy()[0]
+    for k in range(len(c["terminal"])):
+        tg = unhex(c["t_events"][k])
+        yg = unhex(c["y_events"][k])
+        if c["status"] == 0:
+            assert cnt[k] == tg.size, (k, cnt[k], tg.size)
+        # after a terminal stop scipy drops the roots behind it; the count keeps them
+        assert cnt[k] >= tg.size
+        assert np.allclose(t_ev[k, :tg.size], tg, rtol=tol, atol=tol), (k, t_ev[k, :tg.size], tg)
+        if tg.size:
+            assert np.allclose(y_ev[k, :tg.size], yg.reshape(tg.size, -1), rtol=1e-8, atol=1e-8)
+        if c["status"] == 0:
+            assert np.isnan(t_ev[k, tg.size:]).all()
+    t_g, y_g = unhex(c["t"]), unhex(c["y"])
+    if te is None:
+        assert abs(float(r.t_final[0]) - t_g[-1]) <= tol * max(1.0, abs(t_g[-1]))
+        assert np.allclose(r.y_final.cpu().numpy()[0], y_g[:, -1], rtol=1e-8, atol=1e-8)
+    else:
+        # t_eval output stops at the terminal event (ivp.py: t = roots[-1])
+        assert int(r.n_eval_done[0]) == t_g.size
+        y = r.y.cpu().numpy()[0][:, :t_g.size]
+        assert np.allclose(y, y_g.reshape(y.shape), rtol=1e-8, atol=1e-8)
+    assert rtol > 0
+
+
+def test_events_ensemble_poincare_section_vs_oracle():
+    """48 Lorenz lanes, upward crossings of z = 27 (non-terminal) and the 4th
+    zero of x (terminal): per-lane counts, times and states."""
+    N = 48
+    rng = np.random.default_rng(5)
+    y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+    prm = np.tile([10.0, 28.0, 8.0 / 3.0], (N, 1))
+    kw = dict(rtol=1e-7, atol=1e-9)
+    term, direc = [0, 4, 0], [1, 0, -1]
+    ev = events_for("lorenz_sections", term, direc)
+    r = xb.solve_ivp_batched("lorenz63", (0.0, 6.0), y0, xb.Ts5, params=prm, events=ev,
+                             max_event_records=32, **kw)
+    torch.cuda.synchronize()
+    cnt = r.event_counts.cpu().numpy()
+    t_ev = r.t_events.cpu().numpy()
+    status = r.status.cpu().numpy()
+    fns = EVENT_SETS["lorenz_sections"][0]
+    same = 0
+    for i in range(N):
+        o = RO.rk_solve(TABS["Ts5"], make_fun("lorenz63", prm[i]), (0.0, 6.0), y0[i],
+                        events=[(g, a, b) for g, a, b in zip(fns, term, direc)], **kw)
+        assert status[i] == o["status"]
+        if int(r.nfev[i]) != o["nfev"]:
+            continue                     # a flipped accept/reject decision (chaotic system)
+        same += 1
+        for k in range(3):
+            tg = o["t_events"][k]
+            assert cnt[i, k] >= tg.size
+            assert np.allclose(t_ev[i, k, :tg.size], tg, rtol=1e-8, atol=1e-8)
+        assert abs(float(r.t_final[i]) - o["t_final"]) <= 1e-8
+        assert np.allclose(r.y_final[i].cpu().numpy(), o["y_final"], rtol=1e-6, atol=1e-6)
+    assert same >= 0.9 * N
+    assert (status == 1).any() and (cnt[:, 0] > 0).all()
+
+
+def test_events_leave_the_trajectory_untouched_and_validate_arguments():
+    N = 256
+    rng = np.random.default_rng(1)
+    y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+    prm = np.tile([10.0, 28.0, 8.0 / 3.0], (N, 1))
+    kw = dict(params=prm, rtol=1e-6, atol=1e-9)
+    ev = events_for("lorenz_sections", [0, 0, 0], [0, 0, 0])
+    a = xb.solve_ivp_batched("lorenz63", (0.0, 3.0), y0, xb.Pr8, events=ev, **kw)
+    b = xb.solve_ivp_batched("lorenz63", (0.0, 3.0), y0, xb.Pr8, **kw)
+    torch.cuda.synchronize()
+    # (the kernel with events is compiled at run time by NVRTC, the other one
+    # by nvcc: same source and flags, not necessarily the same schedule)
+    assert torch.equal(a.nfev, b.nfev) and torch.equal(a.n_rejected, b.n_rejected)
+    assert torch.allclose(a.y_final, b.y_final, rtol=1e-9, atol=1e-9)
+    assert (a.status == 0).all() and (a.event_counts.sum(1) > 0).all()
+    # more occurrences than records: counted, the first `capacity` are kept
+    c = xb.solve_ivp_batched("lorenz63", (0.0, 3.0), y0, xb.Pr8, events=ev,
+                             max_event_records=2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(c.event_counts, a.event_counts)
+    assert torch.equal(c.t_events[:, :, :2].nan_to_num(-1.0), a.t_events[:, :, :2].nan_to_num(-1.0))
+    with pytest.raises(ValueError):
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.SWAG, events=ev, **kw)
+    with pytest.raises(ValueError):
+        xb.DeviceEvents.from_source("x", "event", 2, terminal=[-1, 0])
