@@ -10,12 +10,13 @@ from .tableaux import (RungeKutta, Ts5, BS5, CK5, CKdisc, Me4, Pr7, Pr8, Pr9,
 from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, solve_ivp_batched, NFS,
                       update_nfs)
 from .sharding import shard_bounds, gather_result
+from .sensitivity import sens_forward, SensitivityOutput
 from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
                   nfesig, maxm)
 
 __version__ = "0.1.0"
 __all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "CKdisc", "Me4", "Pr7", "Pr8", "Pr9",
            "CFMR7osc", "SWAG", "DeviceRHS", "DeviceEvents", "BatchedOdeResult", "solve_ivp_batched",
-           "NFS", "update_nfs", "shard_bounds", "gather_result", "SSV2stab",
+           "NFS", "update_nfs", "shard_bounds", "gather_result", "sens_forward", "SensitivityOutput", "SSV2stab",
            "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc", "slab_of", "nfesig",
            "maxm"]
