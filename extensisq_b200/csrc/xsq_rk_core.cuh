@@ -674,6 +674,13 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
     return stiff_probe_impl<R, true>(slot, stride, xend, maxfcn, cost, stbrad, tanang);
 }
 
+template <bool ON>
+struct CkExtra {
+    double tw[2], q[2];
+};
+template <>
+struct CkExtra<false> {};
+
 // ---- one trajectory ---------------------------------------------------------
 template <class Tab, class R>
 struct Lane {
@@ -714,7 +721,10 @@ struct Lane {
         return s;
     }
     bool standard_sc, fresh, step_rejected;
-    double ck_tw[2], ck_q[2];      // CKdisc's twiddle / quit factors (cash.py:241-243)
+    // CKdisc's twiddle / quit factors (cash.py:241-243).  An empty member for
+    // every other method: the lane is copied as a whole around the stiffness
+    // probes, so an unused member would still cost its registers.
+    CkExtra<Tab::VARIANT == tab::CKDISCV> ck;
 #ifdef XSQ_EVENTS_N
     double ev_g[XSQ_EVENTS_N];     // event function values at (t, y)  (ivp.py `g`)
     int ev_n[XSQ_EVENTS_N];        // occurrences so far               (`event_count`)
@@ -748,9 +758,11 @@ struct Lane {
         h_prev = 0.0;
         lerr_old = 0.0;
         min_step = 0.0;
-        ck_tw[0] = 1.5;
-        ck_tw[1] = 1.1;
-        ck_q[0] = ck_q[1] = 100.0;
+        if constexpr (Tab::VARIANT == tab::CKDISCV) {
+            ck.tw[0] = 1.5;
+            ck.tw[1] = 1.1;
+            ck.q[0] = ck.q[1] = 100.0;
+        }
 #ifdef XSQ_EVENTS_N
 #pragma unroll
         for (int k = 0; k < XSQ_EVENTS_N; ++k) {
@@ -1311,17 +1323,17 @@ struct Lane {
         ++nfev;
         // first order error, second order solution (cash.py:266-270)
         const double E1 = ck_root(P, ck_solution<0>(P, K, h, y_new, lane), 0.25);
-        double esttol = E1 / ck_q[0];
+        double esttol = E1 / ck.q[0];
         int accepted = 0;
         bool retried = false;
-        if (E1 < ck_tw[0] * ck_q[0]) {
+        if (E1 < ck.tw[0] * ck.q[0]) {
             stage<2>(K, h);
             stage<3>(K, h);
             nfev += 2;
             // second order error, third order solution (cash.py:278-282)
             const double E2 = ck_root(P, ck_solution<1>(P, K, h, y_new, lane), 1.0 / 6.0);
-            esttol = E2 / ck_q[1];
-            if (E2 < ck_tw[1] * ck_q[1]) {
+            esttol = E2 / ck.q[1];
+            if (E2 < ck.tw[1] * ck.q[1]) {
                 stage<4>(K, h);
                 stage<5>(K, h);
                 nfev += 2;
@@ -1337,17 +1349,17 @@ struct Lane {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         double q = e12[j] / E4;
-                        if (q > ck_q[j]) q = pymin(q, 10 * ck_q[j]);
-                        else q = pymax(q, 2.0 / 3.0 * ck_q[j]);
-                        ck_q[j] = pymax(1.0, pymin(10000.0, q));
+                        if (q > ck.q[j]) q = pymin(q, 10 * ck.q[j]);
+                        else q = pymax(q, 2.0 / 3.0 * ck.q[j]);
+                        ck.q[j] = pymax(1.0, pymin(10000.0, q));
                     }
                 } else {
                     if (!(E4 < XSQ_INF)) return LANE_OVERFLOW;    // cash.py:320-321
                     const double e12[2] = {E1, E2};               // cash.py:324-328
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const double EQ = e12[i] / ck_q[i];
-                        if (EQ < ck_tw[i]) ck_tw[i] = pymax(1.1, EQ);
+                        const double EQ = e12[i] / ck.q[i];
+                        if (EQ < ck.tw[i]) ck.tw[i] = pymax(1.1, EQ);
                     }
                     // third order fallback over 3/5 of the step (cash.py:331-341)
                     if (E2 < 1.0 && ck_solution<3>(P, K, h, y_new, lane) < NTOT) {
