@@ -144,22 +144,23 @@ __device__ __forceinline__ double pymin(double a, double b) { return b < a ? b :
 // error_norm ** x  (common.py:257, 264-266, 281) is evaluated as
 // exp2(x * log2(error_norm)).  |x| <= 0.25, so plain double-precision log2 and
 // exp2 (each ~1 ulp) give the factor to ~2 ulp, the accuracy class of pow().
+// (16-byte aligned: see tools/gen_header.py)
 // Coefficients sit in __constant__ memory so each one is a c[bank][offset]
 // operand of its DFMA.  Rare inputs (0, subnormal, Inf, NaN, |z| >= 1000) take
 // the libdevice routines.
-static __constant__ double c_xsq_lg[7] = {   // fdlibm e_log.c Lg1..Lg7
+static __constant__ __align__(16) double c_xsq_lg[7] = {   // fdlibm e_log.c Lg1..Lg7
     6.666666666666735130e-01, 3.999999999940941908e-01,
     2.857142874366239149e-01, 2.222219843214978396e-01,
     1.818357216161805012e-01, 1.531383769920937332e-01,
     1.479819860511658591e-01};
-static __constant__ double c_xsq_e2[14] = {  // ln(2)^k / k!
+static __constant__ __align__(16) double c_xsq_e2[14] = {  // ln(2)^k / k!
     0x1.0000000000000p+0, 0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3,
     0x1.c6b08d704a0c0p-5, 0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10,
     0x1.430912f86c787p-13, 0x1.ffcbfc588b0c7p-17, 0x1.62c0223a5c824p-20,
     0x1.b5253d395e7c4p-24, 0x1.e4cf5158b8ecap-28, 0x1.e8cac7351bb25p-32,
     0x1.c3bd650fc2986p-36, 0x1.816193166d0f9p-40};
-static __constant__ double c_xsq_havg[2] = {0.9, 0.1};       // common.py:372
-static __constant__ double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
+static __constant__ __align__(16) double c_xsq_havg[2] = {0.9, 0.1};       // common.py:372
+static __constant__ __align__(16) double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
                                             0x1.8p52};              // rint magic
 
 __device__ __forceinline__ double log2_fast(double x) {

@@ -27,10 +27,10 @@ namespace xsq {
 static constexpr int SWAG_KMAX = 12;
 static constexpr int SWAG_NCOL = SWAG_KMAX + 2;
 
-static __constant__ double c_swag_two[13] = {
+static __constant__ __align__(16) double c_swag_two[13] = {
     2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0, 1024.0, 2048.0,
     4096.0, 8192.0};                                   // shampine.py:125-126
-static __constant__ double c_swag_gstr[13] = {
+static __constant__ __align__(16) double c_swag_gstr[13] = {
     0.5, 0.0833, 0.0417, 0.0264, 0.0188, 0.0143, 0.0114, 0.00936, 0.00789,
     0.00679, 0.00592, 0.00524, 0.00468};               // shampine.py:127-128
 

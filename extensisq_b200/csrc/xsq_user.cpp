@@ -173,7 +173,7 @@ void append_table(std::string* images, std::string* s, const char* fn,
     }
     if (v.empty()) vals = "0.0";
     const std::string n = std::to_string(v.size() ? v.size() : 1);
-    *images += std::string("static __constant__ double c_UserTab_") + fn + "[" +
+    *images += std::string("static __constant__ __align__(16) double c_UserTab_") + fn + "[" +
                n + "] = {" + vals + "};\n";
     *s += std::string("    XSQ_HD static constexpr double ") + fn + "(" + args +
           ") {\n        constexpr double T[" + n + "] = {" + vals +
