@@ -390,12 +390,12 @@ def main():
                 "unit": "TFLOP/s", "frac": achieved / peak.value,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at
                 # this size from the committed capture profiles/r01_ncu_full_
-                # rk_persistent_Ts5_lorenz_1250k_T100.txt: 0.18 GB + 2.48 GB with
+                # rk_persistent_Ts5_lorenz_1250k_T100.txt: 0.23 GB + 2.54 GB with
                 # the stiffness diagnosis on (the 2.4 GB are the probe-queue
                 # records, 17.5 M x 160 B); 69.9 MB + 32.4 MB with it off
                 "traffic": (None if not (args.method == "Ts5" and N == LANES_PER_GPU
                                          and args.t_end == T_END)
-                            else 2.662e9 if args.stiff > 0 else 102.2e6),
+                            else 2.765e9 if args.stiff > 0 else 102.2e6),
                 "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
                 "kernel": f"rk_persistent<{args.method}, Lorenz63>",
                 "flops_per_attempted_step": att_f,

@@ -183,6 +183,18 @@ __device__ double event(int k, double t, const double* y, const double* p) {
     if (k == 1) return y[0];
     return y[0] * y[1] - 30.0;
 }"""),
+    # reference tests/test_ivp.py:371-379 (event_rational_1..3) and :759-760
+    "rational": ([lambda t, y: y[0] - y[1] ** 0.7, lambda t, y: y[1] ** 0.6 - y[0],
+                  lambda t, y: t - 7.4], r"""
+__device__ double event(int k, double t, const double* y, const double* p) {
+    if (k == 0) return y[0] - pow(y[1], 0.7);
+    if (k == 1) return pow(y[1], 0.6) - y[0];
+    return t - 7.4;
+}"""),
+    "early": ([lambda t, y: t - 7.0], r"""
+__device__ double event(int k, double t, const double* y, const double* p) {
+    return t - 7.0;
+}"""),
     "vdp_cross": ([lambda t, y: y[0], lambda t, y: y[1] - 1.0,
                    lambda t, y: t - 7.25], r"""
 __device__ double event(int k, double t, const double* y, const double* p) {

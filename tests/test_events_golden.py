@@ -72,3 +72,80 @@ def test_oracle_events_bit_identical_to_reference(c):
         assert np.array_equal(r["t_events"][k], unhex(c["t_events"][k]))
         ye = unhex(c["y_events"][k])
         assert np.array_equal(np.asarray(r["y_events"][k]).reshape(ye.shape), ye)
+
+
+# ---- the reference's own event tests (tests/test_ivp.py:369-470, 757-783),
+# run on the restated solvers + restated scipy machinery --------------------
+ALL = ["BS5", "Ts5", "CK5", "CKdisc", "Pr7", "Pr8", "Pr9", "CFMR7osc", "Me4"]
+
+
+def sol_rational(t):                       # tests/test_ivp.py:31-32
+    return np.asarray((t / (t + 10), 10 * t / (t + 10) ** 2))
+
+
+def run_rational(method, span, y0, term, direc, solver, **kw):
+    fns = EVENT_SETS["rational"][0]
+    return solver(method, span, y0, [(g, a, b) for g, a, b in zip(fns, term, direc)], **kw)
+
+
+def oracle_solver(method, span, y0, events, **kw):
+    r = RO.rk_solve(TABS[method], make_fun("rational", []), span, y0, events=events, **kw)
+    return dict(status=r["status"], t_events=r["t_events"],
+                y_events=[np.asarray(y) for y in r["y_events"]], t=r["t"], y=r["y"])
+
+
+def check_reference_event_test(method, solver):
+    """Assertions of the reference's test_events, for any solver callable."""
+    e1, e2, e3 = EVENT_SETS["rational"][0]
+    y0 = [1 / 3, 2 / 9]
+    # (the reference passes only the first two events in its first calls; here
+    # the third, `t - 7.4`, rides along as a non-terminal event)
+    res = run_rational(method, [5, 8], y0, [0, 0, 0], [0, 0, 1], solver)
+    assert res["status"] == 0
+    assert res["t_events"][0].size == 1 and res["t_events"][1].size == 1
+    assert 5.3 < res["t_events"][0][0] < 5.7
+    assert 7.3 < res["t_events"][1][0] < 7.7
+    assert res["y_events"][0].shape == (1, 2) and res["y_events"][1].shape == (1, 2)
+    assert np.isclose(e1(res["t_events"][0][0], res["y_events"][0][0]), 0)
+    assert np.isclose(e2(res["t_events"][1][0], res["y_events"][1][0]), 0)
+    res = run_rational(method, [5, 8], y0, [0, 0, 0], [1, 1, 1], solver)
+    assert res["status"] == 0
+    assert res["t_events"][0].size == 1 and res["t_events"][1].size == 0
+    assert 5.3 < res["t_events"][0][0] < 5.7
+    res = run_rational(method, [5, 8], y0, [0, 0, 0], [-1, -1, 1], solver)
+    assert res["status"] == 0
+    assert res["t_events"][0].size == 0 and res["t_events"][1].size == 1
+    assert 7.3 < res["t_events"][1][0] < 7.7
+    res = run_rational(method, [5, 8], y0, [0, 0, 1], [0, 0, 0], solver)
+    assert res["status"] == 1
+    assert res["t_events"][0].size == 1 and res["t_events"][1].size == 0
+    assert res["t_events"][2].size == 1
+    assert 5.3 < res["t_events"][0][0] < 5.7 and 7.3 < res["t_events"][2][0] < 7.5
+    assert np.isclose(e3(res["t_events"][2][0], res["y_events"][2][0]), 0)
+    assert np.allclose(sol_rational(res["t_events"][0][0]), res["y_events"][0][0],
+                       rtol=1e-3, atol=1e-6)
+    # backward direction
+    res = run_rational(method, [8, 5], [4 / 9, 20 / 81], [0, 0, 0], [0, 0, 0], solver)
+    assert res["status"] == 0
+    assert res["t_events"][0].size == 1 and res["t_events"][1].size == 1
+    assert 5.3 < res["t_events"][0][0] < 5.7 and 7.3 < res["t_events"][1][0] < 7.7
+    res = run_rational(method, [8, 5], [4 / 9, 20 / 81], [0, 0, 1], [0, 0, 0], solver)
+    assert res["status"] == 1
+    assert res["t_events"][0].size == 0 and res["t_events"][2].size == 1
+    assert 7.3 < res["t_events"][2][0] < 7.5
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_reference_event_test_on_the_oracle(method):
+    check_reference_event_test(method, oracle_solver)
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_reference_t_eval_early_event_on_the_oracle(method):
+    # tests/test_ivp.py:757-783: terminal event before the first t_eval point
+    te = np.linspace(7.5, 9, 16)
+    r = RO.rk_solve(TABS[method], make_fun("rational", []), [5, 9], [1 / 3, 2 / 9],
+                    t_eval=te, events=[(EVENT_SETS["early"][0][0], 1, 0)])
+    assert r["status"] == 1
+    assert r["t"].size == 0 and r["y"].size == 0
+    assert r["t_events"][0].size == 1 and r["t_events"][0][0] == 7

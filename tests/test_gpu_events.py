@@ -8,7 +8,8 @@ import torch
 import extensisq_b200 as xb
 from oracle import rk_oracle as RO
 from oracle.problems import CUDA_SOURCES, EVENT_SETS, make_fun
-from test_events_golden import CASES, TABS, ev_list, ev_options, ev_t_eval, unhex
+from test_events_golden import (ALL, CASES, TABS, check_reference_event_test, ev_list,
+                                ev_options, ev_t_eval, unhex)
 
 pytestmark = pytest.mark.gpu
 BUILTIN_PROBLEMS = {"lorenz63", "vanderpol", "arenstorf"}
@@ -134,3 +135,33 @@ def test_events_leave_the_trajectory_untouched_and_validate_arguments():
         xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.SWAG, events=ev, **kw)
     with pytest.raises(ValueError):
         xb.DeviceEvents.from_source("x", "event", 2, terminal=[-1, 0])
+
+
+# ---- the reference's own event tests (tests/test_ivp.py:369-470, 757-783) ------
+def gpu_solver(method, span, y0, events, **kw):
+    ev = events_for("rational", [e[1] for e in events], [e[2] for e in events])
+    r = xb.solve_ivp_batched(rhs_for("rational"), span, [y0], getattr(xb, method), events=ev, **kw)
+    torch.cuda.synchronize()
+    cnt = r.event_counts.cpu().numpy()[0]
+    t_ev, y_ev = r.t_events.cpu().numpy()[0], r.y_events.cpu().numpy()[0]
+    keep = [int(np.isfinite(t_ev[k]).sum()) for k in range(len(events))]
+    assert all(k <= c for k, c in zip(keep, cnt))
+    return dict(status=int(r.status[0]), t_events=[t_ev[k, :n] for k, n in enumerate(keep)],
+                y_events=[y_ev[k, :n] for k, n in enumerate(keep)])
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_reference_event_test_on_the_device(method):
+    check_reference_event_test(method, gpu_solver)
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_reference_t_eval_early_event_on_the_device(method):
+    te = np.linspace(7.5, 9, 16)
+    ev = events_for("early", [1], [0])
+    r = xb.solve_ivp_batched(rhs_for("rational"), [5, 9], [[1 / 3, 2 / 9]], getattr(xb, method),
+                             t_eval=te, events=ev)
+    torch.cuda.synchronize()
+    assert int(r.status[0]) == 1 and r.message(0) == "A termination event occurred."
+    assert int(r.n_eval_done[0]) == 0
+    assert float(r.t_events[0, 0, 0]) == 7.0 and float(r.t_final[0]) == 7.0
