@@ -104,6 +104,14 @@ __device__ void rhs(double t, const double* y, const double* p, double* dy) {
     dy[0] = y[1];
     dy[1] = -y[0] + (sin(3.0 * t) >= 0.0 ? 1.0 : -1.0);
 }"""),
+    "zero3": (3, 0, r"""
+__device__ void rhs(double t, const double* y, const double* p, double* dy) {
+    dy[0] = 0.0; dy[1] = 0.0; dy[2] = 0.0;
+}"""),
+    "minus_y": (2, 0, r"""
+__device__ void rhs(double t, const double* y, const double* p, double* dy) {
+    dy[0] = -y[0]; dy[1] = -y[1];
+}"""),
     "ballistic": (2, 0, r"""
 __device__ void rhs(double t, const double* y, const double* p, double* dy) {
     dy[0] = y[1];
