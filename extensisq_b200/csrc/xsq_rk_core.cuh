@@ -18,7 +18,14 @@
 //   CFMR7osc._step_impl + pre-err  calvo.py:152-261
 //   _dense_output_impl / Horner    common.py:358-368, 766-790
 //   BS5 interpolants               bogacki.py:348-393
+//   _diagnose_stiffness, stiff_a-d common.py:370-516, 824-1204 -> Lane::diagnose,
+//                                  stiff_probe_impl, stiff_queue (probe queue)
+//   CKdisc._step_impl              cash.py:245-416     -> Lane::attempt_ckdisc
 //   solve_ivp t_eval slicing       scipy/integrate/_ivp/ivp.py:711-728
+//   solve_ivp events (third party) scipy/integrate/_ivp/ivp.py find_active_events,
+//                                  handle_events, solve_event_equation; optimize/
+//                                  Zeros/brentq.c      -> Lane::after_step, event_root
+//                                  (only in kernels built with XSQ_EVENTS_N)
 //   OdeSolver.step finish test     scipy/integrate/_ivp/base.py:195-210
 //
 // This header is also the translation unit NVRTC compiles for user-supplied
@@ -1110,7 +1117,7 @@ struct Lane {
     // scipy/optimize/Zeros/brentq.c with xtol = rtol = 4 eps, 100 iterations,
     // on  tt -> event(k, tt, sol(tt))   (ivp.py solve_event_equation)
     __device__ double event_root(const Dense& D, double (&K)[KROWS][NL], double t_new,
-                                 const double (&y_new)[NL], int k, double g_old, double g_new) {
+                                 const double (&y_new)[NL], int k) {
         const double tol = 4.0 * 0x1.0p-52;
         double xpre = t, xcur = t_new;
         double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
@@ -1120,7 +1127,6 @@ struct Lane {
         double fpre = user_event(k, xpre, ytmp, prm);
         dense_eval(D, K, t_new, y_new, xcur, ytmp);
         double fcur = user_event(k, xcur, ytmp, prm);
-        (void)g_old; (void)g_new;
         if (fpre == 0.0) return xpre;
         if (fcur == 0.0) return xcur;
         auto neg = [](double v) { return __double2hiint(v) < 0; };
@@ -1195,7 +1201,7 @@ struct Lane {
             for (int k = 0; k < XSQ_EVENTS_N; ++k) {
                 if (!(active >> k & 1u)) continue;
                 ++ev_n[k];
-                root[k] = event_root(D, K, t_new, y_new, k, ev_g[k], g_new[k]);
+                root[k] = event_root(D, K, t_new, y_new, k);
                 if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
                     // handle_events: the first terminal root in time order
                     if (!any_term || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
