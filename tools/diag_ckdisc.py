@@ -1,4 +1,5 @@
-"""GPU box: find where the device's CKdisc step sequence leaves the oracle's
+"""TEST INFRASTRUCTURE (dev-time checker: compares the device path with oracle/;
+not part of the product, not used by bench.py).  GPU box: find where the device's CKdisc step sequence leaves the oracle's
 (one lane; the device is stopped after k attempts with max_steps=k)."""
 import os, sys
 import numpy as np, torch

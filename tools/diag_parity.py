@@ -1,4 +1,5 @@
-"""Diagnostic (GPU box): per-method count parity GPU vs C oracle."""
+"""TEST INFRASTRUCTURE (dev-time checker: compares the device path with oracle/;
+not part of the product, not used by bench.py).  Diagnostic (GPU box): per-method count parity GPU vs C oracle."""
 import sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
