@@ -1197,11 +1197,21 @@ struct Lane {
             dense_build(P, D, K, h, t_new, y_new, cubic);
             bool any_term = false;
             double r_star = 0.0;
+            // Each lane works through ITS OWN active events, so lanes that
+            // solve for different event functions iterate together (the index k
+            // is lane data, not a uniform loop variable): the warp pays for the
+            // longest per-lane sequence, not for one root solve per function.
+            for (unsigned todo = active; todo; todo &= todo - 1u) {
+                const int k = __ffs(todo) - 1;
+                const double r = event_root(D, K, t_new, y_new, k);
+#pragma unroll
+                for (int kk = 0; kk < XSQ_EVENTS_N; ++kk)
+                    if (kk == k) root[kk] = r;
+            }
 #pragma unroll
             for (int k = 0; k < XSQ_EVENTS_N; ++k) {
                 if (!(active >> k & 1u)) continue;
                 ++ev_n[k];
-                root[k] = event_root(D, K, t_new, y_new, k);
                 if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
                     // handle_events: the first terminal root in time order
                     if (!any_term || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
