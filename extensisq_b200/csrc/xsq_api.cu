@@ -369,14 +369,17 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         P.stiff_threads = (long long)threads;
         // ... and, for thread-per-system kernels, in a queue that a separate
         // kernel works off afterwards: up to 48 records per trajectory, at most
-        // a quarter of the free memory.  When it is full the slots take over.
+        // a quarter of the free memory and 8 GB.  When it is full the slots
+        // take over.
         const size_t rec = 5 + 4 * nl + npl;
         size_t qcap = 0;
         if (!warp_rhs) {
             size_t free_b = 0, total_b = 0;
             XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
             qcap = N * 48;
-            const size_t fit = free_b / 4 / (rec * sizeof(double));
+            size_t budget = free_b / 4;
+            if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+            const size_t fit = budget / (rec * sizeof(double));
             if (fit < qcap) qcap = fit;
             if (const char* e = getenv("XSQ_STIFF_QUEUE_RECORDS")) qcap = (size_t)atoll(e);
         }
@@ -541,6 +544,11 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
         d.t_events = (double*)dalloc(nrec * nd);
         d.y_events = (double*)dalloc(nrec * ns * nd);
         d.ev_count = (int32_t*)dalloc(nev * ni);
+        // records that are never written read back as NaN
+        if (rc == XSQ_OK && d.t_events && d.y_events) {
+            cudaMemsetAsync(d.t_events, 0xFF, nrec * nd, st);
+            cudaMemsetAsync(d.y_events, 0xFF, nrec * ns * nd, st);
+        }
     }
     if (rc == XSQ_OK) rc = solve_device(&d, st, nullptr);
     auto d2h = [&](void* dst, const void* src, size_t bytes) {

@@ -165,7 +165,9 @@ typedef struct xsq_rk_args {
     const int32_t* ev_direction; /* HOST [n_event_fns]: -1, 0, +1 (event.direction) */
     int32_t ev_capacity;      /* records kept per event function and lane       */
     int32_t reserved2;
-    double* t_events;         /* [n_lanes][n_event_fns][ev_capacity]            */
+    double* t_events;         /* [n_lanes][n_event_fns][ev_capacity]; records
+                                 beyond min(ev_count, ev_capacity) are left as
+                                 the caller filled them (xsq_rk_solve_host: NaN) */
     double* y_events;         /* [n_lanes][n_event_fns][ev_capacity][n_state]   */
     int32_t* ev_count;        /* [n_lanes][n_event_fns] occurrences found (can
                                  exceed ev_capacity: later ones are not kept)   */
