@@ -165,3 +165,52 @@ def test_reference_t_eval_early_event_on_the_device(method):
     assert int(r.status[0]) == 1 and r.message(0) == "A termination event occurred."
     assert int(r.n_eval_done[0]) == 0
     assert float(r.t_events[0, 0, 0]) == 7.0 and float(r.t_final[0]) == 7.0
+
+
+def test_events_through_the_host_buffer_c_entry_point():
+    """xsq_rk_solve_host with events: host arrays in and out, unused records NaN,
+    same numbers as the device-buffer path."""
+    import ctypes as C
+    from extensisq_b200 import _lib
+    lib = _lib.load()
+    N, cap, ne = 200, 8, 3
+    rng = np.random.default_rng(4)
+    y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+    prm = np.tile([10.0, 28.0, 8.0 / 3.0], (N, 1))
+    ev = events_for("lorenz_sections", [0, 2, 0], [1, 0, 0])
+    y0_soa, prm_soa = np.ascontiguousarray(y0.T), np.ascontiguousarray(prm.T)
+    atol = np.array([1e-9])
+    out = dict(t_final=np.empty(N), y_final=np.empty((3, N)),
+               t_events=np.zeros((N, ne, cap)), y_events=np.zeros((N, ne, cap, 3)))
+    ints = {k: np.empty(N, np.int32) for k in ("n_accepted", "n_rejected", "nfev", "status")}
+    ev_count = np.empty((N, ne), np.int32)
+    term = (C.c_int32 * ne)(*ev.terminal)
+    direc = (C.c_int32 * ne)(*ev.direction)
+    a = _lib.XsqRkArgs()
+    a.struct_size = C.sizeof(_lib.XsqRkArgs)
+    a.method, a.rhs, a.n_state, a.n_param = _lib.METHOD_IDS["Ts5"], 0, 3, 3
+    a.n_lanes = N
+    a.y0, a.params = y0_soa.ctypes.data, prm_soa.ctypes.data
+    a.t0, a.t_bound, a.rtol = 0.0, 3.0, 1e-6
+    a.atol = atol.ctypes.data_as(C.POINTER(C.c_double))
+    a.n_atol = 1
+    a.max_step, a.max_steps, a.nfev_stiff_detect = float("inf"), 1000000, 5000
+    a.t_final, a.y_final = out["t_final"].ctypes.data, out["y_final"].ctypes.data
+    for k, v in ints.items():
+        setattr(a, k, v.ctypes.data)
+    a.events, a.n_event_fns = ev.handle, ne
+    a.ev_terminal = C.cast(term, C.POINTER(C.c_int32))
+    a.ev_direction = C.cast(direc, C.POINTER(C.c_int32))
+    a.ev_capacity = cap
+    a.t_events, a.y_events = out["t_events"].ctypes.data, out["y_events"].ctypes.data
+    a.ev_count = ev_count.ctypes.data
+    assert lib.xsq_rk_solve_host(C.byref(a), 0) == 0, lib.xsq_last_error_detail().decode()
+    r = xb.solve_ivp_batched("lorenz63", (0.0, 3.0), y0, xb.Ts5, params=prm, rtol=1e-6, atol=1e-9,
+                             events=ev, max_event_records=cap, max_steps=1000000)
+    torch.cuda.synchronize()
+    assert np.array_equal(ints["status"], r.status.cpu().numpy()) and (ints["status"] == 1).any()
+    assert np.array_equal(ev_count, r.event_counts.cpu().numpy())
+    assert np.array_equal(out["t_events"], r.t_events.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(out["y_events"], r.y_events.cpu().numpy(), equal_nan=True)
+    assert np.isnan(out["t_events"]).any()                    # unused records
+    assert np.array_equal(out["y_final"].T, r.y_final.cpu().numpy())
