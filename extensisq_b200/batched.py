@@ -254,8 +254,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         if not isinstance(events, DeviceEvents):
             raise ValueError("`events` must be a DeviceEvents (device code; a "
                              "Python callable cannot run inside the kernel)")
-        if is_swag or forced_steps is not None:
-            raise ValueError("events do not apply to SWAG or forced_steps")
+        if forced_steps is not None:
+            raise ValueError("events do not apply to forced_steps")
         if not (isinstance(max_event_records, int) and max_event_records > 0):
             raise ValueError("`max_event_records` must be a positive integer")
     is_ckdisc = not is_swag and getattr(method, "_xsq_method", None) == _lib.METHOD_IDS["CKdisc"]

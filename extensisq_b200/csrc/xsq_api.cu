@@ -221,8 +221,8 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
             g_detail = "events arguments inconsistent";
             return XSQ_ERR_ARG;
         }
-        if (a->n_forced > 0 || a->rhs == XSQ_RHS_NBODY32 || a->method == XSQ_METHOD_SWAG) {
-            g_detail = "events are not available with forced steps, SWAG or nbody32";
+        if (a->n_forced > 0 || a->rhs == XSQ_RHS_NBODY32) {
+            g_detail = "events are not available with forced steps or nbody32";
             return XSQ_ERR_UNSUPPORTED;
         }
         for (int k = 0; k < ne; ++k)

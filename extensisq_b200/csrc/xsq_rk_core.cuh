@@ -682,6 +682,63 @@ __device__ __noinline__ int stiff_probe_dev(const double* slot, long long stride
     return stiff_probe_impl<R, true>(slot, stride, xend, maxfcn, cost, stbrad, tanang);
 }
 
+// scipy/optimize/Zeros/brentq.c with xtol = rtol = 4 eps and 100 iterations, as
+// solve_event_equation calls it (scipy/integrate/_ivp/ivp.py).  f(x) is any
+// callable; shared by the Runge-Kutta and the SWAG lanes.
+template <class F>
+__device__ __forceinline__ double brentq_dev(F&& f, double xa, double xb) {
+    const double tol = 4.0 * 0x1.0p-52;
+    double xpre = xa, xcur = xb;
+    double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+    double fpre = f(xpre);
+    double fcur = f(xcur);
+    if (fpre == 0.0) return xpre;
+    if (fcur == 0.0) return xcur;
+    auto neg = [](double v) { return __double2hiint(v) < 0; };
+    if (neg(fpre) == neg(fcur)) return xcur;     // scipy raises; cannot happen after
+                                                 // find_active_events up to rounding
+    for (int it = 0; it < 100; ++it) {
+        if (fpre != 0.0 && fcur != 0.0 && neg(fpre) != neg(fcur)) {
+            xblk = xpre;
+            fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        const double delta = (tol + tol * fabs(xcur)) / 2;
+        const double sbis = (xblk - xcur) / 2;
+        if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                const double dpre = (fpre - fcur) / (xpre - xcur);
+                const double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            if (2 * fabs(stry) < pymin(fabs(spre), 3 * fabs(sbis) - delta)) {
+                spre = scur;
+                scur = stry;
+            } else {
+                spre = sbis;
+                scur = sbis;
+            }
+        } else {
+            spre = sbis;
+            scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = f(xcur);
+    }
+    return xcur;
+}
+
 template <bool ON>
 struct CkExtra {
     double tw[2], q[2];
@@ -1114,65 +1171,14 @@ struct Lane {
             out[c] = v + (D.anchor_end ? y_new[c] : y[c]);
         }
     }
-    // scipy/optimize/Zeros/brentq.c with xtol = rtol = 4 eps, 100 iterations,
-    // on  tt -> event(k, tt, sol(tt))   (ivp.py solve_event_equation)
+    // the root of  tt -> event(k, tt, sol(tt))  in the step (ivp.py solve_event_equation)
     __device__ double event_root(const Dense& D, double (&K)[KROWS][NL], double t_new,
                                  const double (&y_new)[NL], int k) {
-        const double tol = 4.0 * 0x1.0p-52;
-        double xpre = t, xcur = t_new;
-        double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
-        double ytmp[NL];
-        // f(t_old) and f(t) through the interpolant, as brentq evaluates them
-        dense_eval(D, K, t_new, y_new, xpre, ytmp);
-        double fpre = user_event(k, xpre, ytmp, prm);
-        dense_eval(D, K, t_new, y_new, xcur, ytmp);
-        double fcur = user_event(k, xcur, ytmp, prm);
-        if (fpre == 0.0) return xpre;
-        if (fcur == 0.0) return xcur;
-        auto neg = [](double v) { return __double2hiint(v) < 0; };
-        if (neg(fpre) == neg(fcur)) return xcur;     // scipy raises; cannot happen after
-                                                     // find_active_events up to rounding
-        for (int it = 0; it < 100; ++it) {
-            if (fpre != 0.0 && fcur != 0.0 && neg(fpre) != neg(fcur)) {
-                xblk = xpre;
-                fblk = fpre;
-                spre = scur = xcur - xpre;
-            }
-            if (fabs(fblk) < fabs(fcur)) {
-                xpre = xcur; xcur = xblk; xblk = xpre;
-                fpre = fcur; fcur = fblk; fblk = fpre;
-            }
-            const double delta = (tol + tol * fabs(xcur)) / 2;
-            const double sbis = (xblk - xcur) / 2;
-            if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
-            if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
-                double stry;
-                if (xpre == xblk) {
-                    stry = -fcur * (xcur - xpre) / (fcur - fpre);
-                } else {
-                    const double dpre = (fpre - fcur) / (xpre - xcur);
-                    const double dblk = (fblk - fcur) / (xblk - xcur);
-                    stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
-                }
-                if (2 * fabs(stry) < pymin(fabs(spre), 3 * fabs(sbis) - delta)) {
-                    spre = scur;
-                    scur = stry;
-                } else {
-                    spre = sbis;
-                    scur = sbis;
-                }
-            } else {
-                spre = sbis;
-                scur = sbis;
-            }
-            xpre = xcur;
-            fpre = fcur;
-            if (fabs(scur) > delta) xcur += scur;
-            else xcur += (sbis > 0 ? delta : -delta);
-            dense_eval(D, K, t_new, y_new, xcur, ytmp);
-            fcur = user_event(k, xcur, ytmp, prm);
-        }
-        return xcur;
+        return brentq_dev([&](double tt) {
+            double ytmp[NL];
+            dense_eval(D, K, t_new, y_new, tt, ytmp);
+            return user_event(k, tt, ytmp, prm);
+        }, t, t_new);
     }
     // Everything solve_ivp does after solver.step() returned (ivp.py): events,
     // then the t_eval points of the step.  Returns true when a terminal event

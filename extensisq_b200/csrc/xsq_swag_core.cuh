@@ -50,6 +50,10 @@ struct SwagLane {
     int k, kold, kprev, ns, ivc, kgi, ifail, k_max;
     int n_acc, n_fail, nfev, ieval;
     bool phase1, fresh;
+#ifdef XSQ_EVENTS_N
+    double ev_g[XSQ_EVENTS_N];     // event function values at (t, y)  (ivp.py `g`)
+    int ev_n[XSQ_EVENTS_N];        // occurrences so far               (`event_count`)
+#endif
 
     __device__ __forceinline__ static double iqq(int i) {
         return 1.0 / ((double)(i + 1) * ((double)(i + 1) + 1.0));
@@ -92,6 +96,13 @@ struct SwagLane {
         fresh = true;
         t_old = t;
         min_step = 0.0;
+#ifdef XSQ_EVENTS_N
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            ev_g[k] = user_event(k, t, y, prm);
+            ev_n[k] = 0;
+        }
+#endif
     }
 
     __device__ __forceinline__ double rmsq(const double (&q)[NL]) {
@@ -146,9 +157,10 @@ struct SwagLane {
             yout[c] = hh * acc[c] + (sigma * y[c] + (1.0 - sigma) * y_old[c]);
     }
 
-    __device__ void emit(const RkDev& P, int lane) {
+    // t_eval points of (t_old, tlim]; tlim < t after a terminal event
+    __device__ void emit(const RkDev& P, int lane, double tlim) {
         while (ieval < P.n_eval &&
-               P.direction * (P.t_eval[ieval] - t) <= 0.0) {
+               P.direction * (P.t_eval[ieval] - tlim) <= 0.0) {
             double yout[NL];
             interp(P.t_eval[ieval], yout);
             eval_put<R>(P, sys, lane, ieval, yout);
@@ -173,8 +185,7 @@ struct SwagLane {
                 for (int c = 0; c < NL; ++c) y[c] = fma(d, yp[c], y[c]);
                 t = P.t_bound;
                 ++n_acc;
-                if (P.n_eval > 0) emit(P, lane);
-                return LANE_FINISHED;
+                return finish_step(P, lane) ? LANE_EVENT : LANE_FINISHED;
             }
             if (P.direction * (h - d) > 0.0) h = d;
             if (P.max_step != XSQ_INF)
@@ -379,9 +390,80 @@ struct SwagLane {
         t = x;
         ++n_acc;
         fresh = true;
-        if (P.n_eval > 0) emit(P, lane);
+        if (finish_step(P, lane)) return LANE_EVENT;
         return (P.direction * (t - P.t_bound) >= 0.0) ? LANE_FINISHED
                                                       : LANE_RUNNING;
+    }
+
+    // What solve_ivp does after solver.step() returned (ivp.py): events on the
+    // step's interpolant (SwagDenseOutput / LinearDenseOutput), then the t_eval
+    // points.  Returns true when a terminal event ends the trajectory.
+    __device__ bool finish_step(const RkDev& P, int lane) {
+        double t_stop = t;
+        bool terminate = false;
+#ifdef XSQ_EVENTS_N
+        double g_new[XSQ_EVENTS_N], root[XSQ_EVENTS_N];
+        unsigned active = 0;
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            g_new[k] = user_event(k, t, y, prm);
+            const bool up = ev_g[k] <= 0.0 && g_new[k] >= 0.0;      // find_active_events
+            const bool down = ev_g[k] >= 0.0 && g_new[k] <= 0.0;
+            const int d = P.ev_direction[k];
+            if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) active |= 1u << k;
+        }
+        if (active) {
+            for (unsigned todo = active; todo; todo &= todo - 1u) {
+                const int k = __ffs(todo) - 1;
+                const double r = brentq_dev([&](double tt) {
+                    double ytmp[NL];
+                    interp(tt, ytmp);
+                    return user_event(k, tt, ytmp, prm);
+                }, t_old, t);
+#pragma unroll
+                for (int kk = 0; kk < XSQ_EVENTS_N; ++kk)
+                    if (kk == k) root[kk] = r;
+            }
+            double r_star = 0.0;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                ++ev_n[k];
+                if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
+                    if (!terminate || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
+                    terminate = true;
+                }
+            }
+            if (terminate) t_stop = r_star;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                if (terminate && P.direction * (root[k] - r_star) > 0.0) continue;
+                const int slot = ev_n[k] - 1;
+                if (slot < P.ev_capacity) {
+                    const long long base = (sys * XSQ_EVENTS_N + k) * P.ev_capacity + slot;
+                    double ye[NL];
+                    interp(root[k], ye);
+                    P.t_events[base] = root[k];
+#pragma unroll
+                    for (int c = 0; c < NL; ++c) P.y_events[base * NL + c] = ye[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_g[k] = g_new[k];
+#endif
+        if (P.n_eval > 0) emit(P, lane, t_stop);
+#ifdef XSQ_EVENTS_N
+        if (terminate) {
+            double ys[NL];
+            interp(t_stop, ys);                                     // y = sol(t)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) y[c] = ys[c];
+            t = t_stop;
+        }
+#endif
+        return terminate;
     }
 
     __device__ void store(const RkDev& P, int st, int lane,
@@ -399,7 +481,11 @@ struct SwagLane {
             P.n_acc[sys] = n_acc;
             P.n_rej[sys] = n_fail;
             P.nfev[sys] = nfev;
-            P.status[sys] = st;
+            P.status[sys] = st == LANE_EVENT ? 1 : st;    // 1: a termination event occurred
+#ifdef XSQ_EVENTS_N
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) P.ev_count[sys * XSQ_EVENTS_N + k] = ev_n[k];
+#endif
             if (P.n_eval_done) P.n_eval_done[sys] = ieval;
         }
     }

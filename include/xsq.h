@@ -157,7 +157,8 @@ typedef struct xsq_rk_args {
     /* events: scipy solve_ivp(events=...) on the device -- find_active_events,
      * handle_events, solve_event_equation (scipy/integrate/_ivp/ivp.py) and
      * brentq (scipy/optimize/Zeros/brentq.c), evaluated on the method's own
-     * dense output.  Not for SWAG, forced steps or XSQ_RHS_NBODY32. */
+     * dense output (Horner / cubic / SWAG's interpolant).  Not for forced
+     * steps or XSQ_RHS_NBODY32. */
     int32_t events;           /* handle of xsq_events_register_source, 0 = none */
     int32_t n_event_fns;      /* must equal the handle's n_events               */
     const int32_t* ev_terminal;  /* HOST [n_event_fns]: 0 never terminal, k > 0

@@ -59,7 +59,11 @@ def test_brentq_restatement_matches_scipy():
         assert r0 == r1 and calls == info.function_calls
 
 
-@pytest.mark.parametrize("c", CASES, ids=lambda c: c["id"])
+# SWAG cases pin the device path directly (there is no NumPy SWAG restatement)
+RK_CASES = [c for c in CASES if c["method"] != "SWAG"]
+
+
+@pytest.mark.parametrize("c", RK_CASES, ids=lambda c: c["id"])
 def test_oracle_events_bit_identical_to_reference(c):
     r = RO.rk_solve(TABS[c["method"]], make_fun(c["problem"], c["params"]), c["t_span"],
                     c["y0"], t_eval=ev_t_eval(c), events=ev_list(c), **ev_options(c))

@@ -46,8 +46,13 @@ def test_events_vs_reference_golden(c):
     rtol = o.get("rtol", 1e-3)
     # the step sequence is the reference's (same counts), so event times agree
     # to rounding amplified by the root finder's conditioning, far below rtol
-    assert int(r.nfev[0]) == c["nfev"] and int(r.n_rejected[0]) == c["nfs"]
-    tol = 1e-9
+    if c["method"] == "SWAG":        # variable order: one flipped order choice moves nfev
+        assert abs(int(r.nfev[0]) - c["nfev"]) <= 0.02 * c["nfev"] + 2
+        tol = 1e-9 if int(r.nfev[0]) == c["nfev"] else 10 * rtol
+    else:
+        assert int(r.nfev[0]) == c["nfev"] and int(r.n_rejected[0]) == c["nfs"]
+        tol = 1e-9
+    ytol = 1e-8 if tol == 1e-9 else 10 * rtol
     cnt = r.event_counts.cpu().numpy()[0]
     t_ev = r.t_events.cpu().numpy()[0]
     y_ev = r.y_events.cpu().numpy()[0]
@@ -60,18 +65,18 @@ def test_events_vs_reference_golden(c):
         assert cnt[k] >= tg.size
         assert np.allclose(t_ev[k, :tg.size], tg, rtol=tol, atol=tol), (k, t_ev[k, :tg.size], tg)
         if tg.size:
-            assert np.allclose(y_ev[k, :tg.size], yg.reshape(tg.size, -1), rtol=1e-8, atol=1e-8)
+            assert np.allclose(y_ev[k, :tg.size], yg.reshape(tg.size, -1), rtol=ytol, atol=ytol)
         if c["status"] == 0:
             assert np.isnan(t_ev[k, tg.size:]).all()
     t_g, y_g = unhex(c["t"]), unhex(c["y"])
     if te is None:
         assert abs(float(r.t_final[0]) - t_g[-1]) <= tol * max(1.0, abs(t_g[-1]))
-        assert np.allclose(r.y_final.cpu().numpy()[0], y_g[:, -1], rtol=1e-8, atol=1e-8)
+        assert np.allclose(r.y_final.cpu().numpy()[0], y_g[:, -1], rtol=ytol, atol=ytol)
     else:
         # t_eval output stops at the terminal event (ivp.py: t = roots[-1])
         assert int(r.n_eval_done[0]) == t_g.size
         y = r.y.cpu().numpy()[0][:, :t_g.size]
-        assert np.allclose(y, y_g.reshape(y.shape), rtol=1e-8, atol=1e-8)
+        assert np.allclose(y, y_g.reshape(y.shape), rtol=ytol, atol=ytol)
     assert rtol > 0
 
 
@@ -132,7 +137,8 @@ def test_events_leave_the_trajectory_untouched_and_validate_arguments():
     assert torch.equal(c.event_counts, a.event_counts)
     assert torch.equal(c.t_events[:, :, :2].nan_to_num(-1.0), a.t_events[:, :, :2].nan_to_num(-1.0))
     with pytest.raises(ValueError):
-        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.SWAG, events=ev, **kw)
+        xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, events=ev,
+                             forced_steps=[0.01, 0.01], **kw)
     with pytest.raises(ValueError):
         xb.DeviceEvents.from_source("x", "event", 2, terminal=[-1, 0])
 
@@ -150,12 +156,12 @@ def gpu_solver(method, span, y0, events, **kw):
                 y_events=[y_ev[k, :n] for k, n in enumerate(keep)])
 
 
-@pytest.mark.parametrize("method", ALL)
+@pytest.mark.parametrize("method", ALL + ["SWAG"])
 def test_reference_event_test_on_the_device(method):
     check_reference_event_test(method, gpu_solver)
 
 
-@pytest.mark.parametrize("method", ALL)
+@pytest.mark.parametrize("method", ALL + ["SWAG"])
 def test_reference_t_eval_early_event_on_the_device(method):
     te = np.linspace(7.5, 9, 16)
     ev = events_for("early", [1], [0])

@@ -49,6 +49,11 @@ CASES = [
     ("vdp_Pr7", "Pr7", "vanderpol", [2.0], [2., 0.], [0., 12.], dict(rtol=1e-6, atol=1e-8), None, "vdp_cross", [0, 0, 1], [-1, 0, 0]),
     ("vdp_Ts5_teval_term", "Ts5", "vanderpol", [2.0], [2., 0.], [0., 12.], dict(rtol=1e-5, atol=1e-7), (0., 12., 49), "vdp_cross", [4, 0, 0], [0, 1, 0]),
     ("vdp_CKdisc", "CKdisc", "vanderpol", [5.0], [2., 0.], [0., 12.], dict(rtol=1e-5, atol=1e-7), None, "vdp_cross", [0, 0, 1], [0, 0, 0]),
+    # SWAG (shampine.py): events on SwagDenseOutput / LinearDenseOutput
+    ("swag_ground", "SWAG", "ballistic", [], [10., 5.], [0., 5.], dict(rtol=1e-6, atol=1e-9), None, "ground", [1, 0], [-1, 0]),
+    ("swag_lorenz", "SWAG", "lorenz63", L, [1., 1., 1.], [0., 6.], dict(rtol=1e-6, atol=1e-9), None, "lorenz_sections", [0, 0, 0], [1, 0, -1]),
+    ("swag_vdp_teval_term", "SWAG", "vanderpol", [2.0], [2., 0.], [0., 12.], dict(rtol=1e-5, atol=1e-7), (0., 12., 49), "vdp_cross", [4, 0, 0], [0, 1, 0]),
+    ("swag_lorenz_back", "SWAG", "lorenz63", L, [-5., -7., 20.], [1., 0.], dict(rtol=1e-6, atol=1e-9), (1., 0., 11), "lorenz_sections", [0, 0, 0], [0, 0, 0]),
 ]
 
 
@@ -65,6 +70,9 @@ def main():
             evs.append(f)
         t_eval = np.linspace(*te) if te else None
         refcommon.NFS[()] = 0
+        if mname == "SWAG":
+            import extensisq.shampine as sh
+            sh.NFS[()] = 0
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             r = solve_ivp(fun, span, y0, method=getattr(ref, mname), t_eval=t_eval,
@@ -72,7 +80,7 @@ def main():
         out.append(dict(id=cid, method=mname, problem=prob, params=prm, y0=y0, t_span=span,
                         options=opts, t_eval=list(te) if te else None, events=evset,
                         terminal=term, direction=direc, status=int(r.status),
-                        nfev=int(r.nfev), nfs=int(refcommon.NFS), t=hx(r.t), y=hx(r.y),
+                        nfev=int(r.nfev), nfs=int(sh.NFS) if mname == "SWAG" else int(refcommon.NFS), t=hx(r.t), y=hx(r.y),
                         t_events=[hx(a) for a in r.t_events],
                         y_events=[hx(np.asarray(a).reshape(-1, len(y0))) if len(a) else []
                                   for a in r.y_events]))
