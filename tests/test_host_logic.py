@@ -147,3 +147,27 @@ def test_ckdisc_class_mirrors_the_reference_attributes():
     assert np.array_equal(ck.C_fallback, ck.C[[1, 3]])
     assert ck._xsq_method == 8 and "CKdisc" not in xb.BUILTIN
     assert ck.stbrad is None and ck.tanang is None      # no stiffness diagnosis
+
+
+def test_device_events_and_sens_forward_argument_checks_need_no_gpu():
+    """Validation mirrors scipy's prepare_events and sensitivity.py:135-156 and
+    happens on the host before anything is launched."""
+    import extensisq_b200 as xb
+    src = "__device__ double event(int k, double t, const double* y, const double* p) { return y[0]; }"
+    ev = xb.DeviceEvents.from_source(src, "event", 2, terminal=[True, 3], direction=[-2.5, 0])
+    assert ev.terminal == [1, 3] and ev.direction == [-1, 0] and ev.handle >= 1
+    assert ev.with_attributes(terminal=[0, 0]).handle == ev.handle
+    with pytest.raises(ValueError):
+        xb.DeviceEvents.from_source(src, "event", 2, terminal=[-1, 0])
+    with pytest.raises(ValueError):
+        xb.DeviceEvents.from_source(src, "event", 2, terminal=[1])
+    with pytest.raises(ValueError):                      # 9 event functions: XSQ_MAX_EVENTS is 8
+        xb.DeviceEvents.from_source(src, "event", 9)
+    with pytest.raises(AssertionError):                  # dy0dp must be (ny, np)
+        xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0, 1.0]], np.zeros((2, 3)), [1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):                      # ny (np + 1) > 16 states per lane
+        xb.sens_forward("", (0.0, 1.0), [[1.0] * 6], np.zeros((6, 3)), [1.0, 2.0, 3.0])
+    with pytest.raises(AssertionError):                  # t_eval must end at t_span[1]
+        xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0]], np.zeros((2, 1)), [1.0], t_eval=[0.0, 0.5])
+    with pytest.raises(AssertionError):                  # rtol must be a float
+        xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0]], np.zeros((2, 1)), [1.0], rtol=1)
