@@ -220,3 +220,37 @@ def test_events_through_the_host_buffer_c_entry_point():
     assert np.array_equal(out["y_events"], r.y_events.cpu().numpy(), equal_nan=True)
     assert np.isnan(out["t_events"]).any()                    # unused records
     assert np.array_equal(out["y_final"].T, r.y_final.cpu().numpy())
+
+
+def test_events_with_a_user_tableau():
+    """A user RungeKutta subclass (uploaded tableau, NVRTC kernel) with events:
+    Heun's 2(1) pair on the rational problem, against the restated reference."""
+    from oracle.problems import make_fun
+
+    class Heun(xb.RungeKutta):
+        n_stages, order, order_secondary = 2, 2, 1
+        A = np.array([[0.0, 0.0], [1.0, 0.0]])
+        B = np.array([0.5, 0.5])
+        C = np.array([0.0, 1.0])
+        E = np.array([-0.5, 0.5, 0.0])
+        P = np.array([[1.0, -0.5], [0.0, 0.5], [0.0, 0.0]])
+
+    tab = RO.Tableau(dict(name="Heun", n_stages=2, order=2, order_secondary=1, sc_params="standard",
+                          A=[[v.hex() for v in r] for r in Heun.A.tolist()],
+                          B=[v.hex() for v in Heun.B.tolist()], C=[v.hex() for v in Heun.C.tolist()],
+                          E=[v.hex() for v in Heun.E.tolist()],
+                          P=[[v.hex() for v in r] for r in Heun.P.tolist()]))
+    fns = EVENT_SETS["rational"][0]
+    term, direc = [0, 0, 1], [0, 0, 0]
+    o = RO.rk_solve(tab, make_fun("rational", []), [5, 8], [1 / 3, 2 / 9], rtol=1e-4, atol=1e-7,
+                    events=[(g, a, b) for g, a, b in zip(fns, term, direc)])
+    ev = events_for("rational", term, direc)
+    r = xb.solve_ivp_batched(rhs_for("rational"), [5, 8], [[1 / 3, 2 / 9]], Heun, rtol=1e-4, atol=1e-7,
+                             events=ev, max_steps=100000)
+    torch.cuda.synchronize()
+    assert int(r.status[0]) == o["status"] == 1
+    assert int(r.nfev[0]) == o["nfev"]
+    for k in range(3):
+        tg = o["t_events"][k]
+        assert np.allclose(r.t_events.cpu().numpy()[0, k, :tg.size], tg, rtol=1e-9, atol=1e-9)
+    assert abs(float(r.t_final[0]) - 7.4) < 1e-12
