@@ -128,6 +128,14 @@ class BatchedOdeResult:
     def message(self, lane):
         return _lib.LANE_MESSAGES[int(self.status[lane])]
 
+    def lane_tensors(self):
+        """Every per-lane result tensor (dim 0 = lanes) by name, e.g. as the
+        argument of ``gather_result`` after a sharded solve."""
+        names = ("y", "t_final", "y_final", "h_next", "n_accepted", "n_rejected", "nfev",
+                 "status", "n_eval_done", "stiff_flags", "t_events", "y_events",
+                 "event_counts")
+        return {k: getattr(self, k) for k in names if getattr(self, k) is not None}
+
 
 def _as_device(x, device, dtype=torch.float64):
     if isinstance(x, torch.Tensor):

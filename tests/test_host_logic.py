@@ -106,15 +106,30 @@ def _gather_worker(rank, world, port, n_lanes, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = xb.shard_bounds(n_lanes, rank, world)
-    mine = dict(y_final=torch.arange(lo, hi, dtype=torch.float64)[:, None]
-                * torch.ones(1, 3, dtype=torch.float64),
-                n_accepted=torch.arange(lo, hi, dtype=torch.int32))
+    from extensisq_b200.batched import BatchedOdeResult
+    lanes = torch.arange(lo, hi, dtype=torch.float64)
+    # a shard's result as the solver returns it, events included ([N, n_events,
+    # capacity] and [N, n_events, capacity, n])
+    res = BatchedOdeResult(
+        t=None, y=None, t_final=lanes.clone(), y_final=lanes[:, None] * torch.ones(1, 3, dtype=torch.float64),
+        h_next=lanes.clone(), n_accepted=torch.arange(lo, hi, dtype=torch.int32),
+        n_rejected=torch.zeros(hi - lo, dtype=torch.int32), nfev=torch.zeros(hi - lo, dtype=torch.int32),
+        status=torch.zeros(hi - lo, dtype=torch.int32),
+        t_events=lanes[:, None, None] * torch.ones(1, 2, 4, dtype=torch.float64),
+        y_events=lanes[:, None, None, None] * torch.ones(1, 2, 4, 3, dtype=torch.float64),
+        event_counts=torch.arange(lo, hi, dtype=torch.int32)[:, None] * torch.ones(1, 2, dtype=torch.int32))
+    mine = res.lane_tensors()
+    assert "y" not in mine and "t_events" in mine
     full = xb.gather_result(mine, n_lanes)
     ok = (torch.equal(full["n_accepted"],
                       torch.arange(n_lanes, dtype=torch.int32))
           and full["y_final"].shape == (n_lanes, 3)
           and torch.equal(full["y_final"][:, 1],
-                          torch.arange(n_lanes, dtype=torch.float64)))
+                          torch.arange(n_lanes, dtype=torch.float64))
+          and full["t_events"].shape == (n_lanes, 2, 4)
+          and full["y_events"].shape == (n_lanes, 2, 4, 3)
+          and torch.equal(full["y_events"][:, 1, 2, 0], torch.arange(n_lanes, dtype=torch.float64))
+          and torch.equal(full["event_counts"][:, 1], torch.arange(n_lanes, dtype=torch.int32)))
     root = xb.gather_result(mine, n_lanes, dst=0)
     ok = ok and ((root["n_accepted"] is not None) == (rank == 0))
     out[rank] = bool(ok)
