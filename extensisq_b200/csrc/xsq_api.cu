@@ -250,6 +250,13 @@ static int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     P->safety = sc[3];
     P->safety_sc = std::pow(sc[3], sc[0] + sc[1]);
     P->log2n = std::log2((double)ns);
+    // the controller in the log2 domain (xsq_rk_core.cuh ctl_factor); the same
+    // expressions, in the same order, are in oracle/xsq_oracle.c
+    P->ctl_a1s = 0.5 * P->err_exp;
+    P->ctl_a0s = std::log2(P->safety) - P->ctl_a1s * P->log2n;
+    P->ctl_a1c = 0.5 * P->minbeta1;
+    P->ctl_a2c = 0.5 * P->minbeta2;
+    P->ctl_a0c = std::log2(P->safety_sc) - (P->ctl_a1c + P->ctl_a2c) * P->log2n;
     P->n_lanes = a->n_lanes;
     P->y0 = a->y0;
     P->params = a->params;

@@ -32,6 +32,7 @@
 // right-hand sides, so it includes nothing from the host toolchain.
 #pragma once
 #include "xsq_tableaux_gen.cuh"
+#include "xsq_math_tables_gen.cuh"
 
 namespace xsq {
 
@@ -71,6 +72,13 @@ struct RkDev {
     double first_step, max_step;
     double err_exp, minbeta1, minbeta2, minalpha, safety, safety_sc;
     double log2n;                 // log2(n_state), for log2(error_norm)
+    // step-size controller in the log2 domain (ctl_factor below), with
+    // l2 = log2(sum((err/scale)^2)) = 2 log2(error_norm) + log2 n:
+    //   safety    * error_norm^err_exp                     = 2^(a1s l2 + a0s)
+    //   safety_sc * error_norm^minbeta1 * err_old^minbeta2 = 2^(a1c l2 + a2c l2_old + a0c)
+    double ctl_a1s, ctl_a0s, ctl_a1c, ctl_a2c, ctl_a0c;
+    // rk_fast: high words that bracket "min_step < h_abs < max_step" (xsq_rk_fast.cuh)
+    int fast_hi_min, fast_hi_span;
     const double* t_eval;
     double* y_eval;
     const double* h_forced;
@@ -130,17 +138,6 @@ __device__ __forceinline__ double sys_min(double x) {
     return x;
 }
 
-// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (5 fp64-pipe slots
-// instead of ~11 for the IEEE-exact division; x is a scale >= atol > 0).
-__device__ __forceinline__ double rcp_fast(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
 // Python's built-in max(a, b) / min(a, b): "b if b > a else a".  A plain
 // compare-and-select (3 instructions); fmax()/fmin() cost ~8 on sm_100 because
 // of their NaN rules, and these are the reference's semantics anyway.
@@ -149,80 +146,103 @@ __device__ __forceinline__ double pymin(double a, double b) { return b < a ? b :
 
 // ---- log2 / exp2 for the step-size controller -------------------------------
 // error_norm ** x  (common.py:257, 264-266, 281) is evaluated as
-// exp2(x * log2(error_norm)).  |x| <= 0.25, so plain double-precision log2 and
-// exp2 (each ~1 ulp) give the factor to ~2 ulp, the accuracy class of pow().
-// (16-byte aligned: see tools/gen_header.py)
-// Coefficients sit in __constant__ memory so each one is a c[bank][offset]
-// operand of its DFMA.  Rare inputs (0, subnormal, Inf, NaN, |z| >= 1000) take
-// the libdevice routines.
-static __constant__ __align__(16) double c_xsq_lg[7] = {   // fdlibm e_log.c Lg1..Lg7
-    6.666666666666735130e-01, 3.999999999940941908e-01,
-    2.857142874366239149e-01, 2.222219843214978396e-01,
-    1.818357216161805012e-01, 1.531383769920937332e-01,
-    1.479819860511658591e-01};
-static __constant__ __align__(16) double c_xsq_e2[14] = {  // ln(2)^k / k!
-    0x1.0000000000000p+0, 0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3,
-    0x1.c6b08d704a0c0p-5, 0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10,
-    0x1.430912f86c787p-13, 0x1.ffcbfc588b0c7p-17, 0x1.62c0223a5c824p-20,
-    0x1.b5253d395e7c4p-24, 0x1.e4cf5158b8ecap-28, 0x1.e8cac7351bb25p-32,
-    0x1.c3bd650fc2986p-36, 0x1.816193166d0f9p-40};
+// exp2(x * log2(error_norm)).  Both functions are table driven (tables in
+// shared memory, one LDS.128 + one LDS.64 / one LDS.128 per call; generated by
+// tools/gen_math_tables.py) followed by a short polynomial:
+//   log2:  x = 2^e m,  i = top 7 mantissa bits,  r = fma(m, inv_i, -1), |r| < 2^-8,
+//          log2 x = (e + L_hi) + fma(r, q(r), L_lo)              10 fp64 operations
+//   exp2:  z = n + j/64 + r, |r| <= 2^-7,  2^z = 2^n (T_hi + fma(T_hi, p(r), T_lo))
+//                                                                 10 fp64 operations
+// max error 1.2 ulp (exp2) / 1 ulp, and 1.2e-16 absolute near x = 1 (log2),
+// measured against mpmath.  The kernel is bound by instruction issue (an fp64
+// instruction occupies its scheduler for two cycles, anything else for one),
+// so what counts is the number of operations, not the depth of the chain.
+// Every operation is an IEEE add / mul / fma on table constants: the C oracle
+// (oracle/xsq_devmath.h) repeats them bit for bit.
+// The *_core forms are total functions on bit patterns (finite garbage for 0,
+// Inf, NaN); the callers decide those cases before they use the value.
 static __constant__ __align__(16) double c_xsq_havg[2] = {0.9, 0.1};       // common.py:372
-static __constant__ __align__(16) double c_xsq_misc[2] = {0x1.71547652b82fep+0,   // 1/ln 2
-                                            0x1.8p52};              // rint magic
 
-__device__ __forceinline__ double log2_fast(double x) {
+struct MathTabs {
+    double lg[128 * 4];      // inv_i, L_hi, L_lo, pad
+    double e2[64 * 2];       // T_hi, T_lo
+};
+__device__ __forceinline__ MathTabs& math_tabs() {
+    __shared__ __align__(16) MathTabs s;
+    return s;
+}
+// every kernel that calls log2_* / exp2_* runs this first (all threads)
+__device__ __forceinline__ void math_tabs_init() {
+    MathTabs& m = math_tabs();
+    for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) m.lg[i] = c_xsq_lg_tab[i];
+    for (int i = threadIdx.x; i < 64 * 2; i += blockDim.x) m.e2[i] = c_xsq_e2_tab[i];
+    __syncthreads();
+}
+
+// arithmetic of log2 / exp2 on table entries already loaded (shared by the
+// pointer forms below and the explicit shared-address forms of xsq_rk_fast.cuh)
+__device__ __forceinline__ int log2_tab_offset(double x) {      // in doubles
+    return (__double2hiint(x) >> 11) & (127 << 2);
+}
+__device__ __forceinline__ double log2_arith(double x, double inv, double l_hi, double l_lo) {
     const int hi = __double2hiint(x);
-    // 0 -> -inf, +inf -> +inf, NaN -> NaN by selects at the end (no branch on
-    // the critical path); a subnormal argument gives an (irrelevant) finite
-    // value: such an error norm is below the tiny_err threshold anyway
-    int e = (hi >> 20) - 1023;
-    int mhi = (hi & 0x000fffff) | 0x3ff00000;
-    if (mhi >= 0x3ff6a09f) {            // m in [sqrt(1/2), sqrt(2))
-        mhi -= 0x00100000;
-        ++e;
-    }
-    const double f = __hiloint2double(mhi, __double2loint(x)) - 1.0;
-    const double s = f * rcp_fast(2.0 + f);
-    const double z = s * s;
-    // R(z) = z*(Lg1 + z*(Lg2 + ...)), Estrin's scheme: the controller is a
-    // serial tail of every attempt, so dependency depth (4 instead of 8
-    // dependent DFMAs) matters more than the two extra multiplies
-    const double z2 = z * z, z4 = z2 * z2;
-    const double a0 = fma(c_xsq_lg[1], z, c_xsq_lg[0]);
-    const double a1 = fma(c_xsq_lg[3], z, c_xsq_lg[2]);
-    const double a2 = fma(c_xsq_lg[5], z, c_xsq_lg[4]);
-    const double b0 = fma(a1, z2, a0);
-    const double b1 = fma(c_xsq_lg[6], z2, a2);
-    const double r = fma(b1, z4, b0) * z;
-    const double hfsq = 0.5 * f * f;
-    const double lg = f - (hfsq - s * (hfsq + r));      // ln(1 + f)
-    double r2 = fma(lg, c_xsq_misc[0], (double)e);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double r = fma(m, inv, -1.0);
+    double q = fma(r, c_xsq_lg_pol[5], c_xsq_lg_pol[4]);
+    q = fma(r, q, c_xsq_lg_pol[3]);
+    q = fma(r, q, c_xsq_lg_pol[2]);
+    q = fma(r, q, c_xsq_lg_pol[1]);
+    q = fma(r, q, c_xsq_lg_pol[0]);
+    const double t = fma(r, q, l_lo);
+    // (double)e without a conversion instruction: 2^52 + 2^51 + e, exact
+    const double ed = __hiloint2double(0x43380000, e) - 0x1.8p52;
+    return (ed + l_hi) + t;
+}
+__device__ __forceinline__ double log2_core(double x) {
+    const double* T = math_tabs().lg + log2_tab_offset(x);
+    const double2 t01 = *reinterpret_cast<const double2*>(T);
+    return log2_arith(x, t01.x, t01.y, T[2]);
+}
+
+// |z| < 1000, so 2^n never leaves the exponent range
+struct Exp2Split { double r; int N; };
+__device__ __forceinline__ Exp2Split exp2_split(double z) {
+    const double t = z + 0x1.8p46;                     // rounds z to a multiple of 1/64
+    Exp2Split s;
+    s.N = __double2loint(t);                           // 64 n + j
+    s.r = z - (t - 0x1.8p46);                          // |r| <= 2^-7, exact
+    return s;
+}
+__device__ __forceinline__ double exp2_arith(const Exp2Split& s, double t_hi, double t_lo) {
+    double p = fma(s.r, c_xsq_e2_pol[4], c_xsq_e2_pol[3]);
+    p = fma(s.r, p, c_xsq_e2_pol[2]);
+    p = fma(s.r, p, c_xsq_e2_pol[1]);
+    p = fma(s.r, p, c_xsq_e2_pol[0]);
+    p = s.r * p;                                        // 2^r - 1
+    const double v = fma(t_hi, p, t_lo) + t_hi;
+    return __hiloint2double(__double2hiint(v) + ((s.N >> 6) << 20), __double2loint(v));
+}
+__device__ __forceinline__ double exp2_core(double z) {
+    const Exp2Split s = exp2_split(z);
+    const double2 T = *reinterpret_cast<const double2*>(math_tabs().e2 + ((s.N & 63) << 1));
+    return exp2_arith(s, T.x, T.y);
+}
+
+// log2 with the special values: 0 -> -inf, +inf -> +inf, NaN -> NaN (a
+// subnormal argument gives an irrelevant finite value: such an error norm is
+// below the tiny_err threshold anyway)
+__device__ __forceinline__ double log2_fast(double x) {
+    double r2 = log2_core(x);
     if (x == 0.0) r2 = -XSQ_INF;
     if (!(x < XSQ_INF)) r2 = x;
     return r2;
 }
-
+// exp2 for |z| < 1000; a non-finite z yields NaN, which the caller's
+// max()/min() absorb exactly like the reference's max(min_factor, nan)
 __device__ __forceinline__ double exp2_fast(double z) {
-    // |z| <= 0.25 * 1075 here, so 2^n never leaves the exponent range; a
-    // non-finite z yields NaN, which the caller's max()/min() absorb exactly
-    // like the reference's max(min_factor, nan)
-    const double t = z + c_xsq_misc[1];
-    const int n = __double2loint(t);
-    const double r = z - (t - c_xsq_misc[1]);           // |r| <= 1/2, exact
-    // degree-13 polynomial by Estrin's scheme (depth 4 instead of 13)
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = fma(c_xsq_e2[1], r, c_xsq_e2[0]);
-    const double a1 = fma(c_xsq_e2[3], r, c_xsq_e2[2]);
-    const double a2 = fma(c_xsq_e2[5], r, c_xsq_e2[4]);
-    const double a3 = fma(c_xsq_e2[7], r, c_xsq_e2[6]);
-    const double a4 = fma(c_xsq_e2[9], r, c_xsq_e2[8]);
-    const double a5 = fma(c_xsq_e2[11], r, c_xsq_e2[10]);
-    const double a6 = fma(c_xsq_e2[13], r, c_xsq_e2[12]);
-    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2);
-    const double b2 = fma(a5, r2, a4);
-    const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
-    const double p = fma(d1, r8, d0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    if (!(fabs(z) < 1000.0)) return XSQ_NAN;
+    return exp2_core(z);
 }
 
 // 1/x to ~2^-40: seed + ONE Newton step.  Used for err/scale only: the error
@@ -234,6 +254,35 @@ __device__ __forceinline__ double rcp_scale(double x) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     const double e = fma(-x, r, 1.0);
     return fma(r, e, r);
+}
+
+// ---- the step-size controller, common.py:249-287 ---------------------------
+// factor by which h_abs is multiplied after an attempt.  l2 / l2_old are
+// log2_core(ss) of this attempt and of the last accepted step (ss = sum of
+// squares of err/scale); the caller has decided accept / tiny / the flags.
+// Accepting and rejecting lanes share ONE exp2; a NaN / Inf error norm is
+// handled by the caller (`bad`: the reference's max(0.2, nan) is 0.2).
+//   z_extra: minalpha * log2(h / h_prev), or 0 (all built-in presets)
+struct Exp2Default {
+    __device__ __forceinline__ double operator()(double z) const { return exp2_core(z); }
+};
+template <bool EXTRA, class E2 = Exp2Default>
+__device__ __forceinline__ double ctl_factor(const RkDev& P, double l2, double l2_old,
+                                             double z_extra, bool accept, bool second,
+                                             bool rej, bool tiny, double max_factor,
+                                             E2 e2 = E2()) {
+    const double z_std = fma(P.ctl_a1s, l2, P.ctl_a0s);
+    double z_sc = fma(P.ctl_a1c, l2, fma(P.ctl_a2c, l2_old, P.ctl_a0c));
+    if (EXTRA) z_sc += z_extra;
+    const double raw = e2(second ? z_sc : z_std);
+    // max(min_factor, .) on rejection and in the second order branch only
+    double factor = raw;
+    if ((!accept || second) && !(raw > kMinFactor)) factor = kMinFactor;
+    // min(max_factor, .) in the second order branch; min(1, .) after a rejection
+    const double hi = (accept && rej) ? 1.0 : (second ? max_factor : XSQ_INF);
+    if (!(factor < hi)) factor = hi;
+    if (accept && tiny) factor = rej ? 1.0 : max_factor;
+    return factor;
 }
 
 // RMS norm, common.py:64-66
@@ -377,14 +426,16 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
 #pragma unroll
     for (int c = 0; c < NL; ++c) {
         const double etol = fma(P.rtol, fabs(y[c]), atol_of<R>(P, c, lane));
-        const double te = log10(etol);
+        // log10(etol) in the reference; 10^(c log10 x) = 2^(c log2 x), and the
+        // table-driven log2 / exp2 are repeated bit for bit by the C oracle
+        const double te = log2_fast(etol);
         tolsum += te;
         tolmin = fmin(tolmin, te);
     }
     tolsum = sys_sum<R::WARP>(tolsum);
     tolmin = fmin(sys_min<R::WARP>(tolmin), big);
     const double tolp =
-        pow(10.0, 0.5 * (tolsum / (double)R::N + tolmin) / (double)(morder + 1));
+        exp2_fast(0.5 * (tolsum / (double)R::N + tolmin) / (double)(morder + 1));
     double h = absdx;
     if (ydpb == 0.0 && fbnd == 0.0) {
         if (tolp < 1.0) h = absdx * tolp;
@@ -408,6 +459,7 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
 // time (~15 % of the run for trajectories of a few hundred steps).
 template <class R>
 __device__ __forceinline__ void ens_init_body(const RkDev& P) {
+    math_tabs_init();
     const int lane = threadIdx.x & 31;
     const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long idx = R::WARP ? gthread / 32 : gthread;
@@ -755,7 +807,7 @@ struct Lane {
     static constexpr int KROWS = (Tab::VARIANT == tab::BS5V) ? S + 4 : S + 1;
 
     long long sys;          // trajectory index
-    double t, h_abs, h_prev, lerr_old, max_factor, min_step;  // lerr_old = log2(error_norm_old)
+    double t, h_abs, h_prev, l2_old, max_factor, min_step;  // l2_old: log2_core(ss) of the last accepted step
     double y[NL], f[NL], prm[R::NPL];
     // nfev holds only the evaluations made outside the hot loop (f0, h_start,
     // BS5 extra stages); the per-attempt evaluations are added in store() from
@@ -821,7 +873,7 @@ struct Lane {
         step_rejected = false;
         max_factor = kMaxFactor0;
         h_prev = 0.0;
-        lerr_old = 0.0;
+        l2_old = 0.0;
         min_step = 0.0;
         if constexpr (Tab::VARIANT == tab::CKDISCV) {
             ck.tw[0] = 1.5;
@@ -900,8 +952,9 @@ struct Lane {
         double ss = 0.0;
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
-            const double scale = fma(P.rtol, pymax(fabs(y[c]), fabs(yref[c])),
-                                     atol_of<R>(P, c, lane));
+            // max(|y|, |yref|): pick the operand, |.| is a free modifier of the fma
+            const double big = fabs(yref[c]) > fabs(y[c]) ? yref[c] : y[c];
+            const double scale = fma(P.rtol, fabs(big), atol_of<R>(P, c, lane));
             const double q = errv[c] * rcp_scale(scale);
             ss = fma(q, q, ss);
         }
@@ -1554,26 +1607,18 @@ struct Lane {
         }
         const bool tiny_err = ss < NTOT * 0x1.0p-1022;       // err < sqrt(tiny)
         const bool second = accept && !standard_sc;          // 2nd-order SC
-        const double b1h = 0.5 * (second ? P.minbeta1 : P.err_exp);
-        double zc = -b1h * P.log2n;
-        if (second) zc = fma(P.minbeta2, lerr_old, zc);
-        if (P.minalpha != 0.0 && second)
-            zc = fma(P.minalpha, log2_fast(h / h_prev), zc);
-        const double cfac = second ? P.safety_sc : P.safety;
-        const bool clamp_lo = !accept || second;     // max(min_factor, .)
-        double hi = second ? max_factor : XSQ_INF;   // min(max_factor, .)
-        double tiny_val = max_factor;
-        if (accept && step_rejected) {               // factor = min(1, factor)
-            hi = pymin(1.0, hi);
-            tiny_val = pymin(1.0, tiny_val);
+        const double l2ss = log2_core(ss);
+        double factor;
+        if (P.minalpha != 0.0) {          // user sc_params with an alpha term (uniform branch)
+            const double z_extra = second ? P.minalpha * log2_fast(h / h_prev) : 0.0;
+            factor = ctl_factor<true>(P, l2ss, l2_old, z_extra, accept, second, step_rejected,
+                                      tiny_err, max_factor);
+        } else {
+            factor = ctl_factor<false>(P, l2ss, l2_old, 0.0, accept, second, step_rejected,
+                                       tiny_err, max_factor);
         }
-        const double l2ss = log2_fast(ss);
-        const double raw = cfac * exp2_fast(fma(b1h, l2ss, zc));
-        double factor = clamp_lo ? pymax(kMinFactor, raw) : raw;
-        factor = pymin(hi, factor);
-        if (accept && tiny_err) factor = tiny_val;
+        if (bad || (pre_reject && !(ss < XSQ_INF))) factor = kMinFactor;   // max(0.2, nan)
         h_abs *= factor;
-        const double lerr = 0.5 * (l2ss - P.log2n);  // log2(error_norm)
         if (!accept) {
             step_rejected = true;
             ++n_rej;
@@ -1596,7 +1641,7 @@ struct Lane {
 #endif
         // common.py:294-303
         h_prev = h;
-        lerr_old = lerr;
+        l2_old = l2ss;
         t = t_end;
 #pragma unroll
         for (int c = 0; c < NL; ++c) { y[c] = y_new[c]; f[c] = K[S][c]; }
@@ -1684,6 +1729,9 @@ struct Lane {
         return urgent;
     }
 
+    static __device__ __forceinline__ bool probes_urgent() {
+        return (stiff_state().bits[threadIdx.x] & SB_PEND2) != 0u;
+    }
     static __device__ __forceinline__ bool probes_pending() {
         return (stiff_state().bits[threadIdx.x] & (SB_PEND1 | SB_PEND2)) != 0u;
     }
@@ -1770,6 +1818,7 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     bool live = false;
     bool exhausted = false;
     const bool fast = P.n_forced == 0 && P.n_eval == 0;
+    math_tabs_init();
     Lane<Tab, R>::stiff_state().bits[threadIdx.x] = 0u;
     // Stiffness probes wait in their slots until kProbeWindow attempts have
     // passed, so that one pass serves many lanes of the warp (a trajectory may

@@ -1,0 +1,545 @@
+// xsq_rk_fast.cuh -- the ensemble hot path: adaptive stepping of a generic
+// embedded pair (Ts5, CK5, Me4, Pr7, Pr8, Pr9), one trajectory per thread, final
+// state only (no t_eval, no events, no forced steps, default step budget,
+// controller presets without the alpha term).  Same arithmetic, operation by
+// operation, as rk_persistent<Tab, R> in xsq_rk_core.cuh (the results of the
+// two kernels are bit-identical; tests/test_gpu_rk.py asserts it) -- what
+// differs is how the instructions are spent.
+//
+// Measured on B200 (profiles/r01_*): the persistent kernel is bound by
+// instruction ISSUE, not by the depth of its dependency chains: an fp64
+// instruction occupies its scheduler for two cycles and any other instruction
+// for one, and   2 * (fp64 instructions) + (other instructions)   per attempted
+// step reproduces the measured time within 2 % (749 predicted / 747 measured
+// cycles per warp and attempt for Ts5/Lorenz).  So this kernel minimises
+// instructions:
+//   * tableau coefficients are streamed from shared memory in the order of
+//     use, two per LDS.128; none lives in a uniform register, so the 40-odd
+//     MOV.SPILL / R2UR.FILL / UMOV per attempt of the generic kernel are gone;
+//   * accept / tiny / overflow are integer compares on the high word of the
+//     sum of squares (exact: it is non-negative and the thresholds have a zero
+//     low word);
+//   * _reassess_stepsize (common.py:310-331) runs once per ACCEPTED step behind
+//     three integer compares that prove "nothing to do" (h far from min_step,
+//     max_step and t_bound), falling back to the exact code otherwise;
+//     min_step itself is only formed when h_abs gets within reach of it;
+//   * one exit per attempt: the status is a value, not a control-flow path, so
+//     the loop-carried state is moved once;
+//   * lane flags (standard_sc, step_rejected, max_factor == 4) are bits of one
+//     register; the trajectory index is 32 bit.
+// Reference (file:line in /root/reference/extensisq): common.py:222-356
+// (_step_impl, _reassess_stepsize, _comp_sol_err, _rk_stage), :370-516
+// (_diagnose_stiffness bookkeeping).
+#pragma once
+#include "xsq_rk_core.cuh"
+
+namespace xsq {
+
+// compile-time loop: f(IC<B>{}), ..., f(IC<E-1>{})
+template <int V>
+struct IC { static constexpr int value = V; };
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// ---- coefficient stream ------------------------------------------------------
+// Rows A[1..S-1], B, E with their structural zeros removed, each row padded to
+// an even number of doubles: row I starts at coef_base<Tab>(I), the k-th
+// nonzero of a row sits at base + k.
+template <class Tab>
+struct CoefLayout {
+    static constexpr int S = Tab::S;
+    static constexpr int ROW_B = S, ROW_E = S + 1, ROW_C = S + 2, NROWS = S + 3;
+    XSQ_HD static constexpr int row_len(int row) { return row < S ? row : (row == ROW_E ? S + Tab::FSAL : S); }
+    XSQ_HD static constexpr double value(int row, int j) {
+        return row < S ? Tab::a(row, j)
+             : row == ROW_B ? Tab::b(j)
+             : row == ROW_E ? Tab::e(j) : Tab::c(j);
+    }
+    XSQ_HD static constexpr int nnz(int row) {
+        int n = 0;
+        for (int j = 0; j < row_len(row); ++j) n += value(row, j) != 0.0 ? 1 : 0;
+        return n;
+    }
+    XSQ_HD static constexpr int base(int row) {
+        int b = 0;
+        for (int r = 1; r < row; ++r) b += (nnz(r) + 1) & ~1;
+        return b;
+    }
+    XSQ_HD static constexpr int index(int row, int j) {     // position of (row, j) in its row
+        int k = 0;
+        for (int jj = 0; jj < j; ++jj) k += value(row, jj) != 0.0 ? 1 : 0;
+        return k;
+    }
+    static constexpr int TOTAL = base(NROWS);
+};
+
+template <class Tab>
+struct FastShared {
+    double coef[CoefLayout<Tab>::TOTAL + 2];
+};
+
+// 32-bit shared-memory addresses, formed once per thread and kept opaque so
+// that they stay in registers (re-deriving one costs three instructions)
+struct SmemAddr {
+    unsigned coef, lg, e2;
+};
+__device__ __forceinline__ double log2_core_s(double x, unsigned lg) {
+    const unsigned a = lg + (unsigned)log2_tab_offset(x) * 8u;
+    double inv, l_hi, l_lo;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(inv), "=d"(l_hi) : "r"(a));
+    asm("ld.shared.f64 %0, [%1+16];" : "=d"(l_lo) : "r"(a));
+    return log2_arith(x, inv, l_hi, l_lo);
+}
+struct Exp2Shared {
+    unsigned e2;
+    __device__ __forceinline__ double operator()(double z) const {
+        const Exp2Split s = exp2_split(z);
+        double t_hi, t_lo;
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t_hi), "=d"(t_lo)
+            : "r"(e2 + ((unsigned)(s.N & 63) << 4)));
+        return exp2_arith(s, t_hi, t_lo);
+    }
+};
+
+// two consecutive doubles of the stream (OFF even: one LDS.128), or one
+template <int OFF>
+__device__ __forceinline__ void coef_ld2(unsigned base, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a), "=d"(b) : "r"(base), "n"(OFF * 8));
+}
+template <int OFF>
+__device__ __forceinline__ void coef_ld1(unsigned base, double& a) {
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(a) : "r"(base), "n"(OFF * 8));
+}
+
+template <class Tab, int ROW>
+struct CoefRow {
+    using L = CoefLayout<Tab>;
+    static constexpr int NNZ = L::nnz(ROW);
+    static constexpr int BASE = L::base(ROW);
+    double w[NNZ > 0 ? ((NNZ + 1) & ~1) : 2];
+    template <int Q>
+    __device__ __forceinline__ void load_from(unsigned base) {
+        if constexpr (2 * Q + 1 < NNZ) {
+            coef_ld2<BASE + 2 * Q>(base, w[2 * Q], w[2 * Q + 1]);
+            load_from<Q + 1>(base);
+        } else if constexpr (2 * Q < NNZ) {
+            coef_ld1<BASE + 2 * Q>(base, w[2 * Q]);
+        }
+    }
+    __device__ __forceinline__ explicit CoefRow(unsigned base) { load_from<0>(base); }
+    // coefficient of column J (a structural nonzero)
+    template <int J>
+    __device__ __forceinline__ double at() const { return w[L::index(ROW, J)]; }
+};
+
+template <class Tab, int ROW>
+__device__ __forceinline__ void coef_fill_row(double* coef) {
+    using L = CoefLayout<Tab>;
+    if constexpr (ROW < L::NROWS) {
+        static_for<0, L::row_len(ROW)>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (L::value(ROW, j) != 0.0) {
+                double v;
+                if constexpr (ROW < L::S) v = Tab::av(ROW, j);
+                else if constexpr (ROW == L::ROW_B) v = Tab::bv(j);
+                else if constexpr (ROW == L::ROW_E) v = Tab::ev(j);
+                else v = Tab::cv(j);
+                coef[L::base(ROW) + L::index(ROW, j)] = v;
+            }
+        });
+        coef_fill_row<Tab, ROW + 1>(coef);
+    }
+}
+
+// high word of a non-negative double whose low word is zero
+__host__ __device__ constexpr unsigned hi_word_of_small_int(int n) {
+    // n = m * 2^e with 1 <= m < 2:  (1023 + e) << 20 | top 20 mantissa bits
+    int e = 0;
+    while ((n >> (e + 1)) != 0) ++e;
+    const unsigned frac = ((unsigned)n << (20 - e)) & 0xfffffu;   // n < 2^20
+    return ((unsigned)(1023 + e) << 20) | frac;
+}
+
+// FL_SLOW: this step began on the exact path of _reassess_stepsize
+enum : unsigned { FL_STD = 1u, FL_REJ = 2u, FL_MF4 = 4u, FL_SLOW = 8u };
+
+template <class Tab, class R>
+struct FastLane {
+    static constexpr int S = Tab::S;
+    static constexpr int NL = R::NL;
+    using L = CoefLayout<Tab>;
+    using SS = typename Lane<Tab, R>::StiffState;
+    static_assert(Tab::VARIANT == tab::GENERIC && !R::WARP, "fast kernel: generic pairs, lane per system");
+
+    double t, h_abs, l2_old;
+    double y[NL], f[NL], prm[R::NPL];
+    int sys, n_acc, n_rej, nfev0;
+    unsigned fl;
+
+    // RungeKutta.__init__ (common.py:187-220) from what ens_init left
+    __device__ __forceinline__ void init(const RkDev& P, int idx, double* h0) {
+        sys = idx;
+        t = P.t0;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            y[k] = P.y0[(long long)k * P.n_lanes + idx];
+            f[k] = P.init_f0[(long long)k * P.n_lanes + idx];
+        }
+        R::load_params(P.params, idx, P.n_lanes, 0, prm);
+        n_acc = n_rej = 0;
+        nfev0 = P.init_nfev[idx];
+        fl = FL_STD;
+        l2_old = 0.0;
+        h_abs = P.first_step > 0.0 ? P.first_step : P.init_h[idx];
+        SS& ss = Lane<Tab, R>::stiff_state();
+        ss.bits[threadIdx.x] &= Lane<Tab, R>::SB_PEND1 | Lane<Tab, R>::SB_PEND2;
+        ss.hot[threadIdx.x].havg = 0.0;
+        ss.hot[threadIdx.x].next_many = P.stiff_many_steps > 1 ? P.stiff_many_steps - 1 : 1;
+        ss.hot[threadIdx.x].cnt = 20;           // here: the NEXT okstp at which the window closes
+        ss.rej_base[threadIdx.x] = 0;
+        h0[threadIdx.x] = h_abs;
+    }
+
+    // _reassess_stepsize, common.py:310-331, exact; d = |t_bound - t|.  Returns
+    // false when the step is too small (common.py:234).
+    __device__ __forceinline__ static bool reassess_exact(const RkDev& P, double t, double d,
+                                                       double& h_abs, unsigned& fl) {
+        const double min_step = pymax(Tab::H_MIN_A * (fabs(t) + h_abs), XSQ_SQRT_TINY);
+        if (h_abs < min_step || h_abs > P.max_step) {
+            h_abs = pymin(P.max_step, pymax(min_step, h_abs));
+            fl |= FL_STD;
+        }
+        if (d < 2.0 * h_abs) {
+            if (d > h_abs) {
+                h_abs = pymax(0.5 * d, min_step);
+                fl |= FL_STD;
+            } else {
+                h_abs = d;
+            }
+        }
+        return !(h_abs < min_step);
+    }
+
+    template <int I>
+    __device__ __forceinline__ void stage(unsigned cb, double (&K)[S + 1][NL], double h) {
+        const CoefRow<Tab, I> a(cb);
+        double ys[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            double acc = 0.0;
+            static_for<0, I>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (Tab::a(I, j) != 0.0) {
+                    if constexpr (L::index(I, j) == 0) acc = a.template at<j>() * K[j][c];
+                    else acc = fma(a.template at<j>(), K[j][c], acc);
+                }
+            });
+            ys[c] = fma(h, acc, y[c]);
+        }
+        // right-hand sides of the ensemble path are autonomous or take t from
+        // the tableau image; t + c_i h is dead code for the built-in ones
+        R::f(__dadd_rn(t, __dmul_rn(Tab::cv(I), h)), ys, prm, K[I]);
+    }
+    template <int I>
+    __device__ __forceinline__ void stages(unsigned cb, double (&K)[S + 1][NL], double h) {
+        if constexpr (I < S) {
+            stage<I>(cb, K, h);
+            stages<I + 1>(cb, K, h);
+        }
+    }
+
+    // One attempt of a step; returns the lane status.  `cb`: shared-memory
+    // address of the coefficient stream, `h0`: this thread's word of the
+    // "h_abs at the start of the step" array.
+    __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa, double* h0) {
+        const unsigned cb = sa.coef;
+        constexpr unsigned HI_N = hi_word_of_small_int(R::N);          // (double)N
+        constexpr unsigned HI_TINY = HI_N - (1022u << 20);             // N * 2^-1022
+        const double h = h_abs * P.direction;
+        double K[S + 1][NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) K[0][c] = f[c];
+        stages<1>(cb, K, h);
+        // _comp_sol_err, common.py:341-351
+        double y_new[NL], errv[NL];
+        {
+            const CoefRow<Tab, L::ROW_B> b(cb);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double sb = 0.0;
+                static_for<0, S>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    if constexpr (Tab::b(i) != 0.0) sb = fma(b.template at<i>(), K[i][c], sb);
+                });
+                y_new[c] = fma(h, sb, y[c]);
+            }
+        }
+        const double t_new = t + h;
+        if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+        double ss = 0.0;
+        {
+            const CoefRow<Tab, L::ROW_E> e(cb);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double se = 0.0;
+                static_for<0, S + Tab::FSAL>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    if constexpr (Tab::e(i) != 0.0) se = fma(e.template at<i>(), K[i][c], se);
+                });
+                errv[c] = h * se;
+                const double big = fabs(y_new[c]) > fabs(y[c]) ? y_new[c] : y[c];
+                const double scale = fma(P.rtol, fabs(big), P.atol[c]);
+                const double q = errv[c] * rcp_scale(scale);
+                ss = fma(q, q, ss);
+            }
+        }
+        // ss >= 0 or NaN; N and N * 2^-1022 have a zero low word, so these are
+        // exactly  ss < N,  !(ss < inf),  ss < N * 2^-1022  of the generic kernel
+        const unsigned sh = (unsigned)__double2hiint(ss);
+        const bool accept = sh < HI_N;
+        const bool bad = sh >= 0x7ff00000u;
+        const bool tiny = sh < HI_TINY;
+        const bool rej = (fl & FL_REJ) != 0u;
+        const bool second = accept && !(fl & FL_STD);
+        int st = LANE_RUNNING;
+        if (accept) {
+            // f(t+h, y_new) of non-FSAL pairs (common.py:289-291) and the
+            // stiffness bookkeeping (common.py:306) while errv is live
+            if constexpr (!Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+            if (P.nfev_stiff_detect > 0 && diagnose(P, K, errv, y_new, t_new, h)) st = LANE_FLUSH;
+        }
+        const double l2 = log2_core_s(ss, sa.lg);
+        const double factor = ctl_factor<false>(P, l2, l2_old, 0.0, accept, second, rej, tiny,
+                                                (fl & FL_MF4) ? kMaxFactor : kMaxFactor0,
+                                                Exp2Shared{sa.e2});
+        h_abs *= factor;
+        // common.py:294-303 -- selects, not a branch, so the moves exist once
+        l2_old = accept ? l2 : l2_old;
+        t = accept ? t_new : t;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            y[c] = accept ? y_new[c] : y[c];
+            f[c] = accept ? K[S][c] : f[c];
+        }
+        // "certainly above min_step": min_step <= max(H_MIN_A (|t| + h0), sqrt(tiny))
+        // and h0 <= span / 2 whenever the step started on the short path below
+        const unsigned hh = (unsigned)__double2hiint(h_abs);
+        if (!accept) {
+            fl |= FL_REJ;
+            ++n_rej;
+            if (bad) {                                    // common.py:280-287
+                h_abs = kMinFactor * fabs(h);             // max(0.2, nan) * h_abs
+                st = LANE_OVERFLOW;
+            } else if (hh <= (unsigned)P.fast_hi_min || (fl & FL_SLOW)) {
+                const double min_step =
+                    pymax(Tab::H_MIN_A * (fabs(t) + h0[threadIdx.x]), XSQ_SQRT_TINY);
+                if (h_abs < min_step) st = LANE_TOO_SMALL;               // common.py:234
+            }
+        } else {
+            fl = (tiny ? FL_STD : 0u) | (fl & FL_MF4);
+            if ((unsigned)__double2hiint(factor) < 0x40100000u) fl |= FL_MF4;   // factor < 4
+            ++n_acc;
+            // OdeSolver.step, base.py:207-208, then the next step's
+            // _reassess_stepsize: nothing to do when  min_step < h_abs <
+            // max_step  and  2 h_abs < |t_bound - t|, each proven on high words
+            const double s = t - P.t_bound;
+            if (P.direction * s >= 0.0) {
+                st = LANE_FINISHED;
+            } else {
+                const unsigned dh = (unsigned)__double2hiint(s) & 0x7fffffffu;
+                h0[threadIdx.x] = h_abs;
+                if (hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span ||
+                    (int)(dh - hh) <= 0x100000) {
+                    if (!reassess_exact(P, t, fabs(s), h_abs, fl)) st = LANE_TOO_SMALL;
+                    fl |= FL_SLOW;
+                }
+            }
+        }
+        return st;
+    }
+
+    // _diagnose_stiffness, common.py:370-516 -- same bookkeeping and the same
+    // probe records as Lane::diagnose (xsq_rk_core.cuh); `cnt` holds the okstp
+    // at which the current window closes instead of a countdown, so the common
+    // case is a load, the running mean of h, two compares and a store.
+    __device__ __forceinline__ bool diagnose(const RkDev& P, double (&K)[S + 1][NL],
+                                             const double (&errv)[NL],
+                                             const double (&y_new)[NL], double t_new, double h) {
+        SS& ss = Lane<Tab, R>::stiff_state();
+        const double2 hot = *reinterpret_cast<const double2*>(&ss.hot[threadIdx.x]);
+        double havg = c_xsq_havg[0] * hot.x + c_xsq_havg[1] * h;
+        const int next_many = __double2loint(hot.y), next_cnt = __double2hiint(hot.y);
+        const int okstp = n_acc + 1;
+        if (okstp != next_many && okstp != next_cnt) {
+            ss.hot[threadIdx.x].havg = havg;
+            return false;
+        }
+        return diagnose_event(P, K, errv, y_new, t_new, h, havg, next_many, next_cnt);
+    }
+
+    __device__ __forceinline__ bool diagnose_event(const RkDev& P, double (&K)[S + 1][NL],
+                                                const double (&errv)[NL],
+                                                const double (&y_new)[NL], double t_new,
+                                                double h, double havg, int next_many,
+                                                int next_cnt) {
+        SS& ss = Lane<Tab, R>::stiff_state();
+        const int okstp = n_acc + 1;
+        const bool toomch = okstp == next_many;
+        bool lotsfl = false;
+        if (okstp == next_cnt) {                  // okstp == 20 or okstp % 40 == 39
+            if (okstp == 20) {
+                havg = h;
+                next_cnt = 39;
+            } else {
+                lotsfl = n_rej - ss.rej_base[threadIdx.x] >= 10;
+                next_cnt += 40;
+            }
+            ss.rej_base[threadIdx.x] = n_rej;                // jflstp = 0
+        }
+        if (toomch) next_many += P.stiff_many_steps;
+        *reinterpret_cast<double2*>(&ss.hot[threadIdx.x]) =
+            make_double2(havg, __hiloint2double(next_cnt, next_many));
+        if (!(toomch || lotsfl)) return false;
+        using SL = StiffSlot<R>;
+        double* s = nullptr;
+        long long stride = 1;
+        if (P.stiff_q_cap > 0) {
+            const unsigned long long qi = atomicAdd(P.stiff_q_count, 1ULL);
+            if (qi < (unsigned long long)P.stiff_q_cap) s = P.stiff_q + qi * SL::DOUBLES;
+        }
+        bool urgent = false;
+        if (s == nullptr) {                       // queue full: the thread's slots
+            unsigned sbits = ss.bits[threadIdx.x];
+            stride = P.stiff_threads;
+            const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const int islot = (sbits & Lane<Tab, R>::SB_PEND1) ? 1 : 0;
+            s = P.stiff_slot + (long long)islot * SL::DOUBLES * stride + gtid;
+            sbits += Lane<Tab, R>::SB_PEND1;
+            urgent = (sbits & Lane<Tab, R>::SB_PEND2) != 0u;
+            ss.bits[threadIdx.x] = sbits;
+        }
+        s[0] = t_new;
+        s[stride] = h;
+        s[2 * stride] = havg;
+        s[3 * stride] = lotsfl ? 1.0 : 0.0;
+        s[4 * stride] = __longlong_as_double((long long)sys);
+        s += SL::HEAD * stride;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            s[c * stride] = y_new[c];
+            s[(NL + c) * stride] = y[c];
+            s[(2 * NL + c) * stride] = K[S][c];
+            s[(3 * NL + c) * stride] = errv[c];
+        }
+#pragma unroll
+        for (int c = 0; c < R::NPL; ++c) s[(4 * NL + c) * stride] = prm[c];
+        return urgent;
+    }
+
+    __device__ __forceinline__ void store(const RkDev& P, int st) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) P.y_final[(long long)k * P.n_lanes + sys] = y[k];
+        P.t_final[sys] = t;
+        if (P.h_next) P.h_next[sys] = h_abs;
+        P.n_acc[sys] = n_acc;
+        P.n_rej[sys] = n_rej;
+        P.nfev[sys] = nfev0 + (S - 1 + Tab::FSAL) * (n_acc + n_rej) + (Tab::FSAL ? 0 : n_acc);
+        P.status[sys] = st;
+        if (P.n_eval_done) P.n_eval_done[sys] = 0;
+        if (P.stiff_flags)
+            P.stiff_flags[sys] = (int)((Lane<Tab, R>::stiff_state().bits[threadIdx.x] >>
+                                        Lane<Tab, R>::SB_FLAG_SHIFT) & 7u);
+    }
+};
+
+template <class Tab, class R, int BLOCK>
+__device__ __forceinline__ void rk_fast_body(const RkDev& P) {
+    using FL = FastLane<Tab, R>;
+    using LN = Lane<Tab, R>;
+    __shared__ __align__(16) FastShared<Tab> fs;
+    __shared__ double h0[BLOCK];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    math_tabs_init();
+    if (threadIdx.x == 0) coef_fill_row<Tab, 1>(fs.coef);
+    LN::stiff_state().bits[threadIdx.x] = 0u;
+    __syncthreads();
+    SmemAddr sa;
+    sa.coef = (unsigned)__cvta_generic_to_shared(fs.coef);
+    sa.lg = (unsigned)__cvta_generic_to_shared(math_tabs().lg);
+    sa.e2 = (unsigned)__cvta_generic_to_shared(math_tabs().e2);
+    asm volatile("" : "+r"(sa.coef), "+r"(sa.lg), "+r"(sa.e2));
+    FL L;
+    bool live = false, exhausted = false;
+    auto flush = [&](long long cur) {
+        if (!__any_sync(full, LN::probes_pending())) return;
+        if (LN::probes_pending()) {
+            FL parked = L;
+            asm volatile("" ::"l"(&parked) : "memory");
+            const int evals = LN::flush_probes(P, cur, lane);
+            asm volatile("" ::"l"(&parked) : "memory");
+            L = parked;
+            L.nfev0 += evals;
+        }
+        __syncwarp(full);
+    };
+    for (;;) {
+        // ---- refill: finished threads claim the next trajectories ----
+        const unsigned need = __ballot_sync(full, !live && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(P.queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (!live && !exhausted) {
+                const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (idx < P.n_lanes) {
+                    L.init(P, (int)idx, h0);
+                    live = true;
+                    int st = LANE_RUNNING;
+                    if (P.t0 == P.t_bound) {                 // scipy base.py:197
+                        st = LANE_FINISHED;
+                    } else {                                 // the first step's _reassess_stepsize
+                        if (!FL::reassess_exact(P, L.t, fabs(P.t_bound - L.t), L.h_abs, L.fl))
+                            st = LANE_TOO_SMALL;
+                        L.fl |= FL_SLOW;
+                    }
+                    if (st != LANE_RUNNING) {
+                        L.store(P, st);
+                        live = false;
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        __syncwarp(full);
+        if (__all_sync(full, !live)) break;
+        // ---- attempts, until some lane of the warp ends its trajectory ----
+        int st = LANE_RUNNING;
+        do {
+            if (live) st = L.attempt(P, sa, h0);
+        } while (!__any_sync(full, st != LANE_RUNNING));
+        // both probe slots of some thread taken (queue full): run them now
+        if (P.nfev_stiff_detect > 0 && __any_sync(full, LN::probes_urgent())) flush(live ? L.sys : -1);
+        if (st == LANE_FLUSH) st = LANE_RUNNING;
+        if (st != LANE_RUNNING) {
+            L.store(P, st);
+            live = false;
+        }
+        __syncwarp(full);
+    }
+    if (P.nfev_stiff_detect > 0) flush(-1);
+}
+
+template <class Tab, class R, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) rk_fast(const RkDev P) {
+    rk_fast_body<Tab, R, BLOCK>(P);
+}
+
+}  // namespace xsq
