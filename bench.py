@@ -56,11 +56,13 @@ def make_lanes(n, rank):
     sigma ~ U(9,11), rho ~ U(24,32), beta ~ U(2.4,2.9); one stream per rank
     (seed 12345 + rank) so shards are independent of the rank count."""
     rng = np.random.default_rng(SEED + rank)
-    y0 = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n),
-                   rng.uniform(5, 40, n)], axis=1)
-    prm = np.stack([rng.uniform(9, 11, n), rng.uniform(24, 32, n),
-                    rng.uniform(2.4, 2.9, n)], axis=1)
-    return y0, prm
+    # one row of six uniforms per lane: lane i does not depend on n, so any
+    # prefix of a shard is a true subset of it (tests/test_gpu_exact.py)
+    u = rng.random((n, 6))
+    lo = np.array([-15.0, -20.0, 5.0, 9.0, 24.0, 2.4])
+    hi = np.array([15.0, 20.0, 40.0, 11.0, 32.0, 2.9])
+    v = lo + (hi - lo) * u
+    return np.ascontiguousarray(v[:, :3]), np.ascontiguousarray(v[:, 3:])
 
 
 # ---- algorithmic flops (SURVEY.md section 8d) -------------------------------

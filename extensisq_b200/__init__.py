@@ -7,7 +7,7 @@ Nystrom, sensitivity) is out of scope.
 """
 from .tableaux import (RungeKutta, Ts5, BS5, CK5, CKdisc, Me4, Pr7, Pr8, Pr9,
                        CFMR7osc, SWAG, BUILTIN, REFERENCE_VERSION)
-from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, solve_ivp_batched, NFS,
+from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, solve_ivp_batched, NFS, trim_memory,
                       update_nfs)
 from .sharding import shard_bounds, gather_result
 from .sensitivity import sens_forward, SensitivityOutput
@@ -17,6 +17,6 @@ from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
 __version__ = "0.1.0"
 __all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "CKdisc", "Me4", "Pr7", "Pr8", "Pr9",
            "CFMR7osc", "SWAG", "DeviceRHS", "DeviceEvents", "BatchedOdeResult", "solve_ivp_batched",
-           "NFS", "update_nfs", "shard_bounds", "gather_result", "sens_forward", "SensitivityOutput", "SSV2stab",
+           "NFS", "update_nfs", "trim_memory", "shard_bounds", "gather_result", "sens_forward", "SensitivityOutput", "SSV2stab",
            "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc", "slab_of", "nfesig",
            "maxm"]

@@ -39,7 +39,7 @@ EXPORTS = [
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
     "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
-    "xsq_launch_count",
+    "xsq_launch_count", "xsq_trim_memory",
     "xsq_fp64_peak",
 ]
 
@@ -172,6 +172,7 @@ def load():
     lib.xsq_rkc_stage_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp,
                                         C.c_void_p]
     lib.xsq_launch_count.restype = C.c_int64
+    lib.xsq_trim_memory.argtypes = [C.c_int]
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]
     if lib.xsq_abi_version() != 2:

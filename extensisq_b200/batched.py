@@ -303,7 +303,16 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     if interpolant not in (None, "best", "low", "free"):
         raise ValueError("interpolant should be one of: 'best', 'low', 'free'")
 
-    with torch.cuda.device(device):
+    # Everything below -- host->device copies, transposes, result allocation and
+    # the kernels -- is enqueued on ONE stream: the caller's `stream`, made
+    # current for the duration of the call after it has waited for the work
+    # already queued on the previously current stream (the inputs may have been
+    # produced there).  Allocations made under it belong to it, so the caching
+    # allocator cannot recycle a buffer the kernel still uses.
+    run_stream = stream if stream is not None else torch.cuda.current_stream(device)
+    if stream is not None:
+        run_stream.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.device(device), torch.cuda.stream(run_stream):
         y0_t = _as_device(y0, device)
         if y0_t.ndim == 1:
             y0_t = y0_t[None, :]
@@ -427,7 +436,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
             a.t_events = t_ev.data_ptr()
             a.y_events = y_ev.data_ptr()
             a.ev_count = ev_cnt.data_ptr()
-        st = stream if stream is not None else torch.cuda.current_stream(device)
+        st = run_stream
         if is_swag:
             _lib.check(lib.xsq_swag_solve(C.byref(a), k_max,
                                           C.c_void_p(st.cuda_stream)))
@@ -443,6 +452,15 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         event_counts=ev_cnt)
     res._keepalive = (y0_soa, prm_soa, hf, atol_c)
     return res
+
+
+def trim_memory(device=None):
+    """Return the scratch the library keeps cached in the device's memory pool
+    (work queue, init pass, stiffness probe queue) to the driver."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    _lib.check(lib.xsq_trim_memory(dev.index if dev.index is not None else 0))
 
 
 def update_nfs(result):

@@ -383,12 +383,20 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         if (!warp_rhs) {
             size_t free_b = 0, total_b = 0;
             XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            qcap = N * 48;
-            size_t budget = free_b / 4;
-            if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+            // 16 records per trajectory (a probe every nfev_stiff_detect
+            // evaluations plus the rare `lotsfl` ones: 14 per lane on the
+            // 10^4-step Lorenz benchmark), at most an eighth of the free memory
+            // and 4 GB; whatever does not fit goes through the slots.  The
+            // environment override (tests) can only shrink it.
+            qcap = N * 16;
+            size_t budget = free_b / 8;
+            if (budget > ((size_t)4 << 30)) budget = (size_t)4 << 30;
             const size_t fit = budget / (rec * sizeof(double));
             if (fit < qcap) qcap = fit;
-            if (const char* e = getenv("XSQ_STIFF_QUEUE_RECORDS")) qcap = (size_t)atoll(e);
+            if (const char* e = getenv("XSQ_STIFF_QUEUE_RECORDS")) {
+                const long long want_q = atoll(e);
+                if (want_q >= 0 && (size_t)want_q < qcap) qcap = (size_t)want_q;
+            }
         }
         cudaError_t es = cudaMallocAsync(
             (void**)&slots, (2 * threads + qcap) * rec * sizeof(double), st);
@@ -608,6 +616,18 @@ int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_s
                         void* stream) {
     if (!ms_per_stage || nx < 4 || nx % 4 || rows < 1 || reps < 1) return XSQ_ERR_ARG;
     return rkc_stage_bench(nx, rows, reps, ms_per_stage, (cudaStream_t)stream);
+}
+
+int xsq_trim_memory(int device) {
+    // scratch is cached in the device's stream-ordered pool between calls
+    // (keep_pool_memory); hand it back to the driver, e.g. before another
+    // library needs the memory
+    XSQ_CUDA(cudaSetDevice(device));
+    XSQ_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    XSQ_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    XSQ_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return XSQ_OK;
 }
 
 int64_t xsq_launch_count(int reset) {

@@ -49,6 +49,7 @@ std::vector<UserEvents> g_events;         // handle = index + 1
 struct UserTab {
     bool loaded = false;
     int generation = 0;
+    unsigned long long hash = 0;      // FNV-1a of the tableau image
     xsq_tableau_t t;
     std::string src;
 } g_tab;
@@ -59,8 +60,16 @@ struct UserPde {
     bool ready = false;
     CUmodule mod = nullptr;
     CUfunction fn[3] = {nullptr, nullptr, nullptr};
+    int dev = -1;
 };
 std::vector<UserPde> g_pde;               // handle = XSQ_PDE_USER_BASE + index
+
+// NVRTC options of EVERY runtime compilation: the AOT build disables FMA
+// contraction (Makefile NVFLAGS -fmad=false: only the explicit fma() calls fuse,
+// which keeps device code bit-comparable with the C oracle), so must these.
+static const char* const kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
+                                         "--fmad=false", "-lineinfo", "-default-device"};
+static constexpr int kNumNvrtcOpts = sizeof(kNvrtcOpts) / sizeof(kNvrtcOpts[0]);
 
 struct Compiled {
     CUmodule mod = nullptr;
@@ -91,6 +100,7 @@ struct Api {
                              void**);
     CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t);
     CUresult (*CuGetErrorString)(CUresult, const char**);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
 } g_api;
 
 template <class F>
@@ -131,7 +141,8 @@ bool load_cuda() {
               bind(l, "cuLaunchKernel", &g_api.LaunchKernel) &&
               bind(l, "cuOccupancyMaxActiveBlocksPerMultiprocessor",
                    &g_api.OccupancyMaxActiveBlocks) &&
-              bind(l, "cuGetErrorString", &g_api.CuGetErrorString);
+              bind(l, "cuGetErrorString", &g_api.CuGetErrorString) &&
+              bind(l, "cuFuncSetAttribute", &g_api.FuncSetAttribute);
     if (!ok) set_detail("libcuda is missing a required symbol");
     return ok;
 }
@@ -264,8 +275,7 @@ int compile_module(const std::string& src, CUmodule* mod) {
     nvrtcResult r = g_api.CreateProgram(&prog, src.c_str(), "xsq_user.cu", kNumEmbedded,
                                         kEmbeddedSources, kEmbeddedNames);
     if (r != NVRTC_SUCCESS) { set_detail(g_api.GetErrorString(r)); return XSQ_ERR_NVRTC; }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=false"};
-    r = g_api.CompileProgram(prog, 4, opts);
+    r = g_api.CompileProgram(prog, kNumNvrtcOpts, kNvrtcOpts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
         g_api.GetProgramLogSize(prog, &n);
@@ -320,9 +330,7 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
                                         kNumEmbedded, kEmbeddedSources,
                                         kEmbeddedNames);
     if (r != NVRTC_SUCCESS) { set_detail(g_api.GetErrorString(r)); return XSQ_ERR_NVRTC; }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
-                          "-lineinfo", "-default-device"};
-    r = g_api.CompileProgram(prog, 3, opts);
+    r = g_api.CompileProgram(prog, kNumNvrtcOpts, kNvrtcOpts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
         g_api.GetProgramLogSize(prog, &n);
@@ -391,7 +399,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
         body += g_tab.src;
         tabname = "UserTab";
         s = g_tab.t.n_stages;
-        *key = "T" + std::to_string(g_tab.generation);
+        *key = "T" + std::to_string(g_tab.hash);      // content, not load count
     } else {
         const char* n = builtin_tab_name(method);
         if (!n) return XSQ_ERR_ARG;
@@ -480,6 +488,11 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     std::string src, key;
     int rc = user_build_source(method, rhs, events, &src, &key);
     if (rc != XSQ_OK) return rc;
+    {   // a CUmodule belongs to the context it was loaded in: one per device
+        int kdev = 0;
+        cudaGetDevice(&kdev);
+        key += "@" + std::to_string(kdev);
+    }
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
         Compiled c;
@@ -511,6 +524,16 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     if (rhs >= XSQ_RHS_USER_BASE) { ns = g_rhs[rhs - XSQ_RHS_USER_BASE].n_state; (void)npar; }
     else ns = 6;   // built-in rhs with a user tableau: NL <= 6
     const unsigned smem = P.n_eval > 0 ? (unsigned)(sizeof(double) * 4 * ns * 128) : 0;
+    if (smem > 40u * 1024u) {
+        // 48 KB is the default cap of static + dynamic shared memory; the kernel
+        // also holds ~11 KB statically (stiffness state, math tables)
+        CUresult ca = g_api.FuncSetAttribute(
+            c.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+        if (ca != CUDA_SUCCESS) {
+            set_detail("cuFuncSetAttribute(MAX_DYNAMIC_SHARED_SIZE_BYTES) failed");
+            return XSQ_ERR_CUDA;
+        }
+    }
     CUresult cr = g_api.LaunchKernel(c.fn, (unsigned)grid, 1, 1, 128, 1, 1, smem,
                                      (CUstream)st, args, nullptr);
     count_launch();
@@ -535,7 +558,11 @@ int user_pde_kernels(int pde, void* fn[3], int* n_param) {
     const size_t i = (size_t)(pde - XSQ_PDE_USER_BASE);
     if (pde < XSQ_PDE_USER_BASE || i >= g_pde.size()) { set_detail("unknown pde handle"); return XSQ_ERR_ARG; }
     UserPde& u = g_pde[i];
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (u.ready && u.dev != cur_dev) u.ready = false;   // a module lives in one context
     if (!u.ready) {
+        u.dev = cur_dev;
         int rc = compile_module(pde_source(u), &u.mod);
         if (rc != XSQ_OK) return rc;
         const char* names[3] = {"xsq_pde_eval", "xsq_pde_stage", "xsq_pde_final"};
@@ -585,9 +612,15 @@ int xsq_tableau_load(const xsq_tableau_t* tab) {
         return XSQ_ERR_ARG;
     }
     std::lock_guard<std::mutex> g(g_mu);
+    unsigned long long h = 1469598103934665603ULL;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(tab);
+    for (size_t i = 0; i < sizeof(*tab); ++i) h = (h ^ b[i]) * 1099511628211ULL;
+    if (g_tab.loaded && h == g_tab.hash && std::memcmp(&g_tab.t, tab, sizeof(*tab)) == 0)
+        return XSQ_OK;                 // same image: keep the compiled modules
     g_tab.t = *tab;
     g_tab.src = tableau_source(*tab);
     g_tab.loaded = true;
+    g_tab.hash = h;
     ++g_tab.generation;
     return XSQ_OK;
 }
@@ -633,8 +666,7 @@ int xsq_events_compile_check(int32_t method, int32_t rhs, int32_t events) {
     if (g_api.CreateProgram(&prog, src.c_str(), "xsq_user.cu", kNumEmbedded,
                             kEmbeddedSources, kEmbeddedNames) != NVRTC_SUCCESS)
         return XSQ_ERR_NVRTC;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
-    nvrtcResult r = g_api.CompileProgram(prog, 2, opts);
+    nvrtcResult r = g_api.CompileProgram(prog, kNumNvrtcOpts, kNvrtcOpts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
         g_api.GetProgramLogSize(prog, &n);

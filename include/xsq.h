@@ -315,6 +315,11 @@ int xsq_rkc_solve(const xsq_rkc_args_t* args, void* comm, void* stream);
 int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
                         void* stream);
 
+/* The library caches its scratch (work queue, init pass, stiffness probe queue)
+ * in the device's stream-ordered memory pool between calls.  This returns all
+ * of it to the driver (synchronises the device). */
+int xsq_trim_memory(int device);
+
 /* Kernel-launch bookkeeping for benchmarks: number of kernels this library
  * launched since the last reset. */
 int64_t xsq_launch_count(int reset);

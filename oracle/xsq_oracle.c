@@ -36,6 +36,23 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "xsq_devmath.h"
+
+/* Device arithmetic (xsq_oracle_set_device_math(1)): err/scale by the kernel's
+ * seeded reciprocal, the step-size controller in the log2 domain with the
+ * kernel's table-driven log2 / exp2, h_start's tolerance power likewise --
+ * every place where extensisq_b200/csrc/xsq_rk_core.cuh deliberately departs
+ * from libm / IEEE division.  With it a device run and this file agree BIT FOR
+ * BIT in adaptive mode (tests/test_gpu_exact.py); without it this file follows
+ * the reference's own expressions (pow, true division). */
+const uint8_t* xsq_rcp64h_delta = 0;
+static int g_device_math = 0;
+void xsq_oracle_set_rcp_table(const uint8_t* bits) { xsq_rcp64h_delta = bits; }
+int xsq_oracle_set_device_math(int on) {
+    if (on && !xsq_rcp64h_delta) return -1;
+    g_device_math = on;
+    return 0;
+}
 
 #define MAXS 18
 #define MAXN 192
@@ -138,6 +155,8 @@ typedef struct {
     int interpolant;
     /* state */
     double t, h_abs, h_prev, err_old, max_factor, min_step;
+    double l2_old;                 /* device arithmetic: log2 of the last accepted ss */
+    double ctl_a1s, ctl_a0s, ctl_a1c, ctl_a2c, ctl_a0c;   /* xsq_api.cu build_params */
     double y[MAXN], fcur[MAXN];
     double K[KROWS][MAXN];
     int n_acc, n_rej, nfev, standard_sc;
@@ -212,12 +231,14 @@ static double h_start(lane_t* L, double a, double b, int morder) {
     double tolsum = 0.0, tolmin = INFINITY;
     for (int c = 0; c < n; ++c) {
         const double etol = fma(L->rtol, fabs(y[c]), L->atol[c]);
-        const double te = log10(etol);
+        /* device: 10^(c log10 x) as 2^(c log2 x) with its own log2 / exp2 */
+        const double te = g_device_math ? dev_log2(etol) : log10(etol);
         tolsum += te;
         tolmin = fmin(tolmin, te);
     }
     tolmin = fmin(tolmin, BIG);
-    const double tolp = pow(10.0, 0.5 * (tolsum / (double)n + tolmin) / (double)(morder + 1));
+    const double texp = 0.5 * (tolsum / (double)n + tolmin) / (double)(morder + 1);
+    const double tolp = g_device_math ? dev_exp2(texp) : pow(10.0, texp);
     double h = absdx;
     if (ydpb == 0.0 && fbnd == 0.0) {
         if (tolp < 1.0) h = absdx * tolp;
@@ -269,6 +290,39 @@ static double scaled_norm(lane_t* L, const double* errv, const double* yref) {
         q[c] = errv[c] / scale;
     }
     return rms(q, L->n);
+}
+
+/* device form: sum((err * rcp(scale))^2); error_norm < 1  <=>  ss < n exactly */
+static double scaled_ss_dev(lane_t* L, const double* errv, const double* yref) {
+    double ss = 0.0;
+    for (int c = 0; c < L->n; ++c) {
+        const double big = fabs(yref[c]) > fabs(L->y[c]) ? yref[c] : L->y[c];
+        const double scale = fma(L->rtol, fabs(big), L->atol[c]);
+        const double q = errv[c] * dev_rcp_scale(scale);
+        ss = fma(q, q, ss);
+    }
+    return ss;
+}
+
+/* xsq_rk_core.cuh ctl_factor */
+static double ctl_factor_dev(const lane_t* L, double l2, double z_extra, int use_extra, int accept,
+                             int second, int rej, int tiny) {
+    const double z_std = fma(L->ctl_a1s, l2, L->ctl_a0s);
+    double z_sc = fma(L->ctl_a1c, l2, fma(L->ctl_a2c, L->l2_old, L->ctl_a0c));
+    if (use_extra) z_sc += z_extra;
+    const double raw = dev_exp2(second ? z_sc : z_std);
+    double factor = raw;
+    if ((!accept || second) && !(raw > 0.2)) factor = 0.2;
+    const double hi = (accept && rej) ? 1.0 : (second ? L->max_factor : INFINITY);
+    if (!(factor < hi)) factor = hi;
+    if (accept && tiny) factor = rej ? 1.0 : L->max_factor;
+    return factor;
+}
+static double log2_fast_dev(double x) {
+    double r = dev_log2(x);
+    if (x == 0.0) r = -INFINITY;
+    if (!(x < INFINITY)) r = x;
+    return r;
 }
 
 static void reassess(lane_t* L) { /* common.py:310-331 */
@@ -559,6 +613,15 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     L->minalpha = -sc[2];
     L->safety = sc[3];
     L->safety_sc = pow(sc[3], sc[0] + sc[1]);
+    {   /* the same expressions as xsq_api.cu build_params */
+        const double log2n = log2((double)n);
+        L->ctl_a1s = 0.5 * L->err_exp;
+        L->ctl_a0s = log2(L->safety) - L->ctl_a1s * log2n;
+        L->ctl_a1c = 0.5 * L->minbeta1;
+        L->ctl_a2c = 0.5 * L->minbeta2;
+        L->ctl_a0c = log2(L->safety_sc) - (L->ctl_a1c + L->ctl_a2c) * log2n;
+        L->l2_old = 0.0;
+    }
     double cdiff = 1.0; /* common.py:129-137 */
     for (int i = 0; i < s; ++i)
         for (int j = 0; j < s; ++j) {
@@ -608,6 +671,62 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
             const int nfirst = early ? s - 1 : s;
             for (int i = 1; i < nfirst; ++i) rk_stage(L, h, i);
             double y_new[MAXN], errv[MAXN];
+            int err_dev_done = 0;
+            (void)err_dev_done;
+            if (g_device_math) {
+                /* the kernel's attempt (xsq_rk_core.cuh attempt_rk / xsq_rk_fast.cuh) */
+                const double NTOT = (double)n;
+                double ss = 0.0;
+                int pre_reject = 0;
+                if (early) {
+                    const double* wb = T->variant == V_BS5 ? T->B_scale_pre : T->A[s - 1];
+                    const double* we = T->variant == V_BS5 ? T->E_pre : T->E;
+                    for (int c = 0; c < n; ++c) {
+                        y_new[c] = fma(h, wsum(L, wb, s - 1, c), L->y[c]);
+                        errv[c] = h * wsum(L, we, s - 1, c);
+                    }
+                    ss = scaled_ss_dev(L, errv, y_new);
+                    pre_reject = !forced && ss > NTOT &&
+                        (ss >= NTOT * (1.0 + 0x1.0p-48) || sqrt(ss / NTOT) > 1.0);
+                }
+                if (!pre_reject) {
+                    if (early) rk_stage(L, h, s - 1);
+                    for (int c = 0; c < n; ++c) y_new[c] = fma(h, wsum(L, T->B, s, c), L->y[c]);
+                    if (fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
+                    for (int c = 0; c < n; ++c) errv[c] = h * wsum(L, T->E, s + fsal, c);
+                    ss = scaled_ss_dev(L, errv, y_new);
+                }
+                const int accept = forced || (!pre_reject && ss < NTOT);
+                const int bad = !forced && !pre_reject && !(ss < INFINITY);
+                if (T->variant == V_BS5 && bad) { st = ST_OVERFLOW; break; }
+                const int tiny = ss < NTOT * 0x1.0p-1022;
+                const int second = accept && !L->standard_sc;
+                const double l2 = dev_log2(ss);
+                double factor;
+                if (L->minalpha != 0.0) {
+                    const double zx = second ? L->minalpha * log2_fast_dev(h / L->h_prev) : 0.0;
+                    factor = ctl_factor_dev(L, l2, zx, 1, accept, second, step_rejected, tiny);
+                } else {
+                    factor = ctl_factor_dev(L, l2, 0.0, 0, accept, second, step_rejected, tiny);
+                }
+                if (bad || (pre_reject && !(ss < INFINITY))) factor = 0.2;
+                if (!forced) L->h_abs *= factor;
+                if (!accept) {
+                    step_rejected = 1;
+                    L->n_rej++;
+                    L->jflstp++;
+                    if (bad) { st = ST_OVERFLOW; break; }
+                    continue;
+                }
+                if (!forced) {
+                    L->standard_sc = tiny;
+                    if (factor < 4.0) L->max_factor = 4.0;
+                }
+                L->l2_old = l2;
+                err_dev_done = 1;
+            }
+            double err = 0.0;
+            if (!g_device_math) {
             if (early) { /* bogacki.py:340-346, calvo.py:255-261 */
                 const double* wb = T->variant == V_BS5 ? T->B_scale_pre : T->A[s - 1];
                 const double* we = T->variant == V_BS5 ? T->E_pre : T->E;
@@ -628,7 +747,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
             for (int c = 0; c < n; ++c) y_new[c] = fma(h, wsum(L, T->B, s, c), L->y[c]);
             if (fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
             for (int c = 0; c < n; ++c) errv[c] = h * wsum(L, T->E, s + fsal, c);
-            const double err = scaled_norm(L, errv, y_new);
+            err = scaled_norm(L, errv, y_new);
             if (!forced) {
                 if (err < 1.0) { /* common.py:249-276 */
                     double factor;
@@ -659,6 +778,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                     if (bad) { st = ST_OVERFLOW; break; }
                     continue;
                 }
+            }
             }
             if (!fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
             if (n_eval > 0) ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
@@ -744,4 +864,20 @@ double xsq_oracle_h_start(rhs_fn f, const double* prm, int n, double a, double b
     *nfev += L->nfev;
     free(L);
     return h;
+}
+
+/* element-wise access to the restated device functions (tests):
+ * fn 0 rcp_scale, 1 log2, 2 exp2, 3 rcp64h */
+int xsq_oracle_devmath(int fn, const double* x, double* out, int64_t n) {
+    if (!xsq_rcp64h_delta && (fn == 0 || fn == 3)) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = dev_rcp_scale(x[i]); break;
+            case 1: out[i] = dev_log2(x[i]); break;
+            case 2: out[i] = dev_exp2(x[i]); break;
+            case 3: out[i] = dev_rcp64h(x[i]); break;
+            default: return -1;
+        }
+    }
+    return 0;
 }

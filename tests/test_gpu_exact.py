@@ -1,0 +1,196 @@
+"""Adaptive runs of the CUDA kernels against the C oracle in DEVICE ARITHMETIC
+(oracle/xsq_oracle.c with xsq_oracle_set_device_math(1): the kernel's seeded
+reciprocal for err/scale and its table-driven log2/exp2 in the controller and
+in h_start, restated operation by operation).  The bar is bit equality of
+every output on 100 % of the lanes -- accepted / rejected / nfev counts, final
+time and state, the next step size, the stiffness flags and the dense output --
+for every built-in method and right-hand side, at BASELINE.json's shapes:
+
+* C2: Lorenz-63 lanes of the benchmark ensemble itself, t in [0, 100];
+* C3: Pr8 / Pr9 on the Van der Pol mu-sweep up to mu = 100 with 1000 t_eval points.
+
+What the device arithmetic costs against the REFERENCE's arithmetic (pow, true
+division) is measured separately, C oracle against C oracle and against the
+NumPy restatement that is bit-identical to the reference
+(test_cost_of_device_arithmetic*): the fractions are printed and asserted.
+Reference: common.py:249-287 (controller), ivp.py:711-728 (t_eval slicing).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import extensisq_b200 as xb
+from oracle import c_oracle as CO
+from oracle import rk_oracle as O
+from test_gpu_rk import lorenz_lanes, vdp_lanes, arenstorf_lanes
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TABS = O.load_tableaux()
+METHODS = [xb.Ts5, xb.BS5, xb.CK5, xb.Me4, xb.Pr7, xb.Pr8, xb.Pr9, xb.CFMR7osc]
+THREADS = max(1, len(os.sched_getaffinity(0)))
+KEYS_F = ("t_final", "y_final", "h_next")
+KEYS_I = ("n_accepted", "n_rejected", "nfev", "status")
+
+
+def gpu(rhs, span, y0, m, prm, **kw):
+    res = xb.solve_ivp_batched(rhs, span, y0, m, params=prm, **kw)
+    torch.cuda.synchronize()
+    out = {k: getattr(res, k).cpu().numpy() for k in KEYS_F + KEYS_I}
+    out["stiff_flags"] = res.stiff_flags.cpu().numpy()
+    out["y"] = res.y.cpu().numpy() if res.y is not None else None
+    return out
+
+
+def oracle(rhs, span, y0, m, prm, device_math=True, **kw):
+    kw = dict(kw)
+    kw.setdefault("n_threads", THREADS)
+    if device_math:
+        with CO.device_math():
+            return CO.rk_batch(TABS[m.__name__], rhs, span, y0, params=prm, **kw)
+    return CO.rk_batch(TABS[m.__name__], rhs, span, y0, params=prm, **kw)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def assert_identical(g, o, what, dense=False):
+    for k in KEYS_I + ("stiff_flags",):
+        bad = np.flatnonzero(g[k] != o[k])
+        assert bad.size == 0, (what, k, bad[:5], g[k][bad[:5]], o[k][bad[:5]])
+    for k in KEYS_F:
+        bad = np.flatnonzero((bits(g[k]) != bits(o[k])).reshape(len(g[k]), -1).any(axis=1))
+        assert bad.size == 0, (what, k, bad[:5], g[k][bad[:5]], o[k][bad[:5]])
+    if dense:
+        a, b = g["y"], o["y"]
+        same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), (what, "y(t_eval)", np.argwhere(~same)[:5],
+                            np.nanmax(np.abs(a - b)))
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_adaptive_run_is_bit_identical_to_oracle_in_device_arithmetic(m, prob):
+    lanes, span = {"lorenz63": (lorenz_lanes, (0.0, 12.0)),
+                   "vanderpol": (vdp_lanes, (0.0, 20.0)),
+                   "arenstorf": (arenstorf_lanes, (0.0, 17.0652165601579625588917206249))}[prob]
+    y0, prm = lanes(768)
+    for stiff in (5000, 300):
+        kw = dict(rtol=1e-8, atol=1e-10, nfev_stiff_detect=stiff)
+        g = gpu(prob, span, y0, m, prm, **kw)
+        o = oracle(prob, span, y0, m, prm, **kw)
+        assert g["n_accepted"].min() > 20
+        assert_identical(g, o, (m.__name__, prob, stiff))
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_dense_output_is_bit_identical_to_oracle_in_device_arithmetic(m):
+    y0, prm = lorenz_lanes(384, seed=7)
+    t_eval = np.linspace(0.0, 6.0, 257)
+    kw = dict(rtol=1e-7, atol=1e-9, t_eval=t_eval)
+    g = gpu("lorenz63", (0.0, 6.0), y0, m, prm, **kw)
+    o = oracle("lorenz63", (0.0, 6.0), y0, m, prm, **kw)
+    assert_identical(g, o, (m.__name__, "t_eval"), dense=True)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(rtol=1e-3, atol=1e-6), dict(rtol=1e-11, atol=1e-13),
+    dict(rtol=1e-6, atol=[1e-9, 1e-7, 1e-8]), dict(rtol=1e-8, atol=1e-10, max_step=0.02),
+    dict(rtol=1e-8, atol=1e-10, first_step=1e-3),
+    dict(rtol=1e-6, atol=1e-8, sc_params=(0.6, -0.2, 0.0, 0.9)),
+    dict(rtol=1e-6, atol=1e-8, sc_params=(0.7, -0.4, 0.1, 0.8)),     # alpha term: generic kernel
+], ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items() if k != "atol"))
+def test_options_bit_identical(kw):
+    y0, prm = lorenz_lanes(512, seed=21)
+    for m in (xb.Ts5, xb.BS5, xb.Pr7):
+        g = gpu("lorenz63", (0.0, 5.0), y0, m, prm, **kw)
+        o = oracle("lorenz63", (0.0, 5.0), y0, m, prm, **kw)
+        assert_identical(g, o, (m.__name__, kw))
+
+
+# ---- C3 at its shape ---------------------------------------------------------
+@pytest.mark.parametrize("m", [xb.Pr8, xb.Pr9], ids=lambda m: m.__name__)
+def test_c3_vanderpol_mu_sweep_1000_points(m):
+    """BASELINE.json configs[2]: mu log-uniform on [0.1, 100], y0 = (2, 0),
+    t in [0, 20], 1000 t_eval points, rtol 1e-8, atol 1e-10 -- 4096 lanes spread
+    over the whole 1 M-lane sweep (every 244th lane + both ends)."""
+    N_FULL, N = 1_000_000, 4096
+    idx = np.unique(np.round(np.linspace(0, N_FULL - 1, N)).astype(np.int64))
+    mu = 10.0 ** (-1 + 3 * idx / (N_FULL - 1))
+    assert mu[0] == 0.1 and abs(mu[-1] - 100.0) < 1e-12
+    y0 = np.tile([2.0, 0.0], (len(mu), 1))
+    t_eval = np.linspace(0.0, 20.0, 1000)
+    kw = dict(rtol=1e-8, atol=1e-10, t_eval=t_eval)
+    g = gpu("vanderpol", (0.0, 20.0), y0, m, mu[:, None], **kw)
+    o = oracle("vanderpol", (0.0, 20.0), y0, m, mu[:, None], **kw)
+    assert (g["status"] == 0).all()
+    assert_identical(g, o, (m.__name__, "C3"), dense=True)
+    # the stiff end really is in the sample: rejected steps pile up there
+    assert g["n_rejected"][-64:].mean() > 10 * g["n_rejected"][:64].mean() + 5
+    # and against the reference's arithmetic (pow, true division): solutions at
+    # t_eval within 10 x rtol (BASELINE.json north_star), counts reported
+    r = oracle("vanderpol", (0.0, 20.0), y0, m, mu[:, None], device_math=False, **kw)
+    scale = 1e-10 + 1e-8 * np.abs(r["y"])
+    worst = np.max(np.abs(g["y"] - r["y"]) / scale)
+    same = (g["n_accepted"] == r["n_accepted"]) & (g["n_rejected"] == r["n_rejected"])
+    print(f"\nC3 {m.__name__}: counts identical to reference arithmetic on "
+          f"{same.mean():.4f} of {len(mu)} lanes; total attempts "
+          f"{(g['n_accepted'] + g['n_rejected']).sum()} vs {(r['n_accepted'] + r['n_rejected']).sum()}; "
+          f"max |dy| / (atol + rtol |y|) at t_eval = {worst:.2f}")
+    tot_g = float((g["n_accepted"] + g["n_rejected"]).sum())
+    tot_r = float((r["n_accepted"] + r["n_rejected"]).sum())
+    assert abs(tot_g - tot_r) / tot_r < 1e-3
+
+
+# ---- C2 at its shape ---------------------------------------------------------
+def test_c2_bench_ensemble_t100_exact_and_distribution():
+    """The first 10 240 lanes of the benchmark's own shard (bench.make_lanes,
+    rank 0), t in [0, 100], Ts5 and CK5, reference defaults: bit-identical to
+    the oracle in device arithmetic, lane by lane, at the benchmark's horizon
+    (chaos amplifies any difference, so this is the strongest statement there
+    is); and against the reference's arithmetic the mean accepted / rejected
+    steps per lane agree within 0.1 % (hard part 1c)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    N = 10240
+    y0_full, prm_full = bench.make_lanes(bench.LANES_PER_GPU, 0)
+    y0, prm = y0_full[:N], prm_full[:N]
+    y0_n, prm_n = bench.make_lanes(N, 0)
+    assert np.array_equal(y0, y0_n) and np.array_equal(prm, prm_n)   # a true subset
+    for m in (xb.Ts5, xb.CK5):
+        kw = dict(rtol=bench.RTOL, atol=bench.ATOL)
+        g = gpu("lorenz63", (0.0, bench.T_END), y0, m, prm, **kw)
+        o = oracle("lorenz63", (0.0, bench.T_END), y0, m, prm, **kw)
+        assert (g["status"] == 0).all()
+        assert_identical(g, o, (m.__name__, "C2 T=100"))
+        r = oracle("lorenz63", (0.0, bench.T_END), y0, m, prm, device_math=False, **kw)
+        da = g["n_accepted"].mean() / r["n_accepted"].mean() - 1
+        dr = g["n_rejected"].mean() / r["n_rejected"].mean() - 1
+        print(f"\nC2 {m.__name__} T=100, {N} lanes: accepted/lane {g['n_accepted'].mean():.2f} "
+              f"(reference arithmetic {r['n_accepted'].mean():.2f}, {da:+.2e}), rejected/lane "
+              f"{g['n_rejected'].mean():.2f} ({r['n_rejected'].mean():.2f}, {dr:+.2e})")
+        assert abs(da) < 1e-3 and abs(dr) < 1e-3
+
+
+def test_cost_of_device_arithmetic_vs_numpy_restatement():
+    """C oracle in device arithmetic against the NumPy restatement that is
+    bit-identical to the reference: fraction of lanes with identical
+    accepted / rejected counts inside the predictability horizon."""
+    y0, prm = lorenz_lanes(96, seed=99)
+    tab = TABS["Ts5"]
+    with CO.device_math():
+        d = CO.rk_batch(tab, "lorenz63", (0.0, 10.0), y0, params=prm, rtol=1e-8, atol=1e-10,
+                        n_threads=THREADS)
+    same = 0
+    for i in range(len(y0)):
+        r = O.rk_solve(tab, O.lorenz63(*prm[i]), (0.0, 10.0), y0[i], rtol=1e-8, atol=1e-10)
+        same += int(r["n_accepted"] == d["n_accepted"][i] and r["n_rejected"] == d["n_rejected"][i]
+                    and r["nfev"] == d["nfev"][i])
+    print(f"\ndevice arithmetic vs reference (NumPy restatement), Lorenz T=10: "
+          f"{same}/{len(y0)} lanes with identical accepted/rejected/nfev")
+    assert same >= 0.99 * len(y0)
