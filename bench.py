@@ -4,15 +4,27 @@ configs[1]: Ts5/CK5, 10 M lanes over 8 GPUs = 1.25 M lanes per GPU, randomised
 initial conditions and parameters, rtol 1e-8, atol 1e-10, t in [0, 100]).
 
 A "step" of the benchmark = one pass of the hot path over this rank's shard of
-the ensemble (one xsq_rk_solve call = one persistent-kernel launch).
+the ensemble (one xsq_rk_solve call: init kernel + persistent kernel + probe
+queue kernel).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
   python bench.py --impl reference ...                         # CPU arm
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every
-field is obtained.
+One JSON line on stdout (rank 0).  Besides the headline (C2 / Ts5) the line
+carries, measured in the same run:
+  "ssv2stab"  C5: ONE SSV2stab solve of the 16384^2 reaction-diffusion grid,
+              row slabs over the N ranks with the halo read in place over
+              NVLink (strong scaling), a weak-scaling slab solve, the stage
+              kernel's HBM roofline, and -- for N > 1 -- the same grid solved on
+              one GPU for the state checksum ("parity_vs_1rank");
+  "configs"   (N = 1) C2/CK5, C3 (Pr8, Pr9, 1 M Van der Pol lanes, 1000 t_eval
+              points), C4 (SWAG on the Arenstorf orbit and on 32-body gravity),
+              each with its own roofline;
+  "cpu_baseline" (+ "_serial", "_c")  the reference on this host's cores.
+See DESIGN.md "Measurement" for how every field is obtained.
 """
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -30,6 +42,8 @@ LANES_PER_GPU = 1_250_000           # 10 M lanes / 8 GPUs (BASELINE.json configs
 T_END = 100.0
 RTOL, ATOL = 1e-8, 1e-10
 SEED = 12345
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")     # pip install --target of /root/reference
+C5_NX = 16384
 
 
 def parse():
@@ -47,7 +61,11 @@ def parse():
     ap.add_argument("--stiff", type=int, default=5000,
                     help="nfev_stiff_detect (reference default 5000; 0 = off)")
     ap.add_argument("--no-cpu", action="store_true",
-                    help="skip the cpu_baseline leg (profiling runs)")
+                    help="skip the cpu_baseline legs (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline only: skip the C3/C4/C5 configs")
+    ap.add_argument("--only", default="",
+                    help="comma list of extra configs to run (c2ck5,c3,c4a,c4b,c5)")
     return ap.parse_args()
 
 
@@ -80,6 +98,11 @@ def flops_per_attempt_and_accept(method_cls, n, F):
            2 * n * nnzB + 2 * n + 2 * n + 2 * n * nnzE + 5 * n + 2 + 10)
     acc = 0 if fsal else F
     return att, acc
+
+
+def swag_flops_per_accepted(n, F, k):
+    """2F + n(6k + 30) + O(k^2) per accepted step at order k."""
+    return 2 * F + n * (6 * k + 30) + k * k
 
 
 # ---- clocks during the timed region ----------------------------------------
@@ -144,43 +167,78 @@ class ClockSampler:
 
 
 # ---- CPU legs ----------------------------------------------------------------
-def _np_worker(args):
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "extensisq"))
+
+
+def _ref_worker(args):
+    """The UNMODIFIED reference (baseline/_ref, installed from /root/reference by
+    `pip install --target`): scipy's solve_ivp driving extensisq's own class."""
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    from oracle import rk_oracle as O
-    method, y0, prm, t_end = args
-    tab = O.load_tableaux()[method]
+    method, y0, prm, t_end, use_ref = args
     acc = 0
+    if use_ref:
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import extensisq
+        from scipy.integrate import solve_ivp
+        cls = getattr(extensisq, method)
+        for i in range(len(y0)):
+            s, r, b = prm[i]
+
+            def fun(t, y, s=s, r=r, b=b):
+                return [s * (y[1] - y[0]), y[0] * (r - y[2]) - y[1], y[0] * y[1] - b * y[2]]
+            sol = solve_ivp(fun, (0.0, t_end), y0[i], method=cls, rtol=RTOL, atol=ATOL)
+            acc += len(sol.t) - 1
+        return acc
+    from oracle import rk_oracle as O
+    tab = O.load_tableaux()[method]
     for i in range(len(y0)):
-        r = O.rk_solve(tab, O.lorenz63(*prm[i]), (0.0, t_end), y0[i],
-                       rtol=RTOL, atol=ATOL)
+        r = O.rk_solve(tab, O.lorenz63(*prm[i]), (0.0, t_end), y0[i], rtol=RTOL, atol=ATOL)
         acc += r["n_accepted"]
     return acc
 
 
-def cpu_numpy_port(method, lanes, t_end, cores, target_s=15.0):
-    """The NumPy restatement (bit-identical to the reference's own Python,
-    same per-step cost model), one process per core.  lanes == 0: calibrate
-    on one lane per core and size the sample for ~target_s seconds."""
+def cpu_reference_pool(method, lanes, t_end, cores, target_s=12.0):
+    """One process per core, each on a disjoint slice of the sample.  The
+    unmodified reference when baseline/_ref is there ("reference"), else the
+    NumPy restatement that is bit-identical to it ("port").  lanes == 0:
+    calibrate on one lane per core and size the sample for ~target_s seconds."""
     import multiprocessing as mp
+    use_ref = reference_available()
     with mp.get_context("spawn").Pool(cores) as pool:
         y0, prm = make_lanes(max(lanes, 4 * cores), 0)
-        pool.map(_np_worker, [(method, y0[:1], prm[:1], 0.05)] * cores)  # warm
+        pool.map(_ref_worker, [(method, y0[:1], prm[:1], 0.05, use_ref)] * cores)  # warm
         if lanes <= 0:
             t0 = time.perf_counter()
-            pool.map(_np_worker, [(method, y0[i:i + 1], prm[i:i + 1], t_end)
-                                  for i in range(cores)])
+            pool.map(_ref_worker, [(method, y0[i:i + 1], prm[i:i + 1], t_end, use_ref)
+                                   for i in range(cores)])
             per_lane = time.perf_counter() - t0
             lanes = max(cores, int(cores * target_s / max(per_lane, 1e-3)))
             y0, prm = make_lanes(lanes, 0)
-        chunks = [(method, y0[i:lanes:cores], prm[i:lanes:cores], t_end)
+        chunks = [(method, y0[i:lanes:cores], prm[i:lanes:cores], t_end, use_ref)
                   for i in range(cores)]
         t0 = time.perf_counter()
-        accs = pool.map(_np_worker, chunks)
+        accs = pool.map(_ref_worker, chunks)
         dt = time.perf_counter() - t0
-    return sum(accs) / dt, sum(accs), dt, lanes
+    return sum(accs) / dt, sum(accs), dt, lanes, ("reference" if use_ref else "port")
 
 
-def cpu_c_port(method, lanes, t_end, threads, target_s=10.0):
+def cpu_reference_serial(method, t_end, target_s=8.0):
+    """Serial: one process, one thread, lanes of the same ensemble until ~target_s."""
+    use_ref = reference_available()
+    y0, prm = make_lanes(64, 0)
+    _ref_worker((method, y0[:1], prm[:1], 0.05, use_ref))
+    acc, lanes = 0, 0
+    t0 = time.perf_counter()
+    while lanes < len(y0) and (lanes == 0 or time.perf_counter() - t0 < target_s):
+        acc += _ref_worker((method, y0[lanes:lanes + 1], prm[lanes:lanes + 1], t_end, use_ref))
+        lanes += 1
+    dt = time.perf_counter() - t0
+    return acc / dt, acc, dt, lanes, ("reference" if use_ref else "port")
+
+
+def cpu_c_port(method, lanes, t_end, threads, target_s=6.0):
     from oracle import c_oracle as CO
     from oracle import rk_oracle as O
     tab = O.load_tableaux()[method]
@@ -208,6 +266,7 @@ def config_dict(args, world):
                         "randomised y0 and (sigma, rho, beta), seed 12345+rank",
             "method": args.method, "lanes_per_gpu": args.lanes,
             "t_end": args.t_end, "rtol": RTOL, "atol": ATOL,
+            "nfev_stiff_detect": args.stiff,
             "sharding": f"lanes/{world}", "l2": "flushed between timed iterations (512 MiB write)"}
 
 
@@ -217,18 +276,19 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    # bounded sample: ~15 s of CPU work per step, calibrated on this host
+    # bounded sample: ~12 s of CPU work per step, calibrated on this host
     lanes = args.cpu_lanes
-    vals, t_all = [], []
+    vals, t_all, kind = [], [], "port"
     for i in range(args.warmup + args.steps):
-        v, acc, dt, lanes = cpu_numpy_port(args.method, lanes, args.t_end,
-                                           cores)
+        v, acc, dt, lanes, kind = cpu_reference_pool(args.method, lanes, args.t_end, cores)
         if i >= args.warmup:
             vals.append(v)
             t_all.append(dt)
     value = float(np.mean(vals))
-    sample = (f"{lanes} lanes of the same ensemble (seed 12345), full t span, "
-              f"NumPy restatement of the reference (oracle/rk_oracle.py), "
+    what = ("the unmodified reference (baseline/_ref: scipy solve_ivp + extensisq."
+            f"{args.method})" if kind == "reference" else
+            "NumPy restatement of the reference (oracle/rk_oracle.py, bit-identical to it)")
+    sample = (f"{lanes} lanes of the same ensemble (seed 12345), full t span, {what}, "
               f"one process per core")
     line = {"impl": "reference", "metric": "accepted RK steps/sec (ensemble)",
             "value": value, "unit": "steps/s", "n_gpus": world,
@@ -238,10 +298,284 @@ def run_reference(args):
             "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world),
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores,
-                             "kind": "port", "sample": sample},
+                             "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "steps/s",
                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ---- ncu-measured DRAM traffic, from committed captures ----------------------
+def source_hash(key):
+    """sha16 of the kernel sources the capture named `key` belongs to."""
+    if key.startswith("k_"):
+        files = ("xsq_rkc_kernels.cuh", "xsq_rkc.cu")
+    elif key.startswith("swag"):
+        files = ("xsq_swag_core.cuh", "xsq_rk_core.cuh")
+    else:
+        files = ("xsq_rk_fast.cuh", "xsq_rk_core.cuh", "xsq_tableaux_gen.cuh")
+    h = hashlib.sha256()
+    for f in files:
+        p = os.path.join(ROOT, "extensisq_b200", "csrc", f)
+        if os.path.exists(p):
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key):
+    """profiles/traffic.json (written by tools/ncu_traffic.py from an
+    `ncu --set full` capture): dram__bytes_read.sum + dram__bytes_write.sum per
+    launch of the named kernel at the benchmark's size.  `stale`: the kernel
+    sources changed since the capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        e = json.load(open(p)).get(key)
+    except Exception:
+        return None, None
+    if not e:
+        return None, None
+    note = {"capture": e.get("capture"), "source_sha16": e.get("source_sha16"),
+            "stale": e.get("source_sha16") != source_hash(key)}
+    return e.get("dram_bytes_per_launch"), note
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("hbm_gbs"), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6451.2, "fallback (this pool's measured copy bandwidth, B200_PROFILING.md)"
+
+
+# ---- C5: SSV2stab on the 16384^2 grid ------------------------------------------
+def run_c5(xb, lib, dev, rank, world, dist, quick=False):
+    """ONE solve of u_t = Lap u + u - u^3 on the nx^2 grid,
+    split into row slabs over the ranks; the halo row is read in place from the
+    neighbour over NVLink inside the stage kernel (csrc/xsq_rkc.cu)."""
+    import ctypes as C
+    import torch
+    nx = C5_NX
+    hbm, hbm_src = hbm_peak()
+    out = {"grid": f"{nx} x {nx}", "bytes_per_point_stage": 40, "hbm_peak_gbs": hbm,
+           "hbm_peak_source": hbm_src}
+    rho = 8.0 * (nx + 1.0) ** 2 + 2.0
+    comm = xb.SlabComm() if world > 1 else None
+
+    def slab_u0(row0, rows, rows_global):
+        xg = torch.arange(1, nx + 1, dtype=torch.float64, device=dev) / (nx + 1)
+        yg = torch.arange(row0 + 1, row0 + rows + 1, dtype=torch.float64, device=dev) / (rows_global + 1)
+        return torch.outer(torch.sin(math.pi * yg), torch.sin(math.pi * xg))
+
+    def solve(rows_global, row0, rows, T, cm, reps):
+        u0 = slab_u0(row0, rows, rows_global)
+        best, rr = None, None
+        for _ in range(reps):
+            if cm is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rr = xb.solve_pde_rkc("heat2d_reaction", (0.0, T), u0, rows_global=rows_global,
+                                  row0=row0, rho_jac=rho, rtol=1e-4, atol=1e-4, comm=cm,
+                                  max_steps=1000)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        cs = torch.stack([rr.y_final.sum(), (rr.y_final * rr.y_final).sum()])
+        del u0
+        return rr, best, cs
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def describe(rr, ms, rows, label):
+        gbs = nx * rows * 40.0 * rr.nfev / (ms * 1e-3) / 1e9
+        return {"what": label, "ms": ms, "ms_per_stage": ms / max(rr.nfev, 1),
+                "accepted": rr.n_accepted, "rejected": rr.n_rejected, "nfev": rr.nfev,
+                "s_max": rr.maxm, "status": rr.status, "rows_per_gpu": rows,
+                "algorithmic_GBps_per_gpu": gbs, "frac_of_hbm_peak": gbs / hbm,
+                "kernel_launches": rr.kernel_launches}
+
+    # (1) strong scaling: the fixed 16384^2 grid over all ranks
+    T_strong = 0.05 * (512.0 / nx) ** 2
+    row0, row1 = xb.slab_of(nx, rank, world)
+    rr, ms, cs = solve(nx, row0, row1 - row0, T_strong, comm, 1 if quick else 2)
+    if world > 1:
+        dist.all_reduce(cs)
+    ms = reduce_max(ms)
+    strong = describe(rr, ms, row1 - row0,
+                      f"one solve of the {nx}^2 grid over {world} GPU(s), t in [0,{T_strong:.3e}]")
+    strong["checksum"] = [float(cs[0]), float(cs[1])]
+    out["strong"] = strong
+    # (2) weak scaling: 2048 rows per GPU (the 8-GPU share), same step count
+    rows_w = 2048
+    rw, msw, _ = solve(rows_w * world, rank * rows_w, rows_w, 2e-5, comm, 1 if quick else 2)
+    out["weak"] = describe(rw, reduce_max(msw), rows_w,
+                           f"{rows_w} x {nx} per GPU ({rows_w * world} x {nx} in all), t in [0,2e-5]")
+    # (3) N > 1: the same grid on ONE GPU (rank 0), for the checksum and the speed-up
+    if world > 1:
+        ref = torch.zeros(5, dtype=torch.float64, device=dev)
+        if rank == 0:
+            r1, ms1, cs1 = solve(nx, 0, nx, T_strong, None, 1)
+            ref = torch.tensor([float(cs1[0]), float(cs1[1]), ms1, r1.nfev, r1.n_accepted],
+                               dtype=torch.float64, device=dev)
+        dist.broadcast(ref, src=0)
+        c1 = ref.tolist()
+        relerr = max(abs(strong["checksum"][i] - c1[i]) / abs(c1[i]) for i in range(2))
+        out["one_gpu_same_grid"] = {"ms": c1[2], "nfev": int(c1[3]), "accepted": int(c1[4]),
+                                    "checksum": c1[:2]}
+        out["parity_vs_1rank"] = bool(relerr <= 1e-12 and int(c1[3]) == rr.nfev and
+                                      int(c1[4]) == rr.n_accepted)
+        out["checksum_rel_err_vs_1rank"] = relerr
+        out["strong_speedup_vs_1gpu"] = c1[2] / ms
+        out["strong_efficiency"] = c1[2] / ms / world
+        out["limit"] = ("per stage every rank runs one k_peer_sync handshake (remote flag store + "
+                        "spin, ~5-10 us over NVLink) before its stage kernel; at 16384^2 / N rows "
+                        "the stage itself takes 1.5 ms / N, so the handshake is what the strong "
+                        "curve loses; the weak curve (0.19 ms stages) loses the same few us")
+    # (4) the stage kernel alone on the 8-GPU slab: HBM roofline
+    ms_stage = C.c_double()
+    if lib.xsq_rkc_stage_bench(nx, 2048, 40, C.byref(ms_stage), None) == 0:
+        gbs = nx * 2048 * 40 / 1e9 / (ms_stage.value * 1e-3)
+        traffic, tnote = measured_traffic("k_stage_2048x16384")
+        out["stage_kernel"] = {
+            "kernel": "k_stage (stencil RHS + three-term recurrence)",
+            "slab": f"2048 x {nx}", "ms_per_stage": ms_stage.value,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": gbs / hbm, "traffic": traffic, "traffic_source": tnote}}
+    if comm is not None:
+        comm.close()
+    return out
+
+
+# ---- the other BASELINE.json configs on one GPU --------------------------------
+def timed_solve(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    best, r = None, None
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return r, best
+
+
+def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
+    import torch
+    out = {}
+    hbm, _ = hbm_peak()
+
+    def rk_entry(name, r, ms, m, n, F, extra_flops=0.0):
+        acc, rej = int(r.n_accepted.sum().item()), int(r.n_rejected.sum().item())
+        att_f, acc_f = flops_per_attempt_and_accept(m, n, F)
+        fl = (acc + rej) * att_f + acc * acc_f + extra_flops
+        tf = fl / (ms * 1e-3) / 1e12
+        out[name] = {"value": acc / (ms * 1e-3), "unit": "accepted steps/s", "ms": ms,
+                     "accepted": acc, "rejected": rej,
+                     "ok": bool((r.status == 0).all().item()),
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf,
+                                  "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                  "flops_per_attempted_step": att_f}}
+        return out[name]
+
+    if "c2ck5" in which:
+        r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "lorenz63", (0.0, args.t_end), y0_d, xb.CK5, params=prm_d, rtol=RTOL, atol=ATOL,
+            nfev_stiff_detect=args.stiff), 2)
+        rk_entry("C2_CK5", r, ms, xb.CK5, 3, 8)["workload"] = \
+            f"CK5, {y0_d.shape[0]} Lorenz lanes, t in [0,{args.t_end:g}]"
+        del r
+    if "c3" in which:
+        N = 1_000_000
+        mu = 10.0 ** (-1 + 3 * np.arange(N) / (N - 1))
+        y0 = torch.tensor(np.tile([2.0, 0.0], (N, 1)), device=dev)
+        prm = torch.tensor(mu[:, None], device=dev)
+        te = torch.linspace(0, 20, 1000, dtype=torch.float64, device=dev)
+        for m in (xb.Pr8, xb.Pr9):
+            r0, ms0 = timed_solve(torch, lambda: xb.solve_ivp_batched(
+                "vanderpol", (0.0, 20.0), y0, m, params=prm, rtol=RTOL, atol=ATOL), 2)
+            del r0
+            r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+                "vanderpol", (0.0, 20.0), y0, m, params=prm, rtol=RTOL, atol=ATOL, t_eval=te), 2)
+            npol = m.P.shape[1]
+            dense_flops = N * 1000 * 2 * 2 * npol      # 2 n p per t_eval point
+            e = rk_entry(f"C3_{m.__name__}", r, ms, m, 2, 6, dense_flops)
+            out_bytes = N * 2 * 1000 * 8
+            e["workload"] = ("1 M Van der Pol lanes, mu log-uniform on [0.1,100], t in [0,20], "
+                             "1000 t_eval points (16 GB of dense output)")
+            e["ms_without_t_eval"] = ms0
+            e["t_eval_overhead_ms"] = ms - ms0
+            e["dense_output"] = {"bytes": out_bytes,
+                                 "GBps_over_the_overhead": out_bytes / max(ms - ms0, 1e-3) / 1e6,
+                                 "GBps_over_the_whole_pass": out_bytes / ms / 1e6,
+                                 "hbm_peak_gbs": hbm}
+            del r
+        del y0, prm, te
+    if "c4a" in which:
+        N = 1_000_000
+        rng = np.random.default_rng(2024)
+        y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252240537862224]) + \
+            rng.uniform(-1e-3, 1e-3, (N, 4))
+        y0 = torch.tensor(y0, device=dev)
+        prm = torch.full((N, 1), 0.012277471, dtype=torch.float64, device=dev)
+        T = 17.0652165601579625588917206249
+        r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "arenstorf", (0.0, T), y0, xb.SWAG, params=prm, rtol=RTOL, atol=ATOL,
+            max_steps=200000), 1)
+        acc = int(r.n_accepted.sum().item())
+        k = 9.0
+        tf = acc * swag_flops_per_accepted(4, 60, k) / (ms * 1e-3) / 1e12
+        out["C4_arenstorf_SWAG"] = {
+            "value": acc / (ms * 1e-3), "unit": "accepted steps/s", "ms": ms, "accepted": acc,
+            "rejected": int(r.n_rejected.sum().item()),
+            "ok_frac": float((r.status == 0).double().mean().item()),
+            "workload": "SWAG, 1 M perturbed Arenstorf orbits, one period",
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": tf / peak_tf, "flops_model": f"2F + n(6k+30) + k^2, F=60, n=4, k={k:g}"}}
+        r2, ms2 = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "arenstorf", (0.0, T), y0, xb.Pr8, params=prm, rtol=RTOL, atol=ATOL), 1)
+        rk_entry("C4_arenstorf_Pr8", r2, ms2, xb.Pr8, 4, 60)["workload"] = "Pr8 on the same lanes"
+        del r, r2, y0, prm
+    if "c4b" in which:
+        N, nb = 65536, 32
+        rng = np.random.default_rng(2025)
+        m_ = rng.uniform(0.5, 1.5, (N, nb))
+        pos = rng.normal(0, 1, (N, nb, 3))
+        vel = rng.normal(0, 0.3, (N, nb, 3))
+        vel -= (m_[:, :, None] * vel).sum(1, keepdims=True) / m_.sum(1)[:, None, None]
+        y0 = torch.tensor(np.concatenate([pos.reshape(N, -1), vel.reshape(N, -1)], 1), device=dev)
+        prm = torch.tensor(np.concatenate([np.full((N, 1), 0.05 ** 2), m_], 1), device=dev)
+        r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "nbody32", (0.0, 1.0), y0, xb.SWAG, params=prm, rtol=RTOL, atol=ATOL,
+            max_steps=200000), 1)
+        acc = int(r.n_accepted.sum().item())
+        nfev = int(r.nfev.sum().item())
+        F = 31 * 20 * 32
+        tf = (nfev * F + acc * 192 * (6 * 9 + 30)) / (ms * 1e-3) / 1e12
+        out["C4_nbody32_SWAG"] = {
+            "value": acc / (ms * 1e-3), "unit": "accepted steps/s", "ms": ms, "accepted": acc,
+            "rejected": int(r.n_rejected.sum().item()), "nfev": nfev,
+            "pair_interactions_per_s": nfev * nb * nb / (ms * 1e-3),
+            "ok_frac": float((r.status == 0).double().mean().item()),
+            "workload": "SWAG, 65 536 32-body systems (n = 192, warp per system), t in [0,1]",
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": tf / peak_tf,
+                         "flops_model": "nfev x 31 x 20 x 32 (pair interactions) + SWAG vector work"}}
+        del r, y0, prm
+    return out
 
 
 def main():
@@ -359,20 +693,31 @@ def main():
     max_ms, max_e2e_ms = stats.tolist()
     acc_all, rej_all = tot.tolist()
 
+    which = set(x for x in args.only.split(",") if x) or {"c2ck5", "c3", "c4a", "c4b", "c5"}
+    if args.no_extras:
+        which = set()
+    del flush
+    c5 = None
+    if "c5" in which:       # every rank takes part
+        try:
+            c5 = run_c5(xb, lib, dev, rank, world, dist)
+        except Exception as exc:          # never lose the headline line
+            c5 = {"error": repr(exc)}
+
     if rank == 0:
         value = acc_all * args.steps / (max_ms * 1e-3)
         e2e_value = acc_all * args.steps / (max_e2e_ms * 1e-3)
-        # roofline of the dominant (only) kernel, this rank
+        # roofline of the dominant kernel, this rank
         att_f, acc_f = flops_per_attempt_and_accept(method, 3, 8)
         flops_launch = (acc_total + rej_total) * att_f + acc_total * acc_f
         ms_launch = float(np.mean(kern_ms))
         achieved = flops_launch / (ms_launch * 1e-3) / 1e12
         peak = C.c_double()
         _lib.check(lib.xsq_fp64_peak(local, 2000, C.byref(peak)))
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm = None
-        if os.path.exists(peaks_path):
-            hbm = json.load(open(peaks_path)).get("hbm_gbs")
+        hbm, _ = hbm_peak()
+        kern = "rk_fast" if os.environ.get("XSQ_NO_FAST") != "1" else "rk_persistent"
+        tkey = f"{kern}_{args.method}_lorenz_{N}_T{args.t_end:g}_stiff{args.stiff}"
+        traffic, tnote = measured_traffic(tkey)
         line = {
             "metric": "accepted RK steps/sec (ensemble)",
             "value": value, "unit": "steps/s", "n_gpus": world,
@@ -390,16 +735,10 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at
-                # this size from the committed capture profiles/r01_ncu_full_
-                # rk_persistent_Ts5_lorenz_1250k_T100.txt: 0.23 GB + 2.54 GB with
-                # the stiffness diagnosis on (the 2.4 GB are the probe-queue
-                # records, 17.5 M x 160 B); 69.9 MB + 32.4 MB with it off
-                "traffic": (None if not (args.method == "Ts5" and N == LANES_PER_GPU
-                                         and args.t_end == T_END)
-                            else 2.765e9 if args.stiff > 0 else 102.2e6),
-                "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
-                "kernel": f"rk_persistent<{args.method}, Lorenz63>",
+                "traffic": traffic, "traffic_source": tnote,
+                "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + "
+                                "dram__bytes_write.sum, profiles/traffic.json)",
+                "kernel": f"{kern}<{args.method}, Lorenz63>",
                 "flops_per_attempted_step": att_f,
                 "peak_source": "xsq_fp64_peak: dependent-chain DFMA microbenchmark "
                                "measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry); "
@@ -410,60 +749,30 @@ def main():
             "wall_s_timed_region": t_wall,
             "kernel_ms_each_step": kern_ms,
         }
-        # second hot path of the north star: SSV2stab's fused stage kernel
-        # (HBM-bound, 40 B algorithmic per grid point and stage) on this GPU's
-        # slab of the 16384^2 grid (configs[4]: 2048 rows x 16384 at 8 GPUs)
-        ms_stage = C.c_double()
-        if lib.xsq_rkc_stage_bench(16384, 2048, 40, C.byref(ms_stage), None) == 0:
-            gbs = 16384 * 2048 * 40 / 1e9 / (ms_stage.value * 1e-3)
-            line["ssv2stab"] = {
-                "kernel": "k_stage (stencil RHS + three-term recurrence)",
-                "slab": "2048 x 16384 (1/8 of the 16384^2 grid)",
-                "ms_per_stage": ms_stage.value,
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm,
-                             "unit": "GB/s",
-                             "frac": gbs / hbm if hbm else None,
-                             # ncu, profiles/r01_ncu_full_rkc_k_stage_
-                             # 2048x16384.txt: 1.074 GB read + 0.2525 GB
-                             # written per launch (algorithmic 1.342 GB)
-                             "traffic": 1.3266e9,
-                             "bytes_per_point_stage": 40}}
-            try:    # end-to-end SSV2stab solve on the same slab (host loop,
-                    # error-norm reductions, first/final stages included)
-                import time as _t
-                nxs, rws = 16384, 2048
-                xg = torch.arange(1, nxs + 1, dtype=torch.float64, device=dev) / (nxs + 1)
-                yg = torch.arange(1, rws + 1, dtype=torch.float64, device=dev) / (rws + 1)
-                u0 = torch.outer(torch.sin(math.pi * yg), torch.sin(math.pi * xg))
-                rho = 8.0 * (nxs + 1.0) ** 2 + 2.0
-                for _ in range(2):
-                    torch.cuda.synchronize()
-                    t0 = _t.perf_counter()
-                    rr = xb.solve_pde_rkc("heat2d_reaction", (0.0, 3e-4), u0,
-                                          rho_jac=rho, rtol=1e-4, atol=1e-4,
-                                          max_steps=100)
-                    torch.cuda.synchronize()
-                    dt = _t.perf_counter() - t0
-                line["ssv2stab"]["solve"] = {
-                    "t_span": [0.0, 3e-4], "accepted": rr.n_accepted,
-                    "rejected": rr.n_rejected, "nfev": rr.nfev, "s_max": rr.maxm,
-                    "seconds": dt, "kernel_launches": rr.kernel_launches,
-                    "algorithmic_GBps": nxs * rws * 40 * rr.nfev / dt / 1e9}
-                del u0, rr
-            except Exception as exc:     # never lose the headline line
-                line["ssv2stab"]["solve"] = {"error": repr(exc)}
-        if not args.no_cpu:
+        if c5 is not None:
+            line["ssv2stab"] = c5
+        if world == 1 and which - {"c5"}:
+            try:
+                line["configs"] = run_extras(xb, dev, peak.value, which, y0_d, prm_d, args)
+            except Exception as exc:
+                line["configs"] = {"error": repr(exc)}
+        if not args.no_cpu and world == 1:
             cores = len(os.sched_getaffinity(0))
-            v_np, a_np, dt_np, lanes_np = cpu_numpy_port(
+            v_p, a_p, dt_p, lanes_p, kind = cpu_reference_pool(
                 args.method, args.cpu_lanes, args.t_end, cores)
-            v_c, a_c, dt_c, lanes_c = cpu_c_port(args.method, 0, args.t_end,
-                                                 cores)
+            v_s, a_s, dt_s, lanes_s, kind_s = cpu_reference_serial(args.method, args.t_end)
+            v_c, a_c, dt_c, lanes_c = cpu_c_port(args.method, 0, args.t_end, cores)
+            what = ("the unmodified reference (baseline/_ref: scipy solve_ivp + extensisq."
+                    f"{args.method})" if kind == "reference" else
+                    "NumPy restatement of the reference (bit-identical to it)")
             line["cpu_baseline"] = {
-                "value": v_np, "unit": "steps/s", "cores": cores, "kind": "port",
-                "sample": f"{lanes_np} lanes of the same ensemble, full t span, "
-                          f"{a_np} accepted steps in {dt_np:.1f} s; NumPy restatement "
-                          "of the reference (bit-identical to it, same Python/NumPy "
-                          "cost model), one process per core"}
+                "value": v_p, "unit": "steps/s", "cores": cores, "kind": kind,
+                "sample": f"{lanes_p} lanes of the same ensemble, full t span, "
+                          f"{a_p} accepted steps in {dt_p:.1f} s; {what}, one process per core"}
+            line["cpu_baseline_serial"] = {
+                "value": v_s, "unit": "steps/s", "cores": 1, "kind": kind_s,
+                "sample": f"{lanes_s} lanes, full t span, {a_s} accepted steps in {dt_s:.1f} s; "
+                          "one process, OPENBLAS_NUM_THREADS=1"}
             line["cpu_baseline_c"] = {
                 "value": v_c, "unit": "steps/s", "cores": cores, "kind": "port",
                 "sample": f"{lanes_c} lanes, full t span, {a_c} accepted steps in "
@@ -472,6 +781,7 @@ def main():
                           "reference's own Python"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

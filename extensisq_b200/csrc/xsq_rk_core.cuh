@@ -33,6 +33,8 @@
 #pragma once
 #include "xsq_tableaux_gen.cuh"
 #include "xsq_math_tables_gen.cuh"
+#include "xsq_math.cuh"
+#include "xsq_intrin.cuh"
 
 namespace xsq {
 
@@ -76,7 +78,7 @@ struct RkDev {
     // l2 = log2(sum((err/scale)^2)) = 2 log2(error_norm) + log2 n:
     //   safety    * error_norm^err_exp                     = 2^(a1s l2 + a0s)
     //   safety_sc * error_norm^minbeta1 * err_old^minbeta2 = 2^(a1c l2 + a2c l2_old + a0c)
-    double ctl_a1s, ctl_a0s, ctl_a1c, ctl_a2c, ctl_a0c;
+    CtlConst ctl;
     // rk_fast: high words that bracket "min_step < h_abs < max_step" (xsq_rk_fast.cuh)
     int fast_hi_min, fast_hi_span;
     const double* t_eval;
@@ -179,54 +181,16 @@ __device__ __forceinline__ void math_tabs_init() {
     __syncthreads();
 }
 
-// arithmetic of log2 / exp2 on table entries already loaded (shared by the
-// pointer forms below and the explicit shared-address forms of xsq_rk_fast.cuh)
-__device__ __forceinline__ int log2_tab_offset(double x) {      // in doubles
-    return (__double2hiint(x) >> 11) & (127 << 2);
-}
-__device__ __forceinline__ double log2_arith(double x, double inv, double l_hi, double l_lo) {
-    const int hi = __double2hiint(x);
-    const int e = ((hi >> 20) & 0x7ff) - 1023;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    const double r = fma(m, inv, -1.0);
-    double q = fma(r, c_xsq_lg_pol[5], c_xsq_lg_pol[4]);
-    q = fma(r, q, c_xsq_lg_pol[3]);
-    q = fma(r, q, c_xsq_lg_pol[2]);
-    q = fma(r, q, c_xsq_lg_pol[1]);
-    q = fma(r, q, c_xsq_lg_pol[0]);
-    const double t = fma(r, q, l_lo);
-    // (double)e without a conversion instruction: 2^52 + 2^51 + e, exact
-    const double ed = __hiloint2double(0x43380000, e) - 0x1.8p52;
-    return (ed + l_hi) + t;
-}
 __device__ __forceinline__ double log2_core(double x) {
     const double* T = math_tabs().lg + log2_tab_offset(x);
     const double2 t01 = *reinterpret_cast<const double2*>(T);
-    return log2_arith(x, t01.x, t01.y, T[2]);
+    return log2_arith(x, t01.x, t01.y, T[2], c_xsq_lg_pol);
 }
 
-// |z| < 1000, so 2^n never leaves the exponent range
-struct Exp2Split { double r; int N; };
-__device__ __forceinline__ Exp2Split exp2_split(double z) {
-    const double t = z + 0x1.8p46;                     // rounds z to a multiple of 1/64
-    Exp2Split s;
-    s.N = __double2loint(t);                           // 64 n + j
-    s.r = z - (t - 0x1.8p46);                          // |r| <= 2^-7, exact
-    return s;
-}
-__device__ __forceinline__ double exp2_arith(const Exp2Split& s, double t_hi, double t_lo) {
-    double p = fma(s.r, c_xsq_e2_pol[4], c_xsq_e2_pol[3]);
-    p = fma(s.r, p, c_xsq_e2_pol[2]);
-    p = fma(s.r, p, c_xsq_e2_pol[1]);
-    p = fma(s.r, p, c_xsq_e2_pol[0]);
-    p = s.r * p;                                        // 2^r - 1
-    const double v = fma(t_hi, p, t_lo) + t_hi;
-    return __hiloint2double(__double2hiint(v) + ((s.N >> 6) << 20), __double2loint(v));
-}
 __device__ __forceinline__ double exp2_core(double z) {
     const Exp2Split s = exp2_split(z);
     const double2 T = *reinterpret_cast<const double2*>(math_tabs().e2 + ((s.N & 63) << 1));
-    return exp2_arith(s, T.x, T.y);
+    return exp2_arith(s, T.x, T.y, c_xsq_e2_pol);
 }
 
 // log2 with the special values: 0 -> -inf, +inf -> +inf, NaN -> NaN (a
@@ -250,8 +214,7 @@ __device__ __forceinline__ double exp2_fast(double z) {
 // relative 1e-12 moves an accept/reject decision with probability ~1e-12 per
 // step (measured: step counts unchanged on every parity lane).
 __device__ __forceinline__ double rcp_scale(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double r = rcp64h_seed(x);
     const double e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
@@ -271,18 +234,8 @@ __device__ __forceinline__ double ctl_factor(const RkDev& P, double l2, double l
                                              double z_extra, bool accept, bool second,
                                              bool rej, bool tiny, double max_factor,
                                              E2 e2 = E2()) {
-    const double z_std = fma(P.ctl_a1s, l2, P.ctl_a0s);
-    double z_sc = fma(P.ctl_a1c, l2, fma(P.ctl_a2c, l2_old, P.ctl_a0c));
-    if (EXTRA) z_sc += z_extra;
-    const double raw = e2(second ? z_sc : z_std);
-    // max(min_factor, .) on rejection and in the second order branch only
-    double factor = raw;
-    if ((!accept || second) && !(raw > kMinFactor)) factor = kMinFactor;
-    // min(max_factor, .) in the second order branch; min(1, .) after a rejection
-    const double hi = (accept && rej) ? 1.0 : (second ? max_factor : XSQ_INF);
-    if (!(factor < hi)) factor = hi;
-    if (accept && tiny) factor = rej ? 1.0 : max_factor;
-    return factor;
+    return ctl_factor_arith<EXTRA>(P.ctl, l2, l2_old, z_extra, accept, second, rej, tiny,
+                                   max_factor, e2);
 }
 
 // RMS norm, common.py:64-66
@@ -308,7 +261,11 @@ __device__ __forceinline__ double atol_of(const RkDev& P, int k, int lane) {
 // sector (two 16-byte stores) instead of four scattered 8-byte stores: 4x
 // fewer store instructions and only full-sector writes reach L2/HBM.
 // Shared layout [component][slot][thread]: conflict-free for any mix of slots.
+#ifndef XSQ_HOST_EMU
 extern __shared__ double xsq_eval_stage[];
+#else
+static double xsq_eval_stage[4 * 64];      // host emulation: one thread per block
+#endif
 
 template <class R>
 __device__ __forceinline__ void eval_put(const RkDev& P, long long sys, int lane,
@@ -1833,9 +1790,9 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         if (!__any_sync(full, Lane<Tab, R>::probes_pending())) return;
         if (Lane<Tab, R>::probes_pending()) {
             Lane<Tab, R> parked = L;
-            asm volatile("" ::"l"(&parked) : "memory");
+            memory_fence_for(&parked);
             const int evals = Lane<Tab, R>::flush_probes(P, cur, lane);
-            asm volatile("" ::"l"(&parked) : "memory");
+            memory_fence_for(&parked);
             L = parked;
             L.nfev += evals;
         }
@@ -1885,7 +1842,12 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
             }
             __syncwarp(full);
         }
-        if (__all_sync(full, !live)) break;
+        if (__all_sync(full, !live)) {
+            // nothing to step: done when the queue is exhausted, else refill (lanes
+            // that ended at once -- zero-length span -- must not end the warp)
+            if (__all_sync(full, exhausted)) break;
+            continue;
+        }
         // ---- attempts, until some lane of the warp ends its trajectory ----
         // Leaves the loop when a lane ends or has both probe slots taken
         // (LANE_FLUSH), and after kProbeWindow attempts (see below).
@@ -1901,7 +1863,12 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         }
         const bool expired = it >= kProbeWindow;
         if (expired) it = 0;
-        if (P.nfev_stiff_detect > 0 && (expired || __any_sync(full, st == LANE_FLUSH)))
+        // both slots of some thread taken: run the probes now.  Asked of the slot
+        // state, not of `st`: a trajectory may END on the very step that filled
+        // its thread's second slot (st is then LANE_FINISHED), and the thread's
+        // next trajectory must not find both slots occupied.
+        if (P.nfev_stiff_detect > 0 &&
+            (expired || __any_sync(full, Lane<Tab, R>::probes_urgent())))
             flush(live ? L.sys : -1);
         if (st == LANE_FLUSH) st = LANE_RUNNING;
         if (st != LANE_RUNNING) {

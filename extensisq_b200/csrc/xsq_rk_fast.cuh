@@ -31,6 +31,9 @@
 // (_step_impl, _reassess_stepsize, _comp_sol_err, _rk_stage), :370-516
 // (_diagnose_stiffness bookkeeping).
 #pragma once
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include "xsq_rk_core.cuh"
 
 namespace xsq {
@@ -86,34 +89,33 @@ struct FastShared {
 // 32-bit shared-memory addresses, formed once per thread and kept opaque so
 // that they stay in registers (re-deriving one costs three instructions)
 struct SmemAddr {
-    unsigned coef, lg, e2;
+    SAddr coef, lg, e2;
 };
-__device__ __forceinline__ double log2_core_s(double x, unsigned lg) {
-    const unsigned a = lg + (unsigned)log2_tab_offset(x) * 8u;
+__device__ __forceinline__ double log2_core_s(double x, SAddr lg) {
+    const SAddr a = lg + (unsigned)log2_tab_offset(x) * 8u;
     double inv, l_hi, l_lo;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(inv), "=d"(l_hi) : "r"(a));
-    asm("ld.shared.f64 %0, [%1+16];" : "=d"(l_lo) : "r"(a));
-    return log2_arith(x, inv, l_hi, l_lo);
+    lds2(a, inv, l_hi);
+    lds1_at<16>(a, l_lo);
+    return log2_arith(x, inv, l_hi, l_lo, c_xsq_lg_pol);
 }
 struct Exp2Shared {
-    unsigned e2;
+    SAddr e2;
     __device__ __forceinline__ double operator()(double z) const {
         const Exp2Split s = exp2_split(z);
         double t_hi, t_lo;
-        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t_hi), "=d"(t_lo)
-            : "r"(e2 + ((unsigned)(s.N & 63) << 4)));
-        return exp2_arith(s, t_hi, t_lo);
+        lds2(e2 + ((unsigned)(s.N & 63) << 4), t_hi, t_lo);
+        return exp2_arith(s, t_hi, t_lo, c_xsq_e2_pol);
     }
 };
 
 // two consecutive doubles of the stream (OFF even: one LDS.128), or one
 template <int OFF>
-__device__ __forceinline__ void coef_ld2(unsigned base, double& a, double& b) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a), "=d"(b) : "r"(base), "n"(OFF * 8));
+__device__ __forceinline__ void coef_ld2(SAddr base, double& a, double& b) {
+    lds2_stream<OFF * 8>(base, a, b);
 }
 template <int OFF>
-__device__ __forceinline__ void coef_ld1(unsigned base, double& a) {
-    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(a) : "r"(base), "n"(OFF * 8));
+__device__ __forceinline__ void coef_ld1(SAddr base, double& a) {
+    lds1_stream<OFF * 8>(base, a);
 }
 
 template <class Tab, int ROW>
@@ -123,7 +125,7 @@ struct CoefRow {
     static constexpr int BASE = L::base(ROW);
     double w[NNZ > 0 ? ((NNZ + 1) & ~1) : 2];
     template <int Q>
-    __device__ __forceinline__ void load_from(unsigned base) {
+    __device__ __forceinline__ void load_from(SAddr base) {
         if constexpr (2 * Q + 1 < NNZ) {
             coef_ld2<BASE + 2 * Q>(base, w[2 * Q], w[2 * Q + 1]);
             load_from<Q + 1>(base);
@@ -131,7 +133,7 @@ struct CoefRow {
             coef_ld1<BASE + 2 * Q>(base, w[2 * Q]);
         }
     }
-    __device__ __forceinline__ explicit CoefRow(unsigned base) { load_from<0>(base); }
+    __device__ __forceinline__ explicit CoefRow(SAddr base) { load_from<0>(base); }
     // coefficient of column J (a structural nonzero)
     template <int J>
     __device__ __forceinline__ double at() const { return w[L::index(ROW, J)]; }
@@ -226,7 +228,7 @@ struct FastLane {
     }
 
     template <int I>
-    __device__ __forceinline__ void stage(unsigned cb, double (&K)[S + 1][NL], double h) {
+    __device__ __forceinline__ void stage(SAddr cb, double (&K)[S + 1][NL], double h) {
         const CoefRow<Tab, I> a(cb);
         double ys[NL];
 #pragma unroll
@@ -246,7 +248,7 @@ struct FastLane {
         R::f(__dadd_rn(t, __dmul_rn(Tab::cv(I), h)), ys, prm, K[I]);
     }
     template <int I>
-    __device__ __forceinline__ void stages(unsigned cb, double (&K)[S + 1][NL], double h) {
+    __device__ __forceinline__ void stages(SAddr cb, double (&K)[S + 1][NL], double h) {
         if constexpr (I < S) {
             stage<I>(cb, K, h);
             stages<I + 1>(cb, K, h);
@@ -257,7 +259,7 @@ struct FastLane {
     // address of the coefficient stream, `h0`: this thread's word of the
     // "h_abs at the start of the step" array.
     __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa, double* h0) {
-        const unsigned cb = sa.coef;
+        const SAddr cb = sa.coef;
         constexpr unsigned HI_N = hi_word_of_small_int(R::N);          // (double)N
         constexpr unsigned HI_TINY = HI_N - (1022u << 20);             // N * 2^-1022
         const double h = h_abs * P.direction;
@@ -470,19 +472,21 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     LN::stiff_state().bits[threadIdx.x] = 0u;
     __syncthreads();
     SmemAddr sa;
-    sa.coef = (unsigned)__cvta_generic_to_shared(fs.coef);
-    sa.lg = (unsigned)__cvta_generic_to_shared(math_tabs().lg);
-    sa.e2 = (unsigned)__cvta_generic_to_shared(math_tabs().e2);
-    asm volatile("" : "+r"(sa.coef), "+r"(sa.lg), "+r"(sa.e2));
+    sa.coef = saddr_of(fs.coef);
+    sa.lg = saddr_of(math_tabs().lg);
+    sa.e2 = saddr_of(math_tabs().e2);
+    keep_in_register(sa.coef);
+    keep_in_register(sa.lg);
+    keep_in_register(sa.e2);
     FL L;
     bool live = false, exhausted = false;
     auto flush = [&](long long cur) {
         if (!__any_sync(full, LN::probes_pending())) return;
         if (LN::probes_pending()) {
             FL parked = L;
-            asm volatile("" ::"l"(&parked) : "memory");
+            memory_fence_for(&parked);
             const int evals = LN::flush_probes(P, cur, lane);
-            asm volatile("" ::"l"(&parked) : "memory");
+            memory_fence_for(&parked);
             L = parked;
             L.nfev0 += evals;
         }
@@ -519,7 +523,12 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
             }
         }
         __syncwarp(full);
-        if (__all_sync(full, !live)) break;
+        if (__all_sync(full, !live)) {
+            // nothing to step: done when the queue is exhausted, else refill (lanes
+            // that ended at once -- zero-length span -- must not end the warp)
+            if (__all_sync(full, exhausted)) break;
+            continue;
+        }
         // ---- attempts, until some lane of the warp ends its trajectory ----
         int st = LANE_RUNNING;
         do {
@@ -535,6 +544,40 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         __syncwarp(full);
     }
     if (P.nfev_stiff_detect > 0) flush(-1);
+}
+
+// ---- host side -----------------------------------------------------------------
+// The ensemble hot path: adaptive, final state only, default step budget,
+// controller without the alpha term.  XSQ_NO_FAST=1 forces the generic kernel
+// (tests compare the two bit for bit).
+template <class Tab, class R>
+inline bool fast_eligible(const RkDev& P) {
+    if constexpr (Tab::VARIANT != tab::GENERIC || R::WARP) {
+        return false;
+    } else {
+        if (P.n_forced != 0 || P.n_eval != 0 || P.n_events != 0) return false;
+        if (P.minalpha != 0.0 || P.max_steps != 0x7fffffff) return false;
+        if (P.n_lanes >= (1LL << 31)) return false;
+        const char* e = getenv("XSQ_NO_FAST");
+        return !(e && e[0] == '1');
+    }
+}
+// high words that bracket "min_step < h_abs < max_step":
+// min_step = max(H_MIN_A (|t| + h0), sqrt(tiny)) <= M for every step that starts
+// with 2 h0 < |t_bound - t| (common.py:123-148, 310-331)
+template <class Tab>
+inline void fast_prepare(RkDev& P) {
+    auto hi_word = [](double x) {
+        unsigned long long b;
+        memcpy(&b, &x, 8);
+        return (long long)(unsigned)(b >> 32);
+    };
+    const double tmax = fmax(fabs(P.t0), fabs(P.t_bound));
+    const double span = fabs(P.t_bound - P.t0);
+    const double M = fmax(Tab::H_MIN_A * (tmax + 0.5 * span), 0x1.0p-511) * (1.0 + 0x1.0p-30);
+    const long long lo = hi_word(M), hi = hi_word(P.max_step);
+    P.fast_hi_min = (int)lo;
+    P.fast_hi_span = (int)(hi - lo - 1 > 0 ? hi - lo - 1 : 0);
 }
 
 template <class Tab, class R, int BLOCK, int MINB>

@@ -32,28 +32,6 @@ struct Geometry {
         KDOUBLES <= 21 ? 4 : (KDOUBLES <= 36 ? 3 : 2);
 };
 
-static unsigned hi_word(double x) {
-    unsigned long long b;
-    std::memcpy(&b, &x, 8);
-    return (unsigned)(b >> 32);
-}
-
-// The ensemble hot path (xsq_rk_fast.cuh): adaptive, final state only, default
-// step budget, controller without the alpha term.  XSQ_NO_FAST=1 forces the
-// generic kernel (tests compare the two bit for bit).
-template <class Tab, class R>
-static bool fast_eligible(const RkDev& P) {
-    if constexpr (Tab::VARIANT != tab::GENERIC || R::WARP) {
-        return false;
-    } else {
-        if (P.n_forced != 0 || P.n_eval != 0 || P.n_events != 0) return false;
-        if (P.minalpha != 0.0 || P.max_steps != std::numeric_limits<int>::max()) return false;
-        if (P.n_lanes >= (1LL << 31)) return false;
-        const char* e = getenv("XSQ_NO_FAST");
-        return !(e && e[0] == '1');
-    }
-}
-
 template <class Tab, class R>
 static int launch_fast(const RkDev& P0, cudaStream_t st, LaunchInfo* info) {
     if constexpr (Tab::VARIANT != tab::GENERIC || R::WARP) {
@@ -61,14 +39,7 @@ static int launch_fast(const RkDev& P0, cudaStream_t st, LaunchInfo* info) {
     } else {
         constexpr int BLOCK = Geometry<Tab, R>::BLOCK, MINB = Geometry<Tab, R>::MINB;
         RkDev P = P0;
-        // min_step = max(H_MIN_A (|t| + h0), sqrt(tiny)) <= M for every step that
-        // starts with 2 h0 < |t_bound - t| (common.py:123-148, 310-331)
-        const double tmax = std::fmax(std::fabs(P.t0), std::fabs(P.t_bound));
-        const double span = std::fabs(P.t_bound - P.t0);
-        const double M = std::fmax(Tab::H_MIN_A * (tmax + 0.5 * span), 0x1.0p-511) * (1.0 + 0x1.0p-30);
-        const long long lo = hi_word(M), hi = hi_word(P.max_step);
-        P.fast_hi_min = (int)lo;
-        P.fast_hi_span = (int)(hi - lo - 1 > 0 ? hi - lo - 1 : 0);
+        fast_prepare<Tab>(P);
         auto kern = rk_fast<Tab, R, BLOCK, MINB>;
         int dev = 0, n_sm = 0, occ = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;

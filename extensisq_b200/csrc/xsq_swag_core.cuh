@@ -539,7 +539,12 @@ __device__ __forceinline__ void swag_persistent_body(const RkDev& P) {
             }
             __syncwarp(full);
         }
-        if (__all_sync(full, !live)) break;
+        if (__all_sync(full, !live)) {
+            // nothing to step: done when the queue is exhausted, else refill (lanes
+            // that ended at once -- zero-length span -- must not end the warp)
+            if (__all_sync(full, exhausted)) break;
+            continue;
+        }
         int st = LANE_RUNNING;
         do {
             if (live) st = L.attempt(P, lane);

@@ -881,3 +881,18 @@ int xsq_oracle_devmath(int fn, const double* x, double* out, int64_t n) {
     }
     return 0;
 }
+
+/* the controller restated (ctl_factor_dev) with explicit constants (tests) */
+int xsq_oracle_ctl(const double* c, const double* l2, const double* l2_old, const double* zx,
+                   const int* flags, const double* mf, double* out, int64_t n) {
+    lane_t L;
+    L.ctl_a1s = c[0]; L.ctl_a0s = c[1]; L.ctl_a1c = c[2]; L.ctl_a2c = c[3]; L.ctl_a0c = c[4];
+    for (int64_t i = 0; i < n; ++i) {
+        const int f = flags[i];
+        L.l2_old = l2_old[i];
+        L.max_factor = mf[i];
+        out[i] = ctl_factor_dev(&L, l2[i], zx[i], (f & 16) != 0, f & 1, (f & 2) != 0, (f & 4) != 0,
+                                (f & 8) != 0);
+    }
+    return 0;
+}

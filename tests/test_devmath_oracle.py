@@ -83,3 +83,75 @@ def test_cost_of_device_arithmetic(name, prob, T):
     assert same.mean() >= (0.95 if prob == "arenstorf" else 0.99)
     sel = same & (a["status"] == 0)
     assert np.abs(a["y_final"][sel] - b["y_final"][sel]).max() < 1e-5 * max(1.0, np.abs(a["y_final"]).max())
+
+
+# ---- the device source itself, compiled for the host ---------------------------
+def _host_math():
+    import ctypes as C
+    import tempfile
+    src = os.path.join(ROOT, "tests", "devmath_host", "host_math.cpp")
+    out = os.path.join(tempfile.gettempdir(), f"xsq_host_math_{os.getpid()}.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma",
+                           "-ffp-contract=off", "-I", os.path.join(ROOT, "extensisq_b200", "csrc"),
+                           "-I", os.path.join(ROOT, "oracle"), "-o", out, src])
+    return C.CDLL(out)
+
+
+def _call(fn, x):
+    import ctypes as C
+    x = np.ascontiguousarray(x, dtype=float)
+    o = np.empty_like(x)
+    fn(x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_long(x.size))
+    return o
+
+
+def test_device_source_equals_oracle_restatement_bit_for_bit():
+    """extensisq_b200/csrc/xsq_math.cuh (log2_arith, exp2_arith, ctl_factor_arith:
+    the source the kernels compile) built for the host against
+    oracle/xsq_devmath.h: identical bits on every input, including arguments
+    below 1 (negative exponents), subnormals, 0, Inf and NaN patterns."""
+    import ctypes as C
+    lib = _host_math()
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([2.0 ** rng.uniform(-1070, 1023, 200000), rng.uniform(0, 4, 100000),
+                         [0.0, 1.0, 0.5, 3.0, 2.9999999999, np.inf, np.nan, 5e-324, 1e-310,
+                          2.2250738585072014e-308, 1.7976931348623157e308]])
+    a, b = _call(lib.host_log2, xs), CO.devmath("log2", xs)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    # and it IS a logarithm below 1 (the exponent conversion is sign safe)
+    sel = (xs > 1e-300) & (xs < 1e300)
+    assert np.abs(a[sel] - np.log2(xs[sel])).max() < 1e-12
+    zs = np.concatenate([rng.uniform(-1000, 1000, 200000), rng.uniform(-2, 2, 100000),
+                         [0.0, -0.0, 1.0, -1.0, 0.015625, -0.0078125]])
+    a, b = _call(lib.host_exp2, zs), CO.devmath("exp2", zs)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    # controller: every flag combination, all presets
+    olib = CO.load()
+    n = 200000
+    for kb1, kb2, g, ns in [(0.7, -0.4, 0.9, 3), (0.6, -0.2, 0.9, 2), (1.0, 0.0, 0.9, 4),
+                            (0.7, -0.4, 0.8, 192)]:
+        for order in (3, 4, 5, 6, 7):
+            e = -1.0 / (order + 1)
+            log2n = np.log2(float(ns))
+            a1s = 0.5 * e
+            a1c, a2c = 0.5 * kb1 * e, 0.5 * kb2 * e
+            c = np.array([a1s, np.log2(g) - a1s * log2n, a1c, a2c,
+                          np.log2(g ** (kb1 + kb2)) - (a1c + a2c) * log2n])
+            ss = 2.0 ** rng.uniform(-40, 12, n)
+            l2 = CO.devmath("log2", ss)
+            l2o = CO.devmath("log2", 2.0 ** rng.uniform(-40, 2, n))
+            zx = rng.uniform(-0.3, 0.3, n)
+            flags = rng.integers(0, 32, n).astype(np.int32)
+            flags = np.where((flags & 1) == 0, flags & ~2, flags).astype(np.int32)   # second implies accept
+            mf = np.where(rng.random(n) < 0.5, 4.0, 10.0)
+            o1, o2 = np.empty(n), np.empty(n)
+            args = [x.ctypes.data_as(C.c_void_p) for x in (c, l2, l2o, zx, flags, mf)]
+            lib.host_ctl(*args, o1.ctypes.data_as(C.c_void_p), C.c_long(n))
+            olib.xsq_oracle_ctl(*args, o2.ctypes.data_as(C.c_void_p), C.c_int64(n))
+            assert np.array_equal(o1.view(np.uint64), o2.view(np.uint64))
+            # sanity against the reference's formula (common.py:249-287) in plain pow
+            acc = (flags & 1) != 0
+            std = acc & ((flags & 2) == 0) & ((flags & 8) == 0) & ((flags & 4) == 0)
+            err = np.sqrt(ss / ns)
+            ref = g * err ** e
+            assert np.abs(o1[std] / ref[std] - 1).max() < 5e-15

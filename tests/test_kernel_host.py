@@ -1,0 +1,137 @@
+"""The CUDA kernel SOURCES (extensisq_b200/csrc: ens_init_body, rk_fast_body,
+rk_persistent_body, stiff_queue_body) compiled for the host by g++
+(tests/kernel_host/) and run over small ensembles, against the C oracle in
+device arithmetic: every output must be bit identical.  Checks the real kernel
+logic -- controller, _reassess_stepsize short cuts, stiffness bookkeeping, probe
+queue and slot paths, dense output -- without a GPU; the GPU tests
+(tests/test_gpu_exact.py, tests/test_gpu_fast.py) repeat it on the device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import extensisq_b200 as xb
+from oracle import c_oracle as CO
+from oracle import rk_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_host"))
+import emu  # noqa: E402
+
+TABS = O.load_tableaux()
+METHODS = [xb.Ts5, xb.BS5, xb.CK5, xb.Me4, xb.Pr7, xb.Pr8, xb.Pr9, xb.CFMR7osc]
+GENERIC = [xb.Ts5, xb.CK5, xb.Me4, xb.Pr7, xb.Pr8, xb.Pr9]
+KEYS_F = ("t_final", "y_final", "h_next")
+KEYS_I = ("n_accepted", "n_rejected", "nfev", "status", "stiff_flags")
+
+
+def lanes(prob, N, seed=12345):
+    rng = np.random.default_rng(seed)
+    if prob == "lorenz63":
+        y0 = np.stack([rng.uniform(-15, 15, N), rng.uniform(-20, 20, N), rng.uniform(5, 40, N)], 1)
+        prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
+        return y0, prm, (0.0, 6.0)
+    if prob == "vanderpol":
+        mu = 10.0 ** (-1 + 3 * np.arange(N) / max(N - 1, 1))
+        return np.tile([2.0, 0.0], (N, 1)), mu[:, None], (0.0, 6.0)
+    y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252240537862224]) + rng.uniform(-1e-3, 1e-3, (N, 4))
+    return y0, np.full((N, 1), 0.012277471), (0.0, 17.0652165601579625588917206249)
+
+
+def oracle(prob, span, y0, m, prm, **kw):
+    kw.pop("fast", None)
+    kw.pop("queue_records", None)
+    with CO.device_math():
+        return CO.rk_batch(TABS[m.__name__], prob, span, y0, params=prm, n_threads=CO.max_threads(), **kw)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def same(g, o, what, dense=False):
+    for k in KEYS_I:
+        assert np.array_equal(g[k], o[k]), (what, k, np.flatnonzero(g[k] != o[k])[:5])
+    for k in KEYS_F:
+        assert np.array_equal(bits(g[k]), bits(o[k])), (what, k)
+    if dense:
+        a, b = g["y"], o["y"]
+        ok = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+        assert ok.all(), (what, "y(t_eval)", np.argwhere(~ok)[:3])
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_kernel_source_equals_oracle_bit_for_bit(m, prob):
+    y0, prm, span = lanes(prob, 96)
+    for stiff in (5000, 300, 0):
+        kw = dict(rtol=1e-8, atol=1e-10, nfev_stiff_detect=stiff)
+        o = oracle(prob, span, y0, m, prm, **kw)
+        g = emu.solve(prob, span, y0, m, prm, fast=True, **kw)
+        assert g["used_fast"] == (m in GENERIC)
+        same(g, o, (m.__name__, prob, stiff, "fast"))
+        if m in GENERIC:                      # the generic kernel on the same input
+            g2 = emu.solve(prob, span, y0, m, prm, fast=False, **kw)
+            assert not g2["used_fast"]
+            same(g2, o, (m.__name__, prob, stiff, "generic"))
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_kernel_source_dense_output(m):
+    y0, prm, _ = lanes("lorenz63", 48, seed=7)
+    t_eval = np.linspace(0.0, 4.0, 131)
+    kw = dict(rtol=1e-7, atol=1e-9, t_eval=t_eval)
+    o = oracle("lorenz63", (0.0, 4.0), y0, m, prm, **kw)
+    g = emu.solve("lorenz63", (0.0, 4.0), y0, m, prm, **kw)
+    same(g, o, (m.__name__, "t_eval"), dense=True)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(rtol=1e-3, atol=1e-6), dict(rtol=1e-11, atol=1e-13),
+    dict(rtol=1e-6, atol=[1e-9, 1e-7, 1e-8]), dict(rtol=1e-8, atol=1e-10, max_step=0.02),
+    dict(rtol=1e-8, atol=1e-10, first_step=1e-3),
+    dict(rtol=1e-6, atol=1e-8, max_step=0.3, first_step=0.25),
+    dict(rtol=1e-6, atol=1e-8, sc_params=(0.6, -0.2, 0.0, 0.9)),
+    dict(rtol=1e-6, atol=1e-8, sc_params=(0.7, -0.4, 0.1, 0.8)),
+], ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items() if k != "atol"))
+def test_kernel_source_options(kw):
+    y0, prm, _ = lanes("lorenz63", 64, seed=21)
+    for m in (xb.Ts5, xb.BS5, xb.Pr7):
+        for span in ((0.0, 3.0), (0.4, 0.0)):
+            o = oracle("lorenz63", span, y0, m, prm, **kw)
+            same(emu.solve("lorenz63", span, y0, m, prm, fast=True, **kw), o, (m.__name__, kw, span))
+            same(emu.solve("lorenz63", span, y0, m, prm, fast=False, **kw), o, (m.__name__, kw, span))
+
+
+def test_kernel_source_failures_and_edge_spans():
+    # explicit method on a very stiff lane with absurd tolerances: rejected steps, tiny steps
+    y0 = np.tile([2.0, 0.0], (8, 1))
+    mu = np.full((8, 1), 1e9)
+    for m in (xb.Ts5, xb.Pr9, xb.CFMR7osc):
+        kw = dict(rtol=1e-12, atol=1e-14)
+        o = oracle("vanderpol", (0.0, 1e-5), y0, m, mu, **kw)
+        same(emu.solve("vanderpol", (0.0, 1e-5), y0, m, mu, **kw), o, (m.__name__, "stiff"))
+    # overflow
+    y0 = np.tile([1e200, 1e200, 1e200], (8, 1))
+    prm = np.tile([10.0, 28.0, 8.0 / 3.0], (8, 1))
+    for m in (xb.Ts5, xb.BS5):
+        o = oracle("lorenz63", (0.0, 1.0), y0, m, prm, rtol=1e-8, atol=1e-10)
+        g = emu.solve("lorenz63", (0.0, 1.0), y0, m, prm, rtol=1e-8, atol=1e-10)
+        assert (g["status"] != 0).all()
+        same(g, o, (m.__name__, "overflow"))
+    # zero-length span, span shorter than the first step, time far from zero
+    y0, prm, _ = lanes("lorenz63", 16, seed=5)
+    for span in ((1.0, 1.0), (0.0, 1e-9), (1e6, 1e6 + 2.0), (-3.0, -1.0)):
+        o = oracle("lorenz63", span, y0, xb.Ts5, prm, rtol=1e-7, atol=1e-9)
+        same(emu.solve("lorenz63", span, y0, xb.Ts5, prm, rtol=1e-7, atol=1e-9), o, span)
+
+
+def test_kernel_source_probe_queue_and_slots_agree():
+    y0, prm, _ = lanes("lorenz63", 80, seed=11)
+    kw = dict(rtol=1e-8, atol=1e-10, nfev_stiff_detect=240)
+    o = oracle("lorenz63", (0.0, 8.0), y0, xb.Ts5, prm, **kw)
+    assert o["nfev"].sum() > 0
+    for q in (0, 7, 1000, -1):
+        for fast in (True, False):
+            g = emu.solve("lorenz63", (0.0, 8.0), y0, xb.Ts5, prm, fast=fast, queue_records=q, **kw)
+            same(g, o, ("queue", q, fast))
