@@ -32,12 +32,31 @@ struct Geometry {
         KDOUBLES <= 21 ? 4 : (KDOUBLES <= 36 ? 3 : 2);
 };
 
+// CTAs per SM of the fast kernel.  It is bound by the fp64 pipe, and what keeps
+// the pipe busy is the number of warps per scheduler: one more CTA per SM than
+// the generic kernel (96 instead of 128 registers for a 6-stage pair on a
+// 3-component system, no spills inside the loop) measured faster; XSQ_FAST_MINB
+// overrides it (profiling).
 template <class Tab, class R>
+struct FastGeometry {
+    static constexpr int BASE = Geometry<Tab, R>::MINB;
+    static constexpr int MINB = BASE + 1;
+};
+
+template <class Tab, class R, int MINB = FastGeometry<Tab, R>::MINB>
 static int launch_fast(const RkDev& P0, cudaStream_t st, LaunchInfo* info) {
     if constexpr (Tab::VARIANT != tab::GENERIC || R::WARP) {
         return XSQ_ERR_UNSUPPORTED;
     } else {
-        constexpr int BLOCK = Geometry<Tab, R>::BLOCK, MINB = Geometry<Tab, R>::MINB;
+        constexpr int BLOCK = Geometry<Tab, R>::BLOCK;
+        if constexpr (MINB == FastGeometry<Tab, R>::MINB) {
+            if (const char* e = getenv("XSQ_FAST_MINB")) {
+                const int want = atoi(e);
+                constexpr int B = FastGeometry<Tab, R>::BASE;
+                if (want == B) return launch_fast<Tab, R, B>(P0, st, info);
+                if (want == B + 2) return launch_fast<Tab, R, B + 2>(P0, st, info);
+            }
+        }
         RkDev P = P0;
         fast_prepare<Tab>(P);
         auto kern = rk_fast<Tab, R, BLOCK, MINB>;

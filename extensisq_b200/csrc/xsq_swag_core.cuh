@@ -382,7 +382,9 @@ struct SwagLane {
         } else if (0.5 >= erk) {
             hnew = h;
         } else {
-            const double r = pow(0.5 / erk, 1.0 / (k + 1));
+            // (0.5 / erk) ** (1 / (k + 1)), shampine.py:465, with the controller's
+            // table-driven log2 / exp2 (repeated bit for bit by the C oracle)
+            const double r = exp2_fast(log2_fast(0.5 / erk) / (double)(k + 1));
             hnew = absh * fmax(0.5, fmin(0.9, r));
             hnew = copysign(fmax(hnew, min_step), h);
         }
@@ -497,6 +499,7 @@ __device__ __forceinline__ void swag_persistent_body(const RkDev& P) {
     const int lane = threadIdx.x & 31;
     SwagLane<R> L;
     bool live = false, exhausted = false;
+    math_tabs_init();
     for (;;) {
         if (R::WARP) {
             if (!live && !exhausted) {

@@ -48,6 +48,7 @@
 const uint8_t* xsq_rcp64h_delta = 0;
 static int g_device_math = 0;
 void xsq_oracle_set_rcp_table(const uint8_t* bits) { xsq_rcp64h_delta = bits; }
+int xsq_oracle_device_math(void) { return g_device_math; }
 int xsq_oracle_set_device_math(int on) {
     if (on && !xsq_rcp64h_delta) return -1;
     g_device_math = on;

@@ -23,6 +23,8 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "xsq_devmath.h"     /* the kernels' own log2 / exp2 (device arithmetic mode) */
+int xsq_oracle_device_math(void);
 
 #define SMALL 0x1.0000000000001p-53
 #define MAXN 192
@@ -278,7 +280,17 @@ static int swag_step(swag_t* S, int max_steps) {
     if (S->phase1 || 0.5 >= erk * TWO[k]) hnew = h + h;
     else if (0.5 >= erk) hnew = h;
     else {
-        const double r = pow(0.5 / erk, 1.0 / (k + 1));
+        double r;
+        if (xsq_oracle_device_math()) {      /* the kernel's own log2 / exp2 */
+            const double q = 0.5 / erk;
+            double l = dev_log2(q);
+            if (q == 0.0) l = -INFINITY;
+            if (!(q < INFINITY)) l = q;
+            const double z = l / (double)(k + 1);
+            r = (fabs(z) < 1000.0) ? dev_exp2(z) : NAN;
+        } else {
+            r = pow(0.5 / erk, 1.0 / (k + 1));
+        }
         hnew = absh * fmax(0.5, fmin(0.9, r));
         hnew = copysign(fmax(hnew, min_step), h);
     }

@@ -30,6 +30,7 @@ double xsq_host_rcp64h(double x) {
 }  // namespace xsq
 
 #include "xsq_rk_fast.cuh"
+#include "xsq_swag_core.cuh"
 #include "xsq_rhs.cuh"
 #include "xsq_user.h"
 
@@ -129,6 +130,56 @@ extern "C" int xsq_emu_rk_solve(const xsq_rk_args_t* a, int want_fast, long long
         case XSQ_PR9: return run_rhs<tab::Pr9>(a->rhs, P, mi, want_fast, used_fast);
         case XSQ_CFMR7OSC: return run_rhs<tab::CFMR7osc>(a->rhs, P, mi, want_fast, used_fast);
         case XSQ_CKDISC: return run_rhs<tab::CKdisc>(a->rhs, P, mi, want_fast, used_fast);
+        default: return XSQ_ERR_UNSUPPORTED;
+    }
+}
+
+template <class R>
+static int run_swag(RkDev P) {
+    const long long N = P.n_lanes;
+    gridDim = {1, 1, 1};
+    blockDim = {1, 1, 1};
+    threadIdx = {0, 0, 0};
+    for (long long i = 0; i < N; ++i) {
+        blockIdx = {(unsigned)i, 0, 0};
+        ens_init_body<R>(P);
+    }
+    blockIdx = {0, 0, 0};
+    swag_persistent_body<R>(P);
+    return 0;
+}
+
+// xsq_swag_solve (xsq_api.cu) on the host
+extern "C" int xsq_emu_swag_solve(const xsq_rk_args_t* args, int k_max) {
+    if (!xsq_emu_rcp_bits || k_max < 1 || k_max > 12) return XSQ_ERR_ARG;
+    xsq_rk_args_t a = *args;
+    a.method = XSQ_METHOD_SWAG;
+    a.interpolant = XSQ_INTERP_FREE;
+    a.use_sc_params = 0;
+    a.h_forced = nullptr;
+    a.n_forced = 0;
+    a.reserved0 = k_max;
+    RkDev P;
+    MethodInfo mi;
+    std::vector<double> atol;
+    int rc = build_params(&a, &P, &mi, &atol);
+    if (rc != XSQ_OK) return rc;
+    if (a.n_lanes == 0) return XSQ_OK;
+    const size_t N = (size_t)a.n_lanes, ns = atol.size();
+    std::vector<unsigned long long> counters(2, 0ULL);
+    std::vector<double> init_h(N), init_f0(N * ns);
+    std::vector<int> init_nfev(N);
+    P.queue = &counters[0];
+    P.stiff_q_count = &counters[1];
+    P.atol_dev = atol.data();
+    P.init_h = init_h.data();
+    P.init_f0 = init_f0.data();
+    P.init_nfev = init_nfev.data();
+    P.morder = 1;
+    switch (a.rhs) {
+        case XSQ_RHS_LORENZ63: return run_swag<rhs::Lorenz63>(P);
+        case XSQ_RHS_VANDERPOL: return run_swag<rhs::VanDerPol>(P);
+        case XSQ_RHS_ARENSTORF: return run_swag<rhs::Arenstorf>(P);
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }

@@ -17,7 +17,8 @@ def build():
     src = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h")]
     src += [os.path.join(ROOT, "extensisq_b200", "csrc", f) for f in
             ("xsq_rk_core.cuh", "xsq_rk_fast.cuh", "xsq_math.cuh", "xsq_intrin.cuh",
-             "xsq_params.h", "xsq_rhs.cuh", "xsq_tableaux_gen.cuh", "xsq_math_tables_gen.cuh")]
+             "xsq_params.h", "xsq_rhs.cuh", "xsq_tableaux_gen.cuh", "xsq_math_tables_gen.cuh",
+             "xsq_swag_core.cuh")]
     out = os.path.join(HERE, "_build", "xsq_emu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if (not os.path.exists(out) or
@@ -42,7 +43,7 @@ def load():
 
 def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step=None,
           max_step=np.inf, sc_params=None, interpolant=None, t_eval=None, forced_steps=None,
-          nfev_stiff_detect=5000, max_steps=None, fast=True, queue_records=-1):
+          nfev_stiff_detect=5000, max_steps=None, fast=True, queue_records=-1, k_max=None):
     """Same arguments as extensisq_b200.solve_ivp_batched (built-in rhs names,
     built-in methods); returns numpy arrays."""
     from extensisq_b200 import _lib as L
@@ -70,7 +71,8 @@ def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step
     atol_np = np.atleast_1d(np.asarray(atol, dtype=float))
     a = L.XsqRkArgs()
     a.struct_size = C.sizeof(L.XsqRkArgs)
-    a.method, a.rhs = method._xsq_method, rid
+    is_swag = getattr(method, "__name__", "") == "SWAG"
+    a.method, a.rhs = (0 if is_swag else method._xsq_method), rid
     a.n_state, a.n_param = n, p
     a.interpolant = L.INTERPOLANTS[interpolant]
     a.n_lanes = N
@@ -101,8 +103,12 @@ def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step
     a.nfev_stiff_detect = int(nfev_stiff_detect)
     a.stiff_flags = ptr(ints["stiff_flags"])
     used = C.c_int(0)
-    rc = lib.xsq_emu_rk_solve(C.byref(a), 1 if fast else 0, C.c_longlong(queue_records),
-                              C.byref(used))
+    if is_swag:
+        a.nfev_stiff_detect = 0
+        rc = lib.xsq_emu_swag_solve(C.byref(a), int(k_max) if k_max else 12)
+    else:
+        rc = lib.xsq_emu_rk_solve(C.byref(a), 1 if fast else 0, C.c_longlong(queue_records),
+                                  C.byref(used))
     if rc != 0:
         raise RuntimeError(f"emu rc={rc}: {lib.xsq_emu_detail().decode()}")
     out = dict(t_final=t_final, y_final=np.ascontiguousarray(y_final.T), h_next=h_next,

@@ -77,7 +77,8 @@ def test_fast_kernel_options(kw):
 
 def test_fast_kernel_backward_and_zero_span():
     y0, prm = lorenz_lanes(300, seed=5)
-    for span in ((2.0, 0.5), (1.0, 1.0), (-1.0, -1.5)):
+    # (backward in time the Lorenz system expands: keep the spans short)
+    for span in ((0.4, 0.0), (1.0, 1.0), (-1.0, -1.3)):
         a = solve("lorenz63", span, y0, xb.Ts5, prm, True, rtol=1e-7, atol=1e-9)
         b = solve("lorenz63", span, y0, xb.Ts5, prm, False, rtol=1e-7, atol=1e-9)
         same(a, b)

@@ -135,3 +135,24 @@ def test_kernel_source_probe_queue_and_slots_agree():
         for fast in (True, False):
             g = emu.solve("lorenz63", (0.0, 8.0), y0, xb.Ts5, prm, fast=fast, queue_records=q, **kw)
             same(g, o, ("queue", q, fast))
+
+
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_swag_kernel_source_equals_oracle_bit_for_bit(prob):
+    """swag_persistent_body (xsq_swag_core.cuh) on the host against
+    oracle/xsq_oracle_swag.c in device arithmetic, with and without t_eval."""
+    y0, prm, span = lanes(prob, 96)
+    for te in (None, np.linspace(span[0], span[1], 57)):
+        for kw in (dict(rtol=1e-8, atol=1e-10), dict(rtol=1e-4, atol=1e-7, k_max=5),
+                   dict(rtol=1e-6, atol=1e-9, max_step=0.05 * (span[1] - span[0]))):
+            okw = dict(kw, t_eval=te)
+            with CO.device_math():
+                o = CO.swag_batch(prob, span, y0, params=prm, n_threads=CO.max_threads(), **okw)
+            g = emu.solve(prob, span, y0, xb.SWAG, prm, **okw)
+            for k in ("n_accepted", "n_rejected", "nfev", "status"):
+                assert np.array_equal(g[k], o[k]), (prob, kw, k)
+            for k in ("t_final", "y_final"):
+                assert np.array_equal(bits(g[k]), bits(o[k])), (prob, kw, k)
+            if te is not None:
+                ok = (bits(g["y"]) == bits(o["y"])) | (np.isnan(g["y"]) & np.isnan(o["y"]))
+                assert ok.all(), (prob, kw, "y(t_eval)")
