@@ -90,6 +90,7 @@ struct FastShared {
 // that they stay in registers (re-deriving one costs three instructions)
 struct SmemAddr {
     SAddr coef, lg, e2;
+    SAddr h0;      // this thread's "h_abs at the start of the step" word
 };
 __device__ __forceinline__ double log2_core_s(double x, SAddr lg) {
     const SAddr a = lg + (unsigned)log2_tab_offset(x) * 8u;
@@ -182,9 +183,15 @@ struct FastLane {
     double y[NL], f[NL], prm[R::NPL];
     int sys, n_acc, n_rej, nfev0;
     unsigned fl;
+    // _diagnose_stiffness bookkeeping (common.py:370-400), in registers: the
+    // running mean of h, the okstp at which the 40-step window closes / at
+    // which `toomch` fires next, and n_rej at the last window close
+    // (jflstp = n_rej - rej_base)
+    double havg;
+    int next_cnt, next_many, rej_base;
 
     // RungeKutta.__init__ (common.py:187-220) from what ens_init left
-    __device__ __forceinline__ void init(const RkDev& P, int idx, double* h0) {
+    __device__ __forceinline__ void init(const RkDev& P, int idx, SAddr h0) {
         sys = idx;
         t = P.t0;
 #pragma unroll
@@ -200,11 +207,11 @@ struct FastLane {
         h_abs = P.first_step > 0.0 ? P.first_step : P.init_h[idx];
         SS& ss = Lane<Tab, R>::stiff_state();
         ss.bits[threadIdx.x] &= Lane<Tab, R>::SB_PEND1 | Lane<Tab, R>::SB_PEND2;
-        ss.hot[threadIdx.x].havg = 0.0;
-        ss.hot[threadIdx.x].next_many = P.stiff_many_steps > 1 ? P.stiff_many_steps - 1 : 1;
-        ss.hot[threadIdx.x].cnt = 20;           // here: the NEXT okstp at which the window closes
-        ss.rej_base[threadIdx.x] = 0;
-        h0[threadIdx.x] = h_abs;
+        havg = 0.0;
+        next_many = P.stiff_many_steps > 1 ? P.stiff_many_steps - 1 : 1;
+        next_cnt = 20;
+        rej_base = 0;
+        sts1(h0, h_abs);
     }
 
     // _reassess_stepsize, common.py:310-331, exact; d = |t_bound - t|.  Returns
@@ -258,7 +265,8 @@ struct FastLane {
     // One attempt of a step; returns the lane status.  `cb`: shared-memory
     // address of the coefficient stream, `h0`: this thread's word of the
     // "h_abs at the start of the step" array.
-    __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa, double* h0) {
+    template <bool STIFF>
+    __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa) {
         const SAddr cb = sa.coef;
         constexpr unsigned HI_N = hi_word_of_small_int(R::N);          // (double)N
         constexpr unsigned HI_TINY = HI_N - (1022u << 20);             // N * 2^-1022
@@ -308,105 +316,111 @@ struct FastLane {
         const bool tiny = sh < HI_TINY;
         const bool rej = (fl & FL_REJ) != 0u;
         const bool second = accept && !(fl & FL_STD);
-        int st = LANE_RUNNING;
-        if (accept) {
-            // f(t+h, y_new) of non-FSAL pairs (common.py:289-291) and the
-            // stiffness bookkeeping (common.py:306) while errv is live
-            if constexpr (!Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
-            if (P.nfev_stiff_detect > 0 && diagnose(P, K, errv, y_new, t_new, h)) st = LANE_FLUSH;
+        // f(t+h, y_new) of non-FSAL pairs, accepted lanes only (common.py:289-291)
+        if constexpr (!Tab::FSAL) {
+            if (accept) R::f(t_new, y_new, prm, K[S]);
         }
+        // ---- controller (common.py:249-287) -----------------------------------
         const double l2 = log2_core_s(ss, sa.lg);
         const double factor = ctl_factor<false>(P, l2, l2_old, 0.0, accept, second, rej, tiny,
                                                 (fl & FL_MF4) ? kMaxFactor : kMaxFactor0,
                                                 Exp2Shared{sa.e2});
-        h_abs *= factor;
-        // common.py:294-303 -- selects, not a branch, so the moves exist once
+        const double h_abs_new = bad ? kMinFactor * fabs(h) : h_abs * factor;   // max(0.2, nan)
+        // Everything below is straight-line code with selects: ONE basic block,
+        // so that the loads, the controller and the bookkeeping overlap, and one
+        // rarely taken branch (`slow`) for the exact forms.
+        // ---- stiffness bookkeeping (common.py:370-400), accepted lanes ---------
+        const int okstp = n_acc + 1;
+        bool probe = false, lotsfl = false;
+        double havg_new = havg;
+        if constexpr (STIFF) {
+            havg_new = c_xsq_havg[0] * havg + c_xsq_havg[1] * h;
+            const bool close = accept && okstp == next_cnt;     // okstp == 20 or okstp % 40 == 39
+            const bool first = okstp == 20;
+            lotsfl = close && !first && (n_rej - rej_base >= 10);
+            if (close && first) havg_new = h;
+            if (close) {
+                rej_base = n_rej;                                // jflstp = 0
+                next_cnt = first ? 39 : next_cnt + 40;
+            }
+            const bool toomch = accept && okstp == next_many;
+            if (toomch) next_many += P.stiff_many_steps;
+            probe = toomch || lotsfl;
+            havg = accept ? havg_new : havg;
+        }
+        // ---- state (common.py:294-303) -----------------------------------------
+        const unsigned fl_acc = (tiny ? FL_STD : 0u) | (fl & FL_MF4) |
+            ((unsigned)__double2hiint(factor) < 0x40100000u ? FL_MF4 : 0u);   // factor < 4
+        fl = accept ? fl_acc : (fl | FL_REJ);
+        n_acc += accept ? 1 : 0;
+        n_rej += accept ? 0 : 1;
         l2_old = accept ? l2 : l2_old;
-        t = accept ? t_new : t;
+        const double t_next = accept ? t_new : t;
+        // ---- what the next attempt needs ---------------------------------------
+        // OdeSolver.step (base.py:207-208): done?  Then the next step's
+        // _reassess_stepsize: nothing to do when  min_step < h_abs < max_step  and
+        // 2 h_abs < |t_bound - t|, each proven on high words; after a rejection
+        // h_abs is "certainly above min_step" by the same bound (min_step <=
+        // max(H_MIN_A (|t| + h0), sqrt(tiny)) and h0 <= span / 2 whenever the step
+        // started on the short path)
+        const double s = t_next - P.t_bound;
+        const bool done = accept && (P.direction * s >= 0.0);
+        const unsigned hh = (unsigned)__double2hiint(h_abs_new);
+        const unsigned dh = (unsigned)__double2hiint(s) & 0x7fffffffu;
+        const bool near_min = hh <= (unsigned)P.fast_hi_min;
+        const bool out_of_range = hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span;
+        const bool near_end = (int)(dh - hh) <= 0x100000;
+        // (bitwise, not short-circuit: no branches)
+        const bool slow_acc = probe | (!done & (out_of_range | near_end));
+        const bool slow_rej = bad | near_min | ((fl & FL_SLOW) != 0u);
+        const bool slow = accept ? slow_acc : slow_rej;
+        int st = done ? LANE_FINISHED : LANE_RUNNING;
+        if (accept & !done) sts1(sa.h0, h_abs_new);
+        if (slow) {
+            if (accept) {
+                if (STIFF && probe) {
+                    if (diagnose_record(P, K, errv, y_new, t_new, h, havg_new, lotsfl)) {
+                        if (st == LANE_RUNNING) st = LANE_FLUSH;
+                    }
+                }
+                if (!done && (out_of_range || near_end)) {
+                    h_abs = h_abs_new;
+                    if (!reassess_exact(P, t_next, fabs(s), h_abs, fl)) st = LANE_TOO_SMALL;
+                    fl |= FL_SLOW;
+                } else {
+                    h_abs = h_abs_new;
+                }
+            } else {
+                h_abs = h_abs_new;
+                if (bad) {                                    // common.py:280-287
+                    st = LANE_OVERFLOW;
+                } else {
+                    const double min_step =
+                        pymax(Tab::H_MIN_A * (fabs(t) + lds1_volatile(sa.h0)), XSQ_SQRT_TINY);
+                    if (h_abs < min_step) st = LANE_TOO_SMALL;               // common.py:234
+                }
+            }
+        } else {
+            h_abs = h_abs_new;
+        }
+        t = t_next;
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
             y[c] = accept ? y_new[c] : y[c];
             f[c] = accept ? K[S][c] : f[c];
         }
-        // "certainly above min_step": min_step <= max(H_MIN_A (|t| + h0), sqrt(tiny))
-        // and h0 <= span / 2 whenever the step started on the short path below
-        const unsigned hh = (unsigned)__double2hiint(h_abs);
-        if (!accept) {
-            fl |= FL_REJ;
-            ++n_rej;
-            if (bad) {                                    // common.py:280-287
-                h_abs = kMinFactor * fabs(h);             // max(0.2, nan) * h_abs
-                st = LANE_OVERFLOW;
-            } else if (hh <= (unsigned)P.fast_hi_min || (fl & FL_SLOW)) {
-                const double min_step =
-                    pymax(Tab::H_MIN_A * (fabs(t) + h0[threadIdx.x]), XSQ_SQRT_TINY);
-                if (h_abs < min_step) st = LANE_TOO_SMALL;               // common.py:234
-            }
-        } else {
-            fl = (tiny ? FL_STD : 0u) | (fl & FL_MF4);
-            if ((unsigned)__double2hiint(factor) < 0x40100000u) fl |= FL_MF4;   // factor < 4
-            ++n_acc;
-            // OdeSolver.step, base.py:207-208, then the next step's
-            // _reassess_stepsize: nothing to do when  min_step < h_abs <
-            // max_step  and  2 h_abs < |t_bound - t|, each proven on high words
-            const double s = t - P.t_bound;
-            if (P.direction * s >= 0.0) {
-                st = LANE_FINISHED;
-            } else {
-                const unsigned dh = (unsigned)__double2hiint(s) & 0x7fffffffu;
-                h0[threadIdx.x] = h_abs;
-                if (hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span ||
-                    (int)(dh - hh) <= 0x100000) {
-                    if (!reassess_exact(P, t, fabs(s), h_abs, fl)) st = LANE_TOO_SMALL;
-                    fl |= FL_SLOW;
-                }
-            }
-        }
         return st;
     }
 
-    // _diagnose_stiffness, common.py:370-516 -- same bookkeeping and the same
-    // probe records as Lane::diagnose (xsq_rk_core.cuh); `cnt` holds the okstp
-    // at which the current window closes instead of a countdown, so the common
-    // case is a load, the running mean of h, two compares and a store.
-    __device__ __forceinline__ bool diagnose(const RkDev& P, double (&K)[S + 1][NL],
-                                             const double (&errv)[NL],
-                                             const double (&y_new)[NL], double t_new, double h) {
+    // The probe of _diagnose_stiffness (common.py:401-516) is deferred exactly as
+    // in the generic kernel (Lane::diagnose): its inputs go to a record of the
+    // probe queue, or -- queue full -- to one of the thread's two slots.  Returns
+    // true when both slots are now taken.
+    __device__ __forceinline__ bool diagnose_record(const RkDev& P, double (&K)[S + 1][NL],
+                                                    const double (&errv)[NL],
+                                                    const double (&y_new)[NL], double t_new,
+                                                    double h, double havg_new, bool lotsfl) {
         SS& ss = Lane<Tab, R>::stiff_state();
-        const double2 hot = *reinterpret_cast<const double2*>(&ss.hot[threadIdx.x]);
-        double havg = c_xsq_havg[0] * hot.x + c_xsq_havg[1] * h;
-        const int next_many = __double2loint(hot.y), next_cnt = __double2hiint(hot.y);
-        const int okstp = n_acc + 1;
-        if (okstp != next_many && okstp != next_cnt) {
-            ss.hot[threadIdx.x].havg = havg;
-            return false;
-        }
-        return diagnose_event(P, K, errv, y_new, t_new, h, havg, next_many, next_cnt);
-    }
-
-    __device__ __forceinline__ bool diagnose_event(const RkDev& P, double (&K)[S + 1][NL],
-                                                const double (&errv)[NL],
-                                                const double (&y_new)[NL], double t_new,
-                                                double h, double havg, int next_many,
-                                                int next_cnt) {
-        SS& ss = Lane<Tab, R>::stiff_state();
-        const int okstp = n_acc + 1;
-        const bool toomch = okstp == next_many;
-        bool lotsfl = false;
-        if (okstp == next_cnt) {                  // okstp == 20 or okstp % 40 == 39
-            if (okstp == 20) {
-                havg = h;
-                next_cnt = 39;
-            } else {
-                lotsfl = n_rej - ss.rej_base[threadIdx.x] >= 10;
-                next_cnt += 40;
-            }
-            ss.rej_base[threadIdx.x] = n_rej;                // jflstp = 0
-        }
-        if (toomch) next_many += P.stiff_many_steps;
-        *reinterpret_cast<double2*>(&ss.hot[threadIdx.x]) =
-            make_double2(havg, __hiloint2double(next_cnt, next_many));
-        if (!(toomch || lotsfl)) return false;
         using SL = StiffSlot<R>;
         double* s = nullptr;
         long long stride = 1;
@@ -427,7 +441,7 @@ struct FastLane {
         }
         s[0] = t_new;
         s[stride] = h;
-        s[2 * stride] = havg;
+        s[2 * stride] = havg_new;
         s[3 * stride] = lotsfl ? 1.0 : 0.0;
         s[4 * stride] = __longlong_as_double((long long)sys);
         s += SL::HEAD * stride;
@@ -459,7 +473,7 @@ struct FastLane {
     }
 };
 
-template <class Tab, class R, int BLOCK>
+template <class Tab, class R, int BLOCK, bool STIFF>
 __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     using FL = FastLane<Tab, R>;
     using LN = Lane<Tab, R>;
@@ -475,9 +489,11 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     sa.coef = saddr_of(fs.coef);
     sa.lg = saddr_of(math_tabs().lg);
     sa.e2 = saddr_of(math_tabs().e2);
+    sa.h0 = saddr_of(&h0[threadIdx.x]);
     keep_in_register(sa.coef);
     keep_in_register(sa.lg);
     keep_in_register(sa.e2);
+    keep_in_register(sa.h0);
     FL L;
     bool live = false, exhausted = false;
     auto flush = [&](long long cur) {
@@ -503,7 +519,7 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
             if (!live && !exhausted) {
                 const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
                 if (idx < P.n_lanes) {
-                    L.init(P, (int)idx, h0);
+                    L.init(P, (int)idx, sa.h0);
                     live = true;
                     int st = LANE_RUNNING;
                     if (P.t0 == P.t_bound) {                 // scipy base.py:197
@@ -532,10 +548,10 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         // ---- attempts, until some lane of the warp ends its trajectory ----
         int st = LANE_RUNNING;
         do {
-            if (live) st = L.attempt(P, sa, h0);
+            if (live) st = L.template attempt<STIFF>(P, sa);
         } while (!__any_sync(full, st != LANE_RUNNING));
         // both probe slots of some thread taken (queue full): run them now
-        if (P.nfev_stiff_detect > 0 && __any_sync(full, LN::probes_urgent())) flush(live ? L.sys : -1);
+        if (STIFF && __any_sync(full, LN::probes_urgent())) flush(live ? L.sys : -1);
         if (st == LANE_FLUSH) st = LANE_RUNNING;
         if (st != LANE_RUNNING) {
             L.store(P, st);
@@ -543,7 +559,7 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         }
         __syncwarp(full);
     }
-    if (P.nfev_stiff_detect > 0) flush(-1);
+    if (STIFF) flush(-1);
 }
 
 // ---- host side -----------------------------------------------------------------
@@ -580,9 +596,9 @@ inline void fast_prepare(RkDev& P) {
     P.fast_hi_span = (int)(hi - lo - 1 > 0 ? hi - lo - 1 : 0);
 }
 
-template <class Tab, class R, int BLOCK, int MINB>
+template <class Tab, class R, int BLOCK, int MINB, bool STIFF>
 __global__ void __launch_bounds__(BLOCK, MINB) rk_fast(const RkDev P) {
-    rk_fast_body<Tab, R, BLOCK>(P);
+    rk_fast_body<Tab, R, BLOCK, STIFF>(P);
 }
 
 }  // namespace xsq

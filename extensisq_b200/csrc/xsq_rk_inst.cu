@@ -59,7 +59,8 @@ static int launch_fast(const RkDev& P0, cudaStream_t st, LaunchInfo* info) {
         }
         RkDev P = P0;
         fast_prepare<Tab>(P);
-        auto kern = rk_fast<Tab, R, BLOCK, MINB>;
+        auto kern = P.nfev_stiff_detect > 0 ? rk_fast<Tab, R, BLOCK, MINB, true>
+                                            : rk_fast<Tab, R, BLOCK, MINB, false>;
         int dev = 0, n_sm = 0, occ = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
         if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)

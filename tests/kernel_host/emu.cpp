@@ -61,7 +61,8 @@ static int run(RkDev P, const MethodInfo& mi, bool want_fast, int* used_fast) {
     if constexpr (Tab::VARIANT == tab::GENERIC && !R::WARP) {
         if (want_fast && fast_eligible<Tab, R>(P)) {
             fast_prepare<Tab>(P);
-            rk_fast_body<Tab, R, 1>(P);
+            if (P.nfev_stiff_detect > 0) rk_fast_body<Tab, R, 1, true>(P);
+            else rk_fast_body<Tab, R, 1, false>(P);
             *used_fast = 1;
         }
     }
