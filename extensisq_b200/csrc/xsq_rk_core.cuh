@@ -81,6 +81,7 @@ struct RkDev {
     CtlConst ctl;
     // rk_fast: high words that bracket "min_step < h_abs < max_step" (xsq_rk_fast.cuh)
     int fast_hi_min, fast_hi_span;
+    int fast_dir_mask;            // 0 for forward integration, 0x80000000 for backward
     const double* t_eval;
     double* y_eval;
     const double* h_forced;

@@ -234,9 +234,9 @@ struct FastLane {
         return !(h_abs < min_step);
     }
 
+    // Stage I with its row of A already in registers.
     template <int I>
-    __device__ __forceinline__ void stage(SAddr cb, double (&K)[S + 1][NL], double h) {
-        const CoefRow<Tab, I> a(cb);
+    __device__ __forceinline__ void stage(const CoefRow<Tab, I>& a, double (&K)[S + 1][NL], double h) {
         double ys[NL];
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
@@ -254,11 +254,30 @@ struct FastLane {
         // the tableau image; t + c_i h is dead code for the built-in ones
         R::f(__dadd_rn(t, __dmul_rn(Tab::cv(I), h)), ys, prm, K[I]);
     }
+    // Stages I..S-1, then y_new = y + h K^T B (common.py:341-351).  The NEXT row
+    // of coefficients is requested before the current stage is computed, so the
+    // shared-memory latency (~30 cycles) hides behind a whole stage instead of
+    // standing at the head of each one.
     template <int I>
-    __device__ __forceinline__ void stages(SAddr cb, double (&K)[S + 1][NL], double h) {
-        if constexpr (I < S) {
-            stage<I>(cb, K, h);
-            stages<I + 1>(cb, K, h);
+    __device__ __forceinline__ void stages(SAddr cb, const CoefRow<Tab, I>& a,
+                                           double (&K)[S + 1][NL], double h,
+                                           double (&y_new)[NL]) {
+        if constexpr (I + 1 < S) {
+            const CoefRow<Tab, I + 1> next(cb);
+            stage<I>(a, K, h);
+            stages<I + 1>(cb, next, K, h, y_new);
+        } else {
+            const CoefRow<Tab, L::ROW_B> b(cb);
+            stage<I>(a, K, h);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                double sb = 0.0;
+                static_for<0, S>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    if constexpr (Tab::b(i) != 0.0) sb = fma(b.template at<i>(), K[i][c], sb);
+                });
+                y_new[c] = fma(h, sb, y[c]);
+            }
         }
     }
 
@@ -274,26 +293,16 @@ struct FastLane {
         double K[S + 1][NL];
 #pragma unroll
         for (int c = 0; c < NL; ++c) K[0][c] = f[c];
-        stages<1>(cb, K, h);
-        // _comp_sol_err, common.py:341-351
         double y_new[NL], errv[NL];
         {
-            const CoefRow<Tab, L::ROW_B> b(cb);
-#pragma unroll
-            for (int c = 0; c < NL; ++c) {
-                double sb = 0.0;
-                static_for<0, S>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    if constexpr (Tab::b(i) != 0.0) sb = fma(b.template at<i>(), K[i][c], sb);
-                });
-                y_new[c] = fma(h, sb, y[c]);
-            }
+            const CoefRow<Tab, 1> a1(cb);
+            stages<1>(cb, a1, K, h, y_new);
         }
         const double t_new = t + h;
-        if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
         double ss = 0.0;
         {
-            const CoefRow<Tab, L::ROW_E> e(cb);
+            const CoefRow<Tab, L::ROW_E> e(cb);      // requested before the FSAL evaluation
+            if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
                 double se = 0.0;
@@ -302,7 +311,9 @@ struct FastLane {
                     if constexpr (Tab::e(i) != 0.0) se = fma(e.template at<i>(), K[i][c], se);
                 });
                 errv[c] = h * se;
-                const double big = fabs(y_new[c]) > fabs(y[c]) ? y_new[c] : y[c];
+                // max(|y|, |y_new|): magnitudes order like their bit patterns (integer
+                // compare, off the fp64 pipe); |.| is a free modifier of the fma
+                const double big = (dbits(y_new[c]) << 1) > (dbits(y[c]) << 1) ? y_new[c] : y[c];
                 const double scale = fma(P.rtol, fabs(big), P.atol[c]);
                 const double q = errv[c] * rcp_scale(scale);
                 ss = fma(q, q, ss);
@@ -325,7 +336,7 @@ struct FastLane {
         const double factor = ctl_factor<false>(P, l2, l2_old, 0.0, accept, second, rej, tiny,
                                                 (fl & FL_MF4) ? kMaxFactor : kMaxFactor0,
                                                 Exp2Shared{sa.e2});
-        const double h_abs_new = bad ? kMinFactor * fabs(h) : h_abs * factor;   // max(0.2, nan)
+        const double h_abs_new = h_abs * factor;
         // Everything below is straight-line code with selects: ONE basic block,
         // so that the loads, the controller and the bookkeeping overlap, and one
         // rarely taken branch (`slow`) for the exact forms.
@@ -364,9 +375,11 @@ struct FastLane {
         // max(H_MIN_A (|t| + h0), sqrt(tiny)) and h0 <= span / 2 whenever the step
         // started on the short path)
         const double s = t_next - P.t_bound;
-        const bool done = accept && (P.direction * s >= 0.0);
         const unsigned hh = (unsigned)__double2hiint(h_abs_new);
         const unsigned dh = (unsigned)__double2hiint(s) & 0x7fffffffu;
+        // direction * s >= 0 (s is finite): s == 0, or s has the sign of direction
+        const bool done = accept & (((dh | (unsigned)__double2loint(s)) == 0u) |
+                                    ((int)((unsigned)__double2hiint(s) ^ (unsigned)P.fast_dir_mask) >= 0));
         const bool near_min = hh <= (unsigned)P.fast_hi_min;
         const bool out_of_range = hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span;
         const bool near_end = (int)(dh - hh) <= 0x100000;
@@ -393,6 +406,7 @@ struct FastLane {
             } else {
                 h_abs = h_abs_new;
                 if (bad) {                                    // common.py:280-287
+                    h_abs = kMinFactor * fabs(h);             // max(0.2, nan) * h_abs
                     st = LANE_OVERFLOW;
                 } else {
                     const double min_step =
@@ -594,6 +608,7 @@ inline void fast_prepare(RkDev& P) {
     const long long lo = hi_word(M), hi = hi_word(P.max_step);
     P.fast_hi_min = (int)lo;
     P.fast_hi_span = (int)(hi - lo - 1 > 0 ? hi - lo - 1 : 0);
+    P.fast_dir_mask = P.direction < 0.0 ? (int)0x80000000u : 0;
 }
 
 template <class Tab, class R, int BLOCK, int MINB, bool STIFF>

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd /root/repo
+L=gpurun_out/r02d.log
+: > $L
+step() { echo "=== $1" >> $L; shift; timeout "$@" >> $L 2>&1; echo "rc=$?" >> $L; }
+step "fast tests" 300 python -m pytest tests/test_gpu_fast.py -x -q --timeout 120
+for mb in 5 4 6; do
+  step "bench Ts5 minb=$mb" 200 env XSQ_FAST_MINB=$mb tools/quick_bench.sh ts5_minb$mb --steps 3 --warmup 3 --no-extras --no-cpu
+done
+step "bench Ts5 nostiff" 200 tools/quick_bench.sh ts5_nostiff --steps 3 --warmup 3 --no-extras --no-cpu --stiff 0
+step "bench CK5" 200 tools/quick_bench.sh ck5 --steps 3 --warmup 3 --no-extras --no-cpu --method CK5
+step "exact tests" 600 python -m pytest tests/test_gpu_exact.py -q -x --timeout 240
+BENCH="python bench.py --lanes 1250000 --t-end 100 --steps 1 --warmup 3 --no-cpu --no-extras"
+step "ncu" 420 ncu --set full --clock-control none --import-source on -k regex:rk_fast -s 3 -c 1 -f -o gpurun_out/prof_r02d $BENCH
+grep -E "^===|rc=|passed|failed|steps/s|Error|error" $L | tail -40
