@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxsq.so")
+# XSQ_LIB: another build of the same library (kernel experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("XSQ_LIB") or os.path.join(_HERE, "libxsq.so")
 
 XSQ_MAX_STAGES = 18
 XSQ_MAX_POLY = 8

@@ -69,21 +69,17 @@ template <bool EXTRA, class E2>
 XSQ_MATH_FN double ctl_factor_arith(const CtlConst& C, double l2, double l2_old, double z_extra,
                                     bool accept, bool second, bool rej, bool tiny,
                                     double max_factor, E2 e2) {
-    // one chain for both branches: the standard one has a2 = 0 (l2_old finite)
-    const double a1 = second ? C.a1c : C.a1s;
-    const double a0 = second ? C.a0c : C.a0s;
-    double z = fma(a1, l2, second ? fma(C.a2c, l2_old, a0) : a0);
-    if (EXTRA) z += second ? z_extra : 0.0;
-    const double raw = e2(z);
-    // raw > 0 and finite: doubles of one sign order like their bit patterns, so
-    // the clamps are integer compares (not on the fp64 pipe)
+    const double z_std = fma(C.a1s, l2, C.a0s);
+    double z_sc = fma(C.a1c, l2, fma(C.a2c, l2_old, C.a0c));
+    if (EXTRA) z_sc += z_extra;
+    const double raw = e2(second ? z_sc : z_std);
     // max(min_factor, .) on rejection and in the second order branch only
     double factor = raw;
-    if ((!accept || second) && !(dbits(raw) > dbits(0.2))) factor = 0.2;
+    if ((!accept || second) && !(raw > 0.2)) factor = 0.2;
     // min(max_factor, .) in the second order branch; min(1, .) after a rejection
     const double hi = (accept && rej) ? 1.0
                     : (second ? max_factor : __hiloint2double(0x7ff00000, 0));
-    if (!(dbits(factor) < dbits(hi))) factor = hi;
+    if (!(factor < hi)) factor = hi;
     if (accept && tiny) factor = rej ? 1.0 : max_factor;
     return factor;
 }

@@ -36,6 +36,14 @@
 #include <cstring>
 #include "xsq_rk_core.cuh"
 
+// build-time variants (measured on B200)
+#ifndef XSQ_V_PREFETCH
+#define XSQ_V_PREFETCH 0     // request the next coefficient row one stage ahead
+#endif
+#ifndef XSQ_V_INTDONE
+#define XSQ_V_INTDONE 0      // "t reached t_bound" by sign bits instead of DMUL + DSETP
+#endif
+
 namespace xsq {
 
 // compile-time loop: f(IC<B>{}), ..., f(IC<E-1>{})
@@ -78,6 +86,11 @@ struct CoefLayout {
         for (int jj = 0; jj < j; ++jj) k += value(row, jj) != 0.0 ? 1 : 0;
         return k;
     }
+    XSQ_HD static constexpr int nnz_range(int r0, int r1) {
+        int n = 0;
+        for (int r = r0; r < r1; ++r) n += nnz(r);
+        return n;
+    }
     static constexpr int TOTAL = base(NROWS);
 };
 
@@ -86,26 +99,48 @@ struct FastShared {
     double coef[CoefLayout<Tab>::TOTAL + 2];
 };
 
+// The loop's constants other than the tableau, one copy per CTA in shared
+// memory (filled from the kernel parameters): read with LDS into vector
+// registers where they are used, which keeps them out of the uniform registers.
+struct LoopConsts {
+    double lg_pol[6];        // log2 polynomial        (xsq_math_tables_gen.cuh)
+    double e2_pol[6];        // exp2 polynomial, padded
+    double ctl[6];           // a1s, a0s, a1c, a2c, a0c, pad (CtlConst)
+    double havg[2];          // 0.9, 0.1               (common.py:372)
+    double atol[16];
+};
+
 // 32-bit shared-memory addresses, formed once per thread and kept opaque so
 // that they stay in registers (re-deriving one costs three instructions)
 struct SmemAddr {
     SAddr coef, lg, e2;
     SAddr h0;      // this thread's "h_abs at the start of the step" word
+    SAddr lc;      // LoopConsts
 };
-__device__ __forceinline__ double log2_core_s(double x, SAddr lg) {
+template <int N, int OFF_DOUBLES>
+__device__ __forceinline__ void lc_load(SAddr lc, double (&v)[N]) {
+    static_for<0, N / 2>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        lds2_stream<(OFF_DOUBLES + 2 * q) * 8>(lc, v[2 * q], v[2 * q + 1]);
+    });
+    if constexpr (N & 1) lds1_stream<(OFF_DOUBLES + N - 1) * 8>(lc, v[N - 1]);
+}
+__device__ __forceinline__ double log2_core_s(double x, SAddr lg, SAddr lc) {
     const SAddr a = lg + (unsigned)log2_tab_offset(x) * 8u;
-    double inv, l_hi, l_lo;
+    double inv, l_hi, l_lo, pol[6];
     lds2(a, inv, l_hi);
     lds1_at<16>(a, l_lo);
-    return log2_arith(x, inv, l_hi, l_lo, c_xsq_lg_pol);
+    lc_load<6, 0>(lc, pol);
+    return log2_arith(x, inv, l_hi, l_lo, pol);
 }
 struct Exp2Shared {
-    SAddr e2;
+    SAddr e2, lc;
     __device__ __forceinline__ double operator()(double z) const {
         const Exp2Split s = exp2_split(z);
-        double t_hi, t_lo;
+        double t_hi, t_lo, pol[6];
         lds2(e2 + ((unsigned)(s.N & 63) << 4), t_hi, t_lo);
-        return exp2_arith(s, t_hi, t_lo, c_xsq_e2_pol);
+        lc_load<6, 6>(lc, pol);
+        return exp2_arith(s, t_hi, t_lo, pol);
     }
 };
 
@@ -119,8 +154,42 @@ __device__ __forceinline__ void coef_ld1(SAddr base, double& a) {
     lds1_stream<OFF * 8>(base, a);
 }
 
+// Where a pair's coefficients are taken from.  An fp64 instruction costs
+// max(2, distinct source REGISTERS) issue cycles (a 64-bit operand reads an
+// even and an odd register, the file delivers one of each per cycle; measured:
+// tools/sass_cost.py reproduces the kernel time within 4 %), so
+//   acc = fma(coef, K, acc)   is 3 cycles with the coefficient in a register,
+//                                2 cycles with it in a UNIFORM register.
+// About 36 uniform doubles fit before ptxas starts to spill them through vector
+// registers (measured with a 24..44-constant test kernel): a pair whose A, B, E
+// nonzeros fit -- Ts5, CK5, Me4 -- reads them straight from the constant bank
+// (hoisted into uniform registers once, no load in the loop), and the loop's
+// other constants make room by living in shared memory (LoopConsts).  Larger
+// pairs stream their rows from shared memory into registers, two per LDS.128.
+template <class Tab>
+struct CoefMode {
+    using L = CoefLayout<Tab>;
+    static constexpr int NNZ_ALL = L::nnz_range(1, L::ROW_C);
+    static constexpr bool UNIFORM = NNZ_ALL <= 30;
+};
+
+template <class Tab, int ROW, bool UNIFORM = CoefMode<Tab>::UNIFORM>
+struct CoefRow;
+
 template <class Tab, int ROW>
-struct CoefRow {
+struct CoefRow<Tab, ROW, true> {
+    using L = CoefLayout<Tab>;
+    __device__ __forceinline__ explicit CoefRow(SAddr) {}
+    template <int J>
+    __device__ __forceinline__ double at() const {
+        if constexpr (ROW < L::S) return Tab::av(ROW, J);
+        else if constexpr (ROW == L::ROW_B) return Tab::bv(J);
+        else return Tab::ev(J);
+    }
+};
+
+template <class Tab, int ROW>
+struct CoefRow<Tab, ROW, false> {
     using L = CoefLayout<Tab>;
     static constexpr int NNZ = L::nnz(ROW);
     static constexpr int BASE = L::base(ROW);
@@ -263,12 +332,22 @@ struct FastLane {
                                            double (&K)[S + 1][NL], double h,
                                            double (&y_new)[NL]) {
         if constexpr (I + 1 < S) {
+#if XSQ_V_PREFETCH
             const CoefRow<Tab, I + 1> next(cb);
             stage<I>(a, K, h);
+#else
+            stage<I>(a, K, h);
+            const CoefRow<Tab, I + 1> next(cb);
+#endif
             stages<I + 1>(cb, next, K, h, y_new);
         } else {
+#if XSQ_V_PREFETCH
             const CoefRow<Tab, L::ROW_B> b(cb);
             stage<I>(a, K, h);
+#else
+            stage<I>(a, K, h);
+            const CoefRow<Tab, L::ROW_B> b(cb);
+#endif
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
                 double sb = 0.0;
@@ -300,9 +379,16 @@ struct FastLane {
         }
         const double t_new = t + h;
         double ss = 0.0;
+        double atol[NL];
+        lc_load<NL, 20>(sa.lc, atol);
         {
+#if XSQ_V_PREFETCH
             const CoefRow<Tab, L::ROW_E> e(cb);      // requested before the FSAL evaluation
             if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+#else
+            if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+            const CoefRow<Tab, L::ROW_E> e(cb);
+#endif
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
                 double se = 0.0;
@@ -311,10 +397,9 @@ struct FastLane {
                     if constexpr (Tab::e(i) != 0.0) se = fma(e.template at<i>(), K[i][c], se);
                 });
                 errv[c] = h * se;
-                // max(|y|, |y_new|): magnitudes order like their bit patterns (integer
-                // compare, off the fp64 pipe); |.| is a free modifier of the fma
-                const double big = (dbits(y_new[c]) << 1) > (dbits(y[c]) << 1) ? y_new[c] : y[c];
-                const double scale = fma(P.rtol, fabs(big), P.atol[c]);
+                // max(|y|, |y_new|): pick the operand, |.| is a free modifier of the fma
+                const double big = fabs(y_new[c]) > fabs(y[c]) ? y_new[c] : y[c];
+                const double scale = fma(P.rtol, fabs(big), atol[c]);
                 const double q = errv[c] * rcp_scale(scale);
                 ss = fma(q, q, ss);
             }
@@ -332,10 +417,13 @@ struct FastLane {
             if (accept) R::f(t_new, y_new, prm, K[S]);
         }
         // ---- controller (common.py:249-287) -----------------------------------
-        const double l2 = log2_core_s(ss, sa.lg);
-        const double factor = ctl_factor<false>(P, l2, l2_old, 0.0, accept, second, rej, tiny,
-                                                (fl & FL_MF4) ? kMaxFactor : kMaxFactor0,
-                                                Exp2Shared{sa.e2});
+        const double l2 = log2_core_s(ss, sa.lg, sa.lc);
+        double cc[6];
+        lc_load<6, 12>(sa.lc, cc);
+        const CtlConst C{cc[0], cc[1], cc[2], cc[3], cc[4]};
+        const double factor = ctl_factor_arith<false>(C, l2, l2_old, 0.0, accept, second, rej, tiny,
+                                                      (fl & FL_MF4) ? kMaxFactor : kMaxFactor0,
+                                                      Exp2Shared{sa.e2, sa.lc});
         const double h_abs_new = h_abs * factor;
         // Everything below is straight-line code with selects: ONE basic block,
         // so that the loads, the controller and the bookkeeping overlap, and one
@@ -345,7 +433,9 @@ struct FastLane {
         bool probe = false, lotsfl = false;
         double havg_new = havg;
         if constexpr (STIFF) {
-            havg_new = c_xsq_havg[0] * havg + c_xsq_havg[1] * h;
+            double hc[2];
+            lc_load<2, 18>(sa.lc, hc);
+            havg_new = hc[0] * havg + hc[1] * h;
             const bool close = accept && okstp == next_cnt;     // okstp == 20 or okstp % 40 == 39
             const bool first = okstp == 20;
             lotsfl = close && !first && (n_rej - rej_base >= 10);
@@ -377,9 +467,13 @@ struct FastLane {
         const double s = t_next - P.t_bound;
         const unsigned hh = (unsigned)__double2hiint(h_abs_new);
         const unsigned dh = (unsigned)__double2hiint(s) & 0x7fffffffu;
+#if XSQ_V_INTDONE
         // direction * s >= 0 (s is finite): s == 0, or s has the sign of direction
         const bool done = accept & (((dh | (unsigned)__double2loint(s)) == 0u) |
                                     ((int)((unsigned)__double2hiint(s) ^ (unsigned)P.fast_dir_mask) >= 0));
+#else
+        const bool done = accept & (P.direction * s >= 0.0);
+#endif
         const bool near_min = hh <= (unsigned)P.fast_hi_min;
         const bool out_of_range = hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span;
         const bool near_end = (int)(dh - hh) <= 0x100000;
@@ -493,10 +587,22 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     using LN = Lane<Tab, R>;
     __shared__ __align__(16) FastShared<Tab> fs;
     __shared__ double h0[BLOCK];
+    __shared__ __align__(16) LoopConsts lcs;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     math_tabs_init();
-    if (threadIdx.x == 0) coef_fill_row<Tab, 1>(fs.coef);
+    if (threadIdx.x == 0) {
+        coef_fill_row<Tab, 1>(fs.coef);
+        for (int i = 0; i < 6; ++i) {
+            lcs.lg_pol[i] = c_xsq_lg_pol[i];
+            lcs.e2_pol[i] = c_xsq_e2_pol[i];
+        }
+        lcs.ctl[0] = P.ctl.a1s; lcs.ctl[1] = P.ctl.a0s; lcs.ctl[2] = P.ctl.a1c;
+        lcs.ctl[3] = P.ctl.a2c; lcs.ctl[4] = P.ctl.a0c; lcs.ctl[5] = 0.0;
+        lcs.havg[0] = c_xsq_havg[0]; lcs.havg[1] = c_xsq_havg[1];
+        for (int i = 0; i < 16; ++i) lcs.atol[i] = P.atol[i];
+        memory_fence_for(&lcs);
+    }
     LN::stiff_state().bits[threadIdx.x] = 0u;
     __syncthreads();
     SmemAddr sa;
@@ -504,6 +610,8 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     sa.lg = saddr_of(math_tabs().lg);
     sa.e2 = saddr_of(math_tabs().e2);
     sa.h0 = saddr_of(&h0[threadIdx.x]);
+    sa.lc = saddr_of(&lcs);
+    keep_in_register(sa.lc);
     keep_in_register(sa.coef);
     keep_in_register(sa.lg);
     keep_in_register(sa.e2);
