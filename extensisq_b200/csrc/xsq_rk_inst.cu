@@ -32,15 +32,16 @@ struct Geometry {
         KDOUBLES <= 21 ? 4 : (KDOUBLES <= 36 ? 3 : 2);
 };
 
-// CTAs per SM of the fast kernel.  It is bound by the fp64 pipe, and what keeps
-// the pipe busy is the number of warps per scheduler: one more CTA per SM than
-// the generic kernel (96 instead of 128 registers for a 6-stage pair on a
-// 3-component system, no spills inside the loop) measured faster; XSQ_FAST_MINB
-// overrides it (profiling).
+// CTAs per SM of the fast kernel: the same as the generic kernel's.  One or two
+// more CTAs per SM (96 / 80 registers) were measured on B200 and are slower
+// (Ts5/Lorenz: 0.543 / 0.536 / 0.514 of the fp64 peak at 4 / 5 / 6 CTAs): the
+// kernel is bound by instruction issue, not by latency, so more warps do not
+// help and the tighter register budget costs moves.  XSQ_FAST_MINB=<n>
+// selects the neighbours for profiling.
 template <class Tab, class R>
 struct FastGeometry {
     static constexpr int BASE = Geometry<Tab, R>::MINB;
-    static constexpr int MINB = BASE + 1;
+    static constexpr int MINB = BASE;
 };
 
 template <class Tab, class R, int MINB = FastGeometry<Tab, R>::MINB>
@@ -53,7 +54,7 @@ static int launch_fast(const RkDev& P0, cudaStream_t st, LaunchInfo* info) {
             if (const char* e = getenv("XSQ_FAST_MINB")) {
                 const int want = atoi(e);
                 constexpr int B = FastGeometry<Tab, R>::BASE;
-                if (want == B) return launch_fast<Tab, R, B>(P0, st, info);
+                if (want == B + 1) return launch_fast<Tab, R, B + 1>(P0, st, info);
                 if (want == B + 2) return launch_fast<Tab, R, B + 2>(P0, st, info);
             }
         }

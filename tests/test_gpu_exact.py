@@ -171,10 +171,16 @@ def test_c2_bench_ensemble_t100_exact_and_distribution():
         r = oracle("lorenz63", (0.0, bench.T_END), y0, m, prm, device_math=False, **kw)
         da = g["n_accepted"].mean() / r["n_accepted"].mean() - 1
         dr = g["n_rejected"].mean() / r["n_rejected"].mean() - 1
+        # at T = 100 the two arithmetics follow different (equally valid) chaotic
+        # trajectories, so the lane means are independent samples: their
+        # difference has standard error sqrt((var_g + var_r) / N)
+        se_a = np.sqrt((g["n_accepted"].var() + r["n_accepted"].var()) / N) / r["n_accepted"].mean()
+        se_r = np.sqrt((g["n_rejected"].var() + r["n_rejected"].var()) / N) / r["n_rejected"].mean()
         print(f"\nC2 {m.__name__} T=100, {N} lanes: accepted/lane {g['n_accepted'].mean():.2f} "
-              f"(reference arithmetic {r['n_accepted'].mean():.2f}, {da:+.2e}), rejected/lane "
-              f"{g['n_rejected'].mean():.2f} ({r['n_rejected'].mean():.2f}, {dr:+.2e})")
-        assert abs(da) < 1e-3 and abs(dr) < 1e-3
+              f"(reference arithmetic {r['n_accepted'].mean():.2f}, {da:+.2e}, s.e. {se_a:.1e}), "
+              f"rejected/lane {g['n_rejected'].mean():.2f} ({r['n_rejected'].mean():.2f}, "
+              f"{dr:+.2e}, s.e. {se_r:.1e})")
+        assert abs(da) < max(1e-3, 4 * se_a) and abs(dr) < max(1e-3, 4 * se_r)
 
 
 def test_cost_of_device_arithmetic_vs_numpy_restatement():
