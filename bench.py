@@ -654,8 +654,10 @@ def main():
         sampler.start()
     sampler.mark()
     lib.xsq_launch_count(1)
+    lib.xsq_profile_enable(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
+    main_ms = []                        # the persistent kernel alone, per step
     barrier()
     t_wall0 = time.perf_counter()
     for s0, s1 in ev:
@@ -663,12 +665,20 @@ def main():
         s0.record(stream)
         solve_resident()
         s1.record(stream)
+        a_, b_, c_ = C.c_double(), C.c_double(), C.c_double()
+        if lib.xsq_profile_last(C.byref(a_), C.byref(b_), C.byref(c_)) == 0:
+            main_ms.append((a_.value, b_.value, c_.value))
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    lib.xsq_profile_enable(0)
     launches = int(lib.xsq_launch_count(0))
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     my_ms = float(sum(kern_ms))
     clocks = sampler.stop() if rank == 0 else None
+    # the fp64 peak, measured next to the timed region (same clocks, same thermal state)
+    peak = C.c_double()
+    if rank == 0:
+        _lib.check(lib.xsq_fp64_peak(local, 2000, C.byref(peak)))
 
     # ---- timed region 2: end to end through the public API, host buffers ---
     for _ in range(1):
@@ -710,10 +720,10 @@ def main():
         # roofline of the dominant kernel, this rank
         att_f, acc_f = flops_per_attempt_and_accept(method, 3, 8)
         flops_launch = (acc_total + rej_total) * att_f + acc_total * acc_f
-        ms_launch = float(np.mean(kern_ms))
+        ms_step = float(np.mean(kern_ms))
+        ms_launch = float(np.mean([m[1] for m in main_ms])) if main_ms else ms_step
         achieved = flops_launch / (ms_launch * 1e-3) / 1e12
-        peak = C.c_double()
-        _lib.check(lib.xsq_fp64_peak(local, 2000, C.byref(peak)))
+        achieved_step = flops_launch / (ms_step * 1e-3) / 1e12
         hbm, _ = hbm_peak()
         kern = "rk_fast" if os.environ.get("XSQ_NO_FAST") != "1" else "rk_persistent"
         tkey = f"{kern}_{args.method}_lorenz_{N}_T{args.t_end:g}_stiff{args.stiff}"
@@ -735,6 +745,13 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value,
+                "kernel_ms": ms_launch,
+                "frac_over_whole_step": achieved_step / peak.value,
+                "step_ms": ms_step,
+                "kernels_of_a_step_ms": ({"ens_init": float(np.mean([m[0] for m in main_ms])),
+                                          "persistent": ms_launch,
+                                          "stiff_queue": float(np.mean([m[2] for m in main_ms]))}
+                                         if main_ms else None),
                 "traffic": traffic, "traffic_source": tnote,
                 "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + "
                                 "dram__bytes_write.sum, profiles/traffic.json)",

@@ -40,7 +40,7 @@ EXPORTS = [
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
     "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
-    "xsq_launch_count", "xsq_trim_memory",
+    "xsq_launch_count", "xsq_trim_memory", "xsq_profile_enable", "xsq_profile_last",
     "xsq_fp64_peak",
 ]
 
@@ -174,6 +174,8 @@ def load():
                                         C.c_void_p]
     lib.xsq_launch_count.restype = C.c_int64
     lib.xsq_trim_memory.argtypes = [C.c_int]
+    lib.xsq_profile_enable.argtypes = [C.c_int]
+    lib.xsq_profile_last.argtypes = [_dp, _dp, _dp]
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]
     if lib.xsq_abi_version() != 2:

@@ -106,18 +106,40 @@ static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
 }
 
 // init kernel -> persistent kernel -> (stiffness diagnosis on) probe queue kernel
+// Optional device timing of the three kernels of a solve (xsq_profile_enable):
+// CUDA events on the launching stream around ens_init / the persistent kernel /
+// stiff_queue.  Used by bench.py for the roofline of the dominant kernel.
+static std::atomic<int> g_profile{0};
+static cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static bool g_prof_valid = false;
+static void prof_mark(int i, cudaStream_t st) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    if (!g_prof_ev[i]) cudaEventCreate(&g_prof_ev[i]);
+    cudaEventRecord(g_prof_ev[i], st);
+    if (i == 3) g_prof_valid = true;
+}
+
 static int dispatch(int method, int rhs, int events, const RkDev& P, const MethodInfo& mi,
                     cudaStream_t st, LaunchInfo* info) {
     // user right-hand sides and event functions are device code compiled at
     // run time into their own kernel
     if (rhs >= XSQ_RHS_USER_BASE || events != 0)
         return user_rk_launch(method, rhs, events, P, mi.s, mi.stbrad, mi.tanang, st);
+    prof_mark(0, st);
     int rc = launch_ens_init(rhs, P, st);       // f0 + h_start for all lanes
     if (rc != XSQ_OK) return rc;
-    if (method == XSQ_METHOD_SWAG) return launch_swag(rhs, P, st);
+    prof_mark(1, st);
+    if (method == XSQ_METHOD_SWAG) {
+        rc = launch_swag(rhs, P, st);
+        prof_mark(2, st);
+        prof_mark(3, st);
+        return rc;
+    }
     rc = launch_method(method, rhs, P, st, info);
+    prof_mark(2, st);
     if (rc == XSQ_OK && P.stiff_q_cap > 0)
         rc = launch_stiff_queue(rhs, P, mi.s, mi.stbrad, mi.tanang, st);
+    prof_mark(3, st);
     return rc;
 }
 
@@ -437,6 +459,25 @@ int xsq_trim_memory(int device) {
     cudaMemPool_t pool;
     XSQ_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     XSQ_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return XSQ_OK;
+}
+
+int xsq_profile_enable(int on) {
+    g_profile.store(on ? 1 : 0);
+    if (!on) g_prof_valid = false;
+    return XSQ_OK;
+}
+
+int xsq_profile_last(double* ms_init, double* ms_main, double* ms_probe) {
+    if (!g_prof_valid) { g_detail = "no profiled solve"; return XSQ_ERR_ARG; }
+    XSQ_CUDA(cudaEventSynchronize(g_prof_ev[3]));
+    float a = 0, b = 0, c = 0;
+    XSQ_CUDA(cudaEventElapsedTime(&a, g_prof_ev[0], g_prof_ev[1]));
+    XSQ_CUDA(cudaEventElapsedTime(&b, g_prof_ev[1], g_prof_ev[2]));
+    XSQ_CUDA(cudaEventElapsedTime(&c, g_prof_ev[2], g_prof_ev[3]));
+    if (ms_init) *ms_init = a;
+    if (ms_main) *ms_main = b;
+    if (ms_probe) *ms_probe = c;
     return XSQ_OK;
 }
 

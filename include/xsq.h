@@ -320,6 +320,14 @@ int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_s
  * of it to the driver (synchronises the device). */
 int xsq_trim_memory(int device);
 
+/* Device timing of the kernels of the LAST xsq_rk_solve / xsq_swag_solve issued
+ * after xsq_profile_enable(1): CUDA events on the launching stream around the
+ * init pass, the persistent kernel and the probe-queue kernel (milliseconds;
+ * synchronises with the end of that solve).  For benchmarks: the roofline of
+ * the dominant kernel is quoted on ITS duration. */
+int xsq_profile_enable(int on);
+int xsq_profile_last(double* ms_init, double* ms_main, double* ms_probe);
+
 /* Kernel-launch bookkeeping for benchmarks: number of kernels this library
  * launched since the last reset. */
 int64_t xsq_launch_count(int reset);
