@@ -54,23 +54,9 @@ using namespace rkc;
 // then wait for the same message from them.  Flags live in the RECEIVER's
 // memory (remote store, local spin).  The spin is bounded: on timeout an
 // error word is set and the host aborts the solve instead of hanging the GPU.
-__global__ void k_peer_sync(long long seq, volatile long long* up_flag_remote,
-                            volatile long long* dn_flag_remote,
-                            volatile long long* my_flags, long long* err) {
-    __threadfence_system();
-    if (up_flag_remote) *up_flag_remote = seq;     // my "from_down" slot at the upper rank
-    if (dn_flag_remote) *dn_flag_remote = seq;     // my "from_up" slot at the lower rank
-    __threadfence_system();
-    const long long t0 = clock64();
-    const long long budget = 4000000000LL;         // ~2 s
-    bool ok = true;
-    if (up_flag_remote)
-        while (my_flags[0] < seq) if (clock64() - t0 > budget) { ok = false; break; }
-    if (dn_flag_remote && ok)
-        while (my_flags[1] < seq) if (clock64() - t0 > budget) { ok = false; break; }
-    if (!ok) *err = seq;
-    __threadfence_system();
-}
+// the neighbour barrier on its own (end of a solve): a one-CTA grid is both the
+// first and the last block row, so it posts and waits for both neighbours
+__global__ void k_peer_barrier(PeerSync ps) { peer_handshake(ps); }
 
 // out = a + s * b      (first stage, sommeijer.py:289; step-size probe :152)
 __global__ void __launch_bounds__(TX* TY) k_axpy(Slab S, const double* __restrict__ a,
@@ -219,6 +205,7 @@ struct Ctx {
     const double* peer_up = nullptr;   // IPC mapping of the upper rank's storage
     const double* peer_dn = nullptr;
     int rows_up = 0;                   // interior rows of the upper rank's slab
+    PeerSync ps = {0, nullptr, nullptr, nullptr};   // barrier carried by the next stencil kernel
     long long* flags = nullptr;        // [0] from upper rank, [1] from lower, [2] error
     long long* up_flag_remote = nullptr;   // upper rank's flags[1]
     long long* dn_flag_remote = nullptr;   // lower rank's flags[0]
@@ -239,9 +226,8 @@ struct Ctx {
         const size_t off = (size_t)(u - base);
         if (peer_up) up_row = peer_up + off + nx * rows_up;   // its last interior row
         if (peer_dn) dn_row = peer_dn + off + nx;             // its first interior row
-        ++seq;
-        k_peer_sync<<<1, 1, 0, st>>>(seq, up_flag_remote, dn_flag_remote, flags, flags + 2);
-        launched();
+        ++seq;                 // the next stencil kernel carries the barrier (peer_handshake)
+        ps = PeerSync{seq, up_flag_remote, dn_flag_remote, flags};
     }
 
     // global sum of this rank's block partials: deterministic on every rank
@@ -276,10 +262,10 @@ struct Ctx {
     double t_eval_arg = 0.0;                     // time argument of the next eval()
     void launch_eval(const double* u, double t, double* dy) {
         if (pl.user_fn[0]) {
-            void* args[] = {&S, &u, &up_row, &dn_row, &t, &dy};
+            void* args[] = {&S, &ps, &u, &up_row, &dn_row, &t, &dy};
             if (user_launch(pl.user_fn[0], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde eval");
         } else {
-            k_eval<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, u, up_row, dn_row, t, dy);
+            k_eval<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, ps, u, up_row, dn_row, t, dy);
         }
         launched();
     }
@@ -287,10 +273,10 @@ struct Ctx {
                       double* yj, double t, double mu, double nu, double c3, double hmus,
                       double ajm1) {
         if (pl.user_fn[1]) {
-            void* args[] = {&S, &yjm1, &up_row, &dn_row, &yjm2, &yn, &fn, &yj, &t, &mu, &nu, &c3, &hmus, &ajm1};
+            void* args[] = {&S, &ps, &yjm1, &up_row, &dn_row, &yjm2, &yn, &fn, &yj, &t, &mu, &nu, &c3, &hmus, &ajm1};
             if (user_launch(pl.user_fn[1], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde stage");
         } else {
-            k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, yjm1, up_row, dn_row, yjm2, yn, fn,
+            k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, ps, yjm1, up_row, dn_row, yjm2, yn, fn,
                                                                 yj, t, mu, nu, c3, hmus, ajm1);
         }
         launched();
@@ -299,10 +285,10 @@ struct Ctx {
                       double h, double rtol, double atol) {
         double* part = partial;
         if (pl.user_fn[2]) {
-            void* args[] = {&S, &y, &up_row, &dn_row, &yn, &fn, &f1, &t, &h, &rtol, &atol, &part};
+            void* args[] = {&S, &ps, &y, &up_row, &dn_row, &yn, &fn, &f1, &t, &h, &rtol, &atol, &part};
             if (user_launch(pl.user_fn[2], grid.x, grid.y, block.x, block.y, args, st) != 0) fail("user pde final");
         } else {
-            k_final<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, y, up_row, dn_row, yn, fn, f1, t, h,
+            k_final<pde::Heat2dReaction><<<grid, block, 0, st>>>(S, ps, y, up_row, dn_row, yn, fn, f1, t, h,
                                                                 rtol, atol, part);
         }
         launched();
@@ -717,6 +703,8 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     R->kernel_launches = C.launches;
     if (multi) {              // nobody frees storage a neighbour may still read
         C.halo(yn);
+        k_peer_barrier<<<dim3(1, 1), dim3(1, 1), 0, st>>>(C.ps);
+        C.launched();
         cudaStreamSynchronize(st);
     }
     release();
@@ -743,16 +731,16 @@ int rkc_stage_bench(int nx, int rows, int reps, double* ms_per_stage, cudaStream
     cudaEventCreate(&e1);
     for (int w = 0; w < 3; ++w) {
         k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(
-            S, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2], yn, fn, v[0], 0.0, 1.9, -0.95,
-            0.05, 1e-9, 0.3);
+            S, PeerSync{0, nullptr, nullptr, nullptr}, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2],
+            yn, fn, v[0], 0.0, 1.9, -0.95, 0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e0, st);
     for (int r = 0; r < reps; ++r) {
         const double* in = v[(r + 1) % 3];
         k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(
-            S, in, in, in + (size_t)nx * (rows + 1), v[(r + 2) % 3], yn, fn, v[r % 3], 0.0, 1.9,
-            -0.95, 0.05, 1e-9, 0.3);
+            S, PeerSync{0, nullptr, nullptr, nullptr}, in, in, in + (size_t)nx * (rows + 1),
+            v[(r + 2) % 3], yn, fn, v[r % 3], 0.0, 1.9, -0.95, 0.05, 1e-9, 0.3);
         count_launch();
     }
     cudaEventRecord(e1, st);

@@ -61,6 +61,53 @@ __device__ __forceinline__ void load4_peer(const double* p, double (&v)[PX]) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+// Neighbour barrier, fused into every kernel that reads a halo row.  A stencil
+// kernel with sequence number `seq` starts only after everything enqueued before
+// it on this rank's stream has finished, so at its start (a) the vector the
+// neighbours are about to read is complete and (b) this rank no longer reads
+// the buffers they are about to overwrite.  One thread says so -- a release
+// store of `seq` into the neighbours' flag words over NVLink -- and only the
+// CTAs that hold the slab's first / last row wait (acquire loads of this rank's
+// own flag words) until the neighbour has said the same.  Interior CTAs never
+// wait: the handshake latency hides behind their work, and there is no separate
+// synchronisation kernel between two stages.  The spin is bounded; on timeout
+// an error word is set and the host aborts the solve.
+struct PeerSync {
+    long long seq;             // 0: single rank, nothing to do
+    long long* up_remote;      // upper rank's "from below" flag (null at the domain edge)
+    long long* dn_remote;      // lower rank's "from above" flag
+    long long* mine;           // [0] written by the upper rank, [1] by the lower, [2] error
+};
+__device__ __forceinline__ void peer_handshake(const PeerSync& ps) {
+    if (ps.seq == 0) return;
+    const bool first = blockIdx.y == 0, last = blockIdx.y == gridDim.y - 1;
+    const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;
+    if (t0 && first && blockIdx.x == 0) {
+        if (ps.up_remote)
+            asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(ps.up_remote), "l"(ps.seq) : "memory");
+        if (ps.dn_remote)
+            asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(ps.dn_remote), "l"(ps.seq) : "memory");
+    }
+    const bool wait_up = first && ps.up_remote != nullptr;
+    const bool wait_dn = last && ps.dn_remote != nullptr;
+    if (!(wait_up || wait_dn)) return;            // uniform over the CTA
+    if (t0) {
+        const long long start = clock64(), budget = 4000000000LL;      // ~2 s
+        bool ok = true;
+        for (int i = 0; i < 2 && ok; ++i) {
+            if (!(i == 0 ? wait_up : wait_dn)) continue;
+            for (;;) {
+                long long v;
+                asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(ps.mine + i) : "memory");
+                if (v >= ps.seq) break;
+                if (clock64() - start > budget) { ok = false; break; }
+            }
+        }
+        if (!ok) ps.mine[2] = ps.seq;
+    }
+    __syncthreads();
+}
+
 // f(t, u) at 4 consecutive points of one row
 template <class Pde>
 __device__ __forceinline__ void rhs4(const Slab& S, const double* __restrict__ u,
@@ -107,9 +154,11 @@ __device__ __forceinline__ void block_sum_to(double s, double* __restrict__ part
 
 // dy = f(t, u)
 template <class Pde>
-__device__ __forceinline__ void eval_body(const Slab& S, const double* __restrict__ u,
+__device__ __forceinline__ void eval_body(const Slab& S, const PeerSync& ps,
+                                          const double* __restrict__ u,
                                           const double* up_row, const double* dn_row, double t,
                                           double* __restrict__ dy) {
+    peer_handshake(ps);
     XSQ_RKC_INDEX
     if (!active) return;
     double f[PX];
@@ -120,13 +169,15 @@ __device__ __forceinline__ void eval_body(const Slab& S, const double* __restric
 // Stage j >= 2 (sommeijer.py:311-313), fused with the RHS evaluation:
 //   Y_j = mu*Y_{j-1} + nu*Y_{j-2} + (1-mu-nu)*y_n + h*mus*(f(t_j, Y_{j-1}) - a_{j-1}*f_n)
 template <class Pde>
-__device__ __forceinline__ void stage_body(const Slab& S, const double* __restrict__ yjm1,
+__device__ __forceinline__ void stage_body(const Slab& S, const PeerSync& ps,
+                                           const double* __restrict__ yjm1,
                                            const double* up_row, const double* dn_row,
                                            const double* __restrict__ yjm2,
                                            const double* __restrict__ yn,
                                            const double* __restrict__ fn, double* __restrict__ yj,
                                            double t, double mu, double nu, double c3,
                                            double hmus, double ajm1) {
+    peer_handshake(ps);
     XSQ_RKC_INDEX
     if (!active) return;
     double f[PX], a[PX], b[PX], c[PX], d[PX], o[PX];
@@ -145,12 +196,14 @@ __device__ __forceinline__ void stage_body(const Slab& S, const double* __restri
 //   f1 = f(t+h, y);  est = 0.8*(yn - y) + 0.4*h*(fn + f1);
 //   wt = atol + rtol*max(|y|,|yn|);  partial[block] = sum (est/wt)^2
 template <class Pde>
-__device__ __forceinline__ void final_body(const Slab& S, const double* __restrict__ y,
+__device__ __forceinline__ void final_body(const Slab& S, const PeerSync& ps,
+                                           const double* __restrict__ y,
                                            const double* up_row, const double* dn_row,
                                            const double* __restrict__ yn,
                                            const double* __restrict__ fn, double* __restrict__ f1,
                                            double t, double h, double rtol, double atol,
                                            double* __restrict__ partial) {
+    peer_handshake(ps);
     XSQ_RKC_INDEX
     double s = 0.0;
     if (active) {
@@ -174,23 +227,23 @@ __device__ __forceinline__ void final_body(const Slab& S, const double* __restri
 
 template <class Pde>
 __global__ void __launch_bounds__(TX* TY)
-    k_eval(Slab S, const double* u, const double* up_row, const double* dn_row, double t,
-           double* dy) {
-    eval_body<Pde>(S, u, up_row, dn_row, t, dy);
+    k_eval(Slab S, PeerSync ps, const double* u, const double* up_row, const double* dn_row,
+           double t, double* dy) {
+    eval_body<Pde>(S, ps, u, up_row, dn_row, t, dy);
 }
 template <class Pde>
 __global__ void __launch_bounds__(TX* TY)
-    k_stage(Slab S, const double* yjm1, const double* up_row, const double* dn_row,
+    k_stage(Slab S, PeerSync ps, const double* yjm1, const double* up_row, const double* dn_row,
             const double* yjm2, const double* yn, const double* fn, double* yj, double t,
             double mu, double nu, double c3, double hmus, double ajm1) {
-    stage_body<Pde>(S, yjm1, up_row, dn_row, yjm2, yn, fn, yj, t, mu, nu, c3, hmus, ajm1);
+    stage_body<Pde>(S, ps, yjm1, up_row, dn_row, yjm2, yn, fn, yj, t, mu, nu, c3, hmus, ajm1);
 }
 template <class Pde>
 __global__ void __launch_bounds__(TX* TY)
-    k_final(Slab S, const double* y, const double* up_row, const double* dn_row, const double* yn,
-            const double* fn, double* f1, double t, double h, double rtol, double atol,
-            double* partial) {
-    final_body<Pde>(S, y, up_row, dn_row, yn, fn, f1, t, h, rtol, atol, partial);
+    k_final(Slab S, PeerSync ps, const double* y, const double* up_row, const double* dn_row,
+            const double* yn, const double* fn, double* f1, double t, double h, double rtol,
+            double atol, double* partial) {
+    final_body<Pde>(S, ps, y, up_row, dn_row, yn, fn, f1, t, h, rtol, atol, partial);
 }
 
 }  // namespace rkc

@@ -309,17 +309,18 @@ std::string pde_source(const UserPde& u) {
          "      double c, double n, double s, double w, double e, const double* p) {\n"
          "    return ::" + u.entry + "(t, x, y, inv_h2, c, n, s, w, e, p); }\n};\n} } }\n";
     s += "using namespace xsq::rkc;\n"
-         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_eval(Slab S, const double* u,\n"
-         "    const double* up, const double* dn, double t, double* dy) {\n"
-         "  eval_body<pde::User>(S, u, up, dn, t, dy); }\n"
-         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_stage(Slab S, const double* a,\n"
-         "    const double* up, const double* dn, const double* b, const double* yn, const double* fn,\n"
-         "    double* yj, double t, double mu, double nu, double c3, double hmus, double ajm1) {\n"
-         "  stage_body<pde::User>(S, a, up, dn, b, yn, fn, yj, t, mu, nu, c3, hmus, ajm1); }\n"
-         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_final(Slab S, const double* y,\n"
-         "    const double* up, const double* dn, const double* yn, const double* fn, double* f1,\n"
-         "    double t, double h, double rtol, double atol, double* partial) {\n"
-         "  final_body<pde::User>(S, y, up, dn, yn, fn, f1, t, h, rtol, atol, partial); }\n";
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_eval(Slab S, PeerSync ps,\n"
+         "    const double* u, const double* up, const double* dn, double t, double* dy) {\n"
+         "  eval_body<pde::User>(S, ps, u, up, dn, t, dy); }\n"
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_stage(Slab S, PeerSync ps,\n"
+         "    const double* a, const double* up, const double* dn, const double* b, const double* yn,\n"
+         "    const double* fn, double* yj, double t, double mu, double nu, double c3, double hmus,\n"
+         "    double ajm1) {\n"
+         "  stage_body<pde::User>(S, ps, a, up, dn, b, yn, fn, yj, t, mu, nu, c3, hmus, ajm1); }\n"
+         "extern \"C\" __global__ void __launch_bounds__(256) xsq_pde_final(Slab S, PeerSync ps,\n"
+         "    const double* y, const double* up, const double* dn, const double* yn, const double* fn,\n"
+         "    double* f1, double t, double h, double rtol, double atol, double* partial) {\n"
+         "  final_body<pde::User>(S, ps, y, up, dn, yn, fn, f1, t, h, rtol, atol, partial); }\n";
     return s;
 }
 
