@@ -424,7 +424,7 @@ def run_c5(xb, lib, dev, rank, world, dist, quick=False):
     if world > 1:
         ref = torch.zeros(5, dtype=torch.float64, device=dev)
         if rank == 0:
-            r1, ms1, cs1 = solve(nx, 0, nx, T_strong, None, 1)
+            r1, ms1, cs1 = solve(nx, 0, nx, T_strong, None, 2)      # best of two (first one maps memory)
             ref = torch.tensor([float(cs1[0]), float(cs1[1]), ms1, r1.nfev, r1.n_accepted],
                                dtype=torch.float64, device=dev)
         dist.broadcast(ref, src=0)

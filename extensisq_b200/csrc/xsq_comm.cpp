@@ -21,6 +21,7 @@ namespace xsq {
 struct Comm {
     ncclComm_t nccl;
     int rank, world;
+    CommWorkspace ws;
 };
 
 namespace {
@@ -80,7 +81,7 @@ int comm_create(int rank, int world, const char id[128], Comm** out) {
     if (!load()) return XSQ_ERR_CUDA;
     ncclUniqueId u;
     std::memcpy(&u, id, 128);
-    Comm* c = new Comm{nullptr, rank, world};
+    Comm* c = new Comm{nullptr, rank, world, CommWorkspace()};
     if (check(g.CommInitRank(&c->nccl, world, u, rank), "ncclCommInitRank")) {
         delete c;
         return XSQ_ERR_CUDA;
@@ -89,8 +90,22 @@ int comm_create(int rank, int world, const char id[128], Comm** out) {
     return XSQ_OK;
 }
 
+CommWorkspace* comm_workspace(Comm* c) { return c ? &c->ws : nullptr; }
+
+void comm_workspace_release(CommWorkspace* w) {
+    if (!w) return;
+    if (w->peer_up) cudaIpcCloseMemHandle((void*)w->peer_up);
+    if (w->peer_dn) cudaIpcCloseMemHandle((void*)w->peer_dn);
+    if (w->buf) { cudaDeviceSynchronize(); cudaFree(w->buf); }
+    if (w->xchg) cudaFree(w->xchg);
+    const long long seq = w->seq;
+    *w = CommWorkspace();
+    w->seq = seq;
+}
+
 void comm_destroy(Comm* c) {
     if (!c) return;
+    comm_workspace_release(&c->ws);
     if (g.lib) g.CommDestroy(c->nccl);
     delete c;
 }

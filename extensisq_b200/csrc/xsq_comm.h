@@ -8,6 +8,24 @@ namespace xsq {
 
 struct Comm;   // opaque
 
+// SSV2stab's slab storage on a multi-GPU communicator: allocated, exported with
+// CUDA IPC and mapped by the neighbours ONCE and kept for the next solve of the
+// same shape (mapping a few GB of peer memory costs hundreds of milliseconds,
+// more than the stages of a short solve).  Owned by the communicator, released
+// by comm_destroy.
+struct CommWorkspace {
+    double* buf = nullptr;
+    size_t doubles = 0;
+    long long key[6] = {0, 0, 0, 0, 0, 0};   // nx, rows_global, rows_local, world, rank, extras
+    const double* peer_up = nullptr;         // IPC mapping of the neighbours' storage
+    const double* peer_dn = nullptr;
+    int rows_up = 0;
+    long long seq = 0;                       // handshake sequence number, never reset
+    char* xchg = nullptr;                    // small device buffer for the handle exchange
+};
+CommWorkspace* comm_workspace(Comm* c);
+void comm_workspace_release(CommWorkspace* w);
+
 int comm_unique_id(char id[128]);
 int comm_create(int rank, int world, const char id[128], Comm** out);
 void comm_destroy(Comm* c);

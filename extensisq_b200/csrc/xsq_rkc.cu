@@ -368,63 +368,88 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     double* buf = nullptr;
     const size_t total = na * 6 + C.nblocks + C.world + 8 + 64 + (size_t)A->n_pde_params;
     const bool multi = C.world > 1;
-    // multi-GPU: plain cudaMalloc so the storage can be exported with CUDA IPC
-    cudaError_t me = multi ? cudaMalloc((void**)&buf, total * sizeof(double))
-                           : cudaMallocAsync((void**)&buf, total * sizeof(double), st);
-    if (me != cudaSuccess) {
-        set_detail("rkc: out of device memory");
-        return XSQ_ERR_NOMEM;
-    }
-    auto release = [&]() {
-        if (C.peer_up) cudaIpcCloseMemHandle((void*)C.peer_up);
-        if (C.peer_dn) cudaIpcCloseMemHandle((void*)C.peer_dn);
-        if (multi) { cudaStreamSynchronize(st); cudaFree(buf); }
-        else cudaFreeAsync(buf, st);
+    const size_t flag_off = na * 6 + C.nblocks + C.world + 8;
+    CommWorkspace* ws = multi ? comm_workspace(comm) : nullptr;
+    if (multi && !ws) { set_detail("rkc: world > 1 needs a communicator"); return XSQ_ERR_ARG; }
+    auto release = [&]() {        // single rank: back to the pool; multi: kept in the workspace
+        if (!multi && buf) cudaFreeAsync(buf, st);
     };
-    cudaMemsetAsync(buf, 0, total * sizeof(double), st);      // ghost rows = Dirichlet 0
-    C.base = buf;
-    C.flags = reinterpret_cast<long long*>(buf + na * 6 + C.nblocks + C.world + 8);
-    if (multi) {
-        // exchange (IPC handle, rows_local) with an all-gather, open the two
-        // neighbours' storage
-        struct Card { cudaIpcMemHandle_t h; long long rows; long long pad; };
+    if (!multi) {
+        if (cudaMallocAsync((void**)&buf, total * sizeof(double), st) != cudaSuccess) {
+            set_detail("rkc: out of device memory");
+            return XSQ_ERR_NOMEM;
+        }
+        cudaMemsetAsync(buf, 0, total * sizeof(double), st);      // ghost rows = Dirichlet 0
+    } else {
+        // Storage exported with CUDA IPC (plain cudaMalloc), mapped by the two
+        // neighbours, and KEPT in the communicator for the next solve of the same
+        // shape.  Whether to rebuild is decided collectively: every rank
+        // contributes "my shape changed", any one of them makes all rebuild (a
+        // stale mapping of a neighbour's freed storage must never be used).
+        const long long key[6] = {A->nx, A->rows_global, A->rows_local, C.world, C.rank,
+                                  (long long)A->n_pde_params};
+        const bool mine_changed = !ws->buf || ws->doubles != total ||
+                                  std::memcmp(ws->key, key, sizeof key) != 0;
+        struct Card { cudaIpcMemHandle_t h; long long rows; long long changed; };
         static_assert(sizeof(Card) == 80, "card");
-        Card mine;
-        std::memset(&mine, 0, sizeof mine);
-        if (cudaIpcGetMemHandle(&mine.h, buf) != cudaSuccess) {
-            set_detail("rkc: cudaIpcGetMemHandle failed");
-            release();
-            return XSQ_ERR_CUDA;
-        }
-        mine.rows = A->rows_local;
-        char* xchg = nullptr;
+        bool ok = true;
+        if (!ws->xchg) ok = cudaMalloc((void**)&ws->xchg, sizeof(Card) * (C.world + 1)) == cudaSuccess;
         std::vector<Card> cards(C.world);
-        bool ok = cudaMalloc((void**)&xchg, sizeof(Card) * (C.world + 1)) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(xchg, &mine, sizeof(Card), cudaMemcpyHostToDevice, st) == cudaSuccess;
-        ok = ok && comm_allgather_bytes(comm, xchg, xchg + sizeof(Card), sizeof(Card), st) == 0;
-        ok = ok && cudaMemcpyAsync(cards.data(), xchg + sizeof(Card), sizeof(Card) * C.world,
-                                   cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
-        if (xchg) cudaFree(xchg);
-        void* p = nullptr;
-        if (ok && C.rank > 0) {
-            ok = cudaIpcOpenMemHandle(&p, cards[C.rank - 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            C.peer_up = (const double*)p;
-            C.rows_up = (int)cards[C.rank - 1].rows;
-        }
-        if (ok && C.rank + 1 < C.world) {
-            ok = cudaIpcOpenMemHandle(&p, cards[C.rank + 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            C.peer_dn = (const double*)p;
+        auto exchange = [&](const Card& mine) {
+            bool k = cudaMemcpyAsync(ws->xchg, &mine, sizeof(Card), cudaMemcpyHostToDevice, st) == cudaSuccess;
+            k = k && comm_allgather_bytes(comm, ws->xchg, ws->xchg + sizeof(Card), sizeof(Card), st) == 0;
+            k = k && cudaMemcpyAsync(cards.data(), ws->xchg + sizeof(Card), sizeof(Card) * C.world,
+                                     cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            return k && cudaStreamSynchronize(st) == cudaSuccess;
+        };
+        Card vote;
+        std::memset(&vote, 0, sizeof vote);
+        vote.changed = mine_changed ? 1 : 0;
+        ok = ok && exchange(vote);
+        bool rebuild = false;
+        for (int r = 0; ok && r < C.world; ++r) rebuild = rebuild || cards[r].changed != 0;
+        if (ok && rebuild) {
+            comm_workspace_release(ws);
+            ok = cudaMalloc((void**)&ws->xchg, sizeof(Card) * (C.world + 1)) == cudaSuccess;
+            if (ok && cudaMalloc((void**)&ws->buf, total * sizeof(double)) != cudaSuccess) {
+                set_detail("rkc: out of device memory");
+                return XSQ_ERR_NOMEM;
+            }
+            ws->doubles = total;
+            std::memcpy(ws->key, key, sizeof key);
+            ok = ok && cudaMemsetAsync(ws->buf, 0, total * sizeof(double), st) == cudaSuccess;
+            Card mine;
+            std::memset(&mine, 0, sizeof mine);
+            ok = ok && cudaIpcGetMemHandle(&mine.h, ws->buf) == cudaSuccess;
+            mine.rows = A->rows_local;
+            ok = ok && exchange(mine);
+            void* p = nullptr;
+            if (ok && C.rank > 0) {
+                ok = cudaIpcOpenMemHandle(&p, cards[C.rank - 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                ws->peer_up = (const double*)p;
+                ws->rows_up = (int)cards[C.rank - 1].rows;
+            }
+            if (ok && C.rank + 1 < C.world) {
+                ok = cudaIpcOpenMemHandle(&p, cards[C.rank + 1].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                ws->peer_dn = (const double*)p;
+            }
         }
         if (!ok) {
-            set_detail(std::string("rkc: peer mapping failed: ") + cudaGetErrorString(cudaGetLastError()));
-            release();
+            set_detail(std::string("rkc: peer storage set-up failed: ") + cudaGetErrorString(cudaGetLastError()));
+            comm_workspace_release(ws);
             return XSQ_ERR_CUDA;
         }
-        const size_t flag_off = na * 6 + C.nblocks + C.world + 8;
+        buf = ws->buf;
+        C.peer_up = ws->peer_up;
+        C.peer_dn = ws->peer_dn;
+        C.rows_up = ws->rows_up;
+        C.seq = ws->seq;           // flags hold the last sequence number: keep counting
         if (C.peer_up) C.up_flag_remote = (long long*)(C.peer_up + flag_off) + 1;
         if (C.peer_dn) C.dn_flag_remote = (long long*)(C.peer_dn + flag_off) + 0;
     }
+    C.base = buf;
+    C.flags = reinterpret_cast<long long*>(buf + flag_off);
+    if (multi) cudaMemsetAsync(C.flags + 2, 0, sizeof(long long), st);   // the time-out word
     double *yn = buf, *fn = buf + na, *w0 = buf + 2 * na, *w1 = buf + 3 * na,
            *w2 = buf + 4 * na, *V = buf + 5 * na;
     C.partial = buf + 6 * na;
@@ -706,6 +731,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
         k_peer_barrier<<<dim3(1, 1), dim3(1, 1), 0, st>>>(C.ps);
         C.launched();
         cudaStreamSynchronize(st);
+        ws->seq = C.seq;
     }
     release();
     cudaFreeHost(C.scalar_host);
