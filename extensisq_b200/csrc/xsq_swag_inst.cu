@@ -2,13 +2,46 @@
 // provides launch_swag(), called by xsq_swag_solve (xsq_api.cu).
 #include "xsq_launch.h"
 #include "xsq_swag_core.cuh"
+#include "xsq_swag_fast.cuh"
 #include "xsq_rhs.cuh"
 #include "xsq.h"
 
 namespace xsq {
 
+// Small systems, final state only: registers for phi, shared memory for the
+// coefficient arrays (xsq_swag_fast.cuh).  64-thread CTAs: 47.6 KB of
+// coefficient storage each, four per SM.
+template <class R>
+static int launch_swag_fast(const RkDev& P, cudaStream_t st) {
+    if constexpr (R::WARP || R::NL > 4) {
+        return XSQ_ERR_UNSUPPORTED;
+    } else {
+        constexpr int BLOCK = 64, MINB = 4;
+        auto kern = swag_fast<R, BLOCK, MINB>;
+        int dev = 0, n_sm = 0, occ = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return XSQ_ERR_CUDA;
+        constexpr size_t smem = sizeof(SwagCoefs<BLOCK>);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return XSQ_ERR_CUDA;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem) != cudaSuccess ||
+            occ < 1)
+            return XSQ_ERR_CUDA;
+        long long want = (P.n_lanes + BLOCK - 1) / BLOCK;
+        long long grid = (long long)n_sm * occ;
+        if (want < grid) grid = want;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, BLOCK, smem, st>>>(P);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+    }
+}
+
 template <class R>
 static int launch_swag_one(const RkDev& P, cudaStream_t st) {
+    if (swag_fast_eligible<R>(P)) return launch_swag_fast<R>(P, st);
     constexpr int BLOCK = 128, MINB = 2;
     auto kern = swag_persistent<R, BLOCK, MINB>;
     int dev = 0, n_sm = 0, occ = 0;

@@ -31,6 +31,7 @@ double xsq_host_rcp64h(double x) {
 
 #include "xsq_rk_fast.cuh"
 #include "xsq_swag_core.cuh"
+#include "xsq_swag_fast.cuh"
 #include "xsq_rhs.cuh"
 #include "xsq_user.h"
 
@@ -146,6 +147,12 @@ static int run_swag(RkDev P) {
         ens_init_body<R>(P);
     }
     blockIdx = {0, 0, 0};
+    if constexpr (!R::WARP && R::NL <= 4) {
+        if (swag_fast_eligible<R>(P)) {
+            swag_fast_body<R, 1>(P);
+            return 0;
+        }
+    }
     swag_persistent_body<R>(P);
     return 0;
 }

@@ -18,7 +18,7 @@ def build():
     src += [os.path.join(ROOT, "extensisq_b200", "csrc", f) for f in
             ("xsq_rk_core.cuh", "xsq_rk_fast.cuh", "xsq_math.cuh", "xsq_intrin.cuh",
              "xsq_params.h", "xsq_rhs.cuh", "xsq_tableaux_gen.cuh", "xsq_math_tables_gen.cuh",
-             "xsq_swag_core.cuh")]
+             "xsq_swag_core.cuh", "xsq_swag_fast.cuh")]
     out = os.path.join(HERE, "_build", "xsq_emu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if (not os.path.exists(out) or

@@ -45,24 +45,34 @@ def test_swag_ensemble_parity_vs_c_oracle(prob, lanes, span):
     r = to_np(xb.solve_ivp_batched(prob, span, y0, xb.SWAG, params=prm,
                                    rtol=rtol, atol=atol, t_eval=te,
                                    max_steps=500000))
-    ref = CO.swag_batch(prob, span, y0, params=prm, rtol=rtol, atol=atol,
-                        t_eval=te, n_threads=8)
+    # the oracle in the kernel's own arithmetic: every lane, every output, bit for bit
+    with CO.device_math():
+        ref = CO.swag_batch(prob, span, y0, params=prm, rtol=rtol, atol=atol,
+                            t_eval=te, n_threads=8)
+    assert (r["status"] == 0).all() and (ref["status"] == 0).all()
+    for k in ("n_accepted", "n_rejected", "nfev", "n_eval_done"):
+        assert np.array_equal(r[k], ref[k]), k
+    for k in ("t_final", "y_final", "y"):
+        assert np.array_equal(np.ascontiguousarray(r[k]).view(np.uint64),
+                              np.ascontiguousarray(ref[k]).view(np.uint64)), k
+    # ... and what that arithmetic costs against the reference's (pow, log10):
+    # counts identical on the bulk of the lanes, every lane within 10 x rtol plus
+    # the oracle's own 1-ulp sensitivity
+    ref_ra = CO.swag_batch(prob, span, y0, params=prm, rtol=rtol, atol=atol, t_eval=te,
+                           n_threads=8)
     ref_p = CO.swag_batch(prob, span, np.nextafter(y0, np.inf), params=prm,
                           rtol=rtol, atol=atol, n_threads=8)
-    assert (r["status"] == 0).all() and (ref["status"] == 0).all()
-    same = ((r["n_accepted"] == ref["n_accepted"]) &
-            (r["n_rejected"] == ref["n_rejected"]) & (r["nfev"] == ref["nfev"]))
-    scale = np.abs(ref["y_final"]).max(axis=1) + 1e-300
-    err = np.abs(r["y_final"] - ref["y_final"]).max(axis=1) / scale
-    sens = np.abs(ref_p["y_final"] - ref["y_final"]).max(axis=1) / scale
+    same = ((r["n_accepted"] == ref_ra["n_accepted"]) &
+            (r["n_rejected"] == ref_ra["n_rejected"]) & (r["nfev"] == ref_ra["nfev"]))
+    scale = np.abs(ref_ra["y_final"]).max(axis=1) + 1e-300
+    err = np.abs(r["y_final"] - ref_ra["y_final"]).max(axis=1) / scale
+    sens = np.abs(ref_p["y_final"] - ref_ra["y_final"]).max(axis=1) / scale
+    print(f"\nSWAG {prob}: counts identical to the reference arithmetic on {same.mean():.3f} "
+          f"of {N} lanes; median state difference {np.median(err):.1e}")
     assert (err <= 100 * rtol + 100 * sens).all()
     assert np.median(err) <= 1e-9
-    assert same.mean() >= (0.85 if prob == "lorenz63" else 0.75)
-    assert abs(int(r["nfev"].sum()) - int(ref["nfev"].sum())) <= \
-        0.005 * ref["nfev"].sum()
-    assert (r["n_eval_done"] == te.size).all()
-    ok = same & (err <= 1e-9)
-    assert rel(r["y"][ok], ref["y"][ok]) <= 1e-6
+    assert same.mean() >= 0.5
+    assert abs(int(r["nfev"].sum()) - int(ref_ra["nfev"].sum())) <= 0.005 * ref_ra["nfev"].sum()
 
 
 def test_swag_nbody32_warp_per_system():
