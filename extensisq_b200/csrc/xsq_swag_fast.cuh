@@ -29,7 +29,7 @@ namespace xsq {
 template <int BLOCK>
 struct SwagCoefs {
     double psi[SWAG_KMAX][BLOCK], alpha[SWAG_KMAX][BLOCK], beta[SWAG_KMAX][BLOCK];
-    double sig[SWAG_KMAX + 1][BLOCK], v[SWAG_KMAX][BLOCK], w[SWAG_KMAX + 1][BLOCK];
+    double sig[SWAG_KMAX + 1][BLOCK], v[SWAG_KMAX][BLOCK];
     double g[SWAG_KMAX + 1][BLOCK];
     int iv[SWAG_KMAX][BLOCK];
 };
@@ -121,74 +121,92 @@ struct SwagFastLane {
         if (h != hold) ns = 0;
         if (ns <= kold) ns += 1;
         if (k >= ns) {
+            // Written for the warp: every loop runs to the compile-time bound with
+            // the lane's own range as a predicate, so the lanes of a warp that are
+            // at different (ns, k) walk ONE instruction stream, and the scratch
+            // row w of the reference lives in registers.  Same operations on the
+            // same operands, in the same order per element, as shampine.py:247-316.
             const int nsm1 = ns - 1;
+            const double inv_ns = 1.0 / ns;
             // psi_old[i - nsm1] of the reference is psi[i] before this update; the
             // recurrences below read psi[i - 1] (old) just before writing psi[i]
             double psi_prev = C.psi[nsm1][tid];        // old psi[nsm1]
-            const double psi_first = h * ns;
-            C.psi[nsm1][tid] = psi_first;
-            C.alpha[nsm1][tid] = 1.0 / ns;
+            double psi_im1_new = h * ns;
+            C.psi[nsm1][tid] = psi_im1_new;
+            C.alpha[nsm1][tid] = inv_ns;
             C.beta[nsm1][tid] = 1.0;
-            double bprod = 1.0, psi_im1_new = psi_first;
-            for (int i = ns; i < k; ++i) {
-                const double psi_old_im1 = psi_prev;   // psi_old[i - ns] = old psi[i - 1]
-                psi_prev = C.psi[i][tid];              // old psi[i], for the next round
-                const double psi_i = h + psi_old_im1;
-                C.psi[i][tid] = psi_i;
-                C.alpha[i][tid] = h / psi_i;
-                const double ratio = psi_im1_new / psi_old_im1;
-                bprod = (i == ns) ? ratio : bprod * ratio;
-                C.beta[i][tid] = bprod;
-                psi_im1_new = psi_i;
-            }
-            double sprod = 1.0;
-            for (int i = ns; i <= k; ++i) {
-                const double term = (double)i * C.alpha[i - 1][tid];
-                sprod = (i == ns) ? term : sprod * term;
-                C.sig[i][tid] = sprod;
-            }
-            if (ns == 1) {
-                for (int i = 0; i < k; ++i) {
-                    const double q = iqq(i);
-                    C.w[i][tid] = q;
-                    C.v[i][tid] = q;
+            if (ns != 1 && k > kprev) {                // order was raised at constant h
+                int jv;
+                if (ivc != 0) {
+                    ivc -= 1;
+                    jv = kp1 - C.iv[ivc][tid];
+                } else {
+                    jv = 1;
+                    C.v[km1][tid] = iqq(km1);
                 }
-                ivc = 0;
-            } else {
-                if (k > kprev) {
-                    int jv;
-                    if (ivc != 0) {
-                        ivc -= 1;
-                        jv = kp1 - C.iv[ivc][tid];
-                    } else {
-                        jv = 1;
-                        const double q = iqq(km1);
-                        C.w[km1][tid] = q;
-                        C.v[km1][tid] = q;
-                    }
-                    for (int j = jv; j < nsm1; ++j) {
-                        const int i = km1 - j;
-                        const double vi = fma(-C.alpha[j][tid], C.v[i + 1][tid], C.v[i][tid]);
-                        C.v[i][tid] = vi;
-                        C.w[i][tid] = vi;
-                    }
+                for (int j = jv; j < nsm1; ++j) {
+                    const int i = km1 - j;
+                    C.v[i][tid] = fma(-C.alpha[j][tid], C.v[i + 1][tid], C.v[i][tid]);
                 }
+            }
+            // v (kept between steps) and w (scratch: every element the g recurrence
+            // reads below is written here first, so it never needs to be stored)
+            double w[KMAX + 1];
+            {
                 const int limit1 = kp1 - ns;
-                const double a_ns = C.alpha[nsm1][tid];
-                for (int i = 0; i < limit1; ++i)
-                    C.v[i][tid] = fma(-a_ns, C.v[i + 1][tid], C.v[i][tid]);
-                for (int i = 0; i <= limit1; ++i) C.w[i][tid] = C.v[i][tid];
-                C.g[ns][tid] = C.w[0][tid];
-                if (k < kold) { C.iv[ivc][tid] = limit1 + 2; ivc += 1; }
+                const bool first = ns == 1;
+                double vr[KMAX + 1];
+                static_for<0, KMAX>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    vr[i] = C.v[i][tid];
+                });
+                vr[KMAX] = 0.0;
+                static_for<0, KMAX>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const double q = 1.0 / ((double)(i + 1) * ((double)(i + 1) + 1.0));
+                    const double stepped = fma(-inv_ns, vr[i + 1], vr[i]);
+                    double nv = vr[i];
+                    if (first ? i < k : i < limit1) nv = first ? q : stepped;
+                    C.v[i][tid] = nv;
+                    w[i] = nv;
+                });
+                w[KMAX] = 0.0;
+                if (first) {
+                    ivc = 0;
+                } else {
+                    C.g[ns][tid] = w[0];
+                    if (k < kold) { C.iv[ivc][tid] = limit1 + 2; ivc += 1; }
+                }
             }
             kprev = k;
-            for (int i = ns; i < k; ++i) {
-                const int limit2 = k - i;
-                const double a_i = C.alpha[i][tid];
-                for (int j = 0; j < limit2; ++j)
-                    C.w[j][tid] = fma(-a_i, C.w[j + 1][tid], C.w[j][tid]);
-                C.g[i + 1][tid] = C.w[0][tid];
-            }
+            // psi, alpha, beta, sig and g for ns <= i < k.  Elements of w beyond the
+            // lane's k - i are computed too and never read (the recurrence at i
+            // reads w[0 .. k-i], all valid after round i-1).
+            double bprod = 1.0, sprod = 1.0, a_prev = inv_ns;
+            static_for<1, KMAX>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                if (i >= ns && i < k) {
+                    sprod *= (double)i * a_prev;       // the first factor times 1.0 is exact
+                    C.sig[i][tid] = sprod;
+                    const double psi_old_im1 = psi_prev;   // psi_old[i - ns] = old psi[i - 1]
+                    psi_prev = C.psi[i][tid];              // old psi[i], for the next round
+                    const double psi_i = h + psi_old_im1;
+                    C.psi[i][tid] = psi_i;
+                    const double a_i = div_by(h, div_rcp(psi_i));
+                    C.alpha[i][tid] = a_i;
+                    bprod *= div_by(psi_im1_new, div_rcp(psi_old_im1));
+                    C.beta[i][tid] = bprod;
+                    psi_im1_new = psi_i;
+                    a_prev = a_i;
+                    static_for<0, KMAX - i>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        w[j] = fma(-a_i, w[j + 1], w[j]);
+                    });
+                    C.g[i + 1][tid] = w[0];
+                }
+            });
+            sprod *= (double)k * a_prev;
+            C.sig[k][tid] = sprod;
         }
         // ---- block 2: predict, evaluate, estimate errors (shampine.py:326-364) --
         static_for<1, KMAX>([&](auto ic) {             // phi[i] *= beta[i], ns <= i < k
@@ -283,9 +301,9 @@ struct SwagFastLane {
             static_for<0, KMAX>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 if (i < k) {
-                    const double b = C.beta[i][tid];
+                    const DivRcp b = div_rcp(C.beta[i][tid]);
 #pragma unroll
-                    for (int c = 0; c < NL; ++c) phi[i][c] = (phi[i][c] - phi[i + 1][c]) / b;
+                    for (int c = 0; c < NL; ++c) phi[i][c] = div_by(phi[i][c] - phi[i + 1][c], b);
                 }
             });
             for (int i = 0; i < km1; ++i) C.psi[i][tid] = C.psi[i + 1][tid] - h;
