@@ -199,9 +199,11 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         int dev = 0, n_sm = 0;
         XSQ_CUDA(cudaGetDevice(&dev));
         XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        const bool warp_rhs = a->rhs == XSQ_RHS_NBODY32;
-        const size_t nl = warp_rhs ? 6 : (size_t)a->n_state;
-        const size_t npl = warp_rhs ? 2 : (size_t)(a->n_param > 0 ? a->n_param : 1);
+        const bool wide = a->n_state > XSQ_MAX_LANE_STATE && a->rhs != XSQ_RHS_NBODY32;
+        const bool warp_rhs = a->rhs == XSQ_RHS_NBODY32 || wide;
+        const size_t nl = wide ? (size_t)(a->n_state + 31) / 32
+                               : (warp_rhs ? 6 : (size_t)a->n_state);
+        const size_t npl = a->rhs == XSQ_RHS_NBODY32 ? 2 : (size_t)(a->n_param > 0 ? a->n_param : 1);
         size_t threads = (size_t)n_sm * 2048;
         const size_t want = ((warp_rhs ? N * 32 : N) + 255) & ~(size_t)255;
         if (want < threads) threads = want;

@@ -123,8 +123,9 @@ inline int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
             set_detail("events arguments inconsistent");
             return XSQ_ERR_ARG;
         }
-        if (a->n_forced > 0 || a->rhs == XSQ_RHS_NBODY32) {
-            set_detail("events are not available with forced steps or nbody32");
+        if (a->n_forced > 0 || a->rhs == XSQ_RHS_NBODY32 || a->n_state > XSQ_MAX_LANE_STATE) {
+            set_detail("events are not available with forced steps or warp-per-system "
+                       "right-hand sides");
             return XSQ_ERR_UNSUPPORTED;
         }
         for (int k = 0; k < ne; ++k)

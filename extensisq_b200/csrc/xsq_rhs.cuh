@@ -10,6 +10,7 @@
 //   NPAR   parameters per system in global memory (SoA [NPAR][n_lanes])
 //   NPL    parameters held by one thread
 //   WARP   true: one warp integrates one system
+//   PADDED true: N is not 32 * NL, slots with comp(k, lane) >= N are padding
 //   comp(k, lane)        global component index of local slot k
 //   load_params(...)     fill the thread's parameter registers
 //   f(t, y, p, dy)       the derivative (may use warp shuffles if WARP)
@@ -25,7 +26,7 @@ namespace rhs {
 
 struct Lorenz63 {
     static constexpr int N = 3, NL = 3, NPAR = 3, NPL = 3;
-    static constexpr bool WARP = false;
+    static constexpr bool WARP = false, PADDED = false;
     static constexpr int FLOPS = 8;
     __device__ __forceinline__ static int comp(int k, int) { return k; }
     __device__ __forceinline__ static void load_params(
@@ -45,7 +46,7 @@ struct Lorenz63 {
 
 struct VanDerPol {
     static constexpr int N = 2, NL = 2, NPAR = 1, NPL = 1;
-    static constexpr bool WARP = false;
+    static constexpr bool WARP = false, PADDED = false;
     static constexpr int FLOPS = 6;
     __device__ __forceinline__ static int comp(int k, int) { return k; }
     __device__ __forceinline__ static void load_params(
@@ -65,7 +66,7 @@ struct VanDerPol {
 // orbit; Hairer-Norsett-Wanner I, eq. II.0.1).  y = (x, y, x', y').
 struct Arenstorf {
     static constexpr int N = 4, NL = 4, NPAR = 1, NPL = 1;
-    static constexpr bool WARP = false;
+    static constexpr bool WARP = false, PADDED = false;
     static constexpr int FLOPS = 60;
     __device__ __forceinline__ static int comp(int k, int) { return k; }
     __device__ __forceinline__ static void load_params(
@@ -95,7 +96,7 @@ struct Arenstorf {
 struct NBody32 {
     static constexpr int NB = 32;
     static constexpr int N = 6 * NB, NL = 6, NPAR = 1 + NB, NPL = 2;
-    static constexpr bool WARP = true;
+    static constexpr bool WARP = true, PADDED = false;
     static constexpr int FLOPS = 31 * 20 * 32;
     __device__ __forceinline__ static int comp(int k, int lane) {
         return k < 3 ? 3 * lane + k : 3 * NB + 3 * lane + (k - 3);
@@ -132,6 +133,42 @@ struct NBody32 {
         dy[3] = ax;
         dy[4] = ay;
         dy[5] = az;
+    }
+};
+
+// A user system too large for one thread (n_state > 16; the reference takes any
+// n, common.py:187-217): one warp per system, component i in slot i / 32 of
+// lane i % 32, so that every access of the warp to the state is one contiguous
+// run.  The user's device function returns ONE component,
+//     double f_i(int i, double t, const double* y, const double* p)
+// and sees the whole stage vector y[0..N) through shared memory (one buffer
+// per warp of the 128-thread CTA).  Slots with i >= N are padding (zero).
+template <int N_, int NPAR_, class Fn>
+struct WideSystem {
+    static constexpr int N = N_, NL = (N_ + 31) / 32, NPAR = NPAR_, NPL = NPAR_ > 0 ? NPAR_ : 1;
+    static constexpr bool WARP = true, PADDED = (N_ % 32) != 0;
+    static constexpr int FLOPS = 0;
+    __device__ __forceinline__ static int comp(int k, int lane) { return k * 32 + lane; }
+    __device__ __forceinline__ static void load_params(
+        const double* __restrict__ params, long long sys, long long n_lanes,
+        int, double (&p)[NPL]) {
+#pragma unroll
+        for (int k = 0; k < NPAR; ++k) p[k] = params[k * n_lanes + sys];
+    }
+    __device__ __forceinline__ static void f(double t, const double (&y)[NL],
+                                             const double (&p)[NPL], double (&dy)[NL]) {
+        __shared__ double stage[4][NL * 32];
+        double* s = stage[(threadIdx.x >> 5) & 3];
+        const int lane = threadIdx.x & 31;
+        __syncwarp();                       // the previous evaluation has been read
+#pragma unroll
+        for (int k = 0; k < NL; ++k) s[k * 32 + lane] = y[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const int i = k * 32 + lane;
+            dy[k] = i < N ? Fn::at(i, t, s, p) : 0.0;
+        }
     }
 };
 

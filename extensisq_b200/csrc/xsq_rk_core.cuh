@@ -249,9 +249,28 @@ __device__ __forceinline__ double rms(const double (&x)[R::NL]) {
     return sqrt(s / (double)R::N);
 }
 
+// Warp-per-system policies whose size is not a multiple of 32 have padded
+// slots (comp(k, lane) >= N): they hold zeros, are never loaded or stored, and
+// add exact zeros to every norm.
+template <class R>
+__device__ __forceinline__ bool slot_ok(int k, int lane) {
+    if constexpr (R::PADDED) return R::comp(k, lane) < R::N;
+    else return true;
+}
+template <class R>
+__device__ __forceinline__ double load_slot(const double* __restrict__ base, long long n_lanes,
+                                            long long idx, int k, int lane) {
+    return slot_ok<R>(k, lane) ? base[(long long)R::comp(k, lane) * n_lanes + idx] : 0.0;
+}
+template <class R>
+__device__ __forceinline__ void store_slot(double* __restrict__ base, long long n_lanes,
+                                           long long idx, int k, int lane, double v) {
+    if (slot_ok<R>(k, lane)) base[(long long)R::comp(k, lane) * n_lanes + idx] = v;
+}
+
 template <class R>
 __device__ __forceinline__ double atol_of(const RkDev& P, int k, int lane) {
-    if (R::WARP) return P.atol_dev[R::comp(k, lane)];
+    if (R::WARP) return slot_ok<R>(k, lane) ? P.atol_dev[R::comp(k, lane)] : 1.0;
     return P.atol[k];
 }
 
@@ -280,6 +299,7 @@ __device__ __forceinline__ void eval_put(const RkDev& P, long long sys, int lane
         const int i0 = i & ~3;
 #pragma unroll
         for (int c = 0; c < R::NL; ++c) {
+            if (!slot_ok<R>(c, lane)) continue;
             const long long row = sys * (long long)R::N + R::comp(c, lane);
             double2* dst = reinterpret_cast<double2*>(
                 P.y_eval + row * P.eval_pitch + i0);
@@ -302,6 +322,7 @@ __device__ __forceinline__ void eval_finish(const RkDev& P, long long sys,
     const int i0 = ieval & ~3;
 #pragma unroll
     for (int c = 0; c < R::NL; ++c) {
+        if (!slot_ok<R>(c, lane)) continue;
         const long long row = sys * (long long)R::N + R::comp(c, lane);
         double* dst = P.y_eval + row * P.eval_pitch;
         for (int i = i0; i < ieval; ++i)
@@ -344,7 +365,7 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
         for (int c = 0; c < NL; ++c) { spy[c] = yprime[c]; yp[c] = yprime[c]; }
     } else {
 #pragma unroll
-        for (int c = 0; c < NL; ++c) { spy[c] = 0.0; yp[c] = 1.0; }
+        for (int c = 0; c < NL; ++c) { spy[c] = 0.0; yp[c] = slot_ok<R>(c, lane) ? 1.0 : 0.0; }
         delf = rms<R>(yp);
     }
     double dfdub = 0.0;
@@ -376,6 +397,7 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
             else dy = (pv[c] != 0.0) ? pv[c] : delf;
             if (spy[c] == 0.0) spy[c] = yp[c];
             yp[c] = (spy[c] != 0.0) ? copysign(dy, spy[c]) : dy;
+            if (!slot_ok<R>(c, lane)) yp[c] = 0.0;          // padding stays zero
         }
         delf = rms<R>(yp);
     }
@@ -387,8 +409,10 @@ __device__ double h_start_dev(const RkDev& P, double a, double b,
         // log10(etol) in the reference; 10^(c log10 x) = 2^(c log2 x), and the
         // table-driven log2 / exp2 are repeated bit for bit by the C oracle
         const double te = log2_fast(etol);
-        tolsum += te;
-        tolmin = fmin(tolmin, te);
+        if (slot_ok<R>(c, lane)) {
+            tolsum += te;
+            tolmin = fmin(tolmin, te);
+        }
     }
     tolsum = sys_sum<R::WARP>(tolsum);
     tolmin = fmin(sys_min<R::WARP>(tolmin), big);
@@ -425,7 +449,7 @@ __device__ __forceinline__ void ens_init_body(const RkDev& P) {
     double y[R::NL], f[R::NL], prm[R::NPL];
 #pragma unroll
     for (int k = 0; k < R::NL; ++k)
-        y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+        y[k] = load_slot<R>(P.y0, P.n_lanes, idx, k, lane);
     R::load_params(P.params, idx, P.n_lanes, lane, prm);
     int nfev = 1;
     R::f(P.t0, y, prm, f);
@@ -437,7 +461,7 @@ __device__ __forceinline__ void ens_init_body(const RkDev& P) {
     }
 #pragma unroll
     for (int k = 0; k < R::NL; ++k)
-        P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx] = f[k];
+        store_slot<R>(P.init_f0, P.n_lanes, idx, k, lane, f[k]);
     if (!R::WARP || lane == 0) {
         P.init_h[idx] = h;
         P.init_nfev[idx] = nfev;
@@ -601,8 +625,9 @@ __device__ __forceinline__ int stiff_probe_impl(const double* slot, long long st
         if (v0v0 == 0.0) {
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
-                v0[c] = 1.0;
-                v0q[c] = 1.0 / C.wt[c];
+                const bool ok = slot_ok<R>(c, (int)(threadIdx.x & 31));
+                v0[c] = ok ? 1.0 : 0.0;
+                v0q[c] = ok ? 1.0 / C.wt[c] : 0.0;
             }
             v0v0 = wdotq<R>(v0q, v0q);
         }
@@ -812,7 +837,7 @@ struct Lane {
         t = P.t0;
 #pragma unroll
         for (int k = 0; k < NL; ++k)
-            y[k] = P.y0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+            y[k] = load_slot<R>(P.y0, P.n_lanes, idx, k, lane);
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
         n_acc = n_rej = n_pre = ieval = 0;
         StiffState& ss = stiff_state();
@@ -824,7 +849,7 @@ struct Lane {
         ss.rej_base[threadIdx.x] = 0;
 #pragma unroll
         for (int k = 0; k < NL; ++k)
-            f[k] = P.init_f0[(long long)R::comp(k, lane) * P.n_lanes + idx];
+            f[k] = load_slot<R>(P.init_f0, P.n_lanes, idx, k, lane);
         nfev = P.init_nfev[idx];
         standard_sc = true;
         fresh = true;
@@ -1741,7 +1766,7 @@ struct Lane {
                                           bool constant = false) {
 #pragma unroll
         for (int k = 0; k < NL; ++k)
-            P.y_final[(long long)R::comp(k, lane) * P.n_lanes + sys] = y[k];
+            store_slot<R>(P.y_final, P.n_lanes, sys, k, lane, y[k]);
         if (P.n_eval > 0 && ieval < P.n_eval) {
             eval_finish<R>(P, sys, lane, ieval, constant, y);
             if (constant) ieval = P.n_eval;

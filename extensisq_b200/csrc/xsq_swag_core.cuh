@@ -66,11 +66,11 @@ struct SwagLane {
         k_max = P.interpolant;          // k_max travels in this field
 #pragma unroll
         for (int c = 0; c < NL; ++c)
-            y[c] = P.y0[(long long)R::comp(c, lane) * P.n_lanes + idx];
+            y[c] = load_slot<R>(P.y0, P.n_lanes, idx, c, lane);
         R::load_params(P.params, idx, P.n_lanes, lane, prm);
 #pragma unroll
         for (int c = 0; c < NL; ++c)
-            yp[c] = P.init_f0[(long long)R::comp(c, lane) * P.n_lanes + idx];
+            yp[c] = load_slot<R>(P.init_f0, P.n_lanes, idx, c, lane);
         nfev = P.init_nfev[idx];
         const double b = P.t0 + copysign(
             fmin(fabs(P.t_bound - P.t0), P.max_step), P.direction);
@@ -472,7 +472,7 @@ struct SwagLane {
                           bool constant = false) {
 #pragma unroll
         for (int c = 0; c < NL; ++c)
-            P.y_final[(long long)R::comp(c, lane) * P.n_lanes + sys] = y[c];
+            store_slot<R>(P.y_final, P.n_lanes, sys, c, lane, y[c]);
         if (P.n_eval > 0 && ieval < P.n_eval) {
             eval_finish<R>(P, sys, lane, ieval, constant, y);
             if (constant) ieval = P.n_eval;

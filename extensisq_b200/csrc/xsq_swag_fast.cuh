@@ -473,5 +473,11 @@ template <class R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) swag_fast(const RkDev P) {
     swag_fast_body<R, BLOCK>(P);
 }
+#ifdef XSQ_SWAG_GEOMETRY_SWEEP
+template <class R, int BLOCK, int MAXREG>
+__global__ void __maxnreg__(MAXREG) swag_fast_maxreg(const RkDev P) {
+    swag_fast_body<R, BLOCK>(P);
+}
+#endif
 
 }  // namespace xsq

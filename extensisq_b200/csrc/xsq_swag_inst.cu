@@ -11,31 +11,45 @@ namespace xsq {
 // Small systems, final state only: registers for phi, shared memory for the
 // coefficient arrays (xsq_swag_fast.cuh).  64-thread CTAs: 47.6 KB of
 // coefficient storage each, four per SM.
+template <class R, int BLOCK, int MINB, int MAXREG = 0>
+static int launch_swag_fast_geom(const RkDev& P, cudaStream_t st) {
+#ifdef XSQ_SWAG_GEOMETRY_SWEEP
+    auto kern = MAXREG ? swag_fast_maxreg<R, BLOCK, MAXREG ? MAXREG : 255> : swag_fast<R, BLOCK, MINB>;
+#else
+    auto kern = swag_fast<R, BLOCK, MINB>;
+#endif
+    int dev = 0, n_sm = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return XSQ_ERR_CUDA;
+    constexpr size_t smem = sizeof(SwagCoefs<BLOCK>);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+        return XSQ_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem) != cudaSuccess ||
+        occ < 1)
+        return XSQ_ERR_CUDA;
+    long long want = (P.n_lanes + BLOCK - 1) / BLOCK;
+    long long grid = (long long)n_sm * occ;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, BLOCK, smem, st>>>(P);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+}
+
 template <class R>
 static int launch_swag_fast(const RkDev& P, cudaStream_t st) {
     if constexpr (R::WARP || R::NL > 4) {
         return XSQ_ERR_UNSUPPORTED;
     } else {
-        constexpr int BLOCK = 64, MINB = 4;
-        auto kern = swag_fast<R, BLOCK, MINB>;
-        int dev = 0, n_sm = 0, occ = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return XSQ_ERR_CUDA;
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            return XSQ_ERR_CUDA;
-        constexpr size_t smem = sizeof(SwagCoefs<BLOCK>);
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-            return XSQ_ERR_CUDA;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem) != cudaSuccess ||
-            occ < 1)
-            return XSQ_ERR_CUDA;
-        long long want = (P.n_lanes + BLOCK - 1) / BLOCK;
-        long long grid = (long long)n_sm * occ;
-        if (want < grid) grid = want;
-        if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, BLOCK, smem, st>>>(P);
-        count_launch();
-        return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
+#ifdef XSQ_SWAG_GEOMETRY_SWEEP
+        const char* e = getenv("XSQ_SWAG_GEOM");
+        if (e && e[0] == '5') return launch_swag_fast_geom<R, 64, 4, 200>(P, st);
+        if (e && e[0] == 'b') return launch_swag_fast_geom<R, 32, 4, 184>(P, st);
+        if (e && e[0] == 'c') return launch_swag_fast_geom<R, 32, 4, 216>(P, st);
+#endif
+        return launch_swag_fast_geom<R, 64, 4>(P, st);
     }
 }
 

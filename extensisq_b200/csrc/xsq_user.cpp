@@ -241,12 +241,23 @@ std::string tableau_source(const xsq_tableau_t& t) {
 }
 
 std::string rhs_wrapper(const UserRhs& r) {
-    char buf[1024];
+    char buf[1400];
+    if (r.n_state > XSQ_MAX_LANE_STATE) {
+        // one warp per system (xsq_rhs.cuh, WideSystem): the entry returns one component
+        std::snprintf(
+            buf, sizeof buf,
+            "namespace xsq { namespace rhs {\nstruct UserComponent {\n"
+            "    __device__ __forceinline__ static double at(int i, double t, const double* y,\n"
+            "        const double* p) { return ::%s(i, t, y, p); }\n};\n"
+            "typedef WideSystem<%d, %d, UserComponent> User;\n} }\n",
+            r.entry.c_str(), r.n_state, r.n_param);
+        return buf;
+    }
     std::snprintf(
         buf, sizeof buf,
         "namespace xsq { namespace rhs {\nstruct User {\n"
         "    static constexpr int N = %d, NL = %d, NPAR = %d, NPL = %d;\n"
-        "    static constexpr bool WARP = false;\n"
+        "    static constexpr bool WARP = false, PADDED = false;\n"
         "    static constexpr int FLOPS = 0;\n"
         "    __device__ __forceinline__ static int comp(int k, int) { return k; }\n"
         "    __device__ __forceinline__ static void load_params(\n"
@@ -415,9 +426,11 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
     if (rhs >= XSQ_RHS_USER_BASE) {
         const size_t i = (size_t)(rhs - XSQ_RHS_USER_BASE);
         if (i >= g_rhs.size()) { set_detail("unknown rhs handle"); return XSQ_ERR_ARG; }
+        const bool wide = g_rhs[i].n_state > XSQ_MAX_LANE_STATE;
+        if (wide) body += "#include \"xsq_rhs.cuh\"\n";
         body += g_rhs[i].src + "\n" + rhs_wrapper(g_rhs[i]);
         rhsname = "User";
-        nl = g_rhs[i].n_state;
+        nl = wide ? (g_rhs[i].n_state + 31) / 32 : g_rhs[i].n_state;
         *key += "/U" + std::to_string(i);
     } else {
         const char* n = builtin_rhs_name(rhs);
@@ -506,13 +519,16 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)n_sm * (c.occ > 0 ? c.occ : 1);
-    const long long want = (P.n_lanes + 127) / 128;
+    int ns_user = 0;
+    if (rhs >= XSQ_RHS_USER_BASE) ns_user = g_rhs[rhs - XSQ_RHS_USER_BASE].n_state;
+    const bool warp = rhs == XSQ_RHS_NBODY32 || ns_user > XSQ_MAX_LANE_STATE;
+    const long long per_block = warp ? 4 : 128;          // systems per 128-thread CTA
+    const long long want = (P.n_lanes + per_block - 1) / per_block;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     RkDev Pc = P;
     void* args[] = {&Pc};
     {   // initialisation pass (f0 + h_start), thread per lane
-        const bool warp = rhs == XSQ_RHS_NBODY32;
         const long long threads = warp ? P.n_lanes * 32 : P.n_lanes;
         const unsigned igrid = (unsigned)((threads + 127) / 128);
         CUresult ci = g_api.LaunchKernel(c.init_fn, igrid ? igrid : 1, 1, 1, 128, 1, 1, 0,
@@ -521,9 +537,8 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
         if (ci != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_init) failed"); return XSQ_ERR_CUDA; }
     }
     // dense-output staging buffer (xsq_rk_core.cuh::eval_put): 4 x NL x 128
-    int ns = 0, npar = 0;
-    if (rhs >= XSQ_RHS_USER_BASE) { ns = g_rhs[rhs - XSQ_RHS_USER_BASE].n_state; (void)npar; }
-    else ns = 6;   // built-in rhs with a user tableau: NL <= 6
+    int ns = 6;    // built-in rhs with a user tableau: NL <= 6
+    if (rhs >= XSQ_RHS_USER_BASE) ns = ns_user > XSQ_MAX_LANE_STATE ? (ns_user + 31) / 32 : ns_user;
     const unsigned smem = P.n_eval > 0 ? (unsigned)(sizeof(double) * 4 * ns * 128) : 0;
     if (smem > 40u * 1024u) {
         // 48 KB is the default cap of static + dynamic shared memory; the kernel
@@ -595,8 +610,9 @@ int xsq_rhs_register_source(const char* cuda_src, const char* entry,
                             int32_t n_state, int32_t n_param,
                             int32_t* rhs_out) {
     if (!cuda_src || !entry || !rhs_out || n_state < 1 ||
-        n_state > XSQ_MAX_LANE_STATE || n_param < 0) {
-        set_detail("xsq_rhs_register_source: bad argument (1 <= n_state <= 16)");
+        n_state > XSQ_MAX_WARP_STATE || n_param < 0 ||
+        (n_state > XSQ_MAX_LANE_STATE && n_param > 16)) {
+        set_detail("xsq_rhs_register_source: bad argument (1 <= n_state <= 1024)");
         return XSQ_ERR_ARG;
     }
     std::lock_guard<std::mutex> g(g_mu);

@@ -32,6 +32,7 @@ extern "C" {
 #define XSQ_MAX_STAGES 18      /* Pr9: n_stages=17, +1 row for f(t+h, y_new) */
 #define XSQ_MAX_POLY 8         /* Pr9 interpolant has 8 columns             */
 #define XSQ_MAX_LANE_STATE 16  /* lane-per-system kernels: n_state <= 16    */
+#define XSQ_MAX_WARP_STATE 1024 /* warp-per-system user right-hand sides    */
 
 typedef enum xsq_err {
     XSQ_OK = 0,
@@ -200,7 +201,12 @@ int xsq_rhs_builtin(const char* name, int32_t* rhs_out, int32_t* n_state,
  *   __device__ void <entry>(double t, const double* y, const double* p,
  *                           double* dy);
  * It is compiled with NVRTC together with the solver template so the RHS
- * inlines into the persistent kernel. */
+ * inlines into the persistent kernel.  Systems up to XSQ_MAX_LANE_STATE states
+ * run one per thread.  Larger ones (up to XSQ_MAX_WARP_STATE; the reference
+ * takes any n, common.py:187-217) run one per WARP, and the entry returns one
+ * component of the derivative with the whole stage vector in view:
+ *   __device__ double <entry>(int i, double t, const double* y, const double* p);
+ * (n_param <= 16 there; no events). */
 int xsq_rhs_register_source(const char* cuda_src, const char* entry,
                             int32_t n_state, int32_t n_param,
                             int32_t* rhs_out);

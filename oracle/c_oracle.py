@@ -92,14 +92,26 @@ def devmath(fn, x):
     return out
 
 
+def set_warp_strided(on):
+    """Sum over the components in the order of a warp-per-system kernel with
+    component c in lane c % 32 (xsq_rhs.cuh WideSystem).  Returns the old mode."""
+    return load().xsq_oracle_set_warp_strided(1 if on else 0)
+
+
 class device_math:
     """with c_oracle.device_math(): ...   (restores the reference arithmetic)"""
 
+    def __init__(self, warp_strided=False):
+        self.warp_strided = warp_strided
+
     def __enter__(self):
         set_device_math(True)
+        if self.warp_strided:
+            set_warp_strided(True)
 
     def __exit__(self, *exc):
         set_device_math(False)
+        set_warp_strided(False)
 
 
 def _fill2(dst, src):
@@ -153,7 +165,8 @@ def make_tab(tab, sc_params=None):
 def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
              first_step=None, max_step=np.inf, sc_params=None,
              interpolant=None, t_eval=None, forced_h=None, max_steps=0,
-             n_threads=1, user_fn=None, n_param=None, nfev_stiff_detect=5000):
+             n_threads=1, user_fn=None, n_param=None, nfev_stiff_detect=5000,
+             user_fn_params=False):
     """Integrate N lanes with the C oracle.  y0 [N, n], params [N, p].
     `rhs`: built-in name, or None with `user_fn` = python callable
     f(t, y) -> dy (slow; single thread).  Returns a dict of numpy arrays."""
@@ -192,9 +205,11 @@ def rk_batch(tab, rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
 
         def _cb(tt, yp, pp, dyp):
             yv = np.ctypeslib.as_array(yp, (n,))
-            out = np.asarray(user_fn(tt, yv), dtype=float)
-            for i in range(n):
-                dyp[i] = out[i]
+            if user_fn_params:
+                out = user_fn(tt, yv, np.ctypeslib.as_array(pp, (p,)))
+            else:
+                out = user_fn(tt, yv)
+            np.ctypeslib.as_array(dyp, (n,))[:] = out
         cb = RHS_FN(_cb)
     ip = {None: 0, "free": 1, "low": 2, "best": 3}[interpolant]
     rc = lib.xsq_oracle_rk_batch(

@@ -56,7 +56,7 @@ int xsq_oracle_set_device_math(int on) {
 }
 
 #define MAXS 18
-#define MAXN 192
+#define MAXN 1024
 #define MAXPOL 8
 #define KROWS (MAXS + 4)
 
@@ -166,11 +166,40 @@ typedef struct {
     double havg;
 } lane_t;
 
-/* common.py:64-66, sequential accumulation */
+/* Order of the sums over the components.  Default: sequential, as NumPy's
+ * and the lane-per-system kernels'.  "warp strided" (xsq_oracle_set_warp_strided)
+ * repeats a warp-per-system kernel with component c in lane c % 32
+ * (xsq_rhs.cuh WideSystem): every lane accumulates its own components in
+ * turn, then the 32 partial sums are combined by the xor butterfly of
+ * sys_sum (xsq_rk_core.cuh). */
+static int g_warp_strided = 0;
+int xsq_oracle_set_warp_strided(int on) {
+    const int old = g_warp_strided;
+    g_warp_strided = on != 0;
+    return old;
+}
+typedef struct { double part[32]; } wacc_t;
+static void wacc_init(wacc_t* w) {
+    const int m = g_warp_strided ? 32 : 1;
+    for (int l = 0; l < m; ++l) w->part[l] = 0.0;
+}
+static double* wacc_at(wacc_t* w, int c) { return &w->part[g_warp_strided ? (c & 31) : 0]; }
+static double wacc_total(wacc_t* w) {
+    if (!g_warp_strided) return w->part[0];
+    for (int o = 16; o > 0; o >>= 1) {
+        double t[32];
+        for (int l = 0; l < 32; ++l) t[l] = w->part[l] + w->part[l ^ o];
+        for (int l = 0; l < 32; ++l) w->part[l] = t[l];
+    }
+    return w->part[0];
+}
+
+/* common.py:64-66 */
 static double rms(const double* x, int n) {
-    double s = 0.0;
-    for (int c = 0; c < n; ++c) s = fma(x[c], x[c], s);
-    return sqrt(s / (double)n);
+    wacc_t w;
+    wacc_init(&w);
+    for (int c = 0; c < n; ++c) { double* s = wacc_at(&w, c); *s = fma(x[c], x[c], *s); }
+    return sqrt(wacc_total(&w) / (double)n);
 }
 
 /* common.py:519-763 */
@@ -229,14 +258,17 @@ static double h_start(lane_t* L, double a, double b, int morder) {
         delf = rms(yp, n);
     }
     const double ydpb = fma(dfdub, fbnd, dfdxb);
-    double tolsum = 0.0, tolmin = INFINITY;
+    double tolmin = INFINITY;
+    wacc_t tolacc;
+    wacc_init(&tolacc);
     for (int c = 0; c < n; ++c) {
         const double etol = fma(L->rtol, fabs(y[c]), L->atol[c]);
         /* device: 10^(c log10 x) as 2^(c log2 x) with its own log2 / exp2 */
         const double te = g_device_math ? dev_log2(etol) : log10(etol);
-        tolsum += te;
+        *wacc_at(&tolacc, c) += te;
         tolmin = fmin(tolmin, te);
     }
+    const double tolsum = wacc_total(&tolacc);
     tolmin = fmin(tolmin, BIG);
     const double texp = 0.5 * (tolsum / (double)n + tolmin) / (double)(morder + 1);
     const double tolp = g_device_math ? dev_exp2(texp) : pow(10.0, texp);
@@ -295,14 +327,16 @@ static double scaled_norm(lane_t* L, const double* errv, const double* yref) {
 
 /* device form: sum((err * rcp(scale))^2); error_norm < 1  <=>  ss < n exactly */
 static double scaled_ss_dev(lane_t* L, const double* errv, const double* yref) {
-    double ss = 0.0;
+    wacc_t w;
+    wacc_init(&w);
     for (int c = 0; c < L->n; ++c) {
         const double big = fabs(yref[c]) > fabs(L->y[c]) ? yref[c] : L->y[c];
         const double scale = fma(L->rtol, fabs(big), L->atol[c]);
         const double q = errv[c] * dev_rcp_scale(scale);
-        ss = fma(q, q, ss);
+        double* ss = wacc_at(&w, c);
+        *ss = fma(q, q, *ss);
     }
-    return ss;
+    return wacc_total(&w);
 }
 
 /* xsq_rk_core.cuh ctl_factor */
@@ -435,9 +469,10 @@ static int emit(lane_t* L, double h, double t_new, const double* y_new,
 
 /* ---- stiffness diagnosis: common.py:370-516 and stiff_a..d (:824-1204) ---- */
 static double wdot(const double* a, const double* b, const double* wt, int n) {
-    double s = 0.0;
-    for (int c = 0; c < n; ++c) s = fma(a[c] / wt[c], b[c] / wt[c], s);
-    return s;
+    wacc_t w;
+    wacc_init(&w);
+    for (int c = 0; c < n; ++c) { double* s = wacc_at(&w, c); *s = fma(a[c] / wt[c], b[c] / wt[c], *s); }
+    return wacc_total(&w);
 }
 /* stiff_d: z ~ havg * J * v by a difference of f; returns <z, z> */
 static double jac_times(lane_t* L, const double* v, double havg, double x, const double* y,
