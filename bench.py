@@ -665,11 +665,14 @@ def main():
         s0.record(stream)
         solve_resident()
         s1.record(stream)
-        a_, b_, c_ = C.c_double(), C.c_double(), C.c_double()
-        if lib.xsq_profile_last(C.byref(a_), C.byref(b_), C.byref(c_)) == 0:
-            main_ms.append((a_.value, b_.value, c_.value))
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    # kernel times of the timed steps, read afterwards (no synchronisation in
+    # the loop: the host prepares step k+1 while step k runs)
+    for back in range(min(args.steps, 8) - 1, -1, -1):
+        a_, b_, c_ = C.c_double(), C.c_double(), C.c_double()
+        if lib.xsq_profile_get(back, C.byref(a_), C.byref(b_), C.byref(c_)) == 0:
+            main_ms.append((a_.value, b_.value, c_.value))
     lib.xsq_profile_enable(0)
     launches = int(lib.xsq_launch_count(0))
     kern_ms = [a.elapsed_time(b) for a, b in ev]

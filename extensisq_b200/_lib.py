@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("XSQ_LIB") or os.path.join(_HERE, "libxsq.so")
 XSQ_MAX_STAGES = 18
 XSQ_MAX_POLY = 8
 XSQ_MAX_LANE_STATE = 16
+XSQ_MAX_WARP_STATE = 1024
 XSQ_METHOD_USER = 100
 XSQ_RHS_USER_BASE = 1000
 
@@ -40,7 +41,7 @@ EXPORTS = [
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
     "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
-    "xsq_launch_count", "xsq_trim_memory", "xsq_profile_enable", "xsq_profile_last",
+    "xsq_launch_count", "xsq_trim_memory", "xsq_profile_enable", "xsq_profile_last", "xsq_profile_get",
     "xsq_fp64_peak",
 ]
 
@@ -176,6 +177,7 @@ def load():
     lib.xsq_trim_memory.argtypes = [C.c_int]
     lib.xsq_profile_enable.argtypes = [C.c_int]
     lib.xsq_profile_last.argtypes = [_dp, _dp, _dp]
+    lib.xsq_profile_get.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.xsq_launch_count.argtypes = [C.c_int]
     lib.xsq_fp64_peak.argtypes = [C.c_int, C.c_int32, _dp]
     if lib.xsq_abi_version() != 2:

@@ -110,13 +110,15 @@ static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
 // CUDA events on the launching stream around ens_init / the persistent kernel /
 // stiff_queue.  Used by bench.py for the roofline of the dominant kernel.
 static std::atomic<int> g_profile{0};
-static cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-static bool g_prof_valid = false;
+static constexpr int kProfRing = 8;             // the last 8 profiled solves
+static cudaEvent_t g_prof_ev[kProfRing][4] = {};
+static long long g_prof_count = 0;
 static void prof_mark(int i, cudaStream_t st) {
     if (!g_profile.load(std::memory_order_relaxed)) return;
-    if (!g_prof_ev[i]) cudaEventCreate(&g_prof_ev[i]);
-    cudaEventRecord(g_prof_ev[i], st);
-    if (i == 3) g_prof_valid = true;
+    cudaEvent_t* ev = g_prof_ev[g_prof_count % kProfRing];
+    if (!ev[i]) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[i], st);
+    if (i == 3) ++g_prof_count;
 }
 
 static int dispatch(int method, int rhs, int events, const RkDev& P, const MethodInfo& mi,
@@ -466,21 +468,29 @@ int xsq_trim_memory(int device) {
 
 int xsq_profile_enable(int on) {
     g_profile.store(on ? 1 : 0);
-    if (!on) g_prof_valid = false;
+    if (!on) g_prof_count = 0;
     return XSQ_OK;
 }
 
-int xsq_profile_last(double* ms_init, double* ms_main, double* ms_probe) {
-    if (!g_prof_valid) { g_detail = "no profiled solve"; return XSQ_ERR_ARG; }
-    XSQ_CUDA(cudaEventSynchronize(g_prof_ev[3]));
+int xsq_profile_get(int back, double* ms_init, double* ms_main, double* ms_probe) {
+    if (back < 0 || back >= kProfRing || back >= g_prof_count) {
+        g_detail = "no such profiled solve";
+        return XSQ_ERR_ARG;
+    }
+    cudaEvent_t* ev = g_prof_ev[(g_prof_count - 1 - back) % kProfRing];
+    XSQ_CUDA(cudaEventSynchronize(ev[3]));
     float a = 0, b = 0, c = 0;
-    XSQ_CUDA(cudaEventElapsedTime(&a, g_prof_ev[0], g_prof_ev[1]));
-    XSQ_CUDA(cudaEventElapsedTime(&b, g_prof_ev[1], g_prof_ev[2]));
-    XSQ_CUDA(cudaEventElapsedTime(&c, g_prof_ev[2], g_prof_ev[3]));
+    XSQ_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    XSQ_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+    XSQ_CUDA(cudaEventElapsedTime(&c, ev[2], ev[3]));
     if (ms_init) *ms_init = a;
     if (ms_main) *ms_main = b;
     if (ms_probe) *ms_probe = c;
     return XSQ_OK;
+}
+
+int xsq_profile_last(double* ms_init, double* ms_main, double* ms_probe) {
+    return xsq_profile_get(0, ms_init, ms_main, ms_probe);
 }
 
 int64_t xsq_launch_count(int reset) {

@@ -50,6 +50,30 @@ __device__ void xsq_sens_rhs(double t, const double* Y, const double* p, double*
 """
 
 
+def _combined_source_wide(src, names, ny, npar):
+    """The same combined system, one component per call (xsq_rhs.cuh WideSystem:
+    ny (1 + np) > 16 states, a warp per system).  Every component evaluates the
+    user's functions in full; a system this wide has few states per thread."""
+    f, j, d = names
+    return src + f"""
+__device__ double xsq_sens_rhs(int i, double t, const double* Y, const double* p) {{
+    if (i < {ny}) {{
+        double dy[{ny}];
+        {f}(t, Y, p, dy);
+        return dy[i];
+    }}
+    const int q = (i - {ny}) / {ny}, r = (i - {ny}) % {ny};
+    double J[{ny * ny}], D[{ny * npar}];
+    {j}(t, Y, p, J);
+    {d}(t, Y, p, D);
+    const double fac = p[q] != 0.0 ? fabs(p[q]) : 1.0;
+    double acc = 0.0;
+    for (int k = 0; k < {ny}; ++k) acc = fma(J[r * {ny} + k], Y[{ny} + k + {ny} * q], acc);
+    return fma(fac, D[r * {npar} + q], acc);
+}}
+"""
+
+
 def sens_forward(src, t_span, y0, dy0dp, p, atol=1e-6, rtol=1e-3, method=BS5,
                  t_eval=None, names=("fun", "jac", "dfdp"), device=None, **options):
     """``src``: CUDA source defining
@@ -70,9 +94,11 @@ def sens_forward(src, t_span, y0, dy0dp, p, atol=1e-6, rtol=1e-3, method=BS5,
     if dy0dp.shape[-2:] != (ny, npar):                 # sensitivity.py:139-140
         raise AssertionError("`dy0dp` should be a array of size (ny, np)")
     dy0dp = np.broadcast_to(dy0dp, (N, ny, npar))
-    if ny * (1 + npar) > _lib.XSQ_MAX_LANE_STATE:
+    wide = ny * (1 + npar) > _lib.XSQ_MAX_LANE_STATE
+    if ny * (1 + npar) > _lib.XSQ_MAX_WARP_STATE or (wide and npar > 16):
         raise ValueError(f"ny * (np + 1) = {ny * (1 + npar)} exceeds the "
-                         f"{_lib.XSQ_MAX_LANE_STATE} states of a lane-per-system kernel")
+                         f"{_lib.XSQ_MAX_WARP_STATE} states (16 parameters) of a "
+                         "warp-per-system kernel")
     if t_eval is not None and float(t_eval[-1]) != float(t_span[1]):
         raise AssertionError("if `t_eval` is used, the last point should be "
                              "t_span[-1]")                 # sensitivity.py:143-145
@@ -85,7 +111,8 @@ def sens_forward(src, t_span, y0, dy0dp, p, atol=1e-6, rtol=1e-3, method=BS5,
                              "of length Ny")
     key = (src, tuple(names), ny, npar)
     if key not in _cache:
-        _cache[key] = DeviceRHS.from_source(_combined_source(src, names, ny, npar),
+        gen = _combined_source_wide if wide else _combined_source
+        _cache[key] = DeviceRHS.from_source(gen(src, names, ny, npar),
                                             "xsq_sens_rhs", ny * (1 + npar), npar)
     fac = np.where(p != 0.0, np.abs(p), 1.0)                       # [N, np]
     total_y0 = np.concatenate(

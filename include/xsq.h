@@ -333,6 +333,10 @@ int xsq_trim_memory(int device);
  * the dominant kernel is quoted on ITS duration. */
 int xsq_profile_enable(int on);
 int xsq_profile_last(double* ms_init, double* ms_main, double* ms_probe);
+/* ... and of the solve `back` calls before the last one (0 = the last; the
+ * library keeps 8), so that a benchmark can read the kernel times of a timed
+ * loop afterwards instead of synchronising inside it. */
+int xsq_profile_get(int back, double* ms_init, double* ms_main, double* ms_probe);
 
 /* Kernel-launch bookkeeping for benchmarks: number of kernels this library
  * launched since the last reset. */

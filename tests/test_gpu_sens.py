@@ -68,3 +68,65 @@ def test_sens_forward_argument_checks():
         xb.sens_forward(src, (0.0, 1.0), [[1.0, 1.0, 1.0]], np.zeros((2, 3)), [10.0, 28.0, 2.0])
     with pytest.raises(ValueError):      # 6 * (1 + 3) states do not fit one lane
         xb.sens_forward(src, (0.0, 1.0), [[1.0] * 6], np.zeros((6, 3)), [10.0, 28.0, 2.0])
+
+
+CHAIN_SRC = """
+// a chain of 6 compartments with 5 rate constants: y0 -> y1 -> ... -> y5
+__device__ void fun(double t, const double* y, const double* p, double* dy) {
+    dy[0] = -p[0] * y[0];
+    for (int i = 1; i < 5; ++i) dy[i] = p[i - 1] * y[i - 1] - p[i] * y[i];
+    dy[5] = p[4] * y[4];
+}
+__device__ void jac(double t, const double* y, const double* p, double* J) {
+    for (int k = 0; k < 36; ++k) J[k] = 0.0;
+    for (int i = 0; i < 5; ++i) { J[i * 6 + i] = -p[i]; J[(i + 1) * 6 + i] = p[i]; }
+}
+__device__ void dfdp(double t, const double* y, const double* p, double* D) {
+    for (int k = 0; k < 30; ++k) D[k] = 0.0;
+    for (int q = 0; q < 5; ++q) { D[q * 5 + q] = -y[q]; D[(q + 1) * 5 + q] = y[q]; }
+}
+"""
+
+
+def test_sens_forward_beyond_16_states_runs_a_warp_per_system():
+    """ny (1 + np) = 36 combined states: the generated right-hand side is
+    compiled for the warp-per-system kernel (xsq_rhs.cuh WideSystem); against
+    the restated reference per lane."""
+    def fun(t, y, *p):
+        p = np.asarray(p)
+        d = np.empty(6)
+        d[0] = -p[0] * y[0]
+        d[1:5] = p[:4] * y[:4] - p[1:5] * y[1:5]
+        d[5] = p[4] * y[4]
+        return d
+
+    def jac(t, y, *p):
+        J = np.zeros((6, 6))
+        for i in range(5):
+            J[i, i] = -p[i]
+            J[i + 1, i] = p[i]
+        return J
+
+    def dfdp(t, y, *p):
+        D = np.zeros((6, 5))
+        for q in range(5):
+            D[q, q] = -y[q]
+            D[q + 1, q] = y[q]
+        return D
+
+    N = 6
+    P = np.array([1.0, 0.7, 1.3, 0.4, 0.9])[None, :] * (1.0 + 0.1 * np.arange(N))[:, None]
+    y0 = np.tile([1.0, 0.0, 0.0, 0.0, 0.0, 0.0], (N, 1))
+    kw = dict(rtol=1e-8, atol=1e-10)
+    sens, yf, sol = xb.sens_forward(CHAIN_SRC, (0.0, 3.0), y0, np.zeros((6, 5)), P,
+                                    method=xb.Ts5, **kw)
+    torch.cuda.synchronize()
+    assert (sol.status == 0).all()
+    assert sol.y_final.shape == (N, 36)
+    for i in range(N):
+        so, yo, _ = SO.sens_forward(TABS["Ts5"], fun, (0.0, 3.0), y0[i], jac, dfdp,
+                                    np.zeros((6, 5)), P[i], **kw)
+        np.testing.assert_allclose(yf[i].cpu().numpy(), yo, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(sens[i].cpu().numpy(), so, rtol=1e-5, atol=1e-8)
+    # first compartment: y0(t) = exp(-p0 t), dy0/dp0 = -t exp(-p0 t)
+    np.testing.assert_allclose(sens[:, 0, 0].cpu().numpy(), -3.0 * np.exp(-3.0 * P[:, 0]), rtol=1e-6)

@@ -180,8 +180,8 @@ def test_device_events_and_sens_forward_argument_checks_need_no_gpu():
         xb.DeviceEvents.from_source(src, "event", 9)
     with pytest.raises(AssertionError):                  # dy0dp must be (ny, np)
         xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0, 1.0]], np.zeros((2, 3)), [1.0, 2.0, 3.0])
-    with pytest.raises(ValueError):                      # ny (np + 1) > 16 states per lane
-        xb.sens_forward("", (0.0, 1.0), [[1.0] * 6], np.zeros((6, 3)), [1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):                      # ny (np + 1) > 1024 states per warp
+        xb.sens_forward("", (0.0, 1.0), [[1.0] * 300], np.zeros((300, 3)), [1.0, 2.0, 3.0])
     with pytest.raises(AssertionError):                  # t_eval must end at t_span[1]
         xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0]], np.zeros((2, 1)), [1.0], t_eval=[0.0, 0.5])
     with pytest.raises(AssertionError):                  # rtol must be a float
