@@ -437,10 +437,13 @@ def run_c5(xb, lib, dev, rank, world, dist, quick=False):
         out["checksum_rel_err_vs_1rank"] = relerr
         out["strong_speedup_vs_1gpu"] = c1[2] / ms
         out["strong_efficiency"] = c1[2] / ms / world
-        out["limit"] = ("per stage every rank runs one k_peer_sync handshake (remote flag store + "
-                        "spin, ~5-10 us over NVLink) before its stage kernel; at 16384^2 / N rows "
-                        "the stage itself takes 1.5 ms / N, so the handshake is what the strong "
-                        "curve loses; the weak curve (0.19 ms stages) loses the same few us")
+        out["limit"] = ("the neighbour barrier is fused into the stage kernels (block (0,0) posts a "
+                        "release.sys flag to both neighbours, only the first and last block row "
+                        "acquire); what the strong curve loses is (a) the boundary CTAs' wait, a few "
+                        "us per stage against a stage of 1.8 ms / N, and (b) the slab's share of L2 "
+                        "reuse: a full 16384-row grid leaves ~9% of its reads in the 126 MB L2 "
+                        "(frac 0.91-0.98), a 2048-row slab ~all of the rotating buffers' overlap "
+                        "(frac 0.99); one NCCL all-gather of a double per step attempt")
     # (4) the stage kernel alone on the 8-GPU slab: HBM roofline
     ms_stage = C.c_double()
     if lib.xsq_rkc_stage_bench(nx, 2048, 40, C.byref(ms_stage), None) == 0:
