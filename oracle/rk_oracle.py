@@ -73,6 +73,13 @@ class Tableau:
         for k in ("max_factor", "min_factor", "safety"):      # CKdisc
             if k in d:
                 setattr(self, k, float(d[k]))
+        for k in ("Ap", "Bp", "Ep"):                          # Runge-Kutta-Nystrom
+            if k in d:
+                setattr(self, k, _unhex(d[k]))
+        if "Bp" in d:
+            self.stbre, self.stbim = d.get("stbre"), d.get("stbim")
+            self.velocity_dependent = d["velocity_dependent"]
+            self.embedded_scale = d.get("embedded_scale", 1.0)
         for k in ("A", "B", "C", "E", "P", "E_pre", "B_scale_pre", "C_extra",
                   "A_extra", "Plow", "Pbest", "B_assess", "E_assess",
                   "C_fallback", "B_fallback", "E_fallback"):
@@ -85,12 +92,23 @@ class Tableau:
             self.A_extra = np.asfortranarray(self.A_extra)
         self.variant = {"BS5": "bs5", "CFMR7osc": "cfmr",
                         "CKdisc": "ckdisc"}.get(self.name, "generic")
+        if "Bp" in d:
+            self.variant = "nystrom"
+            if self.embedded_scale != 1.0:         # murua.py:224-227, scale_embedded=True
+                self.E = self.E * self.embedded_scale
+                self.Ep = self.Ep * self.embedded_scale
 
 
 def load_tableaux(path=_TABLEAUX_JSON):
     with open(path) as fh:
         raw = json.load(fh)["tableaux"]
     return {k: Tableau(v) for k, v in raw.items()}
+
+
+def load_tableaux_rkn(path=None):
+    """Fi4N, Fi5N, Mu5Nmb, MR6NN (extensisq/fine.py, murua.py, mikkawy.py)."""
+    path = path or os.path.join(os.path.dirname(_TABLEAUX_JSON), "tableaux_rkn.json")
+    return load_tableaux(path)
 
 
 def load_ckdisc(path=_TABLEAUX_JSON):
@@ -396,11 +414,18 @@ def _diagnose_stiffness(st):                      # common.py:370-516
     s = tab.n_stages
     avgy = 0.5 * (np.abs(st.y) + np.abs(st.y_old))
     wt = np.maximum(avgy, sqrt(np.finfo(float).tiny))
-    v0 = np.atleast_1d(st.h_previous * (st.K[:s + st.FSAL].T @
-                                        tab.E[:s + st.FSAL]))
-    stif, rootre, root = stiff_probe(
-        st.fun, st.t, st.y, st.h_previous, st.havg, st.t_bound,
-        st.nfev_stiff_detect, wt, st.f, v0, s)
+    nystrom = tab.variant == "nystrom"
+    if nystrom:                                   # common.py:1372-1386
+        v0 = np.atleast_1d(_rkn_estimate_error(st, st.h_previous))
+        stif, rootre, root = stiff_probe(
+            st.fun_first_order, st.t, st.y, st.h_previous, st.havg, st.t_bound,
+            st.nfev_stiff_detect, wt, np.concatenate((st.y[st.nh:], st.f)), v0, s)
+    else:
+        v0 = np.atleast_1d(st.h_previous * (st.K[:s + st.FSAL].T @
+                                            tab.E[:s + st.FSAL]))
+        stif, rootre, root = stiff_probe(
+            st.fun, st.t, st.y, st.h_previous, st.havg, st.t_bound,
+            st.nfev_stiff_detect, wt, st.f, v0, s)
     st.n_stiff_tests += 1
     if root is not None:
         root1, root2, rho = root
@@ -413,6 +438,9 @@ def _diagnose_stiffness(st):                      # common.py:370-516
                 stif = False
             elif abs(root1[1]) > abs(root1[0]) * tab.tanang:
                 stif = None
+            elif nystrom:                         # common.py:1412-1413
+                stif = (abs(root1[0]) >= 0.85 * tab.stbre or
+                        abs(root1[1]) >= 0.9 * tab.stbim)
             else:
                 stif = rho >= 0.9 * tab.stbrad
     if stif is None:
@@ -526,6 +554,56 @@ class RKState:
         return np.asarray(self._fun(t, y), dtype=float)
 
 
+class RKNState(RKState):
+    """RungeKuttaNystrom.__init__ (common.py:1240-1277) on top of RungeKutta's:
+    `fun` is the first order form [v, a] = fun(t, [x, v]); K holds accelerations."""
+
+    def __init__(self, tab, fun, t0, y0, t_bound, **kw):
+        stiff = kw.pop("nfev_stiff_detect", 5000)
+        super().__init__(tab, fun, t0, y0, t_bound, nfev_stiff_detect=0, **kw)
+        if not (isinstance(stiff, int) and stiff >= 0):
+            raise ValueError("`nfev_stiff_detect` must be a non-negative integer.")
+        self.nfev_stiff_detect = stiff            # common.py:1225-1238
+        if tab.stbre is None or tab.stbim is None or tab.tanang is None:
+            self.nfev_stiff_detect = 0
+        n = self.nh = self.y.size // 2
+        msg = ('This method is for second order problems'
+               ' and `fun` should have signature: [v, a] = fun(t, [x, v]).')
+        if (self.y.size % 2) or not np.all(self.y[n:] == self.f[:n]):
+            raise AssertionError(msg)
+        elif np.all(self.y[n:] == self.y[:n]):
+            y_test = self.y.copy()
+            y_test[n:] *= 1 + 1e-8
+            y_test[n:] += 1e-8
+            if not np.all(np.asarray(self._fun(t0, y_test))[:n] == y_test[n:]):
+                raise AssertionError(msg)
+        if not tab.velocity_dependent:
+            y_test = self.y.copy()
+            y_test[n:] *= 1 + 1e-8
+            y_test[n:] += 1e-8
+            if not np.all(np.asarray(self._fun(t0, y_test))[n:] == self.f[n:]):
+                raise AssertionError("This method is for velocity independent ODEs, "
+                                     "but `fun` seems velocity dependent.")
+        self.Ap = tab.Ap                          # zeros for a velocity independent method
+        s = tab.n_stages
+        if tab.Ep[s] != 0.:
+            self.FSAL = 1
+        self.K_ext = np.empty((s + 1, n))
+        self.K = self.K_ext
+        self.f = self.f[n:]
+        self._first = self._fun
+
+    def fun_first_order(self, t, y):
+        # the reference keeps the caller's raw function here (common.py:1271), so
+        # the evaluations of the stiffness probe are NOT counted in nfev
+        return np.asarray(self._first(t, y), dtype=float)
+
+    def fun(self, t, y):
+        self.nfev += 1
+        out = np.asarray(self._fun(t, y), dtype=float)
+        return out[self.nh:] if hasattr(self, "_first") else out
+
+
 def _reassess_stepsize(st):                       # common.py:310-331
     h_abs = st.h_abs
     min_step = max(st.h_min_a * (abs(st.t) + h_abs), st.h_min_b)
@@ -543,12 +621,35 @@ def _reassess_stepsize(st):                       # common.py:310-331
 
 
 def _rk_stage(st, h, i):                          # common.py:353-356
+    if st.tab.variant == "nystrom":               # common.py:1279-1285
+        n = st.nh
+        dt = st.tab.C[i] * h
+        du = (st.K[:i, :].T @ st.tab.A[i, :i]) * h**2 + dt * st.y[n:]
+        dv = (st.K[:i, :].T @ st.Ap[i, :i]) * h
+        st.K[i] = st.fun(st.t + dt, st.y + np.concatenate((du, dv)))
+        return
     dy = h * (st.K[:i, :].T @ st.tab.A[i, :i])
     st.K[i] = st.fun(st.t + st.tab.C[i] * h, st.y + dy)
 
 
+def _rkn_estimate_error(st, h):                   # common.py:1303-1309
+    s = st.tab.n_stages
+    eu = (st.K[:s + st.FSAL, :].T @ st.tab.E[:s + st.FSAL]) * h**2
+    ev = (st.K[:s + st.FSAL, :].T @ st.tab.Ep[:s + st.FSAL]) * h
+    return np.concatenate((eu, ev))
+
+
 def _comp_sol_err(st, y, h):                      # common.py:333-351
     s = st.tab.n_stages
+    if st.tab.variant == "nystrom":               # common.py:1287-1301
+        n = st.nh
+        du = (st.K[:s, :].T @ st.tab.B) * h**2 + h * st.y[n:]
+        dv = (st.K[:s, :].T @ st.tab.Bp) * h
+        y_new = y + np.concatenate((du, dv))
+        scale = calculate_scale(st.atol, st.rtol, y, y_new)
+        if st.FSAL:
+            st.K[s, :] = st.fun(st.t + h, y_new)
+        return y_new, norm(_rkn_estimate_error(st, h) / scale)
     y_new = y + h * (st.K[:s].T @ st.tab.B)
     scale = calculate_scale(st.atol, st.rtol, y, y_new)
     if st.FSAL:
@@ -930,13 +1031,14 @@ def rk_solve(tab, fun, t_span, y0, rtol=1e-3, atol=1e-6, max_step=np.inf,
         if forced_h is not None or sc_params is not None:
             raise ValueError("CKdisc has no forced steps / sc_params")
         nfev_stiff_detect = 0                      # cash.py:238-240
+    RKState_ = RKNState if tab.variant == "nystrom" else RKState
     if forced_h is not None:
-        st = RKState(tab, fun, t0, y0, copysign(np.inf, tf - t0),
+        st = RKState_(tab, fun, t0, y0, copysign(np.inf, tf - t0),
                      rtol=rtol, atol=atol, first_step=forced_h[0],
                      sc_params=sc_params, interpolant=interpolant,
                      nfev_stiff_detect=0)
     else:
-        st = RKState(tab, fun, t0, y0, tf, max_step=max_step, rtol=rtol,
+        st = RKState_(tab, fun, t0, y0, tf, max_step=max_step, rtol=rtol,
                      atol=atol, first_step=first_step, sc_params=sc_params,
                      interpolant=interpolant,
                      nfev_stiff_detect=nfev_stiff_detect)
