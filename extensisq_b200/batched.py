@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .tableaux import RungeKutta, SWAG
+from .tableaux import RungeKutta, RungeKuttaNystrom, SWAG
 
 __all__ = ["DeviceRHS", "BatchedOdeResult", "solve_ivp_batched", "NFS"]
 
@@ -266,6 +266,21 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
             raise ValueError("events do not apply to forced_steps")
         if not (isinstance(max_event_records, int) and max_event_records > 0):
             raise ValueError("`max_event_records` must be a positive integer")
+    is_rkn = not is_swag and issubclass(method, RungeKuttaNystrom)
+    if is_rkn:
+        # RungeKuttaNystrom.__init__, common.py:1240-1277
+        if method._xsq_method is None:
+            raise ValueError("user defined Runge-Kutta-Nystrom tableaux are not supported")
+        if fun.n_state % 2:
+            raise AssertionError('This method is for second order problems'
+                                 ' and `fun` should have signature: [v, a] = fun(t, [x, v]).')
+        if t_eval is not None or events is not None or interpolant is not None:
+            raise ValueError("Runge-Kutta-Nystrom methods return the final state only on the "
+                             "device (no t_eval / events / interpolant)")
+        if not method.velocity_dependent and fun.name in ("vanderpol", "arenstorf"):
+            raise AssertionError("This method is for velocity independent ODEs, "
+                                 "but `fun` seems velocity dependent.")
+        nfev_stiff_detect = 0      # the rectangular-domain diagnosis (common.py:1322) is host-only
     is_ckdisc = not is_swag and getattr(method, "_xsq_method", None) == _lib.METHOD_IDS["CKdisc"]
     if is_ckdisc:
         # CKdisc.__init__(fun, t0, y0, t_bound, **extraneous) passes

@@ -101,6 +101,10 @@ static int launch_method(int method, int rhs, const RkDev& P, cudaStream_t st,
         case XSQ_PR9: return launch_Pr9(rhs, P, st, info);
         case XSQ_CFMR7OSC: return launch_CFMR7osc(rhs, P, st, info);
         case XSQ_CKDISC: return launch_CKdisc(rhs, P, st, info);
+        case XSQ_FI4N: return launch_Fi4N(rhs, P, st, info);
+        case XSQ_FI5N: return launch_Fi5N(rhs, P, st, info);
+        case XSQ_MU5NMB: return launch_Mu5Nmb(rhs, P, st, info);
+        case XSQ_MR6NN: return launch_MR6NN(rhs, P, st, info);
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }

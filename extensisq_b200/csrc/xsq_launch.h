@@ -21,6 +21,10 @@ XSQ_DECL_LAUNCH(Pr8)
 XSQ_DECL_LAUNCH(Pr9)
 XSQ_DECL_LAUNCH(CFMR7osc)
 XSQ_DECL_LAUNCH(CKdisc)
+XSQ_DECL_LAUNCH(Fi4N)
+XSQ_DECL_LAUNCH(Fi5N)
+XSQ_DECL_LAUNCH(Mu5Nmb)
+XSQ_DECL_LAUNCH(MR6NN)
 #undef XSQ_DECL_LAUNCH
 
 int launch_swag(int rhs, const RkDev& P, cudaStream_t st);

@@ -36,6 +36,10 @@ inline bool method_info(int method, MethodInfo* mi) {
         case XSQ_PR9: *mi = info_of<tab::Pr9>(); return true;
         case XSQ_CFMR7OSC: *mi = info_of<tab::CFMR7osc>(); return true;
         case XSQ_CKDISC: *mi = info_of<tab::CKdisc>(); return true;
+        case XSQ_FI4N: *mi = info_of<tab::Fi4N>(); return true;
+        case XSQ_FI5N: *mi = info_of<tab::Fi5N>(); return true;
+        case XSQ_MU5NMB: *mi = info_of<tab::Mu5Nmb>(); return true;
+        case XSQ_MR6NN: *mi = info_of<tab::MR6NN>(); return true;
         default: return false;
     }
 }
@@ -78,6 +82,17 @@ inline int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     if (a->n_state != ns || a->n_param != np) {
         set_detail("n_state/n_param do not match the rhs");
         return XSQ_ERR_ARG;
+    }
+    if (a->method >= XSQ_FI4N && a->method <= XSQ_MR6NN) {
+        if (ns % 2) {                               // common.py:1246-1250
+            set_detail("This method is for second order problems and `fun` should have "
+                       "signature: [v, a] = fun(t, [x, v]).");
+            return XSQ_ERR_ARG;
+        }
+        if (a->n_eval > 0 || a->events != 0 || ns > XSQ_MAX_LANE_STATE * 0 + 192) {
+            set_detail("Runge-Kutta-Nystrom methods: final state only (no t_eval, no events)");
+            return XSQ_ERR_UNSUPPORTED;
+        }
     }
     if (a->n_lanes < 0) { set_detail("n_lanes < 0"); return XSQ_ERR_ARG; }
     if (a->n_lanes > 0 &&

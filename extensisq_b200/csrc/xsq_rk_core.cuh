@@ -899,6 +899,35 @@ struct Lane {
     template <int I>
     __device__ __forceinline__ void stage(double (&K)[KROWS][NL], double h) {
         double ys[NL];
+        if constexpr (Tab::VARIANT == tab::NYSTROMV) {
+            // RungeKuttaNystrom._rk_stage, common.py:1279-1285.  Slots [0, NH) of a
+            // thread are positions, [NH, NL) their velocities; rows of K are whole
+            // derivative vectors of which only the acceleration half is read.
+            constexpr int NH = NL / 2;
+            const double dt = Tab::cv(I) * h, hh = h * h;
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+                double au = 0.0, av = 0.0;
+                bool fu = true, fv = true;
+#pragma unroll
+                for (int j = 0; j < I; ++j) {
+                    if (Tab::a(I, j) != 0.0) {
+                        const double a = Tab::av(I, j);
+                        au = fu ? a * K[j][NH + c] : fma(a, K[j][NH + c], au);
+                        fu = false;
+                    }
+                    if (Tab::ap(I, j) != 0.0) {
+                        const double a = Tab::apv(I, j);
+                        av = fv ? a * K[j][NH + c] : fma(a, K[j][NH + c], av);
+                        fv = false;
+                    }
+                }
+                ys[c] = y[c] + (au * hh + dt * y[NH + c]);
+                ys[NH + c] = y[NH + c] + av * h;
+            }
+            R::f(t + dt, ys, prm, K[I]);
+            return;
+        }
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
             double acc = 0.0;
@@ -1504,7 +1533,8 @@ struct Lane {
 #pragma unroll
         for (int c = 0; c < NL; ++c) K[0][c] = f[c];
 
-        constexpr bool EARLY = Tab::VARIANT != tab::GENERIC;
+        constexpr bool EARLY = Tab::VARIANT == tab::BS5V || Tab::VARIANT == tab::CFMRV;
+        constexpr bool NYSTROM = Tab::VARIANT == tab::NYSTROMV;
         constexpr int NFIRST = EARLY ? S - 1 : S;
         stages<1, NFIRST>(K, h);
 
@@ -1543,6 +1573,34 @@ struct Lane {
         }
         if (!pre_reject) {
             if constexpr (EARLY) stage<S - 1>(K, h);
+            if constexpr (NYSTROM) {
+                // RungeKuttaNystrom._comp_sol_err / _estimate_error, common.py:1287-1309
+                constexpr int NH = NL / 2;
+                const double hh = h * h;
+#pragma unroll
+                for (int c = 0; c < NH; ++c) {
+                    double sb = 0.0, sp = 0.0;
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        if (Tab::b(i) != 0.0) sb = fma(Tab::bv(i), K[i][NH + c], sb);
+                        if (Tab::bp(i) != 0.0) sp = fma(Tab::bpv(i), K[i][NH + c], sp);
+                    }
+                    y_new[c] = y[c] + (sb * hh + h * y[NH + c]);
+                    y_new[NH + c] = y[NH + c] + sp * h;
+                }
+                if constexpr (Tab::FSAL) R::f(t_new, y_new, prm, K[S]);
+#pragma unroll
+                for (int c = 0; c < NH; ++c) {
+                    double se = 0.0, sp = 0.0;
+#pragma unroll
+                    for (int i = 0; i < S + Tab::FSAL; ++i) {
+                        if (Tab::e(i) != 0.0) se = fma(Tab::ev(i), K[i][NH + c], se);
+                        if (Tab::ep(i) != 0.0) sp = fma(Tab::epv(i), K[i][NH + c], sp);
+                    }
+                    errv[c] = se * hh;
+                    errv[NH + c] = sp * h;
+                }
+            } else {
             // _comp_sol_err, common.py:341-351
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
@@ -1562,6 +1620,7 @@ struct Lane {
                     if (Tab::e(i) != 0.0) se = fma(Tab::ev(i), K[i][c], se);
                 }
                 errv[c] = h * se;
+            }
             }
             ss = scaled_ss(P, errv, y_new, lane);
         }
@@ -1605,7 +1664,7 @@ struct Lane {
         if (!accept) {
             step_rejected = true;
             ++n_rej;
-            if (Tab::VARIANT != tab::GENERIC && pre_reject) ++n_pre;
+            if (EARLY && pre_reject) ++n_pre;
             // ++jflstp (common.py:284) is ++n_rej, see StiffState
             if (bad) return LANE_OVERFLOW;                   // common.py:286
             if (h_abs < min_step) return LANE_TOO_SMALL;     // common.py:234

@@ -154,16 +154,37 @@ static int launch_one(const RkDev& P, cudaStream_t st, LaunchInfo* info) {
     return cudaGetLastError() == cudaSuccess ? XSQ_OK : XSQ_ERR_CUDA;
 }
 
+// One entry per tableau: the right-hand sides it is instantiated for.
+template <class T>
+static int launch_tab(int rhs, const RkDev& P, cudaStream_t st, LaunchInfo* info) {
+    if constexpr (T::VARIANT == tab::NYSTROMV) {
+        // second order problems only: the built-in Van der Pol and Arenstorf
+        // systems depend on the velocity (not for MR6NN, mikkawy.py), the
+        // N-body problem does not
+        switch (rhs) {
+            case XSQ_RHS_VANDERPOL:
+                if constexpr (T::VELOCITY_DEPENDENT) return launch_one<T, rhs::VanDerPol>(P, st, info);
+                else return XSQ_ERR_UNSUPPORTED;
+            case XSQ_RHS_ARENSTORF:
+                if constexpr (T::VELOCITY_DEPENDENT) return launch_one<T, rhs::Arenstorf>(P, st, info);
+                else return XSQ_ERR_UNSUPPORTED;
+            case XSQ_RHS_NBODY32: return launch_one<T, rhs::NBody32>(P, st, info);
+            default: return XSQ_ERR_UNSUPPORTED;
+        }
+    } else {
+        switch (rhs) {
+            case XSQ_RHS_LORENZ63: return launch_one<T, rhs::Lorenz63>(P, st, info);
+            case XSQ_RHS_VANDERPOL: return launch_one<T, rhs::VanDerPol>(P, st, info);
+            case XSQ_RHS_ARENSTORF: return launch_one<T, rhs::Arenstorf>(P, st, info);
+            case XSQ_RHS_NBODY32: return launch_one<T, rhs::NBody32>(P, st, info);
+            default: return XSQ_ERR_UNSUPPORTED;
+        }
+    }
+}
+
 int XSQ_CAT(launch_, XSQ_INST_TAB)(int rhs, const RkDev& P, cudaStream_t st,
                                    LaunchInfo* info) {
-    using T = tab::XSQ_INST_TAB;
-    switch (rhs) {
-        case XSQ_RHS_LORENZ63: return launch_one<T, rhs::Lorenz63>(P, st, info);
-        case XSQ_RHS_VANDERPOL: return launch_one<T, rhs::VanDerPol>(P, st, info);
-        case XSQ_RHS_ARENSTORF: return launch_one<T, rhs::Arenstorf>(P, st, info);
-        case XSQ_RHS_NBODY32: return launch_one<T, rhs::NBody32>(P, st, info);
-        default: return XSQ_ERR_UNSUPPORTED;
-    }
+    return launch_tab<tab::XSQ_INST_TAB>(rhs, P, st, info);
 }
 
 }  // namespace xsq

@@ -158,6 +158,10 @@ const char* builtin_tab_name(int method) {
         case XSQ_PR9: return "Pr9";
         case XSQ_CFMR7OSC: return "CFMR7osc";
         case XSQ_CKDISC: return "CKdisc";
+        case XSQ_FI4N: return "Fi4N";
+        case XSQ_FI5N: return "Fi5N";
+        case XSQ_MU5NMB: return "Mu5Nmb";
+        case XSQ_MR6NN: return "MR6NN";
         default: return nullptr;
     }
 }
@@ -420,7 +424,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
         (void)mi;
         *key = n;
         s = 17;  // conservative default; refined below for built-ins
-        static const int ks[] = {6, 7, 6, 5, 10, 13, 17, 9, 6};
+        static const int ks[] = {6, 7, 6, 5, 10, 13, 17, 9, 6, 5, 6, 9, 6};
         s = ks[method];
     }
     if (rhs >= XSQ_RHS_USER_BASE) {

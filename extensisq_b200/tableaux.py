@@ -136,6 +136,52 @@ BUILTIN = {c.__name__: c for c in (Ts5, BS5, CK5, Me4, Pr7, Pr8, Pr9,
                                    CFMR7osc)}
 
 
+class RungeKuttaNystrom(RungeKutta):
+    """Base of the explicit Runge-Kutta-Nystrom methods for second order
+    problems in first order form ``[v, a] = fun(t, [x, v])`` (reference:
+    common.py:1207-1320).  Besides ``A, B, C, E`` (positions, with h**2) the
+    classes carry ``Ap, Bp, Ep`` (velocities, with h); ``Ap`` is all zero for a
+    method for velocity independent problems (``velocity_dependent = False``).
+    On the device: final state and counters (no ``t_eval``, no events, no
+    stiffness diagnosis)."""
+    Ap: np.ndarray = NotImplemented
+    Bp: np.ndarray = NotImplemented
+    Ep: np.ndarray = NotImplemented
+    stbre: float = NotImplemented
+    stbim: float = NotImplemented
+    velocity_dependent = True
+
+
+def _make_rkn(name, d):
+    scale = float(d.get("embedded_scale", 1.0))    # murua.py:224-227 (scale_embedded=True)
+    attrs = dict(
+        __doc__=f"{name} Runge-Kutta-Nystrom tableau; reference {d['source']}.",
+        n_stages=d["n_stages"], order=d["order"],
+        order_secondary=d["order_secondary"], sc_params=d["sc_params"],
+        stbre=d["stbre"], stbim=d["stbim"], tanang=d["tanang"], stbrad=None,
+        velocity_dependent=bool(d["velocity_dependent"]),
+        A=_unhex(d["A"]), Ap=_unhex(d["Ap"]), B=_unhex(d["B"]), Bp=_unhex(d["Bp"]),
+        C=_unhex(d["C"]), E=_unhex(d["E"]) * scale, Ep=_unhex(d["Ep"]) * scale,
+        P=None,
+    )
+    for v in attrs.values():
+        if isinstance(v, np.ndarray):
+            v.setflags(write=False)
+    return type(name, (RungeKuttaNystrom,), attrs)
+
+
+with open(os.path.join(os.path.dirname(_JSON), "tableaux_rkn.json")) as _fh:
+    _rkn = json.load(_fh)["tableaux"]
+Fi4N = _make_rkn("Fi4N", _rkn["Fi4N"])
+Fi5N = _make_rkn("Fi5N", _rkn["Fi5N"])
+Mu5Nmb = _make_rkn("Mu5Nmb", _rkn["Mu5Nmb"])
+MR6NN = _make_rkn("MR6NN", _rkn["MR6NN"])
+for _k, _c in enumerate((Fi4N, Fi5N, Mu5Nmb, MR6NN)):
+    _c._xsq_method = 9 + _k                       # XSQ_FI4N .. XSQ_MR6NN
+del _rkn, _fh, _k, _c
+BUILTIN_RKN = {c.__name__: c for c in (Fi4N, Fi5N, Mu5Nmb, MR6NN)}
+
+
 class SWAG:
     """Variable-order (1..12) Adams-Bashforth-Moulton PECE of Shampine, Gordon
     and Watts; reference ``extensisq/shampine.py:10-495``.  Like the tableau

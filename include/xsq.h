@@ -67,6 +67,13 @@ typedef enum xsq_method {
     XSQ_CKDISC = 8,         /* cash.py:115-416: variable order (5,3,2); ignores
                                sc_params, never runs the stiffness diagnosis,
                                no forced step sequences */
+    /* Runge-Kutta-Nystrom methods for second order problems in first order form
+     * [v, a] = f(t, [x, v]) (common.py:1207-1320): Fi4N, Fi5N (fine.py:6,115),
+     * Mu5Nmb (murua.py:6, scale_embedded=True), MR6NN (mikkawy.py:5, velocity
+     * independent problems only).  n_state must be even, the first half of the
+     * state are positions, the second half their velocities.  Final state and
+     * counters only: no t_eval, no events, no stiffness diagnosis. */
+    XSQ_FI4N = 9, XSQ_FI5N = 10, XSQ_MU5NMB = 11, XSQ_MR6NN = 12,
     XSQ_METHOD_USER = 100,
     XSQ_METHOD_SWAG = 200   /* internal tag used by xsq_swag_solve */
 } xsq_method;
