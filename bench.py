@@ -577,6 +577,23 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
             "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": tf / peak_tf,
                          "flops_model": "nfev x 31 x 20 x 32 (pair interactions) + SWAG vector work"}}
+        # the same systems with a Runge-Kutta-Nystrom method (the velocity
+        # independent second order problem they exist for, mikkawy.py)
+        r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "nbody32", (0.0, 1.0), y0, xb.MR6NN, params=prm, rtol=RTOL, atol=ATOL,
+            max_steps=200000), 1)
+        acc = int(r.n_accepted.sum().item())
+        nfev = int(r.nfev.sum().item())
+        tf = nfev * F / (ms * 1e-3) / 1e12
+        out["C4_nbody32_MR6NN"] = {
+            "value": acc / (ms * 1e-3), "unit": "accepted steps/s", "ms": ms, "accepted": acc,
+            "rejected": int(r.n_rejected.sum().item()), "nfev": nfev,
+            "pair_interactions_per_s": nfev * nb * nb / (ms * 1e-3),
+            "ok_frac": float((r.status == 0).double().mean().item()),
+            "workload": "MR6NN (Runge-Kutta-Nystrom, order 6) on the same 65 536 systems",
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": tf / peak_tf,
+                         "flops_model": "nfev x 31 x 20 x 32 (pair interactions)"}}
         del r, y0, prm
     return out
 
