@@ -454,6 +454,16 @@ def run_c5(xb, lib, dev, rank, world, dist, quick=False):
             "slab": f"2048 x {nx}", "ms_per_stage": ms_stage.value,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
                          "frac": gbs / hbm, "traffic": traffic, "traffic_source": tnote}}
+        # the TMA-staged variant of the same stage (cp.async.bulk.tensor.2d), kept as
+        # a measured experiment: DESIGN.md section 3.3
+        ms_tma, diff = C.c_double(), C.c_double()
+        if lib.xsq_rkc_stage_bench_tma(nx, 2048, 40, C.byref(ms_tma), C.byref(diff), None) == 0:
+            g2 = nx * 2048 * 40 / 1e9 / (ms_tma.value * 1e-3)
+            out["stage_kernel"]["tma_experiment"] = {
+                "kernel": "k_stage_tma (stencil operand staged by UTMALDG.2D, one box per CTA)",
+                "ms_per_stage": ms_tma.value, "GBps": g2, "frac": g2 / hbm,
+                "max_abs_diff_vs_k_stage": diff.value,
+                "shipped": "k_stage" if ms_stage.value <= ms_tma.value else "k_stage (TMA variant faster)"}
     if comm is not None:
         comm.close()
     return out

@@ -40,7 +40,7 @@ EXPORTS = [
     "xsq_events_register_source", "xsq_events_compile_check",
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
-    "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench",
+    "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench", "xsq_rkc_stage_bench_tma",
     "xsq_launch_count", "xsq_trim_memory", "xsq_profile_enable", "xsq_profile_last", "xsq_profile_get",
     "xsq_fp64_peak",
 ]
@@ -173,6 +173,7 @@ def load():
                                   C.c_void_p]
     lib.xsq_rkc_stage_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp,
                                         C.c_void_p]
+    lib.xsq_rkc_stage_bench_tma.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, C.c_void_p]
     lib.xsq_launch_count.restype = C.c_int64
     lib.xsq_trim_memory.argtypes = [C.c_int]
     lib.xsq_profile_enable.argtypes = [C.c_int]

@@ -25,6 +25,7 @@ namespace xsq {
 
 int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st);
 int rkc_stage_bench(int nx, int rows, int reps, double* ms, cudaStream_t st);
+int rkc_stage_bench_tma(int nx, int rows, int reps, double* ms, double* max_abs_diff, cudaStream_t st);
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -456,6 +457,12 @@ int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_s
                         void* stream) {
     if (!ms_per_stage || nx < 4 || nx % 4 || rows < 1 || reps < 1) return XSQ_ERR_ARG;
     return rkc_stage_bench(nx, rows, reps, ms_per_stage, (cudaStream_t)stream);
+}
+
+int xsq_rkc_stage_bench_tma(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
+                            double* max_abs_diff, void* stream) {
+    if (!ms_per_stage || nx < 4 || nx % 4 || rows < 1 || reps < 1) return XSQ_ERR_ARG;
+    return rkc_stage_bench_tma(nx, rows, reps, ms_per_stage, max_abs_diff, (cudaStream_t)stream);
 }
 
 int xsq_trim_memory(int device) {

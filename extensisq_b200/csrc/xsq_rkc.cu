@@ -37,6 +37,7 @@
 #include "xsq_comm.h"
 #include "xsq_user.h"   // set_detail, count_launch
 #include "xsq_rkc_kernels.cuh"
+#include "xsq_rkc_tma.cuh"
 
 namespace xsq {
 
@@ -779,6 +780,94 @@ int rkc_stage_bench(int nx, int rows, int reps, double* ms_per_stage, cudaStream
     cudaFree(buf);
     if (e != cudaSuccess) { set_detail(cudaGetErrorString(e)); return XSQ_ERR_CUDA; }
     *ms_per_stage = ms / reps;
+    return XSQ_OK;
+}
+
+// k_stage against its TMA-staged variant (xsq_rkc_tma.cuh) on the same random
+// slab: the largest |difference| of one stage (must be 0) and the average time
+// per stage of the TMA variant.
+__global__ void k_fill_pattern(double* p, size_t n, unsigned long long seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = (i + seed) * 0x9E3779B97F4A7C15ULL;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        p[i] = (double)(z >> 11) * 0x1.0p-53 - 0.5;
+    }
+}
+__global__ void k_max_abs_diff(const double* a, const double* b, size_t n, unsigned long long* out) {
+    double m = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const double d = fabs(a[i] - b[i]);
+        m = (d > m || d != d) ? (d != d ? __longlong_as_double(0x7ff0000000000000LL) : d) : m;
+    }
+    atomicMax(out, (unsigned long long)__double_as_longlong(m));   // non-negative doubles order as integers
+}
+
+int rkc_stage_bench_tma(int nx, int rows, int reps, double* ms_per_stage, double* max_abs_diff,
+                        cudaStream_t st) {
+    Slab S{nx, rows, 0, 0, ((double)nx + 1.0) * ((double)nx + 1.0), 1.0 / ((double)nx + 1.0), nullptr};
+    const size_t na = S.n_alloc();
+    double* buf = nullptr;
+    unsigned long long* dmax = nullptr;
+    if (cudaMalloc((void**)&buf, na * 6 * sizeof(double)) != cudaSuccess) return XSQ_ERR_NOMEM;
+    if (cudaMalloc((void**)&dmax, 8) != cudaSuccess) { cudaFree(buf); return XSQ_ERR_NOMEM; }
+    cudaMemsetAsync(dmax, 0, 8, st);
+    k_fill_pattern<<<1184, 256, 0, st>>>(buf, na * 6, 12345ULL);
+    double* v[3] = {buf, buf + na, buf + 2 * na};
+    double *yn = buf + 3 * na, *fn = buf + 4 * na, *ref = buf + 5 * na;
+    // ghost rows hold the Dirichlet zero
+    for (int k = 0; k < 3; ++k) {
+        cudaMemsetAsync(v[k], 0, (size_t)nx * sizeof(double), st);
+        cudaMemsetAsync(v[k] + (size_t)nx * (rows + 1), 0, (size_t)nx * sizeof(double), st);
+    }
+    CUtensorMap maps[3];
+    for (int k = 0; k < 3; ++k)
+        if (make_stage_map(&maps[k], v[k], nx, rows) != 0) {
+            cudaFree(buf);
+            cudaFree(dmax);
+            set_detail("cuTensorMapEncodeTiled failed");
+            return XSQ_ERR_CUDA;
+        }
+    dim3 block(TX, TY), grid((nx / PX + TX - 1) / TX, (rows + TY - 1) / TY);
+    const double mu = 1.9, nu = -0.95, c3 = 0.05, hmus = 1e-9, ajm1 = 0.3;
+    // one stage each way from the same inputs
+    k_stage<pde::Heat2dReaction><<<grid, block, 0, st>>>(
+        S, PeerSync{0, nullptr, nullptr, nullptr}, v[1], v[1], v[1] + (size_t)nx * (rows + 1), v[2], yn,
+        fn, ref, 0.0, mu, nu, c3, hmus, ajm1);
+    k_stage_tma<pde::Heat2dReaction><<<grid, block, 0, st>>>(maps[1], S, v[2], yn, fn, v[0], 0.0, mu,
+                                                             nu, c3, hmus, ajm1);
+    k_max_abs_diff<<<1184, 256, 0, st>>>(ref + nx, v[0] + nx, (size_t)nx * rows, dmax);
+    count_launch();
+    count_launch();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int w = 0; w < 3; ++w)
+        k_stage_tma<pde::Heat2dReaction><<<grid, block, 0, st>>>(maps[1], S, v[2], yn, fn, v[0], 0.0,
+                                                                 mu, nu, c3, hmus, ajm1);
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps; ++r) {
+        k_stage_tma<pde::Heat2dReaction><<<grid, block, 0, st>>>(
+            maps[(r + 1) % 3], S, v[(r + 2) % 3], yn, fn, v[r % 3], 0.0, mu, nu, c3, hmus, ajm1);
+        count_launch();
+    }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    unsigned long long bits = 0;
+    cudaMemcpy(&bits, dmax, 8, cudaMemcpyDeviceToHost);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(buf);
+    cudaFree(dmax);
+    if (e != cudaSuccess) { set_detail(cudaGetErrorString(e)); return XSQ_ERR_CUDA; }
+    *ms_per_stage = ms / reps;
+    if (max_abs_diff) std::memcpy(max_abs_diff, &bits, 8);
     return XSQ_OK;
 }
 

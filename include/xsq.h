@@ -327,6 +327,12 @@ int xsq_rkc_solve(const xsq_rkc_args_t* args, void* comm, void* stream);
  * average device milliseconds per fused stage on a rows x nx slab. */
 int xsq_rkc_stage_bench(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
                         void* stream);
+/* The same stage with its stencil operand staged through shared memory by the
+ * TMA unit (cp.async.bulk.tensor.2d), an experiment kept for comparison:
+ * average milliseconds per stage, and the largest |difference| of one stage
+ * against the shipped kernel on the same random slab (must be 0). */
+int xsq_rkc_stage_bench_tma(int32_t nx, int32_t rows, int32_t reps, double* ms_per_stage,
+                            double* max_abs_diff, void* stream);
 
 /* The library caches its scratch (work queue, init pass, stiffness probe queue)
  * in the device's stream-ordered memory pool between calls.  This returns all
