@@ -40,7 +40,7 @@ EXPORTS = [
     "xsq_events_register_source", "xsq_events_compile_check",
     "xsq_rk_solve", "xsq_rk_solve_host", "xsq_swag_solve",
     "xsq_comm_unique_id", "xsq_comm_create", "xsq_comm_destroy",
-    "xsq_pde_register_source", "xsq_rkc_solve", "xsq_rkc_stage_bench", "xsq_rkc_stage_bench_tma",
+    "xsq_pde_register_source", "xsq_pde_register_vector_source", "xsq_rkc_solve", "xsq_rkc_stage_bench", "xsq_rkc_stage_bench_tma",
     "xsq_launch_count", "xsq_trim_memory", "xsq_profile_enable", "xsq_profile_last", "xsq_profile_get",
     "xsq_fp64_peak",
 ]
@@ -169,6 +169,7 @@ def load():
     lib.xsq_comm_destroy.argtypes = [C.c_void_p]
     lib.xsq_pde_register_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int32,
                                             _ip]
+    lib.xsq_pde_register_vector_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _ip]
     lib.xsq_rkc_solve.argtypes = [C.POINTER(XsqRkcArgs), C.c_void_p,
                                   C.c_void_p]
     lib.xsq_rkc_stage_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp,

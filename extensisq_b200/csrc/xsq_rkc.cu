@@ -318,10 +318,16 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
         return XSQ_ERR_ARG;
     }
     PdeLaunch pl;
-    int n_pde_param_expected = 0;
+    int n_pde_param_expected = 0, n_vector = 0;
     if (A->pde >= XSQ_PDE_USER_BASE) {
         int rc = user_pde_kernels(A->pde, pl.user_fn, &n_pde_param_expected);
         if (rc != XSQ_OK) return rc;
+        n_vector = user_pde_vector_size(A->pde);
+        if (n_vector > 0 && (A->rows_local != 1 || A->rows_global != 1 || A->world != 1 ||
+                             A->nx < n_vector)) {
+            set_detail("rkc: a general system is one row of nx >= n entries on one GPU");
+            return XSQ_ERR_ARG;
+        }
     } else if (A->pde != XSQ_PDE_HEAT2D_REACTION) {
         set_detail("unknown pde");
         return XSQ_ERR_UNSUPPORTED;
@@ -360,6 +366,7 @@ int rkc_solve(const xsq_rkc_args_t* A, Comm* comm, cudaStream_t st) {
     C.rank = A->world > 1 ? A->rank : 0;
     C.world = A->world > 1 ? A->world : 1;
     C.n_total = (long long)A->nx * A->rows_global;
+    if (n_vector > 0) C.n_total = n_vector;      // padding is not part of the norm
     const size_t na = C.S.n_alloc();
     // device scratch: yn, fn, w0, w1, w2, V + partials + scalars
     keep_pool_memory();

@@ -32,6 +32,7 @@ struct Slab {
 namespace pde {
 // u_t = Lap(u) + u - u^3  
 struct Heat2dReaction {
+    static constexpr bool VECTOR = false;
     __device__ __forceinline__ static double rhs(double, double, double, double inv_h2,
                                                  double c, double n, double s, double w,
                                                  double e, const double*) {
@@ -113,6 +114,17 @@ template <class Pde>
 __device__ __forceinline__ void rhs4(const Slab& S, const double* __restrict__ u,
                                      const double* up_row, const double* dn_row, double t,
                                      int row, size_t idx, int col, double (&f)[PX]) {
+    if constexpr (Pde::VECTOR) {
+        // A general system y' = f(t, y) (the reference takes any `fun`,
+        // sommeijer.py:93-145): the state is ONE row of the slab, the policy returns
+        // component i with the whole vector in view.  Entries beyond Pde::N pad
+        // the row to a multiple of 4 and stay zero.
+        const double* y = u + S.nx;                    // skip the ghost row
+#pragma unroll
+        for (int k = 0; k < PX; ++k)
+            f[k] = col + k < Pde::N ? Pde::at(col + k, t, y, S.prm) : 0.0;
+        return;
+    }
     double c[PX], up[PX], dn[PX];
     load4(u + idx, c);
     if (row == 0) load4_peer(up_row + col, up);

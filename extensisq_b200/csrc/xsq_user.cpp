@@ -57,6 +57,7 @@ struct UserTab {
 struct UserPde {
     std::string src, entry;
     int n_param;
+    int n_vector = 0;          // > 0: a general system of this many equations (one slab row)
     bool ready = false;
     CUmodule mod = nullptr;
     CUfunction fn[3] = {nullptr, nullptr, nullptr};
@@ -319,7 +320,18 @@ int compile_module(const std::string& src, CUmodule* mod) {
 
 std::string pde_source(const UserPde& u) {
     std::string s = "#include \"xsq_rkc_kernels.cuh\"\n" + u.src + "\n";
+    if (u.n_vector > 0)
+        s += "namespace xsq { namespace rkc { namespace pde { struct User {\n"
+             "  static constexpr bool VECTOR = true;\n"
+             "  static constexpr int N = " + std::to_string(u.n_vector) + ";\n"
+             "  __device__ __forceinline__ static double at(int i, double t, const double* y,\n"
+             "      const double* p) { return ::" + u.entry + "(i, t, y, p); }\n"
+             "  __device__ __forceinline__ static double rhs(double, double, double, double,\n"
+             "      double, double, double, double, double, const double*) { return 0.0; }\n"
+             "};\n} } }\n";
+    else
     s += "namespace xsq { namespace rkc { namespace pde { struct User {\n"
+         "  static constexpr bool VECTOR = false;\n"
          "  __device__ __forceinline__ static double rhs(double t, double x, double y, double inv_h2,\n"
          "      double c, double n, double s, double w, double e, const double* p) {\n"
          "    return ::" + u.entry + "(t, x, y, inv_h2, c, n, s, w, e, p); }\n};\n} } }\n";
@@ -573,6 +585,13 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     return XSQ_OK;
 }
 
+int user_pde_vector_size(int pde) {
+    std::lock_guard<std::mutex> g(g_mu);
+    const size_t i = (size_t)(pde - XSQ_PDE_USER_BASE);
+    if (pde < XSQ_PDE_USER_BASE || i >= g_pde.size()) return 0;
+    return g_pde[i].n_vector;
+}
+
 int user_pde_kernels(int pde, void* fn[3], int* n_param) {
     std::lock_guard<std::mutex> g(g_mu);
     const size_t i = (size_t)(pde - XSQ_PDE_USER_BASE);
@@ -654,6 +673,20 @@ int xsq_pde_register_source(const char* cuda_src, const char* entry, int32_t n_p
     u.src = cuda_src;
     u.entry = entry;
     u.n_param = n_param;
+    g_pde.push_back(u);
+    *pde_out = XSQ_PDE_USER_BASE + (int)g_pde.size() - 1;
+    return XSQ_OK;
+}
+
+int xsq_pde_register_vector_source(const char* cuda_src, const char* entry, int32_t n_state,
+                                   int32_t n_param, int32_t* pde_out) {
+    if (!cuda_src || !entry || !pde_out || n_param < 0 || n_state < 1) return XSQ_ERR_ARG;
+    std::lock_guard<std::mutex> g(g_mu);
+    UserPde u;
+    u.src = cuda_src;
+    u.entry = entry;
+    u.n_param = n_param;
+    u.n_vector = n_state;
     g_pde.push_back(u);
     *pde_out = XSQ_PDE_USER_BASE + (int)g_pde.size() - 1;
     return XSQ_OK;

@@ -24,6 +24,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
 int user_events_count(int events);
 // user PDE for SSV2stab: CUfunctions (as void*) of the eval / stage / final kernels
 int user_pde_kernels(int pde, void* fn[3], int* n_param);
+int user_pde_vector_size(int pde);   // > 0: a general system registered with xsq_pde_register_vector_source
 int user_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** args,
                 cudaStream_t st);
 

@@ -38,8 +38,9 @@ class PdeRHS:
     compiled with NVRTC into the fused SSV2stab stage kernels.  Replaces the
     Python callable `fun` of the reference (sommeijer.py:93)."""
 
-    def __init__(self, handle, n_param, name):
+    def __init__(self, handle, n_param, name, n_state=0):
         self.handle, self.n_param, self.name = handle, n_param, name
+        self.n_state = n_state          # > 0: a general system (from_vector_source)
 
     @classmethod
     def from_source(cls, cuda_src, entry, n_param=0):
@@ -49,6 +50,22 @@ class PdeRHS:
                                                entry.encode(), int(n_param),
                                                C.byref(h)))
         return cls(h.value, int(n_param), f"user:{entry}")
+
+    @classmethod
+    def from_vector_source(cls, cuda_src, entry, n_state, n_param=0):
+        """A GENERAL system ``y' = f(t, y)`` of ``n_state`` equations (the
+        reference's SSV2stab takes any ``fun``, sommeijer.py:93-145; its published
+        examples are 3-D and multi-component problems): CUDA source defining
+
+            __device__ double <entry>(int i, double t, const double* y, const double* p);
+
+        the i-th component of f with the whole state in view.  ``solve_pde_rkc``
+        then takes a 1-D ``u0`` of length ``n_state`` (single GPU)."""
+        lib = _lib.load()
+        h = C.c_int32()
+        _lib.check(lib.xsq_pde_register_vector_source(cuda_src.encode(), entry.encode(),
+                                                      int(n_state), int(n_param), C.byref(h)))
+        return cls(h.value, int(n_param), f"user:{entry}", n_state=int(n_state))
 
 
 class SSV2stab:
@@ -198,6 +215,17 @@ def solve_pde_rkc(pde, t_span, u0, rows_global=None, row0=0, t_eval=None,
     dev = u0.device if u0.is_cuda else torch.device(
         "cuda", torch.cuda.current_device())
     u0 = u0.to(device=dev, dtype=torch.float64).contiguous()
+    n_vec = pde.n_state if isinstance(pde, PdeRHS) else 0
+    if n_vec:
+        # a general system: one slab row, padded with zeros to a multiple of 4
+        if u0.ndim != 1 or u0.numel() != n_vec:
+            raise ValueError(f"`u0` must be 1-dimensional with {n_vec} entries")
+        if comm is not None:
+            raise ValueError("general systems run on one GPU")
+        nx_pad = (n_vec + 3) // 4 * 4
+        padded = torch.zeros((1, nx_pad), dtype=torch.float64, device=dev)
+        padded[0, :n_vec] = u0
+        u0 = padded
     if u0.ndim != 2:
         raise ValueError("`u0` must be [rows_local, nx]")
     rows_local, nx = u0.shape
@@ -256,6 +284,9 @@ def solve_pde_rkc(pde, t_span, u0, rows_global=None, row0=0, t_eval=None,
                                      C.c_void_p(st.cuda_stream)))
     nfesig[()] = res.nfesig
     maxm[()] = res.maxm
+    if n_vec:
+        u_final = u_final[0, :n_vec]
+        u_eval = u_eval[:, 0, :n_vec] if u_eval is not None else None
     return PdeResult(t=te, y=u_eval, y_final=u_final, t_final=res.t_final,
                      n_accepted=res.n_accepted, n_rejected=res.n_rejected,
                      nfev=res.nfev, nfesig=res.nfesig, maxm=res.maxm,

@@ -311,6 +311,16 @@ typedef struct xsq_rkc_args {
 int xsq_pde_register_source(const char* cuda_src, const char* entry, int32_t n_param,
                             int32_t* pde_out);
 
+/* A GENERAL system y' = f(t, y) for SSV2stab (the reference takes any `fun`,
+ * sommeijer.py:93-145; its published tables are a 3-D heat problem and a
+ * two-species combustion problem, docs/Demo_SSV2stab.ipynb): CUDA source
+ * defining one component of the right-hand side with the whole state in view,
+ *   __device__ double <entry>(int i, double t, const double* y, const double* p);
+ * Solve it with nx = n_state rounded up to a multiple of 4 (the padding must
+ * be zero in u0), rows_local = rows_global = 1, world = 1. */
+int xsq_pde_register_vector_source(const char* cuda_src, const char* entry, int32_t n_state,
+                                   int32_t n_param, int32_t* pde_out);
+
 /* NCCL communicator for the slab decomposition (new; the reference has no
  * communication layer).  Rank 0 calls xsq_comm_unique_id and distributes the
  * 128 bytes out of band (e.g. torch.distributed.broadcast); every rank then

@@ -211,3 +211,57 @@ __device__ double event(int k, double t, const double* y, const double* p) {
     return t - 7.25;
 }"""),
 }
+
+
+# The same 3-D heat problem as ONE device function per component (the general
+# right-hand side of extensisq_b200.PdeRHS.from_vector_source): y index
+# i = (a N + b) N + c, interior point (x, y, z) = (g[b+1], g[a+1], g[c+1]) of
+# numpy's meshgrid(g, g, g); boundary values from the exact solution.
+HEAT3D_VECTOR_SRC = r"""
+#define NG %d
+__device__ __forceinline__ double h3_sol(double x, double y, double z, double t) {
+    return tanh(5 * x + 10 * y + 7.5 * z - (2.5 + 5 * t));
+}
+__device__ double heat3d(int i, double t, const double* u, const double* p) {
+    const int c = i %% NG, b = (i / NG) %% NG, a = i / (NG * NG);
+    const double h = 1.0 / (NG + 1.0);
+    const double x = (b + 1) * h, y = (a + 1) * h, z = (c + 1) * h;
+    const double w = u[i];
+    const double am = a > 0 ? u[i - NG * NG] : h3_sol(x, 0.0, z, t);
+    const double ap = a < NG - 1 ? u[i + NG * NG] : h3_sol(x, 1.0, z, t);
+    const double bm = b > 0 ? u[i - NG] : h3_sol(0.0, y, z, t);
+    const double bp = b < NG - 1 ? u[i + NG] : h3_sol(1.0, y, z, t);
+    const double cm = c > 0 ? u[i - 1] : h3_sol(x, y, 0.0, t);
+    const double cp = c < NG - 1 ? u[i + 1] : h3_sol(x, y, 1.0, t);
+    const double lap = (1.0 / (h * h)) * (-6 * w + am + ap + bm + bp + cm + cp);
+    const double s = h3_sol(x, y, z, t);
+    return lap + (362.5 * (s - s * s * s) + 5 * (s * s) - 5);
+}
+"""
+
+
+# The two-species combustion problem of docs/Demo_SSV2stab.ipynb (cell 1) as one
+# device function per component: y = [c (N^3), T (N^3)], Neumann boundaries at
+# the low faces (ghost = first interior value), Dirichlet 1 at the high faces,
+# h = 1 / (N + 0.5); p = (L, alpha, delta, D).
+COMBUSTION_VECTOR_SRC = r"""
+#define NG %d
+__device__ __forceinline__ double comb_lap(const double* A, int j, int a, int b, int c, double inv_h2) {
+    const double w = A[j];
+    const double am = a > 0 ? A[j - NG * NG] : w, ap = a < NG - 1 ? A[j + NG * NG] : 1.0;
+    const double bm = b > 0 ? A[j - NG] : w, bp = b < NG - 1 ? A[j + NG] : 1.0;
+    const double cm = c > 0 ? A[j - 1] : w, cp = c < NG - 1 ? A[j + 1] : 1.0;
+    return inv_h2 * (-6 * w + am + ap + bm + bp + cm + cp);
+}
+__device__ double combustion(int i, double t, const double* y, const double* p) {
+    const int n3 = NG * NG * NG;
+    const int j = i < n3 ? i : i - n3;
+    const int c = j %% NG, b = (j / NG) %% NG, a = j / (NG * NG);
+    const double h = 1.0 / (NG + 0.5);
+    const double inv_h2 = 1.0 / (h * h);
+    const double conc = y[j], T = y[n3 + j];
+    const double Dce = p[3] * conc * exp(-p[2] / T);
+    if (i < n3) return comb_lap(y, j, a, b, c, inv_h2) - Dce;
+    return (comb_lap(y + n3, j, a, b, c, inv_h2) + p[1] * Dce) / p[0];
+}
+"""

@@ -190,3 +190,49 @@ def test_user_pde_rhs_vs_c_oracle():
                   ref2["y_final"]).max() <= 10 * 1e-4
     with pytest.raises(ValueError, match="pde_params"):
         xb.solve_pde_rkc(pde, (0.0, 0.05), u0, rho_jac=float(rho))
+
+
+# ---- general systems: the reference's published 3-D table ---------------------
+def test_ssv2stab_general_system_reproduces_the_notebook_table():
+    """docs/Demo_SSV2stab.ipynb:350-356 (3-D heat problem on 39^3 points, linear
+    with a time dependent source and boundary): steps (rejected) / f-evals / s-max
+    for tol = 1e-1 .. 1e-4, as published, through PdeRHS.from_vector_source --
+    one device function per component instead of the built-in 2-D stencil."""
+    from oracle.problems import HEAT3D_VECTOR_SRC, heat3d_notebook
+    N = 39
+    _, y0, rho = heat3d_notebook(N)
+    rhs = xb.PdeRHS.from_vector_source(HEAT3D_VECTOR_SRC % N, "heat3d", N ** 3)
+    table = {1e-1: (6, 1, 402, 132), 1e-2: (15, 4, 729, 85),
+             1e-3: (27, 2, 786, 40), 1e-4: (57, 0, 1087, 26)}
+    meta = {c["id"]: c for c in CASES}
+    for tol, (steps, rej, nfev, smax) in table.items():
+        r = xb.solve_pde_rkc(rhs, (0.0, 0.7), y0, rtol=tol, atol=tol, const_jac=True,
+                             rho_jac=float(rho))
+        assert r.status == 0
+        assert (r.n_accepted + r.n_rejected, r.n_rejected, r.nfev, r.maxm) == (steps, rej, nfev, smax)
+        cid = f"heat3d_tol{tol:g}"
+        assert cid in meta
+        y = r.y_final.cpu().numpy()
+        assert y.shape == (N ** 3,)
+        assert np.abs(y[::97] - Z[cid + "/y_sample"]).max() <= 1e-9
+
+
+def test_ssv2stab_two_species_combustion_table():
+    """docs/Demo_SSV2stab.ipynb cell 9 (printed table): the 3-D two-species
+    combustion problem, 2 x 40^3 equations, nonlinear, spectral radius by the
+    power iteration: steps (rejected) / f-evals / f-sigma / s-max as published."""
+    from oracle.problems import COMBUSTION_VECTOR_SRC
+    N = 40
+    L, alpha, delta, R = 0.9, 1.0, 20.0, 5.0
+    D = R * np.exp(delta) / (alpha * delta)
+    rhs = xb.PdeRHS.from_vector_source(COMBUSTION_VECTOR_SRC % N, "combustion", 2 * N ** 3, 4)
+    y0 = np.ones(2 * N ** 3)
+    table = {1e-4: (51, 1, 525, 21, 36), 1e-5: (124, 0, 781, 27, 29), 1e-6: (270, 0, 1270, 39, 20)}
+    for tol, (steps, rej, nfev, nsig, smax) in table.items():
+        r = xb.solve_pde_rkc(rhs, (0.0, 0.30), y0, rtol=tol, atol=tol, pde_params=[L, alpha, delta, D])
+        assert r.status == 0
+        got = (r.n_accepted + r.n_rejected, r.n_rejected, r.nfev, r.nfesig, r.maxm)
+        print(f"combustion tol {tol:g}: steps {got[0]} ({got[1]}) f-evals {got[2]} f-sigma {got[3]} s-max {got[4]}")
+        assert got == (steps, rej, nfev, nsig, smax)
+        T = r.y_final.cpu().numpy()[N ** 3:]
+        assert 1.0 <= T.min() and T.max() < 2.2          # burnt gas behind the front

@@ -66,8 +66,8 @@ def test_sens_forward_argument_checks():
     src = SO.PROBLEMS["lorenz"][3]
     with pytest.raises(AssertionError):
         xb.sens_forward(src, (0.0, 1.0), [[1.0, 1.0, 1.0]], np.zeros((2, 3)), [10.0, 28.0, 2.0])
-    with pytest.raises(ValueError):      # 6 * (1 + 3) states do not fit one lane
-        xb.sens_forward(src, (0.0, 1.0), [[1.0] * 6], np.zeros((6, 3)), [10.0, 28.0, 2.0])
+    with pytest.raises(ValueError):      # 300 * (1 + 3) states: beyond a warp-per-system kernel
+        xb.sens_forward(src, (0.0, 1.0), [[1.0] * 300], np.zeros((300, 3)), [10.0, 28.0, 2.0])
 
 
 CHAIN_SRC = """
