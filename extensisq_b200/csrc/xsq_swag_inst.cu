@@ -29,6 +29,12 @@ static int launch_swag_fast_geom(const RkDev& P, cudaStream_t st) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem) != cudaSuccess ||
         occ < 1)
         return XSQ_ERR_CUDA;
+#ifdef XSQ_SWAG_GEOMETRY_SWEEP
+    if (const char* e = getenv("XSQ_SWAG_OCC")) {      // fewer resident CTAs than fit
+        const int cap = atoi(e);
+        if (cap >= 1 && cap < occ) occ = cap;
+    }
+#endif
     long long want = (P.n_lanes + BLOCK - 1) / BLOCK;
     long long grid = (long long)n_sm * occ;
     if (want < grid) grid = want;
