@@ -92,6 +92,7 @@ class XsqRkArgs(C.Structure):
         ("ev_capacity", C.c_int32), ("reserved2", C.c_int32),
         ("t_events", C.c_void_p), ("y_events", C.c_void_p),
         ("ev_count", C.c_void_p),
+        ("first_step_lanes", C.c_void_p),
     ]
 
 

@@ -209,6 +209,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
     t_eval : [n_eval] times inside t_span, sorted along the direction
     params : [N, p] per-lane parameters of the RHS
     rtol : float;  atol : float or [n];  first_step, max_step : float
+        (first_step may also be a [N] tensor, one first step per lane: pass the
+        ``h_next`` of the result that ended at ``t_span[0]`` to continue a solve)
     sc_params : "G" | "S" | "standard" | (kb1, kb2, a, g)
     interpolant : BS5 only, 'best' | 'low' | 'free' (bogacki.py:217)
     k_max : SWAG only, maximum order 1..12 (shampine.py:99-103)
@@ -307,6 +309,14 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         raise ValueError("`atol` must be positive.")
     if max_step <= 0:
         raise ValueError("`max_step` must be positive.")
+    first_lanes = None
+    if first_step is not None and np.ndim(first_step) > 0:
+        # one first step per lane: resume with the h_next of a previous solve (the
+        # reference's manual stepping continues with the controller's proposal)
+        if forced_steps is not None:
+            raise ValueError("a per-lane `first_step` does not apply to forced_steps")
+        first_lanes = first_step
+        first_step = None
     if first_step is not None and forced_steps is None:
         if first_step <= 0:
             raise ValueError("`first_step` must be positive.")
@@ -423,6 +433,13 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
             for i in range(4):
                 a.sc_params[i] = sc[i]
         a.first_step = float(first_step) if first_step is not None else 0.0
+        if first_lanes is not None:
+            fl = _as_device(first_lanes, device).to(torch.float64).contiguous()
+            if fl.shape != (N,):
+                raise ValueError("a per-lane `first_step` must have one entry per lane")
+            if not bool((fl > 0).all()):
+                raise ValueError("`first_step` must be positive.")
+            a.first_step_lanes = fl.data_ptr()
         a.max_step = float(max_step)
         a.t_eval = te.data_ptr() if n_eval else None
         a.n_eval = n_eval

@@ -383,6 +383,7 @@ int xsq_rk_solve_host(const xsq_rk_args_t* h, int device) {
     d.params = np ? (const double*)h2d(h->params, (size_t)N * np * nd) : nullptr;
     d.t_eval = h->n_eval ? (const double*)h2d(h->t_eval, (size_t)h->n_eval * nd) : nullptr;
     d.h_forced = h->n_forced ? (const double*)h2d(h->h_forced, (size_t)h->n_forced * nd) : nullptr;
+    d.first_step_lanes = h->first_step_lanes ? (const double*)h2d(h->first_step_lanes, (size_t)N * nd) : nullptr;
     const size_t pitch = ((size_t)h->n_eval + 3) & ~(size_t)3;
     d.y_eval = h->n_eval ? (double*)dalloc((size_t)N * ns * pitch * nd) : nullptr;
     d.t_final = (double*)dalloc((size_t)N * nd);

@@ -183,6 +183,14 @@ inline int build_params(const xsq_rk_args_t* a, RkDev* P, MethodInfo* mi,
     // OdeSolver.__init__, base.py:165
     P->direction = (a->t_bound != a->t0) ? (a->t_bound > a->t0 ? 1.0 : -1.0) : 1.0;
     P->first_step = a->first_step;
+    P->first_h = a->first_step_lanes;
+    if (a->first_step_lanes) {
+        if (a->n_forced > 0) {
+            set_detail("first_step_lanes does not apply to forced steps");
+            return XSQ_ERR_ARG;
+        }
+        P->first_step = 0.0;                 // the kernels then read init_h[lane]
+    }
     P->max_step = a->max_step;
     P->t_eval = a->t_eval;
     P->y_eval = a->y_eval;

@@ -72,6 +72,7 @@ struct RkDev {
     double atol[16];
     const double* atol_dev;       // [n_state], used by warp-per-system kernels
     double first_step, max_step;
+    const double* first_h;      // per-lane first |h| (resume), or null
     double err_exp, minbeta1, minbeta2, minalpha, safety, safety_sc;
     double log2n;                 // log2(n_state), for log2(error_norm)
     // step-size controller in the log2 domain (ctl_factor below), with
@@ -454,7 +455,9 @@ __device__ __forceinline__ void ens_init_body(const RkDev& P) {
     int nfev = 1;
     R::f(P.t0, y, prm, f);
     double h = 0.0;
-    if (P.n_forced == 0 && !(P.first_step > 0.0)) {
+    if (P.first_h != nullptr) {
+        h = fmin(P.first_h[idx], fabs(P.t_bound - P.t0));       // resume: the caller's step
+    } else if (P.n_forced == 0 && !(P.first_step > 0.0)) {
         const double b = P.t0 + P.direction *
             fmin(fabs(P.t_bound - P.t0), P.max_step);
         h = h_start_dev<R>(P, P.t0, b, y, f, prm, P.morder, lane, nfev);

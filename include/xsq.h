@@ -180,6 +180,12 @@ typedef struct xsq_rk_args {
     double* y_events;         /* [n_lanes][n_event_fns][ev_capacity][n_state]   */
     int32_t* ev_count;        /* [n_lanes][n_event_fns] occurrences found (can
                                  exceed ev_capacity: later ones are not kept)   */
+    /* resume: a first |h| PER LANE, e.g. the h_next of the solve that ended at
+     * this call's t0 (the reference's manual stepping, tests/test_ivp.py:839-868,
+     * continues with the step size the controller proposed).  [n_lanes] or NULL;
+     * overrides first_step; each value is clipped to |t_bound - t0|; no h_start
+     * evaluations are made.  Not with forced steps. */
+    const double* first_step_lanes;
 } xsq_rk_args_t;
 
 int xsq_abi_version(void);

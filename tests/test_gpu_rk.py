@@ -605,3 +605,28 @@ def test_stiffness_probe_queue_and_slots_agree(method, monkeypatch):
         assert np.array_equal(a["nfev"], o["nfev"])
         assert np.array_equal(fa, f)
         assert np.array_equal(a["y_final"], o["y_final"])
+
+
+def test_resume_with_the_per_lane_step_proposal():
+    """Manual stepping / resume (reference tests/test_ivp.py:839-868 keeps calling
+    solver.step(), i.e. continues with the step the controller proposed): a solve
+    cut in two legs, the second started with first_step = h_next PER LANE, takes no
+    h_start evaluations and lands on the uninterrupted solution to the tolerance."""
+    N = 512
+    y0, prm = lorenz_lanes(N)
+    kw = dict(params=prm, rtol=1e-9, atol=1e-11)
+    one = xb.solve_ivp_batched("lorenz63", (0.0, 2.0), y0, xb.Ts5, **kw)
+    a = xb.solve_ivp_batched("lorenz63", (0.0, 1.0), y0, xb.Ts5, **kw)
+    b = xb.solve_ivp_batched("lorenz63", (1.0, 2.0), a.y_final, xb.Ts5, first_step=a.h_next, **kw)
+    torch.cuda.synchronize()
+    assert (b.status == 0).all()
+    # second leg: f(t0, y0) + 6 evaluations per attempted step, nothing for a starting step
+    att = (b.n_accepted + b.n_rejected).cpu().numpy()
+    assert np.array_equal(b.nfev.cpu().numpy(), 1 + 6 * att)
+    # the cut costs at most a couple of steps (the last step of leg one is shortened to hit t = 1)
+    tot = (a.n_accepted + b.n_accepted).cpu().numpy()
+    assert (np.abs(tot - one.n_accepted.cpu().numpy()) <= 3).all()
+    err = (b.y_final - one.y_final).abs().max().item()
+    assert err < 1e-5          # Lorenz amplifies the 1e-9 local differences over t in [0, 2]
+    with pytest.raises(ValueError):
+        xb.solve_ivp_batched("lorenz63", (1.0, 2.0), a.y_final, xb.Ts5, first_step=a.h_next[:7], **kw)
