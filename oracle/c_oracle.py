@@ -30,6 +30,10 @@ class OTab(C.Structure):
         ("npol_low", C.c_int32), ("npol_best", C.c_int32),
         ("sc", C.c_double * 4),
         ("stbrad", C.c_double), ("tanang", C.c_double),
+        ("B_assess", (C.c_double * MAXS) * 2), ("E_assess", (C.c_double * MAXS) * 2),
+        ("B_fallback", (C.c_double * MAXS) * 2), ("E_fallback", (C.c_double * MAXS) * 2),
+        ("C_fallback", C.c_double * 2), ("ck_max_factor", C.c_double),
+        ("ck_min_factor", C.c_double), ("ck_safety", C.c_double),
     ]
 
 
@@ -128,7 +132,7 @@ def make_tab(tab, sc_params=None):
     s = tab.n_stages
     t.s, t.order, t.order2 = s, tab.order, tab.order_secondary
     name = getattr(tab, "name", getattr(tab, "__name__", ""))
-    t.variant = {"BS5": 1, "CFMR7osc": 2}.get(name, 0)
+    t.variant = {"BS5": 1, "CFMR7osc": 2, "CKdisc": 3}.get(name, 0)
     _fill2(t.A, tab.A)
     for i in range(s):
         t.B[i] = float(tab.B[i])
@@ -151,6 +155,14 @@ def make_tab(tab, sc_params=None):
         _fill2(t.Plow, tab.Plow)
         _fill2(t.Pbest, tab.Pbest)
         t.npol_low, t.npol_best = tab.Plow.shape[1], tab.Pbest.shape[1]
+    if t.variant == 3:                      # cash.py:184-236
+        for k in ("B_assess", "E_assess", "B_fallback", "E_fallback"):
+            _fill2(getattr(t, k), np.asarray(getattr(tab, k)))
+        for i in range(2):
+            t.C_fallback[i] = float(tab.C_fallback[i])
+        t.ck_max_factor = float(tab.max_factor)
+        t.ck_min_factor = float(tab.min_factor)
+        t.ck_safety = float(tab.safety)
     scp = sc_params if sc_params is not None else tab.sc_params
     if isinstance(scp, str):
         scp = O.SC_PRESETS[scp]

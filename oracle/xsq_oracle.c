@@ -65,7 +65,7 @@ int xsq_oracle_set_device_math(int on) {
 #define SMALL 0x1.0000000000001p-53
 #define RELPER 0x1.172b83c7d517bp-20
 
-enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2 };
+enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2, V_CKDISC = 3 };
 enum { ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_OVERFLOW = -2, ST_BUDGET = -5 };
 enum { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
 enum { RHS_LORENZ = 0, RHS_VDP = 1, RHS_ARENSTORF = 2, RHS_NBODY32 = 3 };
@@ -80,6 +80,9 @@ typedef struct {
     int32_t npol_low, npol_best;
     double sc[4];
     double stbrad, tanang;      /* <= 0: stiffness diagnosis not implemented */
+    /* CKdisc only (cash.py:184-236) */
+    double B_assess[2][MAXS], E_assess[2][MAXS], B_fallback[2][MAXS], E_fallback[2][MAXS];
+    double C_fallback[2], ck_max_factor, ck_min_factor, ck_safety;
 } otab_t;
 
 typedef void (*rhs_fn)(double t, const double* y, const double* p, double* dy);
@@ -157,10 +160,12 @@ typedef struct {
     /* state */
     double t, h_abs, h_prev, err_old, max_factor, min_step;
     double l2_old;                 /* device arithmetic: log2 of the last accepted ss */
+    double log2n;
     double ctl_a1s, ctl_a0s, ctl_a1c, ctl_a2c, ctl_a0c;   /* xsq_api.cu build_params */
     double y[MAXN], fcur[MAXN];
     double K[KROWS][MAXN];
     int n_acc, n_rej, nfev, standard_sc;
+    int force_cubic;               /* CKdisc: a fallback solution was accepted (cash.py:406-416) */
     /* stiffness diagnosis, common.py:150-164 */
     int nfev_stiff_detect, jflstp, okstp, stiff_flags, n_stiff_tests;
     double havg;
@@ -392,7 +397,7 @@ static int emit(lane_t* L, double h, double t_new, const double* y_new,
     const int n = L->n, s = T->s;
     if (ieval >= n_eval) return ieval;
     if (L->direction * (t_eval[ieval] - t_new) > 0.0) return ieval;
-    if (T->npol == 0) { /* CubicDenseOutput, common.py:793-821 */
+    if (T->npol == 0 || L->force_cubic) { /* CubicDenseOutput, common.py:793-821 */
         const double hh = t_new - L->t;
         while (ieval < n_eval && L->direction * (t_eval[ieval] - t_new) <= 0.0) {
             const double x = (t_eval[ieval] - L->t) / hh, omx = 1.0 - x;
@@ -621,6 +626,134 @@ static void diagnose_stiffness(lane_t* L, const double* y_old, const double* err
     else if (stif == 1 && rootre >= 0) L->stiff_flags |= rootre ? 1 : 2;
 }
 
+/* ---- CKdisc._step_impl, cash.py:245-404 (xsq_rk_core.cuh attempt_ckdisc) ----
+ * Reference arithmetic: norm(err/tol) ** (1/p) with sqrt and pow.  Device
+ * arithmetic: (ss/n) ** (1/(2p)) through the kernels' own log2 / exp2, and
+ * norm < 1 decided as ss < n. */
+static double pymax(double a, double b) { return b > a ? b : a; }
+static double pymin(double a, double b) { return b < a ? b : a; }
+/* sel: 0/1 assessment pair, 2/3 fallback pair, 4 the fifth order pair.  Returns
+ * sum((err/tol)^2) in device arithmetic, norm(err/tol) otherwise. */
+static double ck_solution(lane_t* L, int sel, double h, double* sol) {
+    const otab_t* T = L->T;
+    const int ns = (sel == 0 || sel == 2) ? 2 : (sel == 4 ? 6 : 4);
+    const double* wb = sel < 2 ? T->B_assess[sel] : (sel < 4 ? T->B_fallback[sel - 2] : T->B);
+    const double* we = sel < 2 ? T->E_assess[sel] : (sel < 4 ? T->E_fallback[sel - 2] : T->E);
+    double errv[MAXN];
+    for (int c = 0; c < L->n; ++c) {
+        sol[c] = fma(h, wsum(L, wb, ns, c), L->y[c]);
+        errv[c] = h * wsum(L, we, ns, c);
+    }
+    return g_device_math ? scaled_ss_dev(L, errv, sol) : scaled_norm(L, errv, sol);
+}
+static double ck_root(const lane_t* L, double v, int p) {
+    if (!g_device_math) return pow(v, 1.0 / (double)p);
+    if (v == 0.0) return 0.0;
+    if (!(v < INFINITY)) return v;
+    const double inv2p = p == 2 ? 0.25 : (p == 3 ? 1.0 / 6.0 : 0.1);
+    const double z = inv2p * (dev_log2(v) - L->log2n);
+    if (!(fabs(z) < 1000.0)) return NAN;
+    return dev_exp2(z);
+}
+static int ck_below_one(const lane_t* L, double v) {
+    return g_device_math ? v < (double)L->n : v < 1.0;
+}
+
+static void ck_solve_one(lane_t* L, double tf, const double* t_eval, int n_eval, double* y_eval,
+                         int max_steps, int* ieval_out, int* st_out) {
+    const otab_t* T = L->T;
+    const int n = L->n, s = T->s;
+    double tw[2] = {1.5, 1.1}, q[2] = {100.0, 100.0};
+    int ieval = 0, st = 1;
+    while (st == 1) {
+        int step_rejected = 0, accepted = 0;
+        double y_new[MAXN], h = 0.0;
+        reassess(L);
+        while (!accepted) {
+            if (L->h_abs < L->min_step) { st = ST_TOO_SMALL; break; }
+            h = L->h_abs * L->direction;
+            memcpy(L->K[0], L->fcur, sizeof(double) * n);
+            rk_stage(L, h, 1);
+            const double E1 = ck_root(L, ck_solution(L, 0, h, y_new), 2);
+            double esttol = E1 / q[0];
+            int retried = 0;
+            if (E1 < tw[0] * q[0]) {
+                rk_stage(L, h, 2);
+                rk_stage(L, h, 3);
+                const double E2 = ck_root(L, ck_solution(L, 1, h, y_new), 3);
+                esttol = E2 / q[1];
+                if (E2 < tw[1] * q[1]) {
+                    rk_stage(L, h, 4);
+                    rk_stage(L, h, 5);
+                    double E4 = ck_root(L, ck_solution(L, 4, h, y_new), 5);
+                    if (E4 == 0.0) E4 = 1e-160;
+                    esttol = E4;
+                    if (E4 < 1.0) {
+                        accepted = 4;
+                        double factor = pymin(T->ck_max_factor, T->ck_safety / E4);
+                        if (step_rejected) factor = pymin(1.0, factor);
+                        L->h_abs *= factor;
+                        const double e12[2] = {E1, E2};
+                        for (int j = 0; j < 2; ++j) {
+                            double qq = e12[j] / E4;
+                            if (qq > q[j]) qq = pymin(qq, 10 * q[j]);
+                            else qq = pymax(qq, 2.0 / 3.0 * q[j]);
+                            q[j] = pymax(1.0, pymin(10000.0, qq));
+                        }
+                        break;
+                    }
+                    if (!(E4 < INFINITY)) { st = ST_OVERFLOW; break; }
+                    const double e12[2] = {E1, E2};
+                    for (int i = 0; i < 2; ++i) {
+                        const double EQ = e12[i] / q[i];
+                        if (EQ < tw[i]) tw[i] = pymax(1.1, EQ);
+                    }
+                    if (E2 < 1.0 && ck_below_one(L, ck_solution(L, 3, h, y_new))) {
+                        accepted = 2;
+                        L->h_abs *= T->C_fallback[1];
+                        h = L->h_abs * L->direction;
+                        break;
+                    }
+                }
+                if (E1 < 1.0) {
+                    if (ck_below_one(L, ck_solution(L, 2, h, y_new))) {
+                        accepted = 1;
+                        L->h_abs *= T->C_fallback[0];
+                        h = L->h_abs * L->direction;
+                        break;
+                    }
+                    step_rejected = 1;
+                    L->h_abs *= T->C_fallback[0];
+                    L->n_rej++;
+                    retried = 1;
+                }
+            }
+            if (!retried) {
+                step_rejected = 1;
+                L->h_abs *= pymax(T->ck_min_factor, T->ck_safety / esttol);
+                L->n_rej++;
+            }
+            if (L->n_acc + L->n_rej >= max_steps) { st = ST_BUDGET; break; }
+        }
+        if (st != 1) break;
+        const double t_new = L->t + h;
+        L->f(t_new, y_new, L->prm, L->K[s]);
+        L->nfev++;
+        if (n_eval > 0) {
+            L->force_cubic = accepted != 4;
+            ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
+        }
+        L->t = t_new;
+        memcpy(L->y, y_new, sizeof(double) * n);
+        memcpy(L->fcur, L->K[s], sizeof(double) * n);
+        L->n_acc++;
+        if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
+        else if (L->n_acc + L->n_rej >= max_steps) st = ST_BUDGET;
+    }
+    *ieval_out = ieval;
+    *st_out = st;
+}
+
 /* One trajectory: solve_ivp(fun, (t0, tf), y0, method=T, ...). */
 static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                          const double* prm, double t0, double tf, double rtol,
@@ -633,6 +766,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                          int32_t* n_eval_done, int nfev_stiff_detect,
                          int32_t* stiff_flags) {
     lane_t* L = (lane_t*)malloc(sizeof(lane_t));
+    L->force_cubic = 0;
     L->nfev_stiff_detect = (T->stbrad > 0.0 && T->tanang > 0.0) ? nfev_stiff_detect : 0;
     L->jflstp = L->okstp = L->stiff_flags = L->n_stiff_tests = 0;
     L->havg = 0.0;
@@ -651,6 +785,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     L->safety_sc = pow(sc[3], sc[0] + sc[1]);
     {   /* the same expressions as xsq_api.cu build_params */
         const double log2n = log2((double)n);
+        L->log2n = log2n;
         L->ctl_a1s = 0.5 * L->err_exp;
         L->ctl_a0s = log2(L->safety) - L->ctl_a1s * log2n;
         L->ctl_a1c = 0.5 * L->minbeta1;
@@ -691,6 +826,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
         ieval = n_eval;
         st = ST_FINISHED;
     }
+    if (T->variant == V_CKDISC && st == 1) ck_solve_one(L, tf, t_eval, n_eval, y_eval, max_steps, &ieval, &st);
     while (st == 1) {
         int step_rejected = 0;
         if (!forced) reassess(L);

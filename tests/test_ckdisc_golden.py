@@ -74,3 +74,36 @@ def test_both_interpolants_are_exercised():
         assert ok
         st_orders.add(st.order_accepted)
     assert {1, 2, 4} <= st_orders or {2, 4} <= st_orders
+
+
+def test_c_restatement_against_the_reference_goldens():
+    """ck_solve_one (oracle/xsq_oracle.c) in the reference's arithmetic (sqrt,
+    pow, true division; sums in index order with fma instead of dgemv order):
+    the same nfev / NFS / accepted steps as the unmodified reference on the
+    golden cases that are not sensitive to last-digit changes, states close on
+    every case with the same step sequence.  The fraction is printed."""
+    from oracle import c_oracle as CO
+    same = 0
+    for c in CASES:
+        fun = make_fun(c["problem"], c["params"])
+        o = CO.rk_batch(TAB, None, c["t_span"], [c["y0"]], t_eval=ck_t_eval(c),
+                        user_fn=fun, **ck_options(c))
+        t_g, y_g = unhex(c["t"]), unhex(c["y"])
+        assert int(o["status"][0]) == c["status"]
+        eq = int(o["nfev"][0]) == c["nfev"] and int(o["n_rejected"][0]) == c["nfs"]
+        same += eq
+        if eq:
+            # rounding differences grow along the trajectory like the method's
+            # own error: compare at a multiple of the requested tolerance
+            opt = ck_options(c)
+            tol = dict(rtol=max(1e-9, 100 * opt.get("rtol", 1e-3)),
+                       atol=max(1e-11, 100 * float(np.max(opt.get("atol", 1e-6)))))
+            if ck_t_eval(c) is None:
+                assert int(o["n_accepted"][0]) == len(t_g) - 1
+                assert np.allclose(o["y_final"][0], y_g[:, -1], **tol), c["id"]
+            else:
+                assert np.allclose(o["y"][0], y_g, **tol), c["id"]
+        else:
+            assert abs(int(o["nfev"][0]) - c["nfev"]) <= 0.12 * c["nfev"] + 6
+    print(f"\nC restatement of CKdisc: identical nfev/NFS on {same} of {len(CASES)} golden cases")
+    assert same >= len(CASES) // 2

@@ -113,6 +113,54 @@ def test_options_bit_identical(kw):
         assert_identical(g, o, (m.__name__, kw))
 
 
+# ---- CKdisc ------------------------------------------------------------------
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_ckdisc_bit_identical_to_oracle_in_device_arithmetic(prob):
+    """rk_persistent<CKdisc> (Lane::attempt_ckdisc) against ck_solve_one of the C
+    oracle in device arithmetic: the variable order step of cash.py:245-416 --
+    assessments, fallback solutions, twiddle / quit adaptation -- reproduced
+    bit for bit on every lane, dense output through both interpolants included."""
+    tab = O.load_ckdisc()
+    lanes, span = {"lorenz63": (lorenz_lanes, (0.0, 12.0)),
+                   "vanderpol": (vdp_lanes, (0.0, 20.0)),
+                   "arenstorf": (arenstorf_lanes, (0.0, 17.0652165601579625588917206249))}[prob]
+    y0, prm = lanes(768)
+    for kw in (dict(rtol=1e-8, atol=1e-10), dict(rtol=1e-4, atol=1e-6),
+               dict(rtol=1e-6, atol=1e-8, t_eval=np.linspace(span[0], span[1], 200))):
+        g = gpu(prob, span, y0, xb.CKdisc, prm, **kw)
+        with CO.device_math():
+            o = CO.rk_batch(tab, prob, span, y0, params=prm, n_threads=THREADS, **kw)
+        assert g["n_rejected"].sum() > 0
+        assert_identical(g, o, ("CKdisc", prob, sorted(kw)), dense="t_eval" in kw)
+
+
+def test_ckdisc_nonsmooth_ensemble_bit_identical_and_cost_of_arithmetic():
+    """DETEST F2 (docs/Cash_Karp.ipynb; the right-hand side switches at every
+    integer t, which is what CKdisc is for) as a user right-hand side: 96 lanes
+    bit-identical to the C oracle in device arithmetic (a Python callback plays
+    the right-hand side there).  How often the reference's own arithmetic takes
+    the same step sequence is printed: that fraction is a property of the
+    problem (steps land on the discontinuities), not of the kernel."""
+    from oracle.problems import CUDA_SOURCES, make_fun
+    tab = O.load_ckdisc()
+    n, p, src = CUDA_SOURCES["detest_f2"]
+    rhs = xb.DeviceRHS.from_source(src, "rhs", n, p)
+    N = 96
+    y0 = np.random.default_rng(7).uniform(60.0, 140.0, (N, 1))
+    kw = dict(rtol=1e-6, atol=1e-8)
+    g = gpu(rhs, (0.0, 6.0), y0, xb.CKdisc, None, max_steps=100000, **kw)
+    fun = make_fun("detest_f2", [])
+    with CO.device_math():
+        o = CO.rk_batch(tab, None, (0.0, 6.0), y0, user_fn=fun, **kw)
+    assert (g["status"] == 0).all() and g["n_rejected"].min() > 0
+    assert_identical(g, o, ("CKdisc", "detest_f2"))
+    r = CO.rk_batch(tab, None, (0.0, 6.0), y0, user_fn=fun, **kw)
+    same = (r["nfev"] == g["nfev"]) & (r["n_rejected"] == g["n_rejected"])
+    print(f"\nCKdisc DETEST F2: {same.sum()} of {N} lanes take the same step sequence in the "
+          f"reference's arithmetic; nfev per lane {g['nfev'].mean():.1f} vs {r['nfev'].mean():.1f}")
+    assert abs(g["nfev"].mean() / r["nfev"].mean() - 1) < 0.05
+
+
 # ---- C3 at its shape ---------------------------------------------------------
 @pytest.mark.parametrize("m", [xb.Pr8, xb.Pr9], ids=lambda m: m.__name__)
 def test_c3_vanderpol_mu_sweep_1000_points(m):

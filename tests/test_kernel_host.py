@@ -86,6 +86,29 @@ def test_kernel_source_dense_output(m):
     same(g, o, (m.__name__, "t_eval"), dense=True)
 
 
+@pytest.mark.parametrize("prob", ["lorenz63", "vanderpol", "arenstorf"])
+def test_ckdisc_kernel_source_equals_oracle_bit_for_bit(prob):
+    """Lane::attempt_ckdisc (cash.py:245-416: assessment after stages 1 and 3,
+    fallback solutions, twiddle / quit adaptation, Horner or cubic output)
+    against ck_solve_one of oracle/xsq_oracle.c in device arithmetic."""
+    tab = O.load_ckdisc()
+    y0, prm, span = lanes(prob, 96)
+    for kw in (dict(rtol=1e-8, atol=1e-10), dict(rtol=1e-4, atol=1e-6),
+               dict(rtol=1e-6, atol=1e-8, t_eval=np.linspace(span[0], span[1], 57)),
+               dict(rtol=1e-5, atol=1e-7, max_step=0.02 * (span[1] - span[0])),
+               dict(rtol=1e-3, atol=1e-3, max_steps=40)):
+        with CO.device_math():
+            o = CO.rk_batch(tab, prob, span, y0, params=prm, n_threads=CO.max_threads(), **kw)
+        g = emu.solve(prob, span, y0, xb.CKdisc, prm, **kw)
+        assert o["n_rejected"].sum() > 0
+        same(g, o, ("CKdisc", prob, sorted(kw)), dense="t_eval" in kw)
+    # backward in time
+    with CO.device_math():
+        o = CO.rk_batch(tab, prob, (span[1] * 0.1, 0.0), y0, params=prm, rtol=1e-6, atol=1e-8)
+    same(emu.solve(prob, (span[1] * 0.1, 0.0), y0, xb.CKdisc, prm, rtol=1e-6, atol=1e-8), o,
+         ("CKdisc", prob, "backward"))
+
+
 @pytest.mark.parametrize("kw", [
     dict(rtol=1e-3, atol=1e-6), dict(rtol=1e-11, atol=1e-13),
     dict(rtol=1e-6, atol=[1e-9, 1e-7, 1e-8]), dict(rtol=1e-8, atol=1e-10, max_step=0.02),
