@@ -499,6 +499,7 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
         out[name] = {"value": acc / (ms * 1e-3), "unit": "accepted steps/s", "ms": ms,
                      "accepted": acc, "rejected": rej,
                      "ok": bool((r.status == 0).all().item()),
+                     "ok_frac": float((r.status == 0).double().mean().item()),
                      "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf,
                                   "unit": "TFLOP/s", "frac": tf / peak_tf,
                                   "flops_per_attempted_step": att_f}}
@@ -560,7 +561,14 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
                          "frac": tf / peak_tf, "flops_model": f"2F + n(6k+30) + k^2, F=60, n=4, k={k:g}"}}
         r2, ms2 = timed_solve(torch, lambda: xb.solve_ivp_batched(
             "arenstorf", (0.0, T), y0, xb.Pr8, params=prm, rtol=RTOL, atol=ATOL), 1)
-        rk_entry("C4_arenstorf_Pr8", r2, ms2, xb.Pr8, 4, 60)["workload"] = "Pr8 on the same lanes"
+        e = rk_entry("C4_arenstorf_Pr8", r2, ms2, xb.Pr8, 4, 60)
+        e["workload"] = "Pr8 on the same lanes"
+        # ~0.1 % of the perturbed orbits run into the Moon (x -> 1 - mu, |v| > 10^3):
+        # the step size falls below the spacing of t and the lane ends with the
+        # reference's status -1 (common.py:233-234).  The C oracle ends the same
+        # lanes the same way (tests/test_gpu_exact.py::test_c4_collision_orbits).
+        e["too_small_step_lanes"] = int((r2.status == -1).sum().item())
+        e["other_failures"] = int(((r2.status != 0) & (r2.status != -1)).sum().item())
         del r, r2, y0, prm
     if "c4b" in which:
         N, nb = 65536, 32

@@ -174,22 +174,22 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     int rc = build_params(a, &P, &mi, &atol);
     if (rc != XSQ_OK) return rc;
     if (a->n_lanes == 0) return XSQ_OK;
-    // scratch: [queue counter (8 B, padded to 16)] [atol vector]
-    //          [init_h N] [init_f0 n_state x N] [init_nfev N]
+    // scratch: [work counter, probe-queue counter, event-queue counter (8 B each, padded
+    //          to 32)] [atol vector] [init_h N] [init_f0 n_state x N] [init_nfev N]
     const size_t N = (size_t)a->n_lanes, ns = atol.size();
-    const size_t off_h = (16 + ns * sizeof(double) + 15) & ~(size_t)15;
+    const size_t off_h = (32 + ns * sizeof(double) + 15) & ~(size_t)15;
     const size_t off_f = off_h + N * sizeof(double);
     const size_t off_n = off_f + N * ns * sizeof(double);
     const size_t bytes = off_n + N * sizeof(int);
     char* scratch = nullptr;
     XSQ_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
-    XSQ_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
-    XSQ_CUDA(cudaMemcpyAsync(scratch + 16, atol.data(),
+    XSQ_CUDA(cudaMemsetAsync(scratch, 0, 32, st));
+    XSQ_CUDA(cudaMemcpyAsync(scratch + 32, atol.data(),
                              atol.size() * sizeof(double),
                              cudaMemcpyHostToDevice, st));
     // the pageable atol copy is staged by the runtime before returning
     P.queue = (unsigned long long*)scratch;
-    P.atol_dev = (const double*)(scratch + 16);
+    P.atol_dev = (const double*)(scratch + 32);
     P.init_h = (double*)(scratch + off_h);
     P.init_f0 = (double*)(scratch + off_f);
     P.init_nfev = (int*)(scratch + off_n);
@@ -249,7 +249,42 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
         P.stiff_q = slots + 2 * threads * rec;
         P.stiff_q_cap = (long long)qcap;
     }
+    // Event queue (xsq_rk_core.cuh after_step / event_queue_body): steps with a
+    // sign change of a non-terminal event wait here for their root solve.  One
+    // record per located event: at most n_events x ev_capacity per trajectory, at
+    // most a third of the free memory; what does not fit is solved in the lane.
+    double* evq = nullptr;
+    P.evq = nullptr;
+    P.evq_cap = 0;
+    P.evq_count = (unsigned long long*)(scratch + 16);
+    {
+        const bool wide = a->n_state > XSQ_MAX_LANE_STATE && a->rhs != XSQ_RHS_NBODY32;
+        if (a->events != 0 && a->method != XSQ_METHOD_SWAG && a->rhs != XSQ_RHS_NBODY32 && !wide &&
+            P.n_events > 0 && P.ev_capacity > 0) {
+            const size_t fields = 5 + (size_t)(mi.s + 3) * (size_t)a->n_state;
+            size_t free_b = 0, total_b = 0;
+            XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t qcap = N * (size_t)P.n_events * (size_t)P.ev_capacity;
+            const size_t fit = (free_b / 3) / (fields * sizeof(double));
+            if (fit < qcap) qcap = fit;
+            if (const char* e = getenv("XSQ_EVENT_QUEUE_RECORDS")) {   // tests: shrink or switch off
+                const long long want_q = atoll(e);
+                if (want_q >= 0 && (size_t)want_q < qcap) qcap = (size_t)want_q;
+            }
+            if (qcap > 0) {
+                cudaError_t es = cudaMallocAsync((void**)&evq, qcap * fields * sizeof(double), st);
+                if (es != cudaSuccess) {
+                    (void)cudaGetLastError();      // no queue: every root in the lane
+                    evq = nullptr;
+                } else {
+                    P.evq = evq;
+                    P.evq_cap = (long long)qcap;
+                }
+            }
+        }
+    }
     rc = dispatch(a->method, a->rhs, a->events, P, mi, st, info);
+    if (evq) cudaFreeAsync(evq, st);
     if (slots) cudaFreeAsync(slots, st);
     cudaError_t e = cudaFreeAsync(scratch, st);
     if (rc == XSQ_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");

@@ -121,6 +121,12 @@ struct RkDev {
     double* t_events;             // [n_lanes][n_events][ev_capacity]
     double* y_events;             // [n_lanes][n_events][ev_capacity][n_state]
     int* ev_count;                // [n_lanes][n_events]
+    // event queue: a step with a sign change that cannot end the trajectory is
+    // appended here (stages + both end states) and the root is located by
+    // event_queue after the persistent kernel; SoA [field][evq_cap]
+    double* evq;
+    long long evq_cap;                      // records; 0 = locate every root in the lane
+    unsigned long long* evq_count;          // may run past evq_cap
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -1248,6 +1254,64 @@ struct Lane {
             return user_event(k, tt, ytmp, prm);
         }, t, t_new);
     }
+    // One record of the event queue, SoA [field][evq_cap]:
+    //   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
+    //   5.. y_old[NL], y_new[NL], K[0..S][NL]
+    static constexpr int EVQ_FIELDS = 5 + (S + 3) * NL;
+    __device__ __forceinline__ void evq_push(const RkDev& P, long long idx, int k, int slot,
+                                             bool cubic, double (&K)[KROWS][NL], double h,
+                                             double t_new, const double (&y_new)[NL]) {
+        double* q = P.evq + idx;
+        const long long cap = P.evq_cap;
+        q[0] = __longlong_as_double(sys);
+        q[cap] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
+                                      ((long long)slot << 32));
+        q[2 * cap] = t;
+        q[3 * cap] = t_new;
+        q[4 * cap] = h;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            q[(5 + c) * cap] = y[c];
+            q[(5 + NL + c) * cap] = y_new[c];
+        }
+#pragma unroll
+        for (int i = 0; i <= S; ++i)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) q[(5 + (2 + i) * NL + c) * cap] = K[i][c];
+    }
+    // The root of one queued step: what after_step does inside the lane.
+    __device__ void evq_solve(const RkDev& P, long long idx) {
+        const double* q = P.evq + idx;
+        const long long cap = P.evq_cap;
+        sys = __double_as_longlong(q[0]);
+        const long long w = __double_as_longlong(q[cap]);
+        const int k = (int)(w & 0xff), slot = (int)(w >> 32);
+        const bool cubic = (w >> 8) & 1;
+        t = q[2 * cap];
+        double t_new = q[3 * cap];
+        const double h = q[4 * cap];
+        double K[KROWS][NL], y_new[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            y[c] = q[(5 + c) * cap];
+            y_new[c] = q[(5 + NL + c) * cap];
+        }
+#pragma unroll
+        for (int i = 0; i <= S; ++i)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) K[i][c] = q[(5 + (2 + i) * NL + c) * cap];
+        R::load_params(P.params, sys, P.n_lanes, 0, prm);
+        Dense D;
+        dense_build(P, D, K, h, t_new, y_new, cubic);
+        const double r = event_root(D, K, t_new, y_new, k);
+        double ye[NL];
+        dense_eval(D, K, t_new, y_new, r, ye);
+        const long long base = (sys * XSQ_EVENTS_N + k) * P.ev_capacity + slot;
+        P.t_events[base] = r;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) P.y_events[base * NL + c] = ye[c];
+    }
+
     // Everything solve_ivp does after solver.step() returned (ivp.py): events,
     // then the t_eval points of the step.  Returns true when a terminal event
     // ends the trajectory; t_new / y_new are then the event point.
@@ -1267,6 +1331,41 @@ struct Lane {
         }
         bool terminate = false;
         double t_stop = t_new;
+        // Deferred root location.  A root solve inside the lane runs while the
+        // other 31 lanes of the warp wait (4 % of the steps carry an event on a
+        // Poincare-section workload, so 3 of 4 warp iterations used to pay for
+        // one).  When no active event of this step can be terminal at this
+        // occurrence, nothing the lane does next depends on the root: it
+        // reserves the output slot, appends the step (stages, end states) to
+        // the event queue and goes on; event_queue_body locates the roots of all
+        // queued steps afterwards, one thread per record, with the same
+        // dense_build / event_root / dense_eval -- the same bits.  What does
+        // not fit in the queue is solved here.
+        if (active && P.evq_cap > 0 &&
+            (Tab::VARIANT != tab::BS5V || P.interpolant == IP_FREE)) {
+            bool may_end = false;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k)
+                if ((active >> k & 1u) && P.ev_terminal[k] > 0 && ev_n[k] + 1 >= P.ev_terminal[k])
+                    may_end = true;
+            if (!may_end) {
+#pragma unroll
+                for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                    if (!(active >> k & 1u)) continue;
+                    if (ev_n[k] >= P.ev_capacity) {        // no room in the output: count only
+                        ++ev_n[k];
+                        active &= ~(1u << k);
+                        continue;
+                    }
+                    const unsigned long long idx = atomicAdd(P.evq_count, 1ull);
+                    if (idx < (unsigned long long)P.evq_cap) {
+                        evq_push(P, (long long)idx, k, ev_n[k], cubic, K, h, t_new, y_new);
+                        ++ev_n[k];
+                        active &= ~(1u << k);
+                    }
+                }
+            }
+        }
         if (active) {
             dense_build(P, D, K, h, t_new, y_new, cubic);
             bool any_term = false;
@@ -1989,6 +2088,23 @@ __device__ __forceinline__ void stiff_queue_body(const RkDev& P, int cost, doubl
         }
     }
 }
+
+#ifdef XSQ_EVENTS_N
+// Works off the event queue: one thread per queued (step, event) pair.
+template <class Tab, class R>
+__device__ __forceinline__ void event_queue_body(const RkDev& P) {
+    if constexpr (!R::WARP) {
+        unsigned long long n = *P.evq_count;
+        if (n > (unsigned long long)P.evq_cap) n = (unsigned long long)P.evq_cap;
+        const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += step) {
+            Lane<Tab, R> L;
+            L.evq_solve(P, (long long)i);
+        }
+    }
+}
+#endif
 
 template <class R>
 __global__ void __launch_bounds__(128, 6) stiff_queue(const RkDev P, int cost, double stbrad,

@@ -77,6 +77,7 @@ struct Compiled {
     CUfunction fn = nullptr;
     CUfunction init_fn = nullptr;
     CUfunction probe_fn = nullptr;   // null for SWAG modules
+    CUfunction evq_fn = nullptr;     // event queue (modules with event functions)
     int occ = 0;
 };
 std::map<std::string, Compiled> g_cache;
@@ -383,6 +384,9 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
     if (cr == CUDA_SUCCESS &&
         g_api.ModuleGetFunction(&out->probe_fn, out->mod, "xsq_user_probe") != CUDA_SUCCESS)
         out->probe_fn = nullptr;
+    if (cr == CUDA_SUCCESS &&
+        g_api.ModuleGetFunction(&out->evq_fn, out->mod, "xsq_user_evq") != CUDA_SUCCESS)
+        out->evq_fn = nullptr;
     if (cr == CUDA_SUCCESS)
         cr = g_api.OccupancyMaxActiveBlocks(&out->occ, out->fn, 128, 0);
     if (cr != CUDA_SUCCESS) {
@@ -481,7 +485,14 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                       "xsq_user_probe(const xsq::RkDev P, int cost, double stbrad, double tanang) {\n"
                       "    xsq::stiff_queue_body<xsq::rhs::%s>(P, cost, stbrad, tanang);\n}\n",
                       rhsname.c_str());
-    *src = body + buf + buf2 + buf3;
+    char buf4[320] = "";
+    if (!swag && events != 0)
+        std::snprintf(buf4, sizeof buf4,
+                      "extern \"C\" __global__ void __launch_bounds__(128)\n"
+                      "xsq_user_evq(const xsq::RkDev P) {\n"
+                      "    xsq::event_queue_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
+                      tabname.c_str(), rhsname.c_str());
+    *src = body + buf + buf2 + buf3 + buf4;
     if (events != 0) *key += "/E" + std::to_string(events);
     return XSQ_OK;
 }
@@ -581,6 +592,13 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
                                          (CUstream)st, pargs, nullptr);
         count_launch();
         if (cp != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_probe) failed"); return XSQ_ERR_CUDA; }
+    }
+    if (P.evq_cap > 0) {                     // the queued event roots
+        if (!c.evq_fn) { set_detail("event queue kernel missing from the module"); return XSQ_ERR_CUDA; }
+        CUresult ce = g_api.LaunchKernel(c.evq_fn, (unsigned)(n_sm * 8), 1, 1, 128, 1, 1, 0,
+                                         (CUstream)st, args, nullptr);
+        count_launch();
+        if (ce != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_evq) failed"); return XSQ_ERR_CUDA; }
     }
     return XSQ_OK;
 }

@@ -254,3 +254,41 @@ def test_events_with_a_user_tableau():
         tg = o["t_events"][k]
         assert np.allclose(r.t_events.cpu().numpy()[0, k, :tg.size], tg, rtol=1e-9, atol=1e-9)
     assert abs(float(r.t_final[0]) - 7.4) < 1e-12
+
+
+@pytest.mark.parametrize("method", ["Ts5", "BS5", "Pr8", "CKdisc"])
+def test_event_queue_and_in_lane_root_solves_are_bit_identical(method, monkeypatch):
+    """Steps whose sign changes cannot end the trajectory are queued and their
+    roots located by event_queue_body after the persistent kernel; what does not
+    fit in the queue (or may be terminal) is solved inside the lane.  Same
+    dense_build / brentq / dense_eval code on the same stages: every event time
+    and state, count and final state must be equal bit for bit whether the queue
+    is off (0 records), overflows (a few records) or takes everything."""
+    N = 3000
+    rng = np.random.default_rng(11)
+    y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+    prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
+    te = np.linspace(0.0, 5.0, 41)
+    for term, kw in (([0, 0, 0], {}), ([0, 6, 0], {}), ([0, 0, 0], dict(t_eval=te)),
+                     ([3, 0, 0], dict(t_eval=te))):
+        ev = events_for("lorenz_sections", term, [1, 0, -1])
+        runs = []
+        for q in ("0", "1500", None):
+            if q is None:
+                monkeypatch.delenv("XSQ_EVENT_QUEUE_RECORDS", raising=False)
+            else:
+                monkeypatch.setenv("XSQ_EVENT_QUEUE_RECORDS", q)
+            r = xb.solve_ivp_batched("lorenz63", (0.0, 5.0), y0, getattr(xb, method), params=prm,
+                                     rtol=1e-7, atol=1e-9, events=ev, max_event_records=12, **kw)
+            torch.cuda.synchronize()
+            runs.append({k: getattr(r, k).cpu().numpy() for k in
+                         ("t_events", "y_events", "event_counts", "y_final", "t_final", "status",
+                          "nfev", "n_accepted") + (("y",) if kw else ())})
+        assert runs[0]["event_counts"].sum() > 5 * N
+        if term[1]:
+            assert (runs[0]["status"] == 1).any()
+        for other in runs[1:]:
+            for k, a in runs[0].items():
+                b = other[k]
+                same = (a == b) | ((a != a) & (b != b))
+                assert same.all(), (method, term, k, np.argwhere(~same)[:4])

@@ -161,6 +161,31 @@ def test_ckdisc_nonsmooth_ensemble_bit_identical_and_cost_of_arithmetic():
     assert abs(g["nfev"].mean() / r["nfev"].mean() - 1) < 0.05
 
 
+# ---- C4: the perturbed Arenstorf ensemble of bench.py ----------------------------
+def test_c4_collision_orbits():
+    """The first 16 384 lanes of bench.py's C4 ensemble (Arenstorf initial state
+    +- 1e-3, one period) with Pr8.  About one lane in a thousand hits the Moon's
+    singularity: the step size falls below the spacing of t and the reference
+    gives up with 'required step size is less than spacing between numbers'
+    (common.py:233-234) -- status -1 here.  Same lanes, same time of failure,
+    same bits as the C oracle in device arithmetic."""
+    N = 16384
+    rng = np.random.default_rng(2024)
+    y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252240537862224]) + \
+        rng.uniform(-1e-3, 1e-3, (1_000_000, 4))[:N]
+    prm = np.full((N, 1), 0.012277471)
+    span = (0.0, 17.0652165601579625588917206249)
+    kw = dict(rtol=1e-8, atol=1e-10)
+    g = gpu("arenstorf", span, y0, xb.Pr8, prm, **kw)
+    o = oracle("arenstorf", span, y0, xb.Pr8, prm, **kw)
+    assert_identical(g, o, ("Pr8", "C4"))
+    failed = g["status"] != 0
+    print(f"\nC4 Pr8: {failed.sum()} of {N} lanes end with status -1 (collision orbits)")
+    assert (g["status"][failed] == -1).all() and 0 < failed.sum() < 0.01 * N
+    # every failed lane is at the Moon: x = 1 - mu, y = 0
+    assert np.abs(g["y_final"][failed, 0] - (1 - 0.012277471)).max() < 1e-6
+
+
 # ---- C3 at its shape ---------------------------------------------------------
 @pytest.mark.parametrize("m", [xb.Pr8, xb.Pr9], ids=lambda m: m.__name__)
 def test_c3_vanderpol_mu_sweep_1000_points(m):
