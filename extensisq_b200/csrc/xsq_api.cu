@@ -118,7 +118,7 @@ static std::atomic<int> g_profile{0};
 static constexpr int kProfRing = 8;             // the last 8 profiled solves
 static cudaEvent_t g_prof_ev[kProfRing][4] = {};
 static long long g_prof_count = 0;
-static void prof_mark(int i, cudaStream_t st) {
+void prof_mark(int i, cudaStream_t st) {
     if (!g_profile.load(std::memory_order_relaxed)) return;
     cudaEvent_t* ev = g_prof_ev[g_prof_count % kProfRing];
     if (!ev[i]) cudaEventCreate(&ev[i]);

@@ -1188,7 +1188,8 @@ struct Lane {
         int npol;
         bool anchor_end, cubic, built;
     };
-    __device__ void dense_build(const RkDev& P, Dense& D, double (&K)[KROWS][NL], double h,
+    template <class Cfg>
+    __device__ void dense_build(const Cfg& P, Dense& D, double (&K)[KROWS][NL], double h,
                                 double t_new, const double (&y_new)[NL], bool cubic) {
         D.built = true;
         D.cubic = cubic || Tab::NPOL == 0;
@@ -1254,6 +1255,99 @@ struct Lane {
             return user_event(k, tt, ytmp, prm);
         }, t, t_new);
     }
+    // The roots of the active events of this step, located now (scipy's
+    // handle_events, ivp.py): counts, terminal decision, event records.
+    struct EvCfg {
+        int ev_terminal[XSQ_EVENTS_N];
+        int ev_capacity, interpolant;
+        double direction;
+        double* t_events;
+        double* y_events;
+    };
+    template <class Cfg>
+    __device__ __forceinline__ void events_now(const Cfg& P, Dense& D, double (&K)[KROWS][NL],
+                                               double h, double t_new, const double (&y_new)[NL],
+                                               bool cubic, unsigned active, bool& terminate,
+                                               double& t_stop) {
+        double root[XSQ_EVENTS_N];
+        {
+            dense_build(P, D, K, h, t_new, y_new, cubic);
+            bool any_term = false;
+            double r_star = 0.0;
+            // Each lane works through ITS OWN active events, so lanes that
+            // solve for different event functions iterate together (the index k
+            // is lane data, not a uniform loop variable): the warp pays for the
+            // longest per-lane sequence, not for one root solve per function.
+            for (unsigned todo = active; todo; todo &= todo - 1u) {
+                const int k = __ffs(todo) - 1;
+                const double r = event_root(D, K, t_new, y_new, k);
+#pragma unroll
+                for (int kk = 0; kk < XSQ_EVENTS_N; ++kk)
+                    if (kk == k) root[kk] = r;
+            }
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                ++ev_n[k];
+                if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
+                    // handle_events: the first terminal root in time order
+                    if (!any_term || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
+                    any_term = true;
+                }
+            }
+            terminate = any_term;
+            if (terminate) t_stop = r_star;
+#pragma unroll
+            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                if (!(active >> k & 1u)) continue;
+                if (terminate && P.direction * (root[k] - r_star) > 0.0) continue;   // after the stop
+                const int slot = ev_n[k] - 1;
+                if (slot < P.ev_capacity) {
+                    const long long base = (sys * XSQ_EVENTS_N + k) * P.ev_capacity + slot;
+                    double ye[NL];
+                    dense_eval(D, K, t_new, y_new, root[k], ye);
+                    P.t_events[base] = root[k];
+#pragma unroll
+                    for (int c = 0; c < NL; ++c) P.y_events[base * NL + c] = ye[c];
+                }
+            }
+        }
+    }
+    struct EvSlow {
+        double K[S + 1][NL];
+        double y[NL], y_new[NL], prm[R::NPL];
+        double t, t_new, h, t_stop;
+        long long sys;
+        EvCfg cfg;
+        int ev_n[XSQ_EVENTS_N];
+        unsigned active;
+        bool cubic, terminate;
+    };
+    static __device__ __noinline__ void events_slow(EvSlow& a) {
+        Lane L;
+        L.t = a.t;
+        L.sys = a.sys;
+        double K[KROWS][NL], y_new[NL];
+#pragma unroll
+        for (int i = 0; i <= S; ++i)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) K[i][c] = a.K[i][c];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { L.y[c] = a.y[c]; y_new[c] = a.y_new[c]; }
+#pragma unroll
+        for (int c = 0; c < R::NPL; ++c) L.prm[c] = a.prm[c];
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) L.ev_n[k] = a.ev_n[k];
+        Dense D;
+        bool terminate = false;
+        double t_stop = a.t_new;
+        L.events_now(a.cfg, D, K, a.h, a.t_new, y_new, a.cubic, a.active, terminate, t_stop);
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) a.ev_n[k] = L.ev_n[k];
+        a.terminate = terminate;
+        a.t_stop = t_stop;
+    }
+
     // One record of the event queue, SoA [field][evq_cap]:
     //   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
     //   5.. y_old[NL], y_new[NL], K[0..S][NL]
@@ -1319,7 +1413,7 @@ struct Lane {
                                double (&y_new)[NL], int lane, bool cubic) {
         Dense D;
         D.built = false;
-        double g_new[XSQ_EVENTS_N], root[XSQ_EVENTS_N];
+        double g_new[XSQ_EVENTS_N];
         unsigned active = 0;
 #pragma unroll
         for (int k = 0; k < XSQ_EVENTS_N; ++k) {
@@ -1367,45 +1461,40 @@ struct Lane {
             }
         }
         if (active) {
-            dense_build(P, D, K, h, t_new, y_new, cubic);
-            bool any_term = false;
-            double r_star = 0.0;
-            // Each lane works through ITS OWN active events, so lanes that
-            // solve for different event functions iterate together (the index k
-            // is lane data, not a uniform loop variable): the warp pays for the
-            // longest per-lane sequence, not for one root solve per function.
-            for (unsigned todo = active; todo; todo &= todo - 1u) {
-                const int k = __ffs(todo) - 1;
-                const double r = event_root(D, K, t_new, y_new, k);
+            if constexpr (Tab::VARIANT == tab::BS5V) {
+                // BS5's low / best interpolants evaluate extra stages of this lane
+                events_now(P, D, K, h, t_new, y_new, cubic, active, terminate, t_stop);
+            } else {
+                // Rare (a terminal occurrence, or the queue is full): out of line, so
+                // that the root finder's registers and code are not the hot loop's.
+                // The stages are copied into a local-memory block; K itself stays in
+                // registers.
+                EvSlow a;
 #pragma unroll
-                for (int kk = 0; kk < XSQ_EVENTS_N; ++kk)
-                    if (kk == k) root[kk] = r;
-            }
+                for (int i = 0; i <= S; ++i)
 #pragma unroll
-            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
-                if (!(active >> k & 1u)) continue;
-                ++ev_n[k];
-                if (P.ev_terminal[k] > 0 && ev_n[k] >= P.ev_terminal[k]) {
-                    // handle_events: the first terminal root in time order
-                    if (!any_term || P.direction * (root[k] - r_star) < 0.0) r_star = root[k];
-                    any_term = true;
+                    for (int c = 0; c < NL; ++c) a.K[i][c] = K[i][c];
+#pragma unroll
+                for (int c = 0; c < NL; ++c) { a.y[c] = y[c]; a.y_new[c] = y_new[c]; }
+#pragma unroll
+                for (int c = 0; c < R::NPL; ++c) a.prm[c] = prm[c];
+#pragma unroll
+                for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+                    a.ev_n[k] = ev_n[k];
+                    a.cfg.ev_terminal[k] = P.ev_terminal[k];
                 }
-            }
-            terminate = any_term;
-            if (terminate) t_stop = r_star;
+                a.cfg.ev_capacity = P.ev_capacity;
+                a.cfg.interpolant = P.interpolant;
+                a.cfg.direction = P.direction;
+                a.cfg.t_events = P.t_events;
+                a.cfg.y_events = P.y_events;
+                a.t = t; a.t_new = t_new; a.h = h; a.sys = sys;
+                a.active = active; a.cubic = cubic;
+                events_slow(a);
 #pragma unroll
-            for (int k = 0; k < XSQ_EVENTS_N; ++k) {
-                if (!(active >> k & 1u)) continue;
-                if (terminate && P.direction * (root[k] - r_star) > 0.0) continue;   // after the stop
-                const int slot = ev_n[k] - 1;
-                if (slot < P.ev_capacity) {
-                    const long long base = (sys * XSQ_EVENTS_N + k) * P.ev_capacity + slot;
-                    double ye[NL];
-                    dense_eval(D, K, t_new, y_new, root[k], ye);
-                    P.t_events[base] = root[k];
-#pragma unroll
-                    for (int c = 0; c < NL; ++c) P.y_events[base * NL + c] = ye[c];
-                }
+                for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = a.ev_n[k];
+                terminate = a.terminate;
+                t_stop = a.t_stop;
             }
         }
 #pragma unroll
@@ -1425,6 +1514,7 @@ struct Lane {
             } while (P.direction * (te - t_stop) <= 0.0);
         }
         if (terminate) {
+            if (!D.built) dense_build(P, D, K, h, t_new, y_new, cubic);
             double ys[NL];
             dense_eval(D, K, t_new, y_new, t_stop, ys);          // y = sol(t)
 #pragma unroll

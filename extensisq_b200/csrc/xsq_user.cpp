@@ -457,8 +457,14 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
         if (!n) return XSQ_ERR_ARG;
         body += "#include \"xsq_rhs.cuh\"\n";
         rhsname = n;
-        nl = 6;
+        nl = rhs == XSQ_RHS_LORENZ63 ? 3 : (rhs == XSQ_RHS_VANDERPOL ? 2 :
+             (rhs == XSQ_RHS_ARENSTORF ? 4 : 6));
         *key += std::string("/") + n;
+    }
+    int minb = minb_for(s, nl);
+    if (const char* e = getenv("XSQ_USER_MINB")) {       // tuning knob: CTAs per SM
+        const int v = atoi(e);
+        if (v >= 1 && v <= 8) minb = v;
     }
     char buf[512];
     if (swag)
@@ -472,7 +478,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                       "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
                       "xsq_user_kernel(const xsq::RkDev P) {\n"
                       "    xsq::rk_persistent_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
-                      minb_for(s, nl), tabname.c_str(), rhsname.c_str());
+                      minb, tabname.c_str(), rhsname.c_str());
     char buf2[256];
     std::snprintf(buf2, sizeof buf2,
                   "extern \"C\" __global__ void __launch_bounds__(128)\n"
@@ -494,6 +500,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                       tabname.c_str(), rhsname.c_str());
     *src = body + buf + buf2 + buf3 + buf4;
     if (events != 0) *key += "/E" + std::to_string(events);
+    *key += "/B" + std::to_string(minb);
     return XSQ_OK;
 }
 
@@ -555,6 +562,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     if (grid < 1) grid = 1;
     RkDev Pc = P;
     void* args[] = {&Pc};
+    prof_mark(0, st);
     {   // initialisation pass (f0 + h_start), thread per lane
         const long long threads = warp ? P.n_lanes * 32 : P.n_lanes;
         const unsigned igrid = (unsigned)((threads + 127) / 128);
@@ -563,6 +571,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
         count_launch();
         if (ci != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_init) failed"); return XSQ_ERR_CUDA; }
     }
+    prof_mark(1, st);
     // dense-output staging buffer (xsq_rk_core.cuh::eval_put): 4 x NL x 128
     int ns = 6;    // built-in rhs with a user tableau: NL <= 6
     if (rhs >= XSQ_RHS_USER_BASE) ns = ns_user > XSQ_MAX_LANE_STATE ? (ns_user + 31) / 32 : ns_user;
@@ -586,6 +595,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
         set_detail(std::string("cuLaunchKernel: ") + (es ? es : "?"));
         return XSQ_ERR_CUDA;
     }
+    prof_mark(2, st);
     if (P.stiff_q_cap > 0 && c.probe_fn) {   // the queued stiffness probes
         void* pargs[] = {&Pc, &cost, &stbrad, &tanang};
         CUresult cp = g_api.LaunchKernel(c.probe_fn, (unsigned)(n_sm * 8), 1, 1, 128, 1, 1, 0,
@@ -600,6 +610,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
         count_launch();
         if (ce != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_evq) failed"); return XSQ_ERR_CUDA; }
     }
+    prof_mark(3, st);
     return XSQ_OK;
 }
 
@@ -745,6 +756,17 @@ int xsq_events_compile_check(int32_t method, int32_t rhs, int32_t events) {
         std::string log(n, '\0');
         if (n) g_api.GetProgramLog(prog, &log[0]);
         set_detail(std::string("NVRTC: ") + g_api.GetErrorString(r) + "\n" + log);
+    } else if (const char* path = getenv("XSQ_DUMP_CUBIN")) {
+        // developer aid: keep the cubin so that `cuobjdump -res-usage` / `-sass`
+        // can look at a run-time compiled kernel without a GPU
+        size_t n = 0;
+        g_api.GetCUBINSize(prog, &n);
+        std::vector<char> cubin(n);
+        g_api.GetCUBIN(prog, cubin.data());
+        if (FILE* fh = std::fopen(path, "wb")) {
+            std::fwrite(cubin.data(), 1, n, fh);
+            std::fclose(fh);
+        }
     }
     g_api.DestroyProgram(&prog);
     return r == NVRTC_SUCCESS ? XSQ_OK : XSQ_ERR_NVRTC;

@@ -15,6 +15,8 @@ struct MethodInfo {
 
 void set_detail(const std::string& s);
 void count_launch();
+// xsq_profile_*: CUDA events around init / persistent kernel / queue kernels (xsq_api.cu)
+void prof_mark(int i, cudaStream_t st);
 
 bool user_tableau_info(MethodInfo* mi);
 bool user_rhs_shape(int rhs, int* n_state, int* n_param);
