@@ -253,32 +253,50 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     // sign change of a non-terminal event wait here for their root solve.  One
     // record per located event: at most n_events x ev_capacity per trajectory, at
     // most a third of the free memory; what does not fit is solved in the lane.
+    // One region (and one counter, 128 bytes apart) per CTA of the persistent
+    // kernel; with dynamic work distribution the CTAs fill theirs evenly, so a
+    // region gets the mean plus a quarter.
     double* evq = nullptr;
     P.evq = nullptr;
     P.evq_cap = 0;
-    P.evq_count = (unsigned long long*)(scratch + 16);
+    P.evq_stride = 0;
+    P.evq_regions = 1;
+    P.evq_count = nullptr;
     {
         const bool wide = a->n_state > XSQ_MAX_LANE_STATE && a->rhs != XSQ_RHS_NBODY32;
         if (a->events != 0 && a->method != XSQ_METHOD_SWAG && a->rhs != XSQ_RHS_NBODY32 && !wide &&
             P.n_events > 0 && P.ev_capacity > 0) {
+            int dev = 0, n_sm = 0;
+            XSQ_CUDA(cudaGetDevice(&dev));
+            XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            size_t regions = (size_t)n_sm * 4;             // >= the grid user_rk_launch uses
+            if (regions > (N + 127) / 128) regions = (N + 127) / 128;
             const size_t fields = 5 + (size_t)(mi.s + 3) * (size_t)a->n_state;
             size_t free_b = 0, total_b = 0;
             XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
             size_t qcap = N * (size_t)P.n_events * (size_t)P.ev_capacity;
+            if (regions > 1) qcap += qcap / 4;
             const size_t fit = (free_b / 3) / (fields * sizeof(double));
             if (fit < qcap) qcap = fit;
             if (const char* e = getenv("XSQ_EVENT_QUEUE_RECORDS")) {   // tests: shrink or switch off
                 const long long want_q = atoll(e);
                 if (want_q >= 0 && (size_t)want_q < qcap) qcap = (size_t)want_q;
             }
-            if (qcap > 0) {
-                cudaError_t es = cudaMallocAsync((void**)&evq, qcap * fields * sizeof(double), st);
+            const size_t cap_r = qcap / regions;
+            if (cap_r > 0) {
+                const size_t cnt_bytes = regions * 16 * sizeof(unsigned long long);
+                cudaError_t es = cudaMallocAsync(
+                    (void**)&evq, cnt_bytes + cap_r * regions * fields * sizeof(double), st);
                 if (es != cudaSuccess) {
                     (void)cudaGetLastError();      // no queue: every root in the lane
                     evq = nullptr;
                 } else {
-                    P.evq = evq;
-                    P.evq_cap = (long long)qcap;
+                    XSQ_CUDA(cudaMemsetAsync(evq, 0, cnt_bytes, st));
+                    P.evq_count = (unsigned long long*)evq;
+                    P.evq = (double*)((char*)evq + cnt_bytes);
+                    P.evq_cap = (long long)cap_r;
+                    P.evq_regions = (int)regions;
+                    P.evq_stride = (long long)(cap_r * regions);
                 }
             }
         }

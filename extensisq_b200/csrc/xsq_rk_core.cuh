@@ -124,9 +124,14 @@ struct RkDev {
     // event queue: a step with a sign change that cannot end the trajectory is
     // appended here (stages + both end states) and the root is located by
     // event_queue after the persistent kernel; SoA [field][evq_cap]
+    // The queue is split into `evq_regions` regions of evq_cap records, one per
+    // CTA of the persistent kernel, each with its own counter (16 words apart):
+    // 10^8 appends to ONE counter serialise in the L2 atomic unit.
     double* evq;
-    long long evq_cap;                      // records; 0 = locate every root in the lane
-    unsigned long long* evq_count;          // may run past evq_cap
+    long long evq_cap;                      // records per region; 0 = locate every root in the lane
+    long long evq_stride;                   // evq_regions * evq_cap: records per field
+    int evq_regions;
+    unsigned long long* evq_count;          // [evq_regions * 16]; may run past evq_cap
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -1348,7 +1353,7 @@ struct Lane {
         a.t_stop = t_stop;
     }
 
-    // One record of the event queue, SoA [field][evq_cap]:
+    // One record of the event queue, SoA [field][evq_stride]:
     //   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
     //   5.. y_old[NL], y_new[NL], K[0..S][NL]
     static constexpr int EVQ_FIELDS = 5 + (S + 3) * NL;
@@ -1356,7 +1361,7 @@ struct Lane {
                                              bool cubic, double (&K)[KROWS][NL], double h,
                                              double t_new, const double (&y_new)[NL]) {
         double* q = P.evq + idx;
-        const long long cap = P.evq_cap;
+        const long long cap = P.evq_stride;
         q[0] = __longlong_as_double(sys);
         q[cap] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
                                       ((long long)slot << 32));
@@ -1376,7 +1381,7 @@ struct Lane {
     // The root of one queued step: what after_step does inside the lane.
     __device__ void evq_solve(const RkDev& P, long long idx) {
         const double* q = P.evq + idx;
-        const long long cap = P.evq_cap;
+        const long long cap = P.evq_stride;
         sys = __double_as_longlong(q[0]);
         const long long w = __double_as_longlong(q[cap]);
         const int k = (int)(w & 0xff), slot = (int)(w >> 32);
@@ -1451,9 +1456,11 @@ struct Lane {
                         active &= ~(1u << k);
                         continue;
                     }
-                    const unsigned long long idx = atomicAdd(P.evq_count, 1ull);
+                    const int region = (int)(blockIdx.x % (unsigned)P.evq_regions);
+                    const unsigned long long idx = atomicAdd(P.evq_count + 16 * region, 1ull);
                     if (idx < (unsigned long long)P.evq_cap) {
-                        evq_push(P, (long long)idx, k, ev_n[k], cubic, K, h, t_new, y_new);
+                        evq_push(P, region * P.evq_cap + (long long)idx, k, ev_n[k], cubic, K, h,
+                                 t_new, y_new);
                         ++ev_n[k];
                         active &= ~(1u << k);
                     }
@@ -2184,13 +2191,18 @@ __device__ __forceinline__ void stiff_queue_body(const RkDev& P, int cost, doubl
 template <class Tab, class R>
 __device__ __forceinline__ void event_queue_body(const RkDev& P) {
     if constexpr (!R::WARP) {
-        unsigned long long n = *P.evq_count;
-        if (n > (unsigned long long)P.evq_cap) n = (unsigned long long)P.evq_cap;
-        const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-             i < n; i += step) {
-            Lane<Tab, R> L;
-            L.evq_solve(P, (long long)i);
+        // the regions are walked as one sequence of 128-record tiles, so that the
+        // blocks share the work evenly whatever each region holds
+        const long long tiles_per_region = (P.evq_cap + blockDim.x - 1) / blockDim.x;
+        for (long long tile = blockIdx.x; tile < tiles_per_region * P.evq_regions; tile += gridDim.x) {
+            const int region = (int)(tile / tiles_per_region);
+            unsigned long long n = P.evq_count[16 * region];
+            if (n > (unsigned long long)P.evq_cap) n = (unsigned long long)P.evq_cap;
+            const long long i = (tile % tiles_per_region) * blockDim.x + threadIdx.x;
+            if ((unsigned long long)i < n) {
+                Lane<Tab, R> L;
+                L.evq_solve(P, region * P.evq_cap + i);
+            }
         }
     }
 }

@@ -561,6 +561,10 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     RkDev Pc = P;
+    if (Pc.evq_cap > 0 && grid < Pc.evq_regions) {   // one event-queue region per CTA
+        Pc.evq_regions = (int)grid;
+        Pc.evq_cap = Pc.evq_stride / grid;
+    }
     void* args[] = {&Pc};
     prof_mark(0, st);
     {   // initialisation pass (f0 + h_start), thread per lane
