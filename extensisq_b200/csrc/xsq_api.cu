@@ -271,7 +271,7 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
             XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
             size_t regions = (size_t)n_sm * 4;             // >= the grid user_rk_launch uses
             if (regions > (N + 127) / 128) regions = (N + 127) / 128;
-            const size_t fields = 5 + (size_t)(mi.s + 3) * (size_t)a->n_state;
+            const size_t fields = (5 + (size_t)(mi.s + 3) * (size_t)a->n_state + 1) & ~(size_t)1;
             size_t free_b = 0, total_b = 0;
             XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
             size_t qcap = N * (size_t)P.n_events * (size_t)P.ev_capacity;
@@ -284,7 +284,9 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
             }
             const size_t cap_r = qcap / regions;
             if (cap_r > 0) {
-                const size_t cnt_bytes = regions * 16 * sizeof(unsigned long long);
+                // counters for any grid the launch may choose (<= 16 CTAs per SM)
+                const size_t max_regions = (size_t)n_sm * 16;
+                const size_t cnt_bytes = max_regions * sizeof(unsigned long long);
                 cudaError_t es = cudaMallocAsync(
                     (void**)&evq, cnt_bytes + cap_r * regions * fields * sizeof(double), st);
                 if (es != cudaSuccess) {
@@ -295,7 +297,7 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
                     P.evq_count = (unsigned long long*)evq;
                     P.evq = (double*)((char*)evq + cnt_bytes);
                     P.evq_cap = (long long)cap_r;
-                    P.evq_regions = (int)regions;
+                    P.evq_regions = (int)max_regions;      // user_rk_launch: = its grid
                     P.evq_stride = (long long)(cap_r * regions);
                 }
             }

@@ -124,14 +124,16 @@ struct RkDev {
     // event queue: a step with a sign change that cannot end the trajectory is
     // appended here (stages + both end states) and the root is located by
     // event_queue after the persistent kernel; SoA [field][evq_cap]
-    // The queue is split into `evq_regions` regions of evq_cap records, one per
-    // CTA of the persistent kernel, each with its own counter (16 words apart):
-    // 10^8 appends to ONE counter serialise in the L2 atomic unit.
+    // The queue is split into one region of evq_cap records per CTA of the
+    // persistent kernel (evq_regions = its grid).  A CTA appends through a counter
+    // in its shared memory -- a lane that waits for a global atomic keeps its whole
+    // warp waiting (measured: the largest stall of the first version) -- and
+    // publishes the count in evq_count[region] when its warps leave the loop.
     double* evq;
     long long evq_cap;                      // records per region; 0 = locate every root in the lane
-    long long evq_stride;                   // evq_regions * evq_cap: records per field
+    long long evq_stride;                   // records in the whole allocation
     int evq_regions;
-    unsigned long long* evq_count;          // [evq_regions * 16]; may run past evq_cap
+    unsigned long long* evq_count;          // [evq_regions]; may run past evq_cap
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -1353,52 +1355,68 @@ struct Lane {
         a.t_stop = t_stop;
     }
 
-    // One record of the event queue, SoA [field][evq_stride]:
+    // One record of the event queue: EVQ_FIELDS consecutive doubles (16-byte
+    // aligned, written and read with 128-bit accesses):
     //   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
     //   5.. y_old[NL], y_new[NL], K[0..S][NL]
-    static constexpr int EVQ_FIELDS = 5 + (S + 3) * NL;
+    static constexpr int EVQ_FIELDS = (5 + (S + 3) * NL + 1) & ~1;
+    // The CTA's own append counter (its region of the queue belongs to it alone);
+    // the total goes to P.evq_count when a warp leaves the persistent loop.
+    static __device__ __forceinline__ unsigned& evq_counter() {
+        __shared__ unsigned n;
+        return n;
+    }
     __device__ __forceinline__ void evq_push(const RkDev& P, long long idx, int k, int slot,
                                              bool cubic, double (&K)[KROWS][NL], double h,
                                              double t_new, const double (&y_new)[NL]) {
-        double* q = P.evq + idx;
-        const long long cap = P.evq_stride;
-        q[0] = __longlong_as_double(sys);
-        q[cap] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
+        double rec[EVQ_FIELDS];
+        rec[0] = __longlong_as_double(sys);
+        rec[1] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
                                       ((long long)slot << 32));
-        q[2 * cap] = t;
-        q[3 * cap] = t_new;
-        q[4 * cap] = h;
+        rec[2] = t;
+        rec[3] = t_new;
+        rec[4] = h;
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
-            q[(5 + c) * cap] = y[c];
-            q[(5 + NL + c) * cap] = y_new[c];
+            rec[5 + c] = y[c];
+            rec[5 + NL + c] = y_new[c];
         }
 #pragma unroll
         for (int i = 0; i <= S; ++i)
 #pragma unroll
-            for (int c = 0; c < NL; ++c) q[(5 + (2 + i) * NL + c) * cap] = K[i][c];
+            for (int c = 0; c < NL; ++c) rec[5 + (2 + i) * NL + c] = K[i][c];
+        if constexpr (((5 + (S + 3) * NL) & 1) != 0) rec[EVQ_FIELDS - 1] = 0.0;
+        double2* q = reinterpret_cast<double2*>(P.evq + idx * EVQ_FIELDS);
+#pragma unroll
+        for (int j = 0; j < EVQ_FIELDS / 2; ++j) q[j] = make_double2(rec[2 * j], rec[2 * j + 1]);
     }
     // The root of one queued step: what after_step does inside the lane.
     __device__ void evq_solve(const RkDev& P, long long idx) {
-        const double* q = P.evq + idx;
-        const long long cap = P.evq_stride;
-        sys = __double_as_longlong(q[0]);
-        const long long w = __double_as_longlong(q[cap]);
+        double rec[EVQ_FIELDS];
+        const double2* q = reinterpret_cast<const double2*>(P.evq + idx * EVQ_FIELDS);
+#pragma unroll
+        for (int j = 0; j < EVQ_FIELDS / 2; ++j) {
+            const double2 v = q[j];
+            rec[2 * j] = v.x;
+            rec[2 * j + 1] = v.y;
+        }
+        sys = __double_as_longlong(rec[0]);
+        const long long w = __double_as_longlong(rec[1]);
         const int k = (int)(w & 0xff), slot = (int)(w >> 32);
         const bool cubic = (w >> 8) & 1;
-        t = q[2 * cap];
-        double t_new = q[3 * cap];
-        const double h = q[4 * cap];
+        t = rec[2];
+        double t_new = rec[3];
+        const double h = rec[4];
         double K[KROWS][NL], y_new[NL];
 #pragma unroll
         for (int c = 0; c < NL; ++c) {
-            y[c] = q[(5 + c) * cap];
-            y_new[c] = q[(5 + NL + c) * cap];
+            y[c] = rec[5 + c];
+            y_new[c] = rec[5 + NL + c];
         }
 #pragma unroll
         for (int i = 0; i <= S; ++i)
 #pragma unroll
-            for (int c = 0; c < NL; ++c) K[i][c] = q[(5 + (2 + i) * NL + c) * cap];
+            for (int c = 0; c < NL; ++c) K[i][c] = rec[5 + (2 + i) * NL + c];
         R::load_params(P.params, sys, P.n_lanes, 0, prm);
         Dense D;
         dense_build(P, D, K, h, t_new, y_new, cubic);
@@ -1456,11 +1474,10 @@ struct Lane {
                         active &= ~(1u << k);
                         continue;
                     }
-                    const int region = (int)(blockIdx.x % (unsigned)P.evq_regions);
-                    const unsigned long long idx = atomicAdd(P.evq_count + 16 * region, 1ull);
-                    if (idx < (unsigned long long)P.evq_cap) {
-                        evq_push(P, region * P.evq_cap + (long long)idx, k, ev_n[k], cubic, K, h,
-                                 t_new, y_new);
+                    const unsigned idx = atomicAdd(&evq_counter(), 1u);
+                    if ((long long)idx < P.evq_cap) {
+                        evq_push(P, (long long)blockIdx.x * P.evq_cap + (long long)idx, k, ev_n[k],
+                                 cubic, K, h, t_new, y_new);
                         ++ev_n[k];
                         active &= ~(1u << k);
                     }
@@ -2059,6 +2076,9 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     bool live = false;
     bool exhausted = false;
     const bool fast = P.n_forced == 0 && P.n_eval == 0;
+#ifdef XSQ_EVENTS_N
+    if (threadIdx.x == 0) Lane<Tab, R>::evq_counter() = 0u;    // before the barrier below
+#endif
     math_tabs_init();
     Lane<Tab, R>::stiff_state().bits[threadIdx.x] = 0u;
     // Stiffness probes wait in their slots until kProbeWindow attempts have
@@ -2162,6 +2182,12 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
         __syncwarp(full);
     }
     if (P.nfev_stiff_detect > 0) flush(-1);      // probes of stored trajectories
+#ifdef XSQ_EVENTS_N
+    // the counter only grows: the last warp to leave publishes the CTA's total
+    if (P.evq_cap > 0 && lane == 0)
+        atomicMax(P.evq_count + blockIdx.x,
+                  (unsigned long long)*(volatile unsigned*)&Lane<Tab, R>::evq_counter());
+#endif
 }
 
 // Works off the probe queue: one thread per record, grid-stride (the record
@@ -2196,7 +2222,7 @@ __device__ __forceinline__ void event_queue_body(const RkDev& P) {
         const long long tiles_per_region = (P.evq_cap + blockDim.x - 1) / blockDim.x;
         for (long long tile = blockIdx.x; tile < tiles_per_region * P.evq_regions; tile += gridDim.x) {
             const int region = (int)(tile / tiles_per_region);
-            unsigned long long n = P.evq_count[16 * region];
+            unsigned long long n = P.evq_count[region];
             if (n > (unsigned long long)P.evq_cap) n = (unsigned long long)P.evq_cap;
             const long long i = (tile % tiles_per_region) * blockDim.x + threadIdx.x;
             if ((unsigned long long)i < n) {

@@ -561,7 +561,8 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     RkDev Pc = P;
-    if (Pc.evq_cap > 0 && grid < Pc.evq_regions) {   // one event-queue region per CTA
+    if (Pc.evq_cap > 0) {                     // one event-queue region per CTA
+        if (grid > Pc.evq_regions) grid = Pc.evq_regions;     // (counters allocated)
         Pc.evq_regions = (int)grid;
         Pc.evq_cap = Pc.evq_stride / grid;
     }
