@@ -613,6 +613,43 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
                          "frac": tf / peak_tf,
                          "flops_model": "nfev x 31 x 20 x 32 (pair interactions)"}}
         del r, y0, prm
+    if "events" in which:
+        # scipy's `events=` on the C2 lanes (t in [0, 20]): three event functions, none
+        # terminal, ~87 located events per lane.  Roots are located by event_queue
+        # after the persistent kernel (xsq_rk_core.cuh after_step / evq_solve).
+        import ctypes as C
+        from extensisq_b200 import _lib
+        lib = _lib.load()
+        src = """
+__device__ double event(int k, double t, const double* y, const double* p) {
+    if (k == 0) return y[2] - 27.0;          // Poincare section z = 27, upwards
+    if (k == 1) return y[0];                 // x = 0
+    return y[0] * y[1] - 30.0;
+}"""
+        ev = xb.DeviceEvents.from_source(src, "event", 3, terminal=[0, 0, 0], direction=[1, 0, 0])
+        T = 20.0
+        r0, ms0 = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "lorenz63", (0.0, T), y0_d, xb.Ts5, params=prm_d, rtol=RTOL, atol=ATOL,
+            nfev_stiff_detect=args.stiff), 2)
+        del r0
+        lib.xsq_profile_enable(1)
+        r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+            "lorenz63", (0.0, T), y0_d, xb.Ts5, params=prm_d, rtol=RTOL, atol=ATOL,
+            nfev_stiff_detect=args.stiff, events=ev, max_event_records=64), 2)
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        have = lib.xsq_profile_last(C.byref(a), C.byref(b), C.byref(c)) == 0
+        lib.xsq_profile_enable(0)
+        n_ev = int(r.event_counts.sum().item())
+        e = rk_entry("events_Ts5_lorenz", r, ms, xb.Ts5, 3, 8)
+        e["workload"] = (f"Ts5 + 3 event functions (none terminal), {y0_d.shape[0]} Lorenz lanes, "
+                         f"t in [0,{T:g}]")
+        e["events_located"] = n_ev
+        e["events_per_s"] = n_ev / (ms * 1e-3)
+        e["ms_plain_solve"] = ms0
+        e["vs_plain_solve"] = ms / ms0
+        if have:
+            e["kernels_ms"] = {"init": a.value, "persistent": b.value, "queues": c.value}
+        del r
     return out
 
 
@@ -744,7 +781,7 @@ def main():
     max_ms, max_e2e_ms = stats.tolist()
     acc_all, rej_all = tot.tolist()
 
-    which = set(x for x in args.only.split(",") if x) or {"c2ck5", "c3", "c4a", "c4b", "c5"}
+    which = set(x for x in args.only.split(",") if x) or {"c2ck5", "c3", "c4a", "c4b", "c5", "events"}
     if args.no_extras:
         which = set()
     del flush
