@@ -628,6 +628,8 @@ __device__ double event(int k, double t, const double* y, const double* p) {
 }"""
         ev = xb.DeviceEvents.from_source(src, "event", 3, terminal=[0, 0, 0], direction=[1, 0, 0])
         T = 20.0
+        torch.cuda.empty_cache()            # the queue takes up to a third of the free memory
+        lib.xsq_trim_memory(dev.index if dev.index is not None else 0)
         r0, ms0 = timed_solve(torch, lambda: xb.solve_ivp_batched(
             "lorenz63", (0.0, T), y0_d, xb.Ts5, params=prm_d, rtol=RTOL, atol=ATOL,
             nfev_stiff_detect=args.stiff), 2)

@@ -8,7 +8,7 @@ Nystrom, sensitivity) is out of scope.
 from .tableaux import (RungeKutta, Ts5, BS5, CK5, CKdisc, Me4, Pr7, Pr8, Pr9,
                        CFMR7osc, SWAG, BUILTIN, REFERENCE_VERSION,
                        RungeKuttaNystrom, Fi4N, Fi5N, Mu5Nmb, MR6NN, BUILTIN_RKN)
-from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, solve_ivp_batched, NFS, trim_memory,
+from .batched import (DeviceRHS, DeviceEvents, BatchedOdeResult, BatchedOdeSolution, solve_ivp_batched, NFS, trim_memory,
                       update_nfs)
 from .sharding import shard_bounds, gather_result
 from .sensitivity import sens_forward, SensitivityOutput
@@ -17,7 +17,7 @@ from .pde import (SSV2stab, SlabComm, PdeResult, PdeRHS, solve_pde_rkc, slab_of,
 
 __version__ = "0.1.0"
 __all__ = ["RungeKutta", "Ts5", "BS5", "CK5", "CKdisc", "Me4", "Pr7", "Pr8", "Pr9",
-           "CFMR7osc", "SWAG", "RungeKuttaNystrom", "Fi4N", "Fi5N", "Mu5Nmb", "MR6NN", "DeviceRHS", "DeviceEvents", "BatchedOdeResult", "solve_ivp_batched",
+           "CFMR7osc", "SWAG", "RungeKuttaNystrom", "Fi4N", "Fi5N", "Mu5Nmb", "MR6NN", "DeviceRHS", "DeviceEvents", "BatchedOdeResult", "BatchedOdeSolution", "solve_ivp_batched",
            "NFS", "update_nfs", "trim_memory", "shard_bounds", "gather_result", "sens_forward", "SensitivityOutput", "SSV2stab",
            "SlabComm", "PdeResult", "PdeRHS", "solve_pde_rkc", "slab_of", "nfesig",
            "maxm"]

@@ -120,6 +120,7 @@ class BatchedOdeResult:
     event_counts: object = None  # int32 [N, n_events] occurrences found
     njev: int = 0
     nlu: int = 0
+    sol: object = None          # BatchedOdeSolution when dense_output=True
 
     @property
     def success(self):
@@ -135,6 +136,45 @@ class BatchedOdeResult:
                  "status", "n_eval_done", "stiff_flags", "t_events", "y_events",
                  "event_counts")
         return {k: getattr(self, k) for k in names if getattr(self, k) is not None}
+
+
+class BatchedOdeSolution:
+    """``res.sol`` of ``solve_ivp(..., dense_output=True)`` (ivp.py:730-741,
+    scipy's OdeSolution) for an ensemble: ``sol(t)`` is the methods' own dense
+    output -- Horner / BS5 low / best / cubic / SWAG's interpolant, the one
+    ``t_eval`` is served from -- at any time(s) inside the integrated span.
+
+    Keeping the interpolant of every step of 10^6 lanes would take more memory
+    than the GPU has, so nothing is stored: the step sequence of a lane is a
+    deterministic function of its inputs, and a call repeats the solve with the
+    requested times as ``t_eval``.  The values are therefore exactly those a
+    stored interpolant would give (``sol(t_eval) == res.y`` bit for bit, and
+    ``sol(t_final) == y_final``).  Lanes that ended early (terminal event,
+    failure) return NaN beyond their end, like ``res.y``."""
+
+    def __init__(self, fun, t_span, y0, method, kwargs):
+        self._args = (fun, t_span, y0, method)
+        self._kw = kwargs
+        self.t_min, self.t_max = min(t_span), max(t_span)
+        self.ascending = t_span[1] >= t_span[0]
+
+    def __call__(self, t):
+        t_np = np.asarray(t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t,
+                          dtype=float)
+        scalar = t_np.ndim == 0
+        pts = np.atleast_1d(t_np)
+        if pts.ndim != 1:
+            raise ValueError("`t` must be a float or a 1-D array.")
+        if pts.size and (pts.min() < self.t_min or pts.max() > self.t_max):
+            raise ValueError("`t` outside of the integrated span (no extrapolation on "
+                             "the device).")
+        uniq, inverse = np.unique(pts, return_inverse=True)
+        order = uniq if self.ascending else uniq[::-1]
+        fun, t_span, y0, method = self._args
+        r = solve_ivp_batched(fun, t_span, y0, method, t_eval=order, **self._kw)
+        idx = inverse if self.ascending else (len(uniq) - 1 - inverse)
+        y = r.y[:, :, torch.as_tensor(idx, device=r.y.device)]
+        return y[:, :, 0] if scalar else y
 
 
 def _as_device(x, device, dtype=torch.float64):
@@ -197,7 +237,7 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
                       nfev_stiff_detect=5000, max_steps=None, events=None,
                       max_event_records=16,
                       forced_steps=None, device=None, stream=None,
-                      **extraneous):
+                      dense_output=False, **extraneous):
     """Integrate N independent systems ``y' = fun(t, y; params_i)``.
 
     Parameters follow ``solve_ivp`` / ``RungeKutta.__init__`` (common.py:187):
@@ -226,6 +266,8 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         analogue)
     forced_steps : [k] sequence of |h|; takes exactly these steps, accepting
         each (parity mode of BASELINE.json's north_star)
+    dense_output : bool -- as in ``solve_ivp``: the result carries ``sol``, a
+        callable :class:`BatchedOdeSolution` (``sol(t)`` -> [N, n, len(t)])
 
     Returns a :class:`BatchedOdeResult` with device tensors.
     """
@@ -483,6 +525,15 @@ def solve_ivp_batched(fun, t_span, y0, method, t_eval=None, params=None,
         n_eval_done=n_done, stiff_flags=stiff, t_events=t_ev, y_events=y_ev,
         event_counts=ev_cnt)
     res._keepalive = (y0_soa, prm_soa, hf, atol_c)
+    if dense_output:
+        if forced_steps is not None:
+            raise ValueError("dense_output does not apply to forced_steps")
+        res.sol = BatchedOdeSolution(fun, (t0, tf), y0, method, dict(
+            params=params, rtol=rtol, atol=atol, first_step=first_lanes if first_lanes is not None
+            else first_step, max_step=max_step, sc_params=sc_params, interpolant=interpolant,
+            k_max=k_max if is_swag else None, nfev_stiff_detect=nfev_stiff_detect,
+            max_steps=max_steps, events=events, max_event_records=max_event_records,
+            device=device, stream=stream))
     return res
 
 

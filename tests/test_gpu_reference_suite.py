@@ -115,3 +115,35 @@ def test_integration_zero_rhs(method):     # tests/test_ivp.py:1101-1105
     torch.cuda.synchronize()
     assert int(r.status[0]) == 0 and bool(r.success[0])
     np.testing.assert_allclose(r.y_final.cpu().numpy(), 1.0, rtol=1e-15)
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_dense_output_sol(method):         # tests/test_ivp.py:195-213 (res.sol)
+    """dense_output=True: `res.sol` is callable like scipy's OdeSolution; the
+    values are the method's own dense output (the kernel's t_eval emitter)."""
+    rtol, atol = 1e-3, 1e-6
+    for t_span in ([5, 9], [5, 1]):
+        tc = np.linspace(*t_span)
+        res = xb.solve_ivp_batched(rhs_for("rational"), t_span, [[1 / 3, 2 / 9]],
+                                   getattr(xb, method), t_eval=tc, rtol=rtol, atol=atol,
+                                   dense_output=True)
+        assert isinstance(res.sol, xb.BatchedOdeSolution)
+        yc = res.sol(tc)
+        torch.cuda.synchronize()
+        assert torch.equal(yc, res.y)                       # sol(res.t) == res.y, exactly
+        assert np.all(compute_error(yc.cpu().numpy()[0], sol_rational(tc), rtol, atol) < 5)
+        tm = (t_span[0] + t_span[-1]) / 2                   # a scalar time
+        ym = res.sol(tm).cpu().numpy()[0][:, None]
+        assert ym.shape == (2, 1)
+        assert np.all(compute_error(ym, sol_rational(np.array([tm])), rtol, atol) < 5)
+        # any order, repeated points, both ends of the span
+        tq = np.array([t_span[1], tm, t_span[0], tm, tc[7]])
+        yq = res.sol(tq).cpu().numpy()[0]
+        assert np.array_equal(yq[:, 1], yq[:, 3]) and np.array_equal(yq[:, 1], ym[:, 0])
+        assert np.array_equal(yq[:, 2], [1 / 3, 2 / 9])
+        assert np.allclose(yq[:, 0], res.y_final.cpu().numpy()[0], rtol=1e-13, atol=0)
+        assert np.array_equal(yq[:, 4], res.y.cpu().numpy()[0][:, 7])
+        with pytest.raises(ValueError):
+            res.sol(max(t_span) + 1.0)
+    plain = solve(method, [5, 9])
+    assert plain.sol is None
