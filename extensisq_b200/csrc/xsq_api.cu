@@ -251,17 +251,16 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
     }
     // Event queue (xsq_rk_core.cuh after_step / event_queue_body): steps with a
     // sign change of a non-terminal event wait here for their root solve.  One
-    // record per located event: at most n_events x ev_capacity per trajectory, at
-    // most a third of the free memory; what does not fit is solved in the lane.
-    // One region (and one counter, 128 bytes apart) per CTA of the persistent
-    // kernel; with dynamic work distribution the CTAs fill theirs evenly, so a
-    // region gets the mean plus a quarter.
-    double* evq = nullptr;
+    // record per located event: at most n_events x ev_capacity per trajectory (plus
+    // one partly filled chunk per CTA), at most a third of the free memory; what
+    // does not fit is solved in the lane.
+    // Layout: [chunk counter, 16 B] [fill per chunk] [records].
+    char* evq = nullptr;
     P.evq = nullptr;
     P.evq_cap = 0;
-    P.evq_stride = 0;
-    P.evq_regions = 1;
     P.evq_count = nullptr;
+    P.evq_fill = nullptr;
+    P.evq_exact = 0;
     {
         const bool wide = a->n_state > XSQ_MAX_LANE_STATE && a->rhs != XSQ_RHS_NBODY32;
         if (a->events != 0 && a->method != XSQ_METHOD_SWAG && a->rhs != XSQ_RHS_NBODY32 && !wide &&
@@ -269,36 +268,34 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
             int dev = 0, n_sm = 0;
             XSQ_CUDA(cudaGetDevice(&dev));
             XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            size_t regions = (size_t)n_sm * 4;             // >= the grid user_rk_launch uses
-            if (regions > (N + 127) / 128) regions = (N + 127) / 128;
             const size_t fields = (5 + (size_t)(mi.s + 3) * (size_t)a->n_state + 1) & ~(size_t)1;
             size_t free_b = 0, total_b = 0;
             XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            size_t qcap = N * (size_t)P.n_events * (size_t)P.ev_capacity;
-            if (regions > 1) qcap += qcap / 4;
+            size_t ctas = (size_t)n_sm * 16;                       // more than any launch uses
+            if (ctas > (N + 127) / 128) ctas = (N + 127) / 128;
+            const size_t need = N * (size_t)P.n_events * (size_t)P.ev_capacity + ctas * kEvqChunk;
+            size_t qcap = need;
             const size_t fit = (free_b / 3) / (fields * sizeof(double));
             if (fit < qcap) qcap = fit;
             if (const char* e = getenv("XSQ_EVENT_QUEUE_RECORDS")) {   // tests: shrink or switch off
                 const long long want_q = atoll(e);
                 if (want_q >= 0 && (size_t)want_q < qcap) qcap = (size_t)want_q;
             }
-            const size_t cap_r = qcap / regions;
-            if (cap_r > 0) {
-                // counters for any grid the launch may choose (<= 16 CTAs per SM)
-                const size_t max_regions = (size_t)n_sm * 16;
-                const size_t cnt_bytes = max_regions * sizeof(unsigned long long);
+            const size_t chunks = (qcap + kEvqChunk - 1) / kEvqChunk;
+            if (chunks > 0) {
+                const size_t head = (16 + chunks * sizeof(unsigned) + 255) & ~(size_t)255;
                 cudaError_t es = cudaMallocAsync(
-                    (void**)&evq, cnt_bytes + cap_r * regions * fields * sizeof(double), st);
+                    (void**)&evq, head + chunks * kEvqChunk * fields * sizeof(double), st);
                 if (es != cudaSuccess) {
                     (void)cudaGetLastError();      // no queue: every root in the lane
                     evq = nullptr;
                 } else {
-                    XSQ_CUDA(cudaMemsetAsync(evq, 0, cnt_bytes, st));
+                    XSQ_CUDA(cudaMemsetAsync(evq, 0, head, st));
                     P.evq_count = (unsigned long long*)evq;
-                    P.evq = (double*)((char*)evq + cnt_bytes);
-                    P.evq_cap = (long long)cap_r;
-                    P.evq_regions = (int)max_regions;      // user_rk_launch: = its grid
-                    P.evq_stride = (long long)(cap_r * regions);
+                    P.evq_fill = (unsigned*)(evq + 16);
+                    P.evq = (double*)(evq + head);
+                    P.evq_cap = (long long)(chunks * kEvqChunk);
+                    P.evq_exact = chunks * kEvqChunk >= need ? 1 : 0;
                 }
             }
         }

@@ -60,6 +60,7 @@ enum LaneStatus : int {
 #define XSQ_MAX_BLOCK 256   // largest CTA any rk_persistent geometry launches
 #endif
 enum Interp : int { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
+constexpr int kEvqChunk = 512;   // records per chunk of the event queue
 
 // Device-side parameter block; passed by value as the kernel argument so every
 // field is a constant-bank operand.
@@ -124,16 +125,16 @@ struct RkDev {
     // event queue: a step with a sign change that cannot end the trajectory is
     // appended here (stages + both end states) and the root is located by
     // event_queue after the persistent kernel; SoA [field][evq_cap]
-    // The queue is split into one region of evq_cap records per CTA of the
-    // persistent kernel (evq_regions = its grid).  A CTA appends through a counter
-    // in its shared memory -- a lane that waits for a global atomic keeps its whole
-    // warp waiting (measured: the largest stall of the first version) -- and
-    // publishes the count in evq_count[region] when its warps leave the loop.
+    // The queue is handed out in chunks of kEvqChunk records: a CTA of the
+    // persistent kernel appends through a counter in ITS shared memory -- a lane
+    // that waits for a global atomic keeps its whole warp waiting (measured: the
+    // largest stall of the first version) -- and takes a new chunk from the global
+    // counter when its current one is full (once per kEvqChunk appends).
     double* evq;
-    long long evq_cap;                      // records per region; 0 = locate every root in the lane
-    long long evq_stride;                   // records in the whole allocation
-    int evq_regions;
-    unsigned long long* evq_count;          // [evq_regions]; may run past evq_cap
+    long long evq_cap;                      // records (multiple of kEvqChunk); 0 = no queue
+    unsigned long long* evq_count;          // chunks handed out; may run past the capacity
+    unsigned* evq_fill;                     // [evq_cap / kEvqChunk] records written per chunk
+    int evq_exact;                          // host: the queue holds every possible record
 };
 
 // ---- reductions over one system -------------------------------------------
@@ -798,6 +799,97 @@ template <>
 struct CkExtra<false> {};
 
 // ---- one trajectory ---------------------------------------------------------
+#ifdef XSQ_EVENTS_N
+// ---- event queue: chunked allocation ------------------------------------------
+// word = generation << 32 | records taken from the current chunk; chunk[g & 3] is
+// the chunk of generation g (-1: the queue is exhausted).
+struct EvqShared {
+    unsigned long long word;
+    long long chunk[4];
+};
+__device__ __forceinline__ EvqShared& evq_shared() {
+    __shared__ EvqShared s;
+    return s;
+}
+// thread 0 of the CTA, before a __syncthreads(): generation 0 is "full", so the
+// first append installs the first chunk
+__device__ __forceinline__ void evq_cta_init() {
+    EvqShared& s = evq_shared();
+    s.word = (unsigned long long)kEvqChunk;
+    s.chunk[0] = s.chunk[1] = s.chunk[2] = s.chunk[3] = -1;
+}
+// Index of a free record, or -1 when the queue is exhausted.
+__device__ __forceinline__ long long evq_alloc(const RkDev& P) {
+    EvqShared& s = evq_shared();
+    for (;;) {
+        const unsigned long long old = atomicAdd(&s.word, 1ull);
+        const unsigned g = (unsigned)(old >> 32), i = (unsigned)old;
+        if (i < (unsigned)kEvqChunk) {
+            const long long c = *(volatile long long*)&s.chunk[g & 3u];
+            return c < 0 ? -1 : c * kEvqChunk + (long long)i;
+        }
+        if (i == (unsigned)kEvqChunk) {          // exactly one thread installs the next chunk
+            const long long prev = *(volatile long long*)&s.chunk[g & 3u];
+            if (prev >= 0) atomicMax(P.evq_fill + prev, (unsigned)kEvqChunk);
+            const unsigned long long c = atomicAdd(P.evq_count, 1ull);
+            const long long cc =
+                c < (unsigned long long)(P.evq_cap / kEvqChunk) ? (long long)c : -1;
+            *(volatile long long*)&s.chunk[(g + 1u) & 3u] = cc;
+            __threadfence_block();
+            // the installer takes record 0 of the new chunk itself
+            atomicExch(&s.word, ((unsigned long long)(g + 1u) << 32) | (cc >= 0 ? 1ull : 0ull));
+            return cc < 0 ? -1 : cc * kEvqChunk;
+        }
+        // the chunk filled up while another thread installs the next: wait for it
+        while ((unsigned)(*(volatile unsigned long long*)&s.word >> 32) == g) __nanosleep(40);
+    }
+}
+// lane 0 of every warp when it leaves the persistent loop: the counter only
+// grows, so the last warp publishes the fill of the CTA's last chunk
+__device__ __forceinline__ void evq_cta_publish(const RkDev& P) {
+    EvqShared& s = evq_shared();
+    const unsigned long long w = *(volatile unsigned long long*)&s.word;
+    const long long c = *(volatile long long*)&s.chunk[(unsigned)(w >> 32) & 3u];
+    const unsigned n = (unsigned)w < (unsigned)kEvqChunk ? (unsigned)w : (unsigned)kEvqChunk;
+    if (c >= 0) atomicMax(P.evq_fill + c, n);
+}
+// One record: NF consecutive doubles (16-byte aligned, 128-bit accesses):
+//   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
+//   5.. y_old[NL], y_new[NL], K[0..S][NL]
+template <int S, int NL>
+struct EvqRecord {
+    static constexpr int RAW = 5 + (S + 3) * NL;
+    static constexpr int NF = (RAW + 1) & ~1;
+};
+template <int S, int NL, int KR>
+__device__ __forceinline__ void evq_write(const RkDev& P, long long idx, long long sys, int k,
+                                          int slot, bool cubic, double t, double t_new, double h,
+                                          const double (&y)[NL], const double (&y_new)[NL],
+                                          const double (&K)[KR][NL]) {
+    constexpr int NF = EvqRecord<S, NL>::NF;
+    double rec[NF];
+    rec[0] = __longlong_as_double(sys);
+    rec[1] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
+                                  ((long long)slot << 32));
+    rec[2] = t;
+    rec[3] = t_new;
+    rec[4] = h;
+#pragma unroll
+    for (int c = 0; c < NL; ++c) {
+        rec[5 + c] = y[c];
+        rec[5 + NL + c] = y_new[c];
+    }
+#pragma unroll
+    for (int i = 0; i <= S; ++i)
+#pragma unroll
+        for (int c = 0; c < NL; ++c) rec[5 + (2 + i) * NL + c] = K[i][c];
+    if constexpr ((EvqRecord<S, NL>::RAW & 1) != 0) rec[NF - 1] = 0.0;
+    double2* q = reinterpret_cast<double2*>(P.evq + idx * NF);
+#pragma unroll
+    for (int j = 0; j < NF / 2; ++j) q[j] = make_double2(rec[2 * j], rec[2 * j + 1]);
+}
+#endif
+
 template <class Tab, class R>
 struct Lane {
     static constexpr int S = Tab::S;
@@ -1355,41 +1447,7 @@ struct Lane {
         a.t_stop = t_stop;
     }
 
-    // One record of the event queue: EVQ_FIELDS consecutive doubles (16-byte
-    // aligned, written and read with 128-bit accesses):
-    //   0 trajectory   1 event k | cubic << 8 | output slot << 32   2 t_old   3 t_new   4 h
-    //   5.. y_old[NL], y_new[NL], K[0..S][NL]
-    static constexpr int EVQ_FIELDS = (5 + (S + 3) * NL + 1) & ~1;
-    // The CTA's own append counter (its region of the queue belongs to it alone);
-    // the total goes to P.evq_count when a warp leaves the persistent loop.
-    static __device__ __forceinline__ unsigned& evq_counter() {
-        __shared__ unsigned n;
-        return n;
-    }
-    __device__ __forceinline__ void evq_push(const RkDev& P, long long idx, int k, int slot,
-                                             bool cubic, double (&K)[KROWS][NL], double h,
-                                             double t_new, const double (&y_new)[NL]) {
-        double rec[EVQ_FIELDS];
-        rec[0] = __longlong_as_double(sys);
-        rec[1] = __longlong_as_double((long long)k | ((long long)(cubic ? 1 : 0) << 8) |
-                                      ((long long)slot << 32));
-        rec[2] = t;
-        rec[3] = t_new;
-        rec[4] = h;
-#pragma unroll
-        for (int c = 0; c < NL; ++c) {
-            rec[5 + c] = y[c];
-            rec[5 + NL + c] = y_new[c];
-        }
-#pragma unroll
-        for (int i = 0; i <= S; ++i)
-#pragma unroll
-            for (int c = 0; c < NL; ++c) rec[5 + (2 + i) * NL + c] = K[i][c];
-        if constexpr (((5 + (S + 3) * NL) & 1) != 0) rec[EVQ_FIELDS - 1] = 0.0;
-        double2* q = reinterpret_cast<double2*>(P.evq + idx * EVQ_FIELDS);
-#pragma unroll
-        for (int j = 0; j < EVQ_FIELDS / 2; ++j) q[j] = make_double2(rec[2 * j], rec[2 * j + 1]);
-    }
+    static constexpr int EVQ_FIELDS = EvqRecord<S, NL>::NF;
     // The root of one queued step: what after_step does inside the lane.
     __device__ void evq_solve(const RkDev& P, long long idx) {
         double rec[EVQ_FIELDS];
@@ -1474,10 +1532,10 @@ struct Lane {
                         active &= ~(1u << k);
                         continue;
                     }
-                    const unsigned idx = atomicAdd(&evq_counter(), 1u);
-                    if ((long long)idx < P.evq_cap) {
-                        evq_push(P, (long long)blockIdx.x * P.evq_cap + (long long)idx, k, ev_n[k],
-                                 cubic, K, h, t_new, y_new);
+                    const long long idx = evq_alloc(P);
+                    if (idx >= 0) {
+                        evq_write<S, NL, KROWS>(P, idx, sys, k, ev_n[k], cubic, t, t_new, h, y,
+                                                y_new, K);
                         ++ev_n[k];
                         active &= ~(1u << k);
                     }
@@ -2077,7 +2135,7 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     bool exhausted = false;
     const bool fast = P.n_forced == 0 && P.n_eval == 0;
 #ifdef XSQ_EVENTS_N
-    if (threadIdx.x == 0) Lane<Tab, R>::evq_counter() = 0u;    // before the barrier below
+    if (threadIdx.x == 0) evq_cta_init();                      // before the barrier below
 #endif
     math_tabs_init();
     Lane<Tab, R>::stiff_state().bits[threadIdx.x] = 0u;
@@ -2183,10 +2241,7 @@ __device__ __forceinline__ void rk_persistent_body(const RkDev& P) {
     }
     if (P.nfev_stiff_detect > 0) flush(-1);      // probes of stored trajectories
 #ifdef XSQ_EVENTS_N
-    // the counter only grows: the last warp to leave publishes the CTA's total
-    if (P.evq_cap > 0 && lane == 0)
-        atomicMax(P.evq_count + blockIdx.x,
-                  (unsigned long long)*(volatile unsigned*)&Lane<Tab, R>::evq_counter());
+    if (P.evq_cap > 0 && lane == 0) evq_cta_publish(P);
 #endif
 }
 
@@ -2217,17 +2272,19 @@ __device__ __forceinline__ void stiff_queue_body(const RkDev& P, int cost, doubl
 template <class Tab, class R>
 __device__ __forceinline__ void event_queue_body(const RkDev& P) {
     if constexpr (!R::WARP) {
-        // the regions are walked as one sequence of 128-record tiles, so that the
-        // blocks share the work evenly whatever each region holds
-        const long long tiles_per_region = (P.evq_cap + blockDim.x - 1) / blockDim.x;
-        for (long long tile = blockIdx.x; tile < tiles_per_region * P.evq_regions; tile += gridDim.x) {
-            const int region = (int)(tile / tiles_per_region);
-            unsigned long long n = P.evq_count[region];
-            if (n > (unsigned long long)P.evq_cap) n = (unsigned long long)P.evq_cap;
-            const long long i = (tile % tiles_per_region) * blockDim.x + threadIdx.x;
-            if ((unsigned long long)i < n) {
+        // chunks handed out, walked as tiles of blockDim.x records
+        unsigned long long used = *P.evq_count;
+        const unsigned long long n_chunks = (unsigned long long)(P.evq_cap / kEvqChunk);
+        if (used > n_chunks) used = n_chunks;
+        const long long tpc = kEvqChunk / (int)blockDim.x;          // launched with 128 threads
+        for (long long tile = blockIdx.x; tile < (long long)used * tpc; tile += gridDim.x) {
+            const long long c = tile / tpc;
+            unsigned n = P.evq_fill[c];
+            if (n > (unsigned)kEvqChunk) n = (unsigned)kEvqChunk;
+            const unsigned i = (unsigned)(tile % tpc) * blockDim.x + threadIdx.x;
+            if (i < n) {
                 Lane<Tab, R> L;
-                L.evq_solve(P, region * P.evq_cap + i);
+                L.evq_solve(P, c * kEvqChunk + (long long)i);
             }
         }
     }

@@ -565,11 +565,6 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     RkDev Pc = P;
-    if (Pc.evq_cap > 0) {                     // one event-queue region per CTA
-        if (grid > Pc.evq_regions) grid = Pc.evq_regions;     // (counters allocated)
-        Pc.evq_regions = (int)grid;
-        Pc.evq_cap = Pc.evq_stride / grid;
-    }
     void* args[] = {&Pc};
     prof_mark(0, st);
     {   // initialisation pass (f0 + h_start), thread per lane
