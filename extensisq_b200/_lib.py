@@ -30,6 +30,7 @@ LANE_MESSAGES = {
     -3: "tolerance too tight",
     -4: "spectral radius estimation did not converge",
     -5: "step budget (max_steps) exhausted",
+    -6: "event queue exhausted",
 }
 
 # every symbol include/xsq.h declares (checked by tests/test_abi.py)

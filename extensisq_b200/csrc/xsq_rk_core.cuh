@@ -53,6 +53,7 @@ static constexpr double kMaxFactor0 = 10.0;     // common.py:20
 enum LaneStatus : int {
     LANE_FINISHED = 0, LANE_TOO_SMALL = -1, LANE_OVERFLOW = -2,
     LANE_STEP_BUDGET = -5, LANE_RUNNING = 1,
+    LANE_EVQ_FULL = -6,  // the event queue ran out (cannot happen when RkDev::evq_exact)
     LANE_FLUSH = 2,     // internal: still running, stiffness probe slots are full
     LANE_EVENT = 3      // internal: a terminal event ended the trajectory (status 1)
 };

@@ -31,9 +31,11 @@
 // (_step_impl, _reassess_stepsize, _comp_sol_err, _rk_stage), :370-516
 // (_diagnose_stiffness bookkeeping).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#endif
 #include "xsq_rk_core.cuh"
 
 // build-time variants (measured on B200)
@@ -258,6 +260,13 @@ struct FastLane {
     // (jflstp = n_rej - rej_base)
     double havg;
     int next_cnt, next_many, rej_base;
+#ifdef XSQ_EVENTS_N
+    // scipy's `events=` with no terminal event (kernels compiled at run time with
+    // the user's event functions): occurrences so far.  The previous values of
+    // the event functions are not kept -- g(t, y) of the state the step starts
+    // from is the same number -- and every root is located by event_queue_body.
+    int ev_n[XSQ_EVENTS_N];
+#endif
 
     // RungeKutta.__init__ (common.py:187-220) from what ens_init left
     __device__ __forceinline__ void init(const RkDev& P, int idx, SAddr h0) {
@@ -280,6 +289,10 @@ struct FastLane {
         next_many = P.stiff_many_steps > 1 ? P.stiff_many_steps - 1 : 1;
         next_cnt = 20;
         rej_base = 0;
+#ifdef XSQ_EVENTS_N
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = 0;
+#endif
         sts1(h0, h_abs);
     }
 
@@ -416,6 +429,22 @@ struct FastLane {
         if constexpr (!Tab::FSAL) {
             if (accept) R::f(t_new, y_new, prm, K[S]);
         }
+#ifdef XSQ_EVENTS_N
+        // find_active_events (ivp.py) on the accepted step
+        unsigned ev_active = 0u;
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            const double g0 = user_event(k, t, y, prm);
+            const double g1 = user_event(k, t_new, y_new, prm);
+            const bool up = g0 <= 0.0 && g1 >= 0.0;
+            const bool down = g0 >= 0.0 && g1 <= 0.0;
+            const int d = P.ev_direction[k];
+            if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) ev_active |= 1u << k;
+        }
+        if (!accept) ev_active = 0u;
+#else
+        constexpr unsigned ev_active = 0u;
+#endif
         // ---- controller (common.py:249-287) -----------------------------------
         const double l2 = log2_core_s(ss, sa.lg, sa.lc);
         double cc[6];
@@ -478,13 +507,17 @@ struct FastLane {
         const bool out_of_range = hh - (unsigned)P.fast_hi_min - 1u >= (unsigned)P.fast_hi_span;
         const bool near_end = (int)(dh - hh) <= 0x100000;
         // (bitwise, not short-circuit: no branches)
-        const bool slow_acc = probe | (!done & (out_of_range | near_end));
+        const bool slow_acc = probe | (ev_active != 0u) | (!done & (out_of_range | near_end));
         const bool slow_rej = bad | near_min | ((fl & FL_SLOW) != 0u);
         const bool slow = accept ? slow_acc : slow_rej;
         int st = done ? LANE_FINISHED : LANE_RUNNING;
         if (accept & !done) sts1(sa.h0, h_abs_new);
         if (slow) {
             if (accept) {
+#ifdef XSQ_EVENTS_N
+                if (ev_active != 0u && !push_events(P, ev_active, K, y_new, t_new, h))
+                    st = LANE_EVQ_FULL;
+#endif
                 if (STIFF && probe) {
                     if (diagnose_record(P, K, errv, y_new, t_new, h, havg_new, lotsfl)) {
                         if (st == LANE_RUNNING) st = LANE_FLUSH;
@@ -519,6 +552,31 @@ struct FastLane {
         }
         return st;
     }
+
+#ifdef XSQ_EVENTS_N
+    // The step (stages, both end states) of every active event goes to the event
+    // queue; t and y still hold the start of the step.  False: the queue is
+    // exhausted (the host only selects this kernel when it cannot be).
+    __device__ __forceinline__ bool push_events(const RkDev& P, unsigned active,
+                                                const double (&K)[S + 1][NL],
+                                                const double (&y_new)[NL], double t_new, double h) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            if (!(active >> k & 1u)) continue;
+            if (ev_n[k] < P.ev_capacity) {
+                const long long idx = evq_alloc(P);
+                if (idx >= 0)
+                    evq_write<S, NL, S + 1>(P, idx, (long long)sys, k, ev_n[k], false, t, t_new, h, y,
+                                            y_new, K);
+                else
+                    ok = false;
+            }
+            ++ev_n[k];
+        }
+        return ok;
+    }
+#endif
 
     // The probe of _diagnose_stiffness (common.py:401-516) is deferred exactly as
     // in the generic kernel (Lane::diagnose): its inputs go to a record of the
@@ -578,6 +636,11 @@ struct FastLane {
         if (P.stiff_flags)
             P.stiff_flags[sys] = (int)((Lane<Tab, R>::stiff_state().bits[threadIdx.x] >>
                                         Lane<Tab, R>::SB_FLAG_SHIFT) & 7u);
+#ifdef XSQ_EVENTS_N
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k)
+            P.ev_count[(long long)sys * XSQ_EVENTS_N + k] = ev_n[k];
+#endif
     }
 };
 
@@ -602,6 +665,9 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         lcs.havg[0] = c_xsq_havg[0]; lcs.havg[1] = c_xsq_havg[1];
         for (int i = 0; i < 16; ++i) lcs.atol[i] = P.atol[i];
         memory_fence_for(&lcs);
+#ifdef XSQ_EVENTS_N
+        evq_cta_init();
+#endif
     }
     LN::stiff_state().bits[threadIdx.x] = 0u;
     __syncthreads();
@@ -682,8 +748,12 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         __syncwarp(full);
     }
     if (STIFF) flush(-1);
+#ifdef XSQ_EVENTS_N
+    if (P.evq_cap > 0 && lane == 0) evq_cta_publish(P);
+#endif
 }
 
+#ifndef __CUDACC_RTC__
 // ---- host side -----------------------------------------------------------------
 // The ensemble hot path: adaptive, final state only, default step budget,
 // controller without the alpha term.  XSQ_NO_FAST=1 forces the generic kernel
@@ -703,8 +773,7 @@ inline bool fast_eligible(const RkDev& P) {
 // high words that bracket "min_step < h_abs < max_step":
 // min_step = max(H_MIN_A (|t| + h0), sqrt(tiny)) <= M for every step that starts
 // with 2 h0 < |t_bound - t| (common.py:123-148, 310-331)
-template <class Tab>
-inline void fast_prepare(RkDev& P) {
+inline void fast_prepare_h(RkDev& P, double h_min_a) {
     auto hi_word = [](double x) {
         unsigned long long b;
         memcpy(&b, &x, 8);
@@ -712,12 +781,15 @@ inline void fast_prepare(RkDev& P) {
     };
     const double tmax = fmax(fabs(P.t0), fabs(P.t_bound));
     const double span = fabs(P.t_bound - P.t0);
-    const double M = fmax(Tab::H_MIN_A * (tmax + 0.5 * span), 0x1.0p-511) * (1.0 + 0x1.0p-30);
+    const double M = fmax(h_min_a * (tmax + 0.5 * span), 0x1.0p-511) * (1.0 + 0x1.0p-30);
     const long long lo = hi_word(M), hi = hi_word(P.max_step);
     P.fast_hi_min = (int)lo;
     P.fast_hi_span = (int)(hi - lo - 1 > 0 ? hi - lo - 1 : 0);
     P.fast_dir_mask = P.direction < 0.0 ? (int)0x80000000u : 0;
 }
+template <class Tab>
+inline void fast_prepare(RkDev& P) { fast_prepare_h(P, Tab::H_MIN_A); }
+#endif  // __CUDACC_RTC__
 
 template <class Tab, class R, int BLOCK, int MINB, bool STIFF>
 __global__ void __launch_bounds__(BLOCK, MINB) rk_fast(const RkDev P) {

@@ -24,6 +24,7 @@
 
 #include "xsq.h"
 #include "xsq_user.h"
+#include "xsq_rk_fast.cuh"
 
 namespace xsq {
 
@@ -403,7 +404,44 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
 
 // Build the translation unit for (method, rhs); exposed for the CPU-side test
 // that NVRTC accepts it (no device needed to compile).
-int user_build_source(int method, int rhs, int events, std::string* src, std::string* key) {
+// The fast kernel has no root finder and no dense output: it serves the plain
+// adaptive solve of a built-in generic pair and thread-per-system right-hand
+// side with event functions of which none is terminal, when the event queue is
+// large enough for every record the solve can produce (RkDev::evq_exact).
+static int fast_events_variant(int method, int rhs, int events, RkDev* P) {
+    if (events == 0 || P->evq_cap <= 0 || !P->evq_exact) return 0;
+    double h_min_a = 0.0;
+    switch (method) {
+        case XSQ_TS5: h_min_a = tab::Ts5::H_MIN_A; break;
+        case XSQ_CK5: h_min_a = tab::CK5::H_MIN_A; break;
+        case XSQ_ME4: h_min_a = tab::Me4::H_MIN_A; break;
+        case XSQ_PR7: h_min_a = tab::Pr7::H_MIN_A; break;
+        case XSQ_PR8: h_min_a = tab::Pr8::H_MIN_A; break;
+        case XSQ_PR9: h_min_a = tab::Pr9::H_MIN_A; break;
+        default: return 0;
+    }
+    if (rhs == XSQ_RHS_NBODY32) return 0;
+    if (rhs >= XSQ_RHS_USER_BASE) {
+        const size_t i = (size_t)(rhs - XSQ_RHS_USER_BASE);
+        if (i >= g_rhs.size() || g_rhs[i].n_state > XSQ_MAX_LANE_STATE) return 0;
+    }
+    if (P->n_forced != 0 || P->n_eval != 0 || P->minalpha != 0.0 || P->max_steps != 0x7fffffff ||
+        P->n_lanes >= (1LL << 31))
+        return 0;
+    for (int k = 0; k < P->n_events; ++k)
+        if (P->ev_terminal[k] != 0) return 0;
+    if (const char* e = getenv("XSQ_NO_FAST"))
+        if (e[0] == '1') return 0;
+    fast_prepare_h(*P, h_min_a);
+    return P->nfev_stiff_detect > 0 ? 2 : 1;
+}
+
+// variant 0: rk_persistent (everything); 1 / 2: rk_fast without / with the
+// stiffness diagnosis -- adaptive stepping of a built-in generic pair with
+// event functions none of which is terminal, every root located by the event
+// queue kernel (xsq_rk_fast.cuh)
+int user_build_source(int method, int rhs, int events, int variant, std::string* src,
+                      std::string* key) {
     std::string tabname, rhsname, body;
     if (events != 0) {
         // scipy's `events=`: the functions are device code too; the core header
@@ -418,7 +456,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                 "namespace xsq { __device__ __forceinline__ double user_event(int k, double t,\n"
                 "    const double* y, const double* p) { return ::" + e.entry + "(k, t, y, p); } }\n";
     }
-    body += "#include \"xsq_rk_core.cuh\"\n";
+    body += variant != 0 ? "#include \"xsq_rk_fast.cuh\"\n" : "#include \"xsq_rk_core.cuh\"\n";
     if (events != 0) body += g_events[(size_t)events - 1].src + "\n";
     int s = 0, nl = 0;
     const bool swag = method == XSQ_METHOD_SWAG;
@@ -465,7 +503,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
     // the event machinery adds live state (previous event values, counts): at 128
     // registers the hot loop spills; measured on the Lorenz / Ts5 Poincare workload:
     // 4 / 3 / 2 CTAs per SM -> 126.6 / 92.8 / 101.2 ms
-    if (events != 0 && !swag && minb > 2) --minb;
+    if (events != 0 && !swag && variant == 0 && minb > 2) --minb;
     if (const char* e = getenv("XSQ_USER_MINB")) {       // tuning knob: CTAs per SM
         const int v = atoi(e);
         if (v >= 1 && v <= 8) minb = v;
@@ -477,6 +515,12 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                       "xsq_user_kernel(const xsq::RkDev P) {\n"
                       "    xsq::swag_persistent_body<xsq::rhs::%s>(P);\n}\n",
                       rhsname.c_str());
+    else if (variant != 0)
+        std::snprintf(buf, sizeof buf,
+                      "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
+                      "xsq_user_kernel(const xsq::RkDev P) {\n"
+                      "    xsq::rk_fast_body<xsq::tab::%s, xsq::rhs::%s, 128, %s>(P);\n}\n",
+                      minb, tabname.c_str(), rhsname.c_str(), variant == 2 ? "true" : "false");
     else
         std::snprintf(buf, sizeof buf,
                       "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
@@ -504,7 +548,7 @@ int user_build_source(int method, int rhs, int events, std::string* src, std::st
                       tabname.c_str(), rhsname.c_str());
     *src = body + buf + buf2 + buf3 + buf4;
     if (events != 0) *key += "/E" + std::to_string(events);
-    *key += "/B" + std::to_string(minb);
+    *key += "/B" + std::to_string(minb) + "/V" + std::to_string(variant);
     return XSQ_OK;
 }
 
@@ -538,7 +582,9 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
                    double tanang, cudaStream_t st) {
     std::lock_guard<std::mutex> g(g_mu);
     std::string src, key;
-    int rc = user_build_source(method, rhs, events, &src, &key);
+    RkDev Pc = P;
+    const int variant = fast_events_variant(method, rhs, events, &Pc);
+    int rc = user_build_source(method, rhs, events, variant, &src, &key);
     if (rc != XSQ_OK) return rc;
     {   // a CUmodule belongs to the context it was loaded in: one per device
         int kdev = 0;
@@ -564,7 +610,6 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     const long long want = (P.n_lanes + per_block - 1) / per_block;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    RkDev Pc = P;
     void* args[] = {&Pc};
     prof_mark(0, st);
     {   // initialisation pass (f0 + h_start), thread per lane
@@ -746,7 +791,9 @@ int xsq_user_compile_check(int32_t method, int32_t rhs) {
 int xsq_events_compile_check(int32_t method, int32_t rhs, int32_t events) {
     std::lock_guard<std::mutex> g(g_mu);
     std::string src, key;
-    int rc = user_build_source(method, rhs, events, &src, &key);
+    int variant = 0;
+    if (const char* e = getenv("XSQ_CHECK_VARIANT")) variant = atoi(e);   // developer aid
+    int rc = user_build_source(method, rhs, events, variant, &src, &key);
     if (rc != XSQ_OK) return rc;
     if (!load_nvrtc()) return XSQ_ERR_NVRTC;
     nvrtcProgram prog;

@@ -52,8 +52,12 @@ typedef enum xsq_lane_status {
     XSQ_LANE_OVERFLOW = -2,       /* "Overflow or underflow", common.py:286    */
     XSQ_LANE_TOL_TOO_TIGHT = -3,  /* SWAG, shampine.py:235-238                 */
     XSQ_LANE_SPRAD_FAILED = -4,   /* SSV2stab, sommeijer.py:179-182            */
-    XSQ_LANE_STEP_BUDGET = -5     /* max_steps exhausted (no reference analogue;
+    XSQ_LANE_STEP_BUDGET = -5,    /* max_steps exhausted (no reference analogue;
                                      guards the GPU against runaway lanes)     */
+    XSQ_LANE_EVENT_QUEUE = -6     /* the event queue ran out of records (defensive:
+                                     the queue is sized for every possible record
+                                     whenever the kernel without an in-lane root
+                                     finder is selected)                        */
 } xsq_lane_status;
 
 /* Built-in tableau methods: the reference's classes

@@ -269,8 +269,12 @@ def test_event_queue_and_in_lane_root_solves_are_bit_identical(method, monkeypat
     y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
     prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
     te = np.linspace(0.0, 5.0, 41)
-    for term, kw in (([0, 0, 0], {}), ([0, 6, 0], {}), ([0, 0, 0], dict(t_eval=te)),
-                     ([3, 0, 0], dict(t_eval=te))):
+    # without a terminal event and without t_eval the default run (queue large
+    # enough for every record) takes the fast kernel (rk_fast + event hooks) for
+    # the generic pairs, with and without the stiffness diagnosis; the runs with
+    # a limited queue take rk_persistent: the comparison covers both kernels
+    for term, kw in (([0, 0, 0], {}), ([0, 0, 0], dict(nfev_stiff_detect=0)), ([0, 6, 0], {}),
+                     ([0, 0, 0], dict(t_eval=te)), ([3, 0, 0], dict(t_eval=te))):
         ev = events_for("lorenz_sections", term, [1, 0, -1])
         runs = []
         for q in ("0", "1500", None):
@@ -283,7 +287,8 @@ def test_event_queue_and_in_lane_root_solves_are_bit_identical(method, monkeypat
             torch.cuda.synchronize()
             runs.append({k: getattr(r, k).cpu().numpy() for k in
                          ("t_events", "y_events", "event_counts", "y_final", "t_final", "status",
-                          "nfev", "n_accepted") + (("y",) if kw else ())})
+                          "nfev", "n_accepted", "n_rejected", "h_next", "stiff_flags") +
+                         (("y",) if "t_eval" in kw else ())})
         assert runs[0]["event_counts"].sum() > 5 * N
         if term[1]:
             assert (runs[0]["status"] == 1).any()
