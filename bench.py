@@ -637,7 +637,7 @@ __device__ double event(int k, double t, const double* y, const double* p) {
         lib.xsq_profile_enable(1)
         r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
             "lorenz63", (0.0, T), y0_d, xb.Ts5, params=prm_d, rtol=RTOL, atol=ATOL,
-            nfev_stiff_detect=args.stiff, events=ev, max_event_records=64), 2)
+            nfev_stiff_detect=args.stiff, events=ev, max_event_records=48), 2)
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         have = lib.xsq_profile_last(C.byref(a), C.byref(b), C.byref(c)) == 0
         lib.xsq_profile_enable(0)

@@ -159,7 +159,11 @@ void keep_pool_memory() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ULL;
+        // bounded: the scratch of an ordinary solve (init pass, probe queue <= 4 GB)
+        // stays cached, a large event queue (up to a third of the memory) goes back
+        // to the driver at the next synchronisation instead of starving whatever
+        // else shares the GPU
+        unsigned long long keep = 6ULL << 30;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     done[dev] = true;

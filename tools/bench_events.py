@@ -39,7 +39,7 @@ def kernels():
 
 N = int(os.environ.get("LANES", 1_250_000))
 T = float(os.environ.get("TEND", 20.0))
-CAP = int(os.environ.get("EVCAP", 64))
+CAP = int(os.environ.get("EVCAP", 48))
 rng = np.random.default_rng(12345)
 y0 = torch.tensor(np.stack([rng.uniform(-15, 15, N), rng.uniform(-20, 20, N), rng.uniform(5, 40, N)], 1), device="cuda")
 prm = torch.tensor(np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1), device="cuda")
