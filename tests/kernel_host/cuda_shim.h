@@ -49,5 +49,12 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
     const unsigned long long o = *p; *p = o + v; return o;
 }
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) {
+    const unsigned long long o = *p; *p = v; return o;
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+static inline void __threadfence_block() {}
+static inline void __nanosleep(unsigned) {}
 static inline int atomicOr(int* p, int v) { const int o = *p; *p = o | v; return o; }
 using std::fma;

@@ -7,6 +7,21 @@
 // source against the oracle, without a GPU.
 #define XSQ_HOST_EMU 1
 #include "cuda_shim.h"
+#ifdef XSQ_EMU_EVENTS
+// Second build of this file (xsq_emu_events.so): the kernels as NVRTC compiles
+// them for scipy's `events=`, with the three event functions of
+// oracle/problems.py EVENT_SETS["lorenz_sections"] -- in-lane root location, the
+// event queue with event_queue_body, and rk_fast with event hooks.
+#define XSQ_EVENTS_N 3
+namespace xsq {
+static inline double user_event(int k, double t, const double* y, const double* p) {
+    (void)t; (void)p;
+    if (k == 0) return y[2] - 27.0;
+    if (k == 1) return y[0];
+    return y[0] * y[1] - 30.0;
+}
+}  // namespace xsq
+#endif
 
 #include <string>
 #include <vector>
@@ -30,8 +45,10 @@ double xsq_host_rcp64h(double x) {
 }  // namespace xsq
 
 #include "xsq_rk_fast.cuh"
+#ifndef XSQ_EMU_EVENTS
 #include "xsq_swag_core.cuh"
 #include "xsq_swag_fast.cuh"
+#endif
 #include "xsq_rhs.cuh"
 #include "xsq_user.h"
 
@@ -41,7 +58,11 @@ void set_detail(const std::string& s) { g_detail = s; }
 void count_launch() {}
 bool user_tableau_info(MethodInfo*) { return false; }
 bool user_rhs_shape(int, int*, int*) { return false; }
+#ifdef XSQ_EMU_EVENTS
+int user_events_count(int) { return XSQ_EVENTS_N; }
+#else
 int user_events_count(int) { return -1; }
+#endif
 }  // namespace xsq
 #include "xsq_params.h"
 
@@ -60,7 +81,15 @@ static int run(RkDev P, const MethodInfo& mi, bool want_fast, int* used_fast) {
     blockIdx = {0, 0, 0};
     *used_fast = 0;
     if constexpr (Tab::VARIANT == tab::GENERIC && !R::WARP) {
+#ifdef XSQ_EMU_EVENTS
+        // xsq_user.cpp fast_events_variant
+        bool ok = want_fast && P.evq_cap > 0 && P.evq_exact && P.n_forced == 0 && P.n_eval == 0 &&
+                  P.minalpha == 0.0 && P.max_steps == 0x7fffffff;
+        for (int k = 0; k < P.n_events; ++k) ok = ok && P.ev_terminal[k] == 0;
+        if (ok) {
+#else
         if (want_fast && fast_eligible<Tab, R>(P)) {
+#endif
             fast_prepare<Tab>(P);
             if (P.nfev_stiff_detect > 0) rk_fast_body<Tab, R, 1, true>(P);
             else rk_fast_body<Tab, R, 1, false>(P);
@@ -69,6 +98,17 @@ static int run(RkDev P, const MethodInfo& mi, bool want_fast, int* used_fast) {
     }
     if (!*used_fast) rk_persistent_body<Tab, R>(P);
     if (P.stiff_q_cap > 0) stiff_queue_body<R>(P, mi.s, mi.stbrad, mi.tanang);
+#ifdef XSQ_EMU_EVENTS
+    if (P.evq_cap > 0) {
+        blockDim = {128, 1, 1};                 // the queue kernel's tile size
+        for (unsigned tx = 0; tx < 128; ++tx) {
+            threadIdx = {tx, 0, 0};
+            event_queue_body<Tab, R>(P);
+        }
+        blockDim = {1, 1, 1};
+        threadIdx = {0, 0, 0};
+    }
+#endif
     return 0;
 }
 
@@ -82,6 +122,10 @@ static int run_rhs(int rhs, const RkDev& P, const MethodInfo& mi, bool fast, int
     }
 }
 
+#ifdef XSQ_EMU_EVENTS
+static long long g_evq_records = -1;      // -1: every possible record (exact), 0: no queue
+extern "C" void xsq_emu_set_event_queue(long long records) { g_evq_records = records; }
+#endif
 extern "C" const char* xsq_emu_detail() { return g_detail.c_str(); }
 extern "C" void xsq_emu_set_rcp_table(const uint8_t* bits) { xsq_emu_rcp_bits = bits; }
 
@@ -122,6 +166,36 @@ extern "C" int xsq_emu_rk_solve(const xsq_rk_args_t* a, int want_fast, long long
         P.stiff_q = slots.data() + 2 * threads * rec;
         P.stiff_q_cap = (long long)qcap;
     }
+#ifdef XSQ_EMU_EVENTS
+    // the event queue, as solve_device (xsq_api.cu)
+    std::vector<double> evq_mem;
+    std::vector<unsigned> evq_fill;
+    unsigned long long evq_count = 0ULL;
+    P.evq = nullptr; P.evq_cap = 0; P.evq_count = &evq_count; P.evq_fill = nullptr; P.evq_exact = 0;
+    if (a->events != 0 && P.n_events > 0 && P.ev_capacity > 0) {
+        const size_t fields = (5 + (size_t)(mi.s + 3) * (size_t)a->n_state + 1) & ~(size_t)1;
+        const size_t need = N * (size_t)P.n_events * (size_t)P.ev_capacity + (size_t)kEvqChunk;
+        size_t qcap = need;
+        if (g_evq_records >= 0 && (size_t)g_evq_records < qcap) qcap = (size_t)g_evq_records;
+        const size_t chunks = (qcap + kEvqChunk - 1) / kEvqChunk;
+        if (chunks > 0) {
+            evq_mem.assign(chunks * kEvqChunk * fields, 0.0);
+            evq_fill.assign(chunks, 0u);
+            P.evq = evq_mem.data();
+            P.evq_fill = evq_fill.data();
+            P.evq_cap = (long long)(chunks * kEvqChunk);
+            P.evq_exact = chunks * kEvqChunk >= need ? 1 : 0;
+        }
+    }
+    if (a->rhs != XSQ_RHS_LORENZ63) return XSQ_ERR_UNSUPPORTED;
+    switch (a->method) {
+        case XSQ_TS5: return run<tab::Ts5, rhs::Lorenz63>(P, mi, want_fast, used_fast);
+        case XSQ_BS5: return run<tab::BS5, rhs::Lorenz63>(P, mi, want_fast, used_fast);
+        case XSQ_PR8: return run<tab::Pr8, rhs::Lorenz63>(P, mi, want_fast, used_fast);
+        case XSQ_CKDISC: return run<tab::CKdisc, rhs::Lorenz63>(P, mi, want_fast, used_fast);
+        default: return XSQ_ERR_UNSUPPORTED;
+    }
+#endif
     switch (a->method) {
         case XSQ_TS5: return run_rhs<tab::Ts5>(a->rhs, P, mi, want_fast, used_fast);
         case XSQ_BS5: return run_rhs<tab::BS5>(a->rhs, P, mi, want_fast, used_fast);
@@ -136,6 +210,7 @@ extern "C" int xsq_emu_rk_solve(const xsq_rk_args_t* a, int want_fast, long long
     }
 }
 
+#ifndef XSQ_EMU_EVENTS
 template <class R>
 static int run_swag(RkDev P) {
     const long long N = P.n_lanes;
@@ -191,3 +266,4 @@ extern "C" int xsq_emu_swag_solve(const xsq_rk_args_t* args, int k_max) {
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }
+#endif  // XSQ_EMU_EVENTS

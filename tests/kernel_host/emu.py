@@ -10,23 +10,25 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 _lib = None
+_lib_ev = None
 _bits = None
 
 
-def build():
+def build(events=False):
     src = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h")]
     src += [os.path.join(ROOT, "extensisq_b200", "csrc", f) for f in
             ("xsq_rk_core.cuh", "xsq_rk_fast.cuh", "xsq_math.cuh", "xsq_intrin.cuh",
              "xsq_params.h", "xsq_rhs.cuh", "xsq_tableaux_gen.cuh", "xsq_math_tables_gen.cuh",
              "xsq_swag_core.cuh", "xsq_swag_fast.cuh")]
-    out = os.path.join(HERE, "_build", "xsq_emu.so")
+    out = os.path.join(HERE, "_build", "xsq_emu_events.so" if events else "xsq_emu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if (not os.path.exists(out) or
             os.path.getmtime(out) < max(os.path.getmtime(f) for f in src)):
         subprocess.check_call(
             ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-w",
              "-I", os.path.join(ROOT, "extensisq_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
-             "-I", "/usr/local/cuda/include", "-o", out, src[0]])
+             "-I", "/usr/local/cuda/include", "-o", out, src[0]] +
+            (["-DXSQ_EMU_EVENTS"] if events else []))
     return out
 
 
@@ -41,14 +43,29 @@ def load():
     return _lib
 
 
+def load_events():
+    """The same sources compiled with the event machinery (XSQ_EVENTS_N = 3, the
+    event functions of oracle/problems.py EVENT_SETS['lorenz_sections'])."""
+    global _lib_ev
+    if _lib_ev is None:
+        load()
+        _lib_ev = C.CDLL(build(events=True))
+        _lib_ev.xsq_emu_set_rcp_table(_bits.ctypes.data_as(C.c_void_p))
+        _lib_ev.xsq_emu_detail.restype = C.c_char_p
+    return _lib_ev
+
+
 def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step=None,
           max_step=np.inf, sc_params=None, interpolant=None, t_eval=None, forced_steps=None,
-          nfev_stiff_detect=5000, max_steps=None, fast=True, queue_records=-1, k_max=None):
+          nfev_stiff_detect=5000, max_steps=None, fast=True, queue_records=-1, k_max=None,
+          events=None, max_event_records=16, event_queue_records=-1):
     """Same arguments as extensisq_b200.solve_ivp_batched (built-in rhs names,
-    built-in methods); returns numpy arrays."""
+    built-in methods); returns numpy arrays.  `events=(terminal, direction)`
+    selects the events build (three Lorenz section functions, lorenz63 only);
+    `event_queue_records`: -1 every possible record, 0 no queue (roots in the lane)."""
     from extensisq_b200 import _lib as L
     from extensisq_b200.batched import _sc_tuple
-    lib = load()
+    lib = load_events() if events is not None else load()
     rid = {"lorenz63": 0, "vanderpol": 1, "arenstorf": 2}[rhs]      # include/xsq.h XSQ_RHS_*
     y0 = np.atleast_2d(np.asarray(y0, dtype=float))
     N, n = y0.shape
@@ -102,6 +119,20 @@ def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step
     a.n_eval_done = ptr(ints["n_eval_done"]) if n_eval else None
     a.nfev_stiff_detect = int(nfev_stiff_detect)
     a.stiff_flags = ptr(ints["stiff_flags"])
+    if events is not None:
+        term, direc = events
+        ne, cap = 3, int(max_event_records)
+        t_ev = np.full((N, ne, cap), np.nan)
+        y_ev = np.full((N, ne, cap, n), np.nan)
+        ev_cnt = np.zeros((N, ne), np.int32)
+        term_c = (C.c_int32 * ne)(*term)
+        direc_c = (C.c_int32 * ne)(*direc)
+        a.events, a.n_event_fns = 1, ne
+        a.ev_terminal = C.cast(term_c, C.POINTER(C.c_int32))
+        a.ev_direction = C.cast(direc_c, C.POINTER(C.c_int32))
+        a.ev_capacity = cap
+        a.t_events, a.y_events, a.ev_count = ptr(t_ev), ptr(y_ev), ptr(ev_cnt)
+        lib.xsq_emu_set_event_queue(C.c_longlong(event_queue_records))
     used = C.c_int(0)
     if is_swag:
         a.nfev_stiff_detect = 0
@@ -114,4 +145,6 @@ def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step
     out = dict(t_final=t_final, y_final=np.ascontiguousarray(y_final.T), h_next=h_next,
                y=(y_eval[:, :, :n_eval] if n_eval else None), used_fast=bool(used.value))
     out.update(ints)
+    if events is not None:
+        out.update(t_events=t_ev, y_events=y_ev, event_counts=ev_cnt)
     return out

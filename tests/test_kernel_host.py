@@ -179,3 +179,94 @@ def test_swag_kernel_source_equals_oracle_bit_for_bit(prob):
             if te is not None:
                 ok = (bits(g["y"]) == bits(o["y"])) | (np.isnan(g["y"]) & np.isnan(o["y"]))
                 assert ok.all(), (prob, kw, "y(t_eval)")
+
+
+# ---- events (scipy's `events=`): the kernels as NVRTC builds them, on the host ----
+def _lorenz_event_lanes(N, seed=11):
+    rng = np.random.default_rng(seed)
+    y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+    prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
+    return y0, prm
+
+
+def _same_events(a, b, what, keys):
+    for k in keys:
+        x, y = a[k], b[k]
+        ok = (x == y) | ((x != x) & (y != y))
+        assert ok.all(), (what, k, np.argwhere(~ok)[:4])
+
+
+@pytest.mark.parametrize("m", [xb.Ts5, xb.BS5, xb.Pr8, xb.CKdisc], ids=lambda m: m.__name__)
+def test_event_kernel_sources_in_lane_queue_and_fast_agree(m):
+    """xsq_rk_core.cuh / xsq_rk_fast.cuh compiled with XSQ_EVENTS_N = 3 (three
+    Lorenz section functions): roots located inside the lane (no queue), by
+    event_queue_body from the queued steps (rk_persistent), and -- no terminal
+    event, generic pair -- by rk_fast with event hooks.  Every event time and
+    state, count and trajectory output must be equal bit for bit, and the
+    trajectory itself must be the one the C oracle computes without events."""
+    y0, prm = _lorenz_event_lanes(72)
+    te = np.linspace(0.0, 5.0, 41)
+    keys = ("t_events", "y_events", "event_counts", "y_final", "t_final", "h_next", "nfev",
+            "n_accepted", "n_rejected", "status", "stiff_flags")
+    generic = m in (xb.Ts5, xb.Pr8)
+    for term, kw in (([0, 0, 0], {}), ([0, 0, 0], dict(nfev_stiff_detect=0)), ([0, 6, 0], {}),
+                     ([0, 0, 0], dict(t_eval=te)), ([3, 0, 0], dict(t_eval=te))):
+        if m is xb.CKdisc:
+            kw = dict(kw, nfev_stiff_detect=0)
+        base = dict(rtol=1e-7, atol=1e-9, max_event_records=12, events=(term, [1, 0, -1]), **kw)
+        a = emu.solve("lorenz63", (0.0, 5.0), y0, m, prm, event_queue_records=0, **base)
+        b = emu.solve("lorenz63", (0.0, 5.0), y0, m, prm, event_queue_records=700, **base)
+        c = emu.solve("lorenz63", (0.0, 5.0), y0, m, prm, event_queue_records=-1, fast=False, **base)
+        d = emu.solve("lorenz63", (0.0, 5.0), y0, m, prm, event_queue_records=-1, fast=True, **base)
+        assert not a["used_fast"] and not b["used_fast"] and not c["used_fast"]
+        assert d["used_fast"] == (generic and term == [0, 0, 0] and "t_eval" not in kw)
+        assert a["event_counts"].sum() > 5 * len(y0)
+        k2 = keys + (("y",) if "t_eval" in kw else ())
+        for other, name in ((b, "overflowing queue"), (c, "queue"), (d, "fast")):
+            _same_events(a, other, (m.__name__, term, sorted(kw), name), k2)
+        if term == [0, 0, 0]:
+            # events never change t, y, h: the plain solve of the oracle
+            okw = {k: v for k, v in base.items() if k not in ("events", "max_event_records")}
+            with CO.device_math():
+                tab = O.load_ckdisc() if m is xb.CKdisc else TABS[m.__name__]
+                o = CO.rk_batch(tab, "lorenz63", (0.0, 5.0), y0, params=prm,
+                                n_threads=CO.max_threads(), **okw)
+            if m is xb.BS5:
+                # the extra stages of BS5's interpolant on steps with an event count in
+                # nfev (bogacki.py:372-388), as in the reference: everything but nfev
+                for k in ("n_accepted", "n_rejected", "status"):
+                    assert np.array_equal(a[k], o[k]), (k,)
+                for k in KEYS_F:
+                    assert np.array_equal(bits(a[k]), bits(o[k])), (k,)
+                assert (a["nfev"] >= o["nfev"]).all() and (a["nfev"] > o["nfev"]).any()
+            else:
+                same(a, o, (m.__name__, "events vs plain oracle"), dense="t_eval" in kw)
+
+
+def test_event_kernel_sources_against_the_numpy_restatement():
+    """Event times and states of the emulated kernels against the restated
+    reference driven by scipy's event loop (oracle/rk_oracle.py, bit-identical
+    to the reference on the event goldens)."""
+    from oracle.problems import EVENT_SETS, make_fun
+    y0, prm = _lorenz_event_lanes(10, seed=5)
+    term, direc = [0, 4, 0], [1, 0, -1]
+    kw = dict(rtol=1e-7, atol=1e-9)
+    g = emu.solve("lorenz63", (0.0, 6.0), y0, xb.Ts5, prm, events=(term, direc),
+                  max_event_records=32, **kw)
+    fns = EVENT_SETS["lorenz_sections"][0]
+    checked = 0
+    for i in range(len(y0)):
+        o = O.rk_solve(TABS["Ts5"], make_fun("lorenz63", prm[i]), (0.0, 6.0), y0[i],
+                       events=[(f, a, b) for f, a, b in zip(fns, term, direc)], **kw)
+        assert g["status"][i] == o["status"]
+        if g["nfev"][i] != o["nfev"]:
+            continue                     # a flipped accept/reject decision (other arithmetic)
+        checked += 1
+        for k in range(3):
+            tg = o["t_events"][k]
+            assert g["event_counts"][i, k] >= tg.size
+            assert np.allclose(g["t_events"][i, k, :tg.size], tg, rtol=1e-9, atol=1e-9)
+            if tg.size:
+                assert np.allclose(g["y_events"][i, k, :tg.size], o["y_events"][k], rtol=1e-7, atol=1e-7)
+        assert abs(g["t_final"][i] - o["t_final"]) <= 1e-9
+    assert checked >= 8 and (g["status"] == 1).any()
