@@ -159,14 +159,35 @@ void keep_pool_memory() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        // bounded: the scratch of an ordinary solve (init pass, probe queue <= 4 GB)
-        // stays cached, a large event queue (up to a third of the memory) goes back
-        // to the driver at the next synchronisation instead of starving whatever
-        // else shares the GPU
+        // bounded: the scratch of repeated solves stays cached -- mapping the tens
+        // of GB of a large event queue again costs hundreds of milliseconds per
+        // solve (measured) -- but never more than 40 % of the device's memory;
+        // xsq_trim_memory() returns it to the driver at any time
+        size_t free_b = 0, total_b = 0;
         unsigned long long keep = 6ULL << 30;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b / 5 * 2 > keep)
+            keep = total_b / 5 * 2;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     done[dev] = true;
+}
+
+// Memory a new allocation of this library can draw on: what the driver reports
+// free plus what the stream-ordered pool holds without using it.
+static size_t available_bytes() {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long reserved = 0, used = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess &&
+            reserved > used)
+            free_b += (size_t)(reserved - used);
+    }
+    return free_b;
 }
 
 static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
@@ -273,8 +294,7 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
             XSQ_CUDA(cudaGetDevice(&dev));
             XSQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
             const size_t fields = (5 + (size_t)(mi.s + 3) * (size_t)a->n_state + 1) & ~(size_t)1;
-            size_t free_b = 0, total_b = 0;
-            XSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t free_b = available_bytes();
             size_t ctas = (size_t)n_sm * 16;                       // more than any launch uses
             if (ctas > (N + 127) / 128) ctas = (N + 127) / 128;
             const size_t need = N * (size_t)P.n_events * (size_t)P.ev_capacity + ctas * kEvqChunk;

@@ -802,10 +802,12 @@ struct CkExtra<false> {};
 // ---- one trajectory ---------------------------------------------------------
 #ifdef XSQ_EVENTS_N
 // ---- event queue: chunked allocation ------------------------------------------
-// word = generation << 32 | records taken from the current chunk; chunk[g & 3] is
-// the chunk of generation g (-1: the queue is exhausted).
+// word = generation << 20 | records taken from the current chunk (a 32-bit word:
+// native shared-memory atomics); chunk[g & 3] is the chunk of generation g (-1: the
+// queue is exhausted).  At most blockDim.x appends overshoot a full chunk, so the
+// count never reaches 2^20.
 struct EvqShared {
-    unsigned long long word;
+    unsigned word;
     long long chunk[4];
 };
 __device__ __forceinline__ EvqShared& evq_shared() {
@@ -816,42 +818,54 @@ __device__ __forceinline__ EvqShared& evq_shared() {
 // first append installs the first chunk
 __device__ __forceinline__ void evq_cta_init() {
     EvqShared& s = evq_shared();
-    s.word = (unsigned long long)kEvqChunk;
+    s.word = (unsigned)kEvqChunk;
     s.chunk[0] = s.chunk[1] = s.chunk[2] = s.chunk[3] = -1;
 }
-// Index of a free record, or -1 when the queue is exhausted.
-__device__ __forceinline__ long long evq_alloc(const RkDev& P) {
+// The rare part of an append: the chunk is full.  Exactly one thread (the one
+// that drew i == kEvqChunk) installs the next chunk and takes its record 0; the
+// others wait for the new generation and draw again.
+__device__ __noinline__ long long evq_alloc_slow(unsigned* evq_fill, unsigned long long* evq_count,
+                                                 long long n_chunks, unsigned old) {
     EvqShared& s = evq_shared();
     for (;;) {
-        const unsigned long long old = atomicAdd(&s.word, 1ull);
-        const unsigned g = (unsigned)(old >> 32), i = (unsigned)old;
+        const unsigned g = old >> 20, i = old & 0xfffffu;
         if (i < (unsigned)kEvqChunk) {
             const long long c = *(volatile long long*)&s.chunk[g & 3u];
             return c < 0 ? -1 : c * kEvqChunk + (long long)i;
         }
-        if (i == (unsigned)kEvqChunk) {          // exactly one thread installs the next chunk
+        if (i == (unsigned)kEvqChunk) {
             const long long prev = *(volatile long long*)&s.chunk[g & 3u];
-            if (prev >= 0) atomicMax(P.evq_fill + prev, (unsigned)kEvqChunk);
-            const unsigned long long c = atomicAdd(P.evq_count, 1ull);
-            const long long cc =
-                c < (unsigned long long)(P.evq_cap / kEvqChunk) ? (long long)c : -1;
+            if (prev >= 0) atomicMax(evq_fill + prev, (unsigned)kEvqChunk);
+            const unsigned long long c = atomicAdd(evq_count, 1ull);
+            const long long cc = c < (unsigned long long)n_chunks ? (long long)c : -1;
             *(volatile long long*)&s.chunk[(g + 1u) & 3u] = cc;
             __threadfence_block();
-            // the installer takes record 0 of the new chunk itself
-            atomicExch(&s.word, ((unsigned long long)(g + 1u) << 32) | (cc >= 0 ? 1ull : 0ull));
+            atomicExch(&s.word, (((g + 1u) & 0xfffu) << 20) | (cc >= 0 ? 1u : 0u));
             return cc < 0 ? -1 : cc * kEvqChunk;
         }
-        // the chunk filled up while another thread installs the next: wait for it
-        while ((unsigned)(*(volatile unsigned long long*)&s.word >> 32) == g) __nanosleep(40);
+        while ((*(volatile unsigned*)&s.word >> 20) == g) __nanosleep(40);
+        old = atomicAdd(&s.word, 1u);
     }
+}
+// Index of a free record, or -1 when the queue is exhausted.
+__device__ __forceinline__ long long evq_alloc(const RkDev& P) {
+    EvqShared& s = evq_shared();
+    const unsigned old = atomicAdd(&s.word, 1u);
+    const unsigned i = old & 0xfffffu;
+    if (i < (unsigned)kEvqChunk) {
+        const long long c = *(volatile long long*)&s.chunk[(old >> 20) & 3u];
+        if (c >= 0) return c * kEvqChunk + (long long)i;
+    }
+    return evq_alloc_slow(P.evq_fill, P.evq_count, P.evq_cap / kEvqChunk, old);
 }
 // lane 0 of every warp when it leaves the persistent loop: the counter only
 // grows, so the last warp publishes the fill of the CTA's last chunk
 __device__ __forceinline__ void evq_cta_publish(const RkDev& P) {
     EvqShared& s = evq_shared();
-    const unsigned long long w = *(volatile unsigned long long*)&s.word;
-    const long long c = *(volatile long long*)&s.chunk[(unsigned)(w >> 32) & 3u];
-    const unsigned n = (unsigned)w < (unsigned)kEvqChunk ? (unsigned)w : (unsigned)kEvqChunk;
+    const unsigned w = *(volatile unsigned*)&s.word;
+    const long long c = *(volatile long long*)&s.chunk[(w >> 20) & 3u];
+    const unsigned i = w & 0xfffffu;
+    const unsigned n = i < (unsigned)kEvqChunk ? i : (unsigned)kEvqChunk;
     if (c >= 0) atomicMax(P.evq_fill + c, n);
 }
 // One record: NF consecutive doubles (16-byte aligned, 128-bit accesses):

@@ -53,6 +53,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) {
     const unsigned long long o = *p; *p = v; return o;
 }
+static inline unsigned atomicExch(unsigned* p, unsigned v) { const unsigned o = *p; *p = v; return o; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
 static inline void __threadfence_block() {}
 static inline void __nanosleep(unsigned) {}
