@@ -1430,6 +1430,7 @@ struct Lane {
     struct EvSlow {
         double K[S + 1][NL];
         double y[NL], y_new[NL], prm[R::NPL];
+        double y_stop[NL];          // sol(t_stop) when a terminal event ends the trajectory
         double t, t_new, h, t_stop;
         long long sys;
         EvCfg cfg;
@@ -1437,6 +1438,36 @@ struct Lane {
         unsigned active;
         bool cubic, terminate;
     };
+    template <int KR>
+    static __device__ __forceinline__ void evslow_fill(EvSlow& a, const RkDev& P,
+                                                       const double (&K)[KR][NL],
+                                                       const double (&y)[NL],
+                                                       const double (&y_new)[NL],
+                                                       const double (&prm)[R::NPL],
+                                                       const int (&ev_n)[XSQ_EVENTS_N], double t,
+                                                       double t_new, double h, long long sys,
+                                                       unsigned active, bool cubic) {
+#pragma unroll
+        for (int i = 0; i <= S; ++i)
+#pragma unroll
+            for (int c = 0; c < NL; ++c) a.K[i][c] = K[i][c];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) { a.y[c] = y[c]; a.y_new[c] = y_new[c]; }
+#pragma unroll
+        for (int c = 0; c < R::NPL; ++c) a.prm[c] = prm[c];
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) {
+            a.ev_n[k] = ev_n[k];
+            a.cfg.ev_terminal[k] = P.ev_terminal[k];
+        }
+        a.cfg.ev_capacity = P.ev_capacity;
+        a.cfg.interpolant = P.interpolant;
+        a.cfg.direction = P.direction;
+        a.cfg.t_events = P.t_events;
+        a.cfg.y_events = P.y_events;
+        a.t = t; a.t_new = t_new; a.h = h; a.sys = sys;
+        a.active = active; a.cubic = cubic;
+    }
     static __device__ __noinline__ void events_slow(EvSlow& a) {
         Lane L;
         L.t = a.t;
@@ -1460,6 +1491,12 @@ struct Lane {
         for (int k = 0; k < XSQ_EVENTS_N; ++k) a.ev_n[k] = L.ev_n[k];
         a.terminate = terminate;
         a.t_stop = t_stop;
+        if (terminate) {                       // y = sol(t) at the event (ivp.py)
+            double ys[NL];
+            L.dense_eval(D, K, a.t_new, y_new, t_stop, ys);
+#pragma unroll
+            for (int c = 0; c < NL; ++c) a.y_stop[c] = ys[c];
+        }
     }
 
     static constexpr int EVQ_FIELDS = EvqRecord<S, NL>::NF;
@@ -1567,26 +1604,7 @@ struct Lane {
                 // The stages are copied into a local-memory block; K itself stays in
                 // registers.
                 EvSlow a;
-#pragma unroll
-                for (int i = 0; i <= S; ++i)
-#pragma unroll
-                    for (int c = 0; c < NL; ++c) a.K[i][c] = K[i][c];
-#pragma unroll
-                for (int c = 0; c < NL; ++c) { a.y[c] = y[c]; a.y_new[c] = y_new[c]; }
-#pragma unroll
-                for (int c = 0; c < R::NPL; ++c) a.prm[c] = prm[c];
-#pragma unroll
-                for (int k = 0; k < XSQ_EVENTS_N; ++k) {
-                    a.ev_n[k] = ev_n[k];
-                    a.cfg.ev_terminal[k] = P.ev_terminal[k];
-                }
-                a.cfg.ev_capacity = P.ev_capacity;
-                a.cfg.interpolant = P.interpolant;
-                a.cfg.direction = P.direction;
-                a.cfg.t_events = P.t_events;
-                a.cfg.y_events = P.y_events;
-                a.t = t; a.t_new = t_new; a.h = h; a.sys = sys;
-                a.active = active; a.cubic = cubic;
+                evslow_fill(a, P, K, y, y_new, prm, ev_n, t, t_new, h, sys, active, cubic);
                 events_slow(a);
 #pragma unroll
                 for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = a.ev_n[k];

@@ -485,7 +485,7 @@ struct FastLane {
         n_acc += accept ? 1 : 0;
         n_rej += accept ? 0 : 1;
         l2_old = accept ? l2 : l2_old;
-        const double t_next = accept ? t_new : t;
+        double t_next = accept ? t_new : t;
         // ---- what the next attempt needs ---------------------------------------
         // OdeSolver.step (base.py:207-208): done?  Then the next step's
         // _reassess_stepsize: nothing to do when  min_step < h_abs < max_step  and
@@ -514,16 +514,23 @@ struct FastLane {
         if (accept & !done) sts1(sa.h0, h_abs_new);
         if (slow) {
             if (accept) {
-#ifdef XSQ_EVENTS_N
-                if (ev_active != 0u && !push_events(P, ev_active, K, y_new, t_new, h))
-                    st = LANE_EVQ_FULL;
-#endif
                 if (STIFF && probe) {
                     if (diagnose_record(P, K, errv, y_new, t_new, h, havg_new, lotsfl)) {
                         if (st == LANE_RUNNING) st = LANE_FLUSH;
                     }
                 }
-                if (!done && (out_of_range || near_end)) {
+                bool ev_end = false;
+#ifdef XSQ_EVENTS_N
+                if (ev_active != 0u) {                        // after the probe: it records y_new
+                    const int er = handle_events(P, ev_active, K, y_new, t_new, h, t_next);
+                    if (er < 0) st = LANE_EVQ_FULL;
+                    if (er > 0) {                             // a terminal event: t, y at the event
+                        ev_end = true;
+                        st = LANE_EVENT;
+                    }
+                }
+#endif
+                if (!ev_end && !done && (out_of_range || near_end)) {
                     h_abs = h_abs_new;
                     if (!reassess_exact(P, t_next, fabs(s), h_abs, fl)) st = LANE_TOO_SMALL;
                     fl |= FL_SLOW;
@@ -554,6 +561,33 @@ struct FastLane {
     }
 
 #ifdef XSQ_EVENTS_N
+    // handle_events (ivp.py) for the accepted step.  No active event at a terminal
+    // occurrence: the roots are left to the event queue.  Otherwise every root of
+    // the step is located now, out of line (Lane::events_slow: the general
+    // kernel's own code on a copy of the step); 1 = the trajectory ends at
+    // t_stop with y_new = sol(t_stop), -1 = the queue is exhausted.
+    __device__ __forceinline__ int handle_events(const RkDev& P, unsigned active,
+                                                 const double (&K)[S + 1][NL],
+                                                 double (&y_new)[NL], double t_new, double h,
+                                                 double& t_stop) {
+        bool may_end = false;
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k)
+            if ((active >> k & 1u) && P.ev_terminal[k] > 0 && ev_n[k] + 1 >= P.ev_terminal[k])
+                may_end = true;
+        if (!may_end) return push_events(P, active, K, y_new, t_new, h) ? 0 : -1;
+        using LN = Lane<Tab, R>;
+        typename LN::EvSlow a;
+        LN::evslow_fill(a, P, K, y, y_new, prm, ev_n, t, t_new, h, (long long)sys, active, false);
+        LN::events_slow(a);
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = a.ev_n[k];
+        if (!a.terminate) return 0;
+        t_stop = a.t_stop;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) y_new[c] = a.y_stop[c];
+        return 1;
+    }
     // The step (stages, both end states) of every active event goes to the event
     // queue; t and y still hold the start of the step.  False: the queue is
     // exhausted (the host only selects this kernel when it cannot be).
@@ -631,7 +665,7 @@ struct FastLane {
         P.n_acc[sys] = n_acc;
         P.n_rej[sys] = n_rej;
         P.nfev[sys] = nfev0 + (S - 1 + Tab::FSAL) * (n_acc + n_rej) + (Tab::FSAL ? 0 : n_acc);
-        P.status[sys] = st;
+        P.status[sys] = st == LANE_EVENT ? 1 : st;    // 1: a termination event occurred
         if (P.n_eval_done) P.n_eval_done[sys] = 0;
         if (P.stiff_flags)
             P.stiff_flags[sys] = (int)((Lane<Tab, R>::stiff_state().bits[threadIdx.x] >>

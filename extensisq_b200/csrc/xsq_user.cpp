@@ -404,10 +404,11 @@ int compile(const std::string& key, const std::string& src, Compiled* out) {
 
 // Build the translation unit for (method, rhs); exposed for the CPU-side test
 // that NVRTC accepts it (no device needed to compile).
-// The fast kernel has no root finder and no dense output: it serves the plain
-// adaptive solve of a built-in generic pair and thread-per-system right-hand
-// side with event functions of which none is terminal, when the event queue is
-// large enough for every record the solve can produce (RkDev::evq_exact).
+// The fast kernel has no dense output of its own: it serves the adaptive solve
+// (no t_eval) of a built-in generic pair and thread-per-system right-hand side
+// with event functions when the event queue is large enough for every record the
+// solve can produce (RkDev::evq_exact).  Steps on which an event may be terminal
+// go through Lane::events_slow, out of line.
 static int fast_events_variant(int method, int rhs, int events, RkDev* P) {
     if (events == 0 || P->evq_cap <= 0 || !P->evq_exact) return 0;
     double h_min_a = 0.0;
@@ -428,8 +429,6 @@ static int fast_events_variant(int method, int rhs, int events, RkDev* P) {
     if (P->n_forced != 0 || P->n_eval != 0 || P->minalpha != 0.0 || P->max_steps != 0x7fffffff ||
         P->n_lanes >= (1LL << 31))
         return 0;
-    for (int k = 0; k < P->n_events; ++k)
-        if (P->ev_terminal[k] != 0) return 0;
     if (const char* e = getenv("XSQ_NO_FAST"))
         if (e[0] == '1') return 0;
     fast_prepare_h(*P, h_min_a);

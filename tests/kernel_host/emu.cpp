@@ -85,7 +85,6 @@ static int run(RkDev P, const MethodInfo& mi, bool want_fast, int* used_fast) {
         // xsq_user.cpp fast_events_variant
         bool ok = want_fast && P.evq_cap > 0 && P.evq_exact && P.n_forced == 0 && P.n_eval == 0 &&
                   P.minalpha == 0.0 && P.max_steps == 0x7fffffff;
-        for (int k = 0; k < P.n_events; ++k) ok = ok && P.ev_terminal[k] == 0;
         if (ok) {
 #else
         if (want_fast && fast_eligible<Tab, R>(P)) {

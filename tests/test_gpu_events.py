@@ -269,12 +269,13 @@ def test_event_queue_and_in_lane_root_solves_are_bit_identical(method, monkeypat
     y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
     prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
     te = np.linspace(0.0, 5.0, 41)
-    # without a terminal event and without t_eval the default run (queue large
-    # enough for every record) takes the fast kernel (rk_fast + event hooks) for
-    # the generic pairs, with and without the stiffness diagnosis; the runs with
-    # a limited queue take rk_persistent: the comparison covers both kernels
-    for term, kw in (([0, 0, 0], {}), ([0, 0, 0], dict(nfev_stiff_detect=0)), ([0, 6, 0], {}),
-                     ([0, 0, 0], dict(t_eval=te)), ([3, 0, 0], dict(t_eval=te))):
+    # without t_eval the default run (queue large enough for every record) takes
+    # the fast kernel (rk_fast + event hooks) for the generic pairs, with and
+    # without the stiffness diagnosis, terminal occurrences included; the runs
+    # with a limited queue take rk_persistent: the comparison covers both kernels
+    for term, kw in (([0, 0, 0], {}), ([0, 0, 0], dict(nfev_stiff_detect=0)), ([0, 2, 0], {}),
+                     ([2, 0, 3], dict(nfev_stiff_detect=0)), ([0, 0, 0], dict(t_eval=te)),
+                     ([3, 0, 0], dict(t_eval=te))):
         ev = events_for("lorenz_sections", term, [1, 0, -1])
         runs = []
         for q in ("0", "1500", None):
@@ -289,9 +290,9 @@ def test_event_queue_and_in_lane_root_solves_are_bit_identical(method, monkeypat
                          ("t_events", "y_events", "event_counts", "y_final", "t_final", "status",
                           "nfev", "n_accepted", "n_rejected", "h_next", "stiff_flags") +
                          (("y",) if "t_eval" in kw else ())})
-        assert runs[0]["event_counts"].sum() > 5 * N
-        if term[1]:
-            assert (runs[0]["status"] == 1).any()
+        assert runs[0]["event_counts"].sum() > (2 if any(term) else 5) * N
+        if any(term):
+            assert (runs[0]["status"] == 1).sum() > N // 4      # lanes stopped by the event
         for other in runs[1:]:
             for k, a in runs[0].items():
                 b = other[k]
