@@ -20,6 +20,22 @@ for m in (xb.Ts5, xb.BS5, xb.CKdisc):
                              max_event_records=4, rtol=1e-6, atol=1e-9)
     torch.cuda.synchronize()
     print(m.__name__, "events", int(r.event_counts.sum()), "status1", int((r.status == 1).sum()))
+# event queue: general kernel (t_eval above), rk_fast with event hooks (no t_eval; terminal and
+# not), a queue that overflows into the in-lane path, and no queue at all
+for term in ([0, 0], [0, 3]):
+    evq = ev.with_attributes(terminal=term, direction=[1, 0])
+    for q in (None, "700", "0"):
+        if q is None:
+            os.environ.pop("XSQ_EVENT_QUEUE_RECORDS", None)
+        else:
+            os.environ["XSQ_EVENT_QUEUE_RECORDS"] = q
+        for m in (xb.Ts5, xb.Pr8, xb.CKdisc):
+            r = xb.solve_ivp_batched("lorenz63", (0., 4.), y0, m, params=prm, events=evq,
+                                     max_event_records=6, rtol=1e-6, atol=1e-9)
+            torch.cuda.synchronize()
+            print("event queue", q or "default", term, m.__name__, "events", int(r.event_counts.sum()),
+                  "status1", int((r.status == 1).sum()))
+os.environ.pop("XSQ_EVENT_QUEUE_RECORDS", None)
 # stiffness probe queue and slots (queue forced small -> both paths)
 mu = 10.0 ** (-1 + 3 * np.arange(N) / (N - 1))
 for q in ("", "0", "50"):
