@@ -169,7 +169,7 @@ class BatchedOdeSolution:
             raise ValueError("`t` outside of the integrated span (no extrapolation on "
                              "the device).")
         uniq, inverse = np.unique(pts, return_inverse=True)
-        order = uniq if self.ascending else np.ascontiguousarray(uniq[::-1])
+        order = uniq if self.ascending else uniq[::-1].copy()
         fun, t_span, y0, method = self._args
         r = solve_ivp_batched(fun, t_span, y0, method, t_eval=order, **self._kw)
         idx = inverse if self.ascending else (len(uniq) - 1 - inverse)

@@ -313,8 +313,11 @@ static int solve_device(const xsq_rk_args_t* a, cudaStream_t st,
                 if (es != cudaSuccess) {
                     (void)cudaGetLastError();      // no queue: every root in the lane
                     evq = nullptr;
+                } else if (cudaMemsetAsync(evq, 0, head, st) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    cudaFreeAsync(evq, st);
+                    evq = nullptr;
                 } else {
-                    XSQ_CUDA(cudaMemsetAsync(evq, 0, head, st));
                     P.evq_count = (unsigned long long*)evq;
                     P.evq_fill = (unsigned*)(evq + 16);
                     P.evq = (double*)(evq + head);

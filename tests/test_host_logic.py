@@ -186,3 +186,40 @@ def test_device_events_and_sens_forward_argument_checks_need_no_gpu():
         xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0]], np.zeros((2, 1)), [1.0], t_eval=[0.0, 0.5])
     with pytest.raises(AssertionError):                  # rtol must be a float
         xb.sens_forward("", (0.0, 1.0), [[1.0, 1.0]], np.zeros((2, 1)), [1.0], rtol=1)
+
+
+def test_batched_ode_solution_orders_and_scatters_the_requested_times(monkeypatch):
+    """BatchedOdeSolution (dense_output=True) without a GPU: the solve it repeats
+    is replaced by a stub that validates t_eval like the real one (ivp.py:600-612)
+    and returns y = t; any order, repeated points, scalars, both directions."""
+    import numpy as np
+    import torch
+    import extensisq_b200.batched as B
+
+    class R:
+        pass
+
+    def fake(fun, t_span, y0, method, t_eval=None, **kw):
+        t0, tf = map(float, t_span)
+        te = B._as_device(t_eval, "cpu")
+        assert te.ndim == 1 and bool(((te >= min(t0, tf)) & (te <= max(t0, tf))).all())
+        d = te[1:] - te[:-1]
+        assert bool((d > 0).all()) if tf > t0 else bool((d < 0).all())
+        r = R()
+        r.y = torch.zeros(3, 2, te.numel(), dtype=torch.float64) + te
+        return r
+
+    monkeypatch.setattr(B, "solve_ivp_batched", fake)
+    for t_span in ((5.0, 9.0), (5.0, 1.0)):
+        sol = B.BatchedOdeSolution(None, t_span, None, None, {})
+        tc = np.linspace(*t_span)
+        assert np.array_equal(sol(tc)[1, 0].numpy(), tc)
+        tm = (t_span[0] + t_span[1]) / 2
+        assert sol(tm).shape == (3, 2) and float(sol(tm)[0, 1]) == tm
+        tq = np.array([t_span[1], tm, t_span[0], tm, tc[7]])
+        assert np.array_equal(sol(tq)[2, 1].numpy(), tq)
+        assert np.array_equal(sol(torch.tensor(tq))[0, 0].numpy(), tq)
+        with pytest.raises(ValueError):
+            sol(max(t_span) + 1.0)
+        with pytest.raises(ValueError):
+            sol(np.zeros((2, 2)) + tm)
