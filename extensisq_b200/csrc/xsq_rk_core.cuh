@@ -803,12 +803,17 @@ struct CkExtra<false> {};
 #ifdef XSQ_EVENTS_N
 // ---- event queue: chunked allocation ------------------------------------------
 // word = generation << 20 | records taken from the current chunk (a 32-bit word:
-// native shared-memory atomics); chunk[g & 3] is the chunk of generation g (-1: the
-// queue is exhausted).  At most blockDim.x appends overshoot a full chunk, so the
-// count never reaches 2^20.
+// native shared-memory atomics); chunk[g & 15] is the chunk of generation g (-1:
+// the queue is exhausted).  At most blockDim.x appends overshoot a full chunk, so
+// the count never reaches 2^20.
+// Synchronisation is through `word` alone: the installer writes chunk[g + 1], fences,
+// and publishes generation g + 1 with an atomic; a thread reads chunk[g] only after
+// its own atomic on `word` returned generation g.  (compute-sanitizer's racecheck
+// models barriers, not atomics, and reports this write / read pair as a hazard.)
+// A slot is rewritten 16 generations = 8192 appends of the CTA later.
 struct EvqShared {
     unsigned word;
-    long long chunk[4];
+    long long chunk[16];
 };
 __device__ __forceinline__ EvqShared& evq_shared() {
     __shared__ EvqShared s;
@@ -819,7 +824,7 @@ __device__ __forceinline__ EvqShared& evq_shared() {
 __device__ __forceinline__ void evq_cta_init() {
     EvqShared& s = evq_shared();
     s.word = (unsigned)kEvqChunk;
-    s.chunk[0] = s.chunk[1] = s.chunk[2] = s.chunk[3] = -1;
+    for (int i = 0; i < 16; ++i) s.chunk[i] = -1;
 }
 // The rare part of an append: the chunk is full.  Exactly one thread (the one
 // that drew i == kEvqChunk) installs the next chunk and takes its record 0; the
@@ -830,15 +835,15 @@ __device__ __noinline__ long long evq_alloc_slow(unsigned* evq_fill, unsigned lo
     for (;;) {
         const unsigned g = old >> 20, i = old & 0xfffffu;
         if (i < (unsigned)kEvqChunk) {
-            const long long c = *(volatile long long*)&s.chunk[g & 3u];
+            const long long c = *(volatile long long*)&s.chunk[g & 15u];
             return c < 0 ? -1 : c * kEvqChunk + (long long)i;
         }
         if (i == (unsigned)kEvqChunk) {
-            const long long prev = *(volatile long long*)&s.chunk[g & 3u];
+            const long long prev = *(volatile long long*)&s.chunk[g & 15u];
             if (prev >= 0) atomicMax(evq_fill + prev, (unsigned)kEvqChunk);
             const unsigned long long c = atomicAdd(evq_count, 1ull);
             const long long cc = c < (unsigned long long)n_chunks ? (long long)c : -1;
-            *(volatile long long*)&s.chunk[(g + 1u) & 3u] = cc;
+            *(volatile long long*)&s.chunk[(g + 1u) & 15u] = cc;
             __threadfence_block();
             atomicExch(&s.word, (((g + 1u) & 0xfffu) << 20) | (cc >= 0 ? 1u : 0u));
             return cc < 0 ? -1 : cc * kEvqChunk;
@@ -853,7 +858,7 @@ __device__ __forceinline__ long long evq_alloc(const RkDev& P) {
     const unsigned old = atomicAdd(&s.word, 1u);
     const unsigned i = old & 0xfffffu;
     if (i < (unsigned)kEvqChunk) {
-        const long long c = *(volatile long long*)&s.chunk[(old >> 20) & 3u];
+        const long long c = *(volatile long long*)&s.chunk[(old >> 20) & 15u];
         if (c >= 0) return c * kEvqChunk + (long long)i;
     }
     return evq_alloc_slow(P.evq_fill, P.evq_count, P.evq_cap / kEvqChunk, old);
@@ -863,7 +868,7 @@ __device__ __forceinline__ long long evq_alloc(const RkDev& P) {
 __device__ __forceinline__ void evq_cta_publish(const RkDev& P) {
     EvqShared& s = evq_shared();
     const unsigned w = *(volatile unsigned*)&s.word;
-    const long long c = *(volatile long long*)&s.chunk[(w >> 20) & 3u];
+    const long long c = *(volatile long long*)&s.chunk[(w >> 20) & 15u];
     const unsigned i = w & 0xfffffu;
     const unsigned n = i < (unsigned)kEvqChunk ? i : (unsigned)kEvqChunk;
     if (c >= 0) atomicMax(P.evq_fill + c, n);
