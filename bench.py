@@ -613,7 +613,7 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
                          "frac": tf / peak_tf,
                          "flops_model": "nfev x 31 x 20 x 32 (pair interactions)"}}
         del r, y0, prm
-    if "events" in which:
+    def _events_config():
         # scipy's `events=` on the C2 lanes (t in [0, 20]): three event functions, none
         # terminal, ~87 located events per lane.  Roots are located by event_queue
         # after the persistent kernel (xsq_rk_core.cuh after_step / evq_solve).
@@ -652,6 +652,12 @@ __device__ double event(int k, double t, const double* y, const double* p) {
         if have:
             e["kernels_ms"] = {"init": a.value, "persistent": b.value, "queues": c.value}
         del r
+
+    if "events" in which:
+        try:
+            _events_config()
+        except Exception as exc:      # keep the other configurations
+            out["events_Ts5_lorenz"] = {"error": repr(exc)}
     return out
 
 
