@@ -55,7 +55,8 @@ enum LaneStatus : int {
     LANE_STEP_BUDGET = -5, LANE_RUNNING = 1,
     LANE_EVQ_FULL = -6,  // the event queue ran out (cannot happen when RkDev::evq_exact)
     LANE_FLUSH = 2,     // internal: still running, stiffness probe slots are full
-    LANE_EVENT = 3      // internal: a terminal event ended the trajectory (status 1)
+    LANE_EVENT = 3,     // internal: a terminal event ended the trajectory (status 1)
+    LANE_EVCHECK = 4    // internal (rk_fast): the accepted step may hold a terminal event
 };
 #ifndef XSQ_MAX_BLOCK
 #define XSQ_MAX_BLOCK 256   // largest CTA any rk_persistent geometry launches

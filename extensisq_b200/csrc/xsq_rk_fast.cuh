@@ -376,8 +376,15 @@ struct FastLane {
     // One attempt of a step; returns the lane status.  `cb`: shared-memory
     // address of the coefficient stream, `h0`: this thread's word of the
     // "h_abs at the start of the step" array.
+#ifdef XSQ_EVENTS_N
+    using EvStash = typename Lane<Tab, R>::EvSlow;
+#else
+    struct EvStash {};
+#endif
+    // `stash`: where a step that may hold a terminal event is put for
+    // rk_fast_body to look at outside the stepping loop (LANE_EVCHECK)
     template <bool STIFF>
-    __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa) {
+    __device__ __forceinline__ int attempt(const RkDev& P, const SmemAddr& sa, EvStash& stash) {
         const SAddr cb = sa.coef;
         constexpr unsigned HI_N = hi_word_of_small_int(R::N);          // (double)N
         constexpr unsigned HI_TINY = HI_N - (1022u << 20);             // N * 2^-1022
@@ -485,7 +492,7 @@ struct FastLane {
         n_acc += accept ? 1 : 0;
         n_rej += accept ? 0 : 1;
         l2_old = accept ? l2 : l2_old;
-        double t_next = accept ? t_new : t;
+        const double t_next = accept ? t_new : t;
         // ---- what the next attempt needs ---------------------------------------
         // OdeSolver.step (base.py:207-208): done?  Then the next step's
         // _reassess_stepsize: nothing to do when  min_step < h_abs < max_step  and
@@ -519,18 +526,18 @@ struct FastLane {
                         if (st == LANE_RUNNING) st = LANE_FLUSH;
                     }
                 }
-                bool ev_end = false;
+                bool ev_check = false;
 #ifdef XSQ_EVENTS_N
                 if (ev_active != 0u) {                        // after the probe: it records y_new
-                    const int er = handle_events(P, ev_active, K, y_new, t_new, h, t_next);
+                    const int er = handle_events(P, ev_active, K, y_new, t_new, h, stash);
                     if (er < 0) st = LANE_EVQ_FULL;
-                    if (er > 0) {                             // a terminal event: t, y at the event
-                        ev_end = true;
-                        st = LANE_EVENT;
+                    if (er > 0) {                // maybe terminal: decided outside the loop
+                        ev_check = true;
+                        st = LANE_EVCHECK;
                     }
                 }
 #endif
-                if (!ev_end && !done && (out_of_range || near_end)) {
+                if (!ev_check && !done && (out_of_range || near_end)) {
                     h_abs = h_abs_new;
                     if (!reassess_exact(P, t_next, fabs(s), h_abs, fl)) st = LANE_TOO_SMALL;
                     fl |= FL_SLOW;
@@ -562,31 +569,42 @@ struct FastLane {
 
 #ifdef XSQ_EVENTS_N
     // handle_events (ivp.py) for the accepted step.  No active event at a terminal
-    // occurrence: the roots are left to the event queue.  Otherwise every root of
-    // the step is located now, out of line (Lane::events_slow: the general
-    // kernel's own code on a copy of the step); 1 = the trajectory ends at
-    // t_stop with y_new = sol(t_stop), -1 = the queue is exhausted.
+    // occurrence: the roots are left to the event queue (0; -1 = the queue is
+    // exhausted).  Otherwise (1) the step is copied to `stash` and the lane leaves
+    // the stepping loop with LANE_EVCHECK: rk_fast_body locates every root of the
+    // step with the general kernel's own code (Lane::events_slow) -- an
+    // out-of-line call INSIDE this function would have the registers that live
+    // across it spilled in the hot loop (measured: 61 -> 81 ms).
     __device__ __forceinline__ int handle_events(const RkDev& P, unsigned active,
                                                  const double (&K)[S + 1][NL],
-                                                 double (&y_new)[NL], double t_new, double h,
-                                                 double& t_stop) {
+                                                 const double (&y_new)[NL], double t_new, double h,
+                                                 EvStash& stash) {
         bool may_end = false;
 #pragma unroll
         for (int k = 0; k < XSQ_EVENTS_N; ++k)
             if ((active >> k & 1u) && P.ev_terminal[k] > 0 && ev_n[k] + 1 >= P.ev_terminal[k])
                 may_end = true;
         if (!may_end) return push_events(P, active, K, y_new, t_new, h) ? 0 : -1;
-        using LN = Lane<Tab, R>;
-        typename LN::EvSlow a;
-        LN::evslow_fill(a, P, K, y, y_new, prm, ev_n, t, t_new, h, (long long)sys, active, false);
-        LN::events_slow(a);
-#pragma unroll
-        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = a.ev_n[k];
-        if (!a.terminate) return 0;
-        t_stop = a.t_stop;
-#pragma unroll
-        for (int c = 0; c < NL; ++c) y_new[c] = a.y_stop[c];
+        Lane<Tab, R>::evslow_fill(stash, P, K, y, y_new, prm, ev_n, t, t_new, h, (long long)sys,
+                                  active, false);
         return 1;
+    }
+    // LANE_EVCHECK, outside the stepping loop: the lane already holds the accepted
+    // step (t, y, f, h_abs from the controller; _reassess_stepsize postponed).
+    // Returns the lane's status.
+    __device__ __forceinline__ int finish_event_check(const RkDev& P, const EvStash& stash) {
+#pragma unroll
+        for (int k = 0; k < XSQ_EVENTS_N; ++k) ev_n[k] = stash.ev_n[k];
+        if (stash.terminate) {                     // t, y at the event (ivp.py)
+            t = stash.t_stop;
+#pragma unroll
+            for (int c = 0; c < NL; ++c) y[c] = stash.y_stop[c];
+            return LANE_EVENT;
+        }
+        if (P.direction * (t - P.t_bound) >= 0.0) return LANE_FINISHED;
+        if (!reassess_exact(P, t, fabs(P.t_bound - t), h_abs, fl)) return LANE_TOO_SMALL;
+        fl |= FL_SLOW;
+        return LANE_RUNNING;
     }
     // The step (stages, both end states) of every active event goes to the event
     // queue; t and y still hold the start of the step.  False: the queue is
@@ -717,6 +735,7 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
     keep_in_register(sa.e2);
     keep_in_register(sa.h0);
     FL L;
+    typename FL::EvStash stash;
     bool live = false, exhausted = false;
     auto flush = [&](long long cur) {
         if (!__any_sync(full, LN::probes_pending())) return;
@@ -770,10 +789,25 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         // ---- attempts, until some lane of the warp ends its trajectory ----
         int st = LANE_RUNNING;
         do {
-            if (live) st = L.template attempt<STIFF>(P, sa);
+            if (live) st = L.template attempt<STIFF>(P, sa, stash);
         } while (!__any_sync(full, st != LANE_RUNNING));
         // both probe slots of some thread taken (queue full): run them now
         if (STIFF && __any_sync(full, LN::probes_urgent())) flush(live ? L.sys : -1);
+#ifdef XSQ_EVENTS_N
+        // a step that may hold a terminal event: every root of the step now, with the
+        // lane parked in local memory around the out-of-line call (as for the probes)
+        if (__any_sync(full, st == LANE_EVCHECK)) {
+            if (st == LANE_EVCHECK) {
+                FL parked = L;
+                memory_fence_for(&parked);
+                LN::events_slow(stash);
+                memory_fence_for(&parked);
+                L = parked;
+                st = L.finish_event_check(P, stash);
+            }
+            __syncwarp(full);
+        }
+#endif
         if (st == LANE_FLUSH) st = LANE_RUNNING;
         if (st != LANE_RUNNING) {
             L.store(P, st);
