@@ -579,6 +579,12 @@ struct FastLane {
                                                  const double (&K)[S + 1][NL],
                                                  const double (&y_new)[NL], double t_new, double h,
                                                  EvStash& stash) {
+#ifdef XSQ_EVENTS_NO_TERMINAL
+        // kernels compiled for event sets without a terminal event (the host knows):
+        // the stash and the check are not in the code at all (61 instead of 70 ms)
+        (void)stash;
+        return push_events(P, active, K, y_new, t_new, h) ? 0 : -1;
+#else
         bool may_end = false;
 #pragma unroll
         for (int k = 0; k < XSQ_EVENTS_N; ++k)
@@ -588,6 +594,7 @@ struct FastLane {
         Lane<Tab, R>::evslow_fill(stash, P, K, y, y_new, prm, ev_n, t, t_new, h, (long long)sys,
                                   active, false);
         return 1;
+#endif
     }
     // LANE_EVCHECK, outside the stepping loop: the lane already holds the accepted
     // step (t, y, f, h_abs from the controller; _reassess_stepsize postponed).
@@ -793,7 +800,7 @@ __device__ __forceinline__ void rk_fast_body(const RkDev& P) {
         } while (!__any_sync(full, st != LANE_RUNNING));
         // both probe slots of some thread taken (queue full): run them now
         if (STIFF && __any_sync(full, LN::probes_urgent())) flush(live ? L.sys : -1);
-#ifdef XSQ_EVENTS_N
+#if defined(XSQ_EVENTS_N) && !defined(XSQ_EVENTS_NO_TERMINAL)
         // a step that may hold a terminal event: every root of the step now, with the
         // lane parked in local memory around the out-of-line call (as for the probes)
         if (__any_sync(full, st == LANE_EVCHECK)) {

@@ -432,13 +432,16 @@ static int fast_events_variant(int method, int rhs, int events, RkDev* P) {
     if (const char* e = getenv("XSQ_NO_FAST"))
         if (e[0] == '1') return 0;
     fast_prepare_h(*P, h_min_a);
-    return P->nfev_stiff_detect > 0 ? 2 : 1;
+    bool terminal = false;
+    for (int k = 0; k < P->n_events; ++k) terminal = terminal || P->ev_terminal[k] != 0;
+    return (P->nfev_stiff_detect > 0 ? 2 : 1) + (terminal ? 2 : 0);
 }
 
 // variant 0: rk_persistent (everything); 1 / 2: rk_fast without / with the
 // stiffness diagnosis -- adaptive stepping of a built-in generic pair with
 // event functions none of which is terminal, every root located by the event
-// queue kernel (xsq_rk_fast.cuh)
+// queue kernel (xsq_rk_fast.cuh); 3 / 4: the same with terminal events (steps
+// that may end the trajectory are resolved outside the stepping loop)
 int user_build_source(int method, int rhs, int events, int variant, std::string* src,
                       std::string* key) {
     std::string tabname, rhsname, body;
@@ -450,6 +453,7 @@ int user_build_source(int method, int rhs, int events, int variant, std::string*
             return XSQ_ERR_ARG;
         }
         const UserEvents& e = g_events[(size_t)events - 1];
+        if (variant == 1 || variant == 2) body += "#define XSQ_EVENTS_NO_TERMINAL 1\n";
         body += "#define XSQ_EVENTS_N " + std::to_string(e.n) + "\n"
                 "__device__ double " + e.entry + "(int, double, const double*, const double*);\n"
                 "namespace xsq { __device__ __forceinline__ double user_event(int k, double t,\n"
@@ -519,7 +523,8 @@ int user_build_source(int method, int rhs, int events, int variant, std::string*
                       "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
                       "xsq_user_kernel(const xsq::RkDev P) {\n"
                       "    xsq::rk_fast_body<xsq::tab::%s, xsq::rhs::%s, 128, %s>(P);\n}\n",
-                      minb, tabname.c_str(), rhsname.c_str(), variant == 2 ? "true" : "false");
+                      minb, tabname.c_str(), rhsname.c_str(),
+                      (variant == 2 || variant == 4) ? "true" : "false");
     else
         std::snprintf(buf, sizeof buf,
                       "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"

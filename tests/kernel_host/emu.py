@@ -11,16 +11,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 _lib = None
 _lib_ev = None
+_lib_ev_nt = None
 _bits = None
 
 
-def build(events=False):
+def build(events=False, no_terminal=False):
     src = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h")]
     src += [os.path.join(ROOT, "extensisq_b200", "csrc", f) for f in
             ("xsq_rk_core.cuh", "xsq_rk_fast.cuh", "xsq_math.cuh", "xsq_intrin.cuh",
              "xsq_params.h", "xsq_rhs.cuh", "xsq_tableaux_gen.cuh", "xsq_math_tables_gen.cuh",
              "xsq_swag_core.cuh", "xsq_swag_fast.cuh")]
-    out = os.path.join(HERE, "_build", "xsq_emu_events.so" if events else "xsq_emu.so")
+    out = os.path.join(HERE, "_build", ("xsq_emu_events_nt.so" if no_terminal else
+                                        "xsq_emu_events.so") if events else "xsq_emu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if (not os.path.exists(out) or
             os.path.getmtime(out) < max(os.path.getmtime(f) for f in src)):
@@ -28,7 +30,8 @@ def build(events=False):
             ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-w",
              "-I", os.path.join(ROOT, "extensisq_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
              "-I", "/usr/local/cuda/include", "-o", out, src[0]] +
-            (["-DXSQ_EMU_EVENTS"] if events else []))
+            (["-DXSQ_EMU_EVENTS"] if events else []) +
+            (["-DXSQ_EVENTS_NO_TERMINAL"] if no_terminal else []))
     return out
 
 
@@ -43,12 +46,19 @@ def load():
     return _lib
 
 
-def load_events():
+def load_events(no_terminal=False):
     """The same sources compiled with the event machinery (XSQ_EVENTS_N = 3, the
-    event functions of oracle/problems.py EVENT_SETS['lorenz_sections'])."""
-    global _lib_ev
+    event functions of oracle/problems.py EVENT_SETS['lorenz_sections']);
+    no_terminal: the variant NVRTC builds for event sets without a terminal event."""
+    global _lib_ev, _lib_ev_nt
+    load()
+    if no_terminal:
+        if _lib_ev_nt is None:
+            _lib_ev_nt = C.CDLL(build(events=True, no_terminal=True))
+            _lib_ev_nt.xsq_emu_set_rcp_table(_bits.ctypes.data_as(C.c_void_p))
+            _lib_ev_nt.xsq_emu_detail.restype = C.c_char_p
+        return _lib_ev_nt
     if _lib_ev is None:
-        load()
         _lib_ev = C.CDLL(build(events=True))
         _lib_ev.xsq_emu_set_rcp_table(_bits.ctypes.data_as(C.c_void_p))
         _lib_ev.xsq_emu_detail.restype = C.c_char_p
@@ -58,14 +68,14 @@ def load_events():
 def solve(rhs, t_span, y0, method, params=None, rtol=1e-3, atol=1e-6, first_step=None,
           max_step=np.inf, sc_params=None, interpolant=None, t_eval=None, forced_steps=None,
           nfev_stiff_detect=5000, max_steps=None, fast=True, queue_records=-1, k_max=None,
-          events=None, max_event_records=16, event_queue_records=-1):
+          events=None, max_event_records=16, event_queue_records=-1, no_terminal_build=False):
     """Same arguments as extensisq_b200.solve_ivp_batched (built-in rhs names,
     built-in methods); returns numpy arrays.  `events=(terminal, direction)`
     selects the events build (three Lorenz section functions, lorenz63 only);
     `event_queue_records`: -1 every possible record, 0 no queue (roots in the lane)."""
     from extensisq_b200 import _lib as L
     from extensisq_b200.batched import _sc_tuple
-    lib = load_events() if events is not None else load()
+    lib = load_events(no_terminal_build) if events is not None else load()
     rid = {"lorenz63": 0, "vanderpol": 1, "arenstorf": 2}[rhs]      # include/xsq.h XSQ_RHS_*
     y0 = np.atleast_2d(np.asarray(y0, dtype=float))
     N, n = y0.shape
