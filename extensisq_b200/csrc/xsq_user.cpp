@@ -544,15 +544,21 @@ int user_build_source(int method, int rhs, int events, int variant, std::string*
                       "    xsq::stiff_queue_body<xsq::rhs::%s>(P, cost, stbrad, tanang);\n}\n",
                       rhsname.c_str());
     char buf4[320] = "";
+    int evq_minb = 1;                  // CTAs per SM the queue kernel is compiled for (no cap)
+    if (const char* e = getenv("XSQ_EVQ_MINB")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 16) evq_minb = v;
+    }
     if (!swag && events != 0)
         std::snprintf(buf4, sizeof buf4,
-                      "extern \"C\" __global__ void __launch_bounds__(128)\n"
+                      "extern \"C\" __global__ void __launch_bounds__(128, %d)\n"
                       "xsq_user_evq(const xsq::RkDev P) {\n"
                       "    xsq::event_queue_body<xsq::tab::%s, xsq::rhs::%s>(P);\n}\n",
-                      tabname.c_str(), rhsname.c_str());
+                      evq_minb, tabname.c_str(), rhsname.c_str());
     *src = body + buf + buf2 + buf3 + buf4;
     if (events != 0) *key += "/E" + std::to_string(events);
-    *key += "/B" + std::to_string(minb) + "/V" + std::to_string(variant);
+    *key += "/B" + std::to_string(minb) + "/V" + std::to_string(variant) + "/Q" +
+            std::to_string(evq_minb);
     return XSQ_OK;
 }
 
@@ -658,7 +664,7 @@ int user_rk_launch(int method, int rhs, int events, const RkDev& P, int cost, do
     }
     if (P.evq_cap > 0) {                     // the queued event roots
         if (!c.evq_fn) { set_detail("event queue kernel missing from the module"); return XSQ_ERR_CUDA; }
-        CUresult ce = g_api.LaunchKernel(c.evq_fn, (unsigned)(n_sm * 8), 1, 1, 128, 1, 1, 0,
+        CUresult ce = g_api.LaunchKernel(c.evq_fn, (unsigned)(n_sm * 16), 1, 1, 128, 1, 1, 0,
                                          (CUstream)st, args, nullptr);
         count_launch();
         if (ce != CUDA_SUCCESS) { set_detail("cuLaunchKernel(xsq_user_evq) failed"); return XSQ_ERR_CUDA; }

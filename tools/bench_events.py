@@ -51,11 +51,15 @@ MINB = os.environ.get("MINB_SWEEP", "")
 runs = [("in-lane roots", [0, 0, 0], "0", ""), ("event queue", [0, 0, 0], None, ""),
         ("event queue, 2nd event terminal at its 40th occurrence", [0, 40, 0], None, "")]
 runs += [(f"event queue, {b} CTAs/SM", [0, 0, 0], None, b) for b in MINB.split(",") if b]
+runs += [(f"event queue, queue kernel compiled for {b} CTAs/SM", [0, 0, 0], None, "q" + b)
+         for b in os.environ.get("EVQ_MINB_SWEEP", "").split(",") if b]
 for name, term, q, minb in runs:
-    if minb:
+    os.environ.pop("XSQ_USER_MINB", None)
+    os.environ.pop("XSQ_EVQ_MINB", None)
+    if minb.startswith("q"):
+        os.environ["XSQ_EVQ_MINB"] = minb[1:]
+    elif minb:
         os.environ["XSQ_USER_MINB"] = minb
-    else:
-        os.environ.pop("XSQ_USER_MINB", None)
     if q is None:
         os.environ.pop("XSQ_EVENT_QUEUE_RECORDS", None)
     else:
