@@ -66,7 +66,8 @@ int xsq_oracle_set_device_math(int on) {
 #define RELPER 0x1.172b83c7d517bp-20
 
 enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2, V_CKDISC = 3 };
-enum { ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_OVERFLOW = -2, ST_BUDGET = -5 };
+enum { ST_FINISHED = 0, ST_EVENT = 2, ST_TOO_SMALL = -1, ST_OVERFLOW = -2, ST_BUDGET = -5 };
+/* ST_EVENT is internal (1 is "running" in the loops below); reported as status 1 */
 enum { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
 enum { RHS_LORENZ = 0, RHS_VDP = 1, RHS_ARENSTORF = 2, RHS_NBODY32 = 3 };
 
@@ -147,6 +148,7 @@ static rhs_fn builtin_rhs(int id) {
     }
 }
 
+struct ev_ctx_s;
 typedef struct {
     const otab_t* T;
     rhs_fn f;
@@ -166,6 +168,7 @@ typedef struct {
     double K[KROWS][MAXN];
     int n_acc, n_rej, nfev, standard_sc;
     int force_cubic;               /* CKdisc: a fallback solution was accepted (cash.py:406-416) */
+    struct ev_ctx_s* ev;           /* scipy's `events=` (device arithmetic only), or NULL */
     /* stiffness diagnosis, common.py:150-164 */
     int nfev_stiff_detect, jflstp, okstp, stiff_flags, n_stiff_tests;
     double havg;
@@ -391,88 +394,261 @@ static void bs5_extra(lane_t* L, double h, int r) {
     L->nfev++;
 }
 
-static int emit(lane_t* L, double h, double t_new, const double* y_new,
-                const double* t_eval, int n_eval, int ieval, double* out) {
+/* The dense output of the step just accepted (common.py:766-821), formed once per
+ * step and evaluated at the t_eval points and wherever the root finder asks. */
+typedef struct {
+    double Q[MAXPOL][MAXN];
+    double t_anchor, h_anchor;
+    int npol, anchor_end, cubic, built;
+} dense_t;
+
+static void dense_build(lane_t* L, dense_t* D, double h, double t_new, const double* y_new) {
     const otab_t* T = L->T;
     const int n = L->n, s = T->s;
-    if (ieval >= n_eval) return ieval;
-    if (L->direction * (t_eval[ieval] - t_new) > 0.0) return ieval;
-    if (T->npol == 0 || L->force_cubic) { /* CubicDenseOutput, common.py:793-821 */
-        const double hh = t_new - L->t;
-        while (ieval < n_eval && L->direction * (t_eval[ieval] - t_new) <= 0.0) {
-            const double x = (t_eval[ieval] - L->t) / hh, omx = 1.0 - x;
-            const double h00 = (1.0 + 2.0 * x) * (omx * omx);
-            const double h10 = x * (omx * omx) * hh;
-            const double h01 = (x * x) * (3.0 - 2.0 * x);
-            const double h11 = (x * x) * (x - 1.0) * hh;
-            for (int c = 0; c < n; ++c)
-                out[(size_t)c * n_eval + ieval] =
-                    ((h00 * L->y[c] + h10 * L->K[0][c]) + h01 * y_new[c]) + h11 * L->K[s][c];
-            ++ieval;
-        }
-        return ieval;
-    }
-    double Q[MAXPOL][MAXN];
-    int npol = T->npol, anchor_end = 0;
-    double t_anchor = L->t, h_anchor = t_new - L->t;
+    D->built = 1;
+    D->cubic = T->npol == 0 || L->force_cubic;
+    D->npol = T->npol;
+    D->t_anchor = L->t;
+    D->h_anchor = t_new - L->t;
+    D->anchor_end = 0;
+    if (D->cubic) return;
     if (T->variant == V_BS5 && L->interpolant == IP_LOW) {
         bs5_extra(L, h, 0);
-        npol = T->npol_low;
-        for (int k = 0; k < npol; ++k)
+        D->npol = T->npol_low;
+        for (int k = 0; k < D->npol; ++k)
             for (int c = 0; c < n; ++c) {
                 double acc = 0.0;
                 for (int i = 0; i <= s + 1; ++i)
                     if (T->Plow[i][k] != 0.0) acc = fma(T->Plow[i][k], L->K[i][c], acc);
-                Q[k][c] = acc;
+                D->Q[k][c] = acc;
             }
     } else if (T->variant == V_BS5 && L->interpolant == IP_BEST) {
         bs5_extra(L, h, 0);
         bs5_extra(L, h, 1);
         bs5_extra(L, h, 2);
-        npol = T->npol_best;
+        D->npol = T->npol_best;
         for (int c = 0; c < n; ++c) { /* bogacki.py:372-388 */
             double kp[11];
-            Q[0][c] = L->K[7][c];
+            D->Q[0][c] = L->K[7][c];
 #define KP(col) for (int i = 0; i < 11; ++i) kp[i] = L->K[i][c] * T->Pbest[i][col];
-            KP(1) Q[1][c] = (kp[4] + ((kp[5] + kp[7]) + kp[0]) + ((kp[2] + kp[8]) + kp[9]) +
-                             ((kp[3] + kp[10]) + kp[6]));
-            KP(2) Q[2][c] = (kp[4] + kp[5] + ((kp[2] + kp[8]) + (kp[9] + kp[7]) + kp[0]) +
-                             ((kp[3] + kp[10]) + kp[6]));
-            KP(3) Q[3][c] = (((kp[3] + kp[7]) + (kp[6] + kp[5]) + kp[4]) +
-                             ((kp[9] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
-            KP(4) Q[4][c] = ((kp[9] + kp[8]) + ((kp[6] + kp[5]) + kp[4]) +
-                             ((kp[3] + kp[7]) + (kp[2] + kp[10]) + kp[0]));
-            KP(5) Q[5][c] = (kp[4] + ((kp[9] + kp[7]) + (kp[6] + kp[5])) +
-                             ((kp[3] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
+            KP(1) D->Q[1][c] = (kp[4] + ((kp[5] + kp[7]) + kp[0]) + ((kp[2] + kp[8]) + kp[9]) +
+                                ((kp[3] + kp[10]) + kp[6]));
+            KP(2) D->Q[2][c] = (kp[4] + kp[5] + ((kp[2] + kp[8]) + (kp[9] + kp[7]) + kp[0]) +
+                                ((kp[3] + kp[10]) + kp[6]));
+            KP(3) D->Q[3][c] = (((kp[3] + kp[7]) + (kp[6] + kp[5]) + kp[4]) +
+                                ((kp[9] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
+            KP(4) D->Q[4][c] = ((kp[9] + kp[8]) + ((kp[6] + kp[5]) + kp[4]) +
+                                ((kp[3] + kp[7]) + (kp[2] + kp[10]) + kp[0]));
+            KP(5) D->Q[5][c] = (kp[4] + ((kp[9] + kp[7]) + (kp[6] + kp[5])) +
+                                ((kp[3] + kp[8]) + (kp[2] + kp[10]) + kp[0]));
 #undef KP
         }
-        anchor_end = 1;
-        t_anchor = t_new;
-        h_anchor = (t_new + h) - t_new;
+        D->anchor_end = 1;
+        D->t_anchor = t_new;
+        D->h_anchor = (t_new + h) - t_new;
     } else { /* Q = K.T @ P, common.py:363 */
-        for (int k = 0; k < npol; ++k)
+        for (int k = 0; k < D->npol; ++k)
             for (int c = 0; c < n; ++c) {
                 double acc = 0.0;
                 for (int i = 0; i <= s; ++i)
                     if (T->P[i][k] != 0.0) acc = fma(T->P[i][k], L->K[i][c], acc);
-                Q[k][c] = acc;
+                D->Q[k][c] = acc;
             }
     }
-    for (int k = 0; k < npol; ++k)
-        for (int c = 0; c < n; ++c) Q[k][c] *= h_anchor;
-    while (ieval < n_eval && L->direction * (t_eval[ieval] - t_new) <= 0.0) {
-        const double x = (t_eval[ieval] - t_anchor) / h_anchor;
-        for (int c = 0; c < n; ++c) { /* Horner, common.py:781-785 */
-            double v = Q[npol - 1][c] * x;
-            for (int k = npol - 2; k >= 0; --k) v = (v + Q[k][c]) * x;
-            out[(size_t)c * n_eval + ieval] = v + (anchor_end ? y_new[c] : L->y[c]);
-        }
+    for (int k = 0; k < D->npol; ++k)
+        for (int c = 0; c < n; ++c) D->Q[k][c] *= D->h_anchor;
+}
+
+/* sol(te) of the step; out[c * stride] */
+static void dense_eval(const lane_t* L, const dense_t* D, double t_new, const double* y_new,
+                       double te, double* out, size_t stride) {
+    const int n = L->n, s = L->T->s;
+    if (D->cubic) { /* CubicDenseOutput, common.py:793-821 */
+        const double hh = t_new - L->t;
+        const double x = (te - L->t) / hh, omx = 1.0 - x;
+        const double h00 = (1.0 + 2.0 * x) * (omx * omx);
+        const double h10 = x * (omx * omx) * hh;
+        const double h01 = (x * x) * (3.0 - 2.0 * x);
+        const double h11 = (x * x) * (x - 1.0) * hh;
+        for (int c = 0; c < n; ++c)
+            out[(size_t)c * stride] =
+                ((h00 * L->y[c] + h10 * L->K[0][c]) + h01 * y_new[c]) + h11 * L->K[s][c];
+        return;
+    }
+    const double x = (te - D->t_anchor) / D->h_anchor;
+    for (int c = 0; c < n; ++c) { /* Horner, common.py:781-785 */
+        double v = D->Q[D->npol - 1][c] * x;
+        for (int k = D->npol - 2; k >= 0; --k) v = (v + D->Q[k][c]) * x;
+        out[(size_t)c * stride] = v + (D->anchor_end ? y_new[c] : L->y[c]);
+    }
+}
+
+/* the t_eval points of (t_old, t_stop]; writes out[c*n_eval+i] */
+static int emit_upto(lane_t* L, dense_t* D, double h, double t_new, const double* y_new,
+                     double t_stop, const double* t_eval, int n_eval, int ieval, double* out) {
+    if (ieval >= n_eval) return ieval;
+    if (L->direction * (t_eval[ieval] - t_stop) > 0.0) return ieval;
+    if (!D->built) dense_build(L, D, h, t_new, y_new);
+    while (ieval < n_eval && L->direction * (t_eval[ieval] - t_stop) <= 0.0) {
+        dense_eval(L, D, t_new, y_new, t_eval[ieval], out + ieval, (size_t)n_eval);
         ++ieval;
     }
     return ieval;
 }
 
-/* ---- stiffness diagnosis: common.py:370-516 and stiff_a..d (:824-1204) ---- */
+static int emit(lane_t* L, double h, double t_new, const double* y_new,
+                const double* t_eval, int n_eval, int ieval, double* out) {
+    dense_t D;
+    D.built = 0;
+    return emit_upto(L, &D, h, t_new, y_new, t_new, t_eval, n_eval, ieval, out);
+}
+
+/* ---- scipy's `events=` in the kernels' arithmetic (xsq_rk_core.cuh after_step,
+ * events_now, brentq_dev; scipy/integrate/_ivp/ivp.py find_active_events,
+ * handle_events, solve_event_equation; scipy.optimize brentq with
+ * xtol = rtol = 4 eps).  Device arithmetic only: the reference's arithmetic with
+ * events is oracle/rk_oracle.py. ---- */
+typedef double (*event_fn)(int k, double t, const double* y, const double* p);
+#define MAXEV 8
+typedef struct ev_ctx_s {
+    event_fn g;
+    int n_events, capacity;
+    int terminal[MAXEV], direction[MAXEV];
+    double* t_events;   /* [n_events][capacity] */
+    double* y_events;   /* [n_events][capacity][n] */
+    int32_t* counts;    /* [n_events] */
+    double g_old[MAXEV];
+} ev_ctx_t;
+
+static double ev_lorenz_sections(int k, double t, const double* y, const double* p) {
+    (void)t; (void)p;
+    if (k == 0) return y[2] - 27.0;
+    if (k == 1) return y[0];
+    return y[0] * y[1] - 30.0;
+}
+
+typedef struct {
+    lane_t* L; const dense_t* D; const ev_ctx_t* E; const double* y_new; double t_new; int k;
+} ev_root_ctx;
+static double ev_of_t(const ev_root_ctx* c, double tt) {
+    double ytmp[MAXN];
+    dense_eval(c->L, c->D, c->t_new, c->y_new, tt, ytmp, 1);
+    return c->E->g(c->k, tt, ytmp, c->L->prm);
+}
+static double brentq_c(const ev_root_ctx* c, double xa, double xb) {
+    const double tol = 4.0 * 0x1.0p-52;
+    double xpre = xa, xcur = xb;
+    double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+    double fpre = ev_of_t(c, xpre);
+    double fcur = ev_of_t(c, xcur);
+    if (fpre == 0.0) return xpre;
+    if (fcur == 0.0) return xcur;
+    if ((signbit(fpre) != 0) == (signbit(fcur) != 0)) return xcur;
+    for (int it = 0; it < 100; ++it) {
+        if (fpre != 0.0 && fcur != 0.0 && (signbit(fpre) != 0) != (signbit(fcur) != 0)) {
+            xblk = xpre;
+            fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        const double delta = (tol + tol * fabs(xcur)) / 2;
+        const double sbis = (xblk - xcur) / 2;
+        if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                const double dpre = (fpre - fcur) / (xpre - xcur);
+                const double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            const double lim_a = fabs(spre), lim_b = 3 * fabs(sbis) - delta;
+            if (2 * fabs(stry) < (lim_b < lim_a ? lim_b : lim_a)) {
+                spre = scur;
+                scur = stry;
+            } else {
+                spre = sbis;
+                scur = sbis;
+            }
+        } else {
+            spre = sbis;
+            scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = ev_of_t(c, xcur);
+    }
+    return xcur;
+}
+
+/* Everything solve_ivp does after solver.step() returned: events, then the t_eval
+ * points of the step.  Returns 1 when a terminal event ends the trajectory; *t_new
+ * / y_new are then the event point. */
+static int events_after_step(lane_t* L, double h, double* t_new, double* y_new,
+                             const double* t_eval, int n_eval, int* ieval, double* y_eval) {
+    ev_ctx_t* E = L->ev;
+    dense_t D;
+    D.built = 0;
+    double g_new[MAXEV], root[MAXEV];
+    unsigned active = 0;
+    for (int k = 0; k < E->n_events; ++k) {
+        g_new[k] = E->g(k, *t_new, y_new, L->prm);
+        const int up = E->g_old[k] <= 0.0 && g_new[k] >= 0.0;
+        const int down = E->g_old[k] >= 0.0 && g_new[k] <= 0.0;
+        const int d = E->direction[k];
+        if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) active |= 1u << k;
+    }
+    int terminate = 0;
+    double t_stop = *t_new;
+    if (active) {
+        dense_build(L, &D, h, *t_new, y_new);
+        int any_term = 0;
+        double r_star = 0.0;
+        for (int k = 0; k < E->n_events; ++k) {
+            if (!(active >> k & 1u)) continue;
+            ev_root_ctx c = {L, &D, E, y_new, *t_new, k};
+            root[k] = brentq_c(&c, L->t, *t_new);
+        }
+        for (int k = 0; k < E->n_events; ++k) {
+            if (!(active >> k & 1u)) continue;
+            ++E->counts[k];
+            if (E->terminal[k] > 0 && E->counts[k] >= E->terminal[k]) {
+                if (!any_term || L->direction * (root[k] - r_star) < 0.0) r_star = root[k];
+                any_term = 1;
+            }
+        }
+        terminate = any_term;
+        if (terminate) t_stop = r_star;
+        for (int k = 0; k < E->n_events; ++k) {
+            if (!(active >> k & 1u)) continue;
+            if (terminate && L->direction * (root[k] - r_star) > 0.0) continue;
+            const int slot = E->counts[k] - 1;
+            if (slot < E->capacity) {
+                const size_t base = (size_t)k * E->capacity + slot;
+                E->t_events[base] = root[k];
+                dense_eval(L, &D, *t_new, y_new, root[k], E->y_events + base * L->n, 1);
+            }
+        }
+    }
+    for (int k = 0; k < E->n_events; ++k) E->g_old[k] = g_new[k];
+    if (n_eval > 0)
+        *ieval = emit_upto(L, &D, h, *t_new, y_new, t_stop, t_eval, n_eval, *ieval, y_eval);
+    if (terminate) {
+        if (!D.built) dense_build(L, &D, h, *t_new, y_new);
+        double ys[MAXN];
+        dense_eval(L, &D, *t_new, y_new, t_stop, ys, 1);
+        memcpy(y_new, ys, sizeof(double) * L->n);
+        *t_new = t_stop;
+    }
+    return terminate;
+}
+
 static double wdot(const double* a, const double* b, const double* wt, int n) {
     wacc_t w;
     wacc_init(&w);
@@ -739,20 +915,24 @@ static void ck_solve_one(lane_t* L, double tf, const double* t_eval, int n_eval,
         const double t_new = L->t + h;
         L->f(t_new, y_new, L->prm, L->K[s]);
         L->nfev++;
-        if (n_eval > 0) {
-            L->force_cubic = accepted != 4;
-            ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
-        }
-        L->t = t_new;
+        L->force_cubic = accepted != 4;
+        double t_end = t_new;
+        int ev_stop = 0;
+        if (L->ev) ev_stop = events_after_step(L, h, &t_end, y_new, t_eval, n_eval, &ieval, y_eval);
+        else if (n_eval > 0) ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
+        L->t = t_end;
         memcpy(L->y, y_new, sizeof(double) * n);
         memcpy(L->fcur, L->K[s], sizeof(double) * n);
         L->n_acc++;
-        if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
+        if (ev_stop) st = ST_EVENT;
+        else if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
         else if (L->n_acc + L->n_rej >= max_steps) st = ST_BUDGET;
     }
     *ieval_out = ieval;
     *st_out = st;
 }
+
+static _Thread_local ev_ctx_t* g_ev_lane = 0;
 
 /* One trajectory: solve_ivp(fun, (t0, tf), y0, method=T, ...). */
 static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
@@ -767,6 +947,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                          int32_t* stiff_flags) {
     lane_t* L = (lane_t*)malloc(sizeof(lane_t));
     L->force_cubic = 0;
+    L->ev = g_ev_lane;                 /* set per lane by xsq_oracle_rk_events_batch */
     L->nfev_stiff_detect = (T->stbrad > 0.0 && T->tanang > 0.0) ? nfev_stiff_detect : 0;
     L->jflstp = L->okstp = L->stiff_flags = L->n_stiff_tests = 0;
     L->havg = 0.0;
@@ -817,6 +998,8 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
         const double b = t0 + L->direction * fmin(fabs(tf - t0), max_step);
         L->h_abs = h_start(L, t0, b, T->order2);
     }
+    if (L->ev)
+        for (int k = 0; k < L->ev->n_events; ++k) L->ev->g_old[k] = L->ev->g(k, t0, L->y, prm);
     int ieval = 0, st = 1, attempts = 0;
     const int early = T->variant != V_GENERIC;
     const int fsal = T->E[s] != 0.0;
@@ -953,7 +1136,13 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
             }
             }
             if (!fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
-            if (n_eval > 0) ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
+            /* the probe of the stiffness diagnosis sees the step as taken, whatever the
+             * events do with it afterwards (it runs inside solver.step()) */
+            double t_end = t_new, y_end[MAXN];
+            memcpy(y_end, y_new, sizeof(double) * n);
+            int ev_stop = 0;
+            if (L->ev) ev_stop = events_after_step(L, h, &t_end, y_end, t_eval, n_eval, &ieval, y_eval);
+            else if (n_eval > 0) ieval = emit(L, h, t_new, y_new, t_eval, n_eval, ieval, y_eval);
             L->h_prev = h;
             L->err_old = err;
             L->t = t_new;
@@ -963,7 +1152,11 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
             memcpy(L->fcur, L->K[s], sizeof(double) * n);
             L->n_acc++;
             if (!forced) diagnose_stiffness(L, y_old, errv, h);
-            if (forced) { if (L->n_acc >= n_forced) st = ST_FINISHED; }
+            if (ev_stop) {                        /* t, y = the event point (ivp.py) */
+                L->t = t_end;
+                memcpy(L->y, y_end, sizeof(double) * n);
+                st = ST_EVENT;
+            } else if (forced) { if (L->n_acc >= n_forced) st = ST_FINISHED; }
             else if (L->direction * (L->t - tf) >= 0.0) st = ST_FINISHED;
             break;
         }
@@ -973,7 +1166,7 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     *t_final = L->t;
     memcpy(y_final, L->y, sizeof(double) * n);
     if (h_next) *h_next = L->h_abs;
-    *n_acc = L->n_acc; *n_rej = L->n_rej; *nfev = L->nfev; *status = st;
+    *n_acc = L->n_acc; *n_rej = L->n_rej; *nfev = L->nfev; *status = st == ST_EVENT ? 1 : st;
     if (n_eval_done) *n_eval_done = ieval;
     if (stiff_flags) *stiff_flags = L->stiff_flags;
     free(L);
@@ -1008,6 +1201,54 @@ int xsq_oracle_rk_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
                      n_acc + i, n_rej + i, nfev + i, status + i,
                      n_eval_done ? n_eval_done + i : 0, nfev_stiff_detect,
                      stiff_flags ? stiff_flags + i : 0);
+    }
+    return 0;
+}
+
+/* The same with scipy's `events=` (device arithmetic).  ev_set 0: the three Lorenz
+ * section functions of oracle/problems.py EVENT_SETS["lorenz_sections"]; < 0:
+ * `user_g` (a C function pointer, single thread).  t_events [N][n_events][capacity],
+ * y_events [N][n_events][capacity][n] (NaN where unused), ev_count [N][n_events]. */
+int xsq_oracle_rk_events_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
+                               int64_t n_lanes, const double* y0, const double* params,
+                               double t0, double tf, double rtol, const double* atol,
+                               double first_step, double max_step, const double* sc,
+                               int interpolant, const double* t_eval, int n_eval,
+                               double* y_eval, int max_steps, double* t_final, double* y_final,
+                               double* h_next, int32_t* n_acc, int32_t* n_rej,
+                               int32_t* nfev, int32_t* status, int32_t* n_eval_done,
+                               int n_threads, int nfev_stiff_detect, int32_t* stiff_flags,
+                               int ev_set, event_fn user_g, int n_events, const int32_t* terminal,
+                               const int32_t* direction, int capacity, double* t_events,
+                               double* y_events, int32_t* ev_count) {
+    rhs_fn f = rhs >= 0 ? builtin_rhs(rhs) : user_f;
+    event_fn g = ev_set == 0 ? ev_lorenz_sections : user_g;
+    if (!f || !g || n > MAXN || T->s >= MAXS || n_events < 1 || n_events > MAXEV || capacity < 1 ||
+        !g_device_math)
+        return -1;
+    if (max_steps <= 0) max_steps = 2147483647;
+    if (rhs < 0 || ev_set < 0) n_threads = 1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n_lanes; ++i) {
+        ev_ctx_t E;
+        E.g = g; E.n_events = n_events; E.capacity = capacity;
+        for (int k = 0; k < n_events; ++k) { E.terminal[k] = terminal[k]; E.direction[k] = direction[k]; }
+        E.t_events = t_events + (size_t)i * n_events * capacity;
+        E.y_events = y_events + (size_t)i * n_events * capacity * n;
+        E.counts = ev_count + (size_t)i * n_events;
+        for (int k = 0; k < n_events; ++k) E.counts[k] = 0;
+        g_ev_lane = &E;
+        rk_solve_one(T, f, n, y0 + i * n, params ? params + i * p : 0, t0, tf, rtol,
+                     atol, first_step, max_step, sc, interpolant, t_eval, n_eval,
+                     y_eval ? y_eval + (size_t)i * n * n_eval : 0, 0, 0,
+                     max_steps, t_final + i, y_final + i * n, h_next ? h_next + i : 0,
+                     n_acc + i, n_rej + i, nfev + i, status + i,
+                     n_eval_done ? n_eval_done + i : 0, nfev_stiff_detect,
+                     stiff_flags ? stiff_flags + i : 0);
+        g_ev_lane = 0;
     }
     return 0;
 }

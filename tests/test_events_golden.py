@@ -153,3 +153,37 @@ def test_reference_t_eval_early_event_on_the_oracle(method):
     assert r["status"] == 1
     assert r["t"].size == 0 and r["y"].size == 0
     assert r["t_events"][0].size == 1 and r["t_events"][0][0] == 7
+
+
+@pytest.mark.parametrize("c", RK_CASES, ids=lambda c: c["id"])
+def test_c_oracle_events_in_device_arithmetic_against_the_reference(c):
+    """events_after_step / brentq_c of oracle/xsq_oracle.c (the C restatement of
+    the kernels' event handling, bit-identical to the kernel sources:
+    tests/test_kernel_host.py) against the reference's golden runs: same status,
+    and -- where the kernels' arithmetic takes the same steps -- event times to
+    1e-9, event states to 1e-7, the t_eval output cut at the same terminal event."""
+    from oracle import c_oracle as CO
+    opts = ev_options(c)
+    fns, _ = EVENT_SETS[c["events"]]
+    te = ev_t_eval(c)
+    with CO.device_math():
+        o = CO.rk_events_batch(TABS[c["method"]], None, c["t_span"], [c["y0"]], list(fns),
+                               c["terminal"], c["direction"], 64, t_eval=te,
+                               user_fn=make_fun(c["problem"], c["params"]), **opts)
+    assert int(o["status"][0]) == c["status"]
+    if int(o["nfev"][0]) != c["nfev"] or int(o["n_rejected"][0]) != c["nfs"]:
+        pytest.skip("the kernels' arithmetic takes a different step sequence on this case")
+    for k in range(len(c["terminal"])):
+        tg = unhex(c["t_events"][k])
+        assert int(o["event_counts"][0, k]) >= tg.size
+        assert np.allclose(o["t_events"][0, k, :tg.size], tg, rtol=1e-9, atol=1e-9)
+        assert np.isnan(o["t_events"][0, k, tg.size:]).all()
+        if tg.size:
+            ye = unhex(c["y_events"][k]).reshape(tg.size, -1)
+            assert np.allclose(o["y_events"][0, k, :tg.size], ye, rtol=1e-7, atol=1e-7)
+    if te is not None:
+        yg = unhex(c["y"])
+        n_done = int(o["n_eval_done"][0])
+        assert n_done == (yg.shape[1] if yg.ndim == 2 else 0)
+        if n_done:
+            assert np.allclose(o["y"][0][:, :n_done], yg, rtol=1e-7, atol=1e-7)

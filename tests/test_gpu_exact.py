@@ -161,6 +161,48 @@ def test_ckdisc_nonsmooth_ensemble_bit_identical_and_cost_of_arithmetic():
     assert abs(g["nfev"].mean() / r["nfev"].mean() - 1) < 0.05
 
 
+# ---- events ------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [xb.Ts5, xb.BS5, xb.Pr8, xb.CKdisc], ids=lambda m: m.__name__)
+def test_events_bit_identical_to_oracle_in_device_arithmetic(m):
+    """scipy's `events=` on the device (event queue + event_queue_body, rk_fast
+    with event hooks, the in-lane solver for terminal occurrences) against the
+    independent C restatement of ivp.py's event handling in the kernels'
+    arithmetic (oracle/xsq_oracle.c events_after_step / brentq_c, pinned to the
+    reference's golden runs by tests/test_events_golden.py): event times and
+    states, counts, terminal stops, the t_eval output cut at the event, and the
+    trajectory outputs, bit for bit on every lane."""
+    from oracle.problems import EVENT_SETS
+    tab = O.load_ckdisc() if m is xb.CKdisc else TABS[m.__name__]
+    _, src = EVENT_SETS["lorenz_sections"]
+    ev0 = xb.DeviceEvents.from_source(src, "event", 3)
+    y0, prm = lorenz_lanes(768, seed=31)
+    te = np.linspace(0.0, 6.0, 61)
+    cap = 16
+    for term, kw in (([0, 0, 0], {}), ([0, 3, 0], {}), ([2, 0, 4], dict(nfev_stiff_detect=0)),
+                     ([0, 0, 0], dict(t_eval=te)), ([3, 0, 0], dict(t_eval=te))):
+        direc = [1, 0, -1]
+        base = dict(rtol=1e-7, atol=1e-9, **kw)
+        ev = ev0.with_attributes(terminal=term, direction=direc)
+        res = xb.solve_ivp_batched("lorenz63", (0.0, 6.0), y0, m, params=prm, events=ev,
+                                   max_event_records=cap, **base)
+        torch.cuda.synchronize()
+        g = {k: getattr(res, k).cpu().numpy() for k in KEYS_F + KEYS_I + ("t_events", "y_events",
+                                                                          "event_counts")}
+        g["stiff_flags"] = res.stiff_flags.cpu().numpy()
+        g["y"] = res.y.cpu().numpy() if res.y is not None else None
+        with CO.device_math():
+            o = CO.rk_events_batch(tab, "lorenz63", (0.0, 6.0), y0, "lorenz_sections", term, direc,
+                                   cap, params=prm, n_threads=THREADS, **base)
+        assert g["event_counts"].sum() > 2 * len(y0)
+        if any(term):
+            assert (g["status"] == 1).sum() > len(y0) // 4
+        assert_identical(g, o, (m.__name__, term, sorted(kw)), dense="t_eval" in kw)
+        for k in ("t_events", "y_events", "event_counts"):
+            a, b = g[k], o[k]
+            same = (a == b) | ((a != a) & (b != b))
+            assert same.all(), (m.__name__, term, sorted(kw), k, np.argwhere(~same)[:4])
+
+
 # ---- C4: the perturbed Arenstorf ensemble of bench.py ----------------------------
 def test_c4_collision_orbits():
     """The first 16 384 lanes of bench.py's C4 ensemble (Arenstorf initial state

@@ -234,6 +234,16 @@ def test_event_kernel_sources_in_lane_queue_and_fast_agree(m):
             others.append((e, "fast, no-terminal build"))
         for other, name in others:
             _same_events(a, other, (m.__name__, term, sorted(kw), name), k2)
+        # ... and against the INDEPENDENT restatement of the event handling in the C
+        # oracle (events_after_step, brentq_c, dense_build / dense_eval of
+        # oracle/xsq_oracle.c in device arithmetic): every event record, count,
+        # status and trajectory output bit for bit
+        tab_o = O.load_ckdisc() if m is xb.CKdisc else TABS[m.__name__]
+        okw = {k: v for k, v in base.items() if k not in ("events", "max_event_records")}
+        with CO.device_math():
+            oe = CO.rk_events_batch(tab_o, "lorenz63", (0.0, 5.0), y0, "lorenz_sections", term,
+                                    [1, 0, -1], 12, params=prm, n_threads=CO.max_threads(), **okw)
+        _same_events(a, oe, (m.__name__, term, sorted(kw), "C oracle with events"), k2)
         if term == [0, 0, 0]:
             # events never change t, y, h: the plain solve of the oracle
             okw = {k: v for k, v in base.items() if k not in ("events", "max_event_records")}
