@@ -34,6 +34,8 @@ class OTab(C.Structure):
         ("B_fallback", (C.c_double * MAXS) * 2), ("E_fallback", (C.c_double * MAXS) * 2),
         ("C_fallback", C.c_double * 2), ("ck_max_factor", C.c_double),
         ("ck_min_factor", C.c_double), ("ck_safety", C.c_double),
+        ("Ap", (C.c_double * MAXS) * MAXS), ("Bp", C.c_double * MAXS),
+        ("Ep", C.c_double * (MAXS + 1)),
     ]
 
 
@@ -163,6 +165,13 @@ def make_tab(tab, sc_params=None):
         t.ck_max_factor = float(tab.max_factor)
         t.ck_min_factor = float(tab.min_factor)
         t.ck_safety = float(tab.safety)
+    if getattr(tab, "variant", "") == "nystrom":     # common.py:1207-1309
+        t.variant = 4
+        _fill2(t.Ap, tab.Ap)
+        for i in range(s):
+            t.Bp[i] = float(tab.Bp[i])
+        for i in range(s + 1):
+            t.Ep[i] = float(tab.Ep[i])
     scp = sc_params if sc_params is not None else tab.sc_params
     if isinstance(scp, str):
         scp = O.SC_PRESETS[scp]

@@ -65,7 +65,7 @@ int xsq_oracle_set_device_math(int on) {
 #define SMALL 0x1.0000000000001p-53
 #define RELPER 0x1.172b83c7d517bp-20
 
-enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2, V_CKDISC = 3 };
+enum { V_GENERIC = 0, V_BS5 = 1, V_CFMR = 2, V_CKDISC = 3, V_NYSTROM = 4 };
 enum { ST_FINISHED = 0, ST_EVENT = 2, ST_TOO_SMALL = -1, ST_OVERFLOW = -2, ST_BUDGET = -5 };
 /* ST_EVENT is internal (1 is "running" in the loops below); reported as status 1 */
 enum { IP_FREE = 1, IP_LOW = 2, IP_BEST = 3 };
@@ -84,6 +84,8 @@ typedef struct {
     /* CKdisc only (cash.py:184-236) */
     double B_assess[2][MAXS], E_assess[2][MAXS], B_fallback[2][MAXS], E_fallback[2][MAXS];
     double C_fallback[2], ck_max_factor, ck_min_factor, ck_safety;
+    /* Runge-Kutta-Nystrom methods only (common.py:1207-1309): A', B', E' */
+    double Ap[MAXS][MAXS], Bp[MAXS], Ep[MAXS + 1];
 } otab_t;
 
 typedef void (*rhs_fn)(double t, const double* y, const double* p, double* dy);
@@ -315,8 +317,37 @@ static double wsum(lane_t* L, const double* w, int m, int c) {
     return acc;
 }
 
+/* RungeKuttaNystrom._rk_stage, common.py:1279-1285 (xsq_rk_core.cuh Lane::stage):
+ * slots [0, n/2) are positions, [n/2, n) their velocities; rows of K are whole
+ * derivative vectors of which only the acceleration half is read */
+static void rkn_stage(lane_t* L, double h, int i) {
+    const int nh = L->n / 2;
+    const otab_t* T = L->T;
+    double ys[MAXN];
+    const double dt = T->C[i] * h, hh = h * h;
+    for (int c = 0; c < nh; ++c) {
+        double au = 0.0, av = 0.0;
+        int fu = 1, fv = 1;
+        for (int j = 0; j < i; ++j) {
+            if (T->A[i][j] != 0.0) {
+                au = fu ? T->A[i][j] * L->K[j][nh + c] : fma(T->A[i][j], L->K[j][nh + c], au);
+                fu = 0;
+            }
+            if (T->Ap[i][j] != 0.0) {
+                av = fv ? T->Ap[i][j] * L->K[j][nh + c] : fma(T->Ap[i][j], L->K[j][nh + c], av);
+                fv = 0;
+            }
+        }
+        ys[c] = L->y[c] + (au * hh + dt * L->y[nh + c]);
+        ys[nh + c] = L->y[nh + c] + av * h;
+    }
+    L->f(L->t + dt, ys, L->prm, L->K[i]);
+    L->nfev++;
+}
+
 /* common.py:353-356 */
 static void rk_stage(lane_t* L, double h, int i) {
+    if (L->T->variant == V_NYSTROM) { rkn_stage(L, h, i); return; }
     double ys[MAXN];
     for (int c = 0; c < L->n; ++c) ys[c] = fma(h, wsum_first(L, L->T->A[i], i, c), L->y[c]);
     L->f(L->t + L->T->C[i] * h, ys, L->prm, L->K[i]);
@@ -1001,8 +1032,8 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     if (L->ev)
         for (int k = 0; k < L->ev->n_events; ++k) L->ev->g_old[k] = L->ev->g(k, t0, L->y, prm);
     int ieval = 0, st = 1, attempts = 0;
-    const int early = T->variant != V_GENERIC;
-    const int fsal = T->E[s] != 0.0;
+    const int early = T->variant == V_BS5 || T->variant == V_CFMR;
+    const int fsal = T->E[s] != 0.0 || (T->variant == V_NYSTROM && T->Ep[s] != 0.0);
     if (!forced && t0 == tf) { /* scipy base.py:195-200 */
         for (int i = 0; i < n_eval; ++i)
             for (int c = 0; c < n; ++c) y_eval[(size_t)c * n_eval + i] = L->y[c];
@@ -1044,7 +1075,21 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
                     pre_reject = !forced && ss > NTOT &&
                         (ss >= NTOT * (1.0 + 0x1.0p-48) || sqrt(ss / NTOT) > 1.0);
                 }
-                if (!pre_reject) {
+                if (!pre_reject && T->variant == V_NYSTROM) {
+                    /* RungeKuttaNystrom._comp_sol_err / _estimate_error, common.py:1287-1309 */
+                    const int nh = n / 2;
+                    const double hh = h * h;
+                    for (int c = 0; c < nh; ++c) {
+                        y_new[c] = L->y[c] + (wsum(L, T->B, s, nh + c) * hh + h * L->y[nh + c]);
+                        y_new[nh + c] = L->y[nh + c] + wsum(L, T->Bp, s, nh + c) * h;
+                    }
+                    if (fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
+                    for (int c = 0; c < nh; ++c) {
+                        errv[c] = wsum(L, T->E, s + fsal, nh + c) * hh;
+                        errv[nh + c] = wsum(L, T->Ep, s + fsal, nh + c) * h;
+                    }
+                    ss = scaled_ss_dev(L, errv, y_new);
+                } else if (!pre_reject) {
                     if (early) rk_stage(L, h, s - 1);
                     for (int c = 0; c < n; ++c) y_new[c] = fma(h, wsum(L, T->B, s, c), L->y[c]);
                     if (fsal) { f(t_new, y_new, prm, L->K[s]); L->nfev++; }
@@ -1187,6 +1232,9 @@ int xsq_oracle_rk_batch(const otab_t* T, int rhs, rhs_fn user_f, int n, int p,
                         int n_threads, int nfev_stiff_detect, int32_t* stiff_flags) {
     rhs_fn f = rhs >= 0 ? builtin_rhs(rhs) : user_f;
     if (!f || n > MAXN || T->s >= MAXS) return -1;
+    /* the Nystrom methods are restated in device arithmetic only (the reference's
+     * arithmetic: oracle/rk_oracle.py, bit-identical to the reference) */
+    if (T->variant == V_NYSTROM && (!g_device_math || (n & 1))) return -1;
     if (max_steps <= 0) max_steps = 2147483647;
     if (rhs < 0) n_threads = 1;
 #ifdef _OPENMP

@@ -159,3 +159,52 @@ def test_rkn_argument_checks():
     with pytest.raises(ValueError):                  # no dense output on the device
         xb.solve_ivp_batched("vanderpol", (0.0, 1.0), [[2.0, 0.0]], xb.Fi5N, params=[[1.0]],
                              t_eval=[0.0, 0.5, 1.0])
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+@pytest.mark.parametrize("m", METHODS, ids=lambda m: m.__name__)
+def test_rkn_bit_identical_to_oracle_in_device_arithmetic(m):
+    """The Nystrom variant of rk_persistent against the C oracle's restatement in
+    the kernels' arithmetic (oracle/xsq_oracle.c rkn_stage and the Nystrom
+    solution / error block; that restatement takes the same steps as the NumPy
+    one, which is bit-identical to the reference): accepted / rejected / nfev
+    counts, final time and state, next step size -- bit for bit on every lane.
+    Fi4N, Fi5N, Mu5Nmb on the built-in Van der Pol sweep and the perturbed
+    Arenstorf orbits; MR6NN (velocity independent problems only) on Kepler orbits
+    through a user right-hand side, a Python callback playing it in the oracle."""
+    from oracle import c_oracle as CO
+    from test_gpu_rk import vdp_lanes, arenstorf_lanes
+    tab = TABS[m.__name__]
+    threads = max(1, len(os.sched_getaffinity(0)))
+    cases = []
+    if m.velocity_dependent:
+        y0, prm = vdp_lanes(512)
+        keep = prm[:, 0] <= 30.0                       # explicit method: leave the stiff end out
+        cases.append(("vanderpol", (0.0, 20.0), y0[keep], prm[keep], None))
+        y0, prm = arenstorf_lanes(512)
+        cases.append(("arenstorf", (0.0, 17.0652165601579625588917206249), y0, prm, None))
+    else:
+        ecc = np.linspace(0.05, 0.7, 48)
+        y0 = np.stack([1.0 - ecc, 0 * ecc, 0 * ecc, np.sqrt((1.0 + ecc) / (1.0 - ecc))], 1)
+        cases.append(("kepler", (0.0, 12.0), y0, np.zeros((len(ecc), 1)), make_fun("kepler", [0.0])))
+    for prob, span, y0, prm, pyfun in cases:
+        for kw in (dict(rtol=1e-8, atol=1e-10), dict(rtol=1e-5, atol=1e-7)):
+            r = xb.solve_ivp_batched(rhs_for(prob), span, y0, m, params=prm, max_steps=1000000, **kw)
+            torch.cuda.synchronize()
+            with CO.device_math():
+                if pyfun is None:
+                    o = CO.rk_batch(tab, prob, span, y0, params=prm, n_threads=threads,
+                                    nfev_stiff_detect=0, **kw)
+                else:
+                    o = CO.rk_batch(tab, None, span, y0, user_fn=pyfun, nfev_stiff_detect=0, **kw)
+            assert int(r.n_accepted.min()) > 10 and int(r.n_rejected.sum()) > 0
+            for k in ("n_accepted", "n_rejected", "nfev", "status"):
+                g = getattr(r, k).cpu().numpy()
+                bad = np.flatnonzero(g != o[k])
+                assert bad.size == 0, (m.__name__, prob, kw, k, bad[:5], g[bad[:5]], o[k][bad[:5]])
+            for k in ("t_final", "y_final", "h_next"):
+                g = getattr(r, k).cpu().numpy()
+                assert np.array_equal(_bits(g), _bits(o[k])), (m.__name__, prob, kw, k)
