@@ -59,3 +59,33 @@ def test_wrong_problems_are_refused():
         O.rk_solve(TABS["Fi4N"], lambda t, y: np.array([-y[0], y[1]]), (0, 1), [0.5, 1.])
     with pytest.raises(AssertionError):                # velocity dependent with MR6NN
         O.rk_solve(TABS["MR6NN"], lambda t, y: np.array([y[1], -y[0] - y[1]]), (0, 1), [0., 1.])
+
+
+def test_c_restatement_in_device_arithmetic_against_the_reference_goldens():
+    """rkn_stage and the Nystrom solution / error block of oracle/xsq_oracle.c (the
+    kernels' arithmetic; the GPU is bit-identical to it, tests/test_gpu_rkn.py)
+    against the reference's golden runs: status identical, and on every case where
+    the other arithmetic takes the same number of steps the final state agrees to
+    a multiple of the tolerance.  The fraction is printed and asserted."""
+    from oracle import c_oracle as CO
+    same = total = 0
+    for c in CASES:
+        if c["n_t"] > 5000 or c["problem"] == "nbody32":
+            continue                    # long stiff runs / the 192-state callback: CPU time
+        opt = dict(c["options"])
+        opt.pop("nfev_stiff_detect", None)
+        fun = make_fun(c["problem"], c["params"])
+        with CO.device_math():
+            o = CO.rk_batch(TABS[c["method"]], None, c["t_span"], [unhex(c["y0"])], user_fn=fun,
+                            nfev_stiff_detect=0, **opt)
+        assert int(o["status"][0]) == c["status"], c["id"]
+        total += 1
+        # the golden nfev may include the (host-only) stiffness probes: compare steps
+        t, y = unhex(c["t"]), unhex(c["y"])
+        if int(o["n_accepted"][0]) == c["n_t"] - 1:
+            same += 1
+            tol = 100 * (opt.get("atol", 1e-6) + opt.get("rtol", 1e-3) * np.abs(y[:, -1]))
+            assert (np.abs(o["y_final"][0] - y[:, -1]) <= tol).all(), c["id"]
+    print(f"\nC restatement of the Nystrom methods: same number of steps as the reference on "
+          f"{same} of {total} golden cases")
+    assert same >= 0.8 * total
