@@ -380,6 +380,62 @@ def swag_batch(rhs, t_span, y0, params=None, rtol=1e-3, atol=1e-6,
                 n_eval_done=n_done, k_final=k_final)
 
 
+def swag_events_batch(rhs, t_span, y0, events, terminal, direction, capacity, params=None,
+                      rtol=1e-3, atol=1e-6, first_step=None, max_step=np.inf, k_max=12,
+                      t_eval=None, max_steps=0, n_threads=1):
+    """swag_batch with scipy's `events=` on SWAG's interpolant, in the kernels'
+    arithmetic (xsq_oracle_swag.c; call inside ``with device_math():``).  `events`:
+    the name of a built-in set (EVENT_SETS) or a list of callables g(t, y)."""
+    lib = load()
+    y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, dtype=float)))
+    N, n = y0.shape
+    rtol_v, atol_v = O.validate_tol(float(rtol), atol, y0[0])
+    atol_v = np.ascontiguousarray(np.broadcast_to(atol_v, (n,)), dtype=float)
+    if params is not None:
+        params = np.ascontiguousarray(np.asarray(params, dtype=float))
+        if params.ndim == 1:
+            params = params.reshape(N, -1)
+        p = params.shape[1]
+    else:
+        p = 0
+    te = (np.ascontiguousarray(np.asarray(t_eval, dtype=float)) if t_eval is not None else None)
+    n_eval = te.size if te is not None else 0
+    y_eval = np.empty((N, n, n_eval)) if n_eval else None
+    t_final, y_final = np.empty(N), np.empty((N, n))
+    ints = [np.empty(N, np.int32) for _ in range(6)]
+    n_acc, n_fail, nfev, status, n_done, k_final = ints
+    if isinstance(events, str):
+        ev_set, ne = EVENT_SETS[events]
+        gcb = EVENT_FN()
+    else:
+        ev_set, ne = -1, len(events)
+
+        def _g(k, tt, yp, pp):
+            return float(events[k](tt, np.ctypeslib.as_array(yp, (n,))))
+        gcb = EVENT_FN(_g)
+    term = np.ascontiguousarray(np.asarray(terminal, dtype=np.int32))
+    direc = np.ascontiguousarray(np.asarray(direction, dtype=np.int32))
+    t_ev = np.full((N, ne, capacity), np.nan)
+    y_ev = np.full((N, ne, capacity, n), np.nan)
+    ev_cnt = np.zeros((N, ne), np.int32)
+    rc = lib.xsq_oracle_swag_events_batch(
+        C.c_int(RHS_IDS[rhs]), RHS_FN(), C.c_int(n), C.c_int(p), C.c_int64(N), _dp(y0),
+        _dp(params), C.c_double(t_span[0]), C.c_double(t_span[1]),
+        C.c_double(float(rtol_v)), _dp(atol_v),
+        C.c_double(first_step if first_step is not None else 0.0),
+        C.c_double(max_step), C.c_int(k_max), _dp(te), C.c_int(n_eval),
+        _dp(y_eval), C.c_int(max_steps), _dp(t_final), _dp(y_final),
+        _ip(n_acc), _ip(n_fail), _ip(nfev), _ip(status), _ip(n_done),
+        _ip(k_final), C.c_int(n_threads), C.c_int(ev_set), gcb, C.c_int(ne), _ip(term),
+        _ip(direc), C.c_int(capacity), _dp(t_ev), _dp(y_ev), _ip(ev_cnt))
+    if rc != 0:
+        raise RuntimeError("xsq_oracle_swag_events_batch failed (device arithmetic only)")
+    return dict(t=te, y=y_eval, t_final=t_final, y_final=y_final,
+                n_accepted=n_acc, n_rejected=n_fail, nfev=nfev, status=status,
+                n_eval_done=n_done, k_final=k_final, t_events=t_ev, y_events=y_ev,
+                event_counts=ev_cnt)
+
+
 VEC_RHS_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double),
                          C.POINTER(C.c_double), C.c_int64, C.c_void_p)
 

@@ -551,6 +551,7 @@ typedef struct ev_ctx_s {
     double g_old[MAXEV];
 } ev_ctx_t;
 
+event_fn xsq_oracle_builtin_events(int id);
 static double ev_lorenz_sections(int k, double t, const double* y, const double* p) {
     (void)t; (void)p;
     if (k == 0) return y[2] - 27.0;
@@ -558,20 +559,25 @@ static double ev_lorenz_sections(int k, double t, const double* y, const double*
     return y[0] * y[1] - 30.0;
 }
 
+event_fn xsq_oracle_builtin_events(int id) { return id == 0 ? ev_lorenz_sections : 0; }
+
 typedef struct {
     lane_t* L; const dense_t* D; const ev_ctx_t* E; const double* y_new; double t_new; int k;
 } ev_root_ctx;
-static double ev_of_t(const ev_root_ctx* c, double tt) {
+static double ev_of_t(const void* vc, double tt) {
+    const ev_root_ctx* c = (const ev_root_ctx*)vc;
     double ytmp[MAXN];
     dense_eval(c->L, c->D, c->t_new, c->y_new, tt, ytmp, 1);
     return c->E->g(c->k, tt, ytmp, c->L->prm);
 }
-static double brentq_c(const ev_root_ctx* c, double xa, double xb) {
+/* scipy.optimize.brentq(xtol = rtol = 4 eps) as the kernels evaluate it (brentq_dev);
+ * shared with the SWAG restatement */
+double xsq_oracle_brentq(double (*fn)(const void*, double), const void* c, double xa, double xb) {
     const double tol = 4.0 * 0x1.0p-52;
     double xpre = xa, xcur = xb;
     double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
-    double fpre = ev_of_t(c, xpre);
-    double fcur = ev_of_t(c, xcur);
+    double fpre = fn(c, xpre);
+    double fcur = fn(c, xcur);
     if (fpre == 0.0) return xpre;
     if (fcur == 0.0) return xcur;
     if ((signbit(fpre) != 0) == (signbit(fcur) != 0)) return xcur;
@@ -613,7 +619,7 @@ static double brentq_c(const ev_root_ctx* c, double xa, double xb) {
         fpre = fcur;
         if (fabs(scur) > delta) xcur += scur;
         else xcur += (sbis > 0 ? delta : -delta);
-        fcur = ev_of_t(c, xcur);
+        fcur = fn(c, xcur);
     }
     return xcur;
 }
@@ -644,7 +650,7 @@ static int events_after_step(lane_t* L, double h, double* t_new, double* y_new,
         for (int k = 0; k < E->n_events; ++k) {
             if (!(active >> k & 1u)) continue;
             ev_root_ctx c = {L, &D, E, y_new, *t_new, k};
-            root[k] = brentq_c(&c, L->t, *t_new);
+            root[k] = xsq_oracle_brentq(ev_of_t, &c, L->t, *t_new);
         }
         for (int k = 0; k < E->n_events; ++k) {
             if (!(active >> k & 1u)) continue;

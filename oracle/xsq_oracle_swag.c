@@ -37,7 +37,24 @@ double xsq_oracle_h_start(rhs_fn f, const double* prm, int n, double a, double b
                           const double* y, const double* yprime, int morder,
                           double rtol, const double* atol, int* nfev);
 
-enum { ST_RUNNING = 1, ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_TOL = -3, ST_BUDGET = -5 };
+enum { ST_RUNNING = 1, ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_TOL = -3, ST_BUDGET = -5,
+       ST_EVENT = 2 /* internal; reported as status 1 */ };
+
+/* scipy's `events=` on SWAG's interpolant (xsq_swag_core.cuh SwagLane::finish_step),
+ * device arithmetic; brentq and the built-in event sets are shared with xsq_oracle.c */
+typedef double (*event_fn)(int k, double t, const double* y, const double* p);
+double xsq_oracle_brentq(double (*fn)(const void*, double), const void* c, double xa, double xb);
+event_fn xsq_oracle_builtin_events(int id);
+#define MAXEV 8
+typedef struct {
+    event_fn g;
+    int n_events, capacity;
+    int terminal[MAXEV], direction[MAXEV];
+    double* t_events;   /* [n_events][capacity] */
+    double* y_events;   /* [n_events][capacity][n] */
+    int32_t* counts;    /* [n_events] */
+    double g_old[MAXEV];
+} swag_ev_t;
 
 static const double TWO[13] = {2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0,
                                1024.0, 2048.0, 4096.0, 8192.0};
@@ -343,6 +360,10 @@ static void swag_interp(const swag_t* S, double ox, double xout, double* yout) {
     }
 }
 
+typedef struct { const void* S; const swag_ev_t* E; double t_old; int k; } swag_root_ctx;
+static double swag_ev_of_t(const void* vc, double tt);
+static _Thread_local swag_ev_t* g_swag_ev = 0;   /* set per lane by xsq_oracle_swag_events_batch */
+
 static void swag_solve_one(rhs_fn f, int n, const double* y0, const double* prm, double t0,
                            double tf, double rtol, const double* atol, double first_step,
                            double max_step, int k_max, const double* t_eval, int n_eval,
@@ -354,6 +375,9 @@ static void swag_solve_one(rhs_fn f, int n, const double* y0, const double* prm,
     S->rtol = rtol; S->atol = atol; S->t_bound = tf; S->max_step = max_step;
     S->direction = (tf != t0) ? (tf > t0 ? 1.0 : -1.0) : 1.0;
     swag_init(S, t0, y0, first_step);
+    swag_ev_t* E = g_swag_ev;
+    if (E)
+        for (int k = 0; k < E->n_events; ++k) E->g_old[k] = E->g(k, t0, S->y, prm);
     int st = ST_RUNNING, ieval = 0;
     double yout[MAXN];
     if (t0 == tf) { /* scipy base.py:195-200 */
@@ -366,18 +390,64 @@ static void swag_solve_one(rhs_fn f, int n, const double* y0, const double* prm,
         const double t_old = S->t;
         st = swag_step(S, max_steps);
         if (st != ST_RUNNING) break;
-        while (ieval < n_eval && S->direction * (t_eval[ieval] - S->t) <= 0.0) {
+        double t_stop = S->t;
+        int terminate = 0;
+        if (E) { /* find_active_events / handle_events, ivp.py */
+            double g_new[MAXEV], root[MAXEV];
+            unsigned active = 0;
+            for (int k = 0; k < E->n_events; ++k) {
+                g_new[k] = E->g(k, S->t, S->y, prm);
+                const int up = E->g_old[k] <= 0.0 && g_new[k] >= 0.0;
+                const int down = E->g_old[k] >= 0.0 && g_new[k] <= 0.0;
+                const int d = E->direction[k];
+                if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) active |= 1u << k;
+            }
+            if (active) {
+                for (int k = 0; k < E->n_events; ++k) {
+                    if (!(active >> k & 1u)) continue;
+                    swag_root_ctx c = {S, E, t_old, k};
+                    root[k] = xsq_oracle_brentq(swag_ev_of_t, &c, t_old, S->t);
+                }
+                double r_star = 0.0;
+                for (int k = 0; k < E->n_events; ++k) {
+                    if (!(active >> k & 1u)) continue;
+                    ++E->counts[k];
+                    if (E->terminal[k] > 0 && E->counts[k] >= E->terminal[k]) {
+                        if (!terminate || S->direction * (root[k] - r_star) < 0.0) r_star = root[k];
+                        terminate = 1;
+                    }
+                }
+                if (terminate) t_stop = r_star;
+                for (int k = 0; k < E->n_events; ++k) {
+                    if (!(active >> k & 1u)) continue;
+                    if (terminate && S->direction * (root[k] - r_star) > 0.0) continue;
+                    const int slot = E->counts[k] - 1;
+                    if (slot < E->capacity) {
+                        const size_t base = (size_t)k * E->capacity + slot;
+                        E->t_events[base] = root[k];
+                        swag_interp(S, t_old, root[k], E->y_events + base * n);
+                    }
+                }
+            }
+            for (int k = 0; k < E->n_events; ++k) E->g_old[k] = g_new[k];
+        }
+        while (ieval < n_eval && S->direction * (t_eval[ieval] - t_stop) <= 0.0) {
             swag_interp(S, t_old, t_eval[ieval], yout);
             for (int c = 0; c < n; ++c) y_eval[(size_t)c * n_eval + ieval] = yout[c];
             ++ieval;
         }
-        if (S->direction * (S->t - tf) >= 0.0) st = ST_FINISHED;
+        if (terminate) { /* t, y = the event point */
+            swag_interp(S, t_old, t_stop, yout);
+            memcpy(S->y, yout, sizeof(double) * n);
+            S->t = t_stop;
+            st = ST_EVENT;
+        } else if (S->direction * (S->t - tf) >= 0.0) st = ST_FINISHED;
     }
     for (int i = ieval; i < n_eval; ++i)
         for (int c = 0; c < n; ++c) y_eval[(size_t)c * n_eval + i] = NAN;
     *t_final = S->t;
     memcpy(y_final, S->y, sizeof(double) * n);
-    *n_acc = S->n_acc; *n_fail = S->n_fail; *nfev = S->nfev; *status = st;
+    *n_acc = S->n_acc; *n_fail = S->n_fail; *nfev = S->nfev; *status = st == ST_EVENT ? 1 : st;
     if (n_eval_done) *n_eval_done = ieval;
     if (k_final) *k_final = S->k;
     free(S);
@@ -404,5 +474,56 @@ int xsq_oracle_swag_batch(int rhs, rhs_fn user_f, int n, int p, int64_t n_lanes,
                        y_eval ? y_eval + (size_t)i * n * n_eval : 0, max_steps, t_final + i,
                        y_final + i * n, n_acc + i, n_fail + i, nfev + i, status + i,
                        n_eval_done ? n_eval_done + i : 0, k_final ? k_final + i : 0);
+    return 0;
+}
+
+static double swag_ev_of_t(const void* vc, double tt) {
+    const swag_root_ctx* c = (const swag_root_ctx*)vc;
+    const swag_t* S = (const swag_t*)c->S;
+    double ytmp[MAXN];
+    swag_interp(S, c->t_old, tt, ytmp);
+    return c->E->g(c->k, tt, ytmp, S->prm);
+}
+
+/* xsq_oracle_swag_batch with scipy's `events=` (device arithmetic).  ev_set 0: the
+ * Lorenz section functions; < 0: `user_g` (single thread).  Output layout as
+ * xsq_oracle_rk_events_batch. */
+int xsq_oracle_swag_events_batch(int rhs, rhs_fn user_f, int n, int p, int64_t n_lanes,
+                                 const double* y0, const double* params, double t0, double tf,
+                                 double rtol, const double* atol, double first_step,
+                                 double max_step, int k_max, const double* t_eval, int n_eval,
+                                 double* y_eval, int max_steps, double* t_final, double* y_final,
+                                 int32_t* n_acc, int32_t* n_fail, int32_t* nfev, int32_t* status,
+                                 int32_t* n_eval_done, int32_t* k_final, int n_threads,
+                                 int ev_set, event_fn user_g, int n_events,
+                                 const int32_t* terminal, const int32_t* direction, int capacity,
+                                 double* t_events, double* y_events, int32_t* ev_count) {
+    rhs_fn f = rhs >= 0 ? xsq_oracle_builtin_rhs(rhs) : user_f;
+    event_fn g = ev_set >= 0 ? xsq_oracle_builtin_events(ev_set) : user_g;
+    if (!f || !g || n > MAXN || k_max < 1 || k_max > KMAX || n_events < 1 || n_events > MAXEV ||
+        capacity < 1 || !xsq_oracle_device_math())
+        return -1;
+    if (max_steps <= 0) max_steps = 2147483647;
+    if (rhs < 0 || ev_set < 0) n_threads = 1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n_lanes; ++i) {
+        swag_ev_t E;
+        E.g = g; E.n_events = n_events; E.capacity = capacity;
+        for (int k = 0; k < n_events; ++k) { E.terminal[k] = terminal[k]; E.direction[k] = direction[k]; }
+        E.t_events = t_events + (size_t)i * n_events * capacity;
+        E.y_events = y_events + (size_t)i * n_events * capacity * n;
+        E.counts = ev_count + (size_t)i * n_events;
+        for (int k = 0; k < n_events; ++k) E.counts[k] = 0;
+        g_swag_ev = &E;
+        swag_solve_one(f, n, y0 + i * n, params ? params + i * p : 0, t0, tf, rtol, atol,
+                       first_step, max_step, k_max, t_eval, n_eval,
+                       y_eval ? y_eval + (size_t)i * n * n_eval : 0, max_steps, t_final + i,
+                       y_final + i * n, n_acc + i, n_fail + i, nfev + i, status + i,
+                       n_eval_done ? n_eval_done + i : 0, k_final ? k_final + i : 0);
+        g_swag_ev = 0;
+    }
     return 0;
 }

@@ -45,10 +45,8 @@ double xsq_host_rcp64h(double x) {
 }  // namespace xsq
 
 #include "xsq_rk_fast.cuh"
-#ifndef XSQ_EMU_EVENTS
 #include "xsq_swag_core.cuh"
 #include "xsq_swag_fast.cuh"
-#endif
 #include "xsq_rhs.cuh"
 #include "xsq_user.h"
 
@@ -209,7 +207,6 @@ extern "C" int xsq_emu_rk_solve(const xsq_rk_args_t* a, int want_fast, long long
     }
 }
 
-#ifndef XSQ_EMU_EVENTS
 template <class R>
 static int run_swag(RkDev P) {
     const long long N = P.n_lanes;
@@ -265,4 +262,3 @@ extern "C" int xsq_emu_swag_solve(const xsq_rk_args_t* args, int k_max) {
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }
-#endif  // XSQ_EMU_EVENTS

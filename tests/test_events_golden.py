@@ -187,3 +187,29 @@ def test_c_oracle_events_in_device_arithmetic_against_the_reference(c):
         assert n_done == (yg.shape[1] if yg.ndim == 2 else 0)
         if n_done:
             assert np.allclose(o["y"][0][:, :n_done], yg, rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["method"] == "SWAG"], ids=lambda c: c["id"])
+def test_c_swag_oracle_events_against_the_reference(c):
+    """The same for SWAG (oracle/xsq_oracle_swag.c with events, device arithmetic)
+    against the reference's golden runs of SWAG driven by scipy's event loop."""
+    from oracle import c_oracle as CO
+    if c["problem"] not in CO.RHS_IDS:
+        pytest.skip("the SWAG C oracle takes built-in right-hand sides")
+    opts = ev_options(c)
+    fns, _ = EVENT_SETS[c["events"]]
+    te = ev_t_eval(c)
+    with CO.device_math():
+        o = CO.swag_events_batch(c["problem"], c["t_span"], [c["y0"]], list(fns), c["terminal"],
+                                 c["direction"], 64, params=[c["params"]] if c["params"] else None,
+                                 t_eval=te, **opts)
+    assert int(o["status"][0]) == c["status"]
+    if int(o["nfev"][0]) != c["nfev"]:
+        pytest.skip("the kernels' arithmetic takes a different step sequence on this case")
+    for k in range(len(c["terminal"])):
+        tg = unhex(c["t_events"][k])
+        assert int(o["event_counts"][0, k]) >= tg.size
+        assert np.allclose(o["t_events"][0, k, :tg.size], tg, rtol=1e-9, atol=1e-9)
+        if tg.size:
+            ye = unhex(c["y_events"][k]).reshape(tg.size, -1)
+            assert np.allclose(o["y_events"][0, k, :tg.size], ye, rtol=1e-7, atol=1e-7)

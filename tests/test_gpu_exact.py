@@ -203,6 +203,33 @@ def test_events_bit_identical_to_oracle_in_device_arithmetic(m):
             assert same.all(), (m.__name__, term, sorted(kw), k, np.argwhere(~same)[:4])
 
 
+def test_swag_events_bit_identical_to_oracle_in_device_arithmetic():
+    """SWAG with events (roots on SwagDenseOutput inside the lane) against
+    oracle/xsq_oracle_swag.c with events in device arithmetic: bit for bit."""
+    from oracle.problems import EVENT_SETS
+    _, src = EVENT_SETS["lorenz_sections"]
+    ev0 = xb.DeviceEvents.from_source(src, "event", 3)
+    y0, prm = lorenz_lanes(512, seed=33)
+    te = np.linspace(0.0, 6.0, 61)
+    for term, kw in (([0, 0, 0], {}), ([0, 3, 0], {}), ([3, 0, 0], dict(t_eval=te))):
+        direc = [1, 0, -1]
+        base = dict(rtol=1e-7, atol=1e-9, **kw)
+        res = xb.solve_ivp_batched("lorenz63", (0.0, 6.0), y0, xb.SWAG, params=prm,
+                                   events=ev0.with_attributes(terminal=term, direction=direc),
+                                   max_event_records=16, **base)
+        torch.cuda.synchronize()
+        with CO.device_math():
+            o = CO.swag_events_batch("lorenz63", (0.0, 6.0), y0, "lorenz_sections", term, direc, 16,
+                                     params=prm, n_threads=THREADS, **base)
+        if any(term):
+            assert (o["status"] == 1).sum() > len(y0) // 4
+        for k in ("n_accepted", "n_rejected", "nfev", "status", "event_counts", "t_final", "y_final",
+                  "t_events", "y_events") + (("y",) if "t_eval" in kw else ()):
+            a, b = getattr(res, k).cpu().numpy(), o[k]
+            same = (a == b) | ((a != a) & (b != b))
+            assert same.all(), ("SWAG", term, sorted(kw), k, np.argwhere(~same)[:4])
+
+
 # ---- C4: the perturbed Arenstorf ensemble of bench.py ----------------------------
 def test_c4_collision_orbits():
     """The first 16 384 lanes of bench.py's C4 ensemble (Arenstorf initial state

@@ -290,3 +290,26 @@ def test_event_kernel_sources_against_the_numpy_restatement():
                 assert np.allclose(g["y_events"][i, k, :tg.size], o["y_events"][k], rtol=1e-7, atol=1e-7)
         assert abs(g["t_final"][i] - o["t_final"]) <= 1e-9
     assert checked >= 8 and (g["status"] == 1).any()
+
+
+def test_swag_event_kernel_source_equals_the_c_oracle_with_events():
+    """SwagLane::finish_step (events on SWAG's interpolant, xsq_swag_core.cuh built
+    with XSQ_EVENTS_N) against the C restatement (oracle/xsq_oracle_swag.c): event
+    times and states, counts, terminal stops, t_eval output, trajectory -- bit
+    for bit."""
+    y0, prm = _lorenz_event_lanes(72)
+    te = np.linspace(0.0, 5.0, 41)
+    for term, kw in (([0, 0, 0], {}), ([0, 2, 0], {}), ([2, 0, 3], dict(k_max=5)),
+                     ([0, 0, 0], dict(t_eval=te)), ([3, 0, 0], dict(t_eval=te))):
+        base = dict(rtol=1e-7, atol=1e-9, **kw)
+        a = emu.solve("lorenz63", (0.0, 5.0), y0, xb.SWAG, prm, events=(term, [1, 0, -1]),
+                      max_event_records=12, **base)
+        with CO.device_math():
+            o = CO.swag_events_batch("lorenz63", (0.0, 5.0), y0, "lorenz_sections", term, [1, 0, -1],
+                                     12, params=prm, n_threads=CO.max_threads(), **base)
+        assert o["event_counts"].sum() > 2 * len(y0)
+        if any(term):
+            assert (o["status"] == 1).sum() > len(y0) // 4
+        keys = ("t_events", "y_events", "event_counts", "y_final", "t_final", "nfev", "n_accepted",
+                "n_rejected", "status") + (("y",) if "t_eval" in kw else ())
+        _same_events(a, o, ("SWAG", term, sorted(kw)), keys)
