@@ -161,6 +161,41 @@ def test_ckdisc_nonsmooth_ensemble_bit_identical_and_cost_of_arithmetic():
     assert abs(g["nfev"].mean() / r["nfev"].mean() - 1) < 0.05
 
 
+# ---- user tableau + user right-hand side ---------------------------------------------
+def test_user_tableau_and_user_rhs_bit_identical_to_oracle():
+    """docs/Demo_own_RK.ipynb: a user RungeKutta subclass (Heun-Euler pair, no P:
+    cubic Hermite dense output) on a user right-hand side -- both compiled at run
+    time -- against the C oracle in device arithmetic with the same tableau."""
+    from oracle.problems import CUDA_SOURCES, mass_spring_damper
+
+    class Heun(xb.RungeKutta):
+        n_stages = 2
+        order = 2
+        order_secondary = 1
+        C = np.array([0, 1.])
+        A = np.array([[0, 0], [1., 0]])
+        B = np.array([1 / 2, 1 / 2])
+        E = np.array([1., 0, 0])
+        E[:-1] -= B
+
+    class HeunTab:
+        name = "Heun"
+        n_stages, order, order_secondary = 2, 2, 1
+        A, B, C, E = Heun.A, Heun.B, Heun.C, Heun.E
+        P = None
+        sc_params = "standard"
+    n, p, src = CUDA_SOURCES["mass_spring_damper"]
+    msd = xb.DeviceRHS.from_source(src, "rhs", n, p)
+    rng = np.random.default_rng(8)
+    y0 = np.stack([rng.uniform(-1, 1, 64), rng.uniform(-2, 0, 64)], 1)
+    te = np.linspace(0, 16, 33)
+    for kw in (dict(atol=0.05), dict(rtol=1e-5, atol=1e-7), dict(rtol=1e-4, atol=1e-6, t_eval=te)):
+        g = gpu(msd, (0.0, 16.0), y0, Heun, None, **kw)
+        with CO.device_math():
+            o = CO.rk_batch(HeunTab, None, (0.0, 16.0), y0, user_fn=mass_spring_damper, **kw)
+        assert_identical(g, o, ("Heun", sorted(kw)), dense="t_eval" in kw)
+
+
 # ---- events ------------------------------------------------------------------------
 @pytest.mark.parametrize("m", [xb.Ts5, xb.BS5, xb.Pr8, xb.CKdisc], ids=lambda m: m.__name__)
 def test_events_bit_identical_to_oracle_in_device_arithmetic(m):

@@ -130,3 +130,52 @@ def test_sens_forward_beyond_16_states_runs_a_warp_per_system():
         np.testing.assert_allclose(sens[i].cpu().numpy(), so, rtol=1e-5, atol=1e-8)
     # first compartment: y0(t) = exp(-p0 t), dy0/dp0 = -t exp(-p0 t)
     np.testing.assert_allclose(sens[:, 0, 0].cpu().numpy(), -3.0 * np.exp(-3.0 * P[:, 0]), rtol=1e-6)
+
+
+def test_sens_forward_combined_system_bit_identical_to_oracle():
+    """The combined system [y, |p| S] that sens_forward generates and compiles
+    (sensitivity.py:60-217: S' = J S + df/dp) against the C oracle in device
+    arithmetic integrating the same system through a Python mirror of the
+    generated right-hand side (same operations in the same order, libm's fma):
+    counts, final combined state, next step -- bit for bit on every lane."""
+    import ctypes
+    import ctypes.util
+    from oracle import c_oracle as CO
+    from oracle import rk_oracle as O
+    libm = ctypes.CDLL(ctypes.util.find_library("m"))
+    libm.fma.restype = ctypes.c_double
+    libm.fma.argtypes = [ctypes.c_double] * 3
+    fma = libm.fma
+    N, ny, npar = 48, 2, 1
+    mu = np.linspace(0.5, 4.0, N)[:, None]
+    y0 = np.tile([2.0, 0.0], (N, 1))
+    src = SO.PROBLEMS["vanderpol"][3]
+
+    def combined(t, Y, p):                  # _combined_source(...) for Van der Pol
+        y0_, y1_, p0 = float(Y[0]), float(Y[1]), float(p[0])
+        J = [0.0, 1.0, -2 * p0 * y0_ * y1_ - 1, p0 * (1 - y0_ * y0_)]
+        D = [0.0, (1 - y0_ * y0_) * y1_]
+        fac = abs(p0) if p0 != 0.0 else 1.0
+        out = [y1_, p0 * (1 - y0_ * y0_) * y1_ - y0_]
+        for r in range(ny):
+            acc = 0.0
+            for k in range(ny):
+                acc = fma(J[r * ny + k], float(Y[ny + k]), acc)
+            out.append(fma(fac, D[r * npar], acc))
+        return np.array(out)
+
+    tabs = O.load_tableaux()
+    for m, kw in ((xb.Ts5, dict(rtol=1e-7, atol=1e-9)), (xb.Pr8, dict(rtol=1e-9, atol=1e-11))):
+        sens, yf, sol = xb.sens_forward(src, (0.0, 4.0), y0, np.zeros((ny, npar)), mu, method=m, **kw)
+        torch.cuda.synchronize()
+        total_y0 = np.concatenate([y0, np.zeros((N, ny * npar))], axis=1)
+        with CO.device_math():
+            o = CO.rk_batch(tabs[m.__name__], None, (0.0, 4.0), total_y0, params=mu, user_fn=combined,
+                            user_fn_params=True, **kw)
+        for k in ("n_accepted", "n_rejected", "nfev", "status"):
+            g = getattr(sol, k).cpu().numpy()
+            assert np.array_equal(g, o[k]), (m.__name__, k, np.flatnonzero(g != o[k])[:5])
+        for k in ("t_final", "y_final", "h_next"):
+            g = np.ascontiguousarray(getattr(sol, k).cpu().numpy())
+            assert np.array_equal(g.view(np.uint64), np.ascontiguousarray(o[k]).view(np.uint64)), \
+                (m.__name__, k)
