@@ -55,7 +55,7 @@ r, ms = timed(lambda: xb.solve_ivp_batched("lorenz63", (0., T), y0, xb.CKdisc, p
 print(json.dumps(dict(config="CKdisc", lanes=N, T=T, ms=ms, steps_per_s=int(r.n_accepted.sum()) / ms * 1e3)))
 ev = xb.DeviceEvents.from_source(EVENT_SRC, "event", 3, terminal=[0, 0, 0], direction=[1, 0, 0])
 r, ms = timed(lambda: xb.solve_ivp_batched("lorenz63", (0., T), y0, xb.Ts5, params=prm, events=ev,
-                                           max_event_records=64, **kw))
+                                           max_event_records=48, **kw))
 print(json.dumps(dict(config="Ts5 + 3 event functions (NVRTC kernel)", lanes=N, T=T, ms=ms,
                       steps_per_s=int(r.n_accepted.sum()) / ms * 1e3,
                       events_found=int(r.event_counts.sum()),
