@@ -512,6 +512,17 @@ def run_extras(xb, dev, peak_tf, which, y0_d, prm_d, args):
         rk_entry("C2_CK5", r, ms, xb.CK5, 3, 8)["workload"] = \
             f"CK5, {y0_d.shape[0]} Lorenz lanes, t in [0,{args.t_end:g}]"
         del r
+    if "c2ckdisc" in which:
+        # CKdisc (cash.py:115-416, the variable order Cash-Karp step) on the C2 lanes; the
+        # flop model is CK5's with all six stages (an upper bound: early exits take fewer)
+        try:
+            r, ms = timed_solve(torch, lambda: xb.solve_ivp_batched(
+                "lorenz63", (0.0, args.t_end), y0_d, xb.CKdisc, params=prm_d, rtol=RTOL, atol=ATOL), 1)
+            rk_entry("C2_CKdisc", r, ms, xb.CKdisc, 3, 8)["workload"] = \
+                f"CKdisc, {y0_d.shape[0]} Lorenz lanes, t in [0,{args.t_end:g}]"
+            del r
+        except Exception as exc:          # keep the other configurations
+            out["C2_CKdisc"] = {"error": repr(exc)}
     if "c3" in which:
         N = 1_000_000
         mu = 10.0 ** (-1 + 3 * np.arange(N) / (N - 1))
@@ -789,7 +800,7 @@ def main():
     max_ms, max_e2e_ms = stats.tolist()
     acc_all, rej_all = tot.tolist()
 
-    which = set(x for x in args.only.split(",") if x) or {"c2ck5", "c3", "c4a", "c4b", "c5", "events"}
+    which = set(x for x in args.only.split(",") if x) or {"c2ck5", "c2ckdisc", "c3", "c4a", "c4b", "c5", "events"}
     if args.no_extras:
         which = set()
     del flush
