@@ -109,6 +109,20 @@ static int run(RkDev P, const MethodInfo& mi, bool want_fast, int* used_fast) {
     return 0;
 }
 
+// Runge-Kutta-Nystrom methods: second order problems ([x, v] layouts) only
+template <class Tab>
+static int run_rkn(int rhs, const RkDev& P, const MethodInfo& mi, int* used) {
+    if constexpr (Tab::VELOCITY_DEPENDENT) {
+        switch (rhs) {
+            case XSQ_RHS_VANDERPOL: return run<Tab, rhs::VanDerPol>(P, mi, false, used);
+            case XSQ_RHS_ARENSTORF: return run<Tab, rhs::Arenstorf>(P, mi, false, used);
+            default: return XSQ_ERR_UNSUPPORTED;
+        }
+    } else {
+        return XSQ_ERR_UNSUPPORTED;     // MR6NN: no built-in velocity independent lane-per-system rhs
+    }
+}
+
 template <class Tab>
 static int run_rhs(int rhs, const RkDev& P, const MethodInfo& mi, bool fast, int* used) {
     switch (rhs) {
@@ -203,6 +217,12 @@ extern "C" int xsq_emu_rk_solve(const xsq_rk_args_t* a, int want_fast, long long
         case XSQ_PR9: return run_rhs<tab::Pr9>(a->rhs, P, mi, want_fast, used_fast);
         case XSQ_CFMR7OSC: return run_rhs<tab::CFMR7osc>(a->rhs, P, mi, want_fast, used_fast);
         case XSQ_CKDISC: return run_rhs<tab::CKdisc>(a->rhs, P, mi, want_fast, used_fast);
+#ifndef XSQ_EMU_EVENTS
+        case XSQ_FI4N: return run_rkn<tab::Fi4N>(a->rhs, P, mi, used_fast);
+        case XSQ_FI5N: return run_rkn<tab::Fi5N>(a->rhs, P, mi, used_fast);
+        case XSQ_MU5NMB: return run_rkn<tab::Mu5Nmb>(a->rhs, P, mi, used_fast);
+        case XSQ_MR6NN: return run_rkn<tab::MR6NN>(a->rhs, P, mi, used_fast);
+#endif
         default: return XSQ_ERR_UNSUPPORTED;
     }
 }

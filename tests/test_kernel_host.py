@@ -313,3 +313,26 @@ def test_swag_event_kernel_source_equals_the_c_oracle_with_events():
         keys = ("t_events", "y_events", "event_counts", "y_final", "t_final", "nfev", "n_accepted",
                 "n_rejected", "status") + (("y",) if "t_eval" in kw else ())
         _same_events(a, o, ("SWAG", term, sorted(kw)), keys)
+
+
+# ---- Runge-Kutta-Nystrom methods ---------------------------------------------------
+@pytest.mark.parametrize("m", [xb.Fi4N, xb.Fi5N, xb.Mu5Nmb], ids=lambda m: m.__name__)
+@pytest.mark.parametrize("prob", ["vanderpol", "arenstorf"])
+def test_nystrom_kernel_source_equals_oracle_bit_for_bit(m, prob):
+    """The Nystrom variant of rk_persistent (Lane::stage / solution / error for
+    tab::NYSTROMV, common.py:1279-1309) on the host against rkn_stage and the
+    Nystrom block of oracle/xsq_oracle.c in device arithmetic.  (MR6NN takes
+    velocity independent problems only: covered on the GPU with a Kepler user
+    right-hand side, tests/test_gpu_rkn.py.)"""
+    tab = O.load_tableaux_rkn()[m.__name__]
+    y0, prm, span = lanes(prob, 64)
+    if prob == "vanderpol":
+        keep = prm[:, 0] <= 30.0
+        y0, prm = y0[keep], prm[keep]
+    for kw in (dict(rtol=1e-8, atol=1e-10), dict(rtol=1e-4, atol=1e-6)):
+        with CO.device_math():
+            o = CO.rk_batch(tab, prob, span, y0, params=prm, n_threads=CO.max_threads(),
+                            nfev_stiff_detect=0, **kw)
+        g = emu.solve(prob, span, y0, m, prm, nfev_stiff_detect=0, **kw)
+        assert o["n_rejected"].sum() > 0 and (o["status"] == 0).all()
+        same(g, o, (m.__name__, prob, sorted(kw)))
