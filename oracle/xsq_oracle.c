@@ -1049,6 +1049,9 @@ static void rk_solve_one(const otab_t* T, rhs_fn f, int n, const double* y0,
     if (T->variant == V_CKDISC && st == 1) ck_solve_one(L, tf, t_eval, n_eval, y_eval, max_steps, &ieval, &st);
     while (st == 1) {
         int step_rejected = 0;
+        /* the step budget (max_steps: a safety net of the device path, no reference
+         * analogue) ends the lane before the next step is prepared, as in the kernels */
+        if (!forced && attempts >= max_steps) { st = ST_BUDGET; break; }
         if (!forced) reassess(L);
         for (;;) { /* while not step_accepted */
             if (forced) L->h_abs = h_forced[L->n_acc];

@@ -336,3 +336,57 @@ def test_nystrom_kernel_source_equals_oracle_bit_for_bit(m, prob):
         g = emu.solve(prob, span, y0, m, prm, nfev_stiff_detect=0, **kw)
         assert o["n_rejected"].sum() > 0 and (o["status"] == 0).all()
         same(g, o, (m.__name__, prob, sorted(kw)))
+
+
+def test_event_kernels_random_options_against_the_c_oracle():
+    """80 seeded random settings -- method (Ts5, BS5, Pr8, CKdisc, SWAG), span
+    (forward / backward), tolerances, max_step, first_step, t_eval, terminal counts
+    and directions, record capacity, BS5 interpolant, stiffness diagnosis, step
+    budget, event queue size (exact / overflowing / none), fast kernel allowed or
+    not: the emulated kernels and the C oracle with events must agree bit for
+    bit on every output.  (This search found the one disagreement fixed in the
+    oracle: h_next of a lane that runs out of its step budget.)"""
+    rng = np.random.default_rng(2026)
+    methods = [xb.Ts5, xb.BS5, xb.Pr8, xb.CKdisc, xb.SWAG]
+    for _ in range(80):
+        m = methods[rng.integers(len(methods))]
+        N = int(rng.integers(4, 16))
+        y0 = np.stack([rng.uniform(-10, 10, N), rng.uniform(-10, 10, N), rng.uniform(10, 35, N)], 1)
+        prm = np.stack([rng.uniform(9, 11, N), rng.uniform(24, 32, N), rng.uniform(2.4, 2.9, N)], 1)
+        back = rng.random() < 0.25          # (Lorenz backwards blows up: short spans only)
+        T = float(rng.uniform(0.05, 0.4)) if back else float(rng.uniform(0.5, 3.0))
+        span = (T, 0.0) if back else (0.0, T)
+        term = [int(rng.integers(0, 4)) if rng.random() < 0.4 else 0 for _ in range(3)]
+        direc = [int(rng.integers(-1, 2)) for _ in range(3)]
+        kw = dict(rtol=float(10 ** rng.uniform(-9, -3)), atol=float(10 ** rng.uniform(-11, -5)))
+        if rng.random() < 0.3:
+            kw["max_step"] = float(rng.uniform(0.01, 0.3))
+        if rng.random() < 0.3:
+            kw["first_step"] = float(rng.uniform(1e-4, 1e-2))
+        if rng.random() < 0.4:
+            te = np.unique(rng.uniform(0, T, int(rng.integers(1, 30))))
+            kw["t_eval"] = te[::-1].copy() if back else te
+        if rng.random() < 0.3:
+            kw["max_steps"] = int([3000, 200][rng.integers(2)])
+        cap = int(rng.integers(1, 10))
+        swag = m is xb.SWAG
+        if not swag:
+            if m is xb.BS5 and rng.random() < 0.7:
+                kw["interpolant"] = ["best", "low", "free"][rng.integers(3)]
+            kw["nfev_stiff_detect"] = 0 if m is xb.CKdisc else int([0, 300, 5000][rng.integers(3)])
+        q = int([-1, -1, 0, 40][rng.integers(4)])
+        what = (m.__name__, span, term, direc, sorted(kw), cap, q)
+        a = emu.solve("lorenz63", span, y0, m, prm, events=(term, direc), max_event_records=cap,
+                      event_queue_records=q, fast=bool(rng.random() < 0.7), **kw)
+        with CO.device_math():
+            if swag:
+                o = CO.swag_events_batch("lorenz63", span, y0, "lorenz_sections", term, direc, cap,
+                                         params=prm, n_threads=CO.max_threads(), **kw)
+            else:
+                tab = O.load_ckdisc() if m is xb.CKdisc else TABS[m.__name__]
+                o = CO.rk_events_batch(tab, "lorenz63", span, y0, "lorenz_sections", term, direc, cap,
+                                       params=prm, n_threads=CO.max_threads(), **kw)
+        keys = ["t_events", "y_events", "event_counts", "y_final", "t_final", "nfev", "n_accepted",
+                "n_rejected", "status"] + (["y"] if "t_eval" in kw else []) + \
+            ([] if swag else ["h_next", "stiff_flags"])
+        _same_events(a, o, what, keys)
